@@ -1,0 +1,211 @@
+"""ctypes binding of the C ABI in include/hammlet_b200.h (libhammlet_b200.so).
+
+This is the Python-side mirror of the boundary: every method is one C call.  There is no CPU
+fallback: if the shared library is missing or no CUDA device exists, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhammlet_b200.so")
+
+SWEEP_DYNAMIC, SWEEP_LOGLIK, SWEEP_KEEP_ROWS = 1, 2, 4
+MAX_STATES = 32
+
+
+class HmlError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[hammlet_b200 {code}] {msg}")
+        self.code = code
+
+
+class _Model(C.Structure):
+    _fields_ = [("K", C.c_int32), ("use_self_transitions", C.c_int32), ("mean", C.c_void_p), ("var", C.c_void_p),
+                ("A", C.c_void_p), ("pi", C.c_void_p)]
+
+
+class _SweepOut(C.Structure):
+    _fields_ = [("nblocks", C.c_uint64), ("uniform_fallbacks", C.c_uint64), ("loglik", C.c_double),
+                ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p), ("stat_n", C.c_void_p), ("trans", C.c_void_p),
+                ("counts", C.c_void_p)]
+
+
+EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_load_f32", "hml_load_f32_device",
+           "hml_size", "hml_sigma_hat", "hml_get_weights", "hml_get_coeffs", "hml_create_blocks", "hml_nr_blocks",
+           "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
+           "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync"]
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HmlError(-1, f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                               "there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.hml_last_error.restype = C.c_char_p
+        lib.hml_last_error.argtypes = [C.c_void_p]
+        lib.hml_version.restype = C.c_char_p
+        for name in EXPORTS:
+            getattr(lib, name)  # every declared symbol must be exported
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Handle:
+    """One sequence (or shard) resident on one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.hml_create(C.byref(self.h), C.c_int(device))
+        if rc != 0:
+            raise HmlError(rc, self.lib.hml_last_error(None).decode())
+        self.T = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HmlError(rc, self.lib.hml_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.hml_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- load
+    def load(self, x, weight_multiplier=1.0):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        self._ck(self.lib.hml_load_f32(self.h, _ptr(x), C.c_uint64(x.size), C.c_float(weight_multiplier)))
+        self.T = x.size
+
+    def load_device(self, dev_ptr, T, weight_multiplier=1.0):
+        self._ck(self.lib.hml_load_f32_device(self.h, C.c_void_p(dev_ptr), C.c_uint64(T), C.c_float(weight_multiplier)))
+        self.T = int(T)
+
+    def sigma_hat(self):
+        v = C.c_double()
+        self._ck(self.lib.hml_sigma_hat(self.h, C.byref(v)))
+        return v.value
+
+    def weights(self):
+        w = np.empty(self.T, dtype=np.float32)
+        self._ck(self.lib.hml_get_weights(self.h, _ptr(w), C.c_uint64(w.size)))
+        return w
+
+    def coeffs(self):
+        w = np.empty(self.T, dtype=np.float32)
+        self._ck(self.lib.hml_get_coeffs(self.h, _ptr(w), C.c_uint64(w.size)))
+        return w
+
+    # ---- blocks
+    def create_blocks(self, threshold):
+        n = C.c_uint64()
+        self._ck(self.lib.hml_create_blocks(self.h, C.c_float(threshold), C.byref(n)))
+        return n.value
+
+    def nr_blocks(self):
+        n = C.c_uint64()
+        self._ck(self.lib.hml_nr_blocks(self.h, C.byref(n)))
+        return n.value
+
+    def blocks(self, stats=True):
+        B = self.nr_blocks()
+        starts = np.empty(B, dtype=np.uint32)
+        if stats:
+            s, q = np.empty(B, dtype=np.float64), np.empty(B, dtype=np.float64)
+            self._ck(self.lib.hml_get_blocks(self.h, _ptr(starts), _ptr(s), _ptr(q), C.c_uint64(B)))
+            return starts, s, q
+        self._ck(self.lib.hml_get_blocks(self.h, _ptr(starts), None, None, C.c_uint64(B)))
+        return starts
+
+    # ---- sweeps
+    def _sweep(self, fn, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay):
+        K = len(mean)
+        mean, var = np.ascontiguousarray(mean, np.float64), np.ascontiguousarray(var, np.float64)
+        A, pi = np.ascontiguousarray(A, np.float64).reshape(K, K), np.ascontiguousarray(pi, np.float64)
+        m = _Model(K, int(use_self), _ptr(mean), _ptr(var), _ptr(A), _ptr(pi))
+        ssum, ssq = np.zeros(K), np.zeros(K)
+        sn, cnt, tr = np.zeros(K, np.uint64), np.zeros(K, np.uint64), np.zeros((K, K), np.uint64)
+        out = _SweepOut(0, 0, 0.0, _ptr(ssum), _ptr(ssq), _ptr(sn), _ptr(tr), _ptr(cnt))
+        if replay is not None:
+            replay = np.ascontiguousarray(replay, np.float64)
+            rp, rn = _ptr(replay), replay.size
+        else:
+            rp, rn = None, 0
+        self._ck(fn(self.h, C.byref(m), C.c_uint32(flags), C.c_float(threshold), C.c_uint64(seed), C.c_uint64(sweep),
+                    rp, C.c_uint64(rn), C.byref(out)))
+        return dict(nblocks=out.nblocks, fallbacks=out.uniform_fallbacks, loglik=out.loglik, stat_sum=ssum,
+                    stat_sq=ssq, stat_n=sn, trans=tr, counts=cnt)
+
+    def fb_sweep(self, mean, var, A, pi, use_self=True, flags=0, threshold=0.0, seed=0, sweep=0, replay=None):
+        return self._sweep(self.lib.hml_fb_sweep, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay)
+
+    def mix_sweep(self, mean, var, A, pi, use_self=True, flags=0, threshold=0.0, seed=0, sweep=0, replay=None):
+        return self._sweep(self.lib.hml_mix_sweep, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay)
+
+    # ---- records / debug
+    def states(self):
+        B = self.nr_blocks()
+        s = np.empty(B, dtype=np.int16)
+        self._ck(self.lib.hml_get_states(self.h, _ptr(s), C.c_uint64(B)))
+        return s
+
+    def segments(self):
+        n = C.c_uint64()
+        self._ck(self.lib.hml_get_segments(self.h, C.byref(n), None, None, C.c_uint64(0)))
+        sizes, st = np.empty(n.value, dtype=np.uint64), np.empty(n.value, dtype=np.int16)
+        self._ck(self.lib.hml_get_segments(self.h, C.byref(n), _ptr(sizes), _ptr(st), C.c_uint64(sizes.size)))
+        return sizes, st
+
+    def rows(self, K):
+        B = self.nr_blocks()
+        r = np.empty((B + 1, K), dtype=np.float64)
+        self._ck(self.lib.hml_get_rows(self.h, _ptr(r), C.c_uint64(B + 1)))
+        return r
+
+    # ---- measurement
+    def set_timing(self, on=True):
+        self._ck(self.lib.hml_set_timing(self.h, C.c_int(int(on))))
+
+    def timing(self):
+        n = C.c_int()
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        self._ck(self.lib.hml_get_timing(self.h, C.byref(n), names, ms, C.c_int(32)))
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n.value, 32))]
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._ck(self.lib.hml_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def sync(self):
+        self._ck(self.lib.hml_sync(self.h))
+
+
+def philox_uniform(seed, sweep, stream, index):
+    """Host restatement of hml::Philox::uniform (hml_common.cuh) for tests."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    mask = 0xFFFFFFFF
+    c = [index & mask, (index >> 32) & mask, sweep & mask, ((sweep >> 32) & mask) ^ ((stream << 24) & mask)]
+    k0, k1 = seed & mask, (seed >> 32) & mask
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & mask, p1 & mask, ((p0 >> 32) ^ c[3] ^ k1) & mask, p0 & mask]
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    bits = (c[0] << 32) | c[1]
+    return (bits >> 11) * (1.0 / 9007199254740992.0)

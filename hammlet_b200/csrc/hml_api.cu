@@ -1,0 +1,795 @@
+// hammlet_b200 — C ABI (include/hammlet_b200.h): context, load orchestration, sweeps, getters.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hammlet_b200.h"
+#include "hml_common.cuh"
+#include "hml_kernels.h"
+
+using namespace hml;
+
+namespace {
+std::string g_create_error;
+struct Stage {
+  const char* name;
+  cudaEvent_t ev;
+};
+constexpr size_t kOutWords = 2 + 32 + 32 * 32 + 2 + 2 * 32 + 2;  // device/pinned result block, 64-bit words
+}  // namespace
+
+struct hml_ctx {
+  int device = 0;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+
+  // sequence (resident since load)
+  uint64_t T = 0;
+  float* w = nullptr;       // breakpoint weights, padded to a tile multiple
+  float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
+  double2* pq = nullptr;    // integral arrays, T+1 entries
+  double4* cell_pref = nullptr;
+  double sigma_hat = NAN;
+
+  // boundary detection
+  uint64_t* desc = nullptr;
+  uint32_t epoch = 0;
+  unsigned long long* ticket = nullptr;
+  unsigned long long ticket_base = 0;
+  int detect_grid = 0;
+
+  // block structure
+  uint64_t capacity = 0;  // multiple of kTileBlocks
+  uint32_t* starts = nullptr;
+  uint32_t* bN = nullptr;
+  double2* bS = nullptr;
+  bool blocks_valid = false, stats_valid = false, states_valid = false, rows_valid = false;
+  uint64_t nblocks = 0;  // host copy, valid when blocks_valid
+
+  // per-sweep buffers (sized by capacity and KP)
+  int KP = 0;
+  int last_K = 0;
+  double *e = nullptr, *sp = nullptr, *maxE = nullptr;
+  uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *chunk_qin = nullptr;
+  double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr;
+  int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr;
+  double* rows = nullptr;
+  uint64_t rows_cap = 0;
+  double* replay_u = nullptr;
+  uint64_t replay_cap = 0;
+  double* partials = nullptr;
+  unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
+  unsigned long long* outblk_host = nullptr;  // pinned mirror
+
+  // timing
+  bool timing = false;
+  std::vector<Stage> stages;
+  size_t stage_used = 0;
+  std::vector<cudaEvent_t> event_pool;
+  std::vector<std::string> last_names;
+  std::vector<float> last_ms;
+};
+
+namespace {
+
+int fail(hml_t* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) return fail(h, HML_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename P>
+cudaError_t dev_alloc(P*& p, size_t n) {
+  if (p) {
+    cudaFree(p);
+    p = nullptr;
+  }
+  if (n == 0) n = 1;
+  return cudaMalloc((void**)&p, n * sizeof(P));
+}
+template <typename P>
+void dev_free(P*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void stage_cb(void* user, const char* name) {
+  hml_t* h = (hml_t*)user;
+  if (!h->timing) return;
+  if (h->stage_used == h->event_pool.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    h->event_pool.push_back(ev);
+  }
+  cudaEvent_t ev = h->event_pool[h->stage_used++];
+  cudaEventRecord(ev, h->stream);
+  h->stages.push_back({name, ev});
+}
+
+void collect_timing(hml_t* h) {
+  if (!h->timing) return;
+  h->last_names.clear();
+  h->last_ms.clear();
+  for (size_t i = 0; i + 1 < h->stages.size(); ++i) {
+    if (strcmp(h->stages[i].name, "end") == 0) continue;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->stages[i].ev, h->stages[i + 1].ev);
+    h->last_names.push_back(h->stages[i].name);
+    h->last_ms.push_back(ms);
+  }
+  h->stages.clear();
+  h->stage_used = 0;
+}
+
+uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+
+// (re)allocates everything sized by the block capacity; invalidates the block structure
+int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
+  cap = round_up(cap < 1 ? 1 : cap, kTileBlocks);
+  const uint64_t chunks = cap / kChunkLen, tiles = cap / kTileBlocks;
+  const int MB = KP ? map_bytes(KP) : 8;
+  if (cap != h->capacity) {
+    CK(dev_alloc(h->starts, cap + 1));
+    CK(dev_alloc(h->bN, cap));
+    CK(dev_alloc(h->bS, cap));
+    CK(dev_alloc(h->states, cap));
+    CK(dev_alloc(h->chunk_qin, chunks));
+    h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
+    dev_free(h->rows);
+    h->rows_cap = 0;
+  }
+  if (KP && (cap != h->capacity || KP != h->KP)) {
+    CK(dev_alloc(h->e, cap * KP));
+    CK(dev_alloc(h->sp, cap * KP));
+    CK(dev_alloc(h->maxE, cap));
+    CK(dev_alloc(h->maps, cap * MB));
+    CK(dev_alloc(h->chunk_maps, chunks * MB));
+    CK(dev_alloc(h->chunk_ops, chunks * KP * KP));
+    CK(dev_alloc(h->chunk_exp, chunks * KP));
+    CK(dev_alloc(h->tile_ops, tiles * KP * KP));
+    CK(dev_alloc(h->tile_exp, tiles * KP));
+    CK(dev_alloc(h->tile_ain, tiles * KP));
+    CK(dev_alloc(h->group_ops, (size_t)32 * KP * KP));
+    CK(dev_alloc(h->group_exp, (size_t)32 * KP));
+    CK(dev_alloc(h->partials, reduce_partials_doubles(KP, h->sms * 32)));
+    h->KP = KP;
+    h->states_valid = h->rows_valid = false;
+  }
+  h->capacity = cap;
+  return HML_OK;
+}
+
+SweepBuffers make_buffers(hml_t* h, int KP) {
+  SweepBuffers b;
+  memset(&b, 0, sizeof(b));
+  b.pq = h->pq;
+  b.cell_pref = h->cell_pref;
+  b.starts = h->starts;
+  b.nblocks = h->outblk;
+  b.capacity = h->capacity;
+  b.bN = h->bN;
+  b.bS = h->bS;
+  b.e = h->e;
+  b.sp = h->sp;
+  b.maxE = h->maxE;
+  b.maps = h->maps;
+  b.states = h->states;
+  b.chunk_ops = h->chunk_ops;
+  b.chunk_exp = h->chunk_exp;
+  b.chunk_maps = h->chunk_maps;
+  b.chunk_qin = h->chunk_qin;
+  b.tile_ops = h->tile_ops;
+  b.tile_exp = h->tile_exp;
+  b.tile_ain = h->tile_ain;
+  b.group_ops = h->group_ops;
+  b.group_exp = h->group_exp;
+  b.partials = h->partials;
+  b.out_u64 = h->outblk + 2;
+  size_t words = (size_t)KP + (size_t)KP * KP + 1;
+  words += words & 1;
+  b.out_f64 = (double*)(h->outblk + 2 + words);
+  return b;
+}
+
+int run_detect(hml_t* h, float thr) {
+  if (h->epoch >= (1u << 28) - 1) {
+    const uint64_t tiles = (h->T + kTile - 1) / kTile;
+    CK(cudaMemsetAsync(h->desc, 0, tiles * sizeof(uint64_t), h->stream));
+    h->epoch = 0;
+  }
+  h->epoch++;
+  const uint64_t tiles = (h->T + kTile - 1) / kTile;
+  stage_cb(h, "detect_compact");
+  launch_detect_compact(h->w, h->T, thr, 1, h->desc, h->epoch, h->ticket, h->ticket_base, h->starts, h->capacity,
+                        h->outblk, h->detect_grid, h->stream);
+  h->ticket_base += tiles + (uint64_t)h->detect_grid;
+  h->launches++;
+  CK(cudaGetLastError());
+  return HML_OK;
+}
+
+int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
+  // ---- free the previous sequence
+  dev_free(h->w);
+  dev_free(h->coeffs);
+  dev_free(h->pq);
+  dev_free(h->cell_pref);
+  dev_free(h->desc);
+  h->T = 0;
+  h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
+  const uint64_t tiles = (T + kTile - 1) / kTile;
+  const uint64_t cells = T / kCell + 1;
+
+  // ---- level normalisers: running fp32 product of sqrt2half, includes.hpp:126-128, wavelet.hpp:144,172
+  float norms[64];
+  {
+    const float sqrt2 = (float)sqrt(2.0);
+    const float sqrt2half = (float)(sqrt2 / 2.0);
+    float n = sqrt2half;
+    norms[0] = 1.0f;
+    for (int l = 1; l < 64; ++l) {
+      norms[l] = n;
+      n *= sqrt2half;
+    }
+  }
+  upload_level_norms(norms, h->stream);
+
+  // ---- maxlet coefficients, 12 levels per pass
+  CK(dev_alloc(h->coeffs, tiles * kTile));
+  float* sums[2] = {nullptr, nullptr};
+  CK(dev_alloc(sums[0], tiles + 1));
+  CK(dev_alloc(sums[1], tiles / kTile + 2));
+  {
+    const float* in = x_dev;
+    uint64_t n_valid = T, n_pos = T, stride = 1;
+    int level0 = 0, which = 0;
+    while (n_pos > 1) {
+      launch_maxlet_level(in, n_valid, n_pos, stride, level0, h->coeffs, sums[which], h->stream);
+      h->launches++;
+      in = sums[which];
+      which ^= 1;
+      n_valid = n_valid / kTile;
+      n_pos = (n_pos + kTile - 1) / kTile;
+      stride *= kTile;
+      level0 += kTileLog2;
+    }
+    const float inf = INFINITY;
+    CK(cudaMemcpyAsync(h->coeffs, &inf, sizeof(float), cudaMemcpyHostToDevice, h->stream));  // wavelet.hpp:183
+  }
+  CK(cudaGetLastError());
+
+  // ---- sigma-hat numerator (main.cpp:303-311)
+  {
+    const int nb = 512;
+    double* part = nullptr;
+    CK(dev_alloc(part, nb));
+    launch_sum_odd(h->coeffs, T, part, nb, h->stream);
+    h->launches++;
+    std::vector<double> hp(nb);
+    CK(cudaMemcpyAsync(hp.data(), part, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    dev_free(part);
+    long double s = 0;
+    for (double v : hp) s += v;
+    const uint64_t n = T / 2;
+    double est = n ? (double)(s / (long double)n) : NAN;
+    est /= 0.797884560802865355879892119868763736951717262329869315331;
+    h->sigma_hat = est;
+  }
+
+  // ---- breakpoint weights
+  CK(dev_alloc(h->w, tiles * kTile));
+  launch_bp_weights(h->coeffs, T, mult, h->w, h->sms, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+
+  // ---- integral arrays + double-double cell prefix
+  CK(dev_alloc(h->pq, cells * kCell));
+  double2* cell_tot = nullptr;
+  CK(dev_alloc(cell_tot, cells));
+  launch_integral_cells(x_dev, T, h->pq, cell_tot, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  {
+    std::vector<double2> tot(cells);
+    CK(cudaMemcpyAsync(tot.data(), cell_tot, cells * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<double4> pref(cells + 1);
+    // exclusive prefix in double-double (Knuth two-sum), so differences of far-apart cells stay exact to ~1e-32
+    double hx = 0, lx = 0, hq = 0, lq = 0;
+    auto dd_add = [](double& hi, double& lo, double v) {
+      const double s = hi + v;
+      const double bb = s - hi;
+      const double err = (hi - (s - bb)) + (v - bb);
+      const double l2 = lo + err;
+      const double s2 = s + l2;
+      lo = l2 - (s2 - s);
+      hi = s2;
+    };
+    for (uint64_t c = 0; c <= cells; ++c) {
+      pref[c] = make_double4(hx, lx, hq, lq);
+      if (c < cells) {
+        dd_add(hx, lx, tot[c].x);
+        dd_add(hq, lq, tot[c].y);
+      }
+    }
+    CK(dev_alloc(h->cell_pref, cells + 1));
+    CK(cudaMemcpyAsync(h->cell_pref, pref.data(), (cells + 1) * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  dev_free(cell_tot);
+  dev_free(sums[0]);
+  dev_free(sums[1]);
+  if (T > (1ull << 26)) dev_free(h->coeffs);  // 4 B/observation is not worth keeping for big inputs
+
+  // ---- look-back descriptors
+  CK(dev_alloc(h->desc, tiles));
+  CK(cudaMemsetAsync(h->desc, 0, tiles * sizeof(uint64_t), h->stream));
+  h->epoch = 0;
+  h->T = T;
+
+  // ---- initial block capacity: grows on demand (a sweep that overflows is re-run)
+  uint64_t cap = T / 64;
+  if (cap < (1u << 16)) cap = 1u << 16;
+  if (cap > T) cap = T;
+  h->capacity = 0;
+  int rc = alloc_blocks(h, cap, 0);
+  if (rc != HML_OK) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int validate_model(hml_t* h, const hml_model* m, ModelHost& mh) {
+  if (!m || !m->mean || !m->var || !m->A || !m->pi) return fail(h, HML_ERR_ARG, "model pointers must not be NULL");
+  if (m->K < 2 || m->K > HML_MAX_STATES)
+    return fail(h, HML_ERR_ARG, "number of states must be in [2, " + std::to_string(HML_MAX_STATES) + "]");
+  memset(&mh, 0, sizeof(mh));
+  mh.K = m->K;
+  mh.use_self = m->use_self_transitions ? 1 : 0;
+  for (int i = 0; i < m->K; ++i) {
+    if (!isfinite(m->mean[i])) return fail(h, HML_ERR_ARG, "Mean must be set to a finite value!");
+    if (!(m->var[i] > 0) || !isfinite(m->var[i])) return fail(h, HML_ERR_ARG, "Variance must be positive!");
+    if (!(m->pi[i] >= 0)) return fail(h, HML_ERR_NUMERIC, "Negative backward variable!");
+    mh.mean[i] = m->mean[i];
+    mh.var[i] = m->var[i];
+    mh.pi[i] = m->pi[i];
+    for (int j = 0; j < m->K; ++j) {
+      const double a = m->A[i * m->K + j];
+      if (!(a >= 0)) return fail(h, HML_ERR_NUMERIC, "Negative backward variable!");  // FB.hpp:147-149
+      mh.A[i * m->K + j] = a;
+    }
+  }
+  return HML_OK;
+}
+
+int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64_t seed, uint64_t sweep,
+                 const double* replay, uint64_t n_replay, hml_sweep_out* out, bool mixture) {
+  if (!h) return HML_ERR_ARG;
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  if (!out) return fail(h, HML_ERR_ARG, "out must not be NULL");
+  CK(cudaSetDevice(h->device));
+  ModelHost mh;
+  int rc = validate_model(h, m, mh);
+  if (rc != HML_OK) return rc;
+  const int KP = padded_states(mh.K);
+  const bool dynamic = (flags & HML_SWEEP_DYNAMIC) != 0;
+  if (replay && dynamic)
+    return fail(h, HML_ERR_ARG, "replay uniforms need a fixed block structure: call hml_create_blocks first");
+  if (!dynamic && !h->blocks_valid) return fail(h, HML_ERR_STATE, "no block structure: call hml_create_blocks first");
+  if (replay && n_replay < h->nblocks) return fail(h, HML_ERR_ARG, "fewer replay uniforms than blocks");
+
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    if (KP != h->KP) {
+      // per-block statistics survive (their layout does not depend on K); only K-sized buffers change
+      rc = alloc_blocks(h, h->capacity, KP);
+      if (rc != HML_OK) return rc;
+    }
+    if ((flags & HML_SWEEP_KEEP_ROWS) && h->rows_cap < (h->capacity + 1) * (uint64_t)mh.K) {
+      h->rows_cap = (h->capacity + 1) * (uint64_t)mh.K;
+      CK(dev_alloc(h->rows, h->rows_cap));
+    }
+    if (replay) {
+      if (h->replay_cap < h->nblocks) {
+        h->replay_cap = h->capacity;
+        CK(dev_alloc(h->replay_u, h->replay_cap));
+      }
+      CK(cudaMemcpyAsync(h->replay_u, replay, h->nblocks * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    h->stages.clear();
+    h->stage_used = 0;
+    bool gather = !h->stats_valid;
+    if (dynamic) {
+      rc = run_detect(h, thr);
+      if (rc != HML_OK) return rc;
+      gather = true;
+      h->blocks_valid = false;
+    }
+    SweepBuffers b = make_buffers(h, KP);
+    b.rows = (flags & HML_SWEEP_KEEP_ROWS) ? h->rows : nullptr;
+    b.replay_u = replay ? h->replay_u : nullptr;
+    SweepLaunch l;
+    l.flags = flags;
+    l.gather = gather;
+    l.mixture = mixture;
+    l.seed = seed;
+    l.sweep = sweep;
+    l.sms = h->sms;
+    l.nblocks_hint = dynamic ? h->capacity : h->nblocks;
+    const int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
+    if (n < 0) return fail(h, HML_ERR_ARG, "unsupported number of states");
+    h->launches += n;
+    CK(cudaGetLastError());
+    size_t words = (size_t)KP + (size_t)KP * KP + 1;
+    words += words & 1;
+    const size_t copy_words = 2 + words + 2 * KP + 1;
+    CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const uint64_t B = h->outblk_host[0];
+    if (dynamic && B > h->capacity) {  // block arrays too small: grow and run the sweep again
+      rc = alloc_blocks(h, B + B / 4, KP);
+      if (rc != HML_OK) return rc;
+      continue;
+    }
+    h->nblocks = B;
+    h->blocks_valid = true;
+    h->stats_valid = true;
+    const unsigned long long* o64 = h->outblk_host + 2;
+    const double* of = (const double*)(h->outblk_host + 2 + words);
+    uint64_t fallbacks = o64[KP + KP * KP];
+    if (fallbacks > 0 && !mixture) {
+      // A zero forward sum resets the filter to uniform (FB.hpp:106-111); that is not an operator
+      // product, so the exact sequential recursion is run instead (still on the device).
+      l.nblocks_hint = B;
+      const int n2 = launch_sweep_sequential(mh, b, l, h->stream);
+      h->launches += n2;
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      fallbacks = o64[KP + KP * KP];
+    }
+    collect_timing(h);
+    out->nblocks = B;
+    out->uniform_fallbacks = fallbacks;
+    out->loglik = (flags & HML_SWEEP_LOGLIK) ? of[2 * KP] : NAN;
+    for (int s = 0; s < mh.K; ++s) {
+      if (out->stat_sum) out->stat_sum[s] = of[s];
+      if (out->stat_sumsq) out->stat_sumsq[s] = of[KP + s];
+      if (out->stat_n) out->stat_n[s] = o64[s];
+      if (out->counts) out->counts[s] = o64[s];  // univariate: occupancy == observations per parameter
+      if (out->trans)
+        for (int j = 0; j < mh.K; ++j) out->trans[s * mh.K + j] = o64[KP + s * KP + j];
+    }
+    h->states_valid = true;
+    h->rows_valid = (flags & HML_SWEEP_KEEP_ROWS) != 0 && !mixture;
+    h->last_K = mh.K;
+    return HML_OK;
+  }
+  return fail(h, HML_ERR_CAPACITY, "block capacity did not converge");
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+
+extern "C" {
+
+const char* hml_version(void) { return "hammlet_b200 0.1 (sm_100a)"; }
+
+const char* hml_last_error(const hml_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int hml_create(hml_t** out, int device) {
+  if (!out) return HML_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                     "); hammlet_b200 has no CPU fallback";
+    return HML_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return HML_ERR_ARG;
+  }
+  hml_t* h = new hml_ctx();
+  h->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete h;
+    return HML_ERR_CUDA;
+  }
+  if (prop.major < 10) {
+    g_create_error = std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only";
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return HML_ERR_CUDA;
+  }
+  h->sms = prop.multiProcessorCount;
+  h->detect_grid = detect_grid_size(h->sms);
+  if (cudaMalloc((void**)&h->outblk, kOutWords * 8) != cudaSuccess ||
+      cudaMallocHost((void**)&h->outblk_host, kOutWords * 8) != cudaSuccess ||
+      cudaMalloc((void**)&h->ticket, 8) != cudaSuccess) {
+    g_create_error = "allocation of the result block failed";
+    delete h;
+    return HML_ERR_CUDA;
+  }
+  cudaMemset(h->outblk, 0, kOutWords * 8);
+  cudaMemset(h->ticket, 0, 8);
+  *out = h;
+  return HML_OK;
+}
+
+int hml_destroy(hml_t* h) {
+  if (!h) return HML_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  dev_free(h->w);
+  dev_free(h->coeffs);
+  dev_free(h->pq);
+  dev_free(h->cell_pref);
+  dev_free(h->desc);
+  dev_free(h->ticket);
+  dev_free(h->starts);
+  dev_free(h->bN);
+  dev_free(h->bS);
+  dev_free(h->e);
+  dev_free(h->sp);
+  dev_free(h->maxE);
+  dev_free(h->maps);
+  dev_free(h->states);
+  dev_free(h->chunk_maps);
+  dev_free(h->chunk_qin);
+  dev_free(h->chunk_ops);
+  dev_free(h->tile_ops);
+  dev_free(h->tile_ain);
+  dev_free(h->group_ops);
+  dev_free(h->chunk_exp);
+  dev_free(h->tile_exp);
+  dev_free(h->group_exp);
+  dev_free(h->rows);
+  dev_free(h->replay_u);
+  dev_free(h->partials);
+  dev_free(h->outblk);
+  if (h->outblk_host) cudaFreeHost(h->outblk_host);
+  for (cudaEvent_t ev : h->event_pool) cudaEventDestroy(ev);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return HML_OK;
+}
+
+int hml_load_f32_device(hml_t* h, const float* x_dev, uint64_t T, float weight_multiplier) {
+  if (!h) return HML_ERR_ARG;
+  if (!x_dev) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (T == 0) return fail(h, HML_ERR_ARG, "Input vector for breakpoint weights is empty!");
+  if (T >= (1ull << 32)) return fail(h, HML_ERR_ARG, "one handle holds fewer than 2^32 observations; shard the sequence");
+  CK(cudaSetDevice(h->device));
+  return load_common(h, x_dev, T, weight_multiplier);
+}
+
+int hml_load_f32(hml_t* h, const float* x_host, uint64_t T, float weight_multiplier) {
+  if (!h) return HML_ERR_ARG;
+  if (!x_host) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (T == 0) return fail(h, HML_ERR_ARG, "Input vector for breakpoint weights is empty!");
+  if (T >= (1ull << 32)) return fail(h, HML_ERR_ARG, "one handle holds fewer than 2^32 observations; shard the sequence");
+  CK(cudaSetDevice(h->device));
+  float* xd = nullptr;
+  CK(dev_alloc(xd, T));
+  cudaError_t e = cudaMemcpyAsync(xd, x_host, T * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) {
+    dev_free(xd);
+    return fail(h, HML_ERR_CUDA, cudaGetErrorString(e));
+  }
+  const int rc = load_common(h, xd, T, weight_multiplier);
+  cudaStreamSynchronize(h->stream);
+  dev_free(xd);
+  return rc;
+}
+
+int hml_size(const hml_t* h, uint64_t* T) {
+  if (!h || !T) return HML_ERR_ARG;
+  *T = h->T;
+  return HML_OK;
+}
+
+int hml_sigma_hat(hml_t* h, double* sigma_hat) {
+  if (!h || !sigma_hat) return HML_ERR_ARG;
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  *sigma_hat = h->sigma_hat;
+  return HML_OK;
+}
+
+int hml_get_weights(hml_t* h, float* dst, uint64_t n) {
+  if (!h || !dst) return HML_ERR_ARG;
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  if (n < h->T) return fail(h, HML_ERR_CAPACITY, "buffer smaller than T");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(dst, h->w, h->T * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int hml_get_coeffs(hml_t* h, float* dst, uint64_t n) {
+  if (!h || !dst) return HML_ERR_ARG;
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  if (!h->coeffs) return fail(h, HML_ERR_STATE, "coefficients are only kept for T <= 2^26");
+  if (n < h->T) return fail(h, HML_ERR_CAPACITY, "buffer smaller than T");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(dst, h->coeffs, h->T * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks) {
+  if (!h) return HML_ERR_ARG;
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  CK(cudaSetDevice(h->device));
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    h->stages.clear();
+    h->stage_used = 0;
+    int rc = run_detect(h, threshold);
+    if (rc != HML_OK) return rc;
+    stage_cb(h, "block_stats");
+    SweepBuffers b = make_buffers(h, 2);
+    launch_block_stats(b, 0, h->capacity, h->sms, h->stream);
+    h->launches++;
+    stage_cb(h, "end");
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->outblk_host, h->outblk, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const uint64_t B = h->outblk_host[0];
+    if (B > h->capacity) {
+      rc = alloc_blocks(h, B + B / 4, h->KP);
+      if (rc != HML_OK) return rc;
+      continue;
+    }
+    collect_timing(h);
+    h->nblocks = B;
+    h->blocks_valid = h->stats_valid = true;
+    h->states_valid = h->rows_valid = false;
+    if (nblocks) *nblocks = B;
+    return HML_OK;
+  }
+  return fail(h, HML_ERR_CAPACITY, "block capacity did not converge");
+}
+
+int hml_nr_blocks(const hml_t* h, uint64_t* nblocks) {
+  if (!h || !nblocks) return HML_ERR_ARG;
+  if (!h->blocks_valid) return HML_ERR_STATE;
+  *nblocks = h->nblocks;
+  return HML_OK;
+}
+
+int hml_get_blocks(hml_t* h, uint32_t* starts, double* sum, double* sumsq, uint64_t capacity) {
+  if (!h) return HML_ERR_ARG;
+  if (!h->blocks_valid) return fail(h, HML_ERR_STATE, "no block structure");
+  if (capacity < h->nblocks) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of blocks");
+  CK(cudaSetDevice(h->device));
+  const uint64_t B = h->nblocks;
+  if (starts) CK(cudaMemcpyAsync(starts, h->starts, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (sum || sumsq) {
+    if (!sum || !sumsq) return fail(h, HML_ERR_ARG, "sum and sumsq must be given together");
+    double* tmp = nullptr;
+    CK(dev_alloc(tmp, 2 * B));
+    SweepBuffers b = make_buffers(h, 2);
+    launch_unpermute(b, 0, B, nullptr, tmp, tmp + B, h->stream);
+    h->launches++;
+    CK(cudaMemcpyAsync(sum, tmp, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sumsq, tmp + B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    dev_free(tmp);
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int hml_fb_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold, uint64_t seed, uint64_t sweep_index,
+                 const double* replay_uniforms, uint64_t n_replay, hml_sweep_out* out) {
+  return sweep_common(h, m, flags, threshold, seed, sweep_index, replay_uniforms, n_replay, out, false);
+}
+
+int hml_mix_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold, uint64_t seed, uint64_t sweep_index,
+                  const double* replay_uniforms, uint64_t n_replay, hml_sweep_out* out) {
+  return sweep_common(h, m, flags & ~(uint32_t)(HML_SWEEP_LOGLIK | HML_SWEEP_KEEP_ROWS), threshold, seed, sweep_index,
+                      replay_uniforms, n_replay, out, true);
+}
+
+int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity) {
+  if (!h || !states) return HML_ERR_ARG;
+  if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
+  if (capacity < h->nblocks) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of blocks");
+  CK(cudaSetDevice(h->device));
+  int16_t* tmp = nullptr;
+  CK(dev_alloc(tmp, h->nblocks));
+  SweepBuffers b = make_buffers(h, 2);
+  launch_unpermute(b, 0, h->nblocks, tmp, nullptr, nullptr, h->stream);
+  h->launches++;
+  CK(cudaMemcpyAsync(states, tmp, h->nblocks * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  dev_free(tmp);
+  return HML_OK;
+}
+
+int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t* seg_state, uint64_t capacity) {
+  if (!h || !nsegments) return HML_ERR_ARG;
+  if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
+  const uint64_t B = h->nblocks;
+  std::vector<int16_t> st(B);
+  std::vector<uint32_t> starts(B);
+  int rc = hml_get_states(h, st.data(), B);
+  if (rc != HML_OK) return rc;
+  rc = hml_get_blocks(h, starts.data(), nullptr, nullptr, B);
+  if (rc != HML_OK) return rc;
+  // Records.hpp:166-188: a segment ends where the state changes
+  uint64_t n = 0;
+  for (uint64_t b = 0; b < B; ++b) {
+    if (b == 0 || st[b] != st[b - 1]) {
+      if (seg_size && seg_state) {
+        if (n >= capacity) return fail(h, HML_ERR_CAPACITY, "segment buffer too small");
+        seg_state[n] = st[b];
+        seg_size[n] = starts[b];  // start position for now; turned into a size below
+      }
+      ++n;
+    }
+  }
+  if (seg_size && seg_state) {
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t next = (i + 1 < n) ? seg_size[i + 1] : h->T;
+      seg_size[i] = next - seg_size[i];
+    }
+  }
+  *nsegments = n;
+  return HML_OK;
+}
+
+int hml_get_rows(hml_t* h, double* rows, uint64_t capacity_rows) {
+  if (!h || !rows) return HML_ERR_ARG;
+  if (!h->rows_valid) return fail(h, HML_ERR_STATE, "the last sweep did not keep its forward rows");
+  if (capacity_rows < h->nblocks + 1) return fail(h, HML_ERR_CAPACITY, "row buffer too small");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(rows, h->rows, (h->nblocks + 1) * h->last_K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int hml_set_timing(hml_t* h, int on) {
+  if (!h) return HML_ERR_ARG;
+  h->timing = on != 0;
+  return HML_OK;
+}
+
+int hml_get_timing(hml_t* h, int* nstages, const char** names, float* ms, int capacity) {
+  if (!h || !nstages) return HML_ERR_ARG;
+  *nstages = (int)h->last_names.size();
+  for (int i = 0; i < *nstages && i < capacity; ++i) {
+    if (names) names[i] = h->last_names[i].c_str();
+    if (ms) ms[i] = h->last_ms[i];
+  }
+  return HML_OK;
+}
+
+int hml_launch_count(const hml_t* h, uint64_t* n) {
+  if (!h || !n) return HML_ERR_ARG;
+  *n = h->launches;
+  return HML_OK;
+}
+
+int hml_sync(hml_t* h) {
+  if (!h) return HML_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// hammlet_b200 — shared device/host helpers (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hml {
+
+constexpr int kMaxStates = 32;        // HML_MAX_STATES
+constexpr int kCellLog2 = 12;         // integral-array cell = 4096 observations
+constexpr int kCell = 1 << kCellLog2;
+constexpr int kTileLog2 = 12;         // maxlet / detect tile = 4096 observations
+constexpr int kTile = 1 << kTileLog2;
+
+// ---- streaming loads: read-once data bypasses L1 allocation
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// volatile 64-bit accessors for the decoupled look-back descriptors (value and flag travel in one word)
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ double shfl_double(double v, int src, unsigned mask = 0xffffffffu) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(mask, lo, src);
+  hi = __shfl_sync(mask, hi, src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_double(double v, int delta, unsigned mask = 0xffffffffu) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(mask, lo, delta);
+  hi = __shfl_up_sync(mask, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_double(double v, int m, unsigned mask = 0xffffffffu) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(mask, lo, m);
+  hi = __shfl_xor_sync(mask, hi, m);
+  return __hiloint2double(hi, lo);
+}
+
+// ---- exact power-of-two scaling of positive doubles (no rounding): used to keep products of
+// forward operators in range without touching their mantissas.
+__device__ __forceinline__ int exponent_of(double m) {  // m > 0, normal
+  return ((__double2hiint(m) >> 20) & 0x7ff) - 1023;
+}
+__device__ __forceinline__ double pow2i(int e) {  // 2^e, e in [-1022, 1023]; below -> 0
+  if (e < -1022) return 0.0;
+  if (e > 1023) e = 1023;
+  return __hiloint2double((e + 1023) << 20, 0);
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based: uniforms are a pure function of
+// (seed, sweep, block) and therefore independent of launch geometry.
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  __host__ __device__ static inline void run(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t h0, l0, h1, l1;
+      mulhilo(M0, c[0], h0, l0);
+      mulhilo(M1, c[2], h1, l1);
+      uint32_t n0 = h1 ^ c[1] ^ k0, n1 = l1, n2 = h0 ^ c[3] ^ k1, n3 = l0;
+      c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+      k0 += W0; k1 += W1;
+    }
+  }
+  // 53-bit uniform in [0,1) for (seed, sweep, stream, index)
+  __host__ __device__ static inline double uniform(uint64_t seed, uint64_t sweep, uint32_t stream, uint64_t index) {
+    uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), (uint32_t)sweep, (uint32_t)(sweep >> 32) ^ (stream << 24)};
+    run(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint64_t bits = ((uint64_t)c[0] << 32) | c[1];
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+  }
+};
+
+}  // namespace hml

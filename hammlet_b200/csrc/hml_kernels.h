@@ -1,0 +1,94 @@
+// hammlet_b200 — internal kernel launch interface (host side of hammlet_b200/csrc/*.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hml {
+
+// ---- load (hml_load.cu)
+void upload_level_norms(const float* host64, cudaStream_t s);
+void launch_maxlet_level(const float* in, uint64_t n_valid, uint64_t n_pos, uint64_t stride, int level0, float* coeffs,
+                         float* tile_sums, cudaStream_t s);
+void launch_bp_weights(const float* c, uint64_t T, float mult, float* w, int sms, cudaStream_t s);
+void launch_sum_odd(const float* c, uint64_t T, double* partial, int nblocks, cudaStream_t s);
+void launch_integral_cells(const float* x, uint64_t T, double2* pq, double2* cell_tot, cudaStream_t s);
+
+// ---- boundary detection (hml_detect.cu)
+int detect_grid_size(int sms);
+void launch_detect_compact(const float* w, uint64_t T, float thr, int force_first, uint64_t* desc, uint32_t epoch,
+                           unsigned long long* ticket, unsigned long long ticket_base, uint32_t* starts,
+                           uint64_t capacity, unsigned long long* nblocks_out, int grid, cudaStream_t s);
+
+// ---- block-level sweep kernels (hml_sweep.cu)
+struct ModelHost {  // what the C ABI receives, validated
+  int K;
+  int use_self;
+  double mean[32], var[32], A[32 * 32], pi[32];
+};
+
+// Device buffers of one handle that the sweep kernels touch.  All per-block arrays are stored in
+// the chunk-interleaved order defined in hml_sweep.cu (Layout::perm).
+struct SweepBuffers {
+  // inputs resident since load
+  const double2* pq;        // T+1 cell-local running sums of (x, x^2)
+  const double4* cell_pref; // per cell: double-double exclusive prefix of cell totals (hi_x, lo_x, hi_q, lo_q)
+  // block structure
+  const uint32_t* starts;   // capacity+1, natural order
+  const unsigned long long* nblocks;  // device scalar
+  uint64_t capacity;        // blocks the per-block arrays can hold
+  uint32_t* bN;             // block sizes
+  double2* bS;              // block (sum x, sum x^2)
+  // per sweep
+  double* e;                // KP per block: exp(E_s - maxE)
+  double* sp;               // KP per block: exp((N-1) log A_ss)   (self-transition rescale, FB.hpp:115-119)
+  double* maxE;             // per block (only filled for loglik)
+  uint8_t* maps;            // KPB bytes per block: backward map j -> state
+  uint8_t* states;          // sampled state per block
+  double* chunk_ops;        // per chunk KP*KP
+  int* chunk_exp;           // per chunk KP
+  uint8_t* chunk_maps;      // per chunk KPB
+  uint8_t* chunk_qin;       // per chunk: state of the block following the chunk
+  double* tile_ops;         // per tile KP*KP
+  int* tile_exp;            // per tile KP
+  double* tile_ain;         // per tile KP: normalised forward vector entering the tile
+  double* group_ops;        // scratch of the single-CTA tile scan
+  int* group_exp;
+  double* rows;             // (capacity+1)*K, natural order, only with KEEP_ROWS (may be null)
+  const double* replay_u;   // device copy of replay uniforms (may be null)
+  double* partials;         // reduce scratch
+  unsigned long long* out_u64;  // [0..KP) stat_n, [KP..KP+KP*KP) trans, then [fallbacks]
+  double* out_f64;          // [0..KP) sum, [KP..2KP) sumsq, [2KP] loglik
+};
+
+int padded_states(int K);          // KP for K (0 if unsupported)
+int map_bytes(int KP);             // KPB
+int chunks_per_tile(int KP);       // C
+constexpr int kChunkLen = 32;      // L
+constexpr int kTileBlocks = 1024;  // L * C: per-block arrays are sized in multiples of this
+size_t reduce_partials_doubles(int KP, int grid);
+
+struct SweepLaunch {
+  uint32_t flags;      // HML_SWEEP_* bits
+  bool gather;         // recompute block sums from the integral arrays
+  bool mixture;
+  uint64_t seed, sweep;
+  int sms;
+  uint64_t nblocks_hint;  // upper bound used to size grids (capacity if unknown)
+};
+
+// Enqueues all block-level kernels of one sweep on `s`; returns the number of kernels launched.
+// stage_cb(name) is called before each stage so the caller can drop timing events.
+typedef void (*stage_cb_t)(void* user, const char* name);
+int launch_sweep(const ModelHost& m, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s, stage_cb_t cb,
+                 void* user);
+
+// Exact sequential forward pass (one thread) + backward + reductions; used after a uniform fallback.
+int launch_sweep_sequential(const ModelHost& m, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s);
+
+// Copies per-block arrays out of the interleaved order: dst_states (int16), dst_sum/dst_sumsq.
+void launch_unpermute(const SweepBuffers& b, int KP, uint64_t nblocks, int16_t* dst_states, double* dst_sum,
+                      double* dst_sumsq, cudaStream_t s);
+// Only block sums (no model): gather statistics for the current starts.
+void launch_block_stats(const SweepBuffers& b, int KP, uint64_t nblocks_hint, int sms, cudaStream_t s);
+
+}  // namespace hml

@@ -1,0 +1,900 @@
+// hammlet_b200 — templated block-level kernels of one Gibbs sweep (included by hml_sweep.cu, which carries
+// the overview, and by hml_sweep_inst.cu, which instantiates them per padded state count).
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "../../include/hammlet_b200.h"
+#include "hml_common.cuh"
+#include "hml_kernels.h"
+
+namespace hml {
+
+// ------------------------------------------------------------------------------------------------
+// layout
+
+struct Layout {
+  static constexpr int L = kChunkLen;  // blocks per chunk
+  static constexpr int C = 32;         // chunks per tile
+  static constexpr int TB = L * C;     // blocks per tile
+  static_assert(L * C == kTileBlocks, "layout");
+  // natural block index -> storage index: [tile][step t][chunk c]
+  __host__ __device__ static inline uint64_t perm(uint64_t b) {
+    const uint64_t tile = b / TB, r = b % TB;
+    return tile * TB + (r % L) * C + (r / L);
+  }
+  __host__ __device__ static inline uint64_t inv(uint64_t p) {
+    const uint64_t tile = p / TB, r = p % TB;
+    return tile * TB + (r % C) * L + (r / C);
+  }
+  __host__ __device__ static inline uint64_t at(uint64_t tile, int c, int t) { return tile * TB + (uint64_t)t * C + c; }
+};
+
+template <int KP>
+struct ModelDev {
+  double A[KP][KP];
+  double mean[KP], inv2var[KP], lognorm[KP], loga[KP], pi[KP];
+  int K, use_self;
+};
+
+template <int KP>
+static ModelDev<KP> make_model(const ModelHost& m) {
+  ModelDev<KP> d;
+  memset(&d, 0, sizeof(d));
+  d.K = m.K;
+  d.use_self = m.use_self;
+  for (int i = 0; i < m.K; ++i) {
+    d.mean[i] = m.mean[i];
+    d.inv2var[i] = 1.0 / (2.0 * m.var[i]);
+    // EFD.hpp:35-38 with the cached stdev of Observation.hpp:175-185
+    d.lognorm[i] = log(sqrt(m.var[i])) + m.mean[i] * m.mean[i] / (2 * m.var[i]);
+    d.loga[i] = m.use_self ? log(m.A[i * m.K + i]) : 0.0;  // FB.hpp:47-50
+    d.pi[i] = m.pi[i];
+    for (int j = 0; j < m.K; ++j) d.A[i][j] = m.A[i * m.K + j];
+  }
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small-vector helpers (all loops fully unrolled: register-resident vectors)
+
+constexpr int kDeadExp = -(1 << 30);
+
+template <int KP>
+__device__ __forceinline__ void renorm_pow2(double (&v)[KP], int& ex) {
+  double m = v[0];
+#pragma unroll
+  for (int j = 1; j < KP; ++j) m = fmax(m, v[j]);
+  if (m > 0.0) {
+    int e = exponent_of(m);
+    if (e < -1000) e = -1000;
+    const double s = pow2i(-e);
+#pragma unroll
+    for (int j = 0; j < KP; ++j) v[j] *= s;
+    ex += e;
+  } else {
+    ex = kDeadExp;
+  }
+}
+
+// r <- r * Op, Op given as KP x KP row-major mantissas M with per-row binary exponents X.
+template <int KP, bool kViaL2>
+__device__ __forceinline__ void row_times_op(double (&r)[KP], int& rex, const double* M, const int* X) {
+  int xk[KP];
+  int xm = kDeadExp;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    xk[k] = kViaL2 ? __ldcg(X + k) : X[k];
+    if (r[k] > 0.0 && xk[k] > xm) xm = xk[k];
+  }
+  if (rex == kDeadExp || xm == kDeadExp) {
+#pragma unroll
+    for (int j = 0; j < KP; ++j) r[j] = 0.0;
+    rex = kDeadExp;
+    return;
+  }
+  double y[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) y[j] = 0.0;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const double a = r[k] * pow2i(xk[k] - xm);
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      const double mkj = kViaL2 ? __ldcg(M + k * KP + j) : M[k * KP + j];
+      y[j] = fma(a, mkj, y[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KP; ++j) r[j] = y[j];
+  rex += xm;
+  renorm_pow2<KP>(r, rex);
+}
+
+// Warp-cooperative a <- normalise(a * Op): lane j holds a_j (lanes >= KP hold 0).  Returns false if
+// the product vanished (the caller flags a uniform-fallback suspect).
+template <int KP>
+__device__ __forceinline__ bool warp_vec_times_op(double& a, const double* M, const int* X, int lane) {
+  int xm = kDeadExp;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const double ak = shfl_double(a, k);
+    const int x = X[k];
+    if (ak > 0.0 && x > xm) xm = x;
+  }
+  double y = 0.0;
+  if (xm != kDeadExp) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const double ak = shfl_double(a, k) * pow2i(X[k] - xm);
+      const double mkj = lane < KP ? M[k * KP + lane] : 0.0;
+      y = fma(ak, mkj, y);
+    }
+  }
+  double s = y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += shfl_xor_double(s, o);
+  if (!(s > 0.0)) {
+    a = 0.0;
+    return false;
+  }
+  a = y / s;
+  return true;
+}
+
+// ---- byte-packed state maps (KPB = 8, 16 or 32 entries of one byte)
+template <int KP>
+struct Map {
+  static constexpr int W = (KP <= 8 ? 1 : (KP <= 16 ? 2 : 4));
+  uint64_t w[W];
+  __device__ __forceinline__ static Map identity() {
+    Map m;
+#pragma unroll
+    for (int i = 0; i < W; ++i) m.w[i] = 0x0706050403020100ull + 0x0808080808080808ull * i;
+    return m;
+  }
+  __device__ __forceinline__ uint32_t get(uint32_t j) const {
+    if (W == 1) return (uint32_t)(w[0] >> (8 * j)) & 0xffu;
+    uint64_t x = w[0];
+#pragma unroll
+    for (int i = 1; i < W; ++i)
+      if ((j >> 3) == (uint32_t)i) x = w[i];
+    return (uint32_t)(x >> (8 * (j & 7))) & 0xffu;
+  }
+  // static index only
+  __device__ __forceinline__ void set(int j, uint32_t v) { w[j >> 3] |= (uint64_t)v << (8 * (j & 7)); }
+  __device__ __forceinline__ static Map zero() {
+    Map m;
+#pragma unroll
+    for (int i = 0; i < W; ++i) m.w[i] = 0;
+    return m;
+  }
+  // this o f : j -> this[f[j]]
+  __device__ __forceinline__ Map after(const Map& f) const {
+    Map r = zero();
+#pragma unroll
+    for (int j = 0; j < KP; ++j) r.set(j, get(f.get(j)));
+    return r;
+  }
+  __device__ __forceinline__ void store(uint8_t* p) const {
+    uint64_t* q = reinterpret_cast<uint64_t*>(p);
+#pragma unroll
+    for (int i = 0; i < W; ++i) q[i] = w[i];
+  }
+  __device__ __forceinline__ static Map load(const uint8_t* p) {
+    Map m;
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(p);
+#pragma unroll
+    for (int i = 0; i < W; ++i) m.w[i] = q[i];
+    return m;
+  }
+};
+
+// std::discrete_distribution rule (libstdc++ bits/random.tcc, used by Trellis.hpp:61-66 and
+// Mixture.hpp:111-112): normalise, partial sums, last := 1, first k with cp[k] >= u.  A row without
+// positive mass gives NaN partial sums in the reference, for which lower_bound returns index 0.
+template <int KP>
+__device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, double u) {
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) s += (k < K) ? p[k] : 0.0;
+  if (!(s > 0.0)) return 0u;
+  const double inv = 1.0 / s;
+  double acc = 0.0;
+  uint32_t res = (uint32_t)(K - 1);
+  bool found = false;
+#pragma unroll
+  for (int k = 0; k < KP - 1; ++k) {
+    if (k < K - 1) {
+      acc += p[k] * inv;
+      if (!found && acc >= u) {
+        res = (uint32_t)k;
+        found = true;
+      }
+    }
+  }
+  return res;
+}
+
+__device__ __forceinline__ uint64_t device_nblocks(const unsigned long long* nb, uint64_t capacity) {
+  const uint64_t b = *nb;
+  return b < capacity ? b : capacity;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_block_emit: thread per storage slot
+
+template <int KP, bool kGather, bool kEmit, bool kMix>
+__global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<KP> m, int want_maxe) {
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = Layout::inv(p);
+    if (b >= B) continue;
+    uint32_t n;
+    double sx, sq;
+    if (kGather) {
+      const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
+      const double2 ps = buf.pq[s], pe = buf.pq[e];
+      sx = pe.x - ps.x;
+      sq = pe.y - ps.y;
+      const uint32_t cs = s >> kCellLog2, ce = e >> kCellLog2;
+      if (cs != ce) {
+        const double4 a = buf.cell_pref[cs], z = buf.cell_pref[ce];
+        sx += (z.x - a.x) + (z.y - a.y);
+        sq += (z.z - a.z) + (z.w - a.w);
+      }
+      n = e - s;
+      buf.bN[p] = n;
+      buf.bS[p] = make_double2(sx, sq);
+    } else {
+      n = buf.bN[p];
+      const double2 v = buf.bS[p];
+      sx = v.x;
+      sq = v.y;
+    }
+    if (kEmit) {
+      const double N = (double)n;
+      double E[KP];
+      double mx = -INFINITY;
+#pragma unroll
+      for (int s = 0; s < KP; ++s) {
+        // EFD.hpp:23-32 then FB.hpp:74-81 (Mixture.hpp:98 has no self-transition term)
+        double v = (2.0 * m.mean[s] * sx - sq) * m.inv2var[s] - N * m.lognorm[s];
+        if (!kMix) v += (N - 1.0) * m.loga[s];
+        E[s] = v;
+        if (s < m.K) mx = fmax(mx, v);
+      }
+#pragma unroll
+      for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp(E[s] - mx) : 0.0;
+      if (!kMix) {
+#pragma unroll
+        for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+      }
+      if (want_maxe) buf.maxE[p] = mx;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fwd_chunks: CTA per tile; thread (chunk c, row i) runs the row recursion over the chunk.
+
+template <int KP>
+struct FwdCfg {
+  static constexpr int CG = (KP <= 8) ? 32 : (KP <= 16 ? 16 : 8);  // chunks handled per pass
+  static constexpr int THREADS = ((CG * KP + 31) / 32) * 32;
+  static constexpr bool SMEM_OPS = KP <= 8;
+};
+
+template <int KP>
+__global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers buf, ModelDev<KP> m) {
+  constexpr int L = Layout::L, C = Layout::C, CG = FwdCfg<KP>::CG;
+  __shared__ double s_ops[FwdCfg<KP>::SMEM_OPS ? C * KP * KP : 1];
+  __shared__ int s_exp[FwdCfg<KP>::SMEM_OPS ? C * KP : 1];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const int cl = threadIdx.x / KP, i = threadIdx.x % KP;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int cg = 0; cg < C; cg += CG) {
+      const int c = cg + cl;
+      if (cl < CG) {
+        const uint64_t first = tile * Layout::TB + (uint64_t)c * L;
+        int steps = 0;
+        if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+        double r[KP];
+        int rex = 0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+        const double* ep = buf.e + Layout::at(tile, c, 0) * KP;
+#pragma unroll 2
+        for (int t = 0; t < steps; ++t) {
+          double ev[KP];
+#pragma unroll
+          for (int j = 0; j < KP; ++j) ev[j] = ep[(uint64_t)t * C * KP + j];
+          double y[KP];
+#pragma unroll
+          for (int j = 0; j < KP; ++j) y[j] = 0.0;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) y[j] = fma(r[k], m.A[k][j], y[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < KP; ++j) r[j] = y[j] * ev[j];
+          if (rex != kDeadExp) renorm_pow2<KP>(r, rex);
+        }
+        const uint64_t ch = tile * C + c;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.chunk_ops[(ch * KP + i) * KP + j] = r[j];
+        buf.chunk_exp[ch * KP + i] = rex;
+        if (FwdCfg<KP>::SMEM_OPS) {
+#pragma unroll
+          for (int j = 0; j < KP; ++j) s_ops[(c * KP + i) * KP + j] = r[j];
+          s_exp[c * KP + i] = rex;
+        }
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // tile operator = product of the 32 chunk operators, one thread per row
+    if (threadIdx.x < KP) {
+      double r[KP];
+      int rex = 0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) r[j] = (j == (int)threadIdx.x) ? 1.0 : 0.0;
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        if (FwdCfg<KP>::SMEM_OPS)
+          row_times_op<KP, false>(r, rex, s_ops + c * KP * KP, s_exp + c * KP);
+        else
+          row_times_op<KP, true>(r, rex, buf.chunk_ops + (tile * C + c) * KP * KP, buf.chunk_exp + (tile * C + c) * KP);
+      }
+#pragma unroll
+      for (int j = 0; j < KP; ++j) buf.tile_ops[(tile * KP + threadIdx.x) * KP + j] = r[j];
+      buf.tile_exp[tile * KP + threadIdx.x] = rex;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fwd_tilescan: one CTA of 1024 threads.
+
+template <int KP>
+__global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDev<KP> m) {
+  __shared__ double s_gain[32][KP];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
+  if (nt == 0) return;
+  int G = (int)ceil(sqrt((double)nt));
+  if (G > 32) G = 32;
+  if (G > 1024 / KP) G = 1024 / KP;
+  const int S = (nt + G - 1) / G;
+  G = (nt + S - 1) / S;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // step 1: operator of each group of S tiles, thread (g, row)
+  {
+    const int g = threadIdx.x / KP, i = threadIdx.x % KP;
+    if (g < G) {
+      double r[KP];
+      int rex = 0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+      const int t1 = min(nt, (g + 1) * S);
+#pragma unroll 1
+      for (int t = g * S; t < t1; ++t)
+        row_times_op<KP, false>(r, rex, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
+#pragma unroll
+      for (int j = 0; j < KP; ++j) buf.group_ops[(g * KP + i) * KP + j] = r[j];
+      buf.group_exp[g * KP + i] = rex;
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  // step 2: warp 0 walks the groups; lane j holds alpha_j
+  if (warp == 0) {
+    double a = lane < KP ? m.pi[lane] : 0.0;  // row 0 of the trellis is pi itself (FB.hpp:57)
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+      if (lane < KP) s_gain[g][lane] = a;
+      if (!warp_vec_times_op<KP>(a, buf.group_ops + g * KP * KP, buf.group_exp + g * KP, lane) && lane == 0 && g + 1 < G)
+        atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+    }
+  }
+  __syncthreads();
+  // step 3: warp g replays its group and publishes the vector entering every tile
+  if (warp < G) {
+    double a = lane < KP ? s_gain[warp][lane] : 0.0;
+    const int t1 = min(nt, (warp + 1) * S);
+#pragma unroll 1
+    for (int t = warp * S; t < t1; ++t) {
+      if (lane < KP) buf.tile_ain[(uint64_t)t * KP + lane] = a;
+      if (t + 1 < t1) {
+        if (!warp_vec_times_op<KP>(a, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP, lane) && lane == 0)
+          atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fwd_replay: one warp per tile; lane c owns chunk c.
+
+template <int KP, bool kLoglik, bool kRows>
+__global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+  constexpr int L = Layout::L, C = Layout::C;
+  __shared__ double s_ain[C][KP + 1];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const int lane = threadIdx.x;
+  const int K = m.K;
+  double ll = 0.0;
+  unsigned fallbacks = 0;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ---- vector entering each chunk (warp-cooperative walk over the 32 chunk operators)
+    {
+      double a = lane < KP ? buf.tile_ain[tile * KP + lane] : 0.0;
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        if (lane < KP) s_ain[c][lane] = a;
+        const uint64_t ch = tile * C + c;
+        if (c + 1 < C && (ch + 1) * L < B) {
+          if (!warp_vec_times_op<KP>(a, buf.chunk_ops + ch * KP * KP, buf.chunk_exp + ch * KP, lane)) fallbacks += (lane == 0);
+        }
+      }
+    }
+    __syncwarp();
+    // ---- replay of chunk `lane`
+    const int c = lane;
+    const uint64_t first = tile * Layout::TB + (uint64_t)c * L;
+    int steps = 0;
+    if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+    double a[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = s_ain[c][j];
+    if (kRows && first == 0 && steps > 0) {
+      for (int j = 0; j < K; ++j) buf.rows[j] = m.pi[j];
+    }
+    Map<KP> G = Map<KP>::identity();
+#pragma unroll 1
+    for (int t = 0; t < steps; ++t) {
+      const uint64_t p = Layout::at(tile, c, t);
+      const uint64_t b = first + t;
+      double f[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) f[j] = 0.0;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
+      }
+      double fs = 0.0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        f[j] *= buf.e[p * KP + j];
+        fs += f[j];
+      }
+      if (fs != 0.0) {  // FB.hpp:101-105
+        const double inv = 1.0 / fs;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
+        if (kLoglik) ll += buf.maxE[p] + log(fs);
+      } else {          // FB.hpp:106-111: uniform fallback (the host then re-runs the sweep sequentially)
+        fallbacks++;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
+      }
+      // weights the backward pass will see: alpha'_t = alpha_t * A_ss^(N_t - 1) except for the last block
+      const bool last = (b + 1 == B);
+      double ap[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) ap[j] = (last || !m.use_self) ? a[j] : a[j] * buf.sp[p * KP + j];
+      if (kRows) {
+        for (int j = 0; j < K; ++j) buf.rows[(b + 1) * K + j] = ap[j];
+      }
+      const double u = buf.replay_u ? buf.replay_u[B - 1 - b] : Philox::uniform(seed, sweep, 0u, b);
+      Map<KP> fm = Map<KP>::zero();
+      if (last) {  // q_B ~ alpha_B (FB.hpp:138): constant map
+        const uint32_t q = discrete_draw<KP>(ap, K, u);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) fm.set(j, q);
+      } else {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          if (j < K) {
+            double w[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) w[k] = ap[k] * m.A[k][j];  // FB.hpp:145-146
+            fm.set(j, discrete_draw<KP>(w, K, u));
+          }
+        }
+      }
+      fm.store(buf.maps + p * (8 * Map<KP>::W));
+      G = G.after(fm);
+    }
+    if (steps > 0) G.store(buf.chunk_maps + (tile * C + c) * (8 * Map<KP>::W));
+    __syncwarp();
+  }
+  if (kLoglik) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ll += shfl_xor_double(ll, o);
+    if (lane == 0) buf.partials[blockIdx.x] = ll;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
+  if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[KP + KP * KP], (unsigned long long)fallbacks);
+}
+
+// Sequential forward replay (one thread): the exact reference recursion, used only when the
+// parallel pass reported a uniform fallback, whose effect on later blocks the operator products
+// cannot express.  Emits the same maps / chunk maps as k_fwd_replay.
+template <int KP, bool kLoglik, bool kRows>
+__global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  constexpr int L = Layout::L;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int K = m.K;
+  double a[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) a[j] = m.pi[j];
+  if (kRows)
+    for (int j = 0; j < K; ++j) buf.rows[j] = m.pi[j];
+  double ll = 0.0;
+  unsigned long long fallbacks = 0;
+  Map<KP> G = Map<KP>::identity();
+  for (uint64_t b = 0; b < B; ++b) {
+    const uint64_t p = Layout::perm(b);
+    double f[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) f[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
+    }
+    double fs = 0.0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      f[j] *= buf.e[p * KP + j];
+      fs += f[j];
+    }
+    if (fs != 0.0) {
+      const double inv = 1.0 / fs;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
+      if (kLoglik) ll += buf.maxE[p] + log(fs);
+    } else {
+      fallbacks++;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
+    }
+    const bool last = (b + 1 == B);
+    double ap[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) ap[j] = (last || !m.use_self) ? a[j] : a[j] * buf.sp[p * KP + j];
+    if (kRows)
+      for (int j = 0; j < K; ++j) buf.rows[(b + 1) * K + j] = ap[j];
+    const double u = buf.replay_u ? buf.replay_u[B - 1 - b] : Philox::uniform(seed, sweep, 0u, b);
+    Map<KP> fm = Map<KP>::zero();
+    if (last) {
+      const uint32_t q = discrete_draw<KP>(ap, K, u);
+#pragma unroll
+      for (int j = 0; j < KP; ++j) fm.set(j, q);
+    } else {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        if (j < K) {
+          double w[KP];
+#pragma unroll
+          for (int k = 0; k < KP; ++k) w[k] = ap[k] * m.A[k][j];
+          fm.set(j, discrete_draw<KP>(w, K, u));
+        }
+      }
+    }
+    fm.store(buf.maps + p * (8 * Map<KP>::W));
+    G = G.after(fm);
+    if ((b + 1) % L == 0 || last) {
+      G.store(buf.chunk_maps + (b / L) * (8 * Map<KP>::W));
+      G = Map<KP>::identity();
+    }
+  }
+  if (kLoglik) buf.partials[0] = ll;
+  buf.out_u64[KP + KP * KP] = fallbacks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bwd_scan: one CTA; suffix composition of the chunk maps.
+// chunk_qin[ch] = state of the first block after chunk ch (irrelevant for the last chunk, whose last
+// block carries a constant map).
+
+template <int KP>
+__global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
+  constexpr int MB = 8 * Map<KP>::W;
+  __shared__ uint64_t s_w[32][Map<KP>::W];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int64_t nch = (int64_t)((B + Layout::L - 1) / Layout::L);
+  if (nch == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t per = (nch + 1023) / 1024;
+  // thread `tid` owns chunks [lo, hi); threads are ordered by position, so thread 0 holds the earliest
+  const int64_t lo = min(nch, (int64_t)tid * per), hi = min(nch, lo + per);
+  // own = f_lo o f_{lo+1} o ... o f_{hi-1}  (maps a state after chunk hi-1 to the state entering... lo)
+  Map<KP> own = Map<KP>::identity();
+  for (int64_t ch = lo; ch < hi; ++ch) own = own.after(Map<KP>::load(buf.chunk_maps + ch * MB));
+  // suffix scan across threads: suf(tid) = own(tid+1) o own(tid+2) o ...   (exclusive)
+  // inclusive suffix within the warp by shuffles
+  Map<KP> inc = own;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Map<KP> other;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) other.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], o);
+    if (lane + o < 32) inc = inc.after(other);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) s_w[warp][i] = inc.w[i];
+  }
+  __syncthreads();
+  // map of everything after this warp
+  Map<KP> after_warp = Map<KP>::identity();
+  for (int wv = warp + 1; wv < 32; ++wv) {
+    Map<KP> o;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = s_w[wv][i];
+    after_warp = after_warp.after(o);
+  }
+  // exclusive suffix of this thread = inc(lane+1) o after_warp
+  Map<KP> nxt;
+#pragma unroll
+  for (int i = 0; i < Map<KP>::W; ++i) nxt.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
+  Map<KP> suf = (lane == 31) ? after_warp : nxt.after(after_warp);
+  // state following chunk hi-1: the suffix map is constant in its argument (last block's map is constant)
+  uint32_t q = suf.get(0);
+  for (int64_t ch = hi - 1; ch >= lo; --ch) {
+    buf.chunk_qin[ch] = (uint8_t)q;
+    q = Map<KP>::load(buf.chunk_maps + ch * MB).get(q);
+  }
+}
+
+// k_bwd_replay: thread per chunk, q_t = f_t[q_{t+1}]  (FB.hpp:140-160)
+template <int KP>
+__global__ void __launch_bounds__(128) k_bwd_replay(SweepBuffers buf) {
+  constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t nch = (B + L - 1) / L;
+  for (uint64_t ch = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; ch < nch; ch += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t tile = ch / C;
+    const int c = (int)(ch % C);
+    const uint64_t first = ch * L;
+    const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+    uint32_t q = buf.chunk_qin[ch];
+    for (int t = steps - 1; t >= 0; --t) {
+      const uint64_t p = Layout::at(tile, c, t);
+      q = Map<KP>::load(buf.maps + p * MB).get(q);
+      buf.states[p] = (uint8_t)q;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_mix_sample: StateSequence/Mixture.hpp:90-112, thread per storage slot
+
+template <int KP>
+__global__ void __launch_bounds__(256) k_mix_sample(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = Layout::inv(p);
+    if (b >= B) continue;
+    double w[KP];
+#pragma unroll
+    for (int s = 0; s < KP; ++s) w[s] = buf.e[p * KP + s];
+    const double u = buf.replay_u ? buf.replay_u[b] : Philox::uniform(seed, sweep, 1u, b);
+    buf.states[p] = (uint8_t)discrete_draw<KP>(w, m.K, u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions (FB.hpp:170-200).  Fixed grid, fixed per-thread order, fixed trees: results do not
+// depend on scheduling.
+
+constexpr int kReduceThreads = 256;
+
+template <int KP>
+__global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers buf, int K) {
+  __shared__ unsigned long long s_trans[KP * KP];
+  __shared__ unsigned long long s_n[KP];
+  __shared__ double s_sum[kReduceThreads / 32][2 * KP];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  for (int i = threadIdx.x; i < KP * KP; i += blockDim.x) s_trans[i] = 0;
+  for (int i = threadIdx.x; i < KP; i += blockDim.x) s_n[i] = 0;
+  __syncthreads();
+  double ax[KP], aq[KP];
+#pragma unroll
+  for (int s = 0; s < KP; ++s) ax[s] = aq[s] = 0.0;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = Layout::inv(p);
+    if (b >= B) continue;
+    const uint32_t st = buf.states[p];
+    const uint32_t prev = b == 0 ? 0u : buf.states[Layout::perm(b - 1)];  // phantom 0 -> q0 (FB.hpp:177,183)
+    const uint32_t n = buf.bN[p];
+    const double2 v = buf.bS[p];
+#pragma unroll
+    for (int s = 0; s < KP; ++s) {
+      ax[s] += (st == (uint32_t)s) ? v.x : 0.0;
+      aq[s] += (st == (uint32_t)s) ? v.y : 0.0;
+    }
+    atomicAdd(&s_n[st], (unsigned long long)n);
+    if (n > 1) atomicAdd(&s_trans[st * KP + st], (unsigned long long)(n - 1));
+    atomicAdd(&s_trans[prev * KP + st], 1ull);
+  }
+#pragma unroll
+  for (int s = 0; s < KP; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax[s] += shfl_xor_double(ax[s], o);
+      aq[s] += shfl_xor_double(aq[s], o);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int s = 0; s < KP; ++s) {
+      s_sum[threadIdx.x >> 5][s] = ax[s];
+      s_sum[threadIdx.x >> 5][KP + s] = aq[s];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * KP) {
+    double t = 0.0;
+    for (int wv = 0; wv < kReduceThreads / 32; ++wv) t += s_sum[wv][threadIdx.x];
+    buf.partials[(size_t)blockIdx.x * 2 * KP + threadIdx.x] = t;
+  }
+  for (int i = threadIdx.x; i < KP * KP; i += blockDim.x)
+    if (s_trans[i]) atomicAdd(&buf.out_u64[KP + i], s_trans[i]);
+  for (int i = threadIdx.x; i < KP; i += blockDim.x)
+    if (s_n[i]) atomicAdd(&buf.out_u64[i], s_n[i]);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(64) k_reduce_final(SweepBuffers buf, int nparts) {
+  if (threadIdx.x < 2 * KP) {
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += buf.partials[(size_t)i * 2 * KP + threadIdx.x];
+    buf.out_f64[threadIdx.x] = t;
+  }
+}
+
+template <int KP>
+__global__ void k_sum_partials(const double* partials, int n, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += partials[i];
+    *out = t;
+  }
+}
+
+template <int KP>
+__global__ void k_clear_out(SweepBuffers buf) {
+  const int n = KP + KP * KP + 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) buf.out_u64[i] = 0;
+  for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side orchestration (one instantiation per padded state count)
+
+inline int grid_for(uint64_t items, int threads, int sms, int per_sm) {
+  uint64_t g = (items + threads - 1) / threads;
+  const uint64_t cap = (uint64_t)sms * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <int KP>
+int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s, stage_cb_t cb,
+               void* user) {
+  const ModelDev<KP> m = make_model<KP>(mh);
+  const bool loglik = (l.flags & HML_SWEEP_LOGLIK) != 0;
+  const bool rows = (l.flags & HML_SWEEP_KEEP_ROWS) != 0 && b.rows != nullptr;
+  const uint64_t nb = l.nblocks_hint;
+  const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
+  int launches = 0;
+  auto stage = [&](const char* name) {
+    if (cb) cb(user, name);
+  };
+  stage("clear");
+  k_clear_out<KP><<<1, 256, 0, s>>>(b);
+  ++launches;
+  stage("block_emit");
+  {
+    const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 8);
+    if (l.mixture) {
+      if (l.gather)
+        k_block_emit<KP, true, true, true><<<g, 256, 0, s>>>(b, m, 0);
+      else
+        k_block_emit<KP, false, true, true><<<g, 256, 0, s>>>(b, m, 0);
+    } else {
+      if (l.gather)
+        k_block_emit<KP, true, true, false><<<g, 256, 0, s>>>(b, m, loglik);
+      else
+        k_block_emit<KP, false, true, false><<<g, 256, 0, s>>>(b, m, loglik);
+    }
+    ++launches;
+  }
+  if (l.mixture) {
+    stage("mix_sample");
+    k_mix_sample<KP><<<grid_for(ntiles * Layout::TB, 256, l.sms, 8), 256, 0, s>>>(b, m, l.seed, l.sweep);
+    ++launches;
+  } else {
+    stage("fwd_chunks");
+    k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 8), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
+    ++launches;
+    stage("fwd_tilescan");
+    k_fwd_tilescan<KP><<<1, 1024, 0, s>>>(b, m);
+    ++launches;
+    stage("fwd_replay");
+    const int gr = grid_for(ntiles, 1, l.sms, 32);
+    if (loglik) {
+      if (rows)
+        k_fwd_replay<KP, true, true><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
+      else
+        k_fwd_replay<KP, true, false><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
+      k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, gr, b.out_f64 + 2 * KP);
+      ++launches;
+    } else {
+      if (rows)
+        k_fwd_replay<KP, false, true><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
+      else
+        k_fwd_replay<KP, false, false><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
+    }
+    ++launches;
+    stage("bwd_scan");
+    k_bwd_scan<KP><<<1, 1024, 0, s>>>(b);
+    ++launches;
+    stage("bwd_replay");
+    k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
+    ++launches;
+  }
+  stage("reduce");
+  {
+    const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 2);
+    k_reduce_partial<KP><<<g, kReduceThreads, 0, s>>>(b, mh.K);
+    k_reduce_final<KP><<<1, 64, 0, s>>>(b, g);
+    launches += 2;
+  }
+  stage("end");
+  return launches;
+}
+
+template <int KP>
+int sequential_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s) {
+  const ModelDev<KP> m = make_model<KP>(mh);
+  const bool loglik = (l.flags & HML_SWEEP_LOGLIK) != 0;
+  const bool rows = (l.flags & HML_SWEEP_KEEP_ROWS) != 0 && b.rows != nullptr;
+  const uint64_t nb = l.nblocks_hint;
+  const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
+  k_clear_out<KP><<<1, 256, 0, s>>>(b);
+  if (loglik) {
+    if (rows)
+      k_fwd_sequential<KP, true, true><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
+    else
+      k_fwd_sequential<KP, true, false><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
+    k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, 1, b.out_f64 + 2 * KP);
+  } else {
+    if (rows)
+      k_fwd_sequential<KP, false, true><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
+    else
+      k_fwd_sequential<KP, false, false><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
+  }
+  k_bwd_scan<KP><<<1, 1024, 0, s>>>(b);
+  k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
+  const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 2);
+  k_reduce_partial<KP><<<g, kReduceThreads, 0, s>>>(b, mh.K);
+  k_reduce_final<KP><<<1, 64, 0, s>>>(b, g);
+  return 6 + (loglik ? 1 : 0);
+}
+
+}  // namespace hml

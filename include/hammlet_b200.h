@@ -1,0 +1,153 @@
+/* hammlet_b200 — C ABI of the B200-native hot path of HaMMLET
+ * (forward-backward Gibbs sweep over dynamically wavelet-compressed blocks).
+ *
+ * The reference (wiedenhoeft/HaMMLET) has no plugin / FFI boundary: `hammlet` is one translation
+ * unit of C++ templates.  This header is the boundary the new build introduces;
+ * each entry point names the reference code it replaces (paths relative to the reference's src/).
+ * The C++ model surface in hammlet_b200/host/ (Blocks, Statistics, Emissions, StateSequence, ...)
+ * and the ctypes binding in hammlet_b200/capi.py call exactly these functions.
+ *
+ * Conventions: plain C types; the caller owns host buffers, the library owns device memory; no
+ * exceptions cross the boundary — every function returns HML_OK (0) or a negative error code and
+ * hml_last_error() gives the message (host wrappers rethrow it as std::runtime_error, matching
+ * the reference's error behaviour, main.cpp:467-474).  A handle is not thread-safe (the
+ * reference is single-threaded).  There is NO CPU fallback: without a CUDA device hml_create
+ * fails.  One handle = one sequence (or one contiguous shard of a sequence) on one GPU.
+ *
+ * Numerics: breakpoint weights are fp32 and bit-identical to the reference's; block boundaries
+ * and all counts are exact; block statistics, emission terms and the trellis are fp64.
+ */
+#ifndef HAMMLET_B200_H
+#define HAMMLET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hml_ctx hml_t;
+
+enum {
+  HML_OK = 0,
+  HML_ERR_CUDA = -1,     /* a CUDA runtime call or kernel failed */
+  HML_ERR_ARG = -2,      /* invalid argument */
+  HML_ERR_STATE = -3,    /* call order: no data loaded / no blocks created / no sweep run */
+  HML_ERR_CAPACITY = -4, /* a caller buffer is too small */
+  HML_ERR_NUMERIC = -5   /* negative backward variable etc. (ForwardBackward.hpp:147-149) */
+};
+
+#define HML_MAX_STATES 32
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device` (own stream, scratch).  Fails if no device exists. */
+int hml_create(hml_t** out, int device);
+int hml_destroy(hml_t* h);
+/* Message of the last error on this handle (h == NULL: last error of hml_create). */
+const char* hml_last_error(const hml_t* h);
+const char* hml_version(void);
+
+/* ---- load: replaces MaxletTransform (wavelet.hpp:97-188), HaarBreakpointWeights
+ *      (wavelet.hpp:68-93), the weight multiplier (main.cpp:332-334), the Statistics<IntegralArray>
+ *      constructor (Statistics/IntegralArray.hpp:136-191) and the Blocks<BreakpointArray>
+ *      constructor (Blocks/BreakpointArray.hpp:130-184; its skip pointers are not needed here). */
+
+/* x: T values in host memory (univariate).  T < 2^32. */
+int hml_load_f32(hml_t* h, const float* x_host, uint64_t T, float weight_multiplier);
+/* Same with x already in device memory of the context's device (not modified, not retained). */
+int hml_load_f32_device(hml_t* h, const float* x_dev, uint64_t T, float weight_multiplier);
+/* Single-sequence multi-GPU mode: this handle holds positions [offset, offset+T) of a sequence of
+ * total length T_total.  Weights must then be supplied by the caller-side exchange (see
+ * hml_load_shard_* in INTEGRATION.md); offset = 0, T_total = T is the ordinary case. */
+int hml_size(const hml_t* h, uint64_t* T);
+/* Noise estimate of main.cpp:303-311: mean of the level-1 |detail| coefficients / sqrt(2/pi). */
+int hml_sigma_hat(hml_t* h, double* sigma_hat);
+/* Parity/debug: copy the fp32 breakpoint weights (after the multiplier) or the maxlet
+ * coefficients (before HaarBreakpointWeights) to host memory; n = T. */
+int hml_get_weights(hml_t* h, float* dst_host, uint64_t n);
+int hml_get_coeffs(hml_t* h, float* dst_host, uint64_t n);
+
+/* ---- blocks: replaces Blocks::createBlocks/initForward/next (Blocks/BreakpointArray.hpp:189-235)
+ *      and Statistics::setStats/addBlockStats (Statistics/IntegralArray.hpp:104-124,198-212). */
+
+/* Block boundaries {0} U {t : !(w[t] < threshold)} and per-block (N, sum x, sum x^2).
+ * The threshold is the caller's fp32 value, sqrt(2 log T * min var) evaluated on the host exactly
+ * as BreakpointArray.hpp:195-199 does; it is never recomputed on the device. */
+int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks);
+int hml_nr_blocks(const hml_t* h, uint64_t* nblocks);
+/* Copies the current block structure to host: starts[nblocks] (block b = [starts[b], starts[b+1])
+ * with starts[nblocks] = T implied), sum[nblocks], sumsq[nblocks].  Any pointer may be NULL. */
+int hml_get_blocks(hml_t* h, uint32_t* starts, double* sum, double* sumsq, uint64_t capacity);
+
+/* ---- sweeps: replace StateSequence<ForwardBackward>::sample (StateSequence/ForwardBackward.hpp:
+ *      16-213, incl. Trellis.hpp) and StateSequence<Mixture>::sample (StateSequence/Mixture.hpp:
+ *      31-144) up to, but not including, the O(K^2) conjugate updates, which stay on the host. */
+
+typedef struct {
+  int32_t K;               /* number of states, 2..HML_MAX_STATES (univariate: state == parameter) */
+  int32_t use_self_transitions; /* 0 with -S (main.cpp:157) */
+  const double* mean;      /* K   theta.value()[s].mean()  */
+  const double* var;       /* K   theta.value()[s].var()   */
+  const double* A;         /* K*K row-major A(i,j)         */
+  const double* pi;        /* K   pi.valueVector()         */
+} hml_model;
+
+typedef struct {
+  uint64_t nblocks;           /* blocks of the structure the sweep ran on */
+  uint64_t uniform_fallbacks; /* ForwardBackward.hpp:106-111 events ("[WARNING] Uniform sampling...") */
+  double loglik;              /* sum_t (max_s E_t(s) + log forwardSum_t); only if HML_SWEEP_LOGLIK */
+  /* caller-provided arrays, filled on return */
+  double* stat_sum;           /* K    per-state sum x      (ForwardBackward.hpp:189-191) */
+  double* stat_sumsq;         /* K    per-state sum x^2 */
+  uint64_t* stat_n;           /* K    per-state number of observations (Kahan term count) */
+  uint64_t* trans;            /* K*K  transition counts incl. N-1 self transitions per block and the
+                                      phantom 0 -> q0 transition (:182-184) */
+  uint64_t* counts;           /* K    state occupancy (:185) */
+} hml_sweep_out;
+
+enum {
+  HML_SWEEP_DYNAMIC = 1, /* re-derive the block structure from `threshold` first (HMM.hpp:100-102) */
+  HML_SWEEP_LOGLIK = 2,  /* also accumulate the forward log-likelihood */
+  HML_SWEEP_KEEP_ROWS = 4 /* keep the forward rows (B+1)xK for hml_get_rows (parity/debug) */
+};
+
+/* One FBG sweep.  Uniforms: counter-based Philox4x32-10 keyed by (seed, sweep_index, block), or —
+ * replay mode — `replay_uniforms` (host, n_replay >= nblocks) consumed in the reference's order,
+ * i.e. entry 0 samples the LAST block (ForwardBackward.hpp:140-162).  Replay needs the block count
+ * up front, so it cannot be combined with HML_SWEEP_DYNAMIC: call hml_create_blocks first. */
+int hml_fb_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold, uint64_t seed, uint64_t sweep_index,
+                 const double* replay_uniforms, uint64_t n_replay, hml_sweep_out* out);
+/* One mixture sweep (per-block independent draw); replay uniforms are consumed in block order. */
+int hml_mix_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold, uint64_t seed, uint64_t sweep_index,
+                  const double* replay_uniforms, uint64_t n_replay, hml_sweep_out* out);
+
+/* ---- records: inputs of Records::record(state, N) (Records.hpp:155-235) -------------------- */
+
+/* Per-block sampled states of the last sweep (marginal_t = int16, includes.hpp:13). */
+int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity);
+/* The last sweep's state sequence merged into maximal equal-state runs, as Records::record forms
+ * them (Records.hpp:166-188): seg_size[i] observations in state seg_state[i].  Call with NULL
+ * arrays to get *nsegments only. */
+int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t* seg_state, uint64_t capacity);
+/* Parity/debug: forward rows of the last HML_SWEEP_KEEP_ROWS sweep, (nblocks+1) x K, as the
+ * backward pass finds them (row 0 = pi; rows < nblocks carry the self-transition rescale of
+ * ForwardBackward.hpp:115-119). */
+int hml_get_rows(hml_t* h, double* rows, uint64_t capacity_rows);
+
+/* ---- measurement ---------------------------------------------------------------------------- */
+
+/* With timing on, every kernel stage of a sweep is bracketed by CUDA events on the context's
+ * stream.  hml_get_timing returns the stage names and the milliseconds of the LAST sweep. */
+int hml_set_timing(hml_t* h, int on);
+int hml_get_timing(hml_t* h, int* nstages, const char** names, float* ms, int capacity);
+/* Number of kernel launches issued by this handle since creation. */
+int hml_launch_count(const hml_t* h, uint64_t* n);
+/* Blocks until all work queued on the handle's stream has finished. */
+int hml_sync(hml_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAMMLET_B200_H */
