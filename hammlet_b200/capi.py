@@ -35,7 +35,7 @@ class _SweepOut(C.Structure):
 EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_load_f32", "hml_load_f32_device",
            "hml_size", "hml_sigma_hat", "hml_get_weights", "hml_get_coeffs", "hml_create_blocks", "hml_nr_blocks",
            "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
-           "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync"]
+           "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream"]
 
 _lib = None
 
@@ -195,6 +195,11 @@ class Handle:
 
     def sync(self):
         self._ck(self.lib.hml_sync(self.h))
+
+    def stream(self):
+        p = C.c_void_p()
+        self._ck(self.lib.hml_get_stream(self.h, C.byref(p)))
+        return p.value
 
 
 def philox_uniform(seed, sweep, stream, index):

@@ -792,4 +792,10 @@ int hml_sync(hml_t* h) {
   return HML_OK;
 }
 
+int hml_get_stream(hml_t* h, void** stream) {
+  if (!h || !stream) return HML_ERR_ARG;
+  *stream = (void*)h->stream;
+  return HML_OK;
+}
+
 }  // extern "C"

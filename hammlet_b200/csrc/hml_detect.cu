@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256, 6)
         if (tile == num_tiles - 1) {
           const uint64_t nb = running + tile_total;
           *nblocks_out = nb;
-          if (nb < capacity) starts[nb] = (uint32_t)T;  // sentinel: block b = [starts[b], starts[b+1])
+          if (nb <= capacity) starts[nb] = (uint32_t)T;  // sentinel (starts holds capacity + 1 entries)
         }
       }
     }

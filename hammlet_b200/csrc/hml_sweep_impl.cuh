@@ -216,9 +216,12 @@ __device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, 
   return res;
 }
 
+// Number of blocks the kernels may touch.  If boundary detection found more blocks than the per-block
+// arrays hold, the block list is incomplete: every kernel then sees an empty structure and the host,
+// which reads the same counter after the sweep, grows the arrays and repeats the sweep.
 __device__ __forceinline__ uint64_t device_nblocks(const unsigned long long* nb, uint64_t capacity) {
   const uint64_t b = *nb;
-  return b < capacity ? b : capacity;
+  return b <= capacity ? b : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -58,9 +58,6 @@ const char* hml_version(void);
 int hml_load_f32(hml_t* h, const float* x_host, uint64_t T, float weight_multiplier);
 /* Same with x already in device memory of the context's device (not modified, not retained). */
 int hml_load_f32_device(hml_t* h, const float* x_dev, uint64_t T, float weight_multiplier);
-/* Single-sequence multi-GPU mode: this handle holds positions [offset, offset+T) of a sequence of
- * total length T_total.  Weights must then be supplied by the caller-side exchange (see
- * hml_load_shard_* in INTEGRATION.md); offset = 0, T_total = T is the ordinary case. */
 int hml_size(const hml_t* h, uint64_t* T);
 /* Noise estimate of main.cpp:303-311: mean of the level-1 |detail| coefficients / sqrt(2/pi). */
 int hml_sigma_hat(hml_t* h, double* sigma_hat);
@@ -146,6 +143,8 @@ int hml_get_timing(hml_t* h, int* nstages, const char** names, float* ms, int ca
 int hml_launch_count(const hml_t* h, uint64_t* n);
 /* Blocks until all work queued on the handle's stream has finished. */
 int hml_sync(hml_t* h);
+/* The context's cudaStream_t (as void*), so callers can bracket calls with their own CUDA events. */
+int hml_get_stream(hml_t* h, void** stream);
 
 #ifdef __cplusplus
 }
