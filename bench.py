@@ -263,7 +263,7 @@ def main():
     e2e = world * steps / wall
     B = float(np.mean(nblocks))
     peak, peak_src = measured_peak()
-    det = float(np.mean(stage_ms.get("detect_compact", [float("nan")])))
+    det = float(np.mean(stage_ms.get("detect_flags", [float("nan")])))
     alg_bytes = 4.0 * T + 4.0 * B        # fp32 weight stream + uint32 block starts
     achieved = alg_bytes / (det * 1e-3) / 1e9
     busy = {k: float(np.mean(v)) for k, v in stage_ms.items()}
@@ -281,7 +281,7 @@ def main():
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_detect_compact", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_detect_flags", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": det,
                      "sweep_bytes": 4.0 * T + B * (4 + 16 + 16 * K + 2),

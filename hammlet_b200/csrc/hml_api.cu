@@ -36,12 +36,8 @@ struct hml_ctx {
   double4* cell_pref = nullptr;
   double sigma_hat = NAN;
 
-  // boundary detection
-  uint64_t* desc = nullptr;
-  uint32_t epoch = 0;
-  unsigned long long* ticket = nullptr;
-  unsigned long long ticket_base = 0;
-  int detect_grid = 0;
+  // boundary detection scratch (bit masks + per-tile / per-CTA counts)
+  void* detect_scratch = nullptr;
 
   // block structure
   uint64_t capacity = 0;  // multiple of kTileBlocks
@@ -55,7 +51,7 @@ struct hml_ctx {
   int KP = 0;
   int last_K = 0;
   double *e = nullptr, *sp = nullptr, *maxE = nullptr;
-  uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *chunk_qin = nullptr;
+  uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *tile_maps = nullptr, *tile_qin = nullptr;
   double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr;
   int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr;
   double* rows = nullptr;
@@ -143,7 +139,7 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
     CK(dev_alloc(h->bN, cap));
     CK(dev_alloc(h->bS, cap));
     CK(dev_alloc(h->states, cap));
-    CK(dev_alloc(h->chunk_qin, chunks));
+    CK(dev_alloc(h->tile_qin, tiles));
     h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
     dev_free(h->rows);
     h->rows_cap = 0;
@@ -154,6 +150,7 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
     CK(dev_alloc(h->maxE, cap));
     CK(dev_alloc(h->maps, cap * MB));
     CK(dev_alloc(h->chunk_maps, chunks * MB));
+    CK(dev_alloc(h->tile_maps, tiles * MB));
     CK(dev_alloc(h->chunk_ops, chunks * KP * KP));
     CK(dev_alloc(h->chunk_exp, chunks * KP));
     CK(dev_alloc(h->tile_ops, tiles * KP * KP));
@@ -187,7 +184,8 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.chunk_ops = h->chunk_ops;
   b.chunk_exp = h->chunk_exp;
   b.chunk_maps = h->chunk_maps;
-  b.chunk_qin = h->chunk_qin;
+  b.tile_maps = h->tile_maps;
+  b.tile_qin = h->tile_qin;
   b.tile_ops = h->tile_ops;
   b.tile_exp = h->tile_exp;
   b.tile_ain = h->tile_ain;
@@ -202,18 +200,8 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
 }
 
 int run_detect(hml_t* h, float thr) {
-  if (h->epoch >= (1u << 28) - 1) {
-    const uint64_t tiles = (h->T + kTile - 1) / kTile;
-    CK(cudaMemsetAsync(h->desc, 0, tiles * sizeof(uint64_t), h->stream));
-    h->epoch = 0;
-  }
-  h->epoch++;
-  const uint64_t tiles = (h->T + kTile - 1) / kTile;
-  stage_cb(h, "detect_compact");
-  launch_detect_compact(h->w, h->T, thr, 1, h->desc, h->epoch, h->ticket, h->ticket_base, h->starts, h->capacity,
-                        h->outblk, h->detect_grid, h->stream);
-  h->ticket_base += tiles + (uint64_t)h->detect_grid;
-  h->launches++;
+  h->launches += launch_detect(h->w, h->T, thr, 1, h->detect_scratch, h->starts, h->capacity, h->outblk, h->stream,
+                               stage_cb, h);
   CK(cudaGetLastError());
   return HML_OK;
 }
@@ -224,7 +212,8 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
   dev_free(h->coeffs);
   dev_free(h->pq);
   dev_free(h->cell_pref);
-  dev_free(h->desc);
+  if (h->detect_scratch) cudaFree(h->detect_scratch);
+  h->detect_scratch = nullptr;
   h->T = 0;
   h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
   const uint64_t tiles = (T + kTile - 1) / kTile;
@@ -332,10 +321,8 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
   dev_free(sums[1]);
   if (T > (1ull << 26)) dev_free(h->coeffs);  // 4 B/observation is not worth keeping for big inputs
 
-  // ---- look-back descriptors
-  CK(dev_alloc(h->desc, tiles));
-  CK(cudaMemsetAsync(h->desc, 0, tiles * sizeof(uint64_t), h->stream));
-  h->epoch = 0;
+  // ---- boundary-detection scratch
+  CK(cudaMalloc(&h->detect_scratch, detect_scratch_bytes(T)));
   h->T = T;
 
   // ---- initial block capacity: grows on demand (a sweep that overflows is re-run)
@@ -517,16 +504,13 @@ int hml_create(hml_t** out, int device) {
     return HML_ERR_CUDA;
   }
   h->sms = prop.multiProcessorCount;
-  h->detect_grid = detect_grid_size(h->sms);
   if (cudaMalloc((void**)&h->outblk, kOutWords * 8) != cudaSuccess ||
-      cudaMallocHost((void**)&h->outblk_host, kOutWords * 8) != cudaSuccess ||
-      cudaMalloc((void**)&h->ticket, 8) != cudaSuccess) {
+      cudaMallocHost((void**)&h->outblk_host, kOutWords * 8) != cudaSuccess) {
     g_create_error = "allocation of the result block failed";
     delete h;
     return HML_ERR_CUDA;
   }
   cudaMemset(h->outblk, 0, kOutWords * 8);
-  cudaMemset(h->ticket, 0, 8);
   *out = h;
   return HML_OK;
 }
@@ -539,8 +523,7 @@ int hml_destroy(hml_t* h) {
   dev_free(h->coeffs);
   dev_free(h->pq);
   dev_free(h->cell_pref);
-  dev_free(h->desc);
-  dev_free(h->ticket);
+  if (h->detect_scratch) cudaFree(h->detect_scratch);
   dev_free(h->starts);
   dev_free(h->bN);
   dev_free(h->bS);
@@ -550,7 +533,8 @@ int hml_destroy(hml_t* h) {
   dev_free(h->maps);
   dev_free(h->states);
   dev_free(h->chunk_maps);
-  dev_free(h->chunk_qin);
+  dev_free(h->tile_maps);
+  dev_free(h->tile_qin);
   dev_free(h->chunk_ops);
   dev_free(h->tile_ops);
   dev_free(h->tile_ain);

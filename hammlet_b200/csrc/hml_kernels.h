@@ -14,10 +14,11 @@ void launch_sum_odd(const float* c, uint64_t T, double* partial, int nblocks, cu
 void launch_integral_cells(const float* x, uint64_t T, double2* pq, double2* cell_tot, cudaStream_t s);
 
 // ---- boundary detection (hml_detect.cu)
-int detect_grid_size(int sms);
-void launch_detect_compact(const float* w, uint64_t T, float thr, int force_first, uint64_t* desc, uint32_t epoch,
-                           unsigned long long* ticket, unsigned long long ticket_base, uint32_t* starts,
-                           uint64_t capacity, unsigned long long* nblocks_out, int grid, cudaStream_t s);
+typedef void (*stage_cb_t)(void* user, const char* name);
+size_t detect_scratch_bytes(uint64_t T);
+// flags -> counts -> ordered block starts; returns the number of kernels launched
+int launch_detect(const float* w, uint64_t T, float thr, int force_first, void* scratch, uint32_t* starts,
+                  uint64_t capacity, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb, void* user);
 
 // ---- block-level sweep kernels (hml_sweep.cu)
 struct ModelHost {  // what the C ABI receives, validated
@@ -46,8 +47,9 @@ struct SweepBuffers {
   uint8_t* states;          // sampled state per block
   double* chunk_ops;        // per chunk KP*KP
   int* chunk_exp;           // per chunk KP
-  uint8_t* chunk_maps;      // per chunk KPB
-  uint8_t* chunk_qin;       // per chunk: state of the block following the chunk
+  uint8_t* chunk_maps;      // per chunk KPB: composed map of the LATER chunks of the same tile
+  uint8_t* tile_maps;       // per tile KPB: composed map of the tile
+  uint8_t* tile_qin;        // per tile: state of the block following the tile
   double* tile_ops;         // per tile KP*KP
   int* tile_exp;            // per tile KP
   double* tile_ain;         // per tile KP: normalised forward vector entering the tile
@@ -78,7 +80,6 @@ struct SweepLaunch {
 
 // Enqueues all block-level kernels of one sweep on `s`; returns the number of kernels launched.
 // stage_cb(name) is called before each stage so the caller can drop timing events.
-typedef void (*stage_cb_t)(void* user, const char* name);
 int launch_sweep(const ModelHost& m, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s, stage_cb_t cb,
                  void* user);
 

@@ -111,35 +111,61 @@ __device__ __forceinline__ void row_times_op(double (&r)[KP], int& rex, const do
   renorm_pow2<KP>(r, rex);
 }
 
-// Warp-cooperative a <- normalise(a * Op): lane j holds a_j (lanes >= KP hold 0).  Returns false if
-// the product vanished (the caller flags a uniform-fallback suspect).
+// Warp-cooperative a <- normalise(a * Op): lane j holds a_j (lanes >= KP hold 0) and column j of the
+// operator (LaneOp), loaded one step ahead of its use so the dependent chain never waits on memory.
 template <int KP>
-__device__ __forceinline__ bool warp_vec_times_op(double& a, const double* M, const int* X, int lane) {
+struct LaneOp {
+  double col[KP];  // col[k] = M[k][lane]
+  int x;           // lane k holds the binary exponent of row k
+};
+
+template <int KP>
+__device__ __forceinline__ void load_lane_op(LaneOp<KP>& o, const double* M, const int* X, int lane) {
+#pragma unroll
+  for (int k = 0; k < KP; ++k) o.col[k] = lane < KP ? M[k * KP + lane] : 0.0;
+  o.x = lane < KP ? X[lane] : kDeadExp;
+}
+
+// Returns false if the product vanished (the caller flags a uniform-fallback suspect).
+template <int KP>
+__device__ __forceinline__ bool warp_apply_op(double& a, const LaneOp<KP>& o) {
   int xm = kDeadExp;
+  int xk[KP];
+  double ak[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    const double ak = shfl_double(a, k);
-    const int x = X[k];
-    if (ak > 0.0 && x > xm) xm = x;
+    ak[k] = shfl_double(a, k);
+    xk[k] = __shfl_sync(0xffffffffu, o.x, k);
+    if (ak[k] > 0.0 && xk[k] > xm) xm = xk[k];
   }
   double y = 0.0;
   if (xm != kDeadExp) {
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      const double ak = shfl_double(a, k) * pow2i(X[k] - xm);
-      const double mkj = lane < KP ? M[k * KP + lane] : 0.0;
-      y = fma(ak, mkj, y);
-    }
+    for (int k = 0; k < KP; ++k) y = fma(ak[k] * pow2i(xk[k] - xm), o.col[k], y);
   }
   double s = y;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += shfl_xor_double(s, o);
+  for (int o2 = 16; o2 > 0; o2 >>= 1) s += shfl_xor_double(s, o2);
   if (!(s > 0.0)) {
     a = 0.0;
     return false;
   }
   a = y / s;
   return true;
+}
+
+// Thread-local operator copy (small K only) for prefetching ahead of a dependent row recursion.
+template <int KP>
+struct OpVals {
+  double m[KP * KP];
+  int x[KP];
+};
+template <int KP>
+__device__ __forceinline__ void load_op(OpVals<KP>& o, const double* M, const int* X) {
+#pragma unroll
+  for (int k = 0; k < KP * KP; ++k) o.m[k] = M[k];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) o.x[k] = X[k];
 }
 
 // ---- byte-packed state maps (KPB = 8, 16 or 32 entries of one byte)
@@ -362,20 +388,35 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers
 
 // ------------------------------------------------------------------------------------------------
 // k_fwd_tilescan: one CTA of 1024 threads.
+//   step 1  thread (group, row): operator of each group of S consecutive tiles (row recursion, operators
+//           prefetched one tile ahead for K <= 8)
+//   step 2  warp 0 walks the group operators (shared memory for K <= 8): forward vector entering each group
+//   step 3  warp per group (two groups per warp if G > 32): forward vector entering each tile
+
+template <int KP>
+struct ScanCfg {
+  static constexpr int GMAX = (KP <= 8) ? 64 : 32;
+  static constexpr bool SMEM = KP <= 8;
+};
 
 template <int KP>
 __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDev<KP> m) {
-  __shared__ double s_gain[32][KP];
+  constexpr int GMAX = ScanCfg<KP>::GMAX;
+  __shared__ double s_gain[GMAX][KP];
+  __shared__ double s_gop[ScanCfg<KP>::SMEM ? GMAX * KP * KP : 1];
+  __shared__ int s_gexp[ScanCfg<KP>::SMEM ? GMAX * KP : 1];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
   if (nt == 0) return;
   int G = (int)ceil(sqrt((double)nt));
-  if (G > 32) G = 32;
+  if (G > GMAX) G = GMAX;
   if (G > 1024 / KP) G = 1024 / KP;
   const int S = (nt + G - 1) / G;
   G = (nt + S - 1) / S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // step 1: operator of each group of S tiles, thread (g, row)
+  double* gop = ScanCfg<KP>::SMEM ? s_gop : buf.group_ops;
+  int* gexp = ScanCfg<KP>::SMEM ? s_gexp : buf.group_exp;
+  // ---- step 1
   {
     const int g = threadIdx.x / KP, i = threadIdx.x % KP;
     if (g < G) {
@@ -383,39 +424,57 @@ __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDe
       int rex = 0;
 #pragma unroll
       for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
-      const int t1 = min(nt, (g + 1) * S);
+      const int t0 = g * S, t1 = min(nt, (g + 1) * S);
+      if (KP <= 8) {
+        OpVals<KP> cur, nxt;
+        load_op<KP>(cur, buf.tile_ops + (uint64_t)t0 * KP * KP, buf.tile_exp + (uint64_t)t0 * KP);
 #pragma unroll 1
-      for (int t = g * S; t < t1; ++t)
-        row_times_op<KP, false>(r, rex, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
+        for (int t = t0; t < t1; ++t) {
+          const int tn = (t + 1 < t1) ? t + 1 : t;
+          load_op<KP>(nxt, buf.tile_ops + (uint64_t)tn * KP * KP, buf.tile_exp + (uint64_t)tn * KP);
+          row_times_op<KP, false>(r, rex, cur.m, cur.x);
+          cur = nxt;
+        }
+      } else {
+#pragma unroll 1
+        for (int t = t0; t < t1; ++t)
+          row_times_op<KP, false>(r, rex, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
+      }
 #pragma unroll
-      for (int j = 0; j < KP; ++j) buf.group_ops[(g * KP + i) * KP + j] = r[j];
-      buf.group_exp[g * KP + i] = rex;
+      for (int j = 0; j < KP; ++j) gop[(g * KP + i) * KP + j] = r[j];
+      gexp[g * KP + i] = rex;
     }
   }
   __threadfence_block();
   __syncthreads();
-  // step 2: warp 0 walks the groups; lane j holds alpha_j
+  // ---- step 2
   if (warp == 0) {
     double a = lane < KP ? m.pi[lane] : 0.0;  // row 0 of the trellis is pi itself (FB.hpp:57)
+    LaneOp<KP> cur, nxt;
+    load_lane_op<KP>(cur, gop, gexp, lane);
 #pragma unroll 1
     for (int g = 0; g < G; ++g) {
       if (lane < KP) s_gain[g][lane] = a;
-      if (!warp_vec_times_op<KP>(a, buf.group_ops + g * KP * KP, buf.group_exp + g * KP, lane) && lane == 0 && g + 1 < G)
-        atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      const int gn = (g + 1 < G) ? g + 1 : g;
+      load_lane_op<KP>(nxt, gop + gn * KP * KP, gexp + gn * KP, lane);
+      if (g + 1 < G && !warp_apply_op<KP>(a, cur) && lane == 0) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      cur = nxt;
     }
   }
   __syncthreads();
-  // step 3: warp g replays its group and publishes the vector entering every tile
-  if (warp < G) {
-    double a = lane < KP ? s_gain[warp][lane] : 0.0;
-    const int t1 = min(nt, (warp + 1) * S);
+  // ---- step 3
+  for (int g = warp; g < G; g += 32) {
+    double a = lane < KP ? s_gain[g][lane] : 0.0;
+    const int t0 = g * S, t1 = min(nt, (g + 1) * S);
+    LaneOp<KP> cur, nxt;
+    load_lane_op<KP>(cur, buf.tile_ops + (uint64_t)t0 * KP * KP, buf.tile_exp + (uint64_t)t0 * KP, lane);
 #pragma unroll 1
-    for (int t = warp * S; t < t1; ++t) {
+    for (int t = t0; t < t1; ++t) {
       if (lane < KP) buf.tile_ain[(uint64_t)t * KP + lane] = a;
-      if (t + 1 < t1) {
-        if (!warp_vec_times_op<KP>(a, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP, lane) && lane == 0)
-          atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
-      }
+      const int tn = (t + 1 < t1) ? t + 1 : t;
+      load_lane_op<KP>(nxt, buf.tile_ops + (uint64_t)tn * KP * KP, buf.tile_exp + (uint64_t)tn * KP, lane);
+      if (t + 1 < t1 && !warp_apply_op<KP>(a, cur) && lane == 0) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      cur = nxt;
     }
   }
 }
@@ -437,13 +496,18 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
     // ---- vector entering each chunk (warp-cooperative walk over the 32 chunk operators)
     {
       double a = lane < KP ? buf.tile_ain[tile * KP + lane] : 0.0;
+      LaneOp<KP> cur, nxt;
+      load_lane_op<KP>(cur, buf.chunk_ops + tile * C * KP * KP, buf.chunk_exp + tile * C * KP, lane);
 #pragma unroll 1
       for (int c = 0; c < C; ++c) {
         if (lane < KP) s_ain[c][lane] = a;
         const uint64_t ch = tile * C + c;
+        const uint64_t chn = (c + 1 < C) ? ch + 1 : ch;
+        load_lane_op<KP>(nxt, buf.chunk_ops + chn * KP * KP, buf.chunk_exp + chn * KP, lane);
         if (c + 1 < C && (ch + 1) * L < B) {
-          if (!warp_vec_times_op<KP>(a, buf.chunk_ops + ch * KP * KP, buf.chunk_exp + ch * KP, lane)) fallbacks += (lane == 0);
+          if (!warp_apply_op<KP>(a, cur)) fallbacks += (lane == 0);
         }
+        cur = nxt;
       }
     }
     __syncwarp();
@@ -515,7 +579,24 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
       fm.store(buf.maps + p * (8 * Map<KP>::W));
       G = G.after(fm);
     }
-    if (steps > 0) G.store(buf.chunk_maps + (tile * C + c) * (8 * Map<KP>::W));
+    // ---- maps: X_c = G_{c+1} o ... o G_31 (state after chunk c given the state after the tile) and
+    //      the tile map G_0 o ... o G_31, by a suffix scan over the warp
+    {
+      Map<KP> inc = G;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        Map<KP> other;
+#pragma unroll
+        for (int i = 0; i < Map<KP>::W; ++i) other.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], o);
+        if (lane + o < 32) inc = inc.after(other);
+      }
+      Map<KP> excl;
+#pragma unroll
+      for (int i = 0; i < Map<KP>::W; ++i) excl.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
+      if (lane == 31) excl = Map<KP>::identity();
+      excl.store(buf.chunk_maps + (tile * C + c) * (8 * Map<KP>::W));
+      if (lane == 0) inc.store(buf.tile_maps + tile * (8 * Map<KP>::W));
+    }
     __syncwarp();
   }
   if (kLoglik) {
@@ -545,6 +626,8 @@ __global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDe
   double ll = 0.0;
   unsigned long long fallbacks = 0;
   Map<KP> G = Map<KP>::identity();
+  Map<KP> gc[Layout::C];
+  for (int c = 0; c < Layout::C; ++c) gc[c] = Map<KP>::identity();
   for (uint64_t b = 0; b < B; ++b) {
     const uint64_t p = Layout::perm(b);
     double f[KP];
@@ -597,8 +680,18 @@ __global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDe
     fm.store(buf.maps + p * (8 * Map<KP>::W));
     G = G.after(fm);
     if ((b + 1) % L == 0 || last) {
-      G.store(buf.chunk_maps + (b / L) * (8 * Map<KP>::W));
+      gc[(b / L) % Layout::C] = G;
       G = Map<KP>::identity();
+    }
+    if ((b + 1) % Layout::TB == 0 || last) {  // tile complete: exclusive suffix maps per chunk + tile map
+      const uint64_t tile = b / Layout::TB;
+      Map<KP> suf = Map<KP>::identity();
+      for (int c = Layout::C - 1; c >= 0; --c) {
+        suf.store(buf.chunk_maps + (tile * Layout::C + c) * (8 * Map<KP>::W));
+        suf = gc[c].after(suf);
+        gc[c] = Map<KP>::identity();
+      }
+      suf.store(buf.tile_maps + tile * (8 * Map<KP>::W));
     }
   }
   if (kLoglik) buf.partials[0] = ll;
@@ -606,25 +699,23 @@ __global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDe
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_bwd_scan: one CTA; suffix composition of the chunk maps.
-// chunk_qin[ch] = state of the first block after chunk ch (irrelevant for the last chunk, whose last
-// block carries a constant map).
+// k_bwd_scan: one CTA; suffix composition of the tile maps.
+// tile_qin[t] = state of the first block after tile t (irrelevant for the last tile, whose last block
+// carries a constant map).
 
 template <int KP>
 __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
   constexpr int MB = 8 * Map<KP>::W;
   __shared__ uint64_t s_w[32][Map<KP>::W];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
-  const int64_t nch = (int64_t)((B + Layout::L - 1) / Layout::L);
-  if (nch == 0) return;
+  const int64_t nt = (int64_t)((B + Layout::TB - 1) / Layout::TB);
+  if (nt == 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t per = (nch + 1023) / 1024;
-  // thread `tid` owns chunks [lo, hi); threads are ordered by position, so thread 0 holds the earliest
-  const int64_t lo = min(nch, (int64_t)tid * per), hi = min(nch, lo + per);
-  // own = f_lo o f_{lo+1} o ... o f_{hi-1}  (maps a state after chunk hi-1 to the state entering... lo)
-  Map<KP> own = Map<KP>::identity();
-  for (int64_t ch = lo; ch < hi; ++ch) own = own.after(Map<KP>::load(buf.chunk_maps + ch * MB));
-  // suffix scan across threads: suf(tid) = own(tid+1) o own(tid+2) o ...   (exclusive)
+  const int64_t per = (nt + 1023) / 1024;
+  // thread `tid` owns tiles [lo, hi); threads are ordered by position, so thread 0 holds the earliest
+  const int64_t lo = min(nt, (int64_t)tid * per), hi = min(nt, lo + per);
+  Map<KP> own = Map<KP>::identity();  // own = f_lo o f_{lo+1} o ... o f_{hi-1}
+  for (int64_t t = lo; t < hi; ++t) own = own.after(Map<KP>::load(buf.tile_maps + t * MB));
   // inclusive suffix within the warp by shuffles
   Map<KP> inc = own;
 #pragma unroll
@@ -639,24 +730,22 @@ __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
     for (int i = 0; i < Map<KP>::W; ++i) s_w[warp][i] = inc.w[i];
   }
   __syncthreads();
-  // map of everything after this warp
-  Map<KP> after_warp = Map<KP>::identity();
+  Map<KP> after_warp = Map<KP>::identity();  // map of everything after this warp
   for (int wv = warp + 1; wv < 32; ++wv) {
     Map<KP> o;
 #pragma unroll
     for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = s_w[wv][i];
     after_warp = after_warp.after(o);
   }
-  // exclusive suffix of this thread = inc(lane+1) o after_warp
   Map<KP> nxt;
 #pragma unroll
   for (int i = 0; i < Map<KP>::W; ++i) nxt.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
-  Map<KP> suf = (lane == 31) ? after_warp : nxt.after(after_warp);
-  // state following chunk hi-1: the suffix map is constant in its argument (last block's map is constant)
+  const Map<KP> suf = (lane == 31) ? after_warp : nxt.after(after_warp);
+  // the suffix map is constant in its argument because the last block's map is constant
   uint32_t q = suf.get(0);
-  for (int64_t ch = hi - 1; ch >= lo; --ch) {
-    buf.chunk_qin[ch] = (uint8_t)q;
-    q = Map<KP>::load(buf.chunk_maps + ch * MB).get(q);
+  for (int64_t t = hi - 1; t >= lo; --t) {
+    buf.tile_qin[t] = (uint8_t)q;
+    q = Map<KP>::load(buf.tile_maps + t * MB).get(q);
   }
 }
 
@@ -671,7 +760,8 @@ __global__ void __launch_bounds__(128) k_bwd_replay(SweepBuffers buf) {
     const int c = (int)(ch % C);
     const uint64_t first = ch * L;
     const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
-    uint32_t q = buf.chunk_qin[ch];
+    // state following this chunk = (maps of the later chunks of the tile)(state following the tile)
+    uint32_t q = Map<KP>::load(buf.chunk_maps + ch * MB).get(buf.tile_qin[tile]);
     for (int t = steps - 1; t >= 0; --t) {
       const uint64_t p = Layout::at(tile, c, t);
       q = Map<KP>::load(buf.maps + p * MB).get(q);
@@ -715,8 +805,12 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
   for (int i = threadIdx.x; i < KP; i += blockDim.x) s_n[i] = 0;
   __syncthreads();
   double ax[KP], aq[KP];
+  unsigned long long an[KP], ad[KP];  // observations per state; diagonal transition counts
 #pragma unroll
-  for (int s = 0; s < KP; ++s) ax[s] = aq[s] = 0.0;
+  for (int s = 0; s < KP; ++s) {
+    ax[s] = aq[s] = 0.0;
+    an[s] = ad[s] = 0;
+  }
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = Layout::inv(p);
     if (b >= B) continue;
@@ -724,14 +818,16 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
     const uint32_t prev = b == 0 ? 0u : buf.states[Layout::perm(b - 1)];  // phantom 0 -> q0 (FB.hpp:177,183)
     const uint32_t n = buf.bN[p];
     const double2 v = buf.bS[p];
+    const unsigned long long dg = (unsigned long long)(n - 1) + (prev == st ? 1ull : 0ull);  // FB.hpp:182-183
 #pragma unroll
     for (int s = 0; s < KP; ++s) {
-      ax[s] += (st == (uint32_t)s) ? v.x : 0.0;
-      aq[s] += (st == (uint32_t)s) ? v.y : 0.0;
+      const bool hit = st == (uint32_t)s;
+      ax[s] += hit ? v.x : 0.0;
+      aq[s] += hit ? v.y : 0.0;
+      an[s] += hit ? (unsigned long long)n : 0ull;
+      ad[s] += hit ? dg : 0ull;
     }
-    atomicAdd(&s_n[st], (unsigned long long)n);
-    if (n > 1) atomicAdd(&s_trans[st * KP + st], (unsigned long long)(n - 1));
-    atomicAdd(&s_trans[prev * KP + st], 1ull);
+    if (prev != st) atomicAdd(&s_trans[prev * KP + st], 1ull);  // state changes are rare: low contention
   }
 #pragma unroll
   for (int s = 0; s < KP; ++s) {
@@ -739,6 +835,8 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
     for (int o = 16; o > 0; o >>= 1) {
       ax[s] += shfl_xor_double(ax[s], o);
       aq[s] += shfl_xor_double(aq[s], o);
+      an[s] += __shfl_xor_sync(0xffffffffu, an[s], o);
+      ad[s] += __shfl_xor_sync(0xffffffffu, ad[s], o);
     }
   }
   if ((threadIdx.x & 31) == 0) {
@@ -746,6 +844,8 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
     for (int s = 0; s < KP; ++s) {
       s_sum[threadIdx.x >> 5][s] = ax[s];
       s_sum[threadIdx.x >> 5][KP + s] = aq[s];
+      if (an[s]) atomicAdd(&s_n[s], an[s]);
+      if (ad[s]) atomicAdd(&s_trans[s * KP + s], ad[s]);
     }
   }
   __syncthreads();
