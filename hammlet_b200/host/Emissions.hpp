@@ -1,0 +1,250 @@
+// hammlet_b200 host side — compressed emissions: the data of one sequence resident on one B200.
+//
+// Mirrors the reference's layer L2 (src/Emissions.hpp, src/Blocks/BreakpointArray.hpp,
+// src/Statistics/IntegralArray.hpp, src/wavelet.hpp, src/AutoPriors.hpp).  The reference builds host
+// vectors (maxlet coefficients -> breakpoint weights, integral arrays, skip pointers) and iterates
+// blocks on the CPU; here DeviceSequence::load hands the parsed values to hml_load_f32 once, and
+// Blocks / Statistics / Emissions are views onto that device-resident sequence:
+//   * Blocks::createBlocks(thr) only records the fp32 threshold; the samplers pass it to the device,
+//     which derives the block structure inside the sweep (no host round trip);
+//   * the iterator protocol (initForward / next / start / end / blockSize / suffStat / nrBlocks) is kept
+//     for callers that walk blocks on the host (autoPrior does): it materialises the block list through
+//     hml_create_blocks + hml_get_blocks on first use.
+// Differences in construction are listed in INTEGRATION.md.
+#pragma once
+
+#include <memory>
+
+#include "../../include/hammlet_b200.h"
+#include "Model.hpp"
+
+// Thin RAII owner of an hml_t; every C-ABI failure becomes std::runtime_error, like every reference error.
+class DeviceSequence {
+  hml_t* mHandle = nullptr;
+  uint64_t mSize = 0;
+  double mSigmaHat = 0;
+
+ public:
+  DeviceSequence(const DeviceSequence&) = delete;
+  explicit DeviceSequence(int device = 0) {
+    if (hml_create(&mHandle, device) != HML_OK) throw std::runtime_error(hml_last_error(nullptr));
+  }
+  ~DeviceSequence() { hml_destroy(mHandle); }
+  void check(int rc) const {
+    if (rc != HML_OK) throw std::runtime_error(hml_last_error(mHandle));
+  }
+  hml_t* handle() const { return mHandle; }
+  size_t size() const { return mSize; }
+
+  // MaxletTransform + HaarBreakpointWeights + weight multiplier + integral arrays, on the device
+  // (wavelet.hpp:97-188, :68-93; main.cpp:332-334; IntegralArray.hpp:136-191)
+  void load(const std::vector<float>& values, float weightMultiplier) {
+    if (values.empty()) throw std::runtime_error("Input vector for breakpoint weights is empty!");
+    check(hml_load_f32(mHandle, values.data(), values.size(), weightMultiplier));
+    mSize = values.size();
+    check(hml_sigma_hat(mHandle, &mSigmaHat));
+  }
+  // noise estimate from the finest detail coefficients (main.cpp:303-311)
+  double noiseStdev() const { return mSigmaHat; }
+};
+
+// Reads whitespace-separated numbers exactly like `input >> v` (wavelet.hpp:131) and loads them.
+inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size_t nrDim, const float weightMultiplier,
+                            const size_t reserveT = 0) {
+  if (nrDim <= 0) throw std::runtime_error("Number of dimensions must be positive!");
+  if (nrDim != 1) throw std::runtime_error("Multivariate data is not supported by the B200 path yet (d = 1 only)!");
+  if (!input) throw std::runtime_error("Cannot read input file or stream!");
+  std::vector<float> values;
+  values.reserve(reserveT);
+  float v;
+  while (input >> v) values.push_back(v);
+  seq.load(values, weightMultiplier);
+}
+
+template <typename T> class Blocks;
+template <typename T, typename StatsType> class Statistics;
+template <typename DataStructure, typename DistType> class Emissions;
+
+template <>
+class Blocks<BreakpointArray> {
+  DeviceSequence& mSeq;
+  real_t mThreshold = 0;
+  bool mDirty = true;         // threshold changed since the device last built the structure
+  // host copy for the iterator protocol
+  std::vector<uint32_t> mStarts;
+  std::vector<double> mSum, mSumSq;
+  bool mHostValid = false;
+  bool mIterating = false;
+  size_t mCursor = 0, mBlockStart = 0, mBlockEnd = 0, mBlockCounter = 0;
+
+ public:
+  Blocks(const Blocks&) = delete;
+  explicit Blocks(DeviceSequence& seq) : mSeq(seq) {
+    if (seq.size() <= 0) throw std::runtime_error("Input vector for breakpoint weights is empty!");
+  }
+  DeviceSequence& sequence() const { return mSeq; }
+
+  void createBlocks(real_t threshold) {
+    mThreshold = threshold;
+    mDirty = true;
+    mHostValid = false;
+  }
+  // threshold from the smallest emission variance, in real_t like BreakpointArray.hpp:195-199
+  template <typename ParamType>
+  void createBlocks(const Theta<ParamType>& param) {
+    createBlocks(std::sqrt(2 * std::log((real_t)mSeq.size()) * param.thresholdValue()));
+  }
+  real_t threshold() const { return mThreshold; }
+  bool dirty() const { return mDirty; }
+  // the samplers call this after a sweep that rebuilt the structure on the device
+  void markBuilt() { mDirty = false; }
+
+  // make the device structure match the current threshold (static mode, replay mode, host iteration)
+  size_t materialize() {
+    if (mDirty) {
+      uint64_t n = 0;
+      mSeq.check(hml_create_blocks(mSeq.handle(), (float)mThreshold, &n));
+      mDirty = false;
+      mHostValid = false;
+    }
+    uint64_t n = 0;
+    mSeq.check(hml_nr_blocks(mSeq.handle(), &n));
+    return n;
+  }
+  void fetch(bool stats) {
+    const size_t n = materialize();
+    if (mHostValid && (!stats || !mSum.empty())) return;
+    mStarts.resize(n);
+    if (stats) {
+      mSum.resize(n);
+      mSumSq.resize(n);
+      mSeq.check(hml_get_blocks(mSeq.handle(), mStarts.data(), mSum.data(), mSumSq.data(), n));
+    } else {
+      mSum.clear();
+      mSumSq.clear();
+      mSeq.check(hml_get_blocks(mSeq.handle(), mStarts.data(), nullptr, nullptr, n));
+    }
+    mHostValid = true;
+  }
+  const std::vector<uint32_t>& starts() const { return mStarts; }
+
+  void initForward() {
+    fetch(true);
+    mIterating = true;
+    mCursor = mBlockStart = mBlockEnd = mBlockCounter = 0;
+  }
+  bool next() {
+    if (mBlockEnd >= mSeq.size()) {
+      mIterating = false;
+      return false;
+    }
+    mCursor = mBlockCounter++;
+    mBlockStart = mStarts[mCursor];
+    mBlockEnd = mCursor + 1 < mStarts.size() ? mStarts[mCursor + 1] : mSeq.size();
+    return true;
+  }
+  size_t start() const { return mBlockStart; }
+  size_t end() const { return mBlockEnd; }
+  size_t blockSize() const { return mBlockEnd - mBlockStart; }
+  size_t size() const { return mSeq.size(); }
+  size_t pos() const {
+    if (mBlockCounter == 0) throw std::runtime_error("No blocks created yet, position is undefined!");
+    return mBlockCounter - 1;
+  }
+  size_t nrBlocks() const {
+    if (mIterating) throw std::runtime_error("Cannot determine size of block structure before all blocks have been seen!");
+    return mBlockCounter;
+  }
+  double currentSum() const { return mSum[mCursor]; }
+  double currentSumSq() const { return mSumSq[mCursor]; }
+};
+
+template <>
+class Statistics<IntegralArray, Normal> {
+  DeviceSequence& mSeq;
+  SufficientStatistics<Normal> mCurrent;
+
+ public:
+  Statistics(const Statistics&) = delete;
+  Statistics(DeviceSequence& seq, const size_t nrDim) : mSeq(seq) {
+    if (nrDim != 1) throw std::runtime_error("Multivariate data is not supported by the B200 path yet (d = 1 only)!");
+    if (seq.size() <= 0) throw std::runtime_error("Input vector for breakpoint weights is empty!");
+  }
+  // block sums come from the device's fp64 integral arrays, rounded once to real_t
+  template <typename B>
+  void setStats(const Blocks<B>& blocks) {
+    mCurrent = SufficientStatistics<Normal>((real_t)blocks.currentSum(), (real_t)blocks.currentSumSq());
+  }
+  const SufficientStatistics<Normal>& suffStat(size_t) const { return mCurrent; }
+  size_t nrDim() const { return 1; }
+  size_t size() const { return mSeq.size(); }
+};
+
+template <typename S, typename T, typename B>
+class Emissions<Statistics<S, T>, Blocks<B>> {
+  Statistics<S, T>& mStats;
+  Blocks<B>& mBlocks;
+
+ public:
+  Emissions(Statistics<S, T>& stats, Blocks<B>& blocks) : mStats(stats), mBlocks(blocks) {
+    if (mStats.size() != mBlocks.size())
+      throw std::runtime_error("Block structure and statistics have different number of data points!");
+  }
+  Statistics<S, T>& stats() { return mStats; }
+  Blocks<B>& blocks() { return mBlocks; }
+  const Blocks<B>& blocks() const { return mBlocks; }
+  void createBlocks(real_t thresh) { mBlocks.createBlocks(thresh); }
+  template <typename ParamType>
+  void createBlocks(const Theta<ParamType>& theta) { mBlocks.createBlocks(theta); }
+  size_t nrBlocks() const { return mBlocks.nrBlocks(); }
+  size_t nrDim() const { return mStats.nrDim(); }
+  size_t start() const { return mBlocks.start(); }
+  size_t end() const { return mBlocks.end(); }
+  size_t blockSize() const { return mBlocks.blockSize(); }
+  size_t size() const { return mBlocks.size(); }
+  void initForward() { mBlocks.initForward(); }
+  bool next() {
+    if (!mBlocks.next()) return false;
+    mStats.setStats(mBlocks);
+    return true;
+  }
+  const SufficientStatistics<T>& suffStat(size_t dim) const { return mStats.suffStat(dim); }
+};
+
+// ---------------------------------------------------------------------------------------- automatic priors
+
+// closed-form NIG hyper-parameters (reference: AutoPriors.hpp:18-80)
+inline std::vector<real_t> NormalInverseGammaAutoPrior(real_t s2, real_t p, real_t dataMean, real_t dataVar) {
+  if (p < 0 || p > 1) throw std::runtime_error("Parameter p for automatic priors is a probability and must be in [0,1]!");
+  if (s2 <= 0) throw std::runtime_error("Parameter s2  for automatic priors is a variance and must be positive!");
+  if (dataVar <= 0) throw std::runtime_error("Data variance provided to autoprior must be positive!");
+  const real_t M1 = 0.3361, M2 = -0.0042, M3 = -0.0201;
+  const real_t b = -std::log(p);
+  const real_t alpha = 2.0;
+  const real_t beta = s2 * ((2.0 * std::sqrt(b)) / (M1 * std::sqrt(b) + std::sqrt(2.0) * (M2 * b * std::exp(M3 * std::sqrt(b)) + 1)) + b);
+  const real_t mu0 = dataMean;
+  const real_t nu = beta / dataVar;
+  if (beta <= 0) throw std::runtime_error("Autoprior yields non-positive beta!");
+  if (nu <= 0) throw std::runtime_error("Autoprior yields non-positive nu!");
+  if (!std::isfinite(beta)) throw std::runtime_error("Autoprior yields non-finite beta!");
+  if (!std::isfinite(mu0)) throw std::runtime_error("Autoprior yields non-finite mu0!");
+  if (!std::isfinite(nu)) throw std::runtime_error("Autoprior yields non-finite nu!");
+  return std::vector<real_t>{alpha, beta, mu0, nu};
+}
+
+// one pass over the blocks at sqrt(2 log T) * sigma-hat; mean and variance of the block means
+// (reference: AutoPriors.hpp:86-110)
+template <typename Stats, typename BlocksT>
+std::vector<real_t> autoPrior(real_t s2, real_t p, Emissions<Statistics<Stats, Normal>, BlocksT>& y, const double noiseStdev) {
+  // (the reference calls initForward before createBlocks; there createBlocks only stores the threshold,
+  // so the order is immaterial — here initForward fetches the block list and must come second)
+  y.createBlocks(std::sqrt(2 * std::log((double)y.blocks().size())) * noiseStdev);
+  y.initForward();
+  SufficientStatistics<Normal> muStats;
+  while (y.next())
+    for (size_t dim = 0; dim < y.nrDim(); ++dim) muStats.addObs(y.suffStat(dim).sum() / y.blockSize());
+  const size_t N = y.nrBlocks() * y.nrDim();
+  const double blocksMean = sampleMean(muStats, N);
+  const double blocksVariance = sampleVariance(muStats, N);
+  return NormalInverseGammaAutoPrior(s2, p, blocksMean, blocksVariance);
+}

@@ -1,0 +1,210 @@
+// hammlet_b200 host side — output recording with the reference's file formats
+// (reference: src/Records.hpp, src/StateMarginals.hpp; formats in SURVEY.md App. C).
+//
+// StateMarginals keeps, like the reference, the common refinement of all recorded segmentations with
+// one count per state and segment.  The reference threads a run-length code through two deques; here
+// the refinement is rebuilt by a linear merge of the previous segment list with the incoming runs
+// (two flat arrays that swap roles per recorded iteration).  Observable behaviour is the same: the
+// saved lines, nrSegments() and internalSize() (the length the reference's code would have).
+#pragma once
+
+#include "Model.hpp"
+
+class StateMarginals {
+  struct SegList {
+    std::vector<size_t> size;
+    std::vector<marginal_t> count;  // row-major, stride columns per segment
+    void clear() {
+      size.clear();
+      count.clear();
+    }
+  };
+  const size_t mSize;
+  size_t mStride;
+  SegList mCur, mNext;
+  size_t mFront = 0;           // first unconsumed segment of mCur
+  size_t mFrontRemaining = 0;  // observations left in it
+  size_t mNrIterations = 0;
+  size_t mNrStates = 0;        // highest recorded label + 1
+  size_t mNrSegments = 1;
+
+  // length of the reference's code for one segment: a negative count per non-zero state, a positive
+  // "next state" marker whenever states are skipped, and the terminating zero (StateMarginals.hpp:51-137)
+  size_t codeLength(const marginal_t* row) const {
+    size_t len = 1, expected = 0;
+    for (size_t s = 0; s < mStride; ++s)
+      if (row[s] != 0) {
+        len += (s != expected) ? 2 : 1;
+        expected = s + 1;
+      }
+    return len;
+  }
+  void widen(size_t columns) {
+    for (SegList* l : {&mCur, &mNext}) {
+      std::vector<marginal_t> wide(l->size.size() * columns, 0);
+      for (size_t i = 0; i < l->size.size(); ++i)
+        std::copy(l->count.begin() + i * mStride, l->count.begin() + (i + 1) * mStride, wide.begin() + i * columns);
+      l->count.swap(wide);
+    }
+    mStride = columns;
+  }
+
+ public:
+  StateMarginals(const StateMarginals&) = delete;
+  explicit StateMarginals(size_t size, size_t nrStates = 2) : mSize(size), mStride(std::max<size_t>(nrStates, 1)) {
+    mCur.size.push_back(size);
+    mCur.count.assign(mStride, 0);
+    mFrontRemaining = size;
+  }
+  size_t size() const { return mSize; }
+
+  // `blockSize` further observations of the iteration being recorded are in `state`
+  void addRecord(const marginal_t state, size_t blockSize, const marginal_t count = 1) {
+    if ((size_t)state >= mNrStates) mNrStates = state + 1;
+    if ((size_t)state >= mStride) widen(state + 1);
+    while (blockSize > 0) {
+      if (mFront >= mCur.size.size()) throw std::runtime_error("Empty count queue, this is a bug!");
+      const size_t take = std::min(blockSize, mFrontRemaining);
+      mNext.size.push_back(take);
+      mNext.count.insert(mNext.count.end(), mCur.count.begin() + mFront * mStride, mCur.count.begin() + (mFront + 1) * mStride);
+      mNext.count[mNext.count.size() - mStride + state] += count;
+      if (blockSize < mFrontRemaining) {  // the run ends inside the front segment: it is split
+        mFrontRemaining -= blockSize;
+        mNrSegments++;
+        break;
+      }
+      blockSize -= mFrontRemaining;
+      mFront++;
+      mFrontRemaining = mFront < mCur.size.size() ? mCur.size[mFront] : 0;
+    }
+    if (mFront >= mCur.size.size()) {  // the iteration covered all positions
+      std::swap(mCur, mNext);
+      mNext.clear();
+      mFront = 0;
+      mFrontRemaining = mCur.size[0];
+      mNrIterations++;
+    }
+  }
+
+  size_t nrSegments() const { return mNrSegments; }
+  size_t internalSize() const {
+    size_t n = 0;
+    for (size_t i = mFront; i < mCur.size.size(); ++i) n += codeLength(&mCur.count[i * mStride]);
+    for (size_t i = 0; i < mNext.size.size(); ++i) n += codeLength(&mNext.count[i * mStride]);
+    return n;
+  }
+
+  // one line per segment: size TAB count_0 TAB ... count_{S-1}, S = highest recorded label + 1
+  void save(std::ofstream& ofs, size_t chunkSize = 1) const {
+    if (chunkSize <= 0) throw std::runtime_error("Chunk size must be at least one!");
+    if (mFront != 0 || !mNext.size.empty())
+      throw std::runtime_error("Cannot output incomplete marginals, currently processing block " + std::to_string(mFront) + "!");
+    for (size_t i = 0; i < mCur.size.size(); ++i) {
+      size_t iterations = 0;
+      ofs << mCur.size[i];
+      for (size_t s = 0; s < mNrStates; ++s) {
+        const marginal_t c = mCur.count[i * mStride + s];
+        ofs << "\t" << c;
+        iterations += c;
+      }
+      ofs << std::endl;
+      if (iterations != mNrIterations)
+        throw std::runtime_error("Sum of marginals (" + std::to_string(iterations) + ") does not match the number of iterations (" +
+                                 std::to_string(mNrIterations) + ")!");
+    }
+  }
+};
+
+class Records {
+  size_t mNrObservedPos = 0, mNrBlocks = 0, mNrSegments = 0;
+  size_t mSegmentState = 0, mSegmentSize = 0;
+  const size_t mSize;
+  std::string mPrefix, mSuffix;
+  StateMarginals mMarginals;
+  bool mRecordMarginals = true, mRecordBlocks = false, mRecordCompression = false, mRecordSequences = false,
+       mRecordTheta = false, mRecordSegments = false;
+  std::ofstream mMarginalsFile, mSequenceFile, mBlocksFile, mThetaFile, mCompressionsFile, mSegmentFile;
+  bool mClosed = false;
+
+  void setRecordX(std::ofstream& file, const std::string& type, bool& member, const bool flag, const bool overwrite) {
+    member = flag;
+    if (member && !file.is_open()) {
+      const std::string filename = mPrefix + type + mSuffix;
+      if (hammlet::fileExists(filename) && !overwrite)
+        throw std::runtime_error("File " + filename + " already exists! Use -w to allow overwrite!");
+      file.open(filename.c_str());
+      if (!file.is_open()) throw std::runtime_error("Cannot write to file " + filename + "!");
+    }
+  }
+
+ public:
+  Records(const Records&) = delete;
+  Records(size_t T, std::string prefix, std::string suffix, const size_t nrStates)
+      : mSize(T), mPrefix(prefix), mSuffix(suffix), mMarginals(T, nrStates) {}
+  ~Records() {
+    try {
+      close();
+    } catch (...) {
+    }
+  }
+  void close() {
+    if (mClosed) return;
+    mClosed = true;
+    if (mRecordMarginals) {
+      mMarginals.save(mMarginalsFile);
+      mMarginalsFile.close();
+    }
+    if (mRecordSequences) mSequenceFile.close();
+    if (mRecordBlocks) mBlocksFile.close();
+    if (mRecordTheta) mThetaFile.close();
+    if (mRecordCompression) mCompressionsFile.close();
+    if (mRecordSegments) mSegmentFile.close();
+  }
+  void setRecordMarginals(bool b, bool overwrite = false) { setRecordX(mMarginalsFile, "marginals", mRecordMarginals, b, overwrite); }
+  void setRecordBlocks(bool b, bool overwrite = false) { setRecordX(mBlocksFile, "blocks", mRecordBlocks, b, overwrite); }
+  void setRecordCompression(bool b, bool overwrite = false) { setRecordX(mCompressionsFile, "compression", mRecordCompression, b, overwrite); }
+  void setRecordStateSequence(bool b, bool overwrite = false) { setRecordX(mSequenceFile, "sequences", mRecordSequences, b, overwrite); }
+  void setRecordTheta(bool b, bool overwrite = false) { setRecordX(mThetaFile, "parameters", mRecordTheta, b, overwrite); }
+  void setRecordSegments(bool b, bool overwrite = false) { setRecordX(mSegmentFile, "segments", mRecordSegments, b, overwrite); }
+  bool wantsBlocks() const { return mRecordBlocks; }
+
+  template <typename ThetaType>
+  void record(const Theta<ThetaType>& theta) {
+    if (mRecordTheta) mThetaFile << theta << std::endl;
+  }
+
+  // one block of the iteration being recorded: N observations in `state` (Records.hpp:155-235).
+  // Equal-state neighbours merge into segments; a finished segment goes to the marginals and, as
+  // "size:state", to the sequences file; the line ends when all T positions have been seen.
+  void record(const size_t state, const size_t N) {
+    const bool firstBlock = mNrBlocks == 0;
+    if (firstBlock) {
+      mSegmentState = state;
+      mSegmentSize = N;
+    } else if (state != mSegmentState) {
+      flushSegment(false);
+      mSegmentState = state;
+      mSegmentSize = N;
+      mNrSegments++;
+    } else {
+      mSegmentSize += N;
+    }
+    mNrBlocks++;
+    mNrObservedPos += N;
+    const bool lineEnd = mNrObservedPos >= mSize;
+    if (lineEnd) {
+      if (mNrObservedPos > mSize) throw std::runtime_error("Cannot record block, exceeding data size!");
+      if (mRecordCompression) mCompressionsFile << ((double)mSize) / ((double)mNrBlocks) << std::endl;
+      if (mRecordSegments) mSegmentFile << mMarginals.nrSegments() << "\t" << mMarginals.internalSize() << std::endl;
+      flushSegment(true);
+      mNrObservedPos = mNrBlocks = mSegmentSize = mNrSegments = 0;
+    }
+    if (mRecordBlocks) mBlocksFile << (firstBlock ? "" : "\t") << N << (lineEnd ? "\n" : "");
+  }
+
+ private:
+  void flushSegment(bool lineEnd) {
+    if (mRecordMarginals) mMarginals.addRecord(mSegmentState, mSegmentSize);
+    if (mRecordSequences) mSequenceFile << (mNrSegments > 0 ? "\t" : "") << mSegmentSize << ":" << mSegmentState << (lineEnd ? "\n" : "");
+  }
+};

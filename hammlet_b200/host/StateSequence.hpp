@@ -1,0 +1,205 @@
+// hammlet_b200 host side — state-sequence samplers and the Gibbs driver.
+//
+// Same surface as the reference's StateSequence<ForwardBackward> / StateSequence<Mixture>
+// (src/StateSequence.hpp, src/StateSequence/ForwardBackward.hpp, src/StateSequence/Mixture.hpp),
+// Trellis (src/Trellis.hpp) and sampleHMM (src/HMM.hpp:60-125).  sample() has the reference's
+// signature and side effects — it updates tau_theta, tau_A, tau_pi and feeds Records — but the
+// forward filter, backward sampling and the statistics pass run on the device in one
+// hml_fb_sweep / hml_mix_sweep call; only the O(K^2) conjugate updates happen here.
+//
+// Randomness.  Default: every sweep draws one 64-bit key from the shared mt19937 and the device
+// derives its per-block uniforms from it with Philox (counter-based).  Replay mode
+// (setReplay(true)): the per-block 53-bit uniforms themselves are drawn from the shared mt19937
+// with std::generate_canonical, in the order the reference consumes them, so a run is
+// draw-for-draw comparable with the reference built with the same real_t.
+#pragma once
+
+#include "Emissions.hpp"
+#include "Records.hpp"
+
+// The trellis lives on the device; this class keeps the reference's name for the forward rows and
+// gives read access to them for diagnostics (rows as the backward pass sees them).
+class Trellis {
+  std::vector<double> mRows;
+  size_t mNrStates = 2;
+
+ public:
+  Trellis(const Trellis&) = delete;
+  Trellis() {}
+  void setNrStates(size_t K) { mNrStates = K; }
+  size_t size() const { return mNrStates ? mRows.size() / mNrStates : 0; }
+  double operator()(size_t t, size_t d) const {
+    if (d >= mNrStates) throw std::runtime_error("Trellis dimension index out of bounds!");
+    return mRows.at(t * mNrStates + d);
+  }
+  void clear() { mRows.clear(); }
+  void fetch(DeviceSequence& seq, size_t nrBlocks) {
+    mRows.resize((nrBlocks + 1) * mNrStates);
+    seq.check(hml_get_rows(seq.handle(), mRows.data(), nrBlocks + 1));
+  }
+};
+
+template <typename Type>
+class StateSequence {
+  std::vector<marginal_t> mStates;
+  rng_t& mRNG;
+  Trellis mTrellis;
+  bool mReplay = false;
+  bool mKeepTrellis = false;
+  double mLogLikelihood = NAN;
+
+  template <typename ThetaType, typename TransitionsType, typename InitialType>
+  static void fillModel(const ThetaType& theta, const TransitionsType& A, const InitialType& pi, const Mapping& mapping,
+                        bool useSelf, std::vector<double>& mean, std::vector<double>& var, std::vector<double>& a,
+                        std::vector<double>& p, hml_model& m) {
+    const size_t K = A.nrStates();
+    if (mapping.nrDataDims() != 1) throw std::runtime_error("Multivariate data is not supported by the B200 path yet (d = 1 only)!");
+    mean.resize(K);
+    var.resize(K);
+    a.resize(K * K);
+    p = std::vector<double>(K);
+    const std::vector<real_t> pv = pi.valueVector();
+    for (size_t s = 0; s < K; ++s) {
+      const auto& param = theta.value()[mapping[s][0]];
+      mean[s] = param.mean();
+      var[s] = param.var();
+      p[s] = pv[s];
+      for (size_t j = 0; j < K; ++j) a[s * K + j] = A(s, j);
+    }
+    m.K = (int32_t)K;
+    m.use_self_transitions = useSelf ? 1 : 0;
+    m.mean = mean.data();
+    m.var = var.data();
+    m.A = a.data();
+    m.pi = p.data();
+  }
+
+ public:
+  StateSequence(const StateSequence&) = delete;
+  StateSequence(rng_t& RNG) : mRNG(RNG) {}
+
+  void setReplay(bool on) { mReplay = on; }
+  void setKeepTrellis(bool on) { mKeepTrellis = on; }
+  const Trellis& trellis() const { return mTrellis; }
+  double logLikelihood() const { return mLogLikelihood; }
+
+  template <typename StatsStructure, typename StatsType, typename BlocksType, typename ThetaType, typename TauThetaType,
+            typename TransitionsType, typename TauAType, typename InitialType, typename TauPiType>
+  void sample(Emissions<Statistics<StatsStructure, StatsType>, Blocks<BlocksType>>& y, const ThetaType& theta,
+              TauThetaType& tau_theta, const TransitionsType& A, TauAType& tau_A, const InitialType& pi, TauPiType& tau_pi,
+              const Mapping& mapping, Records& records, const bool doRecord, const bool useSelfTransitions);
+
+  size_t size() const { return mStates.size(); }
+  const std::vector<marginal_t>& states() const { return mStates; }
+  const marginal_t& operator[](const size_t s) const {
+    if (s >= mStates.size()) throw std::runtime_error("State sequence index " + std::to_string(s) + " out of bounds!");
+    return mStates[s];
+  }
+  void clear() {
+    std::vector<marginal_t>().swap(mStates);
+    mTrellis.clear();
+  }
+
+ private:
+  static constexpr bool kIsMixture = std::is_same<Type, Mixture>::value;
+};
+
+template <typename Type>
+template <typename StatsStructure, typename StatsType, typename BlocksType, typename ThetaType, typename TauThetaType,
+          typename TransitionsType, typename TauAType, typename InitialType, typename TauPiType>
+void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>, Blocks<BlocksType>>& y,
+                                 const ThetaType& theta, TauThetaType& tau_theta, const TransitionsType& A, TauAType& tau_A,
+                                 const InitialType& pi, TauPiType& tau_pi, const Mapping& mapping, Records& records,
+                                 const bool doRecord, const bool useSelfTransitions) {
+  const size_t nrStates = A.nrStates();
+  const size_t nrParams = tau_theta.nrParams();
+  auto& blocks = y.blocks();
+  DeviceSequence& seq = blocks.sequence();
+
+  std::vector<double> mean, var, a, p;
+  hml_model model;
+  fillModel(theta, A, pi, mapping, useSelfTransitions, mean, var, a, p, model);
+
+  std::vector<double> statSum(nrStates), statSq(nrStates);
+  std::vector<uint64_t> statN(nrStates), trans(nrStates * nrStates), counts(nrStates);
+  hml_sweep_out out;
+  out.stat_sum = statSum.data();
+  out.stat_sumsq = statSq.data();
+  out.stat_n = statN.data();
+  out.trans = trans.data();
+  out.counts = counts.data();
+
+  uint32_t flags = mKeepTrellis && !kIsMixture ? (HML_SWEEP_KEEP_ROWS | HML_SWEEP_LOGLIK) : 0;
+  std::vector<double> uniforms;
+  uint64_t key = 0;
+  if (mReplay) {
+    // one 53-bit uniform per block from the shared stream, as Trellis::sample / discrete_distribution draw them
+    const size_t nb = blocks.materialize();
+    uniforms.resize(nb);
+    for (size_t b = 0; b < nb; ++b) uniforms[b] = std::generate_canonical<double, 53>(mRNG);
+  } else {
+    key = ((uint64_t)mRNG() << 32) | (uint64_t)mRNG();
+    if (blocks.dirty()) flags |= HML_SWEEP_DYNAMIC;
+  }
+  auto fn = kIsMixture ? hml_mix_sweep : hml_fb_sweep;
+  seq.check(fn(seq.handle(), &model, flags, (float)blocks.threshold(), key, 0, mReplay ? uniforms.data() : nullptr,
+               uniforms.size(), &out));
+  blocks.markBuilt();
+  for (uint64_t i = 0; i < out.uniform_fallbacks; ++i) std::cout << "[WARNING] Uniform sampling of forward variables!" << std::endl;
+  mLogLikelihood = out.loglik;
+  if (mKeepTrellis && !kIsMixture) {
+    mTrellis.setNrStates(nrStates);
+    mTrellis.fetch(seq, out.nblocks);
+  }
+
+  // ---- posterior updates (ForwardBackward.hpp:203-211, Mixture.hpp:131-139); univariate: parameter == state
+  for (size_t prm = 0; prm < nrParams; ++prm) {
+    if (statN[prm] > 0) {
+      const SufficientStatistics<StatsType> s((real_t)statSum[prm], (real_t)statSq[prm]);
+      tau_theta.addObservation(s, statN[prm], prm);
+    }
+  }
+  SufficientStatistics<CategoricalVector> transitions(nrStates);
+  SufficientStatistics<Categorical> stateCounts(nrStates);
+  for (size_t i = 0; i < nrStates; ++i) {
+    stateCounts[i] = counts[i];
+    for (size_t j = 0; j < nrStates; ++j) transitions[i][j] = trans[i * nrStates + j];
+  }
+  tau_A.addObservation(transitions);
+  tau_pi.addObservation(stateCounts);
+
+  // ---- records (ForwardBackward.hpp:193-195): block by block, in order
+  if (doRecord || (!kIsMixture && mKeepTrellis)) {
+    mStates.resize(out.nblocks);
+    seq.check(hml_get_states(seq.handle(), mStates.data(), mStates.size()));
+  }
+  if (doRecord) {
+    blocks.fetch(false);
+    const std::vector<uint32_t>& st = blocks.starts();
+    const size_t T = y.size();
+    for (size_t b = 0; b < st.size(); ++b) {
+      const size_t N = (b + 1 < st.size() ? st[b + 1] : T) - st[b];
+      records.record((size_t)mStates[b], N);
+    }
+  }
+}
+
+// The Gibbs driver, reference: HMM.hpp:60-125.
+template <typename StateSequenceType, typename EmissionsType, typename ThetaType, typename ThetaParamType,
+          typename TransitionType, typename TransitionParamType, typename InitialType, typename InitialParamType>
+void sampleHMM(EmissionsType& y, StateSequenceType& q, ThetaType& theta, ThetaParamType& tau_theta, TransitionType& A,
+               TransitionParamType& tau_A, InitialType& pi, InitialParamType& tau_pi, const Mapping& mapping,
+               const size_t iterations, const size_t thinning, Records& records, const bool dynamic = true,
+               const bool useSelfTransitions = true) {
+  if (thinning > iterations)
+    std::cout << "[WARNING] Thinning parameter is larger than number of iterations. No data will be recorded!" << std::endl;
+  for (size_t i = 0; i < iterations; ++i) {
+    if (dynamic) y.createBlocks(theta);
+    const bool doRecord = thinning > 0 && ((i + 1) % thinning == 0);
+    q.sample(y, theta, tau_theta, A, tau_A, pi, tau_pi, mapping, records, doRecord, useSelfTransitions);
+    theta.sample(tau_theta);
+    pi.sample(tau_pi);
+    A.sample(tau_A);
+    if (doRecord) records.record(theta);
+  }
+}
