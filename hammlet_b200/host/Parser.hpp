@@ -5,6 +5,7 @@
 #pragma once
 
 #include <initializer_list>
+#include <iostream>
 #include <map>
 #include <set>
 #include <sstream>
