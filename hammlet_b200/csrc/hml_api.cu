@@ -50,7 +50,7 @@ struct hml_ctx {
   // per-sweep buffers (sized by capacity and KP)
   int KP = 0;
   int last_K = 0;
-  double *e = nullptr, *sp = nullptr, *maxE = nullptr;
+  double *e = nullptr, *sp = nullptr, *maxE = nullptr, *alpha = nullptr;
   uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *tile_maps = nullptr, *tile_qin = nullptr;
   double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr;
   int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr;
@@ -147,6 +147,7 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
   if (KP && (cap != h->capacity || KP != h->KP)) {
     CK(dev_alloc(h->e, cap * KP));
     CK(dev_alloc(h->sp, cap * KP));
+    CK(dev_alloc(h->alpha, cap * KP));
     CK(dev_alloc(h->maxE, cap));
     CK(dev_alloc(h->maps, cap * MB));
     CK(dev_alloc(h->chunk_maps, chunks * MB));
@@ -179,6 +180,7 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.e = h->e;
   b.sp = h->sp;
   b.maxE = h->maxE;
+  b.alpha = h->alpha;
   b.maps = h->maps;
   b.states = h->states;
   b.chunk_ops = h->chunk_ops;
@@ -530,6 +532,7 @@ int hml_destroy(hml_t* h) {
   dev_free(h->e);
   dev_free(h->sp);
   dev_free(h->maxE);
+  dev_free(h->alpha);
   dev_free(h->maps);
   dev_free(h->states);
   dev_free(h->chunk_maps);

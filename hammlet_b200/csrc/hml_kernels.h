@@ -43,6 +43,7 @@ struct SweepBuffers {
   double* e;                // KP per block: exp(E_s - maxE)
   double* sp;               // KP per block: exp((N-1) log A_ss)   (self-transition rescale, FB.hpp:115-119)
   double* maxE;             // per block (only filled for loglik)
+  double* alpha;            // KP per block: normalised forward vector alpha_t
   uint8_t* maps;            // KPB bytes per block: backward map j -> state
   uint8_t* states;          // sampled state per block
   double* chunk_ops;        // per chunk KP*KP

@@ -154,6 +154,39 @@ __device__ __forceinline__ bool warp_apply_op(double& a, const LaneOp<KP>& o) {
   return true;
 }
 
+// Thread-local a <- normalise(a * Op) for small K (operator held in registers).  Returns false if the
+// product vanished.
+template <int KP, typename OpT>
+__device__ __forceinline__ bool vec_apply_op(double (&a)[KP], const OpT& o) {
+  int xm = kDeadExp;
+#pragma unroll
+  for (int k = 0; k < KP; ++k)
+    if (a[k] > 0.0 && o.x[k] > xm) xm = o.x[k];
+  double y[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) y[j] = 0.0;
+  if (xm != kDeadExp) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const double ak = a[k] * pow2i(o.x[k] - xm);
+#pragma unroll
+      for (int j = 0; j < KP; ++j) y[j] = fma(ak, o.m[k * KP + j], y[j]);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) s += y[j];
+  if (!(s > 0.0)) {
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = 0.0;
+    return false;
+  }
+  const double inv = 1.0 / s;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) a[j] = y[j] * inv;
+  return true;
+}
+
 // Thread-local operator copy (small K only) for prefetching ahead of a dependent row recursion.
 template <int KP>
 struct OpVals {
@@ -335,11 +368,18 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers
 #pragma unroll
         for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
         const double* ep = buf.e + Layout::at(tile, c, 0) * KP;
-#pragma unroll 2
+        double en[KP];  // emission terms of the next step, loaded one step ahead of their use
+#pragma unroll
+        for (int j = 0; j < KP; ++j) en[j] = steps > 0 ? ep[j] : 0.0;
+#pragma unroll 1
         for (int t = 0; t < steps; ++t) {
           double ev[KP];
 #pragma unroll
-          for (int j = 0; j < KP; ++j) ev[j] = ep[(uint64_t)t * C * KP + j];
+          for (int j = 0; j < KP; ++j) ev[j] = en[j];
+          if (t + 1 < steps) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) en[j] = ep[(uint64_t)(t + 1) * C * KP + j];
+          }
           double y[KP];
 #pragma unroll
           for (int j = 0; j < KP; ++j) y[j] = 0.0;
@@ -365,19 +405,39 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers
     }
     __threadfence_block();
     __syncthreads();
-    // tile operator = product of the 32 chunk operators, one thread per row
-    if (threadIdx.x < KP) {
+    // tile operator = ordered product of the 32 chunk operators
+    if (FwdCfg<KP>::SMEM_OPS) {
+      // pairwise tree in shared memory: thread (pair, row) replaces row `row` of the left operator by
+      // its product with the right operator; 5 levels
+      for (int stride = 1; stride < C; stride <<= 1) {
+        const int pairs = C / (2 * stride);
+        const int pr = threadIdx.x / KP, row = threadIdx.x % KP;
+        if (pr < pairs) {
+          const int a = pr * 2 * stride, b = a + stride;
+          double r[KP];
+#pragma unroll
+          for (int j = 0; j < KP; ++j) r[j] = s_ops[(a * KP + row) * KP + j];
+          int rex = s_exp[a * KP + row];
+          row_times_op<KP, false>(r, rex, s_ops + b * KP * KP, s_exp + b * KP);
+#pragma unroll
+          for (int j = 0; j < KP; ++j) s_ops[(a * KP + row) * KP + j] = r[j];
+          s_exp[a * KP + row] = rex;
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x < KP) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.tile_ops[(tile * KP + threadIdx.x) * KP + j] = s_ops[threadIdx.x * KP + j];
+        buf.tile_exp[tile * KP + threadIdx.x] = s_exp[threadIdx.x];
+      }
+    } else if (threadIdx.x < KP) {
       double r[KP];
       int rex = 0;
 #pragma unroll
       for (int j = 0; j < KP; ++j) r[j] = (j == (int)threadIdx.x) ? 1.0 : 0.0;
 #pragma unroll 1
-      for (int c = 0; c < C; ++c) {
-        if (FwdCfg<KP>::SMEM_OPS)
-          row_times_op<KP, false>(r, rex, s_ops + c * KP * KP, s_exp + c * KP);
-        else
-          row_times_op<KP, true>(r, rex, buf.chunk_ops + (tile * C + c) * KP * KP, buf.chunk_exp + (tile * C + c) * KP);
-      }
+      for (int c = 0; c < C; ++c)
+        row_times_op<KP, true>(r, rex, buf.chunk_ops + (tile * C + c) * KP * KP, buf.chunk_exp + (tile * C + c) * KP);
 #pragma unroll
       for (int j = 0; j < KP; ++j) buf.tile_ops[(tile * KP + threadIdx.x) * KP + j] = r[j];
       buf.tile_exp[tile * KP + threadIdx.x] = rex;
@@ -395,9 +455,86 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers
 
 template <int KP>
 struct ScanCfg {
-  static constexpr int GMAX = (KP <= 8) ? 64 : 32;
-  static constexpr bool SMEM = KP <= 8;
+  static constexpr int GMAX = 32;
+  static constexpr bool SMEM = false;
 };
+
+// Small K (<= 8): 256 threads, every vector and operator in registers, operators prefetched one step
+// ahead of the dependent chain.  G groups of S consecutive tiles, G ~ sqrt(#tiles):
+//   step 1  thread (group, row): group operator = product of its S tile operators   -> shared memory
+//   step 2  thread 0: forward vector entering each group (G sequential operator applications)
+//   step 3  thread per group: forward vector entering each of its tiles
+template <int KP>
+__global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, ModelDev<KP> m) {
+  constexpr int GMAX = 256 / KP < 48 ? 256 / KP : 48;
+  __shared__ double s_gain[GMAX][KP];
+  __shared__ double s_gop[GMAX * KP * KP];
+  __shared__ int s_gexp[GMAX * KP];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
+  if (nt == 0) return;
+  int G = (int)ceil(sqrt((double)nt));
+  if (G > GMAX) G = GMAX;
+  const int S = (nt + G - 1) / G;
+  G = (nt + S - 1) / S;
+  {
+    const int g = threadIdx.x / KP, i = threadIdx.x % KP;
+    if (g < G) {
+      double r[KP];
+      int rex = 0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+      const int t0 = g * S, t1 = min(nt, (g + 1) * S);
+      OpVals<KP> cur, nxt;
+      load_op<KP>(cur, buf.tile_ops + (uint64_t)t0 * KP * KP, buf.tile_exp + (uint64_t)t0 * KP);
+#pragma unroll 1
+      for (int t = t0; t < t1; ++t) {
+        const int tn = (t + 1 < t1) ? t + 1 : t;
+        load_op<KP>(nxt, buf.tile_ops + (uint64_t)tn * KP * KP, buf.tile_exp + (uint64_t)tn * KP);
+        row_times_op<KP, false>(r, rex, cur.m, cur.x);
+        cur = nxt;
+      }
+#pragma unroll
+      for (int j = 0; j < KP; ++j) s_gop[(g * KP + i) * KP + j] = r[j];
+      s_gexp[g * KP + i] = rex;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = m.pi[j];  // row 0 of the trellis is pi itself (FB.hpp:57)
+#pragma unroll 1
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) s_gain[g][j] = a[j];
+      if (g + 1 < G) {
+        OpVals<KP> o;
+        load_op<KP>(o, s_gop + g * KP * KP, s_gexp + g * KP);
+        if (!vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    double a[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = s_gain[g][j];
+    const int t0 = g * S, t1 = min(nt, (g + 1) * S);
+    OpVals<KP> cur, nxt;
+    load_op<KP>(cur, buf.tile_ops + (uint64_t)t0 * KP * KP, buf.tile_exp + (uint64_t)t0 * KP);
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) buf.tile_ain[(uint64_t)t * KP + j] = a[j];
+      const int tn = (t + 1 < t1) ? t + 1 : t;
+      load_op<KP>(nxt, buf.tile_ops + (uint64_t)tn * KP * KP, buf.tile_exp + (uint64_t)tn * KP);
+      if (t + 1 < t1 && !vec_apply_op<KP>(a, cur)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      cur = nxt;
+    }
+  }
+}
 
 template <int KP>
 __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDev<KP> m) {
@@ -480,10 +617,11 @@ __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDe
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_fwd_replay: one warp per tile; lane c owns chunk c.
+// k_fwd_replay: one warp per tile; lane c owns chunk c.  Only the inherently sequential part of the
+// filter runs here: alpha_t = normalise(e_t o (alpha_{t-1} A)), written per block (interleaved order).
 
-template <int KP, bool kLoglik, bool kRows>
-__global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+template <int KP, bool kLoglik>
+__global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m) {
   constexpr int L = Layout::L, C = Layout::C;
   __shared__ double s_ain[C][KP + 1];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
@@ -519,14 +657,23 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
     double a[KP];
 #pragma unroll
     for (int j = 0; j < KP; ++j) a[j] = s_ain[c][j];
-    if (kRows && first == 0 && steps > 0) {
-      for (int j = 0; j < K; ++j) buf.rows[j] = m.pi[j];
-    }
-    Map<KP> G = Map<KP>::identity();
+    const double* ep = buf.e + Layout::at(tile, c, 0) * KP;
+    double en[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) en[j] = steps > 0 ? ep[j] : 0.0;
+    double mxn = (kLoglik && steps > 0) ? buf.maxE[Layout::at(tile, c, 0)] : 0.0;
 #pragma unroll 1
     for (int t = 0; t < steps; ++t) {
       const uint64_t p = Layout::at(tile, c, t);
-      const uint64_t b = first + t;
+      double ev[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) ev[j] = en[j];
+      const double mx = mxn;
+      if (t + 1 < steps) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) en[j] = ep[(uint64_t)(t + 1) * C * KP + j];
+        if (kLoglik) mxn = buf.maxE[p + C];
+      }
       double f[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) f[j] = 0.0;
@@ -538,64 +685,21 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
       double fs = 0.0;
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        f[j] *= buf.e[p * KP + j];
+        f[j] *= ev[j];
         fs += f[j];
       }
       if (fs != 0.0) {  // FB.hpp:101-105
         const double inv = 1.0 / fs;
 #pragma unroll
         for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
-        if (kLoglik) ll += buf.maxE[p] + log(fs);
+        if (kLoglik) ll += mx + log(fs);
       } else {          // FB.hpp:106-111: uniform fallback (the host then re-runs the sweep sequentially)
         fallbacks++;
 #pragma unroll
         for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
       }
-      // weights the backward pass will see: alpha'_t = alpha_t * A_ss^(N_t - 1) except for the last block
-      const bool last = (b + 1 == B);
-      double ap[KP];
 #pragma unroll
-      for (int j = 0; j < KP; ++j) ap[j] = (last || !m.use_self) ? a[j] : a[j] * buf.sp[p * KP + j];
-      if (kRows) {
-        for (int j = 0; j < K; ++j) buf.rows[(b + 1) * K + j] = ap[j];
-      }
-      const double u = buf.replay_u ? buf.replay_u[B - 1 - b] : Philox::uniform(seed, sweep, 0u, b);
-      Map<KP> fm = Map<KP>::zero();
-      if (last) {  // q_B ~ alpha_B (FB.hpp:138): constant map
-        const uint32_t q = discrete_draw<KP>(ap, K, u);
-#pragma unroll
-        for (int j = 0; j < KP; ++j) fm.set(j, q);
-      } else {
-#pragma unroll
-        for (int j = 0; j < KP; ++j) {
-          if (j < K) {
-            double w[KP];
-#pragma unroll
-            for (int k = 0; k < KP; ++k) w[k] = ap[k] * m.A[k][j];  // FB.hpp:145-146
-            fm.set(j, discrete_draw<KP>(w, K, u));
-          }
-        }
-      }
-      fm.store(buf.maps + p * (8 * Map<KP>::W));
-      G = G.after(fm);
-    }
-    // ---- maps: X_c = G_{c+1} o ... o G_31 (state after chunk c given the state after the tile) and
-    //      the tile map G_0 o ... o G_31, by a suffix scan over the warp
-    {
-      Map<KP> inc = G;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        Map<KP> other;
-#pragma unroll
-        for (int i = 0; i < Map<KP>::W; ++i) other.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], o);
-        if (lane + o < 32) inc = inc.after(other);
-      }
-      Map<KP> excl;
-#pragma unroll
-      for (int i = 0; i < Map<KP>::W; ++i) excl.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
-      if (lane == 31) excl = Map<KP>::identity();
-      excl.store(buf.chunk_maps + (tile * C + c) * (8 * Map<KP>::W));
-      if (lane == 0) inc.store(buf.tile_maps + tile * (8 * Map<KP>::W));
+      for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
     }
     __syncwarp();
   }
@@ -609,25 +713,19 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
   if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[KP + KP * KP], (unsigned long long)fallbacks);
 }
 
-// Sequential forward replay (one thread): the exact reference recursion, used only when the
+// Sequential forward recursion (one thread): the exact reference recursion, used only when the
 // parallel pass reported a uniform fallback, whose effect on later blocks the operator products
-// cannot express.  Emits the same maps / chunk maps as k_fwd_replay.
-template <int KP, bool kLoglik, bool kRows>
-__global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+// cannot express.
+template <int KP, bool kLoglik>
+__global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDev<KP> m) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  constexpr int L = Layout::L;
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int K = m.K;
   double a[KP];
 #pragma unroll
   for (int j = 0; j < KP; ++j) a[j] = m.pi[j];
-  if (kRows)
-    for (int j = 0; j < K; ++j) buf.rows[j] = m.pi[j];
   double ll = 0.0;
   unsigned long long fallbacks = 0;
-  Map<KP> G = Map<KP>::identity();
-  Map<KP> gc[Layout::C];
-  for (int c = 0; c < Layout::C; ++c) gc[c] = Map<KP>::identity();
   for (uint64_t b = 0; b < B; ++b) {
     const uint64_t p = Layout::perm(b);
     double f[KP];
@@ -654,48 +752,89 @@ __global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDe
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
     }
-    const bool last = (b + 1 == B);
-    double ap[KP];
 #pragma unroll
-    for (int j = 0; j < KP; ++j) ap[j] = (last || !m.use_self) ? a[j] : a[j] * buf.sp[p * KP + j];
-    if (kRows)
-      for (int j = 0; j < K; ++j) buf.rows[(b + 1) * K + j] = ap[j];
-    const double u = buf.replay_u ? buf.replay_u[B - 1 - b] : Philox::uniform(seed, sweep, 0u, b);
-    Map<KP> fm = Map<KP>::zero();
-    if (last) {
-      const uint32_t q = discrete_draw<KP>(ap, K, u);
-#pragma unroll
-      for (int j = 0; j < KP; ++j) fm.set(j, q);
-    } else {
+    for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
+  }
+  if (kLoglik) buf.partials[0] = ll;
+  buf.out_u64[KP + KP * KP] = fallbacks;
+}
+
+// k_bwd_maps: thread per block.  Given alpha_t, everything the backward pass will do at block t is a
+// function of the state q_{t+1} it arrives with: the map j -> discrete_distribution(alpha'_t(.) A(., j))(u_t)
+// with alpha'_t = alpha_t * A_ss^(N_t - 1) (FB.hpp:115-119,145-146); the last block draws from alpha_B
+// itself (FB.hpp:138).  u_t is the block's counter-based Philox uniform, or the replayed one.
+template <int KP, bool kRows>
+__global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  const int K = m.K;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = Layout::inv(p);
+    Map<KP> fm = Map<KP>::identity();  // slots past the last block compose as the identity
+    if (b < B) {
+      const bool last = (b + 1 == B);
+      double ap[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
-        if (j < K) {
-          double w[KP];
+        const double al = buf.alpha[p * KP + j];
+        ap[j] = (last || !m.use_self) ? al : al * buf.sp[p * KP + j];
+      }
+      if (kRows) {
+        if (b == 0)
+          for (int j = 0; j < K; ++j) buf.rows[j] = m.pi[j];
+        for (int j = 0; j < K; ++j) buf.rows[(b + 1) * K + j] = ap[j];
+      }
+      const double u = buf.replay_u ? buf.replay_u[B - 1 - b] : Philox::uniform(seed, sweep, 0u, b);
+      fm = Map<KP>::zero();
+      if (last) {
+        const uint32_t q = discrete_draw<KP>(ap, K, u);
 #pragma unroll
-          for (int k = 0; k < KP; ++k) w[k] = ap[k] * m.A[k][j];
-          fm.set(j, discrete_draw<KP>(w, K, u));
+        for (int j = 0; j < KP; ++j) fm.set(j, q);
+      } else {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          if (j < K) {
+            double w[KP];
+#pragma unroll
+            for (int k = 0; k < KP; ++k) w[k] = ap[k] * m.A[k][j];
+            fm.set(j, discrete_draw<KP>(w, K, u));
+          }
         }
       }
     }
     fm.store(buf.maps + p * (8 * Map<KP>::W));
-    G = G.after(fm);
-    if ((b + 1) % L == 0 || last) {
-      gc[(b / L) % Layout::C] = G;
-      G = Map<KP>::identity();
-    }
-    if ((b + 1) % Layout::TB == 0 || last) {  // tile complete: exclusive suffix maps per chunk + tile map
-      const uint64_t tile = b / Layout::TB;
-      Map<KP> suf = Map<KP>::identity();
-      for (int c = Layout::C - 1; c >= 0; --c) {
-        suf.store(buf.chunk_maps + (tile * Layout::C + c) * (8 * Map<KP>::W));
-        suf = gc[c].after(suf);
-        gc[c] = Map<KP>::identity();
-      }
-      suf.store(buf.tile_maps + tile * (8 * Map<KP>::W));
-    }
   }
-  if (kLoglik) buf.partials[0] = ll;
-  buf.out_u64[KP + KP * KP] = fallbacks;
+}
+
+// k_bwd_chunkmaps: warp per tile, lane per chunk: G_c = f_first o ... o f_last of the chunk, then a
+// suffix scan over the warp: X_c = G_{c+1} o ... o G_31 (per chunk) and the tile map G_0 o ... o G_31.
+template <int KP>
+__global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf) {
+  constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t tile = warp; tile < ntiles; tile += nwarps) {
+    Map<KP> G = Map<KP>::identity();
+#pragma unroll 4
+    for (int t = 0; t < L; ++t) G = G.after(Map<KP>::load(buf.maps + Layout::at(tile, lane, t) * MB));
+    Map<KP> inc = G;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      Map<KP> other;
+#pragma unroll
+      for (int i = 0; i < Map<KP>::W; ++i) other.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], o);
+      if (lane + o < 32) inc = inc.after(other);
+    }
+    Map<KP> excl;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) excl.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
+    if (lane == 31) excl = Map<KP>::identity();
+    excl.store(buf.chunk_maps + (tile * C + lane) * MB);
+    if (lane == 0) inc.store(buf.tile_maps + tile * MB);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -860,13 +999,18 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
     if (s_n[i]) atomicAdd(&buf.out_u64[i], s_n[i]);
 }
 
+// one CTA per output value; fixed assignment and fixed tree => deterministic
 template <int KP>
-__global__ void __launch_bounds__(64) k_reduce_final(SweepBuffers buf, int nparts) {
-  if (threadIdx.x < 2 * KP) {
-    double t = 0.0;
-    for (int i = 0; i < nparts; ++i) t += buf.partials[(size_t)i * 2 * KP + threadIdx.x];
-    buf.out_f64[threadIdx.x] = t;
-  }
+__global__ void __launch_bounds__(128) k_reduce_final(SweepBuffers buf, int nparts) {
+  __shared__ double sh[4];
+  const int v = blockIdx.x;  // 0 .. 2*KP-1
+  double t = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += 128) t += buf.partials[(size_t)i * 2 * KP + v];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += shfl_xor_double(t, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) buf.out_f64[v] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
 }
 
 template <int KP>
@@ -897,6 +1041,43 @@ inline int grid_for(uint64_t items, int threads, int sms, int per_sm) {
 }
 
 template <int KP>
+void launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, cudaStream_t s) {
+  if constexpr (KP <= 8)
+    k_fwd_tilescan_small<KP><<<1, 256, 0, s>>>(b, m);
+  else
+    k_fwd_tilescan<KP><<<1, 1024, 0, s>>>(b, m);
+}
+
+// maps -> chunk/tile maps -> suffix scan over tiles -> states; returns the number of launches
+template <int KP>
+int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLaunch& l, bool rows, uint64_t nb,
+                    cudaStream_t s, stage_cb_t cb, void* user) {
+  const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
+  if (cb) cb(user, "bwd_maps");
+  const int gm = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
+  if (rows)
+    k_bwd_maps<KP, true><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
+  else
+    k_bwd_maps<KP, false><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
+  if (cb) cb(user, "bwd_chunkmaps");
+  k_bwd_chunkmaps<KP><<<grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s>>>(b);
+  if (cb) cb(user, "bwd_scan");
+  k_bwd_scan<KP><<<1, 1024, 0, s>>>(b);
+  if (cb) cb(user, "bwd_replay");
+  k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
+  return 4;
+}
+
+template <int KP>
+int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, int sms, cudaStream_t s) {
+  const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
+  const int g = grid_for(ntiles * Layout::TB, kReduceThreads, sms, 4);
+  k_reduce_partial<KP><<<g, kReduceThreads, 0, s>>>(b, K);
+  k_reduce_final<KP><<<2 * KP, 128, 0, s>>>(b, g);
+  return 2;
+}
+
+template <int KP>
 int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s, stage_cb_t cb,
                void* user) {
   const ModelDev<KP> m = make_model<KP>(mh);
@@ -913,7 +1094,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   ++launches;
   stage("block_emit");
   {
-    const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 8);
+    const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
     if (l.mixture) {
       if (l.gather)
         k_block_emit<KP, true, true, true><<<g, 256, 0, s>>>(b, m, 0);
@@ -929,45 +1110,29 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   }
   if (l.mixture) {
     stage("mix_sample");
-    k_mix_sample<KP><<<grid_for(ntiles * Layout::TB, 256, l.sms, 8), 256, 0, s>>>(b, m, l.seed, l.sweep);
+    k_mix_sample<KP><<<grid_for(ntiles * Layout::TB, 256, l.sms, 32), 256, 0, s>>>(b, m, l.seed, l.sweep);
     ++launches;
   } else {
     stage("fwd_chunks");
-    k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 8), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
+    k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
     ++launches;
     stage("fwd_tilescan");
-    k_fwd_tilescan<KP><<<1, 1024, 0, s>>>(b, m);
+    launch_fwd_tilescan<KP>(b, m, s);
     ++launches;
     stage("fwd_replay");
     const int gr = grid_for(ntiles, 1, l.sms, 32);
     if (loglik) {
-      if (rows)
-        k_fwd_replay<KP, true, true><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
-      else
-        k_fwd_replay<KP, true, false><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
+      k_fwd_replay<KP, true><<<gr, 32, 0, s>>>(b, m);
       k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, gr, b.out_f64 + 2 * KP);
       ++launches;
     } else {
-      if (rows)
-        k_fwd_replay<KP, false, true><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
-      else
-        k_fwd_replay<KP, false, false><<<gr, 32, 0, s>>>(b, m, l.seed, l.sweep);
+      k_fwd_replay<KP, false><<<gr, 32, 0, s>>>(b, m);
     }
     ++launches;
-    stage("bwd_scan");
-    k_bwd_scan<KP><<<1, 1024, 0, s>>>(b);
-    ++launches;
-    stage("bwd_replay");
-    k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
-    ++launches;
+    launches += launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
   }
   stage("reduce");
-  {
-    const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 2);
-    k_reduce_partial<KP><<<g, kReduceThreads, 0, s>>>(b, mh.K);
-    k_reduce_final<KP><<<1, 64, 0, s>>>(b, g);
-    launches += 2;
-  }
+  launches += launch_reduce<KP>(b, mh.K, nb, l.sms, s);
   stage("end");
   return launches;
 }
@@ -978,26 +1143,19 @@ int sequential_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunc
   const bool loglik = (l.flags & HML_SWEEP_LOGLIK) != 0;
   const bool rows = (l.flags & HML_SWEEP_KEEP_ROWS) != 0 && b.rows != nullptr;
   const uint64_t nb = l.nblocks_hint;
-  const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
+  int launches = 1;
   k_clear_out<KP><<<1, 256, 0, s>>>(b);
   if (loglik) {
-    if (rows)
-      k_fwd_sequential<KP, true, true><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
-    else
-      k_fwd_sequential<KP, true, false><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
+    k_fwd_sequential<KP, true><<<1, 32, 0, s>>>(b, m);
     k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, 1, b.out_f64 + 2 * KP);
+    launches += 2;
   } else {
-    if (rows)
-      k_fwd_sequential<KP, false, true><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
-    else
-      k_fwd_sequential<KP, false, false><<<1, 32, 0, s>>>(b, m, l.seed, l.sweep);
+    k_fwd_sequential<KP, false><<<1, 32, 0, s>>>(b, m);
+    launches += 1;
   }
-  k_bwd_scan<KP><<<1, 1024, 0, s>>>(b);
-  k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
-  const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 2);
-  k_reduce_partial<KP><<<g, kReduceThreads, 0, s>>>(b, mh.K);
-  k_reduce_final<KP><<<1, 64, 0, s>>>(b, g);
-  return 6 + (loglik ? 1 : 0);
+  launches += launch_backward<KP>(b, m, l, rows, nb, s, nullptr, nullptr);
+  launches += launch_reduce<KP>(b, mh.K, nb, l.sms, s);
+  return launches;
 }
 
 }  // namespace hml
