@@ -35,7 +35,10 @@ class _SweepOut(C.Structure):
 EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_load_f32", "hml_load_f32_device",
            "hml_size", "hml_sigma_hat", "hml_get_weights", "hml_get_coeffs", "hml_create_blocks", "hml_nr_blocks",
            "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
-           "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream"]
+           "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream",
+           "hml_comm_unique_id", "hml_comm_init", "hml_segment_plan", "hml_load_segment_f32",
+           "hml_load_segment_f32_device", "hml_segment_info"]
+UNIQUE_ID_BYTES = 128
 
 _lib = None
 
@@ -96,13 +99,57 @@ class Handle:
         self._ck(self.lib.hml_load_f32_device(self.h, C.c_void_p(dev_ptr), C.c_uint64(T), C.c_float(weight_multiplier)))
         self.T = int(T)
 
+    # ---- multi-GPU: one sequence split into contiguous segments (one handle per rank)
+    @staticmethod
+    def unique_id():
+        """NCCL unique id (bytes) created by rank 0; distribute it to all ranks, then comm_init everywhere."""
+        lib = load_library()
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES)()
+        rc = lib.hml_comm_unique_id(buf)
+        if rc != 0:
+            raise HmlError(rc, lib.hml_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, world, uid):
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(uid)
+        self._ck(self.lib.hml_comm_init(self.h, C.c_int(rank), C.c_int(world), buf))
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def segment_plan(T, world, rank):
+        lib = load_library()
+        s, n = C.c_uint64(), C.c_uint64()
+        rc = lib.hml_segment_plan(C.c_uint64(T), C.c_int(world), C.c_int(rank), C.byref(s), C.byref(n))
+        if rc != 0:
+            raise HmlError(rc, "sequence too short to split: T < 4096 * world")
+        return s.value, n.value
+
+    def load_segment(self, x_local, T, weight_multiplier=1.0):
+        x = np.ascontiguousarray(x_local, dtype=np.float32)
+        self._ck(self.lib.hml_load_segment_f32(self.h, _ptr(x), C.c_uint64(x.size), C.c_uint64(T),
+                                               C.c_float(weight_multiplier)))
+        self.T = int(T)
+
+    def load_segment_device(self, dev_ptr, n, T, weight_multiplier=1.0):
+        self._ck(self.lib.hml_load_segment_f32_device(self.h, C.c_void_p(dev_ptr), C.c_uint64(n), C.c_uint64(T),
+                                                      C.c_float(weight_multiplier)))
+        self.T = int(T)
+
+    def segment_info(self):
+        r, w = C.c_int(), C.c_int()
+        s, n, fb, gb = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.hml_segment_info(self.h, C.byref(r), C.byref(w), C.byref(s), C.byref(n), C.byref(fb), C.byref(gb)))
+        return dict(rank=r.value, world=w.value, seg_start=s.value, seg_len=n.value, first_block=fb.value,
+                    global_blocks=gb.value)
+
     def sigma_hat(self):
         v = C.c_double()
         self._ck(self.lib.hml_sigma_hat(self.h, C.byref(v)))
         return v.value
 
     def weights(self):
-        w = np.empty(self.T, dtype=np.float32)
+        """fp32 breakpoint weights (segment mode: of the local segment)."""
+        w = np.empty(self.segment_info()["seg_len"] if getattr(self, "world", 1) > 1 else self.T, dtype=np.float32)
         self._ck(self.lib.hml_get_weights(self.h, _ptr(w), C.c_uint64(w.size)))
         return w
 

@@ -1,5 +1,7 @@
 // hammlet_b200 — C ABI (include/hammlet_b200.h): context, load orchestration, sweeps, getters.
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>  // types only: the library is loaded with dlopen in hml_comm_init (single-GPU use needs no NCCL)
 #include <stdio.h>
 #include <string.h>
 
@@ -19,6 +21,40 @@ struct Stage {
   cudaEvent_t ev;
 };
 constexpr size_t kOutWords = 2 + 32 + 32 * 32 + 2 + 2 * 32 + 2;  // device/pinned result block, 64-bit words
+constexpr int kMaxWorld = 64;
+constexpr size_t kOpDoubles = 32 * 32 + 32;  // largest segment operator (mantissas + exponents)
+
+// NCCL entry points, resolved at run time from libnccl.so.2 (the copy PyTorch already loaded, if any)
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool load() {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+      error = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return false;
+    }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy || !GetErrorString) {
+      error = "libnccl.so.2 lacks a required symbol";
+      lib = nullptr;
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
 }  // namespace
 
 struct hml_ctx {
@@ -28,7 +64,16 @@ struct hml_ctx {
   std::string err;
   uint64_t launches = 0;
 
-  // sequence (resident since load)
+  // segment mode (one sequence split over the ranks of a communicator)
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  uint64_t T_global = 0, seg_start = 0;
+  uint64_t first_block = 0, global_blocks = 0;  // of the last sweep / block structure
+  double* seg_dev = nullptr;                    // send slots + gathered carries (one allocation)
+  unsigned long long* stats_gather = nullptr;   // world x kOutWords
+  unsigned long long* stats_gather_host = nullptr;
+
+  // sequence (resident since load); in segment mode T is the length of the local segment
   uint64_t T = 0;
   float* w = nullptr;       // breakpoint weights, padded to a tile multiple
   float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
@@ -198,18 +243,66 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   size_t words = (size_t)KP + (size_t)KP * KP + 1;
   words += words & 1;
   b.out_f64 = (double*)(h->outblk + 2 + words);
+  if (h->world > 1) {
+    double* d = h->seg_dev;
+    b.seg.rank = h->rank;
+    b.seg.world = h->world;
+    b.seg.send_head = d;
+    b.seg.send_map = (uint64_t*)(d + 4);
+    b.seg.send_op = d + 8;
+    d += 8 + kOpDoubles;
+    b.seg.heads = d;
+    b.seg.maps = (const uint64_t*)(d + 4 * (size_t)h->world);
+    b.seg.ops = d + 8 * (size_t)h->world;
+    b.seg.overflow = h->outblk + 1;
+  }
   return b;
 }
 
-int run_detect(hml_t* h, float thr) {
-  h->launches += launch_detect(h->w, h->T, thr, 1, h->detect_scratch, h->starts, h->capacity, h->outblk, h->stream,
-                               stage_cb, h);
-  CK(cudaGetLastError());
+#define CKN(call)                                                                                             \
+  do {                                                                                                        \
+    ncclResult_t r__ = (call);                                                                                \
+    if (r__ != ncclSuccess) return fail(h, HML_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r__)); \
+  } while (0)
+
+int all_gather(hml_t* h, const void* send, void* recv, size_t bytes) {
+  CKN(g_nccl.AllGather(send, recv, bytes, ncclUint8, h->comm, h->stream));
   return HML_OK;
 }
 
-int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
-  // ---- free the previous sequence
+// all-gathers one of the per-sweep carries (send slot -> gathered array), on the handle's stream
+int exchange_cb(void* user, int which) {
+  hml_t* h = (hml_t*)user;
+  SweepBuffers b = make_buffers(h, h->KP ? h->KP : 2);
+  switch (which) {
+    case kExchangeHeads: return all_gather(h, b.seg.send_head, (void*)b.seg.heads, 4 * sizeof(double));
+    case kExchangeMaps: return all_gather(h, b.seg.send_map, (void*)b.seg.maps, 4 * sizeof(uint64_t));
+    case kExchangeOps: {
+      const size_t n = (size_t)h->KP * h->KP + h->KP;
+      return all_gather(h, b.seg.send_op, (void*)b.seg.ops, n * sizeof(double));
+    }
+    default: return HML_ERR_ARG;
+  }
+}
+
+
+int run_detect(hml_t* h, float thr) {
+  h->launches += launch_detect(h->w, h->T, thr, h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity,
+                               h->outblk, h->stream, stage_cb, h);
+  CK(cudaGetLastError());
+  if (h->world > 1) {
+    // the partial block in front of each rank's first boundary joins the last block of its owner
+    stage_cb(h, "seg_head");
+    launch_seg_head(make_buffers(h, h->KP ? h->KP : 2), h->T, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    stage_cb(h, "exchange_heads");
+    return exchange_cb(h, kExchangeHeads);
+  }
+  return HML_OK;
+}
+
+void load_reset(hml_t* h) {
   dev_free(h->w);
   dev_free(h->coeffs);
   dev_free(h->pq);
@@ -217,63 +310,136 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
   if (h->detect_scratch) cudaFree(h->detect_scratch);
   h->detect_scratch = nullptr;
   h->T = 0;
+  h->T_global = 0;
+  h->seg_start = 0;
   h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
-  const uint64_t tiles = (T + kTile - 1) / kTile;
-  const uint64_t cells = T / kCell + 1;
+}
 
-  // ---- level normalisers: running fp32 product of sqrt2half, includes.hpp:126-128, wavelet.hpp:144,172
+// level normalisers: running fp32 product of sqrt2half, includes.hpp:126-128, wavelet.hpp:144,172
+void load_norms(hml_t* h) {
   float norms[64];
-  {
-    const float sqrt2 = (float)sqrt(2.0);
-    const float sqrt2half = (float)(sqrt2 / 2.0);
-    float n = sqrt2half;
-    norms[0] = 1.0f;
-    for (int l = 1; l < 64; ++l) {
-      norms[l] = n;
-      n *= sqrt2half;
-    }
+  const float sqrt2 = (float)sqrt(2.0);
+  const float sqrt2half = (float)(sqrt2 / 2.0);
+  float n = sqrt2half;
+  norms[0] = 1.0f;
+  for (int l = 1; l < 64; ++l) {
+    norms[l] = n;
+    n *= sqrt2half;
   }
   upload_level_norms(norms, h->stream);
+}
+
+// sum of the odd-index coefficients of c[0..n) (main.cpp:303-311), fp64 partials summed on the host
+int load_sum_odd(hml_t* h, const float* c, uint64_t n, double* out) {
+  const int nb = 512;
+  double* part = nullptr;
+  CK(dev_alloc(part, nb));
+  launch_sum_odd(c, n, part, nb, h->stream);
+  h->launches++;
+  std::vector<double> hp(nb);
+  CK(cudaMemcpyAsync(hp.data(), part, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  dev_free(part);
+  long double s = 0;
+  for (double v : hp) s += v;
+  *out = (double)s;
+  return HML_OK;
+}
+
+// integral arrays + double-double cell prefix of the local observations x[0..T)
+int load_integral(hml_t* h, const float* x_dev, uint64_t T) {
+  const uint64_t cells = T / kCell + 1;
+  CK(dev_alloc(h->pq, cells * kCell));
+  double2* cell_tot = nullptr;
+  CK(dev_alloc(cell_tot, cells));
+  launch_integral_cells(x_dev, T, h->pq, cell_tot, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  std::vector<double2> tot(cells);
+  CK(cudaMemcpyAsync(tot.data(), cell_tot, cells * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<double4> pref(cells + 1);
+  // exclusive prefix in double-double (Knuth two-sum), so differences of far-apart cells stay exact to ~1e-32
+  double hx = 0, lx = 0, hq = 0, lq = 0;
+  auto dd_add = [](double& hi, double& lo, double v) {
+    const double s = hi + v;
+    const double bb = s - hi;
+    const double err = (hi - (s - bb)) + (v - bb);
+    const double l2 = lo + err;
+    const double s2 = s + l2;
+    lo = l2 - (s2 - s);
+    hi = s2;
+  };
+  for (uint64_t c = 0; c <= cells; ++c) {
+    pref[c] = make_double4(hx, lx, hq, lq);
+    if (c < cells) {
+      dd_add(hx, lx, tot[c].x);
+      dd_add(hq, lq, tot[c].y);
+    }
+  }
+  CK(dev_alloc(h->cell_pref, cells + 1));
+  CK(cudaMemcpyAsync(h->cell_pref, pref.data(), (cells + 1) * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  dev_free(cell_tot);
+  return HML_OK;
+}
+
+// boundary-detection scratch and the initial block capacity (grows on demand: a sweep that overflows is re-run)
+int load_finish(hml_t* h, uint64_t T) {
+  CK(cudaMalloc(&h->detect_scratch, detect_scratch_bytes(T)));
+  h->T = T;
+  uint64_t cap = T / 64;
+  if (cap < (1u << 16)) cap = 1u << 16;
+  if (cap > T) cap = T;
+  h->capacity = 0;
+  int rc = alloc_blocks(h, cap, 0);
+  if (rc != HML_OK) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+// Haar passes above the first: `in` holds per-tile sums of the previous pass; coefficients of pass p go to
+// coeffs[j * stride] (stride counted in elements of `coeffs`).
+int load_upper_passes(hml_t* h, const float* in, uint64_t n_valid, uint64_t n_pos, uint64_t stride, int level0,
+                      float* coeffs, float* sums[2]) {
+  int which = 0;
+  while (n_pos > 1) {
+    launch_maxlet_level(in, n_valid, n_pos, stride, level0, coeffs, sums[which], h->stream);
+    h->launches++;
+    in = sums[which];
+    which ^= 1;
+    n_valid = n_valid / kTile;
+    n_pos = (n_pos + kTile - 1) / kTile;
+    stride *= kTile;
+    level0 += kTileLog2;
+  }
+  CK(cudaGetLastError());
+  return HML_OK;
+}
+
+int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
+  if (h->world > 1) return fail(h, HML_ERR_STATE, "this handle joined a communicator: use hml_load_segment_f32");
+  load_reset(h);
+  const uint64_t tiles = (T + kTile - 1) / kTile;
+  load_norms(h);
 
   // ---- maxlet coefficients, 12 levels per pass
   CK(dev_alloc(h->coeffs, tiles * kTile));
   float* sums[2] = {nullptr, nullptr};
   CK(dev_alloc(sums[0], tiles + 1));
   CK(dev_alloc(sums[1], tiles / kTile + 2));
-  {
-    const float* in = x_dev;
-    uint64_t n_valid = T, n_pos = T, stride = 1;
-    int level0 = 0, which = 0;
-    while (n_pos > 1) {
-      launch_maxlet_level(in, n_valid, n_pos, stride, level0, h->coeffs, sums[which], h->stream);
-      h->launches++;
-      in = sums[which];
-      which ^= 1;
-      n_valid = n_valid / kTile;
-      n_pos = (n_pos + kTile - 1) / kTile;
-      stride *= kTile;
-      level0 += kTileLog2;
-    }
-    const float inf = INFINITY;
-    CK(cudaMemcpyAsync(h->coeffs, &inf, sizeof(float), cudaMemcpyHostToDevice, h->stream));  // wavelet.hpp:183
-  }
-  CK(cudaGetLastError());
+  int rc = load_upper_passes(h, x_dev, T, T, 1, 0, h->coeffs, sums);
+  if (rc != HML_OK) return rc;
+  const float inf = INFINITY;
+  CK(cudaMemcpyAsync(h->coeffs, &inf, sizeof(float), cudaMemcpyHostToDevice, h->stream));  // wavelet.hpp:183
 
-  // ---- sigma-hat numerator (main.cpp:303-311)
+  // ---- sigma-hat (main.cpp:303-311)
   {
-    const int nb = 512;
-    double* part = nullptr;
-    CK(dev_alloc(part, nb));
-    launch_sum_odd(h->coeffs, T, part, nb, h->stream);
-    h->launches++;
-    std::vector<double> hp(nb);
-    CK(cudaMemcpyAsync(hp.data(), part, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    dev_free(part);
-    long double s = 0;
-    for (double v : hp) s += v;
+    double s = 0;
+    rc = load_sum_odd(h, h->coeffs, T, &s);
+    if (rc != HML_OK) return rc;
     const uint64_t n = T / 2;
-    double est = n ? (double)(s / (long double)n) : NAN;
+    double est = n ? s / (double)n : NAN;
     est /= 0.797884560802865355879892119868763736951717262329869315331;
     h->sigma_hat = est;
   }
@@ -284,58 +450,117 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
   h->launches++;
   CK(cudaGetLastError());
 
-  // ---- integral arrays + double-double cell prefix
-  CK(dev_alloc(h->pq, cells * kCell));
-  double2* cell_tot = nullptr;
-  CK(dev_alloc(cell_tot, cells));
-  launch_integral_cells(x_dev, T, h->pq, cell_tot, h->stream);
-  h->launches++;
-  CK(cudaGetLastError());
-  {
-    std::vector<double2> tot(cells);
-    CK(cudaMemcpyAsync(tot.data(), cell_tot, cells * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    std::vector<double4> pref(cells + 1);
-    // exclusive prefix in double-double (Knuth two-sum), so differences of far-apart cells stay exact to ~1e-32
-    double hx = 0, lx = 0, hq = 0, lq = 0;
-    auto dd_add = [](double& hi, double& lo, double v) {
-      const double s = hi + v;
-      const double bb = s - hi;
-      const double err = (hi - (s - bb)) + (v - bb);
-      const double l2 = lo + err;
-      const double s2 = s + l2;
-      lo = l2 - (s2 - s);
-      hi = s2;
-    };
-    for (uint64_t c = 0; c <= cells; ++c) {
-      pref[c] = make_double4(hx, lx, hq, lq);
-      if (c < cells) {
-        dd_add(hx, lx, tot[c].x);
-        dd_add(hq, lq, tot[c].y);
-      }
-    }
-    CK(dev_alloc(h->cell_pref, cells + 1));
-    CK(cudaMemcpyAsync(h->cell_pref, pref.data(), (cells + 1) * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
-  dev_free(cell_tot);
+  rc = load_integral(h, x_dev, T);
+  if (rc != HML_OK) return rc;
   dev_free(sums[0]);
   dev_free(sums[1]);
   if (T > (1ull << 26)) dev_free(h->coeffs);  // 4 B/observation is not worth keeping for big inputs
+  rc = load_finish(h, T);
+  h->T_global = T;
+  return rc;
+}
 
-  // ---- boundary-detection scratch
-  CK(cudaMalloc(&h->detect_scratch, detect_scratch_bytes(T)));
-  h->T = T;
+void segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t* len) {
+  const uint64_t tiles = (T + kTile - 1) / kTile;
+  const uint64_t per = (tiles + world - 1) / world;  // tiles per rank (the last ranks may hold fewer)
+  uint64_t s = (uint64_t)rank * per * kTile, e = (uint64_t)(rank + 1) * per * kTile;
+  if (s > T) s = T;
+  if (e > T) e = T;
+  *start = s;
+  *len = e - s;
+}
 
-  // ---- initial block capacity: grows on demand (a sweep that overflows is re-run)
-  uint64_t cap = T / 64;
-  if (cap < (1u << 16)) cap = 1u << 16;
-  if (cap > T) cap = T;
-  h->capacity = 0;
-  int rc = alloc_blocks(h, cap, 0);
+// Collective load of one segment.  Levels 1..12 of the Haar transform are local to 4096-tiles; the levels
+// above are computed by every rank from the all-gathered tile sums (T/4096 floats), so no rank needs
+// another rank's observations.
+int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float mult) {
+  if (h->world <= 1 || !h->comm) return fail(h, HML_ERR_STATE, "hml_comm_init has not been called on this handle");
+  uint64_t start = 0, plan_len = 0;
+  if (T < (uint64_t)kTile * h->world) return fail(h, HML_ERR_ARG, "sequence too short to split: T < 4096 * world");
+  segment_plan(T, h->world, h->rank, &start, &plan_len);
+  if (len != plan_len || len == 0) return fail(h, HML_ERR_ARG, "segment length does not match hml_segment_plan");
+  load_reset(h);
+  load_norms(h);
+  const int world = h->world;
+  const uint64_t tiles_total = (T + kTile - 1) / kTile;
+  const uint64_t per = (tiles_total + world - 1) / world;
+  const uint64_t tiles = (len + kTile - 1) / kTile;
+  const uint64_t slot = per + 16;  // floats per rank in the all-gather: tile sums + 12 edge coefficients
+
+  // ---- pass 0 on the local observations
+  CK(dev_alloc(h->coeffs, tiles * kTile));
+  float *send = nullptr, *recv = nullptr, *gsum = nullptr, *ctop = nullptr;
+  CK(dev_alloc(send, slot));
+  CK(dev_alloc(recv, slot * world));
+  CK(cudaMemsetAsync(send, 0, slot * sizeof(float), h->stream));
+  launch_maxlet_level(x_dev, len, len, 1, 0, h->coeffs, send, h->stream);
+  h->launches++;
+  launch_pack_edge(h->coeffs, len, send + per, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  int rc = all_gather(h, send, recv, slot * sizeof(float));
+  if (rc != HML_OK) return rc;
+
+  // ---- upper levels from the global tile sums, replicated: ctop[m] = coefficient at position 4096 m
+  CK(dev_alloc(gsum, per * world));
+  CK(cudaMemcpy2DAsync(gsum, per * sizeof(float), recv, slot * sizeof(float), per * sizeof(float), world,
+                       cudaMemcpyDeviceToDevice, h->stream));
+  const uint64_t top_tiles = (tiles_total + kTile - 1) / kTile;
+  CK(dev_alloc(ctop, top_tiles * kTile));
+  {
+    std::vector<float> infs(top_tiles * kTile, INFINITY);
+    CK(cudaMemcpyAsync(ctop, infs.data(), infs.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  float* sums[2] = {nullptr, nullptr};
+  CK(dev_alloc(sums[0], top_tiles + 1));
+  CK(dev_alloc(sums[1], top_tiles / kTile + 2));
+  rc = load_upper_passes(h, gsum, T / kTile, tiles_total, 1, kTileLog2, ctop, sums);
+  if (rc != HML_OK) return rc;
+
+  // ---- sigma-hat: odd positions are odd locally too (segments start at multiples of 4096)
+  {
+    double part = 0;
+    rc = load_sum_odd(h, h->coeffs, len, &part);
+    if (rc != HML_OK) return rc;
+    double *ds = nullptr, *dr = nullptr;
+    CK(dev_alloc(ds, 1));
+    CK(dev_alloc(dr, world));
+    CK(cudaMemcpyAsync(ds, &part, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = all_gather(h, ds, dr, sizeof(double));
+    if (rc != HML_OK) return rc;
+    std::vector<double> parts(world);
+    CK(cudaMemcpyAsync(parts.data(), dr, world * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    dev_free(ds);
+    dev_free(dr);
+    long double s = 0;
+    for (double v : parts) s += v;
+    const uint64_t n = T / 2;
+    h->sigma_hat = (double)(s / (long double)n) / 0.797884560802865355879892119868763736951717262329869315331;
+  }
+
+  // ---- breakpoint weights of the local segment
+  CK(dev_alloc(h->w, tiles * kTile));
+  const float* halo = recv + (size_t)(h->rank > 0 ? h->rank - 1 : 0) * slot + per;
+  launch_bp_weights_segment(h->coeffs, ctop, halo, start, len, T, mult, h->w, h->sms, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+
+  rc = load_integral(h, x_dev, len);
   if (rc != HML_OK) return rc;
   CK(cudaStreamSynchronize(h->stream));
-  return HML_OK;
+  dev_free(send);
+  dev_free(recv);
+  dev_free(gsum);
+  dev_free(ctop);
+  dev_free(sums[0]);
+  dev_free(sums[1]);
+  if (len > (1ull << 26)) dev_free(h->coeffs);
+  rc = load_finish(h, len);
+  h->T_global = T;
+  h->seg_start = start;
+  return rc;
 }
 
 int validate_model(hml_t* h, const hml_model* m, ModelHost& mh) {
@@ -361,6 +586,53 @@ int validate_model(hml_t* h, const hml_model* m, ModelHost& mh) {
   return HML_OK;
 }
 
+// Copies the result block(s) of the sweep to the host.  Single handle: its own block.  Segment mode: the
+// blocks of all ranks are all-gathered first; `res` then holds the rank-ordered sums (identical on every rank).
+struct SweepResult {
+  std::vector<unsigned long long> o64;  // [0..KP) n, [KP..KP+KP*KP) trans, [KP+KP*KP] fallbacks
+  std::vector<double> of;               // [0..KP) sum, [KP..2KP) sumsq, [2KP] loglik
+  uint64_t local_blocks = 0, global_blocks = 0, first_block = 0;
+  bool any_overflow = false, own_overflow = false;
+};
+
+int fetch_result(hml_t* h, int KP, SweepResult& res) {
+  size_t words = (size_t)KP + (size_t)KP * KP + 1;
+  words += words & 1;
+  const size_t copy_words = 2 + words + 2 * KP + 1;
+  res.o64.assign(words, 0);
+  res.of.assign(2 * KP + 1, 0.0);
+  const int world = h->world > 1 ? h->world : 1;
+  const unsigned long long* host = h->outblk_host;
+  if (world > 1) {
+    int rc = all_gather(h, h->outblk, h->stats_gather, copy_words * 8);
+    if (rc != HML_OK) return rc;
+    CK(cudaMemcpyAsync(h->stats_gather_host, h->stats_gather, world * copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
+    host = h->stats_gather_host;
+  } else {
+    CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  res.global_blocks = res.first_block = 0;
+  res.any_overflow = res.own_overflow = false;
+  for (int r = 0; r < world; ++r) {
+    const unsigned long long* blk = host + (size_t)r * copy_words;
+    const uint64_t raw = blk[0];
+    const bool over = world > 1 ? blk[1] != 0 : raw > h->capacity;
+    if (r == h->rank || world == 1) {
+      res.local_blocks = raw;
+      res.own_overflow = over;
+    }
+    res.any_overflow |= over;
+    if (r < h->rank) res.first_block += raw;
+    res.global_blocks += raw;
+    const unsigned long long* o64 = blk + 2;
+    const double* of = (const double*)(blk + 2 + words);
+    for (size_t i = 0; i < words; ++i) res.o64[i] += o64[i];
+    for (int i = 0; i < 2 * KP + 1; ++i) res.of[i] += of[i];
+  }
+  return HML_OK;
+}
+
 int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64_t seed, uint64_t sweep,
                  const double* replay, uint64_t n_replay, hml_sweep_out* out, bool mixture) {
   if (!h) return HML_ERR_ARG;
@@ -372,10 +644,14 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
   if (rc != HML_OK) return rc;
   const int KP = padded_states(mh.K);
   const bool dynamic = (flags & HML_SWEEP_DYNAMIC) != 0;
+  const bool seg = h->world > 1;
   if (replay && dynamic)
     return fail(h, HML_ERR_ARG, "replay uniforms need a fixed block structure: call hml_create_blocks first");
   if (!dynamic && !h->blocks_valid) return fail(h, HML_ERR_STATE, "no block structure: call hml_create_blocks first");
-  if (replay && n_replay < h->nblocks) return fail(h, HML_ERR_ARG, "fewer replay uniforms than blocks");
+  const uint64_t replay_need = seg ? h->global_blocks : h->nblocks;
+  if (replay && n_replay < replay_need) return fail(h, HML_ERR_ARG, "fewer replay uniforms than blocks");
+  if (seg && (flags & HML_SWEEP_KEEP_ROWS))
+    return fail(h, HML_ERR_ARG, "forward rows are not kept in segment mode");
 
   for (int attempt = 0; attempt < 8; ++attempt) {
     if (KP != h->KP) {
@@ -388,11 +664,11 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
       CK(dev_alloc(h->rows, h->rows_cap));
     }
     if (replay) {
-      if (h->replay_cap < h->nblocks) {
-        h->replay_cap = h->capacity;
+      if (h->replay_cap < replay_need) {
+        h->replay_cap = replay_need > h->capacity ? replay_need : h->capacity;
         CK(dev_alloc(h->replay_u, h->replay_cap));
       }
-      CK(cudaMemcpyAsync(h->replay_u, replay, h->nblocks * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->replay_u, replay, replay_need * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     h->stages.clear();
     h->stage_used = 0;
@@ -414,49 +690,53 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     l.sweep = sweep;
     l.sms = h->sms;
     l.nblocks_hint = dynamic ? h->capacity : h->nblocks;
+    l.exchange = exchange_cb;
+    l.exchange_user = h;
     const int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
-    if (n < 0) return fail(h, HML_ERR_ARG, "unsupported number of states");
+    if (n == -2) return fail(h, HML_ERR_ARG, "unsupported number of states");
+    if (n < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
     h->launches += n;
     CK(cudaGetLastError());
-    size_t words = (size_t)KP + (size_t)KP * KP + 1;
-    words += words & 1;
-    const size_t copy_words = 2 + words + 2 * KP + 1;
-    CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    const uint64_t B = h->outblk_host[0];
-    if (dynamic && B > h->capacity) {  // block arrays too small: grow and run the sweep again
-      rc = alloc_blocks(h, B + B / 4, KP);
-      if (rc != HML_OK) return rc;
+    SweepResult res;
+    rc = fetch_result(h, KP, res);
+    if (rc != HML_OK) return rc;
+    if (dynamic && res.any_overflow) {  // some rank's block arrays were too small: grow and run the sweep again
+      if (res.own_overflow) {
+        rc = alloc_blocks(h, res.local_blocks + res.local_blocks / 4, KP);
+        if (rc != HML_OK) return rc;
+      }
       continue;
     }
+    const uint64_t B = res.local_blocks;
     h->nblocks = B;
+    h->global_blocks = res.global_blocks;
+    h->first_block = res.first_block;
     h->blocks_valid = true;
     h->stats_valid = true;
-    const unsigned long long* o64 = h->outblk_host + 2;
-    const double* of = (const double*)(h->outblk_host + 2 + words);
-    uint64_t fallbacks = o64[KP + KP * KP];
+    uint64_t fallbacks = res.o64[KP + KP * KP];
     if (fallbacks > 0 && !mixture) {
       // A zero forward sum resets the filter to uniform (FB.hpp:106-111); that is not an operator
       // product, so the exact sequential recursion is run instead (still on the device).
       l.nblocks_hint = B;
       const int n2 = launch_sweep_sequential(mh, b, l, h->stream);
+      if (n2 < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
       h->launches += n2;
       CK(cudaGetLastError());
-      CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      fallbacks = o64[KP + KP * KP];
+      rc = fetch_result(h, KP, res);
+      if (rc != HML_OK) return rc;
+      fallbacks = res.o64[KP + KP * KP];
     }
     collect_timing(h);
-    out->nblocks = B;
+    out->nblocks = res.global_blocks;
     out->uniform_fallbacks = fallbacks;
-    out->loglik = (flags & HML_SWEEP_LOGLIK) ? of[2 * KP] : NAN;
+    out->loglik = (flags & HML_SWEEP_LOGLIK) ? res.of[2 * KP] : NAN;
     for (int s = 0; s < mh.K; ++s) {
-      if (out->stat_sum) out->stat_sum[s] = of[s];
-      if (out->stat_sumsq) out->stat_sumsq[s] = of[KP + s];
-      if (out->stat_n) out->stat_n[s] = o64[s];
-      if (out->counts) out->counts[s] = o64[s];  // univariate: occupancy == observations per parameter
+      if (out->stat_sum) out->stat_sum[s] = res.of[s];
+      if (out->stat_sumsq) out->stat_sumsq[s] = res.of[KP + s];
+      if (out->stat_n) out->stat_n[s] = res.o64[s];
+      if (out->counts) out->counts[s] = res.o64[s];  // univariate: occupancy == observations per parameter
       if (out->trans)
-        for (int j = 0; j < mh.K; ++j) out->trans[s * mh.K + j] = o64[KP + s * KP + j];
+        for (int j = 0; j < mh.K; ++j) out->trans[s * mh.K + j] = res.o64[KP + s * KP + j];
     }
     h->states_valid = true;
     h->rows_valid = (flags & HML_SWEEP_KEEP_ROWS) != 0 && !mixture;
@@ -549,6 +829,10 @@ int hml_destroy(hml_t* h) {
   dev_free(h->replay_u);
   dev_free(h->partials);
   dev_free(h->outblk);
+  dev_free(h->seg_dev);
+  dev_free(h->stats_gather);
+  if (h->stats_gather_host) cudaFreeHost(h->stats_gather_host);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
   if (h->outblk_host) cudaFreeHost(h->outblk_host);
   for (cudaEvent_t ev : h->event_pool) cudaEventDestroy(ev);
   cudaStreamDestroy(h->stream);
@@ -586,7 +870,7 @@ int hml_load_f32(hml_t* h, const float* x_host, uint64_t T, float weight_multipl
 
 int hml_size(const hml_t* h, uint64_t* T) {
   if (!h || !T) return HML_ERR_ARG;
-  *T = h->T;
+  *T = h->world > 1 ? h->T_global : h->T;
   return HML_OK;
 }
 
@@ -622,6 +906,7 @@ int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks) {
   if (!h) return HML_ERR_ARG;
   if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
   CK(cudaSetDevice(h->device));
+  const int world = h->world > 1 ? h->world : 1;
   for (int attempt = 0; attempt < 8; ++attempt) {
     h->stages.clear();
     h->stage_used = 0;
@@ -633,19 +918,39 @@ int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks) {
     h->launches++;
     stage_cb(h, "end");
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->outblk_host, h->outblk, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    const uint64_t B = h->outblk_host[0];
-    if (B > h->capacity) {
-      rc = alloc_blocks(h, B + B / 4, h->KP);
+    // block counts of all ranks (a rank whose arrays were too small makes every rank repeat the call)
+    const unsigned long long* host = h->outblk_host;
+    if (world > 1) {
+      rc = all_gather(h, h->outblk, h->stats_gather, 16);
       if (rc != HML_OK) return rc;
+      CK(cudaMemcpyAsync(h->stats_gather_host, h->stats_gather, world * 16, cudaMemcpyDeviceToHost, h->stream));
+      host = h->stats_gather_host;
+    } else {
+      CK(cudaMemcpyAsync(h->outblk_host, h->outblk, 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    const uint64_t B = host[2 * (world > 1 ? h->rank : 0)];
+    bool any_over = false;
+    uint64_t total = 0, first = 0;
+    for (int r = 0; r < world; ++r) {
+      any_over |= world > 1 ? host[2 * r + 1] != 0 : host[0] > h->capacity;
+      total += host[2 * r];
+      if (r < h->rank) first += host[2 * r];
+    }
+    if (any_over) {
+      if (B > h->capacity) {
+        rc = alloc_blocks(h, B + B / 4, h->KP);
+        if (rc != HML_OK) return rc;
+      }
       continue;
     }
     collect_timing(h);
     h->nblocks = B;
+    h->global_blocks = total;
+    h->first_block = first;
     h->blocks_valid = h->stats_valid = true;
     h->states_valid = h->rows_valid = false;
-    if (nblocks) *nblocks = B;
+    if (nblocks) *nblocks = world > 1 ? total : B;
     return HML_OK;
   }
   return fail(h, HML_ERR_CAPACITY, "block capacity did not converge");
@@ -664,7 +969,13 @@ int hml_get_blocks(hml_t* h, uint32_t* starts, double* sum, double* sumsq, uint6
   if (capacity < h->nblocks) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of blocks");
   CK(cudaSetDevice(h->device));
   const uint64_t B = h->nblocks;
-  if (starts) CK(cudaMemcpyAsync(starts, h->starts, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  if (starts) {
+    CK(cudaMemcpyAsync(starts, h->starts, B * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (h->seg_start) {  // segment mode: report positions in the whole sequence
+      CK(cudaStreamSynchronize(h->stream));
+      for (uint64_t i = 0; i < B; ++i) starts[i] += (uint32_t)h->seg_start;
+    }
+  }
   if (sum || sumsq) {
     if (!sum || !sumsq) return fail(h, HML_ERR_ARG, "sum and sumsq must be given together");
     double* tmp = nullptr;
@@ -732,7 +1043,7 @@ int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t*
   }
   if (seg_size && seg_state) {
     for (uint64_t i = 0; i < n; ++i) {
-      const uint64_t next = (i + 1 < n) ? seg_size[i + 1] : h->T;
+      const uint64_t next = (i + 1 < n) ? seg_size[i + 1] : h->seg_start + h->T;
       seg_size[i] = next - seg_size[i];
     }
   }
@@ -747,6 +1058,96 @@ int hml_get_rows(hml_t* h, double* rows, uint64_t capacity_rows) {
   CK(cudaSetDevice(h->device));
   CK(cudaMemcpyAsync(rows, h->rows, (h->nblocks + 1) * h->last_K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int hml_comm_unique_id(uint8_t id[HML_UNIQUE_ID_BYTES]) {
+  if (!id) return HML_ERR_ARG;
+  static_assert(sizeof(ncclUniqueId) == HML_UNIQUE_ID_BYTES, "NCCL unique id size");
+  if (!g_nccl.load()) {
+    g_create_error = g_nccl.error;
+    return HML_ERR_CUDA;
+  }
+  ncclUniqueId u;
+  const ncclResult_t r = g_nccl.GetUniqueId(&u);
+  if (r != ncclSuccess) {
+    g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r);
+    return HML_ERR_CUDA;
+  }
+  memcpy(id, &u, sizeof(u));
+  return HML_OK;
+}
+
+int hml_comm_init(hml_t* h, int rank, int world, const uint8_t id[HML_UNIQUE_ID_BYTES]) {
+  if (!h || !id) return HML_ERR_ARG;
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail(h, HML_ERR_ARG, "invalid rank / world size");
+  if (h->comm) return fail(h, HML_ERR_STATE, "the handle already joined a communicator");
+  if (h->T) return fail(h, HML_ERR_STATE, "join the communicator before loading data");
+  if (world == 1) return HML_OK;
+  if (!g_nccl.load()) return fail(h, HML_ERR_CUDA, g_nccl.error);
+  CK(cudaSetDevice(h->device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  CKN(g_nccl.CommInitRank(&h->comm, world, u, rank));
+  h->rank = rank;
+  h->world = world;
+  const size_t seg_words = 8 + kOpDoubles + (size_t)world * (8 + kOpDoubles);
+  CK(dev_alloc(h->seg_dev, seg_words));
+  CK(cudaMemsetAsync(h->seg_dev, 0, seg_words * sizeof(double), h->stream));
+  CK(dev_alloc(h->stats_gather, (size_t)world * kOutWords));
+  CK(cudaMallocHost((void**)&h->stats_gather_host, (size_t)world * kOutWords * 8));
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int hml_segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t* len) {
+  if (!start || !len || world < 1 || rank < 0 || rank >= world) return HML_ERR_ARG;
+  if (world > 1 && T < (uint64_t)kTile * world) return HML_ERR_ARG;
+  if (world == 1) {
+    *start = 0;
+    *len = T;
+    return HML_OK;
+  }
+  segment_plan(T, world, rank, start, len);
+  return HML_OK;
+}
+
+int hml_load_segment_f32_device(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float weight_multiplier) {
+  if (!h) return HML_ERR_ARG;
+  if (!x_dev) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (T >= (1ull << 32)) return fail(h, HML_ERR_ARG, "a sequence holds fewer than 2^32 observations");
+  CK(cudaSetDevice(h->device));
+  if (h->world <= 1) return len == T ? load_common(h, x_dev, T, weight_multiplier) : fail(h, HML_ERR_ARG, "len != T without a communicator");
+  return load_segment_common(h, x_dev, len, T, weight_multiplier);
+}
+
+int hml_load_segment_f32(hml_t* h, const float* x_host, uint64_t len, uint64_t T, float weight_multiplier) {
+  if (!h) return HML_ERR_ARG;
+  if (!x_host) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (len == 0) return fail(h, HML_ERR_ARG, "Input vector for breakpoint weights is empty!");
+  CK(cudaSetDevice(h->device));
+  float* xd = nullptr;
+  CK(dev_alloc(xd, len));
+  cudaError_t e = cudaMemcpyAsync(xd, x_host, len * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) {
+    dev_free(xd);
+    return fail(h, HML_ERR_CUDA, cudaGetErrorString(e));
+  }
+  const int rc = hml_load_segment_f32_device(h, xd, len, T, weight_multiplier);
+  cudaStreamSynchronize(h->stream);
+  dev_free(xd);
+  return rc;
+}
+
+int hml_segment_info(const hml_t* h, int* rank, int* world, uint64_t* seg_start, uint64_t* seg_len,
+                     uint64_t* first_block, uint64_t* global_blocks) {
+  if (!h) return HML_ERR_ARG;
+  if (rank) *rank = h->rank;
+  if (world) *world = h->world;
+  if (seg_start) *seg_start = h->seg_start;
+  if (seg_len) *seg_len = h->T;
+  if (first_block) *first_block = h->first_block;
+  if (global_blocks) *global_blocks = h->world > 1 ? h->global_blocks : h->nblocks;
   return HML_OK;
 }
 

@@ -12,6 +12,12 @@ void launch_maxlet_level(const float* in, uint64_t n_valid, uint64_t n_pos, uint
 void launch_bp_weights(const float* c, uint64_t T, float mult, float* w, int sms, cudaStream_t s);
 void launch_sum_odd(const float* c, uint64_t T, double* partial, int nblocks, cudaStream_t s);
 void launch_integral_cells(const float* x, uint64_t T, double2* pq, double2* cell_tot, cudaStream_t s);
+// segment mode (one sequence split over ranks): edge coefficients c[len - 2^k], k < 12, for the next rank
+void launch_pack_edge(const float* coeffs_local, uint64_t len, float* edge16, cudaStream_t s);
+// breakpoint weights of the local segment from local coefficients, the replicated table of the
+// coefficients at multiples of 4096 (ctop[m] = c[4096 m]) and the 12 edge coefficients of the previous rank
+void launch_bp_weights_segment(const float* c_local, const float* ctop, const float* halo, uint64_t seg_start,
+                               uint64_t len, uint64_t T, float mult, float* w, int sms, cudaStream_t s);
 
 // ---- boundary detection (hml_detect.cu)
 typedef void (*stage_cb_t)(void* user, const char* name);
@@ -29,7 +35,20 @@ struct ModelHost {  // what the C ABI receives, validated
 
 // Device buffers of one handle that the sweep kernels touch.  All per-block arrays are stored in
 // the chunk-interleaved order defined in hml_sweep.cu (Layout::perm).
+// Segment mode (world > 1): gathered carries of all ranks and this rank's send slots.
+struct SegInfo {
+  int rank, world;
+  const double* heads;   // world x 4: {blocks of the rank, head length, head sum x, head sum x^2}
+  const double* ops;     // world x (KP*KP + KP): segment operator mantissas (row-major) then row exponents
+  const uint64_t* maps;  // world x 4 words: segment map f_first o ... o f_last (byte-packed)
+  double* send_head;
+  double* send_op;
+  uint64_t* send_map;
+  unsigned long long* overflow;  // set if this rank's block arrays were too small
+};
+
 struct SweepBuffers {
+  SegInfo seg;
   // inputs resident since load
   const double2* pq;        // T+1 cell-local running sums of (x, x^2)
   const double4* cell_pref; // per cell: double-double exclusive prefix of cell totals (hi_x, lo_x, hi_q, lo_q)
@@ -77,7 +96,13 @@ struct SweepLaunch {
   uint64_t seed, sweep;
   int sms;
   uint64_t nblocks_hint;  // upper bound used to size grids (capacity if unknown)
+  // segment mode: all-gathers the named carry (send slot -> gathered array) on the stream; 0 on success
+  int (*exchange)(void* user, int which);
+  void* exchange_user;
 };
+enum { kExchangeHeads = 0, kExchangeOps = 1, kExchangeMaps = 2 };
+// segment mode: head partial of this rank -> seg.send_head (to be all-gathered before the block statistics)
+void launch_seg_head(const SweepBuffers& b, uint64_t seg_len, cudaStream_t s);
 
 // Enqueues all block-level kernels of one sweep on `s`; returns the number of kernels launched.
 // stage_cb(name) is called before each stage so the caller can drop timing events.

@@ -110,6 +110,45 @@ __global__ void __launch_bounds__(256) k_bp_weights(const float* __restrict__ c,
   }
 }
 
+// Segment mode.  Rank r holds the coefficients of its own observations; the closed form above reaches
+// outside the segment only (a) at multiples of 4096, whose coefficients belong to Haar levels above 12
+// and are derived by every rank from the all-gathered tile sums (ctop[m] = c[4096 m]), and (b) for the
+// first position of the segment, at seg_start - 2^k, k < 12, which the previous rank sends (halo[k]).
+__global__ void __launch_bounds__(256)
+    k_bp_weights_segment(const float* __restrict__ c_local, const float* __restrict__ ctop,
+                         const float* __restrict__ halo, uint64_t seg_start, uint64_t len, uint64_t T, float mult,
+                         float* __restrict__ w) {
+  const float inf = __int_as_float(0x7f800000);
+  auto coef = [&](uint64_t j) -> float {  // c'[j]: +inf if the wavelet's right end is not inside the sequence
+    const uint64_t h = 1ull << (__ffsll((long long)j) - 1);
+    if (!(j + h < T)) return inf;
+    if ((j & (uint64_t)(kTile - 1)) == 0) return ctop[j >> kTileLog2];
+    if (j >= seg_start) return c_local[j - seg_start];
+    return halo[__ffsll((long long)(seg_start - j)) - 1];
+  };
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t t = seg_start + i;
+    float v;
+    if (t == 0) {
+      v = inf;
+    } else {
+      const int z = __ffsll((long long)t) - 1;
+      v = coef(t);
+      for (int k = 0; k < z; ++k) {
+        const uint64_t d = 1ull << k;
+        v = fmaxf(v, coef(t - d));
+        if (t + d < T) v = fmaxf(v, coef(t + d));
+      }
+    }
+    w[i] = __fmul_rn(v, mult);
+  }
+}
+
+__global__ void k_pack_edge(const float* __restrict__ c_local, uint64_t len, float* __restrict__ edge16) {
+  const int k = threadIdx.x;
+  if (k < 16) edge16[k] = (k < kTileLog2 && len >= (1ull << k)) ? c_local[len - (1ull << k)] : 0.f;
+}
+
 // sum of coeffs[1], coeffs[3], ... in fp64; per-CTA partials, summed on the host.
 __global__ void __launch_bounds__(256) k_sum_odd(const float* __restrict__ c, uint64_t T, double* __restrict__ partial) {
   double s = 0.0;
@@ -196,6 +235,16 @@ void launch_bp_weights(const float* c, uint64_t T, float mult, float* w, int sms
   uint64_t blocks = (T + 255) / 256;
   if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
   k_bp_weights<<<(unsigned)blocks, 256, 0, s>>>(c, T, mult, w);
+}
+void launch_pack_edge(const float* coeffs_local, uint64_t len, float* edge16, cudaStream_t s) {
+  k_pack_edge<<<1, 32, 0, s>>>(coeffs_local, len, edge16);
+}
+void launch_bp_weights_segment(const float* c_local, const float* ctop, const float* halo, uint64_t seg_start,
+                               uint64_t len, uint64_t T, float mult, float* w, int sms, cudaStream_t s) {
+  uint64_t blocks = (len + 255) / 256;
+  if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
+  if (blocks == 0) return;
+  k_bp_weights_segment<<<(unsigned)blocks, 256, 0, s>>>(c_local, ctop, halo, seg_start, len, T, mult, w);
 }
 void launch_sum_odd(const float* c, uint64_t T, double* partial, int nblocks, cudaStream_t s) {
   k_sum_odd<<<nblocks, 256, 0, s>>>(c, T, partial);

@@ -83,7 +83,7 @@ HML_EXTERN(20) HML_EXTERN(32)
 int launch_sweep(const ModelHost& m, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s, stage_cb_t cb,
                  void* user) {
   const int KP = padded_states(m.K);
-  int n = -1;
+  int n = -2;  // unsupported number of states (-1: a carry exchange failed)
 #define CALL(X) n = sweep_impl<X>(m, b, l, s, cb, user)
   HML_DISPATCH_KP(KP, CALL)
 #undef CALL
@@ -104,6 +104,10 @@ void launch_unpermute(const SweepBuffers& b, int, uint64_t nblocks, int16_t* dst
   if (nblocks == 0) return;
   const int g = (int)((nblocks + 255) / 256 > 4096 ? 4096 : (nblocks + 255) / 256);
   k_unpermute<<<g, 256, 0, s>>>(b.states, b.bS, nblocks, dst_states, dst_sum, dst_sumsq);
+}
+
+void launch_seg_head(const SweepBuffers& b, uint64_t seg_len, cudaStream_t s) {
+  k_seg_head<<<1, 32, 0, s>>>(b, (uint32_t)seg_len);
 }
 
 void launch_block_stats(const SweepBuffers& b, int, uint64_t nblocks_hint, int sms, cudaStream_t s) {

@@ -283,6 +283,54 @@ __device__ __forceinline__ uint64_t device_nblocks(const unsigned long long* nb,
   return b <= capacity ? b : 0;
 }
 
+// ---- segment mode: what a rank derives from the all-gathered heads {blocks, head length, head sums}
+__device__ __forceinline__ uint64_t seg_first_block(const SegInfo& g) {  // global index of this rank's block 0
+  uint64_t o = 0;
+  for (int r = 0; r < g.rank; ++r) o += (uint64_t)g.heads[4 * r];
+  return o;
+}
+__device__ __forceinline__ uint64_t seg_global_blocks(const SegInfo& g, uint64_t local) {
+  if (g.world <= 1) return local;
+  uint64_t o = 0;
+  for (int r = 0; r < g.world; ++r) o += (uint64_t)g.heads[4 * r];
+  return o;
+}
+__device__ __forceinline__ bool seg_later_blocks(const SegInfo& g) {  // does any later rank own a block?
+  for (int r = g.rank + 1; r < g.world; ++r)
+    if (g.heads[4 * r] > 0.0) return true;
+  return false;
+}
+
+// (sum x, sum x^2) over the local observations [s, e) from the integral arrays
+// (Statistics/IntegralArray.hpp:104-124): cell-local running sums + double-double cell offsets
+__device__ __forceinline__ void range_sums(const SweepBuffers& buf, uint32_t s, uint32_t e, double& sx, double& sq) {
+  const double2 ps = buf.pq[s], pe = buf.pq[e];
+  sx = pe.x - ps.x;
+  sq = pe.y - ps.y;
+  const uint32_t cs = s >> kCellLog2, ce = e >> kCellLog2;
+  if (cs != ce) {
+    const double4 a = buf.cell_pref[cs], z = buf.cell_pref[ce];
+    sx += (z.x - a.x) + (z.y - a.y);
+    sq += (z.z - a.z) + (z.w - a.w);
+  }
+}
+
+// k_seg_head: the observations in front of this rank's first boundary belong to a block that starts on
+// an earlier rank; their partial statistics travel with the rank's block count.
+static __global__ void k_seg_head(SweepBuffers buf, uint32_t seg_len) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint64_t raw = *buf.nblocks;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  if (buf.seg.overflow) *buf.seg.overflow = raw > buf.capacity ? 1ull : 0ull;
+  const uint32_t e = B ? buf.starts[0] : seg_len;
+  double sx = 0.0, sq = 0.0;
+  if (e > 0) range_sums(buf, 0u, e, sx, sq);
+  buf.seg.send_head[0] = (double)B;
+  buf.seg.send_head[1] = (double)e;
+  buf.seg.send_head[2] = sx;
+  buf.seg.send_head[3] = sq;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_block_emit: thread per storage slot
 
@@ -297,16 +345,18 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
     double sx, sq;
     if (kGather) {
       const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
-      const double2 ps = buf.pq[s], pe = buf.pq[e];
-      sx = pe.x - ps.x;
-      sq = pe.y - ps.y;
-      const uint32_t cs = s >> kCellLog2, ce = e >> kCellLog2;
-      if (cs != ce) {
-        const double4 a = buf.cell_pref[cs], z = buf.cell_pref[ce];
-        sx += (z.x - a.x) + (z.y - a.y);
-        sq += (z.z - a.z) + (z.w - a.w);
-      }
+      range_sums(buf, s, e, sx, sq);
       n = e - s;
+      if (buf.seg.world > 1 && b + 1 == B) {
+        // the rank's last block continues on the following ranks up to their first boundary
+        for (int r = buf.seg.rank + 1; r < buf.seg.world; ++r) {
+          const double* hd = buf.seg.heads + 4 * r;
+          n += (uint32_t)hd[1];
+          sx += hd[2];
+          sq += hd[3];
+          if (hd[0] > 0.0) break;
+        }
+      }
       buf.bN[p] = n;
       buf.bS[p] = make_double2(sx, sq);
     } else {
@@ -459,12 +509,24 @@ struct ScanCfg {
   static constexpr bool SMEM = false;
 };
 
+// Segment mode splits the tile scan in two phases around the all-gather of the segment operators:
+//   kPhase 1  group operators (kept in global memory) and this rank's segment operator -> seg.send_op
+//   kPhase 2  forward vector entering the segment = pi * Op_0 * ... * Op_{rank-1} (normalised), then steps 2-3
+//   kPhase 0  everything in one launch (single handle)
+template <int KP>
+__device__ __forceinline__ void load_gathered_op(OpVals<KP>& o, const double* g) {
+#pragma unroll
+  for (int k = 0; k < KP * KP; ++k) o.m[k] = g[k];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) o.x[k] = (int)g[KP * KP + k];
+}
+
 // Small K (<= 8): 256 threads, every vector and operator in registers, operators prefetched one step
 // ahead of the dependent chain.  G groups of S consecutive tiles, G ~ sqrt(#tiles):
 //   step 1  thread (group, row): group operator = product of its S tile operators   -> shared memory
 //   step 2  thread 0: forward vector entering each group (G sequential operator applications)
 //   step 3  thread per group: forward vector entering each of its tiles
-template <int KP>
+template <int KP, int kPhase>
 __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, ModelDev<KP> m) {
   constexpr int GMAX = 256 / KP < 48 ? 256 / KP : 48;
   __shared__ double s_gain[GMAX][KP];
@@ -472,12 +534,15 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
   __shared__ int s_gexp[GMAX * KP];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
-  if (nt == 0) return;
-  int G = (int)ceil(sqrt((double)nt));
-  if (G > GMAX) G = GMAX;
-  const int S = (nt + G - 1) / G;
-  G = (nt + S - 1) / S;
-  {
+  int G = 0, S = 1;
+  if (nt > 0) {
+    G = (int)ceil(sqrt((double)nt));
+    if (G > GMAX) G = GMAX;
+    S = (nt + G - 1) / G;
+    G = (nt + S - 1) / S;
+  }
+  if (kPhase == 0 && nt == 0) return;
+  if (kPhase != 2) {
     const int g = threadIdx.x / KP, i = threadIdx.x % KP;
     if (g < G) {
       double r[KP];
@@ -497,13 +562,47 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
 #pragma unroll
       for (int j = 0; j < KP; ++j) s_gop[(g * KP + i) * KP + j] = r[j];
       s_gexp[g * KP + i] = rex;
+      if (kPhase == 1) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.group_ops[(g * KP + i) * KP + j] = r[j];
+        buf.group_exp[g * KP + i] = rex;
+      }
     }
+    __syncthreads();
+    if (kPhase == 1) {
+      // segment operator: row i of the ordered product of the group operators (identity without blocks)
+      if (threadIdx.x < KP) {
+        const int i = threadIdx.x;
+        double r[KP];
+        int rex = 0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) row_times_op<KP, false>(r, rex, s_gop + g * KP * KP, s_gexp + g * KP);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.seg.send_op[i * KP + j] = r[j];
+        buf.seg.send_op[KP * KP + i] = (double)rex;
+      }
+      return;
+    }
+  } else {
+    if (nt == 0) return;
+    for (int k = threadIdx.x; k < G * KP * KP; k += blockDim.x) s_gop[k] = buf.group_ops[k];
+    for (int k = threadIdx.x; k < G * KP; k += blockDim.x) s_gexp[k] = buf.group_exp[k];
+    __syncthreads();
   }
-  __syncthreads();
   if (threadIdx.x == 0) {
     double a[KP];
 #pragma unroll
     for (int j = 0; j < KP; ++j) a[j] = m.pi[j];  // row 0 of the trellis is pi itself (FB.hpp:57)
+    if (kPhase == 2) {
+#pragma unroll 1
+      for (int r = 0; r < buf.seg.rank; ++r) {
+        OpVals<KP> o;
+        load_gathered_op<KP>(o, buf.seg.ops + (size_t)r * (KP * KP + KP));
+        if (buf.seg.heads[4 * r] > 0.0 && !vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      }
+    }
 #pragma unroll 1
     for (int g = 0; g < G; ++g) {
 #pragma unroll
@@ -536,25 +635,26 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
   }
 }
 
-template <int KP>
+template <int KP, int kPhase>
 __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDev<KP> m) {
   constexpr int GMAX = ScanCfg<KP>::GMAX;
   __shared__ double s_gain[GMAX][KP];
-  __shared__ double s_gop[ScanCfg<KP>::SMEM ? GMAX * KP * KP : 1];
-  __shared__ int s_gexp[ScanCfg<KP>::SMEM ? GMAX * KP : 1];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
-  if (nt == 0) return;
-  int G = (int)ceil(sqrt((double)nt));
-  if (G > GMAX) G = GMAX;
-  if (G > 1024 / KP) G = 1024 / KP;
-  const int S = (nt + G - 1) / G;
-  G = (nt + S - 1) / S;
+  if (kPhase != 1 && nt == 0) return;
+  int G = 0, S = 1;
+  if (nt > 0) {
+    G = (int)ceil(sqrt((double)nt));
+    if (G > GMAX) G = GMAX;
+    if (G > 1024 / KP) G = 1024 / KP;
+    S = (nt + G - 1) / G;
+    G = (nt + S - 1) / S;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* gop = ScanCfg<KP>::SMEM ? s_gop : buf.group_ops;
-  int* gexp = ScanCfg<KP>::SMEM ? s_gexp : buf.group_exp;
+  double* gop = buf.group_ops;
+  int* gexp = buf.group_exp;
   // ---- step 1
-  {
+  if (kPhase != 2) {
     const int g = threadIdx.x / KP, i = threadIdx.x % KP;
     if (g < G) {
       double r[KP];
@@ -562,31 +662,46 @@ __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDe
 #pragma unroll
       for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
       const int t0 = g * S, t1 = min(nt, (g + 1) * S);
-      if (KP <= 8) {
-        OpVals<KP> cur, nxt;
-        load_op<KP>(cur, buf.tile_ops + (uint64_t)t0 * KP * KP, buf.tile_exp + (uint64_t)t0 * KP);
 #pragma unroll 1
-        for (int t = t0; t < t1; ++t) {
-          const int tn = (t + 1 < t1) ? t + 1 : t;
-          load_op<KP>(nxt, buf.tile_ops + (uint64_t)tn * KP * KP, buf.tile_exp + (uint64_t)tn * KP);
-          row_times_op<KP, false>(r, rex, cur.m, cur.x);
-          cur = nxt;
-        }
-      } else {
-#pragma unroll 1
-        for (int t = t0; t < t1; ++t)
-          row_times_op<KP, false>(r, rex, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
-      }
+      for (int t = t0; t < t1; ++t)
+        row_times_op<KP, false>(r, rex, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
 #pragma unroll
       for (int j = 0; j < KP; ++j) gop[(g * KP + i) * KP + j] = r[j];
       gexp[g * KP + i] = rex;
     }
+    __threadfence_block();
+    __syncthreads();
+    if (kPhase == 1) {
+      if (threadIdx.x < KP) {
+        const int i = threadIdx.x;
+        double r[KP];
+        int rex = 0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) row_times_op<KP, true>(r, rex, gop + g * KP * KP, gexp + g * KP);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.seg.send_op[i * KP + j] = r[j];
+        buf.seg.send_op[KP * KP + i] = (double)rex;
+      }
+      return;
+    }
   }
-  __threadfence_block();
-  __syncthreads();
   // ---- step 2
   if (warp == 0) {
     double a = lane < KP ? m.pi[lane] : 0.0;  // row 0 of the trellis is pi itself (FB.hpp:57)
+    if (kPhase == 2) {
+#pragma unroll 1
+      for (int r = 0; r < buf.seg.rank; ++r) {
+        const double* go = buf.seg.ops + (size_t)r * (KP * KP + KP);
+        LaneOp<KP> o;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) o.col[k] = lane < KP ? go[k * KP + lane] : 0.0;
+        o.x = lane < KP ? (int)go[KP * KP + lane] : kDeadExp;
+        if (buf.seg.heads[4 * r] > 0.0 && !warp_apply_op<KP>(a, o) && lane == 0)
+          atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      }
+    }
     LaneOp<KP> cur, nxt;
     load_lane_op<KP>(cur, gop, gexp, lane);
 #pragma unroll 1
@@ -716,14 +831,16 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
 // Sequential forward recursion (one thread): the exact reference recursion, used only when the
 // parallel pass reported a uniform fallback, whose effect on later blocks the operator products
 // cannot express.
+// Segment mode: ranks run it one after the other; `ain` is the final vector of the previous rank and
+// the rank's own final vector goes to seg.send_op[0..KP) for the next one.
 template <int KP, bool kLoglik>
-__global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDev<KP> m) {
+__global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDev<KP> m, const double* ain) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int K = m.K;
   double a[KP];
 #pragma unroll
-  for (int j = 0; j < KP; ++j) a[j] = m.pi[j];
+  for (int j = 0; j < KP; ++j) a[j] = ain ? ain[j] : m.pi[j];
   double ll = 0.0;
   unsigned long long fallbacks = 0;
   for (uint64_t b = 0; b < B; ++b) {
@@ -757,6 +874,10 @@ __global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDe
   }
   if (kLoglik) buf.partials[0] = ll;
   buf.out_u64[KP + KP * KP] = fallbacks;
+  if (buf.seg.world > 1) {
+#pragma unroll
+    for (int j = 0; j < KP; ++j) buf.seg.send_op[j] = a[j];
+  }
 }
 
 // k_bwd_maps: thread per block.  Given alpha_t, everything the backward pass will do at block t is a
@@ -772,7 +893,8 @@ __global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP>
     const uint64_t b = Layout::inv(p);
     Map<KP> fm = Map<KP>::identity();  // slots past the last block compose as the identity
     if (b < B) {
-      const bool last = (b + 1 == B);
+      const bool last = (b + 1 == B) && !(buf.seg.world > 1 && seg_later_blocks(buf.seg));
+      const uint64_t gb = buf.seg.world > 1 ? seg_first_block(buf.seg) + b : b;  // global block index
       double ap[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
@@ -784,7 +906,8 @@ __global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP>
           for (int j = 0; j < K; ++j) buf.rows[j] = m.pi[j];
         for (int j = 0; j < K; ++j) buf.rows[(b + 1) * K + j] = ap[j];
       }
-      const double u = buf.replay_u ? buf.replay_u[B - 1 - b] : Philox::uniform(seed, sweep, 0u, b);
+      const double u = buf.replay_u ? buf.replay_u[seg_global_blocks(buf.seg, B) - 1 - gb]
+                                    : Philox::uniform(seed, sweep, 0u, gb);
       fm = Map<KP>::zero();
       if (last) {
         const uint32_t q = discrete_draw<KP>(ap, K, u);
@@ -842,13 +965,23 @@ __global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf) {
 // tile_qin[t] = state of the first block after tile t (irrelevant for the last tile, whose last block
 // carries a constant map).
 
-template <int KP>
+// kSegMap: only the composed map of the whole segment is wanted (-> seg.send_map, identity without
+// blocks); otherwise the state following the segment comes from the gathered maps of the later ranks
+// (the last block of the sequence carries a constant map, so the start value is irrelevant).
+template <int KP, bool kSegMap>
 __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
   constexpr int MB = 8 * Map<KP>::W;
   __shared__ uint64_t s_w[32][Map<KP>::W];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int64_t nt = (int64_t)((B + Layout::TB - 1) / Layout::TB);
-  if (nt == 0) return;
+  if (nt == 0) {
+    if (kSegMap && threadIdx.x == 0) {
+      const Map<KP> id = Map<KP>::identity();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? id.w[i] : 0ull;
+    }
+    return;
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t per = (nt + 1023) / 1024;
   // thread `tid` owns tiles [lo, hi); threads are ordered by position, so thread 0 holds the earliest
@@ -869,6 +1002,27 @@ __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
     for (int i = 0; i < Map<KP>::W; ++i) s_w[warp][i] = inc.w[i];
   }
   __syncthreads();
+  if (kSegMap) {
+    if (tid == 0) {
+      Map<KP> tot = Map<KP>::identity();
+      for (int wv = 0; wv < 32; ++wv) {
+        Map<KP> o;
+#pragma unroll
+        for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = s_w[wv][i];
+        tot = tot.after(o);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? tot.w[i] : 0ull;
+    }
+    return;
+  }
+  uint32_t q_end = 0;
+  for (int r = buf.seg.world - 1; r > buf.seg.rank; --r) {
+    Map<KP> o;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = buf.seg.maps[4 * r + i];
+    q_end = o.get(q_end);
+  }
   Map<KP> after_warp = Map<KP>::identity();  // map of everything after this warp
   for (int wv = warp + 1; wv < 32; ++wv) {
     Map<KP> o;
@@ -880,8 +1034,8 @@ __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
 #pragma unroll
   for (int i = 0; i < Map<KP>::W; ++i) nxt.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
   const Map<KP> suf = (lane == 31) ? after_warp : nxt.after(after_warp);
-  // the suffix map is constant in its argument because the last block's map is constant
-  uint32_t q = suf.get(0);
+  // on the rank holding the sequence's last block the suffix map is constant in its argument
+  uint32_t q = suf.get(q_end);
   for (int64_t t = hi - 1; t >= lo; --t) {
     buf.tile_qin[t] = (uint8_t)q;
     q = Map<KP>::load(buf.tile_maps + t * MB).get(q);
@@ -915,6 +1069,7 @@ __global__ void __launch_bounds__(128) k_bwd_replay(SweepBuffers buf) {
 template <int KP>
 __global__ void __launch_bounds__(256) k_mix_sample(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t first = buf.seg.world > 1 ? seg_first_block(buf.seg) : 0;
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = Layout::inv(p);
@@ -922,7 +1077,8 @@ __global__ void __launch_bounds__(256) k_mix_sample(SweepBuffers buf, ModelDev<K
     double w[KP];
 #pragma unroll
     for (int s = 0; s < KP; ++s) w[s] = buf.e[p * KP + s];
-    const double u = buf.replay_u ? buf.replay_u[b] : Philox::uniform(seed, sweep, 1u, b);
+    const uint64_t gb = buf.seg.world > 1 ? first + b : b;  // global block index
+    const double u = buf.replay_u ? buf.replay_u[gb] : Philox::uniform(seed, sweep, 1u, gb);
     buf.states[p] = (uint8_t)discrete_draw<KP>(w, m.K, u);
   }
 }
@@ -950,14 +1106,31 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
     ax[s] = aq[s] = 0.0;
     an[s] = ad[s] = 0;
   }
+  // Transitions are counted at their source block: (q_b -> q_{b+1}) for every block that has a successor
+  // anywhere in the sequence, plus the phantom 0 -> q_0 of the first block (FB.hpp:177,182-184).  In
+  // segment mode the successor of a rank's last block is the state following the segment.
+  const bool seg = buf.seg.world > 1;
+  const bool has_after = seg && seg_later_blocks(buf.seg);
+  const bool first_rank = !seg || buf.seg.rank == 0;
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = Layout::inv(p);
     if (b >= B) continue;
     const uint32_t st = buf.states[p];
-    const uint32_t prev = b == 0 ? 0u : buf.states[Layout::perm(b - 1)];  // phantom 0 -> q0 (FB.hpp:177,183)
+    const bool has_next = (b + 1 < B) || has_after;
+    uint32_t next = st;
+    if (b + 1 < B)
+      next = buf.states[Layout::perm(b + 1)];
+    else if (has_after)
+      next = buf.tile_qin[(B - 1) / Layout::TB];
     const uint32_t n = buf.bN[p];
     const double2 v = buf.bS[p];
-    const unsigned long long dg = (unsigned long long)(n - 1) + (prev == st ? 1ull : 0ull);  // FB.hpp:182-183
+    unsigned long long dg = (unsigned long long)(n - 1) + ((has_next && next == st) ? 1ull : 0ull);
+    if (b == 0 && first_rank) {
+      if (st == 0u)
+        dg += 1ull;
+      else
+        atomicAdd(&s_trans[st], 1ull);  // row 0, column st
+    }
 #pragma unroll
     for (int s = 0; s < KP; ++s) {
       const bool hit = st == (uint32_t)s;
@@ -966,7 +1139,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
       an[s] += hit ? (unsigned long long)n : 0ull;
       ad[s] += hit ? dg : 0ull;
     }
-    if (prev != st) atomicAdd(&s_trans[prev * KP + st], 1ull);  // state changes are rare: low contention
+    if (has_next && next != st) atomicAdd(&s_trans[st * KP + next], 1ull);  // state changes are rare: low contention
   }
 #pragma unroll
   for (int s = 0; s < KP; ++s) {
@@ -1040,12 +1213,50 @@ inline int grid_for(uint64_t items, int threads, int sms, int per_sm) {
   return (int)g;
 }
 
+// Mixture sampler in segment mode: the "map" a rank publishes is the constant map onto the state of its
+// first block (identity without blocks), so the same resolution over later ranks yields the state of the
+// next block of the sequence.
 template <int KP>
-void launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, cudaStream_t s) {
-  if constexpr (KP <= 8)
-    k_fwd_tilescan_small<KP><<<1, 256, 0, s>>>(b, m);
-  else
-    k_fwd_tilescan<KP><<<1, 1024, 0, s>>>(b, m);
+__global__ void k_mix_segmap(SweepBuffers buf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  Map<KP> mp = Map<KP>::identity();
+  if (B > 0) {
+    const uint32_t q = buf.states[Layout::perm(0)];
+    mp = Map<KP>::zero();
+#pragma unroll
+    for (int j = 0; j < KP; ++j) mp.set(j, q);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? mp.w[i] : 0ull;
+}
+template <int KP>
+__global__ void k_mix_qend(SweepBuffers buf) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  if (B == 0) return;
+  uint32_t q_end = 0;
+  for (int r = buf.seg.world - 1; r > buf.seg.rank; --r) {
+    Map<KP> o;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = buf.seg.maps[4 * r + i];
+    q_end = o.get(q_end);
+  }
+  buf.tile_qin[(B - 1) / Layout::TB] = (uint8_t)q_end;
+}
+
+// phase 0: single handle; 1 / 2: before / after the all-gather of the segment operators
+template <int KP>
+void launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, int phase, cudaStream_t s) {
+  if constexpr (KP <= 8) {
+    if (phase == 0) k_fwd_tilescan_small<KP, 0><<<1, 256, 0, s>>>(b, m);
+    if (phase == 1) k_fwd_tilescan_small<KP, 1><<<1, 256, 0, s>>>(b, m);
+    if (phase == 2) k_fwd_tilescan_small<KP, 2><<<1, 256, 0, s>>>(b, m);
+  } else {
+    if (phase == 0) k_fwd_tilescan<KP, 0><<<1, 1024, 0, s>>>(b, m);
+    if (phase == 1) k_fwd_tilescan<KP, 1><<<1, 1024, 0, s>>>(b, m);
+    if (phase == 2) k_fwd_tilescan<KP, 2><<<1, 1024, 0, s>>>(b, m);
+  }
 }
 
 // maps -> chunk/tile maps -> suffix scan over tiles -> states; returns the number of launches
@@ -1053,6 +1264,7 @@ template <int KP>
 int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLaunch& l, bool rows, uint64_t nb,
                     cudaStream_t s, stage_cb_t cb, void* user) {
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
+  int launches = 4;
   if (cb) cb(user, "bwd_maps");
   const int gm = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
   if (rows)
@@ -1061,11 +1273,18 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
     k_bwd_maps<KP, false><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
   if (cb) cb(user, "bwd_chunkmaps");
   k_bwd_chunkmaps<KP><<<grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s>>>(b);
+  if (b.seg.world > 1) {
+    if (cb) cb(user, "bwd_segmap");
+    k_bwd_scan<KP, true><<<1, 1024, 0, s>>>(b);
+    ++launches;
+    if (cb) cb(user, "exchange_maps");
+    if (l.exchange(l.exchange_user, kExchangeMaps) != 0) return -1;
+  }
   if (cb) cb(user, "bwd_scan");
-  k_bwd_scan<KP><<<1, 1024, 0, s>>>(b);
+  k_bwd_scan<KP, false><<<1, 1024, 0, s>>>(b);
   if (cb) cb(user, "bwd_replay");
   k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
-  return 4;
+  return launches;
 }
 
 template <int KP>
@@ -1083,6 +1302,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   const ModelDev<KP> m = make_model<KP>(mh);
   const bool loglik = (l.flags & HML_SWEEP_LOGLIK) != 0;
   const bool rows = (l.flags & HML_SWEEP_KEEP_ROWS) != 0 && b.rows != nullptr;
+  const bool seg = b.seg.world > 1;
   const uint64_t nb = l.nblocks_hint;
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
   int launches = 0;
@@ -1112,12 +1332,28 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     stage("mix_sample");
     k_mix_sample<KP><<<grid_for(ntiles * Layout::TB, 256, l.sms, 32), 256, 0, s>>>(b, m, l.seed, l.sweep);
     ++launches;
+    if (seg) {
+      k_mix_segmap<KP><<<1, 32, 0, s>>>(b);
+      stage("exchange_maps");
+      if (l.exchange(l.exchange_user, kExchangeMaps) != 0) return -1;
+      k_mix_qend<KP><<<1, 32, 0, s>>>(b);
+      launches += 2;
+    }
   } else {
     stage("fwd_chunks");
     k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
     ++launches;
     stage("fwd_tilescan");
-    launch_fwd_tilescan<KP>(b, m, s);
+    if (seg) {
+      launch_fwd_tilescan<KP>(b, m, 1, s);
+      stage("exchange_ops");
+      if (l.exchange(l.exchange_user, kExchangeOps) != 0) return -1;
+      stage("fwd_tilescan2");
+      launch_fwd_tilescan<KP>(b, m, 2, s);
+      ++launches;
+    } else {
+      launch_fwd_tilescan<KP>(b, m, 0, s);
+    }
     ++launches;
     stage("fwd_replay");
     const int gr = grid_for(ntiles, 1, l.sms, 32);
@@ -1129,7 +1365,9 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       k_fwd_replay<KP, false><<<gr, 32, 0, s>>>(b, m);
     }
     ++launches;
-    launches += launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
+    const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
+    if (nbw < 0) return -1;
+    launches += nbw;
   }
   stage("reduce");
   launches += launch_reduce<KP>(b, mh.K, nb, l.sms, s);
@@ -1137,6 +1375,8 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   return launches;
 }
 
+// Exact sequential forward pass.  In segment mode the ranks take turns: rank r starts from the final
+// vector of rank r-1, which travels through the operator slots of the all-gather.
 template <int KP>
 int sequential_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s) {
   const ModelDev<KP> m = make_model<KP>(mh);
@@ -1145,15 +1385,24 @@ int sequential_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunc
   const uint64_t nb = l.nblocks_hint;
   int launches = 1;
   k_clear_out<KP><<<1, 256, 0, s>>>(b);
-  if (loglik) {
-    k_fwd_sequential<KP, true><<<1, 32, 0, s>>>(b, m);
-    k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, 1, b.out_f64 + 2 * KP);
-    launches += 2;
-  } else {
-    k_fwd_sequential<KP, false><<<1, 32, 0, s>>>(b, m);
-    launches += 1;
+  const int world = b.seg.world > 1 ? b.seg.world : 1;
+  for (int turn = 0; turn < world; ++turn) {
+    if (turn == (world > 1 ? b.seg.rank : 0)) {
+      const double* ain = turn == 0 ? nullptr : b.seg.ops + (size_t)(turn - 1) * (KP * KP + KP);
+      if (loglik) {
+        k_fwd_sequential<KP, true><<<1, 32, 0, s>>>(b, m, ain);
+        k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, 1, b.out_f64 + 2 * KP);
+        launches += 2;
+      } else {
+        k_fwd_sequential<KP, false><<<1, 32, 0, s>>>(b, m, ain);
+        launches += 1;
+      }
+    }
+    if (world > 1 && l.exchange(l.exchange_user, kExchangeOps) != 0) return -1;
   }
-  launches += launch_backward<KP>(b, m, l, rows, nb, s, nullptr, nullptr);
+  const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, nullptr, nullptr);
+  if (nbw < 0) return -1;
+  launches += nbw;
   launches += launch_reduce<KP>(b, mh.K, nb, l.sms, s);
   return launches;
 }

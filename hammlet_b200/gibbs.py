@@ -14,12 +14,22 @@ from . import capi
 F = np.float32
 
 
-def auto_prior(handle, s2=0.2, p=0.9):
-    """AutoPriors.hpp:18-110 on device-computed block sums: blocks at (float)(sqrt(2 log T) sigma_hat)."""
+def auto_prior(handle, s2=0.2, p=0.9, allgather=None):
+    """AutoPriors.hpp:18-110 on device-computed block sums: blocks at (float)(sqrt(2 log T) sigma_hat).
+
+    Segment mode (one sequence split over ranks): `allgather(obj) -> [obj of rank 0, ...]` collects the
+    per-rank block lists, so that every rank accumulates the block means of the whole sequence in the
+    reference's order and arrives at the same hyper-parameters."""
     T = handle.T
     thr = F(np.sqrt(2.0 * np.log(float(T))) * handle.sigma_hat())
     handle.create_blocks(float(thr))
     starts, s, _ = handle.blocks()
+    if getattr(handle, "world", 1) > 1:
+        if allgather is None:
+            raise ValueError("auto_prior on a segment-split sequence needs an allgather callable")
+        parts = allgather((starts, s))
+        starts = np.concatenate([q[0] for q in parts])
+        s = np.concatenate([q[1] for q in parts])
     n = np.diff(np.append(starts.astype(np.int64), T))
     m = (s.astype(F) / n.astype(F)).astype(F)
     # SufficientStatistics.hpp:88-91 accumulates in real_t, sequentially

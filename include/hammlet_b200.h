@@ -133,6 +133,38 @@ int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t*
  * ForwardBackward.hpp:115-119). */
 int hml_get_rows(hml_t* h, double* rows, uint64_t capacity_rows);
 
+/* ---- multi-GPU: one sequence split into contiguous segments -----------------
+ *
+ * The reference is single-process; this mode has no counterpart there.  One handle (one process,
+ * one GPU) per rank; rank r owns the observations [start_r, start_r + len_r) given by
+ * hml_segment_plan (segments are aligned to 4096 observations).  A block belongs to the rank where
+ * it starts.  Collectives are NCCL all-gathers of a few hundred bytes on the handle's stream:
+ * at load the per-tile Haar sums (so every rank derives the top levels of the transform) and the
+ * edge coefficients; per sweep (i) the partial block in front of each rank's first boundary,
+ * (ii) one KxK forward operator per rank, (iii) one K->K backward map per rank, (iv) the per-rank
+ * statistics, which every rank sums in rank order.  Every rank must make the same sequence of
+ * calls with the same model, threshold, seed and flags; all ranks then return identical
+ * hml_sweep_out contents (so host-side parameter draws stay in lock-step), identical to what a
+ * single handle holding the whole sequence returns (counts, states) or within fp64 rounding
+ * (sums, log-likelihood).  Independent sequences need none of this: use one handle each. */
+
+#define HML_UNIQUE_ID_BYTES 128
+/* rank 0 creates the id, the caller distributes it (torch.distributed, MPI, a file, ...). */
+int hml_comm_unique_id(uint8_t id[HML_UNIQUE_ID_BYTES]);
+/* Joins the communicator (collective over all ranks).  libnccl.so.2 is loaded at this point. */
+int hml_comm_init(hml_t* h, int rank, int world, const uint8_t id[HML_UNIQUE_ID_BYTES]);
+/* Observations of rank `rank` for a sequence of T observations; fails if T < 4096 * world. */
+int hml_segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t* len);
+/* Collective load: x holds this rank's observations [start, start+len) per hml_segment_plan
+ * (host or device memory respectively); T is the length of the whole sequence. */
+int hml_load_segment_f32(hml_t* h, const float* x_host, uint64_t len, uint64_t T, float weight_multiplier);
+int hml_load_segment_f32_device(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float weight_multiplier);
+/* After a sweep in segment mode: this rank's first global block index and the global block count
+ * (hml_sweep_out.nblocks is the global count; hml_nr_blocks / hml_get_* stay rank-local, with
+ * block starts reported as global positions). */
+int hml_segment_info(const hml_t* h, int* rank, int* world, uint64_t* seg_start, uint64_t* seg_len,
+                     uint64_t* first_block, uint64_t* global_blocks);
+
 /* ---- measurement ---------------------------------------------------------------------------- */
 
 /* With timing on, every kernel stage of a sweep is bracketed by CUDA events on the context's

@@ -1,0 +1,28 @@
+"""Segment-split mode on real GPUs: one process per GPU under torchrun, checked against a
+single handle holding the whole sequence (tests/mgpu_worker.py).  Needs >= 2 GPUs; the 1-GPU box skips it."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_segment_split_matches_single_handle(world):
+    if _gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "MGPU WORKER OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
