@@ -51,16 +51,22 @@ def gen_chunk(torch, n, K, L, gen, carry_state, device):
     return x, int(st[-1].item())
 
 
-def generate(torch, T, K, L, seed, device, limit=None):
+def generate(torch, T, K, L, seed, device, limit=None, keep=None):
+    """The first min(T, limit) observations of the sequence, or — keep=(start, n) — only that slice of it (every
+    rank of a segment-split run walks the same generator stream and keeps its own segment)."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     n_total = T if limit is None else min(T, limit)
-    x = torch.empty(n_total, dtype=torch.float32, device=device)
+    k0, kn = keep if keep is not None else (0, n_total)
+    n_total = min(n_total, k0 + kn)
+    x = torch.empty(kn, dtype=torch.float32, device=device)
     chunk, done, carry = 1 << 26, 0, seed % K
     while done < n_total:
-        n = min(chunk, n_total - done)
+        n = min(chunk, T - done)         # chunk sizes depend on T only, so every slice sees the same stream
         xc, carry = gen_chunk(torch, n, K, L, gen, carry, device)
-        x[done:done + n] = xc
+        lo, hi = max(done, k0), min(done + n, k0 + kn)
+        if lo < hi:
+            x[lo - k0:hi - k0] = xc[lo - done:hi - done]
         done += n
     return x
 
@@ -140,6 +146,9 @@ def main():
     ap.add_argument("--L", type=int, default=5000)
     ap.add_argument("--sample", type=float, default=1e7, help="observations of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="segments", choices=["segments", "independent"],
+                    help="N > 1: one sequence split into contiguous segments with NCCL carry exchange (strong scaling, "
+                         "BASELINE configs[3]) or one independent sequence per GPU (weak scaling, no collective)")
     args = ap.parse_args()
     T, K, L = int(args.T), args.K, args.L
     steps, warmup = args.steps, max(args.warmup, 3)
@@ -190,26 +199,45 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
 
+    segments = world > 1 and args.mode == "segments"
     t0 = time.time()
-    x = generate(torch, T, K, L, seed=4 + rank, device=device)
-    torch.cuda.synchronize()
-    sample_host = x[:int(min(args.sample, T))].cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
     h = capi.Handle(local_rank)
-    h.load_device(x.data_ptr(), T)
+    if segments:
+        # one sequence, contiguous segments: every rank keeps its slice of the same generator stream
+        uid = [capi.Handle.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, 0)
+        h.comm_init(rank, world, uid[0])
+        seg_start, seg_len = capi.Handle.segment_plan(T, world, rank)
+        x = generate(torch, T, K, L, seed=4, device=device, keep=(seg_start, seg_len))
+        torch.cuda.synchronize()
+        sample_host = x[:int(min(args.sample, seg_len))].cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
+        h.load_segment_device(x.data_ptr(), seg_len, T)
+        T_local = seg_len
+    else:
+        x = generate(torch, T, K, L, seed=4 + rank, device=device)
+        torch.cuda.synchronize()
+        sample_host = x[:int(min(args.sample, T))].cpu().numpy() if (rank == 0 and not args.no_cpu_baseline) else None
+        h.load_device(x.data_ptr(), T)
+        T_local = T
     del x
     torch.cuda.empty_cache()
     t_load = time.time() - t0
-    log(f"[rank {rank}] generated + loaded T={T} in {t_load:.1f}s, sigma_hat={h.sigma_hat():.4f}")
+    log(f"[rank {rank}] generated + loaded {T_local} of T={T} in {t_load:.1f}s, sigma_hat={h.sigma_hat():.4f}")
 
-    tau = gibbs.auto_prior(h, 0.2, 0.9)
-    st = gibbs.GibbsState(K, tau, seed=100 + rank)
+    def allgather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    # The chain is the C++ host side (include/hammlet_host.h): sampleHMM, conjugate updates and parameter draws
+    # in C++ with libstdc++ <random> like the reference; Python only starts and stops the clock.
+    tau = gibbs.auto_prior(h, 0.2, 0.9, allgather=allgather) if segments else capi.Chain.auto_prior(h, 0.2, 0.9)
+    # segment mode: every rank draws the same parameters from the same (all-gathered) statistics
+    chain = capi.Chain(h, K, tau, trans=0.5, self_trans=0.5, alpha_pi=0.5, seed=100 if segments else 100 + rank)
     # start near the generating model so that the warm-up sweeps reach the stationary compression ratio quickly
-    st.mean = ((np.arange(K) - (K - 1) / 2.0) * SPACING).astype(np.float32)
-    st.var = np.full(K, SIGMA * SIGMA, np.float32)
-    st.A = (np.full((K, K), 0.0002 / (K - 1)) + np.eye(K) * (0.9998 - 0.0002 / (K - 1))).astype(np.float32)
-    st.pi = np.full(K, 1.0 / K, np.float32)
-
-    h.set_timing(True)
+    chain.set(((np.arange(K) - (K - 1) / 2.0) * SPACING).astype(np.float32), np.full(K, SIGMA * SIGMA, np.float32),
+              (np.full((K, K), 0.0002 / (K - 1)) + np.eye(K) * (0.9998 - 0.0002 / (K - 1))).astype(np.float32),
+              np.full(K, 1.0 / K, np.float32))
     stream = torch.cuda.ExternalStream(h.stream(), device=device)
 
     def barrier():
@@ -217,36 +245,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    gibbs.sample_hmm(h, st, warmup, seed=7, sweep0=0)
-    blocks_warm = h.nr_blocks()
+    chain.run(warmup)
 
     # ---- timed region 1: device clock (CUDA events on the library's stream), K steps
     sampler = ClockSampler(local_rank)
     sampler.start()
-    stage_ms = {}
-    nblocks = []
     launches0 = h.launch_count()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for i in range(steps):
-        out = gibbs.sample_hmm(h, st, 1, seed=7, sweep0=warmup + i)
-        nblocks.append(out["nblocks"])
-        for name, ms in h.timing():
-            stage_ms.setdefault(name, []).append(ms)
+    chain.run(steps)
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = h.launch_count() - launches0
 
-    # ---- timed region 2: end to end (wall clock around the public call; host buffers in and out)
+    # ---- timed region 2: end to end (wall clock around the public call; host buffers in and out every sweep)
     barrier()
     w0 = time.perf_counter()
-    for i in range(steps):
-        gibbs.sample_hmm(h, st, 1, seed=7, sweep0=warmup + steps + i)
+    chain.run(steps)
     torch.cuda.synchronize()
     wall = time.perf_counter() - w0
     clocks = sampler.stop()
+
+    # ---- region 3 (not part of `value`): the same steps with per-stage CUDA events, for the roofline and stage table
+    h.set_timing(True)
+    stage_ms, nblocks = {}, []
+    for i in range(steps):
+        nblocks.append(chain.run(1))
+        for name, ms in h.timing():
+            stage_ms.setdefault(name, []).append(ms)
+    h.set_timing(False)
 
     if dist is not None:
         t = torch.tensor([dev_ms, wall * 1000.0], device=device, dtype=torch.float64)
@@ -259,24 +288,33 @@ def main():
         return
 
     ms_per_step = dev_ms / steps
-    value = world * steps / (dev_ms / 1000.0)
-    e2e = world * steps / wall
-    B = float(np.mean(nblocks))
+    jobs = 1 if segments else world      # sequences swept per step by the whole job
+    value = jobs * steps / (dev_ms / 1000.0)
+    e2e = jobs * steps / wall
+    B = float(np.mean(nblocks))          # blocks of one whole sequence
     peak, peak_src = measured_peak()
     det = float(np.mean(stage_ms.get("detect_flags", [float("nan")])))
-    alg_bytes = 4.0 * T + 4.0 * B        # fp32 weight stream + uint32 block starts
+    # roofline kernel on rank 0: fp32 weight stream of the rank's observations + uint32 block starts
+    alg_bytes = 4.0 * T_local + 4.0 * B * T_local / T
     achieved = alg_bytes / (det * 1e-3) / 1e9
     busy = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     h2d = 8 * (2 * K + K * K + K)        # mean, var, A, pi as doubles (kernel parameters built from host buffers)
-    d2h = 8 * (2 + K + K * K + 2 + 2 * K + 1)
+    d2h = 8 * (2 + K + K * K + 2 + 2 * K + 1) * (world if segments else 1)
+    if world == 1:
+        wl = workload
+    elif segments:
+        wl = f"{workload}; split into {world} contiguous segments, one per GPU, scan carries exchanged with NCCL all-gathers"
+    else:
+        wl = f"{world} independent sequences, one per GPU, each: " + workload
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload if world == 1 else f"{world} independent sequences, one per GPU, each: " + workload,
-                   "states": K, "observations": T, "blocks_per_sweep": B, "compression_ratio": T / B,
-                   "l2_policy": "inputs larger than L2 (4 GB weight stream per sweep vs 126 MB L2)",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if segments else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl, "mode": "segments" if segments else ("independent" if world > 1 else "single"),
+                   "states": K, "observations": T, "observations_per_gpu": T_local, "blocks_per_sweep": B,
+                   "compression_ratio": T / B,
+                   "l2_policy": f"inputs larger than L2 ({4.0 * T_local / 1e9:.2f} GB weight stream per GPU and sweep vs 126 MB L2)",
                    "load_seconds": t_load},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
@@ -285,7 +323,8 @@ def main():
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": det,
                      "sweep_bytes": 4.0 * T + B * (4 + 16 + 16 * K + 2),
-                     "sweep_frac_of_hbm_roofline": (4.0 * T + B * (4 + 16 + 16 * K + 2)) / peak / 1e9 / (ms_per_step * 1e-3)},
+                     "sweep_frac_of_hbm_roofline": (4.0 * T + B * (4 + 16 + 16 * K + 2)) / (world if segments else 1)
+                                                   / peak / 1e9 / (ms_per_step * 1e-3)},
         "stage_ms": busy,
         "device_busy_ms_per_step": float(sum(busy.values())),
     }

@@ -37,7 +37,10 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
            "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream",
            "hml_comm_unique_id", "hml_comm_init", "hml_segment_plan", "hml_load_segment_f32",
-           "hml_load_segment_f32_device", "hml_segment_info"]
+           "hml_load_segment_f32_device", "hml_segment_info",
+           # include/hammlet_host.h
+           "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
+           "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -53,6 +56,10 @@ def load_library():
         lib.hml_last_error.restype = C.c_char_p
         lib.hml_last_error.argtypes = [C.c_void_p]
         lib.hml_version.restype = C.c_char_p
+        lib.hammlet_chain_error.restype = C.c_char_p
+        lib.hammlet_chain_error.argtypes = [C.c_void_p]
+        lib.hammlet_chain_destroy.argtypes = [C.c_void_p]
+        lib.hammlet_chain_destroy.restype = None
         for name in EXPORTS:
             getattr(lib, name)  # every declared symbol must be exported
         _lib = lib
@@ -247,6 +254,59 @@ class Handle:
         p = C.c_void_p()
         self._ck(self.lib.hml_get_stream(self.h, C.byref(p)))
         return p.value
+
+
+class Chain:
+    """The C++ host side's Gibbs chain (include/hammlet_host.h): theta, A, pi, conjugates and the shared
+    mt19937 of main.cpp, driven by sampleHMM (HMM.hpp:99-121) in C++ — no Python in the sweep loop."""
+
+    def __init__(self, handle, K, prior, trans=0.5, self_trans=0.5, alpha_pi=0.5, seed=0):
+        self.lib, self.handle, self.K = handle.lib, handle, K
+        self.c = C.c_void_p()
+        pr = (C.c_float * 4)(*[float(v) for v in prior])
+        rc = self.lib.hammlet_chain_create(C.byref(self.c), handle.h, C.c_int(K), pr, C.c_float(trans),
+                                           C.c_float(self_trans), C.c_float(alpha_pi), C.c_uint32(seed))
+        if rc != 0:
+            raise HmlError(rc, self.lib.hammlet_chain_error(None).decode())
+
+    @staticmethod
+    def auto_prior(handle, s2=0.2, p=0.9):
+        out = (C.c_float * 4)()
+        rc = handle.lib.hammlet_auto_prior(handle.h, C.c_float(s2), C.c_float(p), out)
+        if rc != 0:
+            raise HmlError(rc, handle.lib.hammlet_chain_error(None).decode())
+        return np.array(list(out), dtype=np.float32)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HmlError(rc, self.lib.hammlet_chain_error(self.c).decode())
+
+    def get(self):
+        K = self.K
+        mean, var, A, pi = (np.empty(n, np.float32) for n in (K, K, K * K, K))
+        self._ck(self.lib.hammlet_chain_get(self.c, _ptr(mean), _ptr(var), _ptr(A), _ptr(pi)))
+        return mean, var, A.reshape(K, K), pi
+
+    def set(self, mean, var, A, pi):
+        a = [np.ascontiguousarray(v, np.float32) for v in (mean, var, A, pi)]
+        self._ck(self.lib.hammlet_chain_set(self.c, *[_ptr(v) for v in a]))
+
+    def run(self, iterations, method="F", dynamic=True, use_self=True):
+        nb = C.c_uint64()
+        self._ck(self.lib.hammlet_chain_run(self.c, C.c_char(method.encode()), C.c_uint64(iterations), C.c_int(int(dynamic)),
+                                            C.c_int(int(use_self)), C.byref(nb)))
+        return nb.value
+
+    def close(self):
+        if self.c:
+            self.lib.hammlet_chain_destroy(self.c)
+            self.c = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def philox_uniform(seed, sweep, stream, index):

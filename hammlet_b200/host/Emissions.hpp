@@ -21,6 +21,7 @@
 // Thin RAII owner of an hml_t; every C-ABI failure becomes std::runtime_error, like every reference error.
 class DeviceSequence {
   hml_t* mHandle = nullptr;
+  bool mOwns = true;
   uint64_t mSize = 0;
   double mSigmaHat = 0;
 
@@ -29,7 +30,16 @@ class DeviceSequence {
   explicit DeviceSequence(int device = 0) {
     if (hml_create(&mHandle, device) != HML_OK) throw std::runtime_error(hml_last_error(nullptr));
   }
-  ~DeviceSequence() { hml_destroy(mHandle); }
+  // view of a handle that the caller created and loaded (and keeps owning); for a segment of a split
+  // sequence size() is the length of the whole sequence, which is what the threshold depends on
+  explicit DeviceSequence(hml_t* loaded) : mHandle(loaded), mOwns(false) {
+    if (!loaded) throw std::runtime_error("NULL device handle");
+    check(hml_size(mHandle, &mSize));
+    check(hml_sigma_hat(mHandle, &mSigmaHat));
+  }
+  ~DeviceSequence() {
+    if (mOwns) hml_destroy(mHandle);
+  }
   void check(int rc) const {
     if (rc != HML_OK) throw std::runtime_error(hml_last_error(mHandle));
   }

@@ -350,3 +350,40 @@ def test_large_sequence_properties(dev):
     # idempotence: static re-run on the cached structure with the same counters gives the same result
     out2 = dev.fb_sweep(mu, var, A, pi, seed=1, sweep=0)
     assert np.array_equal(dev.states(), st) and np.array_equal(out2["trans"], out["trans"])
+
+
+# ------------------------------------------------------------------------------------------------
+# the C++ host side as C entry points (include/hammlet_host.h)
+
+@pytest.mark.gpu
+def test_cpp_chain_runs_sample_hmm(dev):
+    from hammlet_b200 import gibbs
+    from hammlet_b200.synth import piecewise_gaussian
+    T, K = 400_000, 4
+    x = piecewise_gaussian(T, K, 800, seed=21)
+    h = capi.Handle(0)
+    h.load(x)
+    tau_cpp = capi.Chain.auto_prior(h, 0.2, 0.9)
+    tau_py = gibbs.auto_prior(h, 0.2, 0.9)
+    assert np.allclose(tau_cpp, tau_py, rtol=1e-6), (tau_cpp, tau_py)   # AutoPriors.hpp:18-110, two host mirrors
+    chain = capi.Chain(h, K, tau_cpp, seed=3)
+    mean0, var0, A0, pi0 = chain.get()
+    assert np.all(var0 > 0) and np.allclose(A0.sum(1), 1, atol=1e-5) and abs(pi0.sum() - 1) < 1e-5
+    nb = chain.run(30, method="M")        # the default scheme starts with mixture sweeps (main.cpp:57)
+    nb = chain.run(60, method="F")
+    mean, var, A, pi = chain.get()
+    assert 0 < nb < T and np.all(np.isfinite(mean)) and np.all(var > 0)
+    # the chain must have found the generating levels (spacing 1, sigma 0.3): every true level has a state near it
+    levels = np.arange(K) - (K - 1) / 2.0
+    assert all(np.min(np.abs(mean - lv)) < 0.15 for lv in levels), mean
+    # static structure ("S" token): the block count stays what the frozen threshold gave
+    nb_s = chain.run(1, method="F", dynamic=False)
+    assert chain.run(5, method="F", dynamic=False) == nb_s
+    # same seed, same chain
+    chain2 = capi.Chain(h, K, tau_cpp, seed=3)
+    chain2.run(30, method="M")
+    chain2.run(60, method="F")
+    assert all(np.array_equal(a, b) for a, b in zip(chain2.get(), (mean, var, A, pi)))
+    chain.close()
+    chain2.close()
+    h.close()
