@@ -136,6 +136,9 @@ def cpu_model():
 
 
 def main():
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -184,7 +187,7 @@ def main():
                                        f"number of blocks (SURVEY.md §6.2)"},
             "e2e": {"value": scaled, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -339,7 +342,7 @@ def main():
                           f"sweeps, scaled by {Ts}/{T} (sweep cost linear in #blocks)"}
         except Exception as e:  # the checker is optional for the number, never for the product
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

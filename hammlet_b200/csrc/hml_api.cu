@@ -460,10 +460,14 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
   return rc;
 }
 
+// Tiles (4096 observations) are dealt out as evenly as possible: the first tiles % world ranks hold one more.
+uint64_t plan_first_tile(uint64_t tiles, int world, int rank) {
+  const uint64_t q = tiles / world, rem = tiles % world;
+  return (uint64_t)rank * q + ((uint64_t)rank < rem ? (uint64_t)rank : rem);
+}
 void segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t* len) {
   const uint64_t tiles = (T + kTile - 1) / kTile;
-  const uint64_t per = (tiles + world - 1) / world;  // tiles per rank (the last ranks may hold fewer)
-  uint64_t s = (uint64_t)rank * per * kTile, e = (uint64_t)(rank + 1) * per * kTile;
+  uint64_t s = plan_first_tile(tiles, world, rank) * kTile, e = plan_first_tile(tiles, world, rank + 1) * kTile;
   if (s > T) s = T;
   if (e > T) e = T;
   *start = s;
@@ -503,8 +507,11 @@ int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, 
 
   // ---- upper levels from the global tile sums, replicated: ctop[m] = coefficient at position 4096 m
   CK(dev_alloc(gsum, per * world));
-  CK(cudaMemcpy2DAsync(gsum, per * sizeof(float), recv, slot * sizeof(float), per * sizeof(float), world,
-                       cudaMemcpyDeviceToDevice, h->stream));
+  for (int r = 0; r < world; ++r) {
+    const uint64_t t0 = plan_first_tile(tiles_total, world, r), t1 = plan_first_tile(tiles_total, world, r + 1);
+    if (t1 > t0)
+      CK(cudaMemcpyAsync(gsum + t0, recv + (size_t)r * slot, (t1 - t0) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  }
   const uint64_t top_tiles = (tiles_total + kTile - 1) / kTile;
   CK(dev_alloc(ctop, top_tiles * kTile));
   {

@@ -1,0 +1,99 @@
+"""Multi-process host logic on CPU (gloo, world_size 2 and 3): the segment plan of the C ABI and the carry-exchange
+protocol of the segment-split mode (tests/segment_protocol.py) against the unsplit oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _worker(rank, world, port, case, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        import segment_protocol as sp
+        from hammlet_b200 import capi
+        from hammlet_b200.synth import model_guess, piecewise_gaussian
+        T, K, L, thr, use_self = case
+        x = piecewise_gaussian(T, K, L, seed=31)
+        mu, var, A, pi = (np.asarray(v, np.float64) for v in model_guess(K, seed=5))
+        O32, O64 = oracle.Oracle(False), oracle.Oracle(True)
+        w = O32.weights(x)
+        starts = O32.boundaries(w, thr).astype(np.int64)
+        n, s, q = O64.block_stats(O64.integral(x), starts, T)
+        u = np.random.default_rng(2).random(starts.size)
+        ref = O64.fb_sweep(n, s, q, mu, var, A, pi, use_self, u)
+
+        seg_start, seg_len = capi.Handle.segment_plan(T, world, rank)     # the C ABI's plan (host-only call)
+        assert seg_start % 4096 == 0
+        mine = starts[(starts >= seg_start) & (starts < seg_start + seg_len)] - seg_start
+        states, tot = sp.run_rank(dist, rank, world, seg_start, seg_len, T, mine, x[seg_start:seg_start + seg_len],
+                                  mu, var, A, pi, use_self, u)
+        fb = tot["first_block"]
+        assert tot["nblocks"] == starts.size
+        assert np.array_equal(states, ref["states"][fb:fb + states.size]), "states differ from the unsplit oracle"
+        assert np.array_equal(tot["trans"], ref["trans"]) and np.array_equal(tot["counts"], ref["counts"])
+        assert int(tot["trans"].sum()) == T
+        assert np.allclose(tot["stat_sum"], ref["stat_sum"], rtol=1e-9, atol=1e-7)
+        assert np.allclose(tot["stat_sq"], ref["stat_sq"], rtol=1e-9, atol=1e-7)
+        assert abs(tot["loglik"] - ref["loglik"]) <= 1e-9 * abs(ref["loglik"])
+        # every rank ends up with the same totals (lock-step parameter draws depend on it)
+        allt = [None] * world
+        dist.all_gather_object(allt, (tot["trans"].tobytes(), tot["stat_sum"].tobytes(), tot["loglik"]))
+        assert all(t == allt[0] for t in allt)
+        ret[rank] = "ok"
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        ret[rank] = traceback.format_exc()
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+CASES = [
+    (3 * 4096, 3, 40, 0.9, 1),
+    (40_000, 5, 150, 1.1, 1),
+    (33_000, 2, 60, 1e30, 1),      # only forced boundaries: a rank without any block start
+    (50_000, 4, 300, 0.6, 0),
+]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"T{c[0]}K{c[1]}")
+def test_segment_protocol_matches_unsplit_oracle(world, case):
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    port = 29600 + (hash((world, case)) % 300)
+    mp.spawn(_worker, args=(world, port, case, ret), nprocs=world, join=True)
+    assert all(ret.get(r) == "ok" for r in range(world)), dict(ret)
+
+
+def test_segment_plan_partitions_the_sequence():
+    from hammlet_b200 import capi
+    for T in (4096 * 8, 4096 * 8 + 1, 1_000_000_000, 300_007, 3_088_269_832):
+        for world in (1, 2, 3, 4, 8):
+            pos = 0
+            for r in range(world):
+                s, n = capi.Handle.segment_plan(T, world, r)
+                assert s == pos and n > 0 and (s % 4096 == 0)
+                pos += n
+            assert pos == T
+    with pytest.raises(capi.HmlError):
+        capi.Handle.segment_plan(4096 * 2 - 1, 2, 0)
+
+
+def test_lpt_assignment_balances_chromosomes():
+    from hammlet_b200.synth import HG38, lpt_assign
+    bins = lpt_assign(np.array(HG38), 8)
+    assert sorted(i for b in bins for i in b) == list(range(24))
+    load = [sum(HG38[i] for i in b) for b in bins]
+    assert max(load) / (sum(HG38) / 8) < 1.05      # C3: ~386 M observations per GPU
