@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhammlet_b200.so")
 
 SWEEP_DYNAMIC, SWEEP_LOGLIK, SWEEP_KEEP_ROWS = 1, 2, 4
+DETECT_STREAM, DETECT_PYRAMID = 0, 1
 MAX_STATES = 32
 
 
@@ -37,7 +38,7 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
            "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream",
            "hml_comm_unique_id", "hml_comm_init", "hml_segment_plan", "hml_load_segment_f32",
-           "hml_load_segment_f32_device", "hml_segment_info",
+           "hml_load_segment_f32_device", "hml_segment_info", "hml_set_detect_mode", "hml_detect_info",
            # include/hammlet_host.h
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run"]
@@ -170,6 +171,15 @@ class Handle:
         n = C.c_uint64()
         self._ck(self.lib.hml_create_blocks(self.h, C.c_float(threshold), C.byref(n)))
         return n.value
+
+    def set_detect_mode(self, mode):
+        """DETECT_STREAM (read every weight) or DETECT_PYRAMID (default: read only sub-blocks that can hold a boundary)."""
+        self._ck(self.lib.hml_set_detect_mode(self.h, C.c_int(mode)))
+
+    def detect_info(self):
+        mode, hot = C.c_int(), C.c_uint64()
+        self._ck(self.lib.hml_detect_info(self.h, C.byref(mode), C.byref(hot)))
+        return mode.value, hot.value
 
     def nr_blocks(self):
         n = C.c_uint64()

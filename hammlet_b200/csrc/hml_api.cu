@@ -76,6 +76,8 @@ struct hml_ctx {
   // sequence (resident since load); in segment mode T is the length of the local segment
   uint64_t T = 0;
   float* w = nullptr;       // breakpoint weights, padded to a tile multiple
+  float* smax = nullptr;    // max pyramid over sub-blocks of 32 weights (boundary detection reads only hot sub-blocks)
+  int detect_mode = HML_DETECT_PYRAMID;
   float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
   double2* pq = nullptr;    // integral arrays, T+1 entries
   double4* cell_pref = nullptr;
@@ -287,8 +289,9 @@ int exchange_cb(void* user, int which) {
 
 
 int run_detect(hml_t* h, float thr) {
-  h->launches += launch_detect(h->w, h->T, thr, h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity,
-                               h->outblk, h->stream, stage_cb, h);
+  h->launches += launch_detect(h->w, h->detect_mode == HML_DETECT_PYRAMID ? h->smax : nullptr, h->T, thr,
+                               h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity, h->outblk, h->stream,
+                               stage_cb, h);
   CK(cudaGetLastError());
   if (h->world > 1) {
     // the partial block in front of each rank's first boundary joins the last block of its owner
@@ -304,6 +307,7 @@ int run_detect(hml_t* h, float thr) {
 
 void load_reset(hml_t* h) {
   dev_free(h->w);
+  dev_free(h->smax);
   dev_free(h->coeffs);
   dev_free(h->pq);
   dev_free(h->cell_pref);
@@ -386,7 +390,12 @@ int load_integral(hml_t* h, const float* x_dev, uint64_t T) {
 
 // boundary-detection scratch and the initial block capacity (grows on demand: a sweep that overflows is re-run)
 int load_finish(hml_t* h, uint64_t T) {
+  CK(dev_alloc(h->smax, pyramid_floats(T)));
+  launch_build_pyramid(h->w, T, h->smax, h->sms, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
   CK(cudaMalloc(&h->detect_scratch, detect_scratch_bytes(T)));
+  CK(cudaMemsetAsync(h->detect_scratch, 0, detect_scratch_bytes(T), h->stream));
   h->T = T;
   uint64_t cap = T / 64;
   if (cap < (1u << 16)) cap = 1u << 16;
@@ -809,6 +818,7 @@ int hml_destroy(hml_t* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   dev_free(h->w);
+  dev_free(h->smax);
   dev_free(h->coeffs);
   dev_free(h->pq);
   dev_free(h->cell_pref);
@@ -1155,6 +1165,29 @@ int hml_segment_info(const hml_t* h, int* rank, int* world, uint64_t* seg_start,
   if (seg_len) *seg_len = h->T;
   if (first_block) *first_block = h->first_block;
   if (global_blocks) *global_blocks = h->world > 1 ? h->global_blocks : h->nblocks;
+  return HML_OK;
+}
+
+int hml_set_detect_mode(hml_t* h, int mode) {
+  if (!h) return HML_ERR_ARG;
+  if (mode != HML_DETECT_STREAM && mode != HML_DETECT_PYRAMID) return fail(h, HML_ERR_ARG, "unknown detection mode");
+  h->detect_mode = mode;
+  return HML_OK;
+}
+
+int hml_detect_info(hml_t* h, int* mode, uint64_t* hot_subblocks) {
+  if (!h) return HML_ERR_ARG;
+  if (mode) *mode = h->detect_mode;
+  if (hot_subblocks) {
+    *hot_subblocks = 0;
+    if (h->T && h->detect_scratch) {
+      CK(cudaSetDevice(h->device));
+      unsigned long long v = 0;
+      CK(cudaMemcpyAsync(&v, detect_hot_count_ptr(h->detect_scratch, h->T), sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      *hot_subblocks = v;
+    }
+  }
   return HML_OK;
 }
 

@@ -22,9 +22,14 @@ void launch_bp_weights_segment(const float* c_local, const float* ctop, const fl
 // ---- boundary detection (hml_detect.cu)
 typedef void (*stage_cb_t)(void* user, const char* name);
 size_t detect_scratch_bytes(uint64_t T);
-// flags -> counts -> ordered block starts; returns the number of kernels launched
-int launch_detect(const float* w, uint64_t T, float thr, int force_first, void* scratch, uint32_t* starts,
-                  uint64_t capacity, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb, void* user);
+// flags -> counts -> ordered block starts; returns the number of kernels launched.  smax != nullptr: pyramid
+// mode (only sub-blocks of 32 weights whose maximum reaches the threshold are read), else the streaming kernel.
+int launch_detect(const float* w, const float* smax, uint64_t T, float thr, int force_first, void* scratch,
+                  uint32_t* starts, uint64_t capacity, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
+                  void* user);
+size_t pyramid_floats(uint64_t T);
+void launch_build_pyramid(const float* w, uint64_t T, float* smax, int sms, cudaStream_t s);
+const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);
 
 // ---- block-level sweep kernels (hml_sweep.cu)
 struct ModelHost {  // what the C ABI receives, validated

@@ -73,6 +73,15 @@ int hml_get_coeffs(hml_t* h, float* dst_host, uint64_t n);
  * The threshold is the caller's fp32 value, sqrt(2 log T * min var) evaluated on the host exactly
  * as BreakpointArray.hpp:195-199 does; it is never recomputed on the device. */
 int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks);
+/* How the boundary positions are found (the result is the same set):
+ *   HML_DETECT_STREAM   every weight is read each time (4 bytes/observation, the HBM-roofline formulation);
+ *   HML_DETECT_PYRAMID  (default) the device analogue of the reference's skip pointers
+ *                       (Blocks/BreakpointArray.hpp:150-182): a max pyramid over sub-blocks of 32 weights is
+ *                       built at load, and only sub-blocks whose maximum reaches the threshold are read.
+ * hml_detect_info reports the mode and the number of sub-blocks the last detection pass had to read. */
+enum { HML_DETECT_STREAM = 0, HML_DETECT_PYRAMID = 1 };
+int hml_set_detect_mode(hml_t* h, int mode);
+int hml_detect_info(hml_t* h, int* mode, uint64_t* hot_subblocks);
 int hml_nr_blocks(const hml_t* h, uint64_t* nblocks);
 /* Copies the current block structure to host: starts[nblocks] (block b = [starts[b], starts[b+1])
  * with starts[nblocks] = T implied), sum[nblocks], sumsq[nblocks].  Any pointer may be NULL. */

@@ -87,8 +87,10 @@ def test_weights_vs_reference_fixture(dev, path):
 
 # ------------------------------------------------------------------------------------------ boundaries + statistics
 
+@pytest.mark.parametrize("mode", [capi.DETECT_PYRAMID, capi.DETECT_STREAM], ids=["pyramid", "stream"])
 @pytest.mark.parametrize("T,L", [(1, 5), (7, 3), (4096, 40), (100_000, 200), (3_000_017, 500)])
-def test_boundaries_exact_and_stats(dev, T, L):
+def test_boundaries_exact_and_stats(dev, T, L, mode):
+    dev.set_detect_mode(mode)
     x = piecewise_gaussian(T, 5, L, seed=T % 97 + 2)
     O32, O64 = oracle.Oracle(False), oracle.Oracle(True)
     w = O32.weights(x)
@@ -108,6 +110,35 @@ def test_boundaries_exact_and_stats(dev, T, L):
             n, rs, rq = O64.block_stats(integ, ref, T)
             assert rel_err(q, rq, scale=msq) <= RTOL
             assert rel_err(s, rs, scale=np.maximum(np.sqrt(n * rq), np.sqrt(msq))) <= RTOL
+    dev.set_detect_mode(capi.DETECT_PYRAMID)
+
+
+def test_pyramid_and_stream_detection_agree_on_hostile_weights(dev):
+    """NaN / inf / huge observations give NaN and inf weights; a NaN weight is a boundary for every threshold
+    (BreakpointArray.hpp:224-231 tests !(w < thr)).  Both detection modes must return the same list."""
+    T = 777_777
+    x = piecewise_gaussian(T, 4, 3000, seed=8)
+    rng = np.random.default_rng(1)
+    x[rng.integers(0, T, 40)] = np.nan
+    x[rng.integers(0, T, 40)] = np.inf
+    x[rng.integers(0, T, 40)] = -np.inf
+    x[rng.integers(0, T, 40)] = 3e38
+    dev.load(x)
+    w = dev.weights()
+    for thr in (0.3, 1.2, 50.0, 1e30, np.inf, np.nan):
+        lists = []
+        for mode in (capi.DETECT_STREAM, capi.DETECT_PYRAMID):
+            dev.set_detect_mode(mode)
+            B = dev.create_blocks(thr)
+            lists.append(dev.blocks(stats=False))
+            assert B == lists[-1].size
+        expect = np.flatnonzero(~(w < np.float32(thr)))
+        expect = expect if expect.size and expect[0] == 0 else np.concatenate([[0], expect])
+        assert np.array_equal(lists[0], lists[1]) and np.array_equal(lists[0].astype(np.int64), expect)
+    dev.set_detect_mode(capi.DETECT_PYRAMID)
+    B = dev.create_blocks(1.2)
+    mode, hot = dev.detect_info()
+    assert mode == capi.DETECT_PYRAMID and 0 < hot <= B     # every hot sub-block holds at least one boundary
 
 
 def test_block_stats_vs_exact_sums(dev):
