@@ -72,39 +72,61 @@ def generate(torch, T, K, L, seed, device, limit=None, keep=None):
 
 
 class ClockSampler:
+    """SM clock and clock-event reasons of one GPU, polled through NVML from a thread for as long as the timed
+    regions run (the sweeps are ctypes calls, so the GIL is free).  `nvidia-smi -lms` needs ~100 ms per row and
+    misses a 20 ms timed region; NVML answers in well under a millisecond."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop_flag, self.thread, self.err = index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                         pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+        except Exception as e:  # noqa: BLE001 - reported in the JSON line
+            self.nv, self.err = None, f"NVML unavailable: {e}"
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+                power = nv.nvmlDeviceGetPowerUsage(self.dev) / 1000.0
+                self.rows.append((sm, reasons, power))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.nv is None or self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "sampler not started"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({self.NAMES[i] for r in self.rows for i in range(4) if r[1] & self.bits[i]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max((r[2] for r in self.rows), default=None),
+                "how": "NVML polled every ~2 ms from a thread across the timed regions (device-clock, end-to-end and "
+                       "per-stage passes: the same sweeps)"}
 
 
 def measured_peak():
@@ -141,8 +163,8 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--T", type=float, default=1e9)
     ap.add_argument("--K", type=int, default=5)
@@ -269,7 +291,6 @@ def main():
     chain.run(steps)
     torch.cuda.synchronize()
     wall = time.perf_counter() - w0
-    clocks = sampler.stop()
 
     # ---- region 3 (not part of `value`): the same steps with per-stage CUDA events, for the roofline and stage table
     h.set_timing(True)
@@ -279,6 +300,7 @@ def main():
         for name, ms in h.timing():
             stage_ms.setdefault(name, []).append(ms)
     h.set_timing(False)
+    clocks = sampler.stop()
 
     # ---- the streaming formulation of boundary detection (4 B/observation), timed on the same data
     # (collective in segment mode, so every rank runs it)
