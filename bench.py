@@ -337,7 +337,7 @@ def main():
     busy = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     # algorithmic bytes per launch of the kernels that can dominate a sweep
     alg = {
-        "detect_pyramid": T_local / 8.0 + 128.0 * hot + 16.0 * hot / 4.0 + 4.0 * Bl,   # pyramid + hot sub-blocks + masks/starts
+        "detect_hot": T_local / 16.0 + 128.0 * hot + 8.0 * hot,                        # bf16 pyramid + hot sub-blocks + triples
         "detect_flags": 4.0 * T_local + 4.0 * Bl,                                      # every weight + starts
         "block_emit": Bl * (4 + 16 + 4 + 16 + 16 * K),                                 # starts, integral gathers, N, sums, e, sp
         "fwd_chunks": Bl * 8 * K * (1 + K / 32.0),
@@ -368,7 +368,7 @@ def main():
         "config": {"workload": wl, "mode": "segments" if segments else ("independent" if world > 1 else "single"),
                    "states": K, "observations": T, "observations_per_gpu": T_local, "blocks_per_sweep": B,
                    "compression_ratio": T / B,
-                   "l2_policy": f"inputs larger than L2 (per GPU and sweep: {T_local / 8e9:.3f} GB pyramid + {128.0 * hot / 1e9:.3f} GB of "
+                   "l2_policy": f"inputs larger than L2 (per GPU and sweep: {T_local / 16e9:.3f} GB pyramid + {128.0 * hot / 1e9:.3f} GB of "
                                 f"hot weight sub-blocks + the block-level arrays vs 126 MB L2; weights {4.0 * T_local / 1e9:.2f} GB)",
                    "detect_mode": "pyramid", "hot_subblocks_per_sweep": hot,
                    "load_seconds": t_load},

@@ -76,7 +76,7 @@ struct hml_ctx {
   // sequence (resident since load); in segment mode T is the length of the local segment
   uint64_t T = 0;
   float* w = nullptr;       // breakpoint weights, padded to a tile multiple
-  float* smax = nullptr;    // max pyramid over sub-blocks of 32 weights (boundary detection reads only hot sub-blocks)
+  uint16_t* smax = nullptr; // bf16 max pyramid over sub-blocks of 32 weights (boundary detection reads only hot sub-blocks)
   int detect_mode = HML_DETECT_PYRAMID;
   float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
   double2* pq = nullptr;    // integral arrays, T+1 entries
@@ -390,7 +390,7 @@ int load_integral(hml_t* h, const float* x_dev, uint64_t T) {
 
 // boundary-detection scratch and the initial block capacity (grows on demand: a sweep that overflows is re-run)
 int load_finish(hml_t* h, uint64_t T) {
-  CK(dev_alloc(h->smax, pyramid_floats(T)));
+  CK(dev_alloc(h->smax, pyramid_entries(T)));
   launch_build_pyramid(h->w, T, h->smax, h->sms, h->stream);
   h->launches++;
   CK(cudaGetLastError());

@@ -20,13 +20,13 @@
 //
 // Pyramid mode (default).  The reference's walk is sub-linear in T: its uint16 skip pointers jump over
 // runs of small weights (BreakpointArray.hpp:150-182,216-235).  The device analogue is a one-level max
-// pyramid built at load: smax[g] = max of the 32 weights of sub-block g (NaN counts as +inf).  A sub-block
-// can hold a boundary only if !(smax[g] < thr), so
-//   k_detect_pyramid  reads the pyramid (T/8 bytes) and then only the hot sub-blocks (128 B each, eight
-//                     loads in flight per lane); one ballot per hot sub-block is its 32-bit mask
-//   k_scatter_pyramid ranks the masks of the hot sub-blocks as above
+// pyramid built at load: entry g = max of the 32 weights of sub-block g, rounded up to bf16 (NaN counts as
+// +inf).  A sub-block can hold a boundary only if !(entry < thr), so
+//   k_detect_hot   reads the pyramid (T/16 bytes) and then only the hot sub-blocks (128 B each); per hot
+//                  sub-block one 32-bit boundary mask; the last CTA to finish scans the per-span counts
+//   k_scatter_hot  writes the positions of the set bits in increasing order
 // The boundary set is identical to the streaming kernels' (tests compare both with the oracle); the traffic
-// drops from 4 T bytes to T/8 + 128 * (hot sub-blocks).
+// drops from 4 T bytes to T/16 + 128 * (hot sub-blocks).
 #include "hml_common.cuh"
 #include "hml_kernels.h"
 
@@ -34,7 +34,8 @@ namespace hml {
 
 constexpr int kTilesPerCta = 8;  // 8 warps, one tile each
 constexpr int kSub = 32;         // observations per pyramid entry
-constexpr int kSubsPerTile = kTile / kSub;  // 128: four per lane
+constexpr int kSpanSubs = 4096;               // pyramid entries per CTA of the pyramid kernels
+constexpr int kSpanObs = kSpanSubs * kSub;    // 131072 observations
 
 // Per tile: its boundary count and its offset inside the CTA, packed as count | offset << 16 (count <= 4096,
 // offset <= 7 * 4096); per CTA: the total.  Called by all threads after s_cnt was filled and synchronised.
@@ -98,14 +99,26 @@ __global__ void __launch_bounds__(256)
   finish_cta_counts(s_cnt, cnt, tile, num_tiles, tile_count, cta_count);
 }
 
-// smax[g] = max over the sub-block's weights that exist (t < T); NaN -> +inf (a NaN weight is always a boundary)
-__global__ void __launch_bounds__(256) k_build_pyramid(const float* __restrict__ w, uint64_t T, uint64_t num_subs,
-                                                       float* __restrict__ smax) {
+// ---- pyramid mode -------------------------------------------------------------------------------------------
+// Entry g of the pyramid is the maximum of the 32 weights of sub-block g, rounded UP to bf16 (2 bytes per 32
+// observations).  Rounding up keeps the test conservative: a sub-block whose true maximum reaches the threshold
+// is always flagged; the few extra sub-blocks flagged by the rounding are read and turn out empty.  The decision
+// itself is always taken on the exact fp32 weights, so the boundary set is bit-identical to the stream kernels'.
+__device__ __forceinline__ uint16_t bf16_round_up(float v) {
+  if (v != v) return 0x7f80u;  // a NaN weight is always a boundary: +inf
+  const uint32_t b = __float_as_uint(v);
+  if (b & 0x80000000u) return (uint16_t)(b >> 16);  // negative: truncation rounds towards +inf
+  return (uint16_t)((b + 0xffffu) >> 16);            // smallest bf16 >= v (overflows to +inf)
+}
+
+// entries past the last real sub-block (up to a whole number of spans) hold -inf: never hot
+__global__ void __launch_bounds__(256) k_build_pyramid(const float* __restrict__ w, uint64_t T, uint64_t num_entries,
+                                                       uint16_t* __restrict__ smax) {
   const float inf = __int_as_float(0x7f800000);
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t g0 = warp * 32; g0 < num_subs; g0 += nwarps * 32) {
+  for (uint64_t g0 = warp * 32; g0 < num_entries; g0 += nwarps * 32) {
     float mine = -inf;
 #pragma unroll 4
     for (int k = 0; k < 32; ++k) {  // sub-block g0 + k: one coalesced 128-byte row per step
@@ -119,125 +132,237 @@ __global__ void __launch_bounds__(256) k_build_pyramid(const float* __restrict__
       for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
       if (lane == k) mine = v;
     }
-    if (g0 + lane < num_subs) smax[g0 + lane] = mine;
+    if (g0 + lane < num_entries) smax[g0 + lane] = bf16_round_up(mine);
   }
 }
 
-__global__ void __launch_bounds__(256)
-    k_detect_pyramid(const float* __restrict__ w, const float4* __restrict__ smax4, uint64_t T, float thr, int force_first,
-                     uint32_t num_tiles, uint4* __restrict__ masks, uint4* __restrict__ tile_hot,
-                     uint32_t* __restrict__ tile_count, uint32_t* __restrict__ cta_count,
-                     unsigned long long* __restrict__ hot_counter) {
-  __shared__ uint32_t s_cnt[kTilesPerCta];
-  __shared__ uint32_t s_hot[kTilesPerCta];
-  __shared__ uint8_t s_list[kTilesPerCta][kSubsPerTile + 4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t tile = blockIdx.x * kTilesPerCta + warp;
-  uint32_t cnt = 0, nhot = 0;
-  if (tile < num_tiles) {
-    const uint64_t tbase = (uint64_t)tile * kTile;
-    const float* __restrict__ wt = w + tbase + lane;
-    const float4 m = smax4[(uint64_t)tile * 32 + lane];  // sub-blocks 4*lane .. 4*lane+3
-    uint32_t hot = (!(m.x < thr) ? 1u : 0u) | (!(m.y < thr) ? 2u : 0u) | (!(m.z < thr) ? 4u : 0u) | (!(m.w < thr) ? 8u : 0u);
-    const bool first = tile == 0 && force_first;
-    if (first && lane == 0) hot |= 1u;
-    const uint32_t hb0 = __ballot_sync(0xffffffffu, hot & 1u), hb1 = __ballot_sync(0xffffffffu, hot & 2u);
-    const uint32_t hb2 = __ballot_sync(0xffffffffu, hot & 4u), hb3 = __ballot_sync(0xffffffffu, hot & 8u);
-    const uint32_t n0 = __popc(hb0), n1 = __popc(hb1), n2 = __popc(hb2);
-    nhot = n0 + n1 + n2 + __popc(hb3);
-    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
-    if (nhot) {
-      // list of the hot sub-blocks (any order: every mask lands in its owner's register)
-      const uint32_t lt = lanemask_lt();
-      if (hot & 1u) s_list[warp][__popc(hb0 & lt)] = (uint8_t)(4 * lane);
-      if (hot & 2u) s_list[warp][n0 + __popc(hb1 & lt)] = (uint8_t)(4 * lane + 1);
-      if (hot & 4u) s_list[warp][n0 + n1 + __popc(hb2 & lt)] = (uint8_t)(4 * lane + 2);
-      if (hot & 8u) s_list[warp][n0 + n1 + n2 + __popc(hb3 & lt)] = (uint8_t)(4 * lane + 3);
-      __syncwarp();
-      const bool full = tbase + kTile <= T && !first;
-      const uint32_t rem = full ? (uint32_t)kTile : (uint32_t)(T > tbase ? T - tbase : 0);  // valid observations
-      for (uint32_t i = 0; i < nhot; i += 4) {
-        // four sub-blocks per round: the loads are issued before the first ballot consumes one
-        const uint32_t quad = *reinterpret_cast<const uint32_t*>(&s_list[warp][i]);
-        const uint32_t left = nhot - i;
-        float v[4];
-        uint32_t sub[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          sub[k] = (quad >> (8 * k)) & 0xffu;
-          v[k] = (k == 0 || (uint32_t)k < left) ? wt[sub[k] * kSub] : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k == 0 || (uint32_t)k < left) {  // warp-uniform
-            bool f = !(v[k] < thr);
-            if (!full) {
-              const uint32_t p = sub[k] * kSub + lane;
-              f = (f && p < rem) || (first && p == 0);
-            }
-            const uint32_t mk = __ballot_sync(0xffffffffu, f);
-            cnt += __popc(mk);
-            if ((uint32_t)lane == (sub[k] >> 2)) {
-              const uint32_t c = sub[k] & 3u;
-              mine.x = c == 0 ? mk : mine.x;
-              mine.y = c == 1 ? mk : mine.y;
-              mine.z = c == 2 ? mk : mine.z;
-              mine.w = c == 3 ? mk : mine.w;
-            }
-          }
-        }
-      }
-      if (hot) masks[(uint64_t)tile * 32 + lane] = mine;
-    }
-    if (lane == 0) tile_hot[tile] = make_uint4(hb0, hb1, hb2, hb3);
-  }
-  if (lane == 0) {
-    s_cnt[warp] = cnt;
-    s_hot[warp] = nhot;
-  }
-  __syncthreads();
-  finish_cta_counts(s_cnt, cnt, tile, num_tiles, tile_count, cta_count);
-  if (threadIdx.x == 0) {
-    uint32_t hsum = 0;
-#pragma unroll
-    for (int i = 0; i < kTilesPerCta; ++i) hsum += s_hot[i];
-    if (hsum) atomicAdd(hot_counter, (unsigned long long)hsum);
-  }
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
 }
 
+// hot bits of the eight bf16 entries of one 16-byte pyramid word
+__device__ __forceinline__ uint32_t hot_bits8(const uint4 v, float thr) {
+  const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+  uint32_t h = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float lo = __uint_as_float(wd[i] << 16), hi = __uint_as_float(wd[i] & 0xffff0000u);
+    h |= (!(lo < thr) ? 1u : 0u) << (2 * i);
+    h |= (!(hi < thr) ? 1u : 0u) << (2 * i + 1);
+  }
+  return h;
+}
+
+// k_detect_hot: one CTA per span of 4096 pyramid entries (131072 observations).
+//   phase 1  every thread reads two 16-byte pyramid words (both loads in flight); the hot sub-blocks are compacted,
+//            in position order, into a list in shared memory (ballot-free: packed warp scans of the popcounts)
+//   phase 2  the hot sub-blocks are read 16 per warp and round: a quarter warp reads one sub-block as float4 per
+//            lane, four loads in flight per lane; redux.or over the quarter assembles the 32-bit boundary mask
+//   phase 3  exclusive scan of the mask popcounts; (sub-block, offset, mask) triples go to global memory,
+//            8 bytes per hot sub-block, and the span's boundary count to span_info
+//   last CTA (atomic ticket): exclusive scan over the span counts -> span_off, total -> *nblocks_out and the
+//            sentinel starts[total] = T.  No CTA ever waits for another one.
 __global__ void __launch_bounds__(256)
-    k_scatter_pyramid(const uint4* __restrict__ masks, const uint4* __restrict__ tile_hot,
-                      const uint32_t* __restrict__ tile_count, const uint32_t* __restrict__ cta_off, uint32_t num_tiles,
-                      uint32_t* __restrict__ starts, uint64_t capacity) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t tile0 = blockIdx.x * kTilesPerCta;
-  const uint32_t tile = tile0 + warp;
-  if (tile >= num_tiles) return;
-  const uint32_t tc = tile_count[tile];
-  if ((tc & 0xffffu) == 0) return;
-  const uint32_t c = tc >> 16;  // offset of this tile inside the CTA
-  const uint4 hb = tile_hot[tile];
-  const bool any_hot = ((hb.x | hb.y | hb.z | hb.w) >> lane) & 1u;
-  uint4 m = make_uint4(0u, 0u, 0u, 0u);
-  if (any_hot) m = masks[(uint64_t)tile * 32 + lane];
-  // components of sub-blocks that were not hot hold zeros (the producer starts from zero)
-  const uint32_t mine = __popc(m.x) + __popc(m.y) + __popc(m.z) + __popc(m.w);
-  uint32_t incl = mine;
+    k_detect_hot(const float* __restrict__ w, const uint4* __restrict__ smax8, uint64_t T, float thr, int force_first,
+                 uint32_t nspans, uint2* __restrict__ hot, uint32_t* __restrict__ span_info, uint32_t* __restrict__ span_off,
+                 unsigned int* __restrict__ ticket, unsigned long long* __restrict__ nblocks_out,
+                 uint32_t* __restrict__ starts, uint64_t capacity, unsigned long long* __restrict__ hot_counter) {
+  __shared__ uint16_t s_list[kSpanSubs];
+  __shared__ uint32_t s_mask[kSpanSubs];
+  __shared__ uint32_t s_warp[2][8];
+  __shared__ uint32_t s_red[8];
+  __shared__ uint64_t s_red64[8];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t span = blockIdx.x;
+  const bool first = span == 0 && force_first;
+  const uint64_t nsubs = (T + kSub - 1) / kSub;
+
+  // ---- phase 1
+  uint4 pv[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) pv[k] = ld_stream_u4(smax8 + (uint64_t)span * (kSpanSubs / 8) + k * 256 + tid);
+  uint32_t h[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    h[k] = hot_bits8(pv[k], thr);
+    // entries past the last sub-block never count (a NaN or -inf threshold flags even their -inf padding)
+    const uint64_t e0 = (uint64_t)span * kSpanSubs + (uint64_t)(k * 256 + tid) * 8;
+    if (e0 + 8 > nsubs) h[k] = e0 < nsubs ? (h[k] & ((1u << (uint32_t)(nsubs - e0)) - 1u)) : 0u;
+  }
+  if (first && tid == 0) h[0] |= 1u;
+  const uint32_t c0 = __popc(h[0]), c1 = __popc(h[1]);
+  uint32_t incl = c0 | (c1 << 16);  // both counts scanned at once: a warp total is at most 256
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += u;
   }
-  uint64_t o = (uint64_t)cta_off[blockIdx.x] + c + (incl - mine);
-  const uint32_t pbase = tile * (uint32_t)kTile + (uint32_t)lane * (4u * kSub);
-  const uint32_t word[4] = {m.x, m.y, m.z, m.w};
+  if (lane == 31) {
+    s_warp[0][warp] = incl & 0xffffu;
+    s_warp[1][warp] = incl >> 16;
+  }
+  __syncthreads();
+  uint32_t base0 = 0, base1 = 0, nhot = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint32_t bits = word[k];
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t a = s_warp[0][i], b = s_warp[1][i];
+    if (i < warp) {
+      base0 += a;
+      base1 += b;
+    }
+    nhot += a + b;
+    base1 += a;  // every k = 0 entry precedes the k = 1 entries
+  }
+  {
+    uint32_t p0 = base0 + (incl & 0xffffu) - c0, p1 = base1 + (incl >> 16) - c1;
+    uint32_t b0 = h[0], b1 = h[1];
+    while (b0) {
+      const int l = __ffs(b0) - 1;
+      b0 &= b0 - 1;
+      s_list[p0++] = (uint16_t)(tid * 8 + l);
+    }
+    while (b1) {
+      const int l = __ffs(b1) - 1;
+      b1 &= b1 - 1;
+      s_list[p1++] = (uint16_t)((256 + tid) * 8 + l);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2
+  {
+    const int q = lane >> 3, l8 = lane & 7;
+    const uint32_t qmask = 0xffu << (8 * q);
+    const float4* wq = reinterpret_cast<const float4*>(w + (uint64_t)span * kSpanObs) + l8;
+    for (uint32_t i0 = warp * 16; i0 < nhot; i0 += 8 * 16) {
+      uint32_t sub[4];
+      float4 v[4];
+      bool ok[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t idx = i0 + 4 * k + q;
+        ok[k] = idx < nhot;
+        sub[k] = ok[k] ? s_list[idx] : 0u;
+        if (ok[k]) v[k] = ld_stream_f4(wq + sub[k] * (kSub / 4));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t f = 0;
+        if (ok[k])
+          f = (!(v[k].x < thr) ? 1u : 0u) | (!(v[k].y < thr) ? 2u : 0u) | (!(v[k].z < thr) ? 4u : 0u) |
+              (!(v[k].w < thr) ? 8u : 0u);
+        uint32_t m = __reduce_or_sync(qmask, f << (4 * l8));
+        if (ok[k] && l8 == 0) {
+          const uint64_t pos0 = ((uint64_t)span * kSpanSubs + sub[k]) * kSub;
+          if (pos0 + kSub > T) m = pos0 < T ? (m & ((1u << (uint32_t)(T - pos0)) - 1u)) : 0u;  // past the end
+          if (first && sub[k] == 0) m |= 1u;
+          s_mask[i0 + 4 * k + q] = m;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: thread t owns entries [t * per, t * per + per)
+  const uint32_t per = (nhot + 255) >> 8;
+  const uint32_t lo = min(nhot, (uint32_t)tid * per), hi = min(nhot, lo + per);
+  uint32_t mine = 0;
+  for (uint32_t i = lo; i < hi; ++i) mine += __popc(s_mask[i]);
+  uint32_t inc2 = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc2, o);
+    if (lane >= o) inc2 += u;
+  }
+  if (lane == 31) s_red[warp] = inc2;
+  __syncthreads();
+  uint32_t wpre = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < warp) wpre += s_red[i];
+    total += s_red[i];
+  }
+  {
+    uint32_t off = wpre + inc2 - mine;
+    uint2* dst = hot + (uint64_t)span * kSpanSubs;
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint32_t m = s_mask[i];
+      dst[i] = make_uint2((uint32_t)s_list[i] | (off << 12), m);
+      off += __popc(m);
+    }
+  }
+  if (tid == 0) {
+    span_info[span] = total | (nhot << 18);
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == nspans - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- last CTA: exclusive scan over the span counts
+  __threadfence();
+  const uint32_t per2 = (nspans + 255) >> 8;
+  const uint32_t lo2 = min(nspans, (uint32_t)tid * per2), hi2 = min(nspans, lo2 + per2);
+  uint64_t sum = 0, hsum = 0;
+  for (uint32_t i = lo2; i < hi2; ++i) {
+    const uint32_t v = __ldcg(span_info + i);
+    sum += v & 0x3ffffu;
+    hsum += v >> 18;
+  }
+  uint64_t inc3 = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t u = __shfl_up_sync(0xffffffffu, inc3, o);
+    if (lane >= o) inc3 += u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+  __syncthreads();  // s_red is reused below
+  if (lane == 31) s_red64[warp] = inc3;
+  if (lane == 0) s_red[warp] = (uint32_t)hsum;  // a sequence holds fewer than 2^32 / 32 sub-blocks
+  __syncthreads();
+  uint64_t wpre3 = 0, tot3 = 0, hot_total = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < warp) wpre3 += s_red64[i];
+    tot3 += s_red64[i];
+    hot_total += s_red[i];
+  }
+  uint64_t run = wpre3 + inc3 - sum;
+  for (uint32_t i = lo2; i < hi2; ++i) {
+    span_off[i] = (uint32_t)run;  // < 2^32 because T < 2^32
+    run += __ldcg(span_info + i) & 0x3ffffu;
+  }
+  if (tid == 0) {
+    *nblocks_out = tot3;
+    if (tot3 <= capacity) starts[tot3] = (uint32_t)T;  // sentinel: block b = [starts[b], starts[b+1])
+    hot_counter[1] = hot_total;                        // hot sub-blocks of this pass, for the traffic accounting
+    *ticket = 0u;
+  }
+}
+
+// k_scatter_hot: thread per hot sub-block: its boundary positions go to starts[span_off + offset ...]
+__global__ void __launch_bounds__(128)
+    k_scatter_hot(const uint2* __restrict__ hot, const uint32_t* __restrict__ span_info, const uint32_t* __restrict__ span_off,
+                  uint32_t* __restrict__ starts, uint64_t capacity) {
+  const uint32_t span = blockIdx.x;
+  const uint32_t info = span_info[span];
+  if ((info & 0x3ffffu) == 0) return;
+  const uint32_t nhot = info >> 18;
+  const uint64_t base = span_off[span];
+  const uint2* src = hot + (uint64_t)span * kSpanSubs;
+  for (uint32_t i = threadIdx.x; i < nhot; i += blockDim.x) {
+    const uint2 e = src[i];
+    uint64_t o = base + (e.x >> 12);
+    const uint32_t pos = (span * (uint32_t)kSpanSubs + (e.x & 0xfffu)) * (uint32_t)kSub;
+    uint32_t bits = e.y;
     while (bits) {
       const int l = __ffs(bits) - 1;
       bits &= bits - 1;
-      if (o < capacity) starts[o] = pbase + (uint32_t)k * kSub + (uint32_t)l;
+      if (o < capacity) starts[o] = pos + (uint32_t)l;
       ++o;
     }
   }
@@ -247,7 +372,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(1024)
     k_scan_counts(const uint32_t* __restrict__ cta_count, uint32_t n, uint32_t* __restrict__ cta_off,
                   unsigned long long* __restrict__ nblocks_out, uint32_t* __restrict__ starts, uint64_t capacity,
-                  uint64_t T, unsigned long long* __restrict__ hot_counter) {
+                  uint64_t T) {
   __shared__ uint64_t s_warp[32];
   __shared__ uint64_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -283,8 +408,6 @@ __global__ void __launch_bounds__(1024)
     const uint64_t nb = s_carry;
     *nblocks_out = nb;
     if (nb <= capacity) starts[nb] = (uint32_t)T;  // sentinel: block b = [starts[b], starts[b+1])
-    hot_counter[1] = hot_counter[0];  // hot sub-blocks of this pass (pyramid mode), for the traffic accounting
-    hot_counter[0] = 0;
   }
 }
 
@@ -321,55 +444,81 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-size_t detect_scratch_bytes(uint64_t T) {
+// scratch layout: [stream mode] masks (512 B per tile), per-tile counts, per-CTA counts and offsets;
+// [pyramid mode] hot triples (8 B per pyramid entry), span_info, span_off, ticket; [both] hot counters
+struct DetectScratch {
+  uint4* masks;
+  uint32_t *tile_count, *cta_count, *cta_off;
+  uint2* hot;
+  uint32_t *span_info, *span_off;
+  unsigned int* ticket;
+  unsigned long long* hot_counter;  // [0] unused, [1] hot sub-blocks of the last pyramid pass
+  size_t bytes;
+};
+
+static DetectScratch carve_scratch(void* scratch, uint64_t T) {
   const uint64_t tiles = (T + kTile - 1) / kTile;
   const uint64_t ctas = (tiles + kTilesPerCta - 1) / kTilesPerCta;
-  return tiles * 32 * sizeof(uint4) + tiles * sizeof(uint4) + (tiles + 2 * ctas + 16) * sizeof(uint32_t) + 64;
+  const uint64_t spans = (T + kSpanObs - 1) / kSpanObs;
+  DetectScratch d;
+  char* p = reinterpret_cast<char*>(scratch);
+  auto take = [&](size_t n) {
+    char* r = p;
+    p += (n + 255) / 256 * 256;
+    return r;
+  };
+  d.masks = reinterpret_cast<uint4*>(take(tiles * 32 * sizeof(uint4)));
+  d.hot = reinterpret_cast<uint2*>(take(spans * kSpanSubs * sizeof(uint2)));
+  d.tile_count = reinterpret_cast<uint32_t*>(take(tiles * 4));
+  d.cta_count = reinterpret_cast<uint32_t*>(take(ctas * 4));
+  d.cta_off = reinterpret_cast<uint32_t*>(take(ctas * 4));
+  d.span_info = reinterpret_cast<uint32_t*>(take(spans * 4));
+  d.span_off = reinterpret_cast<uint32_t*>(take((spans + 1) * 4));
+  d.hot_counter = reinterpret_cast<unsigned long long*>(take(16));
+  d.ticket = reinterpret_cast<unsigned int*>(take(4));
+  d.bytes = (size_t)(p - reinterpret_cast<char*>(scratch));
+  return d;
 }
 
-size_t pyramid_floats(uint64_t T) { return (T + kTile - 1) / kTile * kSubsPerTile; }
+size_t detect_scratch_bytes(uint64_t T) { return carve_scratch(nullptr, T).bytes; }
 
-void launch_build_pyramid(const float* w, uint64_t T, float* smax, int sms, cudaStream_t s) {
-  const uint64_t subs = pyramid_floats(T);
-  uint64_t blocks = (subs + 255) / 256;
+size_t pyramid_entries(uint64_t T) { return (T + kSpanObs - 1) / kSpanObs * kSpanSubs; }
+
+void launch_build_pyramid(const float* w, uint64_t T, uint16_t* smax, int sms, cudaStream_t s) {
+  const uint64_t n = pyramid_entries(T);
+  uint64_t blocks = (n + 255) / 256;
   if (blocks > (uint64_t)sms * 16) blocks = (uint64_t)sms * 16;
-  k_build_pyramid<<<(unsigned)blocks, 256, 0, s>>>(w, T, subs, smax);
+  k_build_pyramid<<<(unsigned)blocks, 256, 0, s>>>(w, T, n, smax);
 }
 
-int launch_detect(const float* w, const float* smax, uint64_t T, float thr, int force_first, void* scratch,
+int launch_detect(const float* w, const uint16_t* smax, uint64_t T, float thr, int force_first, void* scratch,
                   uint32_t* starts, uint64_t capacity, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
                   void* user) {
+  const DetectScratch d = carve_scratch(scratch, T);
+  if (smax != nullptr) {
+    const uint32_t spans = (uint32_t)((T + kSpanObs - 1) / kSpanObs);
+    if (cb) cb(user, "detect_hot");
+    k_detect_hot<<<spans, 256, 0, s>>>(w, reinterpret_cast<const uint4*>(smax), T, thr, force_first, spans, d.hot,
+                                       d.span_info, d.span_off, d.ticket, nblocks_out, starts, capacity, d.hot_counter);
+    if (cb) cb(user, "detect_scatter");
+    k_scatter_hot<<<spans, 128, 0, s>>>(d.hot, d.span_info, d.span_off, starts, capacity);
+    return 2;
+  }
   const uint32_t tiles = (uint32_t)((T + kTile - 1) / kTile);
   const uint32_t ctas = (tiles + kTilesPerCta - 1) / kTilesPerCta;
-  uint4* masks = reinterpret_cast<uint4*>(scratch);
-  uint4* tile_hot = masks + (uint64_t)tiles * 32;
-  unsigned long long* hot_counter = reinterpret_cast<unsigned long long*>(tile_hot + tiles);  // [0] running, [1] last pass
-  uint32_t* tile_count = reinterpret_cast<uint32_t*>(hot_counter + 2);
-  uint32_t* cta_count = tile_count + tiles;
-  uint32_t* cta_off = cta_count + ctas;
-  const bool pyramid = smax != nullptr && thr == thr;  // a NaN threshold makes every position a boundary: stream
-  if (cb) cb(user, pyramid ? "detect_pyramid" : "detect_flags");
-  if (pyramid)
-    k_detect_pyramid<<<ctas, 256, 0, s>>>(w, reinterpret_cast<const float4*>(smax), T, thr, force_first, tiles, masks,
-                                          tile_hot, tile_count, cta_count, hot_counter);
-  else
-    k_detect_flags<<<ctas, 256, 0, s>>>(reinterpret_cast<const float4*>(w), T, thr, force_first, tiles, masks, tile_count,
-                                        cta_count);
+  if (cb) cb(user, "detect_flags");
+  k_detect_flags<<<ctas, 256, 0, s>>>(reinterpret_cast<const float4*>(w), T, thr, force_first, tiles, d.masks, d.tile_count,
+                                      d.cta_count);
   if (cb) cb(user, "detect_scan");
-  k_scan_counts<<<1, 1024, 0, s>>>(cta_count, ctas, cta_off, nblocks_out, starts, capacity, T, hot_counter);
+  k_scan_counts<<<1, 1024, 0, s>>>(d.cta_count, ctas, d.cta_off, nblocks_out, starts, capacity, T);
   if (cb) cb(user, "detect_scatter");
-  if (pyramid)
-    k_scatter_pyramid<<<ctas, 256, 0, s>>>(masks, tile_hot, tile_count, cta_off, tiles, starts, capacity);
-  else
-    k_scatter_starts<<<ctas, 256, 0, s>>>(masks, tile_count, cta_off, tiles, starts, capacity);
+  k_scatter_starts<<<ctas, 256, 0, s>>>(d.masks, d.tile_count, d.cta_off, tiles, starts, capacity);
   return 3;
 }
 
-// device address of the hot sub-block count of the last pass
+// device address of the hot sub-block count of the last pyramid pass
 const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T) {
-  const uint64_t tiles = (T + kTile - 1) / kTile;
-  const uint4* masks = reinterpret_cast<const uint4*>(scratch);
-  return reinterpret_cast<const unsigned long long*>(masks + tiles * 32 + tiles) + 1;
+  return carve_scratch(const_cast<void*>(scratch), T).hot_counter + 1;
 }
 
 }  // namespace hml

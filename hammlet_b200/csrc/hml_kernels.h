@@ -24,11 +24,11 @@ typedef void (*stage_cb_t)(void* user, const char* name);
 size_t detect_scratch_bytes(uint64_t T);
 // flags -> counts -> ordered block starts; returns the number of kernels launched.  smax != nullptr: pyramid
 // mode (only sub-blocks of 32 weights whose maximum reaches the threshold are read), else the streaming kernel.
-int launch_detect(const float* w, const float* smax, uint64_t T, float thr, int force_first, void* scratch,
+int launch_detect(const float* w, const uint16_t* smax, uint64_t T, float thr, int force_first, void* scratch,
                   uint32_t* starts, uint64_t capacity, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
                   void* user);
-size_t pyramid_floats(uint64_t T);
-void launch_build_pyramid(const float* w, uint64_t T, float* smax, int sms, cudaStream_t s);
+size_t pyramid_entries(uint64_t T);  // bf16 entries, one per 32 weights, padded to whole spans
+void launch_build_pyramid(const float* w, uint64_t T, uint16_t* smax, int sms, cudaStream_t s);
 const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);
 
 // ---- block-level sweep kernels (hml_sweep.cu)

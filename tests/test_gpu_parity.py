@@ -138,7 +138,10 @@ def test_pyramid_and_stream_detection_agree_on_hostile_weights(dev):
     dev.set_detect_mode(capi.DETECT_PYRAMID)
     B = dev.create_blocks(1.2)
     mode, hot = dev.detect_info()
-    assert mode == capi.DETECT_PYRAMID and 0 < hot <= B     # every hot sub-block holds at least one boundary
+    # the pyramid holds sub-block maxima rounded UP to bf16: every sub-block with a boundary is hot, and the
+    # rounding flags only a few more
+    true_hot = np.unique(dev.blocks(stats=False) // 32).size
+    assert mode == capi.DETECT_PYRAMID and true_hot <= hot <= true_hot * 1.1 + 8
 
 
 def test_block_stats_vs_exact_sums(dev):
