@@ -1,6 +1,7 @@
 // hammlet_b200 — templated block-level kernels of one Gibbs sweep (included by hml_sweep.cu, which carries
 // the overview, and by hml_sweep_inst.cu, which instantiates them per padded state count).
 #pragma once
+#include <cooperative_groups.h>
 #include <math.h>
 #include <string.h>
 
@@ -497,6 +498,273 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_fwd_chunks_prefix (K <= 8): as k_fwd_chunks, but what it leaves in chunk_ops is, for every chunk, the
+// ordered product of the EARLIER chunk operators of its tile (exclusive prefix; identity for chunk 0), so that
+// the replay kernel gets the vector entering a chunk from one vector-operator product instead of a serial walk.
+//   rows    thread (chunk, row): row recursion over the 32 blocks of the chunk; emission terms loaded four
+//           steps at a time, exact power-of-two rescaling every fourth step
+//   scan    work-efficient exclusive scan over the 32 chunk operators in shared memory (up-sweep: tile
+//           operator; down-sweep: prefixes); products are formed in registers between two barriers because a
+//           node's operand is overwritten in place
+template <int KP>
+__global__ void __launch_bounds__(FwdCfg<KP>::THREADS, (KP <= 5 ? 4 : (KP <= 6 ? 3 : 2))) k_fwd_chunks_prefix(SweepBuffers buf, ModelDev<KP> m) {
+  constexpr int L = Layout::L, C = Layout::C;
+  static_assert(FwdCfg<KP>::CG == C && L % 4 == 0, "small-K configuration");
+  __shared__ double s_ops[C * KP * KP];
+  __shared__ int s_exp[C * KP];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const int c = threadIdx.x / KP, i = threadIdx.x % KP;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (c < C) {
+      const uint64_t first = tile * Layout::TB + (uint64_t)c * L;
+      int steps = 0;
+      if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+      double r[KP];
+      int rex = 0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+      const double* ep = buf.e + Layout::at(tile, c, 0) * KP;
+#pragma unroll 1
+      for (int t0 = 0; t0 < steps; t0 += 4) {
+        double ev[4][KP];  // emission terms of four steps: all loads in flight before the first use
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int j = 0; j < KP; ++j) ev[q][j] = (t0 + q < steps) ? ep[(uint64_t)(t0 + q) * C * KP + j] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (t0 + q < steps) {
+            double y[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) y[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+#pragma unroll
+              for (int j = 0; j < KP; ++j) y[j] = fma(r[k], m.A[k][j], y[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < KP; ++j) r[j] = y[j] * ev[q][j];
+          }
+        }
+        // four steps shrink the largest entry by at most min(A)^4 unless the product dies; a row that underflows
+        // here is reported like a dead one and the host falls back to the exact sequential recursion
+        if (rex != kDeadExp) renorm_pow2<KP>(r, rex);
+      }
+#pragma unroll
+      for (int j = 0; j < KP; ++j) s_ops[(c * KP + i) * KP + j] = r[j];
+      s_exp[c * KP + i] = rex;
+    }
+    __syncthreads();
+    // ---- up-sweep: node at index n = (k+1)*2*stride - 1 becomes (its left neighbour's product) x (itself)
+    const int pr = threadIdx.x / KP, row = threadIdx.x % KP;
+    for (int stride = 1; stride < C; stride <<= 1) {
+      const int n = (pr + 1) * 2 * stride - 1;
+      const bool on = n < C;
+      double r[KP];
+      int rex = 0;
+      if (on) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = s_ops[((n - stride) * KP + row) * KP + j];
+        rex = s_exp[(n - stride) * KP + row];
+        row_times_op<KP, false>(r, rex, s_ops + n * KP * KP, s_exp + n * KP);
+      }
+      __syncthreads();
+      if (on) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) s_ops[(n * KP + row) * KP + j] = r[j];
+        s_exp[n * KP + row] = rex;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < KP) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        buf.tile_ops[(tile * KP + threadIdx.x) * KP + j] = s_ops[((C - 1) * KP + threadIdx.x) * KP + j];
+        s_ops[((C - 1) * KP + threadIdx.x) * KP + j] = (j == (int)threadIdx.x) ? 1.0 : 0.0;  // root prefix: identity
+      }
+      buf.tile_exp[tile * KP + threadIdx.x] = s_exp[(C - 1) * KP + threadIdx.x];
+      s_exp[(C - 1) * KP + threadIdx.x] = 0;
+    }
+    __syncthreads();
+    // ---- down-sweep: left child takes the node's prefix, right child takes prefix x (left child's product)
+    for (int stride = C / 2; stride >= 1; stride >>= 1) {
+      const int n = (pr + 1) * 2 * stride - 1;
+      const bool on = n < C;
+      double pfx[KP], r[KP];
+      int pex = 0, rex = 0;
+      if (on) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) pfx[j] = r[j] = s_ops[(n * KP + row) * KP + j];
+        pex = rex = s_exp[n * KP + row];
+        row_times_op<KP, false>(r, rex, s_ops + (n - stride) * KP * KP, s_exp + (n - stride) * KP);
+      }
+      __syncthreads();
+      if (on) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          s_ops[((n - stride) * KP + row) * KP + j] = pfx[j];
+          s_ops[(n * KP + row) * KP + j] = r[j];
+        }
+        s_exp[(n - stride) * KP + row] = pex;
+        s_exp[n * KP + row] = rex;
+      }
+      __syncthreads();
+    }
+    // ---- prefixes to global memory (coalesced)
+    for (int k = threadIdx.x; k < C * KP * KP; k += blockDim.x) buf.chunk_ops[tile * C * KP * KP + k] = s_ops[k];
+    for (int k = threadIdx.x; k < C * KP; k += blockDim.x) buf.chunk_exp[tile * C * KP + k] = s_exp[k];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fwd_replay_prefix (K <= 8): one warp per tile, lane c owns chunk c.  The vector entering the chunk is
+// normalise(vector entering the tile x prefix operator of the chunk); then the reference's own recursion
+// alpha_t = e_t o (alpha_{t-1} A) runs over the chunk, with e arriving in slabs of kSlab steps by
+// double-buffered bulk copies.
+//   kExact   every step divides by the forward sum like the reference (FB.hpp:101-105); required for the
+//            log-likelihood and for kept rows
+//   !kExact  every step rescales by an exact power of two instead: the rows written are c_t * alpha_t with
+//            c_t = 2^k, which is all the backward pass needs (it normalises its weights itself)
+template <int KP>
+struct ReplayCfg {
+  static constexpr int kSlab = 4;                                                    // steps per stage
+  static constexpr size_t kStage = (size_t)kSlab * Layout::C * KP * sizeof(double);  // e of a slab
+  static constexpr size_t kSmem = 2 * kStage;
+};
+
+template <int KP, bool kExact, bool kLoglik>
+__global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m) {
+  using Cfg = ReplayCfg<KP>;
+  constexpr int L = Layout::L, C = Layout::C, S = Cfg::kSlab, NS = L / S;
+  static_assert(!kLoglik || kExact, "the log-likelihood needs the forward sums");
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  unsigned char* stage0 = s_dyn;
+  unsigned char* stage1 = s_dyn + Cfg::kStage;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const int lane = threadIdx.x;
+  const int K = m.K;
+  if (lane == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_init_fence();
+  }
+  __syncwarp();
+  uint32_t ph0 = 0, ph1 = 0;
+  double ll = 0.0;
+  unsigned fallbacks = 0;
+  auto issue_slab = [&](uint64_t tile, int slab, unsigned char* dst, uint64_t* bar) {
+    const uint64_t off = (tile * Layout::TB + (uint64_t)slab * S * C) * KP;
+    mbar_expect_tx(bar, (uint32_t)Cfg::kStage);
+    bulk_g2s(dst, buf.e + off, (uint32_t)Cfg::kStage, bar);
+  };
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (lane == 0) {
+      fence_proxy_async();
+      issue_slab(tile, 0, stage0, &s_bar[0]);
+      issue_slab(tile, 1, stage1, &s_bar[1]);
+    }
+    const int c = lane;
+    const uint64_t first = tile * Layout::TB + (uint64_t)c * L;
+    int steps = 0;
+    if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+    // ---- vector entering chunk c
+    double a[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = buf.tile_ain[tile * KP + j];
+    if (c > 0 && steps > 0) {
+      OpVals<KP> o;
+      load_op<KP>(o, buf.chunk_ops + (tile * C + c) * KP * KP, buf.chunk_exp + (tile * C + c) * KP);
+      if (!vec_apply_op<KP>(a, o)) fallbacks++;
+    }
+#pragma unroll 1
+    for (int slab = 0; slab < NS; ++slab) {
+      const int bi = slab & 1;
+      if (bi == 0) {
+        mbar_wait(&s_bar[0], ph0);
+        ph0 ^= 1u;
+      } else {
+        mbar_wait(&s_bar[1], ph1);
+        ph1 ^= 1u;
+      }
+      const double* se = reinterpret_cast<const double*>(bi ? stage1 : stage0);
+#pragma unroll
+      for (int tt = 0; tt < S; ++tt) {
+        const int t = slab * S + tt;
+        if (t < steps) {
+          const uint64_t p = Layout::at(tile, c, t);
+          const double* ev = se + (tt * C + c) * KP;
+          double f[KP];
+#pragma unroll
+          for (int j = 0; j < KP; ++j) f[j] = 0.0;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
+          }
+          if (kExact) {
+            double fs = 0.0;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+              f[j] *= ev[j];
+              fs += f[j];
+            }
+            if (fs != 0.0) {  // FB.hpp:101-105
+              const double inv = 1.0 / fs;
+#pragma unroll
+              for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
+              if (kLoglik) ll += buf.maxE[p] + log(fs);
+            } else {          // FB.hpp:106-111: uniform fallback (the host then re-runs the sweep sequentially)
+              fallbacks++;
+#pragma unroll
+              for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
+            }
+          } else {
+            double mxv = 0.0;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+              f[j] *= ev[j];
+              mxv = fmax(mxv, f[j]);
+            }
+            if (mxv > 0.0) {
+              int e2 = exponent_of(mxv);
+              if (e2 < -1000) e2 = -1000;
+              const double sc = pow2i(-e2);
+#pragma unroll
+              for (int j = 0; j < KP; ++j) a[j] = f[j] * sc;
+            } else {
+              fallbacks++;
+#pragma unroll
+              for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
+        }
+      }
+      __syncwarp();
+      if (slab + 2 < NS && lane == 0) {
+        fence_proxy_async();
+        issue_slab(tile, slab + 2, bi ? stage1 : stage0, bi ? &s_bar[1] : &s_bar[0]);
+      }
+    }
+    __syncwarp();
+  }
+  if (kLoglik) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ll += shfl_xor_double(ll, o);
+    if (lane == 0) buf.partials[blockIdx.x] = ll;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
+  if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[KP + KP * KP], (unsigned long long)fallbacks);
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_fwd_tilescan: one CTA of 1024 threads.
 //   step 1  thread (group, row): operator of each group of S consecutive tiles (row recursion, operators
 //           prefetched one tile ahead for K <= 8)
@@ -527,7 +795,7 @@ __device__ __forceinline__ void load_gathered_op(OpVals<KP>& o, const double* g)
 //   step 2  thread 0: forward vector entering each group (G sequential operator applications)
 //   step 3  thread per group: forward vector entering each of its tiles
 template <int KP, int kPhase>
-__global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, ModelDev<KP> m) {
+__global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, ModelDev<KP> m, int skip_upto) {
   constexpr int GMAX = 256 / KP < 48 ? 256 / KP : 48;
   __shared__ double s_gain[GMAX][KP];
   __shared__ double s_gop[GMAX * KP * KP];
@@ -542,6 +810,7 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
     G = (nt + S - 1) / S;
   }
   if (kPhase == 0 && nt == 0) return;
+  if (nt <= skip_upto) return;  // the cluster kernel took this sweep
   if (kPhase != 2) {
     const int g = threadIdx.x / KP, i = threadIdx.x % KP;
     if (g < G) {
@@ -633,6 +902,172 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
       cur = nxt;
     }
   }
+}
+
+// Small K, cluster version: 8 CTAs of one thread-block cluster split the tile operators among them and keep
+// their share in shared memory (one coalesced load with every access in flight), so that none of the serial walks
+// below ever waits on global memory:
+//   step 1  thread (subgroup, row): operator of each subgroup of S consecutive tiles, S ~ sqrt(own tiles)
+//   step 2  pairwise tree over the subgroup operators -> the CTA's operator, published in shared memory
+//   step 3  after a cluster barrier, thread 0 of CTA r applies the operators of CTAs 0..r-1 (distributed shared
+//           memory) to the start vector and walks its own subgroups
+//   step 4  thread per subgroup: forward vector entering each of its tiles
+// Handles up to kClusterCtas * CAP tiles; larger sweeps are left to k_fwd_tilescan_small, launched right after.
+constexpr int kClusterCtas = 8;
+template <int KP>
+struct ClusterScanCfg {
+  static constexpr int CAP = KP <= 5 ? 512 : (KP <= 6 ? 384 : 224);  // tiles per CTA
+  static constexpr int SGMAX = 32;
+  static constexpr size_t kSmem = (size_t)CAP * (KP * KP * sizeof(double) + KP * sizeof(int));
+  static constexpr int kMaxTiles = kClusterCtas * CAP;
+};
+
+template <int KP, int kPhase>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(256)
+    k_fwd_tilescan_cluster(SweepBuffers buf, ModelDev<KP> m) {
+  namespace cg = cooperative_groups;
+  using Cfg = ClusterScanCfg<KP>;
+  constexpr int SGMAX = Cfg::SGMAX;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  double* s_op = reinterpret_cast<double*>(s_dyn);
+  int* s_ex = reinterpret_cast<int*>(s_op + (size_t)Cfg::CAP * KP * KP);
+  __shared__ double s_gop[SGMAX * KP * KP];   // subgroup operators (kept for step 3)
+  __shared__ int s_gex[SGMAX * KP];
+  __shared__ double s_tree[SGMAX * KP * KP];  // working copy consumed by the tree
+  __shared__ int s_treex[SGMAX * KP];
+  __shared__ double s_cop[KP * KP];           // this CTA's operator, read by the other CTAs of the cluster
+  __shared__ int s_cex[KP];
+  __shared__ double s_gain[SGMAX][KP];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
+  if (nt > Cfg::kMaxTiles) return;  // uniform over the cluster: nobody reaches a cluster barrier
+  const int per = (nt + kClusterCtas - 1) / kClusterCtas;
+  const int t0 = min(nt, rank * per), t1 = min(nt, t0 + per), n_own = t1 - t0;
+  // ---- step 0
+  {
+    const double* src = buf.tile_ops + (uint64_t)t0 * KP * KP;
+    for (int i = tid; i < n_own * KP * KP; i += 256) s_op[i] = src[i];
+    const int* srx = buf.tile_exp + (uint64_t)t0 * KP;
+    for (int i = tid; i < n_own * KP; i += 256) s_ex[i] = srx[i];
+  }
+  int S = 1, SG = 0;
+  if (n_own > 0) {
+    S = (int)ceil(sqrt((double)n_own));
+    if (S * SGMAX < n_own) S = (n_own + SGMAX - 1) / SGMAX;
+    SG = (n_own + S - 1) / S;
+  }
+  __syncthreads();
+  // ---- step 1
+  {
+    const int g = tid / KP, i = tid % KP;
+    if (g < SG) {
+      double r[KP];
+      int rex = 0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+      const int a = g * S, b = min(n_own, a + S);
+#pragma unroll 1
+      for (int t = a; t < b; ++t) row_times_op<KP, false>(r, rex, s_op + t * KP * KP, s_ex + t * KP);
+#pragma unroll
+      for (int j = 0; j < KP; ++j) s_gop[(g * KP + i) * KP + j] = s_tree[(g * KP + i) * KP + j] = r[j];
+      s_gex[g * KP + i] = s_treex[g * KP + i] = rex;
+    }
+  }
+  __syncthreads();
+  // ---- step 2
+  for (int stride = 1; stride < SG; stride <<= 1) {
+    const int pr = tid / KP, row = tid % KP;
+    const int a = pr * 2 * stride, b = a + stride;
+    if (b < SG) {
+      double r[KP];
+#pragma unroll
+      for (int j = 0; j < KP; ++j) r[j] = s_tree[(a * KP + row) * KP + j];
+      int rex = s_treex[a * KP + row];
+      row_times_op<KP, false>(r, rex, s_tree + b * KP * KP, s_treex + b * KP);
+#pragma unroll
+      for (int j = 0; j < KP; ++j) s_tree[(a * KP + row) * KP + j] = r[j];
+      s_treex[a * KP + row] = rex;
+    }
+    __syncthreads();
+  }
+  if (tid < KP) {
+#pragma unroll
+    for (int j = 0; j < KP; ++j) s_cop[tid * KP + j] = SG ? s_tree[tid * KP + j] : (j == tid ? 1.0 : 0.0);
+    s_cex[tid] = SG ? s_treex[tid] : 0;
+  }
+  cluster.sync();
+  if (kPhase == 1) {
+    // segment operator: row i of the ordered product of the CTA operators (identity without blocks)
+    if (rank == 0 && tid < KP) {
+      const int i = tid;
+      double r[KP];
+      int rex = 0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+#pragma unroll 1
+      for (int p = 0; p < kClusterCtas; ++p) {
+        if (min(nt, p * per) >= nt) break;  // CTA p and the later ones own no tile
+        row_times_op<KP, false>(r, rex, cluster.map_shared_rank(s_cop, p), cluster.map_shared_rank(s_cex, p));
+      }
+#pragma unroll
+      for (int j = 0; j < KP; ++j) buf.seg.send_op[i * KP + j] = r[j];
+      buf.seg.send_op[KP * KP + i] = (double)rex;
+    }
+    cluster.sync();  // shared memory of every CTA stays alive until CTA 0 has read it
+    return;
+  }
+  // ---- step 3
+  if (tid == 0 && n_own > 0) {
+    double a[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = m.pi[j];  // row 0 of the trellis is pi itself (FB.hpp:57)
+    if (kPhase == 2) {
+#pragma unroll 1
+      for (int r = 0; r < buf.seg.rank; ++r) {
+        OpVals<KP> o;
+        load_gathered_op<KP>(o, buf.seg.ops + (size_t)r * (KP * KP + KP));
+        if (buf.seg.heads[4 * r] > 0.0 && !vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      }
+    }
+#pragma unroll 1
+    for (int p = 0; p < rank; ++p) {
+      OpVals<KP> o;
+      load_op<KP>(o, cluster.map_shared_rank(s_cop, p), cluster.map_shared_rank(s_cex, p));
+      if (!vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+    }
+#pragma unroll 1
+    for (int g = 0; g < SG; ++g) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) s_gain[g][j] = a[j];
+      if (g + 1 < SG) {
+        OpVals<KP> o;
+        load_op<KP>(o, s_gop + g * KP * KP, s_gex + g * KP);
+        if (!vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- step 4
+  if (tid < SG) {
+    double a[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = s_gain[tid][j];
+    const int lo = tid * S, hi = min(n_own, lo + S);
+#pragma unroll 1
+    for (int t = lo; t < hi; ++t) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) buf.tile_ain[(uint64_t)(t0 + t) * KP + j] = a[j];
+      if (t + 1 < hi) {
+        OpVals<KP> o;
+        load_op<KP>(o, s_op + t * KP * KP, s_ex + t * KP);
+        if (!vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+      }
+    }
+  }
+  cluster.sync();  // no CTA leaves while another may still read its operator
 }
 
 template <int KP, int kPhase>
@@ -1245,34 +1680,49 @@ __global__ void k_mix_qend(SweepBuffers buf) {
   buf.tile_qin[(B - 1) / Layout::TB] = (uint8_t)q_end;
 }
 
-// phase 0: single handle; 1 / 2: before / after the all-gather of the segment operators
-template <int KP>
-void launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, int phase, cudaStream_t s) {
+// phase 0: single handle; 1 / 2: before / after the all-gather of the segment operators.  Returns the number of
+// launches.  K <= 8: the cluster kernel handles sweeps of up to kMaxTiles tiles; if the block arrays could hold
+// more than that, the single-CTA kernel is launched too and takes over exactly when the cluster kernel stood down
+// (the block count is only known on the device).
+template <int KP, int kPhase>
+int launch_fwd_tilescan_phase(const SweepBuffers& b, const ModelDev<KP>& m, uint64_t ntiles_hint, cudaStream_t s) {
   if constexpr (KP <= 8) {
-    if (phase == 0) k_fwd_tilescan_small<KP, 0><<<1, 256, 0, s>>>(b, m);
-    if (phase == 1) k_fwd_tilescan_small<KP, 1><<<1, 256, 0, s>>>(b, m);
-    if (phase == 2) k_fwd_tilescan_small<KP, 2><<<1, 256, 0, s>>>(b, m);
+    using Cfg = ClusterScanCfg<KP>;
+    // per device, so set on every launch (a host-side table lookup)
+    cudaFuncSetAttribute(k_fwd_tilescan_cluster<KP, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    k_fwd_tilescan_cluster<KP, kPhase><<<kClusterCtas, 256, Cfg::kSmem, s>>>(b, m);
+    if (ntiles_hint <= (uint64_t)Cfg::kMaxTiles) return 1;
+    k_fwd_tilescan_small<KP, kPhase><<<1, 256, 0, s>>>(b, m, Cfg::kMaxTiles);
+    return 2;
   } else {
-    if (phase == 0) k_fwd_tilescan<KP, 0><<<1, 1024, 0, s>>>(b, m);
-    if (phase == 1) k_fwd_tilescan<KP, 1><<<1, 1024, 0, s>>>(b, m);
-    if (phase == 2) k_fwd_tilescan<KP, 2><<<1, 1024, 0, s>>>(b, m);
+    k_fwd_tilescan<KP, kPhase><<<1, 1024, 0, s>>>(b, m);
+    return 1;
   }
+}
+template <int KP>
+int launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, int phase, uint64_t ntiles_hint, cudaStream_t s) {
+  if (phase == 0) return launch_fwd_tilescan_phase<KP, 0>(b, m, ntiles_hint, s);
+  if (phase == 1) return launch_fwd_tilescan_phase<KP, 1>(b, m, ntiles_hint, s);
+  return launch_fwd_tilescan_phase<KP, 2>(b, m, ntiles_hint, s);
 }
 
 // maps -> chunk/tile maps -> suffix scan over tiles -> states; returns the number of launches
 template <int KP>
 int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLaunch& l, bool rows, uint64_t nb,
-                    cudaStream_t s, stage_cb_t cb, void* user) {
+                    cudaStream_t s, stage_cb_t cb, void* user, bool have_maps = false) {
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
-  int launches = 4;
-  if (cb) cb(user, "bwd_maps");
-  const int gm = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
-  if (rows)
-    k_bwd_maps<KP, true><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
-  else
-    k_bwd_maps<KP, false><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
-  if (cb) cb(user, "bwd_chunkmaps");
-  k_bwd_chunkmaps<KP><<<grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s>>>(b);
+  int launches = 2;
+  if (!have_maps) {  // k_replay_maps already wrote the block, chunk and tile maps
+    launches += 2;
+    if (cb) cb(user, "bwd_maps");
+    const int gm = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
+    if (rows)
+      k_bwd_maps<KP, true><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
+    else
+      k_bwd_maps<KP, false><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
+    if (cb) cb(user, "bwd_chunkmaps");
+    k_bwd_chunkmaps<KP><<<grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s>>>(b);
+  }
   if (b.seg.world > 1) {
     if (cb) cb(user, "bwd_segmap");
     k_bwd_scan<KP, true><<<1, 1024, 0, s>>>(b);
@@ -1312,6 +1762,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   stage("clear");
   k_clear_out<KP><<<1, 256, 0, s>>>(b);
   ++launches;
+  constexpr bool kPrefix = KP <= 8;  // k_fwd_chunks_prefix + k_fwd_replay_prefix
   stage("block_emit");
   {
     const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
@@ -1341,28 +1792,42 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     }
   } else {
     stage("fwd_chunks");
-    k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
+    if constexpr (kPrefix)
+      k_fwd_chunks_prefix<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
+    else
+      k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
     ++launches;
     stage("fwd_tilescan");
     if (seg) {
-      launch_fwd_tilescan<KP>(b, m, 1, s);
+      launches += launch_fwd_tilescan<KP>(b, m, 1, ntiles, s);
       stage("exchange_ops");
       if (l.exchange(l.exchange_user, kExchangeOps) != 0) return -1;
       stage("fwd_tilescan2");
-      launch_fwd_tilescan<KP>(b, m, 2, s);
-      ++launches;
+      launches += launch_fwd_tilescan<KP>(b, m, 2, ntiles, s);
     } else {
-      launch_fwd_tilescan<KP>(b, m, 0, s);
+      launches += launch_fwd_tilescan<KP>(b, m, 0, ntiles, s);
     }
-    ++launches;
     stage("fwd_replay");
     const int gr = grid_for(ntiles, 1, l.sms, 32);
-    if (loglik) {
-      k_fwd_replay<KP, true><<<gr, 32, 0, s>>>(b, m);
-      k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, gr, b.out_f64 + 2 * KP);
-      ++launches;
+    if constexpr (kPrefix) {
+      using RCfg = ReplayCfg<KP>;
+      if (loglik) {
+        k_fwd_replay_prefix<KP, true, true><<<gr, 32, RCfg::kSmem, s>>>(b, m);
+        k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, gr, b.out_f64 + 2 * KP);
+        ++launches;
+      } else if (rows) {
+        k_fwd_replay_prefix<KP, true, false><<<gr, 32, RCfg::kSmem, s>>>(b, m);
+      } else {
+        k_fwd_replay_prefix<KP, false, false><<<gr, 32, RCfg::kSmem, s>>>(b, m);
+      }
     } else {
-      k_fwd_replay<KP, false><<<gr, 32, 0, s>>>(b, m);
+      if (loglik) {
+        k_fwd_replay<KP, true><<<gr, 32, 0, s>>>(b, m);
+        k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, gr, b.out_f64 + 2 * KP);
+        ++launches;
+      } else {
+        k_fwd_replay<KP, false><<<gr, 32, 0, s>>>(b, m);
+      }
     }
     ++launches;
     const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
