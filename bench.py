@@ -357,7 +357,7 @@ def main():
     if world == 1:
         wl = workload
     elif segments:
-        wl = f"{workload}; split into {world} contiguous segments, one per GPU, scan carries exchanged with NCCL all-gathers"
+        wl = f"{workload}; split into {world} contiguous segments, one per GPU, scan carries exchanged over NVLink peer memory (NCCL fallback)"
     else:
         wl = f"{world} independent sequences, one per GPU, each: " + workload
 
@@ -371,6 +371,7 @@ def main():
                    "l2_policy": f"inputs larger than L2 (per GPU and sweep: {T_local / 16e9:.3f} GB pyramid + {128.0 * hot / 1e9:.3f} GB of "
                                 f"hot weight sub-blocks + the block-level arrays vs 126 MB L2; weights {4.0 * T_local / 1e9:.2f} GB)",
                    "detect_mode": "pyramid", "hot_subblocks_per_sweep": hot,
+                   "carry_exchange": h.exchange_transport(),
                    "load_seconds": t_load},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

@@ -38,7 +38,8 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
            "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream",
            "hml_comm_unique_id", "hml_comm_init", "hml_segment_plan", "hml_load_segment_f32",
-           "hml_load_segment_f32_device", "hml_segment_info", "hml_set_detect_mode", "hml_detect_info",
+           "hml_load_segment_f32_device", "hml_segment_info", "hml_exchange_transport", "hml_set_detect_mode",
+           "hml_detect_info",
            # include/hammlet_host.h
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run"]
@@ -142,6 +143,12 @@ class Handle:
         self._ck(self.lib.hml_load_segment_f32_device(self.h, C.c_void_p(dev_ptr), C.c_uint64(n), C.c_uint64(T),
                                                       C.c_float(weight_multiplier)))
         self.T = int(T)
+
+    def exchange_transport(self):
+        """'peer' (mailboxes written over NVLink), 'nccl' (all-gathers) or 'none' (single handle)."""
+        t = C.c_int()
+        self._ck(self.lib.hml_exchange_transport(self.h, C.byref(t)))
+        return {0: "none", 1: "peer", 2: "nccl"}[t.value]
 
     def segment_info(self):
         r, w = C.c_int(), C.c_int()

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <nccl.h>  // types only: the library is loaded with dlopen in hml_comm_init (single-GPU use needs no NCCL)
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -69,6 +70,12 @@ struct hml_ctx {
   int rank = 0, world = 1;
   uint64_t T_global = 0, seg_start = 0;
   uint64_t first_block = 0, global_blocks = 0;  // of the last sweep / block structure
+  bool p2p = false;                             // carries travel through peer mailboxes (else NCCL all-gathers)
+  unsigned char* mbox = nullptr;                // this rank's mailbox (peers write into it over NVLink)
+  P2PPeers peers = {};                          // every rank's mailbox as mapped here
+  uint64_t p2p_seq[kP2PSlots] = {0, 0, 0, 0};
+  unsigned int* p2p_timeout_host = nullptr;     // mapped host word raised by an exchange that gave up waiting
+  unsigned int* p2p_timeout_dev = nullptr;
   double* seg_dev = nullptr;                    // send slots + gathered carries (one allocation)
   unsigned long long* stats_gather = nullptr;   // world x kOutWords
   unsigned long long* stats_gather_host = nullptr;
@@ -272,16 +279,36 @@ int all_gather(hml_t* h, const void* send, void* recv, size_t bytes) {
   return HML_OK;
 }
 
+enum { kSlotHeads = 0, kSlotOps = 1, kSlotMaps = 2, kSlotStats = 3 };
+
+// per-sweep carry exchange: peer mailboxes over NVLink (one kernel) or, without peer access, an NCCL all-gather
+int exchange(hml_t* h, int slot, const void* send, void* recv, size_t bytes) {
+  if (!h->p2p) return all_gather(h, send, recv, bytes);
+  if (bytes % 8 != 0 || bytes > kP2PPayload) return fail(h, HML_ERR_ARG, "carry payload does not fit a mailbox entry");
+  launch_p2p_exchange(h->peers, h->rank, h->world, slot, ++h->p2p_seq[slot], send, bytes, recv, h->p2p_timeout_dev,
+                      h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  return HML_OK;
+}
+
+// after a stream synchronisation: did an exchange give up waiting for a peer?
+int check_exchange(hml_t* h) {
+  if (h->p2p && h->p2p_timeout_host && *h->p2p_timeout_host)
+    return fail(h, HML_ERR_CUDA, "carry exchange timed out waiting for a peer rank");
+  return HML_OK;
+}
+
 // all-gathers one of the per-sweep carries (send slot -> gathered array), on the handle's stream
 int exchange_cb(void* user, int which) {
   hml_t* h = (hml_t*)user;
   SweepBuffers b = make_buffers(h, h->KP ? h->KP : 2);
   switch (which) {
-    case kExchangeHeads: return all_gather(h, b.seg.send_head, (void*)b.seg.heads, 4 * sizeof(double));
-    case kExchangeMaps: return all_gather(h, b.seg.send_map, (void*)b.seg.maps, 4 * sizeof(uint64_t));
+    case kExchangeHeads: return exchange(h, kSlotHeads, b.seg.send_head, (void*)b.seg.heads, 4 * sizeof(double));
+    case kExchangeMaps: return exchange(h, kSlotMaps, b.seg.send_map, (void*)b.seg.maps, 4 * sizeof(uint64_t));
     case kExchangeOps: {
       const size_t n = (size_t)h->KP * h->KP + h->KP;
-      return all_gather(h, b.seg.send_op, (void*)b.seg.ops, n * sizeof(double));
+      return exchange(h, kSlotOps, b.seg.send_op, (void*)b.seg.ops, n * sizeof(double));
     }
     default: return HML_ERR_ARG;
   }
@@ -620,7 +647,7 @@ int fetch_result(hml_t* h, int KP, SweepResult& res) {
   const int world = h->world > 1 ? h->world : 1;
   const unsigned long long* host = h->outblk_host;
   if (world > 1) {
-    int rc = all_gather(h, h->outblk, h->stats_gather, copy_words * 8);
+    int rc = exchange(h, kSlotStats, h->outblk, h->stats_gather, copy_words * 8);
     if (rc != HML_OK) return rc;
     CK(cudaMemcpyAsync(h->stats_gather_host, h->stats_gather, world * copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
     host = h->stats_gather_host;
@@ -628,6 +655,7 @@ int fetch_result(hml_t* h, int KP, SweepResult& res) {
     CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  if (int rc = check_exchange(h)) return rc;
   res.global_blocks = res.first_block = 0;
   res.any_overflow = res.own_overflow = false;
   for (int r = 0; r < world; ++r) {
@@ -762,6 +790,88 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
   return fail(h, HML_ERR_CAPACITY, "block capacity did not converge");
 }
 
+// Peer mailboxes for the per-sweep carries.  Every rank allocates its mailbox, the CUDA IPC handles travel by
+// one NCCL all-gather, every rank maps the others'.  Any failure (no peer access, IPC unavailable, or
+// HML_EXCHANGE=nccl in the environment) leaves the NCCL all-gathers in place; the decision is collective, so
+// all ranks use the same transport.
+int setup_p2p(hml_t* h) {
+  const int world = h->world;
+  const char* env = getenv("HML_EXCHANGE");
+  int ok = !(env && strcmp(env, "nccl") == 0) && world <= kP2PMaxWorld ? 1 : 0;
+  const size_t bytes = p2p_mailbox_bytes(world);
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMalloc((void**)&h->mbox, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaMemsetAsync(h->mbox, 0, bytes, h->stream) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, h->mbox) != cudaSuccess) ok = 0;
+  if (ok && cudaHostAlloc((void**)&h->p2p_timeout_host, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) ok = 0;
+  if (ok) {
+    *h->p2p_timeout_host = 0;
+    if (cudaHostGetDevicePointer((void**)&h->p2p_timeout_dev, h->p2p_timeout_host, 0) != cudaSuccess) ok = 0;
+  }
+  cudaGetLastError();
+  // round 1: handles + readiness of every rank
+  struct Msg {
+    cudaIpcMemHandle_t handle;
+    int ok;
+    int pad[3];
+  };
+  static_assert(sizeof(Msg) % 8 == 0, "Msg");
+  Msg msg;
+  memset(&msg, 0, sizeof(msg));
+  msg.handle = mine;
+  msg.ok = ok;
+  Msg *dsend = nullptr, *drecv = nullptr;
+  CK(dev_alloc(dsend, 1));
+  CK(dev_alloc(drecv, world));
+  std::vector<Msg> all(world);
+  CK(cudaMemcpyAsync(dsend, &msg, sizeof(Msg), cudaMemcpyHostToDevice, h->stream));
+  int rc = all_gather(h, dsend, drecv, sizeof(Msg));
+  if (rc != HML_OK) return rc;
+  CK(cudaMemcpyAsync(all.data(), drecv, world * sizeof(Msg), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < world; ++r) ok = ok && all[r].ok;
+  memset(&h->peers, 0, sizeof(h->peers));
+  if (ok) {
+    for (int r = 0; r < world && ok; ++r) {
+      if (r == h->rank) {
+        h->peers.box[r] = h->mbox;
+        continue;
+      }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0;
+        cudaGetLastError();
+      } else {
+        h->peers.box[r] = (unsigned char*)p;
+      }
+    }
+  }
+  // round 2: did every rank map every mailbox?
+  msg.ok = ok;
+  CK(cudaMemcpyAsync(dsend, &msg, sizeof(Msg), cudaMemcpyHostToDevice, h->stream));
+  rc = all_gather(h, dsend, drecv, sizeof(Msg));
+  if (rc != HML_OK) return rc;
+  CK(cudaMemcpyAsync(all.data(), drecv, world * sizeof(Msg), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < world; ++r) ok = ok && all[r].ok;
+  dev_free(dsend);
+  dev_free(drecv);
+  h->p2p = ok != 0;
+  return HML_OK;
+}
+
+void teardown_p2p(hml_t* h) {
+  for (int r = 0; r < kP2PMaxWorld; ++r)
+    if (h->peers.box[r] && r != h->rank) cudaIpcCloseMemHandle(h->peers.box[r]);
+  memset(&h->peers, 0, sizeof(h->peers));
+  if (h->mbox) cudaFree(h->mbox);
+  h->mbox = nullptr;
+  if (h->p2p_timeout_host) cudaFreeHost(h->p2p_timeout_host);
+  h->p2p_timeout_host = nullptr;
+  h->p2p = false;
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -848,6 +958,7 @@ int hml_destroy(hml_t* h) {
   dev_free(h->outblk);
   dev_free(h->seg_dev);
   dev_free(h->stats_gather);
+  teardown_p2p(h);
   if (h->stats_gather_host) cudaFreeHost(h->stats_gather_host);
   if (h->comm) g_nccl.CommDestroy(h->comm);
   if (h->outblk_host) cudaFreeHost(h->outblk_host);
@@ -938,7 +1049,7 @@ int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks) {
     // block counts of all ranks (a rank whose arrays were too small makes every rank repeat the call)
     const unsigned long long* host = h->outblk_host;
     if (world > 1) {
-      rc = all_gather(h, h->outblk, h->stats_gather, 16);
+      rc = exchange(h, kSlotStats, h->outblk, h->stats_gather, 16);
       if (rc != HML_OK) return rc;
       CK(cudaMemcpyAsync(h->stats_gather_host, h->stats_gather, world * 16, cudaMemcpyDeviceToHost, h->stream));
       host = h->stats_gather_host;
@@ -946,6 +1057,7 @@ int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks) {
       CK(cudaMemcpyAsync(h->outblk_host, h->outblk, 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
+    if ((rc = check_exchange(h)) != HML_OK) return rc;
     const uint64_t B = host[2 * (world > 1 ? h->rank : 0)];
     bool any_over = false;
     uint64_t total = 0, first = 0;
@@ -1114,7 +1226,7 @@ int hml_comm_init(hml_t* h, int rank, int world, const uint8_t id[HML_UNIQUE_ID_
   CK(dev_alloc(h->stats_gather, (size_t)world * kOutWords));
   CK(cudaMallocHost((void**)&h->stats_gather_host, (size_t)world * kOutWords * 8));
   CK(cudaStreamSynchronize(h->stream));
-  return HML_OK;
+  return setup_p2p(h);
 }
 
 int hml_segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t* len) {
@@ -1165,6 +1277,12 @@ int hml_segment_info(const hml_t* h, int* rank, int* world, uint64_t* seg_start,
   if (seg_len) *seg_len = h->T;
   if (first_block) *first_block = h->first_block;
   if (global_blocks) *global_blocks = h->world > 1 ? h->global_blocks : h->nblocks;
+  return HML_OK;
+}
+
+int hml_exchange_transport(const hml_t* h, int* transport) {
+  if (!h || !transport) return HML_ERR_ARG;
+  *transport = h->world <= 1 ? HML_EXCHANGE_NONE : (h->p2p ? HML_EXCHANGE_PEER : HML_EXCHANGE_NCCL);
   return HML_OK;
 }
 

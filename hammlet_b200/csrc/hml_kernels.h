@@ -31,6 +31,24 @@ size_t pyramid_entries(uint64_t T);  // bf16 entries, one per 32 weights, padded
 void launch_build_pyramid(const float* w, uint64_t T, uint16_t* smax, int sms, cudaStream_t s);
 const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);
 
+// ---- peer-memory carry exchange of the segment-split mode (hml_p2p.cu)
+constexpr int kP2PMaxWorld = 64;
+constexpr int kP2PSlots = 4;            // heads, operators, maps, statistics
+constexpr size_t kP2PHeader = 64;       // sequence number (8 bytes) + padding in front of each payload
+constexpr size_t kP2PPayload = 9216;    // largest payload: the result block of a K = 32 sweep
+constexpr unsigned long long kP2PTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+struct P2PPeers {
+  unsigned char* box[kP2PMaxWorld];  // mailbox of every rank as mapped into this process (own one included)
+};
+// entry written by rank `src` for exchange `slot`, sequence parity `parity`, inside any mailbox
+__host__ __device__ inline size_t p2p_entry_offset(int parity, int slot, int src, int world) {
+  return ((size_t)(parity * kP2PSlots + slot) * world + src) * (kP2PHeader + kP2PPayload);
+}
+inline size_t p2p_mailbox_bytes(int world) { return 2 * (size_t)kP2PSlots * world * (kP2PHeader + kP2PPayload); }
+// all-gather of `bytes` (a multiple of 8, <= kP2PPayload) per rank into recv (rank-major), one kernel per rank
+void launch_p2p_exchange(const P2PPeers& peers, int rank, int world, int slot, uint64_t seq, const void* send,
+                         size_t bytes, void* recv, unsigned int* timeout_flag_dev, cudaStream_t s);
+
 // ---- block-level sweep kernels (hml_sweep.cu)
 struct ModelHost {  // what the C ABI receives, validated
   int K;

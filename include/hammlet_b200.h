@@ -174,6 +174,14 @@ int hml_load_segment_f32_device(hml_t* h, const float* x_dev, uint64_t len, uint
 int hml_segment_info(const hml_t* h, int* rank, int* world, uint64_t* seg_start, uint64_t* seg_len,
                      uint64_t* first_block, uint64_t* global_blocks);
 
+/* How the per-sweep carries travel: peer mailboxes written over NVLink by one exchange kernel per rank
+ * (CUDA IPC mappings made in hml_comm_init), or NCCL all-gathers when peer mapping is unavailable or the
+ * environment says HML_EXCHANGE=nccl.  The choice is collective: all ranks use the same transport. */
+#define HML_EXCHANGE_NONE 0
+#define HML_EXCHANGE_PEER 1
+#define HML_EXCHANGE_NCCL 2
+int hml_exchange_transport(const hml_t* h, int* transport);
+
 /* ---- measurement ---------------------------------------------------------------------------- */
 
 /* With timing on, every kernel stage of a sweep is bracketed by CUDA events on the context's

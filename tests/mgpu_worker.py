@@ -56,6 +56,9 @@ def main():
     dist.broadcast_object_list(uid, 0)
     h = capi.Handle(dev)
     h.comm_init(rank, world, uid[0])
+    expect = os.environ.get("HML_EXPECT_TRANSPORT")
+    if expect:
+        assert h.exchange_transport() == expect, (h.exchange_transport(), expect)
     ref = capi.Handle(dev)
 
     cases = [  # T, K, L, thr, use_self
