@@ -13,9 +13,11 @@
 // Differences in construction are listed in INTEGRATION.md.
 #pragma once
 
+#include <cstdlib>
 #include <memory>
 
 #include "../../include/hammlet_b200.h"
+#include "FastParse.hpp"
 #include "Model.hpp"
 
 // Thin RAII owner of an hml_t; every C-ABI failure becomes std::runtime_error, like every reference error.
@@ -58,7 +60,8 @@ class DeviceSequence {
   double noiseStdev() const { return mSigmaHat; }
 };
 
-// Reads whitespace-separated numbers exactly like `input >> v` (wavelet.hpp:131) and loads them.
+// Reads whitespace-separated numbers with the result of `input >> v` (wavelet.hpp:131), through the
+// multi-threaded parser of FastParse.hpp, and loads them.
 inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size_t nrDim, const float weightMultiplier,
                             const size_t reserveT = 0) {
   if (nrDim <= 0) throw std::runtime_error("Number of dimensions must be positive!");
@@ -66,8 +69,13 @@ inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size
   if (!input) throw std::runtime_error("Cannot read input file or stream!");
   std::vector<float> values;
   values.reserve(reserveT);
-  float v;
-  while (input >> v) values.push_back(v);
+  if (std::getenv("HAMMLET_SLOW_PARSE")) {  // the reference's own extraction loop, kept for comparison
+    float v;
+    while (input >> v) values.push_back(v);
+  } else {
+    const std::string text = fastparse::slurp(input);
+    fastparse::parseFloats(text.data(), text.size(), values);
+  }
   seq.load(values, weightMultiplier);
 }
 
