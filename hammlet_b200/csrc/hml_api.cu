@@ -76,6 +76,7 @@ struct hml_ctx {
   uint64_t p2p_seq[kP2PSlots] = {0, 0, 0, 0};
   unsigned int* p2p_timeout_host = nullptr;     // mapped host word raised by an exchange that gave up waiting
   unsigned int* p2p_timeout_dev = nullptr;
+  P2PDev* p2p_dev = nullptr;                    // device copy of what the exchanging kernels need
   double* seg_dev = nullptr;                    // send slots + gathered carries (one allocation)
   unsigned long long* stats_gather = nullptr;   // world x kOutWords
   unsigned long long* stats_gather_host = nullptr;
@@ -264,6 +265,9 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
     b.seg.maps = (const uint64_t*)(d + 4 * (size_t)h->world);
     b.seg.ops = d + 8 * (size_t)h->world;
     b.seg.overflow = h->outblk + 1;
+    b.seg.p2p = h->p2p ? h->p2p_dev : nullptr;
+    b.seg.stats_send = h->outblk;
+    b.seg.stats_recv = h->stats_gather;
   }
   return b;
 }
@@ -279,14 +283,11 @@ int all_gather(hml_t* h, const void* send, void* recv, size_t bytes) {
   return HML_OK;
 }
 
-enum { kSlotHeads = 0, kSlotOps = 1, kSlotMaps = 2, kSlotStats = 3 };
-
 // per-sweep carry exchange: peer mailboxes over NVLink (one kernel) or, without peer access, an NCCL all-gather
 int exchange(hml_t* h, int slot, const void* send, void* recv, size_t bytes) {
   if (!h->p2p) return all_gather(h, send, recv, bytes);
   if (bytes % 8 != 0 || bytes > kP2PPayload) return fail(h, HML_ERR_ARG, "carry payload does not fit a mailbox entry");
-  launch_p2p_exchange(h->peers, h->rank, h->world, slot, ++h->p2p_seq[slot], send, bytes, recv, h->p2p_timeout_dev,
-                      h->stream);
+  launch_p2p_exchange(h->p2p_dev, slot, ++h->p2p_seq[slot], send, bytes, recv, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   return HML_OK;
@@ -315,6 +316,19 @@ int exchange_cb(void* user, int which) {
 }
 
 
+unsigned long long next_seq_cb(void* user, int which) {
+  hml_t* h = (hml_t*)user;
+  const int slot = which == kExchangeHeads ? kSlotHeads : which == kExchangeOps ? kSlotOps
+                 : which == kExchangeMaps ? kSlotMaps : kSlotStats;
+  return ++h->p2p_seq[slot];
+}
+
+size_t result_words(int KP) {  // 8-byte words of the result block that travel to the host (and between ranks)
+  size_t words = (size_t)KP + (size_t)KP * KP + 1;
+  words += words & 1;
+  return 2 + words + 2 * KP + 1;
+}
+
 int run_detect(hml_t* h, float thr) {
   h->launches += launch_detect(h->w, h->detect_mode == HML_DETECT_PYRAMID ? h->smax : nullptr, h->T, thr,
                                h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity, h->outblk, h->stream,
@@ -323,9 +337,10 @@ int run_detect(hml_t* h, float thr) {
   if (h->world > 1) {
     // the partial block in front of each rank's first boundary joins the last block of its owner
     stage_cb(h, "seg_head");
-    launch_seg_head(make_buffers(h, h->KP ? h->KP : 2), h->T, h->stream);
+    launch_seg_head(make_buffers(h, h->KP ? h->KP : 2), h->T, h->p2p ? ++h->p2p_seq[kSlotHeads] : 0ull, h->stream);
     h->launches++;
     CK(cudaGetLastError());
+    if (h->p2p) return HML_OK;  // the kernel exchanged the heads itself
     stage_cb(h, "exchange_heads");
     return exchange_cb(h, kExchangeHeads);
   }
@@ -638,17 +653,20 @@ struct SweepResult {
   bool any_overflow = false, own_overflow = false;
 };
 
-int fetch_result(hml_t* h, int KP, SweepResult& res) {
+// exchanged: the sweep's last kernel already gathered the result blocks of all ranks into stats_gather
+int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged) {
   size_t words = (size_t)KP + (size_t)KP * KP + 1;
   words += words & 1;
-  const size_t copy_words = 2 + words + 2 * KP + 1;
+  const size_t copy_words = result_words(KP);
   res.o64.assign(words, 0);
   res.of.assign(2 * KP + 1, 0.0);
   const int world = h->world > 1 ? h->world : 1;
   const unsigned long long* host = h->outblk_host;
   if (world > 1) {
-    int rc = exchange(h, kSlotStats, h->outblk, h->stats_gather, copy_words * 8);
-    if (rc != HML_OK) return rc;
+    if (!exchanged) {
+      int rc = exchange(h, kSlotStats, h->outblk, h->stats_gather, copy_words * 8);
+      if (rc != HML_OK) return rc;
+    }
     CK(cudaMemcpyAsync(h->stats_gather_host, h->stats_gather, world * copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
     host = h->stats_gather_host;
   } else {
@@ -735,14 +753,17 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     l.sms = h->sms;
     l.nblocks_hint = dynamic ? h->capacity : h->nblocks;
     l.exchange = exchange_cb;
+    l.next_seq = next_seq_cb;
     l.exchange_user = h;
+    const bool fused_stats = seg && h->p2p;
+    l.stats_words = fused_stats ? (uint32_t)result_words(KP) : 0u;
     const int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
     if (n == -2) return fail(h, HML_ERR_ARG, "unsupported number of states");
     if (n < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
     h->launches += n;
     CK(cudaGetLastError());
     SweepResult res;
-    rc = fetch_result(h, KP, res);
+    rc = fetch_result(h, KP, res, fused_stats);
     if (rc != HML_OK) return rc;
     if (dynamic && res.any_overflow) {  // some rank's block arrays were too small: grow and run the sweep again
       if (res.own_overflow) {
@@ -766,7 +787,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
       if (n2 < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
       h->launches += n2;
       CK(cudaGetLastError());
-      rc = fetch_result(h, KP, res);
+      rc = fetch_result(h, KP, res, fused_stats);
       if (rc != HML_OK) return rc;
       fallbacks = res.o64[KP + KP * KP];
     }
@@ -857,6 +878,17 @@ int setup_p2p(hml_t* h) {
   for (int r = 0; r < world; ++r) ok = ok && all[r].ok;
   dev_free(dsend);
   dev_free(drecv);
+  if (ok) {
+    P2PDev dev;
+    memset(&dev, 0, sizeof(dev));
+    dev.peers = h->peers;
+    dev.timeout_flag = h->p2p_timeout_dev;
+    dev.rank = h->rank;
+    dev.world = world;
+    CK(dev_alloc(h->p2p_dev, 1));
+    CK(cudaMemcpyAsync(h->p2p_dev, &dev, sizeof(dev), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   h->p2p = ok != 0;
   return HML_OK;
 }
@@ -867,6 +899,7 @@ void teardown_p2p(hml_t* h) {
   memset(&h->peers, 0, sizeof(h->peers));
   if (h->mbox) cudaFree(h->mbox);
   h->mbox = nullptr;
+  dev_free(h->p2p_dev);
   if (h->p2p_timeout_host) cudaFreeHost(h->p2p_timeout_host);
   h->p2p_timeout_host = nullptr;
   h->p2p = false;

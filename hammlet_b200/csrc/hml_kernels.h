@@ -45,9 +45,16 @@ __host__ __device__ inline size_t p2p_entry_offset(int parity, int slot, int src
   return ((size_t)(parity * kP2PSlots + slot) * world + src) * (kP2PHeader + kP2PPayload);
 }
 inline size_t p2p_mailbox_bytes(int world) { return 2 * (size_t)kP2PSlots * world * (kP2PHeader + kP2PPayload); }
-// all-gather of `bytes` (a multiple of 8, <= kP2PPayload) per rank into recv (rank-major), one kernel per rank
-void launch_p2p_exchange(const P2PPeers& peers, int rank, int world, int slot, uint64_t seq, const void* send,
-                         size_t bytes, void* recv, unsigned int* timeout_flag_dev, cudaStream_t s);
+// what the device side needs, resident in global memory (SegInfo::p2p points at it)
+struct P2PDev {
+  P2PPeers peers;
+  unsigned int* timeout_flag;  // mapped host word raised by an exchange that gave up waiting
+  int rank, world;
+};
+enum { kSlotHeads = 0, kSlotOps = 1, kSlotMaps = 2, kSlotStats = 3 };
+// all-gather of `bytes` (a multiple of 8, <= kP2PPayload) per rank into recv (rank-major), one single-CTA kernel
+void launch_p2p_exchange(const P2PDev* d, int slot, uint64_t seq, const void* send, size_t bytes, void* recv,
+                         cudaStream_t s);
 
 // ---- block-level sweep kernels (hml_sweep.cu)
 struct ModelHost {  // what the C ABI receives, validated
@@ -68,6 +75,10 @@ struct SegInfo {
   double* send_op;
   uint64_t* send_map;
   unsigned long long* overflow;  // set if this rank's block arrays were too small
+  // peer-memory exchange embedded in the producing kernels (null: the caller exchanges between launches)
+  const P2PDev* p2p;
+  const unsigned long long* stats_send;  // the rank's result block
+  unsigned long long* stats_recv;        // world x stats_words
 };
 
 struct SweepBuffers {
@@ -121,11 +132,15 @@ struct SweepLaunch {
   uint64_t nblocks_hint;  // upper bound used to size grids (capacity if unknown)
   // segment mode: all-gathers the named carry (send slot -> gathered array) on the stream; 0 on success
   int (*exchange)(void* user, int which);
+  // kernels that embed the exchange (seg.p2p != null) ask for the sequence number of their collective
+  unsigned long long (*next_seq)(void* user, int which);
   void* exchange_user;
+  uint32_t stats_words;  // 8-byte words of the result block travelling in the statistics exchange (0: not fused)
 };
-enum { kExchangeHeads = 0, kExchangeOps = 1, kExchangeMaps = 2 };
+enum { kExchangeHeads = 0, kExchangeOps = 1, kExchangeMaps = 2, kExchangeStats = 3 };
 // segment mode: head partial of this rank -> seg.send_head (to be all-gathered before the block statistics)
-void launch_seg_head(const SweepBuffers& b, uint64_t seg_len, cudaStream_t s);
+// seq != 0: the kernel also runs the head exchange itself (seg.p2p != null)
+void launch_seg_head(const SweepBuffers& b, uint64_t seg_len, unsigned long long seq, cudaStream_t s);
 
 // Enqueues all block-level kernels of one sweep on `s`; returns the number of kernels launched.
 // stage_cb(name) is called before each stage so the caller can drop timing events.

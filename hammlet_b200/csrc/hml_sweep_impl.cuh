@@ -8,6 +8,7 @@
 #include "../../include/hammlet_b200.h"
 #include "hml_common.cuh"
 #include "hml_kernels.h"
+#include "hml_p2p.cuh"
 
 namespace hml {
 
@@ -318,18 +319,26 @@ __device__ __forceinline__ void range_sums(const SweepBuffers& buf, uint32_t s, 
 
 // k_seg_head: the observations in front of this rank's first boundary belong to a block that starts on
 // an earlier rank; their partial statistics travel with the rank's block count.
-static __global__ void k_seg_head(SweepBuffers buf, uint32_t seg_len) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const uint64_t raw = *buf.nblocks;
-  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
-  if (buf.seg.overflow) *buf.seg.overflow = raw > buf.capacity ? 1ull : 0ull;
-  const uint32_t e = B ? buf.starts[0] : seg_len;
-  double sx = 0.0, sq = 0.0;
-  if (e > 0) range_sums(buf, 0u, e, sx, sq);
-  buf.seg.send_head[0] = (double)B;
-  buf.seg.send_head[1] = (double)e;
-  buf.seg.send_head[2] = sx;
-  buf.seg.send_head[3] = sq;
+// seq != 0: the head exchange runs inside this kernel (peer mailboxes), else the caller exchanges afterwards.
+static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint32_t seg_len, unsigned long long seq) {
+  if (threadIdx.x == 0) {
+    const uint64_t raw = *buf.nblocks;
+    const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+    if (buf.seg.overflow) *buf.seg.overflow = raw > buf.capacity ? 1ull : 0ull;
+    const uint32_t e = B ? buf.starts[0] : seg_len;
+    double sx = 0.0, sq = 0.0;
+    if (e > 0) range_sums(buf, 0u, e, sx, sq);
+    buf.seg.send_head[0] = (double)B;
+    buf.seg.send_head[1] = (double)e;
+    buf.seg.send_head[2] = sx;
+    buf.seg.send_head[3] = sq;
+  }
+  if (seq && buf.seg.p2p) {
+    __threadfence();
+    __syncthreads();
+    p2p_exchange_cta(buf.seg.p2p, kSlotHeads, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_head), 4,
+                     reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.heads)));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -782,11 +791,11 @@ struct ScanCfg {
 //   kPhase 2  forward vector entering the segment = pi * Op_0 * ... * Op_{rank-1} (normalised), then steps 2-3
 //   kPhase 0  everything in one launch (single handle)
 template <int KP>
-__device__ __forceinline__ void load_gathered_op(OpVals<KP>& o, const double* g) {
+__device__ __forceinline__ void load_gathered_op(OpVals<KP>& o, const double* g) {  // through L2: another CTA may have
+#pragma unroll                                                                     // written it in this very kernel
+  for (int k = 0; k < KP * KP; ++k) o.m[k] = __ldcg(g + k);
 #pragma unroll
-  for (int k = 0; k < KP * KP; ++k) o.m[k] = g[k];
-#pragma unroll
-  for (int k = 0; k < KP; ++k) o.x[k] = (int)g[KP * KP + k];
+  for (int k = 0; k < KP; ++k) o.x[k] = (int)__ldcg(g + KP * KP + k);
 }
 
 // Small K (<= 8): 256 threads, every vector and operator in registers, operators prefetched one step
@@ -795,7 +804,8 @@ __device__ __forceinline__ void load_gathered_op(OpVals<KP>& o, const double* g)
 //   step 2  thread 0: forward vector entering each group (G sequential operator applications)
 //   step 3  thread per group: forward vector entering each of its tiles
 template <int KP, int kPhase>
-__global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, ModelDev<KP> m, int skip_upto) {
+__global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, ModelDev<KP> m, int skip_upto,
+                                                            unsigned long long seq) {
   constexpr int GMAX = 256 / KP < 48 ? 256 / KP : 48;
   __shared__ double s_gain[GMAX][KP];
   __shared__ double s_gop[GMAX * KP * KP];
@@ -809,8 +819,8 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
     S = (nt + G - 1) / G;
     G = (nt + S - 1) / S;
   }
-  if (kPhase == 0 && nt == 0) return;
   if (nt <= skip_upto) return;  // the cluster kernel took this sweep
+  if (kPhase == 0 && nt == 0) return;
   if (kPhase != 2) {
     const int g = threadIdx.x / KP, i = threadIdx.x % KP;
     if (g < G) {
@@ -838,7 +848,7 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
       }
     }
     __syncthreads();
-    if (kPhase == 1) {
+    if (kPhase == 1 || kPhase == 3) {
       // segment operator: row i of the ordered product of the group operators (identity without blocks)
       if (threadIdx.x < KP) {
         const int i = threadIdx.x;
@@ -852,7 +862,12 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
         for (int j = 0; j < KP; ++j) buf.seg.send_op[i * KP + j] = r[j];
         buf.seg.send_op[KP * KP + i] = (double)rex;
       }
-      return;
+      if (kPhase == 1) return;
+      __threadfence();
+      __syncthreads();
+      p2p_exchange_cta(buf.seg.p2p, kSlotOps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_op), KP * KP + KP,
+                       reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.ops)));
+      if (nt == 0) return;
     }
   } else {
     if (nt == 0) return;
@@ -864,7 +879,7 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
     double a[KP];
 #pragma unroll
     for (int j = 0; j < KP; ++j) a[j] = m.pi[j];  // row 0 of the trellis is pi itself (FB.hpp:57)
-    if (kPhase == 2) {
+    if (kPhase >= 2) {
 #pragma unroll 1
       for (int r = 0; r < buf.seg.rank; ++r) {
         OpVals<KP> o;
@@ -924,7 +939,7 @@ struct ClusterScanCfg {
 
 template <int KP, int kPhase>
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(256)
-    k_fwd_tilescan_cluster(SweepBuffers buf, ModelDev<KP> m) {
+    k_fwd_tilescan_cluster(SweepBuffers buf, ModelDev<KP> m, unsigned long long seq) {
   namespace cg = cooperative_groups;
   using Cfg = ClusterScanCfg<KP>;
   constexpr int SGMAX = Cfg::SGMAX;
@@ -999,7 +1014,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(256)
     s_cex[tid] = SG ? s_treex[tid] : 0;
   }
   cluster.sync();
-  if (kPhase == 1) {
+  if (kPhase == 1 || kPhase == 3) {
     // segment operator: row i of the ordered product of the CTA operators (identity without blocks)
     if (rank == 0 && tid < KP) {
       const int i = tid;
@@ -1016,15 +1031,23 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(256)
       for (int j = 0; j < KP; ++j) buf.seg.send_op[i * KP + j] = r[j];
       buf.seg.send_op[KP * KP + i] = (double)rex;
     }
+    if (kPhase == 3 && rank == 0) {
+      // the collective runs right here: CTA 0 trades segment operators with the other GPUs while the rest of
+      // the cluster waits at the barrier below
+      __threadfence();
+      __syncthreads();
+      p2p_exchange_cta(buf.seg.p2p, kSlotOps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_op), KP * KP + KP,
+                       reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.ops)));
+    }
     cluster.sync();  // shared memory of every CTA stays alive until CTA 0 has read it
-    return;
+    if (kPhase == 1) return;
   }
   // ---- step 3
   if (tid == 0 && n_own > 0) {
     double a[KP];
 #pragma unroll
     for (int j = 0; j < KP; ++j) a[j] = m.pi[j];  // row 0 of the trellis is pi itself (FB.hpp:57)
-    if (kPhase == 2) {
+    if (kPhase >= 2) {
 #pragma unroll 1
       for (int r = 0; r < buf.seg.rank; ++r) {
         OpVals<KP> o;
@@ -1403,17 +1426,26 @@ __global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf) {
 // kSegMap: only the composed map of the whole segment is wanted (-> seg.send_map, identity without
 // blocks); otherwise the state following the segment comes from the gathered maps of the later ranks
 // (the last block of the sequence carries a constant map, so the start value is irrelevant).
-template <int KP, bool kSegMap>
-__global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
+// kMode 0: resolve (gathered maps of the later ranks, if any); 1: segment map only; 2: segment map, map
+// exchange through the peer mailboxes and resolution in one kernel
+template <int KP, int kMode>
+__global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf, unsigned long long seq) {
+  constexpr bool kSegMap = kMode == 1;
   constexpr int MB = 8 * Map<KP>::W;
   __shared__ uint64_t s_w[32][Map<KP>::W];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int64_t nt = (int64_t)((B + Layout::TB - 1) / Layout::TB);
   if (nt == 0) {
-    if (kSegMap && threadIdx.x == 0) {
+    if (kMode != 0 && threadIdx.x == 0) {
       const Map<KP> id = Map<KP>::identity();
 #pragma unroll
       for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? id.w[i] : 0ull;
+    }
+    if (kMode == 2) {  // a rank without blocks still takes part in the collective
+      __threadfence();
+      __syncthreads();
+      p2p_exchange_cta(buf.seg.p2p, kSlotMaps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_map), 4,
+                       const_cast<uint64_t*>(buf.seg.maps));
     }
     return;
   }
@@ -1437,7 +1469,7 @@ __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
     for (int i = 0; i < Map<KP>::W; ++i) s_w[warp][i] = inc.w[i];
   }
   __syncthreads();
-  if (kSegMap) {
+  if (kMode != 0) {
     if (tid == 0) {
       Map<KP> tot = Map<KP>::identity();
       for (int wv = 0; wv < 32; ++wv) {
@@ -1449,13 +1481,17 @@ __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? tot.w[i] : 0ull;
     }
-    return;
+    if (kSegMap) return;
+    __threadfence();
+    __syncthreads();
+    p2p_exchange_cta(buf.seg.p2p, kSlotMaps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_map), 4,
+                     const_cast<uint64_t*>(buf.seg.maps));
   }
   uint32_t q_end = 0;
   for (int r = buf.seg.world - 1; r > buf.seg.rank; --r) {
     Map<KP> o;
 #pragma unroll
-    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = buf.seg.maps[4 * r + i];
+    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = __ldcg(buf.seg.maps + 4 * r + i);
     q_end = o.get(q_end);
   }
   Map<KP> after_warp = Map<KP>::identity();  // map of everything after this warp
@@ -1621,6 +1657,25 @@ __global__ void __launch_bounds__(128) k_reduce_final(SweepBuffers buf, int npar
   if (threadIdx.x == 0) buf.out_f64[v] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
 }
 
+// Segment mode with peer mailboxes: the final sums and the statistics exchange in one single-CTA kernel.  Warp
+// w sums output values w, w + 8, ... over the partials (fixed order, fixed tree => deterministic).
+template <int KP>
+__global__ void __launch_bounds__(256) k_reduce_final_exchange(SweepBuffers buf, int nparts, uint32_t stats_words,
+                                                               unsigned long long seq) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int v = warp; v < 2 * KP; v += 8) {
+    double t = 0.0;
+    for (int i = lane; i < nparts; i += 32) t += buf.partials[(size_t)i * 2 * KP + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += shfl_xor_double(t, o);
+    if (lane == 0) buf.out_f64[v] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  p2p_exchange_cta(buf.seg.p2p, kSlotStats, seq, reinterpret_cast<const uint64_t*>(buf.seg.stats_send), stats_words,
+                   reinterpret_cast<uint64_t*>(buf.seg.stats_recv));
+}
+
 template <int KP>
 __global__ void k_sum_partials(const double* partials, int n, double* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1685,25 +1740,31 @@ __global__ void k_mix_qend(SweepBuffers buf) {
 // more than that, the single-CTA kernel is launched too and takes over exactly when the cluster kernel stood down
 // (the block count is only known on the device).
 template <int KP, int kPhase>
-int launch_fwd_tilescan_phase(const SweepBuffers& b, const ModelDev<KP>& m, uint64_t ntiles_hint, cudaStream_t s) {
+int launch_fwd_tilescan_phase(const SweepBuffers& b, const ModelDev<KP>& m, uint64_t ntiles_hint, unsigned long long seq,
+                              cudaStream_t s) {
   if constexpr (KP <= 8) {
     using Cfg = ClusterScanCfg<KP>;
     // per device, so set on every launch (a host-side table lookup)
     cudaFuncSetAttribute(k_fwd_tilescan_cluster<KP, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-    k_fwd_tilescan_cluster<KP, kPhase><<<kClusterCtas, 256, Cfg::kSmem, s>>>(b, m);
+    k_fwd_tilescan_cluster<KP, kPhase><<<kClusterCtas, 256, Cfg::kSmem, s>>>(b, m, seq);
     if (ntiles_hint <= (uint64_t)Cfg::kMaxTiles) return 1;
-    k_fwd_tilescan_small<KP, kPhase><<<1, 256, 0, s>>>(b, m, Cfg::kMaxTiles);
+    k_fwd_tilescan_small<KP, kPhase><<<1, 256, 0, s>>>(b, m, Cfg::kMaxTiles, seq);
     return 2;
   } else {
+    static_assert(KP <= 8 || kPhase != 3, "the embedded exchange exists for K <= 8");
     k_fwd_tilescan<KP, kPhase><<<1, 1024, 0, s>>>(b, m);
     return 1;
   }
 }
+// phase 3 (K <= 8, peer mailboxes): phases 1 and 2 with the operator exchange between them, in one kernel
 template <int KP>
-int launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, int phase, uint64_t ntiles_hint, cudaStream_t s) {
-  if (phase == 0) return launch_fwd_tilescan_phase<KP, 0>(b, m, ntiles_hint, s);
-  if (phase == 1) return launch_fwd_tilescan_phase<KP, 1>(b, m, ntiles_hint, s);
-  return launch_fwd_tilescan_phase<KP, 2>(b, m, ntiles_hint, s);
+int launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, int phase, uint64_t ntiles_hint,
+                        unsigned long long seq, cudaStream_t s) {
+  if (phase == 0) return launch_fwd_tilescan_phase<KP, 0>(b, m, ntiles_hint, 0, s);
+  if (phase == 1) return launch_fwd_tilescan_phase<KP, 1>(b, m, ntiles_hint, 0, s);
+  if (phase == 2) return launch_fwd_tilescan_phase<KP, 2>(b, m, ntiles_hint, 0, s);
+  if constexpr (KP <= 8) return launch_fwd_tilescan_phase<KP, 3>(b, m, ntiles_hint, seq, s);
+  return 0;
 }
 
 // maps -> chunk/tile maps -> suffix scan over tiles -> states; returns the number of launches
@@ -1723,26 +1784,33 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
     if (cb) cb(user, "bwd_chunkmaps");
     k_bwd_chunkmaps<KP><<<grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s>>>(b);
   }
-  if (b.seg.world > 1) {
-    if (cb) cb(user, "bwd_segmap");
-    k_bwd_scan<KP, true><<<1, 1024, 0, s>>>(b);
-    ++launches;
-    if (cb) cb(user, "exchange_maps");
-    if (l.exchange(l.exchange_user, kExchangeMaps) != 0) return -1;
-  }
   if (cb) cb(user, "bwd_scan");
-  k_bwd_scan<KP, false><<<1, 1024, 0, s>>>(b);
+  if (b.seg.world > 1 && b.seg.p2p != nullptr) {
+    k_bwd_scan<KP, 2><<<1, 1024, 0, s>>>(b, l.next_seq(l.exchange_user, kExchangeMaps));
+  } else {
+    if (b.seg.world > 1) {
+      k_bwd_scan<KP, 1><<<1, 1024, 0, s>>>(b, 0);
+      ++launches;
+      if (cb) cb(user, "exchange_maps");
+      if (l.exchange(l.exchange_user, kExchangeMaps) != 0) return -1;
+      if (cb) cb(user, "bwd_scan2");
+    }
+    k_bwd_scan<KP, 0><<<1, 1024, 0, s>>>(b, 0);
+  }
   if (cb) cb(user, "bwd_replay");
   k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
   return launches;
 }
 
 template <int KP>
-int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, int sms, cudaStream_t s) {
+int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, const SweepLaunch& l, cudaStream_t s) {
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
-  const int g = grid_for(ntiles * Layout::TB, kReduceThreads, sms, 4);
+  const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 4);
   k_reduce_partial<KP><<<g, kReduceThreads, 0, s>>>(b, K);
-  k_reduce_final<KP><<<2 * KP, 128, 0, s>>>(b, g);
+  if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
+    k_reduce_final_exchange<KP><<<1, 256, 0, s>>>(b, g, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
+  else
+    k_reduce_final<KP><<<2 * KP, 128, 0, s>>>(b, g);
   return 2;
 }
 
@@ -1798,14 +1866,17 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
     ++launches;
     stage("fwd_tilescan");
-    if (seg) {
-      launches += launch_fwd_tilescan<KP>(b, m, 1, ntiles, s);
+    const bool embed = seg && b.seg.p2p != nullptr && KP <= 8;  // collectives inside the producing kernels
+    if (embed) {
+      launches += launch_fwd_tilescan<KP>(b, m, 3, ntiles, l.next_seq(l.exchange_user, kExchangeOps), s);
+    } else if (seg) {
+      launches += launch_fwd_tilescan<KP>(b, m, 1, ntiles, 0, s);
       stage("exchange_ops");
       if (l.exchange(l.exchange_user, kExchangeOps) != 0) return -1;
       stage("fwd_tilescan2");
-      launches += launch_fwd_tilescan<KP>(b, m, 2, ntiles, s);
+      launches += launch_fwd_tilescan<KP>(b, m, 2, ntiles, 0, s);
     } else {
-      launches += launch_fwd_tilescan<KP>(b, m, 0, ntiles, s);
+      launches += launch_fwd_tilescan<KP>(b, m, 0, ntiles, 0, s);
     }
     stage("fwd_replay");
     const int gr = grid_for(ntiles, 1, l.sms, 32);
@@ -1835,7 +1906,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     launches += nbw;
   }
   stage("reduce");
-  launches += launch_reduce<KP>(b, mh.K, nb, l.sms, s);
+  launches += launch_reduce<KP>(b, mh.K, nb, l, s);
   stage("end");
   return launches;
 }
@@ -1868,7 +1939,7 @@ int sequential_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunc
   const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, nullptr, nullptr);
   if (nbw < 0) return -1;
   launches += nbw;
-  launches += launch_reduce<KP>(b, mh.K, nb, l.sms, s);
+  launches += launch_reduce<KP>(b, mh.K, nb, l, s);
   return launches;
 }
 
