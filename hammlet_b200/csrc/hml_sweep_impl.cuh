@@ -346,6 +346,11 @@ static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint3
 
 template <int KP, bool kGather, bool kEmit, bool kMix>
 __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<KP> m, int want_maxe) {
+  if (kEmit && blockIdx.x == 0) {
+    // first kernel of a sweep: zero the result block that the later kernels accumulate into
+    for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
+    for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
+  }
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
@@ -1827,9 +1832,6 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   auto stage = [&](const char* name) {
     if (cb) cb(user, name);
   };
-  stage("clear");
-  k_clear_out<KP><<<1, 256, 0, s>>>(b);
-  ++launches;
   constexpr bool kPrefix = KP <= 8;  // k_fwd_chunks_prefix + k_fwd_replay_prefix
   stage("block_emit");
   {
