@@ -34,17 +34,17 @@ const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);
 // ---- peer-memory carry exchange of the segment-split mode (hml_p2p.cu)
 constexpr int kP2PMaxWorld = 64;
 constexpr int kP2PSlots = 4;            // heads, operators, maps, statistics
-constexpr size_t kP2PHeader = 64;       // sequence number (8 bytes) + padding in front of each payload
 constexpr size_t kP2PPayload = 9216;    // largest payload: the result block of a K = 32 sweep
+constexpr size_t kP2PEntry = 2 * kP2PPayload;  // on the wire every 4 payload bytes travel with a 4-byte sequence tag
 constexpr unsigned long long kP2PTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
 struct P2PPeers {
   unsigned char* box[kP2PMaxWorld];  // mailbox of every rank as mapped into this process (own one included)
 };
 // entry written by rank `src` for exchange `slot`, sequence parity `parity`, inside any mailbox
 __host__ __device__ inline size_t p2p_entry_offset(int parity, int slot, int src, int world) {
-  return ((size_t)(parity * kP2PSlots + slot) * world + src) * (kP2PHeader + kP2PPayload);
+  return ((size_t)(parity * kP2PSlots + slot) * world + src) * kP2PEntry;
 }
-inline size_t p2p_mailbox_bytes(int world) { return 2 * (size_t)kP2PSlots * world * (kP2PHeader + kP2PPayload); }
+inline size_t p2p_mailbox_bytes(int world) { return 2 * (size_t)kP2PSlots * world * kP2PEntry; }
 // what the device side needs, resident in global memory (SegInfo::p2p points at it)
 struct P2PDev {
   P2PPeers peers;

@@ -5,13 +5,14 @@
 // the per-rank statistics; 32 bytes to 9 kB each.  An NCCL all-gather of that size costs about 20 us of
 // launch and protocol latency, four of them a third of the sweep at 8 GPUs.  Here every rank owns a mailbox
 // in its own HBM that its peers map through CUDA IPC; an exchange is one CTA per rank — inside the kernel that produced the carry (hml_p2p.cuh) — that
-//   1. stores the rank's payload straight into every peer's mailbox over NVLink (plain stores, 8-byte words),
-//   2. fences system-wide and releases a sequence number next to each copy,
-//   3. spins (acquire loads on its OWN mailbox, i.e. local L2) until all peers' numbers arrived,
-//   4. copies the gathered payloads where the following kernels read them.
+//   1. stores the rank's payload straight into every peer's mailbox over NVLink, as 8-byte cells holding 4 bytes
+//      of payload and the 32-bit sequence number of the exchange (an aligned 8-byte store arrives whole, so no
+//      fence and no separate flag are needed: one one-way write per cell),
+//   2. polls the cells of its OWN mailbox (local L2) until all peers' numbers match and assembles the payloads
+//      where the following code reads them.
 // No rank ever waits on a remote load.  Mailbox entries are double-buffered by sequence parity, so a rank
 // that is one exchange ahead never overwrites an entry a slower rank is still reading; it cannot be two
-// ahead because each exchange needs every rank's contribution.  A spin that exceeds its time budget (a
+// ahead because each exchange needs every rank's contribution.  A poll that exceeds its time budget (a
 // peer died) raises a flag in mapped host memory and returns, so the host reports an error instead of
 // hanging the device.
 #include "hml_p2p.cuh"
