@@ -361,6 +361,16 @@ def main():
     else:
         wl = f"{world} independent sequences, one per GPU, each: " + workload
 
+    # DRAM bytes of one launch of the roofline kernel from an `ncu --set full` capture of this workload (profiles/)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            rec = json.load(f).get("k_" + top)
+        if rec and int(rec["T"]) == T_local and int(rec["K"]) == K:
+            traffic = float(rec["dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        pass
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if segments else "weak",
@@ -377,7 +387,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": det,
                      "sweep_bytes": 4.0 * T + B * (4 + 16 + 16 * K + 2),
                      "sweep_frac_of_hbm_roofline": (4.0 * T + B * (4 + 16 + 16 * K + 2)) / (world if segments else 1)
