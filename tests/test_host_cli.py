@@ -129,6 +129,14 @@ def test_replay_run_is_identical_to_the_double_reference(tmp_path, seed, scheme)
     assert r.returncode == 0 and p.returncode == 0, p.stderr + r.stderr
     for kind in ("blocks", "compression", "sequences", "parameters", "marginals", "segments"):
         assert (tmp_path / f"our-{kind}.csv").read_text() == (tmp_path / f"ref-{kind}.csv").read_text(), kind
+    # the reference's own post-processing tool runs unchanged on our marginals
+    tool = os.path.join(REF, "maxSegmentation")
+    if os.path.exists(tool):
+        seg = run([tool, "-i", "our-marginals.csv"], cwd=tmp_path)
+        assert seg.returncode == 0, seg.stderr
+        rows = [line.split("\t") for line in seg.stdout.strip().split("\n")]
+        assert sum(int(r[0]) for r in rows) == 60000 and all(0 <= int(r[1]) < 3 for r in rows)
+        assert seg.stdout == run([tool, "-i", "ref-marginals.csv"], cwd=tmp_path).stdout
 
 
 @pytest.mark.gpu
