@@ -159,7 +159,7 @@ __device__ __forceinline__ uint32_t hot_bits8(const uint4 v, float thr) {
 //   phase 1  every thread reads two 16-byte pyramid words (both loads in flight); the hot sub-blocks are compacted,
 //            in position order, into a list in shared memory (ballot-free: packed warp scans of the popcounts)
 //   phase 2  the hot sub-blocks are read 16 per warp and round: a quarter warp reads one sub-block as float4 per
-//            lane, four loads in flight per lane; redux.or over the quarter assembles the 32-bit boundary mask
+//            lane, four loads in flight per lane; an OR butterfly over the quarter assembles the 32-bit boundary mask
 //   phase 3  exclusive scan of the mask popcounts; (sub-block, offset, mask) triples go to global memory,
 //            8 bytes per hot sub-block, and the span's boundary count to span_info
 //   last CTA (atomic ticket): exclusive scan over the span counts -> span_off, total -> *nblocks_out and the
@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(256)
   const uint32_t span = blockIdx.x;
   const bool first = span == 0 && force_first;
   const uint64_t nsubs = (T + kSub - 1) / kSub;
+  const bool tail_span = ((uint64_t)span + 1) * kSpanObs > T;  // only the last span can reach past the sequence
 
   // ---- phase 1
   uint4 pv[2];
@@ -189,8 +190,10 @@ __global__ void __launch_bounds__(256)
   for (int k = 0; k < 2; ++k) {
     h[k] = hot_bits8(pv[k], thr);
     // entries past the last sub-block never count (a NaN or -inf threshold flags even their -inf padding)
-    const uint64_t e0 = (uint64_t)span * kSpanSubs + (uint64_t)(k * 256 + tid) * 8;
-    if (e0 + 8 > nsubs) h[k] = e0 < nsubs ? (h[k] & ((1u << (uint32_t)(nsubs - e0)) - 1u)) : 0u;
+    if (tail_span) {
+      const uint64_t e0 = (uint64_t)span * kSpanSubs + (uint64_t)(k * 256 + tid) * 8;
+      if (e0 + 8 > nsubs) h[k] = e0 < nsubs ? (h[k] & ((1u << (uint32_t)(nsubs - e0)) - 1u)) : 0u;
+    }
   }
   if (first && tid == 0) h[0] |= 1u;
   const uint32_t c0 = __popc(h[0]), c1 = __popc(h[1]);
@@ -235,7 +238,6 @@ __global__ void __launch_bounds__(256)
   // ---- phase 2
   {
     const int q = lane >> 3, l8 = lane & 7;
-    const uint32_t qmask = 0xffu << (8 * q);
     const float4* wq = reinterpret_cast<const float4*>(w + (uint64_t)span * kSpanObs) + l8;
     for (uint32_t i0 = warp * 16; i0 < nhot; i0 += 8 * 16) {
       uint32_t sub[4];
@@ -254,10 +256,17 @@ __global__ void __launch_bounds__(256)
         if (ok[k])
           f = (!(v[k].x < thr) ? 1u : 0u) | (!(v[k].y < thr) ? 2u : 0u) | (!(v[k].z < thr) ? 4u : 0u) |
               (!(v[k].w < thr) ? 8u : 0u);
-        uint32_t m = __reduce_or_sync(qmask, f << (4 * l8));
+        // OR over the quarter warp: three butterfly steps stay inside groups of eight lanes (a redux.sync with a
+        // partial member mask compiles to a slow generic path)
+        uint32_t m = f << (4 * l8);
+        m |= __shfl_xor_sync(0xffffffffu, m, 1);
+        m |= __shfl_xor_sync(0xffffffffu, m, 2);
+        m |= __shfl_xor_sync(0xffffffffu, m, 4);
         if (ok[k] && l8 == 0) {
-          const uint64_t pos0 = ((uint64_t)span * kSpanSubs + sub[k]) * kSub;
-          if (pos0 + kSub > T) m = pos0 < T ? (m & ((1u << (uint32_t)(T - pos0)) - 1u)) : 0u;  // past the end
+          if (tail_span) {  // positions past the end of the sequence never count
+            const uint64_t pos0 = ((uint64_t)span * kSpanSubs + sub[k]) * kSub;
+            if (pos0 + kSub > T) m = pos0 < T ? (m & ((1u << (uint32_t)(T - pos0)) - 1u)) : 0u;
+          }
           if (first && sub[k] == 0) m |= 1u;
           s_mask[i0 + 4 * k + q] = m;
         }
