@@ -29,6 +29,27 @@ def piecewise_gaussian(T, K, L, seed, spacing=1.0, sigma=0.3, quantum_bits=None,
     return (x, states) if return_states else x
 
 
+def piecewise_gaussian_md(T, P, D, L, seed, spacing=1.0, sigma=0.3, quantum_bits=None):
+    """D-dimensional observations, (T, D) position-major like the reference's input stream (wavelet.hpp:131-136):
+    common change points, every dimension at one of P shared levels (the `-s C P D` model, K = P**D states)."""
+    rng = np.random.default_rng(seed)
+    seg = np.cumsum(rng.random(T) < 1.0 / L)
+    levels = rng.integers(0, P, size=(int(seg[-1]) + 1, D))
+    mu = (np.arange(P) - (P - 1) / 2.0) * spacing
+    x = mu[levels[seg]] + sigma * rng.standard_normal((T, D))
+    if quantum_bits is None:
+        return np.round(x, 5).astype(np.float32)
+    q = float(1 << quantum_bits)
+    return (np.round(x * q) / q).astype(np.float32)
+
+
+def model_guess_md(P, D, seed, spacing=1.0, sigma=0.3, stay=0.9):
+    """(mean[P], var[P]) of the shared emission parameters and (A, pi) over the K = P**D states."""
+    mu, var, _, _ = model_guess(P, seed, spacing, sigma, stay)
+    _, _, A, pi = model_guess(P ** D, seed + 7, spacing, sigma, stay)
+    return mu, var, A, pi
+
+
 def model_guess(K, seed, spacing=1.0, sigma=0.3, stay=0.9):
     """A plausible (theta, A, pi) near the generating model, as float32 like the reference's real_t."""
     rng = np.random.default_rng(seed + 1000)

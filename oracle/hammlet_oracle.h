@@ -6,6 +6,16 @@
 #include <stdint.h>
 #define HO_DECL(R, X)                                                                                        \
   void ho_maxlet_##X(const R* x, size_t T, R* coeffs);                                                       \
+  void ho_maxlet_md_##X(const R* x, size_t T, size_t D, R* coeffs);                                          \
+  int ho_fb_sweep_md_##X(size_t B, const uint64_t* bsize, const R* bsum, const R* bsq, int D, int P,         \
+                         const int* mapping, int K, const R* mean, const R* var, const R* A, const R* pi,   \
+                         int use_self, const double* uniforms, R* rows_out, int16_t* states, R* stat_sum,   \
+                         R* stat_sq, uint64_t* stat_n, uint64_t* trans, uint64_t* counts, double* loglik);  \
+  int ho_mix_sweep_md_##X(size_t B, const uint64_t* bsize, const R* bsum, const R* bsq, int D, int P,        \
+                          const int* mapping, int K, const R* mean, const R* var, const double* uniforms,   \
+                          int16_t* states, R* stat_sum, R* stat_sq, uint64_t* stat_n, uint64_t* trans,      \
+                          uint64_t* counts);                                                                 \
+  int ho_auto_prior_md_##X(size_t B, const uint64_t* bsize, const R* bsum, size_t D, R s2, R p, R* out4);    \
   double ho_sigma_hat_##X(const R* coeffs, size_t T);                                                        \
   void ho_breakpoint_weights_##X(R* w, size_t T, R mult);                                                    \
   size_t ho_boundaries_##X(const R* w, size_t T, R thr, uint64_t* starts);                                   \

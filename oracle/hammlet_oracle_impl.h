@@ -64,34 +64,42 @@ static int ho_discrete(const double* w, int K, double u) {
 
 /* ------------------------------------------------------------------ load-time transforms */
 
-/* wavelet.hpp:97-188 (MaxletTransform, nrDim = 1): streaming in-order Haar.  coeffs[j] is the
- * absolute detail coefficient of the wavelet whose mid discontinuity sits at j, normalised by a
- * RUNNING product of sqrt2half (includes.hpp:126-128); incomplete wavelets and position 0 stay inf. */
-void FN(ho_maxlet)(const REAL* x, size_t T, REAL* coeffs) {
+/* wavelet.hpp:97-188 (MaxletTransform): streaming in-order Haar over D interleaved dimensions (x holds T*D
+ * values, position-major).  coeffs[j] is the maximum over the dimensions (:155-160, starting from 0) of the
+ * absolute detail coefficient of the wavelet whose mid discontinuity sits at j, normalised by a RUNNING product
+ * of sqrt2half (includes.hpp:126-128); incomplete wavelets and position 0 stay inf. */
+void FN(ho_maxlet_md)(const REAL* x, size_t T, size_t D, REAL* coeffs) {
   const REAL sqrt2 = (REAL)sqrt(2.0);
   const REAL sqrt2half = (REAL)(sqrt2 / 2.0);
-  REAL stack[80];
-  size_t sp = 0, i;
+  REAL* stack = (REAL*)malloc(sizeof(REAL) * 80 * D);
+  size_t sp = 0, i, d;
   for (i = 0; i < T; ++i) {
     size_t j = i, m = 1;
     REAL normalizer = sqrt2half;
-    stack[sp++] = x[i];
+    for (d = 0; d < D; ++d) stack[sp++] = x[i * D + d];
     coeffs[i] = (REAL)INFINITY;
     while ((j & m) > 0) {
       REAL maxCoeff = 0;
-      REAL d = stack[sp - 2] - stack[sp - 1];
-      REAL c = normalizer * (REAL)RFABS(d);
-      if (c > maxCoeff) maxCoeff = c; /* std::max(0, c): NaN-safe order as in :156 */
-      stack[sp - 2] += stack[sp - 1];
+      size_t L = sp - 2 * D, R = L + D;
+      for (d = 0; d < D; ++d) {
+        REAL df = stack[L] - stack[R];
+        REAL c = normalizer * (REAL)RFABS(df);
+        if (maxCoeff < c) maxCoeff = c; /* std::max(maxCoeff, c): NaN-safe order as in :156 */
+        stack[L] += stack[R];
+        L++;
+        R++;
+      }
       coeffs[j] = maxCoeff;
-      sp--;
+      sp -= D;
       j = j - m;
       m *= 2;
       normalizer *= sqrt2half;
     }
   }
   if (T > 0) coeffs[0] = (REAL)INFINITY;
+  free(stack);
 }
+void FN(ho_maxlet)(const REAL* x, size_t T, REAL* coeffs) { FN(ho_maxlet_md)(x, T, 1, coeffs); }
 
 /* main.cpp:303-311: mean of the finest-level coefficients (odd indices) over sqrt(2/pi) */
 double FN(ho_sigma_hat)(const REAL* coeffs, size_t T) {
@@ -238,19 +246,21 @@ static REAL FN(ho_inner_product)(REAL mean, REAL var, REAL sum, REAL sumsq) {
  * counts[K] (:185), loglik = sum_t (maxE_t + log forwardSum_t) (never materialised by the
  * reference; accumulated here in double for the parity tests).  Returns the number of
  * "uniform fallback" events (:106-111), or -1 for a negative backward variable (:147-149). */
-int FN(ho_fb_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REAL* bsq, int K, const REAL* mean,
-                    const REAL* var, const REAL* A, const REAL* pi, int use_self, const double* uniforms,
-                    REAL* rows_out, int16_t* states, REAL* stat_sum, REAL* stat_sq, uint64_t* stat_n,
-                    uint64_t* trans, uint64_t* counts, double* loglik) {
+int FN(ho_fb_sweep_md)(size_t B, const uint64_t* bsize, const REAL* bsum, const REAL* bsq, int D, int P,
+                       const int* mapping, int K, const REAL* mean, const REAL* var, const REAL* A, const REAL* pi,
+                       int use_self, const double* uniforms, REAL* rows_out, int16_t* states, REAL* stat_sum,
+                       REAL* stat_sq, uint64_t* stat_n, uint64_t* trans, uint64_t* counts, double* loglik) {
   REAL logA[HO_MAXK], logNorm[HO_MAXK], forward[HO_MAXK];
   REAL* rows = rows_out ? rows_out : (REAL*)malloc(sizeof(REAL) * (B + 1) * (size_t)K);
   int s, i, j, fallbacks = 0;
   size_t t;
+  int d;
   REAL prevN = 1;
   double ll = 0;
   for (s = 0; s < K; ++s) {
     logA[s] = use_self ? (REAL)RLOG(A[s * K + s]) : 0;
-    logNorm[s] = FN(ho_log_normalizer)(mean[s], var[s]);
+    logNorm[s] = 0; /* Theta.hpp:154-164: sum over the state's parameters, accumulated in REAL */
+    for (d = 0; d < D; ++d) logNorm[s] += FN(ho_log_normalizer)(mean[mapping[s * D + d]], var[mapping[s * D + d]]);
     rows[s] = pi[s]; /* :57 */
   }
   for (t = 1; t <= B; ++t) { /* :65-125 */
@@ -259,7 +269,12 @@ int FN(ho_fb_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REA
     REAL fsum = 0;
     REAL* prev = rows + (t - 1) * (size_t)K;
     for (s = 0; s < K; ++s) {
-      REAL E = FN(ho_inner_product)(mean[s], var[s], bsum[t - 1], bsq[t - 1]) - N * logNorm[s];
+      REAL ip = 0, E; /* EFD.hpp:83-93: per-dimension inner products accumulated in REAL */
+      for (d = 0; d < D; ++d) {
+        const int p = mapping[s * D + d];
+        ip += FN(ho_inner_product)(mean[p], var[p], bsum[(t - 1) * D + d], bsq[(t - 1) * D + d]);
+      }
+      E = ip - N * logNorm[s];
       if (use_self) E += (N - 1) * logA[s];
       forward[s] = E;
       if (maxE < E) maxE = E;
@@ -311,12 +326,12 @@ int FN(ho_fb_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REA
   if (states && stat_sum) { /* :170-212 */
     REAL e1[HO_MAXK], e2[HO_MAXK];
     size_t prevState = 0;
-    for (s = 0; s < K; ++s) {
+    for (s = 0; s < P; ++s) {
       stat_sum[s] = stat_sq[s] = 0;
       e1[s] = e2[s] = 0;
       stat_n[s] = 0;
-      counts[s] = 0;
     }
+    for (s = 0; s < K; ++s) counts[s] = 0;
     for (s = 0; s < K * K; ++s) trans[s] = 0;
     for (t = 0; t < B; ++t) {
       const int st = states[t];
@@ -324,15 +339,18 @@ int FN(ho_fb_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REA
       trans[st * K + st] += bsize[t] - 1;
       trans[prevState * K + st] += 1;
       counts[st] += bsize[t];
-      y = bsum[t] - e1[st];
-      tmp = stat_sum[st] + y;
-      e1[st] = (tmp - stat_sum[st]) - y;
-      stat_sum[st] = tmp;
-      y = bsq[t] - e2[st];
-      tmp = stat_sq[st] + y;
-      e2[st] = (tmp - stat_sq[st]) - y;
-      stat_sq[st] = tmp;
-      stat_n[st] += bsize[t];
+      for (d = 0; d < D; ++d) { /* :189-191: stats[mapping[state][d]].add(y.suffStat(d), N) */
+        const int p = mapping[st * D + d];
+        y = bsum[t * D + d] - e1[p];
+        tmp = stat_sum[p] + y;
+        e1[p] = (tmp - stat_sum[p]) - y;
+        stat_sum[p] = tmp;
+        y = bsq[t * D + d] - e2[p];
+        tmp = stat_sq[p] + y;
+        e2[p] = (tmp - stat_sq[p]) - y;
+        stat_sq[p] = tmp;
+        stat_n[p] += bsize[t];
+      }
       prevState = (size_t)st;
     }
   }
@@ -340,21 +358,36 @@ int FN(ho_fb_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REA
   return fallbacks;
 }
 
+/* univariate data: one parameter per state, identity mapping */
+int FN(ho_fb_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REAL* bsq, int K, const REAL* mean,
+                    const REAL* var, const REAL* A, const REAL* pi, int use_self, const double* uniforms,
+                    REAL* rows_out, int16_t* states, REAL* stat_sum, REAL* stat_sq, uint64_t* stat_n,
+                    uint64_t* trans, uint64_t* counts, double* loglik) {
+  int ident[HO_MAXK], s;
+  for (s = 0; s < K; ++s) ident[s] = s;
+  return FN(ho_fb_sweep_md)(B, bsize, bsum, bsq, 1, K, ident, K, mean, var, A, pi, use_self, uniforms, rows_out,
+                            states, stat_sum, stat_sq, stat_n, trans, counts, loglik);
+}
+
 /* StateSequence/Mixture.hpp:31-144: independent categorical draw per block; uniforms are consumed
  * in block order; no transition term, no self-transition term, pi ignored. */
-int FN(ho_mix_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REAL* bsq, int K, const REAL* mean,
-                     const REAL* var, const double* uniforms, int16_t* states, REAL* stat_sum, REAL* stat_sq,
-                     uint64_t* stat_n, uint64_t* trans, uint64_t* counts) {
+int FN(ho_mix_sweep_md)(size_t B, const uint64_t* bsize, const REAL* bsum, const REAL* bsq, int D, int P,
+                        const int* mapping, int K, const REAL* mean, const REAL* var, const double* uniforms,
+                        int16_t* states, REAL* stat_sum, REAL* stat_sq, uint64_t* stat_n, uint64_t* trans,
+                        uint64_t* counts) {
   REAL logNorm[HO_MAXK], wts[HO_MAXK], e1[HO_MAXK], e2[HO_MAXK];
   double w[HO_MAXK];
-  int s;
+  int s, d;
   size_t t, prevState = 0;
   for (s = 0; s < K; ++s) {
-    logNorm[s] = FN(ho_log_normalizer)(mean[s], var[s]);
+    logNorm[s] = 0;
+    for (d = 0; d < D; ++d) logNorm[s] += FN(ho_log_normalizer)(mean[mapping[s * D + d]], var[mapping[s * D + d]]);
+    counts[s] = 0;
+  }
+  for (s = 0; s < P; ++s) {
     stat_sum[s] = stat_sq[s] = 0;
     e1[s] = e2[s] = 0;
     stat_n[s] = 0;
-    counts[s] = 0;
   }
   for (s = 0; s < K * K; ++s) trans[s] = 0;
   for (t = 0; t < B; ++t) {
@@ -363,7 +396,12 @@ int FN(ho_mix_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const RE
     int st;
     for (s = 0; s < K; ++s) {
       /* Mixture.hpp:98: `N * logNormalizers[s]` with N a size_t -> converted to REAL */
-      REAL E = FN(ho_inner_product)(mean[s], var[s], bsum[t], bsq[t]) - (REAL)N * logNorm[s];
+      REAL ip = 0, E;
+      for (d = 0; d < D; ++d) {
+        const int p = mapping[s * D + d];
+        ip += FN(ho_inner_product)(mean[p], var[p], bsum[t * D + d], bsq[t * D + d]);
+      }
+      E = ip - (REAL)N * logNorm[s];
       wts[s] = E;
       if (maxE < E) maxE = E;
     }
@@ -376,18 +414,30 @@ int FN(ho_mix_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const RE
     counts[st] += N;
     trans[st * K + st] += N - 1;
     trans[prevState * K + st] += 1;
-    y = bsum[t] - e1[st];
-    tmp = stat_sum[st] + y;
-    e1[st] = (tmp - stat_sum[st]) - y;
-    stat_sum[st] = tmp;
-    y = bsq[t] - e2[st];
-    tmp = stat_sq[st] + y;
-    e2[st] = (tmp - stat_sq[st]) - y;
-    stat_sq[st] = tmp;
-    stat_n[st] += N;
+    for (d = 0; d < D; ++d) {
+      const int p = mapping[st * D + d];
+      y = bsum[t * D + d] - e1[p];
+      tmp = stat_sum[p] + y;
+      e1[p] = (tmp - stat_sum[p]) - y;
+      stat_sum[p] = tmp;
+      y = bsq[t * D + d] - e2[p];
+      tmp = stat_sq[p] + y;
+      e2[p] = (tmp - stat_sq[p]) - y;
+      stat_sq[p] = tmp;
+      stat_n[p] += N;
+    }
     prevState = (size_t)st;
   }
   return 0;
+}
+
+int FN(ho_mix_sweep)(size_t B, const uint64_t* bsize, const REAL* bsum, const REAL* bsq, int K, const REAL* mean,
+                     const REAL* var, const double* uniforms, int16_t* states, REAL* stat_sum, REAL* stat_sq,
+                     uint64_t* stat_n, uint64_t* trans, uint64_t* counts) {
+  int ident[HO_MAXK], s;
+  for (s = 0; s < K; ++s) ident[s] = s;
+  return FN(ho_mix_sweep_md)(B, bsize, bsum, bsq, 1, K, ident, K, mean, var, uniforms, states, stat_sum, stat_sq,
+                             stat_n, trans, counts);
 }
 
 /* ------------------------------------------------------------------ conjugate updates */
@@ -421,16 +471,17 @@ void FN(ho_dirichlet_update)(REAL* alphas, const uint64_t* counts, size_t n) {
 /* AutoPriors.hpp:18-110 given the block list at threshold (REAL)(sqrt(2 log T) * sigma_hat):
  * block means and their squares are accumulated in REAL (SufficientStatistics.hpp:88-91), mean and
  * variance formed in double but RETURNED as REAL (EFD.hpp:41-60), closed form in mixed precision. */
-int FN(ho_auto_prior)(size_t B, const uint64_t* bsize, const REAL* bsum, REAL s2, REAL p, REAL* out4) {
+int FN(ho_auto_prior_md)(size_t B, const uint64_t* bsize, const REAL* bsum, size_t D, REAL s2, REAL p, REAL* out4) {
   REAL mSum = 0, mSumSq = 0;
-  size_t t;
-  for (t = 0; t < B; ++t) {
-    const REAL m = bsum[t] / (REAL)bsize[t];
-    mSum += m;
-    mSumSq += m * m;
-  }
+  size_t t, d;
+  for (t = 0; t < B; ++t)
+    for (d = 0; d < D; ++d) { /* :99-104: block-major, dimension-minor; N = nrBlocks * nrDim */
+      const REAL m = bsum[t * D + d] / (REAL)bsize[t];
+      mSum += m;
+      mSumSq += m * m;
+    }
   {
-    const double n = (double)B;
+    const double n = (double)(B * D);
     const REAL meanR = (REAL)(mSum / n);
     const double blocksMean = meanR;
     const double avg = meanR;
@@ -451,6 +502,10 @@ int FN(ho_auto_prior)(size_t B, const uint64_t* bsize, const REAL* bsum, REAL s2
     out4[3] = nu;
   }
   return 0;
+}
+
+int FN(ho_auto_prior)(size_t B, const uint64_t* bsize, const REAL* bsum, REAL s2, REAL p, REAL* out4) {
+  return FN(ho_auto_prior_md)(B, bsize, bsum, 1, s2, p, out4);
 }
 
 #undef FN

@@ -58,7 +58,12 @@ class Oracle:
 
     # ---- load-time transforms
     def maxlet(self, x):
+        """x: T values, or a (T, D) array of D-dimensional observations (position-major, as in the input file)."""
         x = self._a(x)
+        if x.ndim == 2:
+            out = np.empty(x.shape[0], dtype=self.dt)
+            self._f("ho_maxlet_md")(_p(x), C.c_size_t(x.shape[0]), C.c_size_t(x.shape[1]), _p(out))
+            return out
         out = np.empty_like(x)
         self._f("ho_maxlet")(_p(x), C.c_size_t(x.size), _p(out))
         return out
@@ -107,6 +112,78 @@ class Oracle:
             s[i] = a.value
             q[i] = b.value
         return (ends - starts).astype(np.uint64), s, q
+
+    # ---- multivariate data (Mapping.hpp:89-117, EFD.hpp:83-93, IntegralArray.hpp:136-212)
+    @staticmethod
+    def mapping(P, D):
+        """mapping[s][d] = emission parameter of state s in dimension d: reversed P-ary digits of s."""
+        K = P ** D
+        m = np.empty((K, D), dtype=np.int32)
+        for s in range(K):
+            n = s
+            for d in range(D):
+                m[s, d] = n % P
+                n //= P
+        return m
+
+    def integral_md(self, x):
+        """Per-dimension integral arrays: the reference's strided cells are the univariate construction on each
+        dimension's plane (IntegralArray.hpp:176-182)."""
+        x = self._a(x)
+        return [self.integral(np.ascontiguousarray(x[:, d])) for d in range(x.shape[1])]
+
+    def block_stats_md(self, integrals, starts, T):
+        """-> sizes[B], sum[B, D], sumsq[B, D]"""
+        cols = [self.block_stats(ig, starts, T) for ig in integrals]
+        return cols[0][0], np.stack([c[1] for c in cols], 1), np.stack([c[2] for c in cols], 1)
+
+    def fb_sweep_md(self, bsize, bsum, bsq, mapping, mean, var, A, pi, use_self, uniforms, want_rows=True):
+        bsize = np.ascontiguousarray(bsize, dtype=np.uint64)
+        mapping = np.ascontiguousarray(mapping, dtype=np.int32)
+        K, D = mapping.shape
+        B, P = bsize.size, len(mean)
+        bsum, bsq, mean, var = self._a(bsum).reshape(B, D), self._a(bsq).reshape(B, D), self._a(mean), self._a(var)
+        A, pi = self._a(A).reshape(K, K), self._a(pi)
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        rows = np.empty((B + 1, K), dtype=self.dt) if want_rows else None
+        states = np.empty(B, dtype=np.int16)
+        ssum, ssq = np.empty(P, dtype=self.dt), np.empty(P, dtype=self.dt)
+        sn, cnt = np.empty(P, dtype=np.uint64), np.empty(K, dtype=np.uint64)
+        trans = np.empty((K, K), dtype=np.uint64)
+        ll = C.c_double()
+        rc = self._f("ho_fb_sweep_md", C.c_int)(
+            C.c_size_t(B), _p(bsize), _p(bsum), _p(bsq), C.c_int(D), C.c_int(P), _p(mapping), C.c_int(K), _p(mean),
+            _p(var), _p(A), _p(pi), C.c_int(int(use_self)), _p(u), _p(rows) if want_rows else None, _p(states),
+            _p(ssum), _p(ssq), _p(sn), _p(trans), _p(cnt), C.byref(ll))
+        return dict(rc=rc, rows=rows, states=states, stat_sum=ssum, stat_sq=ssq, stat_n=sn, trans=trans,
+                    counts=cnt, loglik=ll.value)
+
+    def mix_sweep_md(self, bsize, bsum, bsq, mapping, mean, var, uniforms):
+        bsize = np.ascontiguousarray(bsize, dtype=np.uint64)
+        mapping = np.ascontiguousarray(mapping, dtype=np.int32)
+        K, D = mapping.shape
+        B, P = bsize.size, len(mean)
+        bsum, bsq, mean, var = self._a(bsum).reshape(B, D), self._a(bsq).reshape(B, D), self._a(mean), self._a(var)
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        states = np.empty(B, dtype=np.int16)
+        ssum, ssq = np.empty(P, dtype=self.dt), np.empty(P, dtype=self.dt)
+        sn, cnt = np.empty(P, dtype=np.uint64), np.empty(K, dtype=np.uint64)
+        trans = np.empty((K, K), dtype=np.uint64)
+        rc = self._f("ho_mix_sweep_md", C.c_int)(
+            C.c_size_t(B), _p(bsize), _p(bsum), _p(bsq), C.c_int(D), C.c_int(P), _p(mapping), C.c_int(K), _p(mean),
+            _p(var), _p(u), _p(states), _p(ssum), _p(ssq), _p(sn), _p(trans), _p(cnt))
+        return dict(rc=rc, states=states, stat_sum=ssum, stat_sq=ssq, stat_n=sn, trans=trans, counts=cnt)
+
+    def auto_prior_md(self, bsize, bsum, s2=0.2, p=0.9):
+        bsize = np.ascontiguousarray(bsize, dtype=np.uint64)
+        bsum = self._a(bsum)
+        D = bsum.shape[1] if bsum.ndim == 2 else 1
+        out = np.empty(4, dtype=self.dt)
+        rc = self._f("ho_auto_prior_md", C.c_int)(C.c_size_t(bsize.size), _p(bsize), _p(bsum), C.c_size_t(D),
+                                                  self.ct(s2), self.ct(p), _p(out))
+        if rc != 0:
+            raise ValueError("auto prior rejected its inputs")
+        return out
 
     # ---- sweeps
     def fb_sweep(self, bsize, bsum, bsq, mean, var, A, pi, use_self, uniforms, want_rows=True):
@@ -157,8 +234,9 @@ class Oracle:
     def posterior(self, res, tau_theta, tau_A, tau_pi):
         """Posterior hyper-parameters after one sweep (ForwardBackward.hpp:203-211)."""
         K = len(res["counts"])
-        pt = np.tile(self._a(tau_theta), (K, 1))
-        for s in range(K):
+        P = len(res["stat_n"])  # emission parameters (== K for univariate data)
+        pt = np.tile(self._a(tau_theta), (P, 1))
+        for s in range(P):
             if res["stat_n"][s] > 0:
                 _, pt[s] = self.nig_update(pt[s], res["stat_sum"][s], res["stat_sq"][s], res["stat_n"][s])
         pa = np.full((K, K), tau_A[0], dtype=self.dt)

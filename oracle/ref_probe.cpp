@@ -163,7 +163,8 @@ int main( int argc, const char* argv[] ) {
 			char buf[64];
 			for ( double v : raw ) { snprintf( buf, sizeof buf, "%.17g\n", v ); text << buf; }
 		}
-		const size_t nrDataDim = 1;
+		// multivariate jobs ("dims D"): the data file holds T*D values, position-major (wavelet.hpp:131-136)
+		const size_t nrDataDim = has( "dims" ) ? jint( "dims" ) : 1;
 		std::vector<real_t> inputValues;
 		std::vector<SufficientStatistics<Normal>> stats;
 		MaxletTransform( text, inputValues, stats, nrDataDim, raw.size() + 1 );      // main.cpp:277
@@ -190,13 +191,15 @@ int main( int argc, const char* argv[] ) {
 
 		auto dumpBlocks = [&]( const std::string & prefix ) {
 			std::vector<int64_t> st, en;
-			std::vector<double> sm, sq;
+			std::vector<double> sm, sq;          // block-major, dimension-minor
 			y.initForward();
 			while ( y.next() ) {
 				st.push_back( y.start() );
 				en.push_back( y.end() );
-				sm.push_back( y.suffStat( 0 ).sum() );
-				sq.push_back( y.suffStat( 0 ).sumSq() );
+				for ( size_t dim = 0; dim < nrDataDim; ++dim ) {
+					sm.push_back( y.suffStat( dim ).sum() );
+					sq.push_back( y.suffStat( dim ).sumSq() );
+				}
 			}
 			dumpI64( prefix + "starts", st );
 			dumpI64( prefix + "ends", en );
@@ -220,9 +223,10 @@ int main( int argc, const char* argv[] ) {
 			return 0;
 		}
 
-		const size_t K = jint( "K" );
+		const size_t P = jint( "K" );            // emission parameters ("-s C P D"); univariate: P == number of states
 		rng_t RNG( jint( "seed" ) );
-		Mapping mapping( nrDataDim, K, combinations );
+		Mapping mapping( nrDataDim, P, combinations );
+		const size_t K = mapping.nrStates();     // main.cpp:137
 
 		if ( mode == "sweep" ) {
 			// ---- model objects exactly as main.cpp:154-166,354-362 builds them
@@ -230,13 +234,15 @@ int main( int argc, const char* argv[] ) {
 			TransitionHyperParam<DirichletParamVector> tau_A( K, ( real_t ) jnum( "tau_A", 0 ), ( real_t ) jnum( "tau_A", 1 ) );
 			Initial<Dirichlet> pi( K, RNG );
 			InitialHyperParam<DirichletParam> tau_pi( K, ( real_t ) jnum( "tau_pi" ) );
-			std::vector<std::vector<real_t>> thetaParams( K, std::vector<real_t> {
+			std::vector<std::vector<real_t>> thetaParams( P, std::vector<real_t> {
 				( real_t ) jnum( "tau_theta", 0 ), ( real_t ) jnum( "tau_theta", 1 ), ( real_t ) jnum( "tau_theta", 2 ), ( real_t ) jnum( "tau_theta", 3 )} );
 			ThetaHyperParam<NormalInverseGammaParam> tau_theta( thetaParams );
 			Theta<NormalInverseGamma> theta( tau_theta, nrDataDim, combinations, RNG );
 			// ---- overwrite the sampled values with the job's fixed parameters
-			for ( size_t s = 0; s < K; ++s ) {
+			for ( size_t s = 0; s < P; ++s ) {
 				theta.mParams[s].setValue( ( real_t ) jnum( "theta", 2 * s ), ( real_t ) jnum( "theta", 2 * s + 1 ) );
+			}
+			for ( size_t s = 0; s < K; ++s ) {
 				pi.mValue.mProbs[s] = ( real_t ) jnum( "pi", s );
 				for ( size_t j = 0; j < K; ++j ) { A( s, j ) = ( real_t ) jnum( "A", s * K + j ); }
 			}
@@ -285,9 +291,11 @@ int main( int argc, const char* argv[] ) {
 #endif
 					dumpBlocks( "" );
 					std::vector<double> pt, pa, pp;
-					for ( size_t s = 0; s < K; ++s ) {
+					for ( size_t s = 0; s < P; ++s ) {
 						const auto& po = tau_theta.posterior( s );
 						pt.push_back( po.alpha() ); pt.push_back( po.beta() ); pt.push_back( po.mu0() ); pt.push_back( po.nu() );
+					}
+					for ( size_t s = 0; s < K; ++s ) {
 						pp.push_back( tau_pi.posterior()[s] );
 						for ( size_t j = 0; j < K; ++j ) { pa.push_back( tau_A.posterior()[s][j] ); }
 					}
@@ -301,11 +309,11 @@ int main( int argc, const char* argv[] ) {
 				pi.sample( tau_pi );
 				A.sample( tau_A );
 				records.record( theta );
-				for ( size_t s = 0; s < K; ++s ) { drawn.push_back( theta.value()[s].mean() ); drawn.push_back( theta.value()[s].var() ); }
+				for ( size_t s = 0; s < P; ++s ) { drawn.push_back( theta.value()[s].mean() ); drawn.push_back( theta.value()[s].var() ); }
 				for ( size_t s = 0; s < K; ++s ) { drawn.push_back( pi.valueVector()[s] ); }
 				for ( size_t s = 0; s < K; ++s ) for ( size_t j = 0; j < K; ++j ) { drawn.push_back( A( s, j ) ); }
 			}
-			dumpF64( "drawn", drawn );               // per sweep: K*(mean,var), K pi, K*K A
+			dumpF64( "drawn", drawn );               // per sweep: P*(mean,var), K pi, K*K A
 			dumpF64( "all_uniforms", allUniforms );
 			dumpI64( "all_states", allStates );
 			return 0;
@@ -319,7 +327,7 @@ int main( int argc, const char* argv[] ) {
 			Initial<Dirichlet> pi( K, RNG );
 			InitialHyperParam<DirichletParam> tau_pi( K, ( real_t ) 0.5 );
 			std::vector<real_t> ap = autoPrior( ( real_t ) 0.2, ( real_t ) 0.9, y, stdEstimate );
-			std::vector<std::vector<real_t>> thetaParams( K, ap );
+			std::vector<std::vector<real_t>> thetaParams( P, ap );
 			ThetaHyperParam<NormalInverseGammaParam> tau_theta( thetaParams );
 			Theta<NormalInverseGamma> theta( tau_theta, nrDataDim, combinations, RNG );
 			theta.sample( tau_theta );
