@@ -14,6 +14,12 @@ LIB_PATH = os.path.join(HERE, "libhammlet_b200.so")
 SWEEP_DYNAMIC, SWEEP_LOGLIK, SWEEP_KEEP_ROWS = 1, 2, 4
 DETECT_STREAM, DETECT_PYRAMID = 0, 1
 MAX_STATES = 32
+MAX_DIMS = 5
+
+
+def combinations_mapping(P, D):
+    """Mapping.hpp:89-117 (`combinations`): state s uses parameter (s // P**d) % P in dimension d; K = P**D states."""
+    return np.array([[(s // P ** d) % P for d in range(D)] for s in range(P ** D)], dtype=np.int32)
 
 
 class HmlError(RuntimeError):
@@ -24,7 +30,9 @@ class HmlError(RuntimeError):
 
 class _Model(C.Structure):
     _fields_ = [("K", C.c_int32), ("use_self_transitions", C.c_int32), ("mean", C.c_void_p), ("var", C.c_void_p),
-                ("A", C.c_void_p), ("pi", C.c_void_p)]
+                ("A", C.c_void_p), ("pi", C.c_void_p),
+                # multivariate data only: handle's nr_dims, number of emission parameters, mapping[s * nr_dims + d]
+                ("nr_dims", C.c_int32), ("nr_params", C.c_int32), ("mapping", C.c_void_p)]
 
 
 class _SweepOut(C.Structure):
@@ -34,7 +42,7 @@ class _SweepOut(C.Structure):
 
 
 EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_load_f32", "hml_load_f32_device",
-           "hml_size", "hml_sigma_hat", "hml_get_weights", "hml_get_coeffs", "hml_create_blocks", "hml_nr_blocks",
+           "hml_load_f32_md", "hml_load_f32_device_md", "hml_nr_dims", "hml_get_block_sums", "hml_size", "hml_sigma_hat", "hml_get_weights", "hml_get_coeffs", "hml_create_blocks", "hml_nr_blocks",
            "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
            "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream",
            "hml_comm_unique_id", "hml_comm_init", "hml_segment_plan", "hml_load_segment_f32",
@@ -100,9 +108,25 @@ class Handle:
 
     # ---- load
     def load(self, x, weight_multiplier=1.0):
+        """x: T values, or (T, D) for D-dimensional observations (position-major like the input stream)."""
         x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim == 2:
+            self._ck(self.lib.hml_load_f32_md(self.h, _ptr(x), C.c_uint64(x.shape[0]), C.c_uint32(x.shape[1]),
+                                              C.c_float(weight_multiplier)))
+            self.T = x.shape[0]
+            return
         self._ck(self.lib.hml_load_f32(self.h, _ptr(x), C.c_uint64(x.size), C.c_float(weight_multiplier)))
         self.T = x.size
+
+    def load_device_md(self, dev_ptr, T, nr_dims, weight_multiplier=1.0):
+        self._ck(self.lib.hml_load_f32_device_md(self.h, C.c_void_p(dev_ptr), C.c_uint64(T), C.c_uint32(nr_dims),
+                                                 C.c_float(weight_multiplier)))
+        self.T = int(T)
+
+    def nr_dims(self):
+        d = C.c_uint32()
+        self._ck(self.lib.hml_nr_dims(self.h, C.byref(d)))
+        return d.value
 
     def load_device(self, dev_ptr, T, weight_multiplier=1.0):
         self._ck(self.lib.hml_load_f32_device(self.h, C.c_void_p(dev_ptr), C.c_uint64(T), C.c_float(weight_multiplier)))
@@ -203,14 +227,27 @@ class Handle:
         self._ck(self.lib.hml_get_blocks(self.h, _ptr(starts), None, None, C.c_uint64(B)))
         return starts
 
+    def block_sums(self, dim=0):
+        """(sum x, sum x^2) per block of data dimension `dim`."""
+        B = self.nr_blocks()
+        s, q = np.empty(B, dtype=np.float64), np.empty(B, dtype=np.float64)
+        self._ck(self.lib.hml_get_block_sums(self.h, C.c_uint32(dim), _ptr(s), _ptr(q), C.c_uint64(B)))
+        return s, q
+
     # ---- sweeps
-    def _sweep(self, fn, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay):
-        K = len(mean)
+    def _sweep(self, fn, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay, mapping=None):
+        P = len(mean)   # emission parameters; with a mapping (K, D) the model has K = mapping.shape[0] states
         mean, var = np.ascontiguousarray(mean, np.float64), np.ascontiguousarray(var, np.float64)
+        if mapping is not None:
+            mapping = np.ascontiguousarray(mapping, np.int32)
+            K, D = mapping.shape
+        else:
+            K, D = P, 0
         A, pi = np.ascontiguousarray(A, np.float64).reshape(K, K), np.ascontiguousarray(pi, np.float64)
-        m = _Model(K, int(use_self), _ptr(mean), _ptr(var), _ptr(A), _ptr(pi))
-        ssum, ssq = np.zeros(K), np.zeros(K)
-        sn, cnt, tr = np.zeros(K, np.uint64), np.zeros(K, np.uint64), np.zeros((K, K), np.uint64)
+        m = _Model(K, int(use_self), _ptr(mean), _ptr(var), _ptr(A), _ptr(pi), D, P if mapping is not None else 0,
+                   _ptr(mapping) if mapping is not None else None)
+        ssum, ssq = np.zeros(P), np.zeros(P)
+        sn, cnt, tr = np.zeros(P, np.uint64), np.zeros(K, np.uint64), np.zeros((K, K), np.uint64)
         out = _SweepOut(0, 0, 0.0, _ptr(ssum), _ptr(ssq), _ptr(sn), _ptr(tr), _ptr(cnt))
         if replay is not None:
             replay = np.ascontiguousarray(replay, np.float64)
@@ -222,11 +259,15 @@ class Handle:
         return dict(nblocks=out.nblocks, fallbacks=out.uniform_fallbacks, loglik=out.loglik, stat_sum=ssum,
                     stat_sq=ssq, stat_n=sn, trans=tr, counts=cnt)
 
-    def fb_sweep(self, mean, var, A, pi, use_self=True, flags=0, threshold=0.0, seed=0, sweep=0, replay=None):
-        return self._sweep(self.lib.hml_fb_sweep, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay)
+    def fb_sweep(self, mean, var, A, pi, use_self=True, flags=0, threshold=0.0, seed=0, sweep=0, replay=None,
+                 mapping=None):
+        return self._sweep(self.lib.hml_fb_sweep, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay,
+                           mapping)
 
-    def mix_sweep(self, mean, var, A, pi, use_self=True, flags=0, threshold=0.0, seed=0, sweep=0, replay=None):
-        return self._sweep(self.lib.hml_mix_sweep, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay)
+    def mix_sweep(self, mean, var, A, pi, use_self=True, flags=0, threshold=0.0, seed=0, sweep=0, replay=None,
+                  mapping=None):
+        return self._sweep(self.lib.hml_mix_sweep, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay,
+                           mapping)
 
     # ---- records / debug
     def states(self):

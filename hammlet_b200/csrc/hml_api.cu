@@ -21,7 +21,8 @@ struct Stage {
   const char* name;
   cudaEvent_t ev;
 };
-constexpr size_t kOutWords = 2 + 32 + 32 * 32 + 2 + 2 * 32 + 2;  // device/pinned result block, 64-bit words
+// device/pinned result block, 64-bit words (the last term: per-state sums of the further dimensions of multivariate data)
+constexpr size_t kOutWords = 2 + 32 + 32 * 32 + 2 + 2 * 32 + 2 + 2 * 32 * (kMaxDims - 1);
 constexpr int kMaxWorld = 64;
 constexpr size_t kOpDoubles = 32 * 32 + 32;  // largest segment operator (mantissas + exponents)
 
@@ -87,8 +88,10 @@ struct hml_ctx {
   uint16_t* smax = nullptr; // bf16 max pyramid over sub-blocks of 32 weights (boundary detection reads only hot sub-blocks)
   int detect_mode = HML_DETECT_PYRAMID;
   float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
-  double2* pq = nullptr;    // integral arrays, T+1 entries
+  double2* pq = nullptr;    // integral arrays, T+1 entries (multivariate data: D planes, pq_stride entries apart)
   double4* cell_pref = nullptr;
+  int D = 1;                // data dimensions (hml_load_f32_md)
+  uint64_t pq_stride = 0, cell_stride = 0;
   double sigma_hat = NAN;
 
   // boundary detection scratch (bit masks + per-tile / per-CTA counts)
@@ -192,7 +195,7 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
   if (cap != h->capacity) {
     CK(dev_alloc(h->starts, cap + 1));
     CK(dev_alloc(h->bN, cap));
-    CK(dev_alloc(h->bS, cap));
+    CK(dev_alloc(h->bS, cap * (uint64_t)h->D));
     CK(dev_alloc(h->states, cap));
     CK(dev_alloc(h->tile_qin, tiles));
     h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
@@ -227,6 +230,9 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   memset(&b, 0, sizeof(b));
   b.pq = h->pq;
   b.cell_pref = h->cell_pref;
+  b.D = h->D;
+  b.pq_stride = h->pq_stride;
+  b.cell_stride = h->cell_stride;
   b.starts = h->starts;
   b.nblocks = h->outblk;
   b.capacity = h->capacity;
@@ -323,10 +329,11 @@ unsigned long long next_seq_cb(void* user, int which) {
   return ++h->p2p_seq[slot];
 }
 
-size_t result_words(int KP) {  // 8-byte words of the result block that travel to the host (and between ranks)
+// 8-byte words of the result block that travel to the host (and between ranks)
+size_t result_words(int KP, int D = 1) {
   size_t words = (size_t)KP + (size_t)KP * KP + 1;
   words += words & 1;
-  return 2 + words + 2 * KP + 1;
+  return 2 + words + 2 * KP + 1 + (size_t)(D - 1) * 2 * KP;
 }
 
 int run_detect(hml_t* h, float thr) {
@@ -358,6 +365,8 @@ void load_reset(hml_t* h) {
   h->T = 0;
   h->T_global = 0;
   h->seg_start = 0;
+  h->D = 1;
+  h->pq_stride = h->cell_stride = 0;
   h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
 }
 
@@ -392,13 +401,21 @@ int load_sum_odd(hml_t* h, const float* c, uint64_t n, double* out) {
   return HML_OK;
 }
 
-// integral arrays + double-double cell prefix of the local observations x[0..T)
-int load_integral(hml_t* h, const float* x_dev, uint64_t T) {
+// integral arrays + double-double cell prefix of the local observations x[0..T) (data dimension `dim` of `dims`:
+// every dimension has its own plane, Statistics/IntegralArray.hpp:176-182)
+int load_integral(hml_t* h, const float* x_dev, uint64_t T, int dim = 0, int dims = 1) {
   const uint64_t cells = T / kCell + 1;
-  CK(dev_alloc(h->pq, cells * kCell));
+  if (dim == 0) {
+    h->pq_stride = cells * kCell;
+    h->cell_stride = cells + 1;
+    CK(dev_alloc(h->pq, h->pq_stride * dims));
+    CK(dev_alloc(h->cell_pref, h->cell_stride * dims));
+  }
+  double2* const pq = h->pq + (size_t)dim * h->pq_stride;
+  double4* const cell_pref = h->cell_pref + (size_t)dim * h->cell_stride;
   double2* cell_tot = nullptr;
   CK(dev_alloc(cell_tot, cells));
-  launch_integral_cells(x_dev, T, h->pq, cell_tot, h->stream);
+  launch_integral_cells(x_dev, T, pq, cell_tot, h->stream);
   h->launches++;
   CK(cudaGetLastError());
   std::vector<double2> tot(cells);
@@ -423,8 +440,7 @@ int load_integral(hml_t* h, const float* x_dev, uint64_t T) {
       dd_add(hq, lq, tot[c].y);
     }
   }
-  CK(dev_alloc(h->cell_pref, cells + 1));
-  CK(cudaMemcpyAsync(h->cell_pref, pref.data(), (cells + 1) * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(cell_pref, pref.data(), (cells + 1) * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   dev_free(cell_tot);
   return HML_OK;
@@ -468,9 +484,11 @@ int load_upper_passes(hml_t* h, const float* in, uint64_t n_valid, uint64_t n_po
   return HML_OK;
 }
 
-int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
+// x_dev: T positions x D values, position-major (D = 1: the plain sequence)
+int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult, int D = 1) {
   if (h->world > 1) return fail(h, HML_ERR_STATE, "this handle joined a communicator: use hml_load_segment_f32");
   load_reset(h);
+  h->D = D;
   const uint64_t tiles = (T + kTile - 1) / kTile;
   load_norms(h);
 
@@ -479,8 +497,29 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
   float* sums[2] = {nullptr, nullptr};
   CK(dev_alloc(sums[0], tiles + 1));
   CK(dev_alloc(sums[1], tiles / kTile + 2));
-  int rc = load_upper_passes(h, x_dev, T, T, 1, 0, h->coeffs, sums);
-  if (rc != HML_OK) return rc;
+  int rc = HML_OK;
+  float *plane = nullptr, *cdim = nullptr;  // multivariate: one dimension at a time
+  if (D == 1) {
+    rc = load_upper_passes(h, x_dev, T, T, 1, 0, h->coeffs, sums);
+    if (rc != HML_OK) return rc;
+  } else {
+    CK(dev_alloc(plane, T));
+    CK(dev_alloc(cdim, tiles * kTile));
+    for (int d = 0; d < D; ++d) {
+      launch_deinterleave(x_dev, T, D, d, plane, h->sms, h->stream);
+      h->launches++;
+      // wavelet.hpp:150-163: the coefficient is the maximum over the dimensions of the normalised |detail|
+      rc = load_upper_passes(h, plane, T, T, 1, 0, d == 0 ? h->coeffs : cdim, sums);
+      if (rc != HML_OK) return rc;
+      if (d > 0) {
+        launch_max_combine(h->coeffs, cdim, T, h->sms, h->stream);
+        h->launches++;
+      }
+      rc = load_integral(h, plane, T, d, D);
+      if (rc != HML_OK) return rc;
+    }
+    dev_free(cdim);
+  }
   const float inf = INFINITY;
   CK(cudaMemcpyAsync(h->coeffs, &inf, sizeof(float), cudaMemcpyHostToDevice, h->stream));  // wavelet.hpp:183
 
@@ -501,8 +540,11 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult) {
   h->launches++;
   CK(cudaGetLastError());
 
-  rc = load_integral(h, x_dev, T);
-  if (rc != HML_OK) return rc;
+  if (D == 1) {
+    rc = load_integral(h, x_dev, T);
+    if (rc != HML_OK) return rc;
+  }
+  dev_free(plane);
   dev_free(sums[0]);
   dev_free(sums[1]);
   if (T > (1ull << 26)) dev_free(h->coeffs);  // 4 B/observation is not worth keeping for big inputs
@@ -621,19 +663,44 @@ int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, 
   return rc;
 }
 
-int validate_model(hml_t* h, const hml_model* m, ModelHost& mh) {
+// P = number of emission parameters (K for univariate data), map[s * D + d] = parameter of state s in dimension d
+int validate_model(hml_t* h, const hml_model* m, ModelHost& mh, int& P, std::vector<int>& map) {
   if (!m || !m->mean || !m->var || !m->A || !m->pi) return fail(h, HML_ERR_ARG, "model pointers must not be NULL");
   if (m->K < 2 || m->K > HML_MAX_STATES)
     return fail(h, HML_ERR_ARG, "number of states must be in [2, " + std::to_string(HML_MAX_STATES) + "]");
   memset(&mh, 0, sizeof(mh));
   mh.K = m->K;
+  mh.D = h->D;
   mh.use_self = m->use_self_transitions ? 1 : 0;
+  const int D = h->D;
+  const bool mapped = m->mapping != nullptr || m->nr_dims > 1;
+  if (D > 1 || mapped) {
+    if (m->nr_dims != D)
+      return fail(h, HML_ERR_ARG, "model.nr_dims (" + std::to_string(m->nr_dims) + ") does not match the loaded data (" +
+                                      std::to_string(D) + " dimensions)");
+    if (!m->mapping || m->nr_params < 1 || m->nr_params > HML_MAX_STATES)
+      return fail(h, HML_ERR_ARG, "multivariate data needs model.mapping and model.nr_params in [1, 32]");
+    P = m->nr_params;
+    map.assign(m->mapping, m->mapping + (size_t)m->K * D);
+    for (int v : map)
+      if (v < 0 || v >= P) return fail(h, HML_ERR_ARG, "model.mapping refers to a parameter outside [0, nr_params)");
+  } else {
+    P = m->K;
+    map.resize(m->K);
+    for (int i = 0; i < m->K; ++i) map[i] = i;
+  }
+  for (int p = 0; p < P; ++p) {
+    if (!isfinite(m->mean[p])) return fail(h, HML_ERR_ARG, "Mean must be set to a finite value!");
+    if (!(m->var[p] > 0) || !isfinite(m->var[p])) return fail(h, HML_ERR_ARG, "Variance must be positive!");
+  }
   for (int i = 0; i < m->K; ++i) {
-    if (!isfinite(m->mean[i])) return fail(h, HML_ERR_ARG, "Mean must be set to a finite value!");
-    if (!(m->var[i] > 0) || !isfinite(m->var[i])) return fail(h, HML_ERR_ARG, "Variance must be positive!");
     if (!(m->pi[i] >= 0)) return fail(h, HML_ERR_NUMERIC, "Negative backward variable!");
-    mh.mean[i] = m->mean[i];
-    mh.var[i] = m->var[i];
+    for (int d = 0; d < D; ++d) {
+      mh.mean_sd[d][i] = m->mean[map[(size_t)i * D + d]];
+      mh.var_sd[d][i] = m->var[map[(size_t)i * D + d]];
+    }
+    mh.mean[i] = mh.mean_sd[0][i];
+    mh.var[i] = mh.var_sd[0][i];
     mh.pi[i] = m->pi[i];
     for (int j = 0; j < m->K; ++j) {
       const double a = m->A[i * m->K + j];
@@ -657,9 +724,10 @@ struct SweepResult {
 int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged) {
   size_t words = (size_t)KP + (size_t)KP * KP + 1;
   words += words & 1;
-  const size_t copy_words = result_words(KP);
+  const size_t copy_words = result_words(KP, h->D);
+  const int nf = 2 * KP + 1 + (h->D - 1) * 2 * KP;  // + per-state sums of the further dimensions
   res.o64.assign(words, 0);
-  res.of.assign(2 * KP + 1, 0.0);
+  res.of.assign(nf, 0.0);
   const int world = h->world > 1 ? h->world : 1;
   const unsigned long long* host = h->outblk_host;
   if (world > 1) {
@@ -690,7 +758,7 @@ int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged) {
     const unsigned long long* o64 = blk + 2;
     const double* of = (const double*)(blk + 2 + words);
     for (size_t i = 0; i < words; ++i) res.o64[i] += o64[i];
-    for (int i = 0; i < 2 * KP + 1; ++i) res.of[i] += of[i];
+    for (int i = 0; i < nf; ++i) res.of[i] += of[i];
   }
   return HML_OK;
 }
@@ -702,7 +770,9 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
   if (!out) return fail(h, HML_ERR_ARG, "out must not be NULL");
   CK(cudaSetDevice(h->device));
   ModelHost mh;
-  int rc = validate_model(h, m, mh);
+  int P = 0;
+  std::vector<int> map;
+  int rc = validate_model(h, m, mh, P, map);
   if (rc != HML_OK) return rc;
   const int KP = padded_states(mh.K);
   const bool dynamic = (flags & HML_SWEEP_DYNAMIC) != 0;
@@ -796,12 +866,34 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     out->uniform_fallbacks = fallbacks;
     out->loglik = (flags & HML_SWEEP_LOGLIK) ? res.of[2 * KP] : NAN;
     for (int s = 0; s < mh.K; ++s) {
-      if (out->stat_sum) out->stat_sum[s] = res.of[s];
-      if (out->stat_sumsq) out->stat_sumsq[s] = res.of[KP + s];
-      if (out->stat_n) out->stat_n[s] = res.o64[s];
-      if (out->counts) out->counts[s] = res.o64[s];  // univariate: occupancy == observations per parameter
+      if (out->counts) out->counts[s] = res.o64[s];  // occupancy: observations per state
       if (out->trans)
         for (int j = 0; j < mh.K; ++j) out->trans[s * mh.K + j] = res.o64[KP + s * KP + j];
+    }
+    if (h->D == 1 && P == mh.K) {
+      for (int s = 0; s < mh.K; ++s) {  // univariate: state == parameter
+        if (out->stat_sum) out->stat_sum[s] = res.of[s];
+        if (out->stat_sumsq) out->stat_sumsq[s] = res.of[KP + s];
+        if (out->stat_n) out->stat_n[s] = res.o64[s];
+      }
+    } else {
+      // ForwardBackward.hpp:189-191: stats[mapping[state][d]].add(y.suffStat(d), N) — the per-(state, dimension)
+      // sums of the device are folded into the parameters in a fixed order (state-major, dimension-minor)
+      for (int p = 0; p < P; ++p) {
+        double sx = 0.0, sq = 0.0;
+        uint64_t n = 0;
+        for (int s = 0; s < mh.K; ++s)
+          for (int d = 0; d < h->D; ++d)
+            if (map[(size_t)s * h->D + d] == p) {
+              const double* base = d == 0 ? res.of.data() : res.of.data() + 2 * KP + 1 + (size_t)(d - 1) * 2 * KP;
+              sx += base[s];
+              sq += base[KP + s];
+              n += res.o64[s];
+            }
+        if (out->stat_sum) out->stat_sum[p] = sx;
+        if (out->stat_sumsq) out->stat_sumsq[p] = sq;
+        if (out->stat_n) out->stat_n[p] = n;
+      }
     }
     h->states_valid = true;
     h->rows_valid = (flags & HML_SWEEP_KEEP_ROWS) != 0 && !mixture;
@@ -1029,6 +1121,46 @@ int hml_load_f32(hml_t* h, const float* x_host, uint64_t T, float weight_multipl
   return rc;
 }
 
+int hml_load_f32_device_md(hml_t* h, const float* x_dev, uint64_t T, uint32_t nr_dims, float weight_multiplier) {
+  if (!h) return HML_ERR_ARG;
+  if (!x_dev) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (nr_dims == 0) return fail(h, HML_ERR_ARG, "Number of dimensions must be positive!");  // wavelet.hpp:106-108
+  if (nr_dims > HML_MAX_DIMS)
+    return fail(h, HML_ERR_ARG, "at most " + std::to_string(HML_MAX_DIMS) + " data dimensions are supported");
+  if (T == 0) return fail(h, HML_ERR_ARG, "Input vector for breakpoint weights is empty!");
+  if (T >= (1ull << 32)) return fail(h, HML_ERR_ARG, "one handle holds fewer than 2^32 observations; shard the sequence");
+  CK(cudaSetDevice(h->device));
+  return load_common(h, x_dev, T, weight_multiplier, (int)nr_dims);
+}
+
+int hml_load_f32_md(hml_t* h, const float* x_host, uint64_t T, uint32_t nr_dims, float weight_multiplier) {
+  if (!h) return HML_ERR_ARG;
+  if (!x_host) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (nr_dims == 0) return fail(h, HML_ERR_ARG, "Number of dimensions must be positive!");
+  if (nr_dims > HML_MAX_DIMS)
+    return fail(h, HML_ERR_ARG, "at most " + std::to_string(HML_MAX_DIMS) + " data dimensions are supported");
+  if (T == 0) return fail(h, HML_ERR_ARG, "Input vector for breakpoint weights is empty!");
+  if (T >= (1ull << 32)) return fail(h, HML_ERR_ARG, "one handle holds fewer than 2^32 observations; shard the sequence");
+  CK(cudaSetDevice(h->device));
+  float* xd = nullptr;
+  CK(dev_alloc(xd, T * nr_dims));
+  cudaError_t e = cudaMemcpyAsync(xd, x_host, T * nr_dims * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) {
+    dev_free(xd);
+    return fail(h, HML_ERR_CUDA, cudaGetErrorString(e));
+  }
+  const int rc = load_common(h, xd, T, weight_multiplier, (int)nr_dims);
+  cudaStreamSynchronize(h->stream);
+  dev_free(xd);
+  return rc;
+}
+
+int hml_nr_dims(const hml_t* h, uint32_t* nr_dims) {
+  if (!h || !nr_dims) return HML_ERR_ARG;
+  *nr_dims = (uint32_t)h->D;
+  return HML_OK;
+}
+
 int hml_size(const hml_t* h, uint64_t* T) {
   if (!h || !T) return HML_ERR_ARG;
   *T = h->world > 1 ? h->T_global : h->T;
@@ -1122,6 +1254,27 @@ int hml_nr_blocks(const hml_t* h, uint64_t* nblocks) {
   if (!h || !nblocks) return HML_ERR_ARG;
   if (!h->blocks_valid) return HML_ERR_STATE;
   *nblocks = h->nblocks;
+  return HML_OK;
+}
+
+int hml_get_block_sums(hml_t* h, uint32_t dim, double* sum, double* sumsq, uint64_t capacity) {
+  if (!h) return HML_ERR_ARG;
+  if (!h->blocks_valid) return fail(h, HML_ERR_STATE, "no block structure");
+  if (dim >= (uint32_t)h->D) return fail(h, HML_ERR_ARG, "dimension out of range");
+  if (!sum || !sumsq) return fail(h, HML_ERR_ARG, "sum and sumsq must be given together");
+  if (capacity < h->nblocks) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of blocks");
+  CK(cudaSetDevice(h->device));
+  const uint64_t B = h->nblocks;
+  double* tmp = nullptr;
+  CK(dev_alloc(tmp, 2 * B));
+  SweepBuffers b = make_buffers(h, 2);
+  b.bS = h->bS + (size_t)dim * h->capacity;
+  launch_unpermute(b, 0, B, nullptr, tmp, tmp + B, h->stream);
+  h->launches++;
+  CK(cudaMemcpyAsync(sum, tmp, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(sumsq, tmp + B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  dev_free(tmp);
   return HML_OK;
 }
 

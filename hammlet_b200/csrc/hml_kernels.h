@@ -12,6 +12,9 @@ void launch_maxlet_level(const float* in, uint64_t n_valid, uint64_t n_pos, uint
 void launch_bp_weights(const float* c, uint64_t T, float mult, float* w, int sms, cudaStream_t s);
 void launch_sum_odd(const float* c, uint64_t T, double* partial, int nblocks, cudaStream_t s);
 void launch_integral_cells(const float* x, uint64_t T, double2* pq, double2* cell_tot, cudaStream_t s);
+// multivariate input: plane[t] = x[t * nr_dims + dim]; dst[i] = max(dst[i], src[i]) (maxlet, wavelet.hpp:155-160)
+void launch_deinterleave(const float* x, uint64_t T, int nr_dims, int dim, float* plane, int sms, cudaStream_t s);
+void launch_max_combine(float* dst, const float* src, uint64_t n, int sms, cudaStream_t s);
 // segment mode (one sequence split over ranks): edge coefficients c[len - 2^k], k < 12, for the next rank
 void launch_pack_edge(const float* coeffs_local, uint64_t len, float* edge16, cudaStream_t s);
 // breakpoint weights of the local segment from local coefficients, the replicated table of the
@@ -57,10 +60,14 @@ void launch_p2p_exchange(const P2PDev* d, int slot, uint64_t seq, const void* se
                          cudaStream_t s);
 
 // ---- block-level sweep kernels (hml_sweep.cu)
+constexpr int kMaxDims = 5;  // HML_MAX_DIMS
 struct ModelHost {  // what the C ABI receives, validated
   int K;
   int use_self;
-  double mean[32], var[32], A[32 * 32], pi[32];
+  double mean[32], var[32], A[32 * 32], pi[32];  // univariate: per state (= per parameter)
+  // multivariate (D > 1): parameters resolved through the mapping, per state and dimension
+  int D;
+  double mean_sd[kMaxDims][32], var_sd[kMaxDims][32];
 };
 
 // Device buffers of one handle that the sweep kernels touch.  All per-block arrays are stored in
@@ -86,6 +93,9 @@ struct SweepBuffers {
   // inputs resident since load
   const double2* pq;        // T+1 cell-local running sums of (x, x^2)
   const double4* cell_pref; // per cell: double-double exclusive prefix of cell totals (hi_x, lo_x, hi_q, lo_q)
+  // multivariate data: D planes of pq / cell_pref / bS, `*_stride` elements apart (bS: `capacity` apart)
+  int D;
+  uint64_t pq_stride, cell_stride;
   // block structure
   const uint32_t* starts;   // capacity+1, natural order
   const unsigned long long* nblocks;  // device scalar
@@ -113,7 +123,8 @@ struct SweepBuffers {
   const double* replay_u;   // device copy of replay uniforms (may be null)
   double* partials;         // reduce scratch
   unsigned long long* out_u64;  // [0..KP) stat_n, [KP..KP+KP*KP) trans, then [fallbacks]
-  double* out_f64;          // [0..KP) sum, [KP..2KP) sumsq, [2KP] loglik
+  double* out_f64;          // [0..KP) sum, [KP..2KP) sumsq, [2KP] loglik; then per extra dimension d >= 1:
+                            // [2KP+1 + (d-1)*2KP ..) per-state sum and sumsq of dimension d
 };
 
 int padded_states(int K);          // KP for K (0 if unsupported)

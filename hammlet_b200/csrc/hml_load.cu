@@ -75,6 +75,20 @@ __global__ void __launch_bounds__(256) k_maxlet_level(const float* __restrict__ 
   }
 }
 
+// Multivariate input arrives position-major (wavelet.hpp:131-136); every dimension is transformed as its own plane.
+__global__ void __launch_bounds__(256) k_deinterleave(const float* __restrict__ x, uint64_t T, int nr_dims, int dim,
+                                                      float* __restrict__ plane) {
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x)
+    plane[t] = x[t * nr_dims + dim];
+}
+
+// Maxlet coefficient = maximum over the dimensions of the normalised |detail| (wavelet.hpp:155-160; max is exact,
+// incomplete wavelets are +inf in every dimension).
+__global__ void __launch_bounds__(256) k_max_combine(float* __restrict__ dst, const float* __restrict__ src, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    dst[i] = fmaxf(dst[i], src[i]);
+}
+
 // HaarBreakpointWeights in closed form.  The reference walks the levels top-down and pushes each
 // wavelet's |coefficient| to its left end L, its mid point and its right end R by max(), turning
 // wavelets with R >= T into +inf (also at L).  A wavelet with mid point j has half width
@@ -248,6 +262,18 @@ void launch_bp_weights_segment(const float* c_local, const float* ctop, const fl
 }
 void launch_sum_odd(const float* c, uint64_t T, double* partial, int nblocks, cudaStream_t s) {
   k_sum_odd<<<nblocks, 256, 0, s>>>(c, T, partial);
+}
+void launch_deinterleave(const float* x, uint64_t T, int nr_dims, int dim, float* plane, int sms, cudaStream_t s) {
+  uint64_t blocks = (T + 255) / 256;
+  if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
+  if (blocks == 0) return;
+  k_deinterleave<<<(unsigned)blocks, 256, 0, s>>>(x, T, nr_dims, dim, plane);
+}
+void launch_max_combine(float* dst, const float* src, uint64_t n, int sms, cudaStream_t s) {
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > (uint64_t)sms * 32) blocks = (uint64_t)sms * 32;
+  if (blocks == 0) return;
+  k_max_combine<<<(unsigned)blocks, 256, 0, s>>>(dst, src, n);
 }
 void launch_integral_cells(const float* x, uint64_t T, double2* pq, double2* cell_tot, cudaStream_t s) {
   const uint64_t cells = T / kCell + 1;  // covers index T

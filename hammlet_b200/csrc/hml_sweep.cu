@@ -112,6 +112,12 @@ void launch_seg_head(const SweepBuffers& b, uint64_t seg_len, unsigned long long
 
 void launch_block_stats(const SweepBuffers& b, int, uint64_t nblocks_hint, int sms, cudaStream_t s) {
   const uint64_t ntiles = (nblocks_hint + Layout::TB - 1) / Layout::TB;
+  if (b.D > 1) {
+    EmitMD<2> dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    k_block_emit_md<2, true, false, false><<<grid_for(ntiles * Layout::TB, 256, sms, 8), 256, 0, s>>>(b, dummy, 0);
+    return;
+  }
   ModelDev<2> dummy;
   memset(&dummy, 0, sizeof(dummy));
   k_block_emit<2, true, false, false><<<grid_for(ntiles * Layout::TB, 256, sms, 8), 256, 0, s>>>(b, dummy, 0);

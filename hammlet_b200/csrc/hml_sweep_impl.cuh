@@ -57,6 +57,36 @@ static ModelDev<KP> make_model(const ModelHost& m) {
   return d;
 }
 
+// Multivariate data (D > 1): state s uses parameter mapping[s][d] in dimension d (Mapping.hpp:89-117), so the
+// emission term is a sum over the dimensions (EFD.hpp:83-93) and the log-normaliser a sum over the state's
+// parameters (Theta.hpp:154-164).
+template <int KP>
+struct EmitMD {
+  double mean[kMaxDims][KP], inv2var[kMaxDims][KP];
+  double lognorm[KP], loga[KP];
+  int K, D;
+};
+
+template <int KP>
+static EmitMD<KP> make_emit_md(const ModelHost& m) {
+  EmitMD<KP> d;
+  memset(&d, 0, sizeof(d));
+  d.K = m.K;
+  d.D = m.D;
+  for (int s = 0; s < m.K; ++s) {
+    double ln = 0.0;
+    for (int dim = 0; dim < m.D; ++dim) {
+      const double mu = m.mean_sd[dim][s], var = m.var_sd[dim][s];
+      d.mean[dim][s] = mu;
+      d.inv2var[dim][s] = 1.0 / (2.0 * var);
+      ln += log(sqrt(var)) + mu * mu / (2 * var);
+    }
+    d.lognorm[s] = ln;
+    d.loga[s] = m.use_self ? log(m.A[s * m.K + s]) : 0.0;
+  }
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------------
 // small-vector helpers (all loops fully unrolled: register-resident vectors)
 
@@ -317,6 +347,22 @@ __device__ __forceinline__ void range_sums(const SweepBuffers& buf, uint32_t s, 
   }
 }
 
+// the same for data dimension d of multivariate input (per-dimension planes of the integral arrays)
+__device__ __forceinline__ void range_sums_dim(const SweepBuffers& buf, int d, uint32_t s, uint32_t e, double& sx,
+                                               double& sq) {
+  const double2* pq = buf.pq + (size_t)d * buf.pq_stride;
+  const double2 ps = pq[s], pe = pq[e];
+  sx = pe.x - ps.x;
+  sq = pe.y - ps.y;
+  const uint32_t cs = s >> kCellLog2, ce = e >> kCellLog2;
+  if (cs != ce) {
+    const double4* cp = buf.cell_pref + (size_t)d * buf.cell_stride;
+    const double4 a = cp[cs], z = cp[ce];
+    sx += (z.x - a.x) + (z.y - a.y);
+    sq += (z.z - a.z) + (z.w - a.w);
+  }
+}
+
 // k_seg_head: the observations in front of this rank's first boundary belong to a block that starts on
 // an earlier rank; their partial statistics travel with the rank's block count.
 // seq != 0: the head exchange runs inside this kernel (peer mailboxes), else the caller exchanges afterwards.
@@ -388,6 +434,70 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
       for (int s = 0; s < KP; ++s) {
         // EFD.hpp:23-32 then FB.hpp:74-81 (Mixture.hpp:98 has no self-transition term)
         double v = (2.0 * m.mean[s] * sx - sq) * m.inv2var[s] - N * m.lognorm[s];
+        if (!kMix) v += (N - 1.0) * m.loga[s];
+        E[s] = v;
+        if (s < m.K) mx = fmax(mx, v);
+      }
+#pragma unroll
+      for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp(E[s] - mx) : 0.0;
+      if (!kMix) {
+#pragma unroll
+        for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+      }
+      if (want_maxe) buf.maxE[p] = mx;
+    }
+  }
+}
+
+// k_block_emit_md: the same for multivariate data — block sums of every dimension (plane d of bS at d * capacity)
+// and emission terms summed over the dimensions.  Single handle only (no segment heads).
+template <int KP, bool kGather, bool kEmit, bool kMix>
+__global__ void __launch_bounds__(256) k_block_emit_md(SweepBuffers buf, EmitMD<KP> m, int want_maxe) {
+  if (kEmit && blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
+    for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
+  }
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  const int D = buf.D;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = Layout::inv(p);
+    if (b >= B) continue;
+    uint32_t n;
+    double sx[kMaxDims], sq[kMaxDims];
+    if (kGather) {
+      const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
+      n = e - s;
+      buf.bN[p] = n;
+#pragma unroll
+      for (int d = 0; d < kMaxDims; ++d) {
+        if (d < D) {
+          range_sums_dim(buf, d, s, e, sx[d], sq[d]);
+          buf.bS[(size_t)d * buf.capacity + p] = make_double2(sx[d], sq[d]);
+        }
+      }
+    } else {
+      n = buf.bN[p];
+#pragma unroll
+      for (int d = 0; d < kMaxDims; ++d) {
+        if (d < D) {
+          const double2 v = buf.bS[(size_t)d * buf.capacity + p];
+          sx[d] = v.x;
+          sq[d] = v.y;
+        }
+      }
+    }
+    if (kEmit) {
+      const double N = (double)n;
+      double E[KP];
+      double mx = -INFINITY;
+#pragma unroll
+      for (int s = 0; s < KP; ++s) {
+        double ip = 0.0;  // EFD.hpp:83-93: sum over the dimensions of the per-dimension inner products
+#pragma unroll
+        for (int d = 0; d < kMaxDims; ++d)
+          if (d < D) ip += (2.0 * m.mean[d][s] * sx[d] - sq[d]) * m.inv2var[d][s];
+        double v = ip - N * m.lognorm[s];
         if (!kMix) v += (N - 1.0) * m.loga[s];
         E[s] = v;
         if (s < m.K) mx = fmax(mx, v);
@@ -1662,6 +1772,51 @@ __global__ void __launch_bounds__(128) k_reduce_final(SweepBuffers buf, int npar
   if (threadIdx.x == 0) buf.out_f64[v] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
 }
 
+// Multivariate data: per-state (sum x, sum x^2) of one further dimension (plane `bS`), same fixed trees as
+// k_reduce_partial; counts and transitions do not depend on the dimension and are not recomputed.
+template <int KP>
+__global__ void __launch_bounds__(kReduceThreads) k_reduce_dim(SweepBuffers buf, const double2* __restrict__ bS,
+                                                               double* __restrict__ partials) {
+  __shared__ double s_sum[kReduceThreads / 32][2 * KP];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  double ax[KP], aq[KP];
+#pragma unroll
+  for (int s = 0; s < KP; ++s) ax[s] = aq[s] = 0.0;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
+    if (Layout::inv(p) >= B) continue;
+    const uint32_t st = buf.states[p];
+    const double2 v = bS[p];
+#pragma unroll
+    for (int s = 0; s < KP; ++s) {
+      const bool hit = st == (uint32_t)s;
+      ax[s] += hit ? v.x : 0.0;
+      aq[s] += hit ? v.y : 0.0;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < KP; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax[s] += shfl_xor_double(ax[s], o);
+      aq[s] += shfl_xor_double(aq[s], o);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int s = 0; s < KP; ++s) {
+      s_sum[threadIdx.x >> 5][s] = ax[s];
+      s_sum[threadIdx.x >> 5][KP + s] = aq[s];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * KP) {
+    double t = 0.0;
+    for (int wv = 0; wv < kReduceThreads / 32; ++wv) t += s_sum[wv][threadIdx.x];
+    partials[(size_t)blockIdx.x * 2 * KP + threadIdx.x] = t;
+  }
+}
+
 // Segment mode with peer mailboxes: the final sums and the statistics exchange in one single-CTA kernel.  Warp
 // w sums output values w, w + 8, ... over the partials (fixed order, fixed tree => deterministic).
 template <int KP>
@@ -1816,7 +1971,15 @@ int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, const SweepLaunch& 
     k_reduce_final_exchange<KP><<<1, 256, 0, s>>>(b, g, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
   else
     k_reduce_final<KP><<<2 * KP, 128, 0, s>>>(b, g);
-  return 2;
+  int launches = 2;
+  for (int d = 1; d < b.D; ++d) {  // multivariate data: the remaining dimensions, written behind the log-likelihood
+    SweepBuffers bd = b;
+    bd.out_f64 = b.out_f64 + 2 * KP + 1 + (size_t)(d - 1) * 2 * KP;
+    k_reduce_dim<KP><<<g, kReduceThreads, 0, s>>>(b, b.bS + (size_t)d * b.capacity, b.partials);
+    k_reduce_final<KP><<<2 * KP, 128, 0, s>>>(bd, g);
+    launches += 2;
+  }
+  return launches;
 }
 
 template <int KP>
@@ -1834,7 +1997,22 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   };
   constexpr bool kPrefix = KP <= 8;  // k_fwd_chunks_prefix + k_fwd_replay_prefix
   stage("block_emit");
-  {
+  if (b.D > 1) {
+    const EmitMD<KP> md = make_emit_md<KP>(mh);
+    const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
+    if (l.mixture) {
+      if (l.gather)
+        k_block_emit_md<KP, true, true, true><<<g, 256, 0, s>>>(b, md, 0);
+      else
+        k_block_emit_md<KP, false, true, true><<<g, 256, 0, s>>>(b, md, 0);
+    } else {
+      if (l.gather)
+        k_block_emit_md<KP, true, true, false><<<g, 256, 0, s>>>(b, md, loglik);
+      else
+        k_block_emit_md<KP, false, true, false><<<g, 256, 0, s>>>(b, md, loglik);
+    }
+    ++launches;
+  } else {
     const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
     if (l.mixture) {
       if (l.gather)

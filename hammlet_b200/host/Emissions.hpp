@@ -25,6 +25,7 @@ class DeviceSequence {
   hml_t* mHandle = nullptr;
   bool mOwns = true;
   uint64_t mSize = 0;
+  size_t mNrDim = 1;
   double mSigmaHat = 0;
 
  public:
@@ -38,6 +39,9 @@ class DeviceSequence {
     if (!loaded) throw std::runtime_error("NULL device handle");
     check(hml_size(mHandle, &mSize));
     check(hml_sigma_hat(mHandle, &mSigmaHat));
+    uint32_t d = 1;
+    check(hml_nr_dims(mHandle, &d));
+    mNrDim = d;
   }
   ~DeviceSequence() {
     if (mOwns) hml_destroy(mHandle);
@@ -46,14 +50,22 @@ class DeviceSequence {
     if (rc != HML_OK) throw std::runtime_error(hml_last_error(mHandle));
   }
   hml_t* handle() const { return mHandle; }
-  size_t size() const { return mSize; }
+  size_t size() const { return mSize; }     // positions
+  size_t nrDim() const { return mNrDim; }   // values per position
 
   // MaxletTransform + HaarBreakpointWeights + weight multiplier + integral arrays, on the device
-  // (wavelet.hpp:97-188, :68-93; main.cpp:332-334; IntegralArray.hpp:136-191)
-  void load(const std::vector<float>& values, float weightMultiplier) {
+  // (wavelet.hpp:97-188, :68-93; main.cpp:332-334; IntegralArray.hpp:136-191).  `values` holds the stream as read:
+  // nrDim values per position (wavelet.hpp:131-136).
+  void load(const std::vector<float>& values, float weightMultiplier, size_t nrDim = 1) {
     if (values.empty()) throw std::runtime_error("Input vector for breakpoint weights is empty!");
-    check(hml_load_f32(mHandle, values.data(), values.size(), weightMultiplier));
-    mSize = values.size();
+    if (values.size() % nrDim != 0)
+      throw std::runtime_error("Input stream did not contain enough values to fill all dimensions at last position!");
+    if (nrDim == 1)
+      check(hml_load_f32(mHandle, values.data(), values.size(), weightMultiplier));
+    else
+      check(hml_load_f32_md(mHandle, values.data(), values.size() / nrDim, (uint32_t)nrDim, weightMultiplier));
+    mSize = values.size() / nrDim;
+    mNrDim = nrDim;
     check(hml_sigma_hat(mHandle, &mSigmaHat));
   }
   // noise estimate from the finest detail coefficients (main.cpp:303-311)
@@ -65,7 +77,6 @@ class DeviceSequence {
 inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size_t nrDim, const float weightMultiplier,
                             const size_t reserveT = 0) {
   if (nrDim <= 0) throw std::runtime_error("Number of dimensions must be positive!");
-  if (nrDim != 1) throw std::runtime_error("Multivariate data is not supported by the B200 path yet (d = 1 only)!");
   if (!input) throw std::runtime_error("Cannot read input file or stream!");
   std::vector<float> values;
   values.reserve(reserveT);
@@ -76,7 +87,7 @@ inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size
     const std::string text = fastparse::slurp(input);
     fastparse::parseFloats(text.data(), text.size(), values);
   }
-  seq.load(values, weightMultiplier);
+  seq.load(values, weightMultiplier, nrDim);
 }
 
 template <typename T> class Blocks;
@@ -90,7 +101,7 @@ class Blocks<BreakpointArray> {
   bool mDirty = true;         // threshold changed since the device last built the structure
   // host copy for the iterator protocol
   std::vector<uint32_t> mStarts;
-  std::vector<double> mSum, mSumSq;
+  std::vector<double> mSum, mSumSq;  // dimension-major: [dim * nrBlocks + block]
   bool mHostValid = false;
   bool mIterating = false;
   size_t mCursor = 0, mBlockStart = 0, mBlockEnd = 0, mBlockCounter = 0;
@@ -134,9 +145,12 @@ class Blocks<BreakpointArray> {
     if (mHostValid && (!stats || !mSum.empty())) return;
     mStarts.resize(n);
     if (stats) {
-      mSum.resize(n);
-      mSumSq.resize(n);
+      const size_t D = mSeq.nrDim();
+      mSum.resize(n * D);
+      mSumSq.resize(n * D);
       mSeq.check(hml_get_blocks(mSeq.handle(), mStarts.data(), mSum.data(), mSumSq.data(), n));
+      for (size_t d = 1; d < D; ++d)
+        mSeq.check(hml_get_block_sums(mSeq.handle(), (uint32_t)d, mSum.data() + d * n, mSumSq.data() + d * n, n));
     } else {
       mSum.clear();
       mSumSq.clear();
@@ -173,28 +187,31 @@ class Blocks<BreakpointArray> {
     if (mIterating) throw std::runtime_error("Cannot determine size of block structure before all blocks have been seen!");
     return mBlockCounter;
   }
-  double currentSum() const { return mSum[mCursor]; }
-  double currentSumSq() const { return mSumSq[mCursor]; }
+  double currentSum(size_t dim = 0) const { return mSum[dim * mStarts.size() + mCursor]; }
+  double currentSumSq(size_t dim = 0) const { return mSumSq[dim * mStarts.size() + mCursor]; }
 };
 
 template <>
 class Statistics<IntegralArray, Normal> {
   DeviceSequence& mSeq;
-  SufficientStatistics<Normal> mCurrent;
+  std::vector<SufficientStatistics<Normal>> mCurrent;  // one per data dimension (IntegralArray.hpp:198-212)
 
  public:
   Statistics(const Statistics&) = delete;
-  Statistics(DeviceSequence& seq, const size_t nrDim) : mSeq(seq) {
-    if (nrDim != 1) throw std::runtime_error("Multivariate data is not supported by the B200 path yet (d = 1 only)!");
+  Statistics(DeviceSequence& seq, const size_t nrDim) : mSeq(seq), mCurrent(nrDim) {
     if (seq.size() <= 0) throw std::runtime_error("Input vector for breakpoint weights is empty!");
+    if (nrDim != seq.nrDim())
+      throw std::runtime_error("Cannot infer data dimension, the loaded sequence has " + std::to_string(seq.nrDim()) +
+                               " values per position!");
   }
   // block sums come from the device's fp64 integral arrays, rounded once to real_t
   template <typename B>
   void setStats(const Blocks<B>& blocks) {
-    mCurrent = SufficientStatistics<Normal>((real_t)blocks.currentSum(), (real_t)blocks.currentSumSq());
+    for (size_t dim = 0; dim < mCurrent.size(); ++dim)
+      mCurrent[dim] = SufficientStatistics<Normal>((real_t)blocks.currentSum(dim), (real_t)blocks.currentSumSq(dim));
   }
-  const SufficientStatistics<Normal>& suffStat(size_t) const { return mCurrent; }
-  size_t nrDim() const { return 1; }
+  const SufficientStatistics<Normal>& suffStat(size_t dim) const { return mCurrent[dim]; }
+  size_t nrDim() const { return mCurrent.size(); }
   size_t size() const { return mSeq.size(); }
 };
 

@@ -51,23 +51,45 @@ class StateSequence {
   template <typename ThetaType, typename TransitionsType, typename InitialType>
   static void fillModel(const ThetaType& theta, const TransitionsType& A, const InitialType& pi, const Mapping& mapping,
                         bool useSelf, std::vector<double>& mean, std::vector<double>& var, std::vector<double>& a,
-                        std::vector<double>& p, hml_model& m) {
+                        std::vector<double>& p, std::vector<int32_t>& map, hml_model& m) {
     const size_t K = A.nrStates();
-    if (mapping.nrDataDims() != 1) throw std::runtime_error("Multivariate data is not supported by the B200 path yet (d = 1 only)!");
-    mean.resize(K);
-    var.resize(K);
+    const size_t D = mapping.nrDataDims();
     a.resize(K * K);
     p = std::vector<double>(K);
     const std::vector<real_t> pv = pi.valueVector();
     for (size_t s = 0; s < K; ++s) {
-      const auto& param = theta.value()[mapping[s][0]];
-      mean[s] = param.mean();
-      var[s] = param.var();
       p[s] = pv[s];
       for (size_t j = 0; j < K; ++j) a[s * K + j] = A(s, j);
     }
+    m = hml_model{};
     m.K = (int32_t)K;
     m.use_self_transitions = useSelf ? 1 : 0;
+    if (D == 1) {
+      // univariate data: the device sees one (mean, var) per state, resolved through the mapping here
+      mean.resize(K);
+      var.resize(K);
+      for (size_t s = 0; s < K; ++s) {
+        const auto& param = theta.value()[mapping[s][0]];
+        mean[s] = param.mean();
+        var[s] = param.var();
+      }
+    } else {
+      // multivariate data: the P shared parameters and the state -> parameter mapping go to the device
+      // (Mapping.hpp:89-117); it returns per-parameter statistics (ForwardBackward.hpp:189-191)
+      const size_t P = theta.nrParams();
+      mean.resize(P);
+      var.resize(P);
+      for (size_t prm = 0; prm < P; ++prm) {
+        mean[prm] = theta.value()[prm].mean();
+        var[prm] = theta.value()[prm].var();
+      }
+      map.resize(K * D);
+      for (size_t s = 0; s < K; ++s)
+        for (size_t d = 0; d < D; ++d) map[s * D + d] = (int32_t)mapping[s][d];
+      m.nr_dims = (int32_t)D;
+      m.nr_params = (int32_t)P;
+      m.mapping = map.data();
+    }
     m.mean = mean.data();
     m.var = var.data();
     m.A = a.data();
@@ -117,11 +139,14 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
   DeviceSequence& seq = blocks.sequence();
 
   std::vector<double> mean, var, a, p;
+  std::vector<int32_t> map;
   hml_model model;
-  fillModel(theta, A, pi, mapping, useSelfTransitions, mean, var, a, p, model);
+  fillModel(theta, A, pi, mapping, useSelfTransitions, mean, var, a, p, map, model);
 
-  std::vector<double> statSum(nrStates), statSq(nrStates);
-  std::vector<uint64_t> statN(nrStates), trans(nrStates * nrStates), counts(nrStates);
+  // per-parameter statistics: one per state for univariate data, nrParams with a multivariate mapping
+  const size_t nrStatSlots = std::max(nrStates, nrParams);
+  std::vector<double> statSum(nrStatSlots), statSq(nrStatSlots);
+  std::vector<uint64_t> statN(nrStatSlots), trans(nrStates * nrStates), counts(nrStates);
   hml_sweep_out out;
   out.stat_sum = statSum.data();
   out.stat_sumsq = statSq.data();
@@ -152,7 +177,7 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
     mTrellis.fetch(seq, out.nblocks);
   }
 
-  // ---- posterior updates (ForwardBackward.hpp:203-211, Mixture.hpp:131-139); univariate: parameter == state
+  // ---- posterior updates (ForwardBackward.hpp:203-211, Mixture.hpp:131-139)
   for (size_t prm = 0; prm < nrParams; ++prm) {
     if (statN[prm] > 0) {
       const SufficientStatistics<StatsType> s((real_t)statSum[prm], (real_t)statSq[prm]);

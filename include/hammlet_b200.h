@@ -39,6 +39,7 @@ enum {
 };
 
 #define HML_MAX_STATES 32
+#define HML_MAX_DIMS 5 /* data dimensions of multivariate input (`-s C p d`: states = p^d <= HML_MAX_STATES) */
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
 
@@ -58,6 +59,14 @@ const char* hml_version(void);
 int hml_load_f32(hml_t* h, const float* x_host, uint64_t T, float weight_multiplier);
 /* Same with x already in device memory of the context's device (not modified, not retained). */
 int hml_load_f32_device(hml_t* h, const float* x_dev, uint64_t T, float weight_multiplier);
+/* Multivariate data (main.cpp:114-137 `-s C p d`, wavelet.hpp:131-163): x holds T positions x nr_dims values,
+ * position-major as they stand in the input stream.  The breakpoint weights come from the maxlet transform (the
+ * maximum over the dimensions of the absolute Haar coefficients, wavelet.hpp:155-160); integral arrays are kept per
+ * dimension (Statistics/IntegralArray.hpp:176-182).  nr_dims = 1 is hml_load_f32.  Not available on a handle that
+ * joined a communicator (a segment-split sequence is univariate). */
+int hml_load_f32_md(hml_t* h, const float* x_host, uint64_t T, uint32_t nr_dims, float weight_multiplier);
+int hml_load_f32_device_md(hml_t* h, const float* x_dev, uint64_t T, uint32_t nr_dims, float weight_multiplier);
+int hml_nr_dims(const hml_t* h, uint32_t* nr_dims);
 int hml_size(const hml_t* h, uint64_t* T);
 /* Noise estimate of main.cpp:303-311: mean of the level-1 |detail| coefficients / sqrt(2/pi). */
 int hml_sigma_hat(hml_t* h, double* sigma_hat);
@@ -86,6 +95,8 @@ int hml_nr_blocks(const hml_t* h, uint64_t* nblocks);
 /* Copies the current block structure to host: starts[nblocks] (block b = [starts[b], starts[b+1])
  * with starts[nblocks] = T implied), sum[nblocks], sumsq[nblocks].  Any pointer may be NULL. */
 int hml_get_blocks(hml_t* h, uint32_t* starts, double* sum, double* sumsq, uint64_t capacity);
+/* Block sums of data dimension `dim` (y.suffStat(dim), Emissions.hpp:60-64); dim 0 is what hml_get_blocks returns. */
+int hml_get_block_sums(hml_t* h, uint32_t dim, double* sum, double* sumsq, uint64_t capacity);
 
 /* ---- sweeps: replace StateSequence<ForwardBackward>::sample (StateSequence/ForwardBackward.hpp:
  *      16-213, incl. Trellis.hpp) and StateSequence<Mixture>::sample (StateSequence/Mixture.hpp:
@@ -94,10 +105,15 @@ int hml_get_blocks(hml_t* h, uint32_t* starts, double* sum, double* sumsq, uint6
 typedef struct {
   int32_t K;               /* number of states, 2..HML_MAX_STATES (univariate: state == parameter) */
   int32_t use_self_transitions; /* 0 with -S (main.cpp:157) */
-  const double* mean;      /* K   theta.value()[s].mean()  */
-  const double* var;       /* K   theta.value()[s].var()   */
+  const double* mean;      /* P   theta.value()[p].mean()   (P = K for univariate data) */
+  const double* var;       /* P   theta.value()[p].var()   */
   const double* A;         /* K*K row-major A(i,j)         */
   const double* pi;        /* K   pi.valueVector()         */
+  /* Multivariate data only (leave zero / NULL otherwise): the handle's nr_dims, the number P of emission
+   * parameters and mapping[s * nr_dims + d] = parameter used by state s in dimension d (Mapping.hpp:53-137). */
+  int32_t nr_dims;
+  int32_t nr_params;
+  const int32_t* mapping;
 } hml_model;
 
 typedef struct {
@@ -105,9 +121,9 @@ typedef struct {
   uint64_t uniform_fallbacks; /* ForwardBackward.hpp:106-111 events ("[WARNING] Uniform sampling...") */
   double loglik;              /* sum_t (max_s E_t(s) + log forwardSum_t); only if HML_SWEEP_LOGLIK */
   /* caller-provided arrays, filled on return */
-  double* stat_sum;           /* K    per-state sum x      (ForwardBackward.hpp:189-191) */
-  double* stat_sumsq;         /* K    per-state sum x^2 */
-  uint64_t* stat_n;           /* K    per-state number of observations (Kahan term count) */
+  double* stat_sum;           /* P    per-parameter sum x  (ForwardBackward.hpp:189-191; P = K for univariate data) */
+  double* stat_sumsq;         /* P    per-parameter sum x^2 */
+  uint64_t* stat_n;           /* P    per-parameter number of observations (Kahan term count) */
   uint64_t* trans;            /* K*K  transition counts incl. N-1 self transitions per block and the
                                       phantom 0 -> q0 transition (:182-184) */
   uint64_t* counts;           /* K    state occupancy (:185) */

@@ -140,6 +140,37 @@ def test_replay_run_is_identical_to_the_double_reference(tmp_path, seed, scheme)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("P,D,seed,scheme", [(2, 2, 7, "F 40 1"), (3, 2, 9, "M 10 0 F 30 2"), (2, 3, 4, "F 20 1 S F 20 1")])
+def test_multivariate_replay_run_is_identical_to_the_double_reference(tmp_path, P, D, seed, scheme):
+    """`-s C P D`: D values per position, P shared emission parameters, P**D states.  As in the
+    univariate case the -replay run of bin/hammlet64 must reproduce every output file of the real_t = double
+    reference byte for byte (maxlet weights, mapped emission terms, per-parameter statistics, auto priors)."""
+    from hammlet_b200.synth import piecewise_gaussian_md
+    ours, ref = need(os.path.join(BIN, "hammlet64")), need(os.path.join(REF, "hammlet64"))
+    T = 40000
+    x = piecewise_gaussian_md(T, P, D, 250, seed, quantum_bits=10)
+    with open(tmp_path / "in.txt", "w") as f:
+        f.write("\n".join(" ".join(f"{v:.10f}" for v in row) for row in x.astype(np.float64)) + "\n")
+    common = ["-f", "in.txt", "-a", "-R", str(seed), "-s", "C", str(P), str(D), "-i"] + scheme.split() + \
+             ["-O", "M", "S", "P", "B", "C", "G", "-w"]
+    r = run([ref] + common + ["-o", "ref-", ".csv"], cwd=tmp_path)
+    p = run([ours, "-replay"] + common + ["-o", "our-", ".csv"], cwd=tmp_path)
+    assert r.returncode == 0 and p.returncode == 0, p.stderr + r.stderr
+    for kind in ("blocks", "compression", "sequences", "parameters", "marginals", "segments"):
+        assert (tmp_path / f"our-{kind}.csv").read_text() == (tmp_path / f"ref-{kind}.csv").read_text(), kind
+    sizes, counts = read_marginals(tmp_path / "our-marginals.csv")
+    assert sizes.sum() == T and counts.shape[1] <= P ** D
+
+
+@pytest.mark.gpu
+def test_multivariate_input_must_fill_all_dimensions(tmp_path):
+    ours = need(os.path.join(BIN, "hammlet"))
+    p = run([ours, "-a", "-s", "C", "2", "2", "-w"], stdin="1 2 3 4 5\n", cwd=tmp_path)
+    assert p.returncode == 1
+    assert "Input stream did not contain enough values to fill all dimensions at last position!" in p.stderr
+
+
+@pytest.mark.gpu
 def test_default_scheme_marginals_agree_in_distribution(tmp_path):
     """Philox uniforms, float host parameters, the reference's default sampling scheme: posterior state
     marginals agree with the float reference within a total-variation tolerance (different RNG streams);
