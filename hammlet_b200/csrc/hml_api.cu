@@ -110,8 +110,9 @@ struct hml_ctx {
   int last_K = 0;
   double *e = nullptr, *sp = nullptr, *maxE = nullptr, *alpha = nullptr;
   uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *tile_maps = nullptr, *tile_qin = nullptr;
-  double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr;
-  int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr;
+  double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr, *group_ain = nullptr;
+  int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr, *wide_exp = nullptr;
+  double* wide_ops = nullptr;  // K > 8: scratch of k_fwd_chunks_wide
   double* rows = nullptr;
   uint64_t rows_cap = 0;
   double* replay_u = nullptr;
@@ -215,8 +216,16 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
     CK(dev_alloc(h->tile_ops, tiles * KP * KP));
     CK(dev_alloc(h->tile_exp, tiles * KP));
     CK(dev_alloc(h->tile_ain, tiles * KP));
-    CK(dev_alloc(h->group_ops, (size_t)32 * KP * KP));
-    CK(dev_alloc(h->group_exp, (size_t)32 * KP));
+    CK(dev_alloc(h->group_ops, (size_t)256 * KP * KP));  // kScanGroupsMax entries
+    CK(dev_alloc(h->group_exp, (size_t)256 * KP));
+    CK(dev_alloc(h->group_ain, (size_t)256 * KP));
+    if (wide_scratch_doubles(KP)) {
+      CK(dev_alloc(h->wide_ops, wide_scratch_doubles(KP) * h->sms * kWideCtasPerSm));
+      CK(dev_alloc(h->wide_exp, wide_scratch_ints(KP) * h->sms * kWideCtasPerSm));
+    } else {
+      dev_free(h->wide_ops);
+      dev_free(h->wide_exp);
+    }
     CK(dev_alloc(h->partials, reduce_partials_doubles(KP, h->sms * 32)));
     h->KP = KP;
     h->states_valid = h->rows_valid = false;
@@ -254,6 +263,9 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.tile_ain = h->tile_ain;
   b.group_ops = h->group_ops;
   b.group_exp = h->group_exp;
+  b.group_ain = h->group_ain;
+  b.wide_ops = h->wide_ops;
+  b.wide_exp = h->wide_exp;
   b.partials = h->partials;
   b.out_u64 = h->outblk + 2;
   size_t words = (size_t)KP + (size_t)KP * KP + 1;
@@ -1074,6 +1086,9 @@ int hml_destroy(hml_t* h) {
   dev_free(h->tile_ops);
   dev_free(h->tile_ain);
   dev_free(h->group_ops);
+  dev_free(h->group_ain);
+  dev_free(h->wide_ops);
+  dev_free(h->wide_exp);
   dev_free(h->chunk_exp);
   dev_free(h->tile_exp);
   dev_free(h->group_exp);

@@ -117,8 +117,11 @@ struct SweepBuffers {
   double* tile_ops;         // per tile KP*KP
   int* tile_exp;            // per tile KP
   double* tile_ain;         // per tile KP: normalised forward vector entering the tile
-  double* group_ops;        // scratch of the single-CTA tile scan
+  double* group_ops;        // scratch of the tile scan: operators of groups of tiles (256 entries)
   int* group_exp;
+  double* group_ain;        // forward vector entering each group of tiles (K > 8, multi-CTA tile scan)
+  double* wide_ops;         // K > 8: per-CTA scratch of k_fwd_chunks_wide (tree nodes of the tile operator), or null
+  int* wide_exp;
   double* rows;             // (capacity+1)*K, natural order, only with KEEP_ROWS (may be null)
   const double* replay_u;   // device copy of replay uniforms (may be null)
   double* partials;         // reduce scratch
@@ -133,6 +136,9 @@ int chunks_per_tile(int KP);       // C
 constexpr int kChunkLen = 32;      // L
 constexpr int kTileBlocks = 1024;  // L * C: per-block arrays are sized in multiples of this
 size_t reduce_partials_doubles(int KP, int grid);
+constexpr int kWideCtasPerSm = 2;  // CTAs of k_fwd_chunks_wide launched per SM (each owns a scratch area)
+size_t wide_scratch_doubles(int KP);  // per CTA; 0 for K <= 8
+size_t wide_scratch_ints(int KP);
 
 struct SweepLaunch {
   uint32_t flags;      // HML_SWEEP_* bits

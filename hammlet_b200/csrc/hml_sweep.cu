@@ -57,6 +57,8 @@ __global__ void k_unpermute(const uint8_t* states, const double2* bS, uint64_t B
 
 
 size_t reduce_partials_doubles(int KP, int grid) { return (size_t)grid * 2 * KP + 64; }
+size_t wide_scratch_doubles(int KP) { return KP > 8 ? (size_t)31 * KP * KP : 0; }
+size_t wide_scratch_ints(int KP) { return KP > 8 ? (size_t)31 * KP : 0; }
 
 #define HML_EXTERN(KP)                                                                                         \
   extern template int sweep_impl<KP>(const ModelHost&, const SweepBuffers&, const SweepLaunch&, cudaStream_t, \

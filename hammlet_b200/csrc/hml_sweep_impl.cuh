@@ -622,6 +622,149 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_fwd_chunks_wide (K > 8): the arithmetic of k_fwd_chunks (same row recursion, same rescaling, so the chunk
+// operators are bit-identical), laid out for the fp64 pipe instead of for registers:
+//   * thread (chunk, row) for ALL chunks of the tile at once where the register file allows (K <= 20: 32 K threads,
+//     12-20 warps per SM instead of 5), the row vector and its product in registers, A as constant-bank operands, the
+//     emission terms read at their use (the K threads of a chunk read the same values: one L1 line, broadcast);
+//   * the tile operator is a pairwise tree over the 32 chunk operators (5 levels of row-times-operator products
+//     through L2, every thread busy) instead of one warp walking the 32 operators one after the other.
+// Intermediate tree nodes live in a per-CTA scratch area in global memory (30 operators; L2-resident).
+template <int KP>
+struct WideCfg {
+  static constexpr int CG = (KP <= 20) ? 32 : 8;  // chunks per pass
+  static constexpr int THREADS = ((CG * KP + 31) / 32) * 32;
+  static constexpr int kTreeNodes = 31;            // 16 + 8 + 4 + 2 + 1
+  static constexpr size_t kScratchDoubles = (size_t)kTreeNodes * KP * KP;
+  static constexpr size_t kScratchInts = (size_t)kTreeNodes * KP;
+};
+
+// r <- r * Op through L2 (operands written by other threads of the CTA), without keeping the KP exponents in registers
+template <int KP>
+__device__ __forceinline__ void row_times_op_lean(double (&r)[KP], int& rex, const double* M, const int* X) {
+  int xm = kDeadExp;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const int x = __ldcg(X + k);
+    if (r[k] > 0.0 && x > xm) xm = x;
+  }
+  if (rex == kDeadExp || xm == kDeadExp) {
+#pragma unroll
+    for (int j = 0; j < KP; ++j) r[j] = 0.0;
+    rex = kDeadExp;
+    return;
+  }
+  double y[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) y[j] = 0.0;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const double a = r[k] * pow2i(__ldcg(X + k) - xm);
+#pragma unroll
+    for (int j = 0; j < KP; ++j) y[j] = fma(a, __ldcg(M + k * KP + j), y[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < KP; ++j) r[j] = y[j];
+  rex += xm;
+  renorm_pow2<KP>(r, rex);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(WideCfg<KP>::THREADS) k_fwd_chunks_wide(SweepBuffers buf, ModelDev<KP> m,
+                                                                         double* __restrict__ scratch_ops,
+                                                                         int* __restrict__ scratch_exp) {
+  constexpr int L = Layout::L, C = Layout::C, CG = WideCfg<KP>::CG;
+  static_assert(KP % 2 == 0, "emission terms are read as double2");
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const int cl = threadIdx.x / KP, i = threadIdx.x % KP;
+  double* const sops = scratch_ops + (size_t)blockIdx.x * WideCfg<KP>::kScratchDoubles;
+  int* const sexp = scratch_exp + (size_t)blockIdx.x * WideCfg<KP>::kScratchInts;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ---- chunk operators: K independent row recursions per chunk (FB.hpp:64-125 as operator products)
+#pragma unroll 1
+    for (int cg = 0; cg < C; cg += CG) {
+      const int c = cg + cl;
+      if (cl < CG) {
+        const uint64_t first = tile * Layout::TB + (uint64_t)c * L;
+        int steps = 0;
+        if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+        double r[KP];
+        int rex = 0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+        const double2* ep = reinterpret_cast<const double2*>(buf.e + Layout::at(tile, c, 0) * KP);
+#pragma unroll 1
+        for (int t = 0; t < steps; ++t) {
+          double y[KP];
+#pragma unroll
+          for (int j = 0; j < KP; ++j) y[j] = 0.0;
+#pragma unroll
+          for (int k = 0; k < KP; ++k) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) y[j] = fma(r[k], m.A[k][j], y[j]);
+          }
+          const double2* et = ep + (size_t)t * C * (KP / 2);
+#pragma unroll
+          for (int j = 0; j < KP; j += 2) {
+            const double2 ev = et[j / 2];
+            r[j] = y[j] * ev.x;
+            r[j + 1] = y[j + 1] * ev.y;
+          }
+          if (rex != kDeadExp) renorm_pow2<KP>(r, rex);
+        }
+        const uint64_t ch = tile * C + c;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.chunk_ops[(ch * KP + i) * KP + j] = r[j];
+        buf.chunk_exp[ch * KP + i] = rex;
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- tile operator: pairwise tree.  Level 0 reads the chunk operators, level l > 0 the nodes of level l - 1;
+    // node p of a level is (left operand 2p) x (right operand 2p + 1); the root goes to tile_ops.
+    int in_base = 0;   // first node of the previous level inside the scratch area
+    int out_base = 0;  // first node of this level
+#pragma unroll 1
+    for (int pairs = C / 2, level = 0; pairs >= 1; pairs >>= 1, ++level) {
+#pragma unroll 1
+      for (int task = threadIdx.x; task < pairs * KP; task += blockDim.x) {
+        const int pr = task / KP, row = task % KP;
+        const double* lop;
+        const int* lex;
+        const double* rop;
+        const int* rexp;
+        if (level == 0) {
+          lop = buf.chunk_ops + (tile * C + 2 * pr) * KP * KP;
+          lex = buf.chunk_exp + (tile * C + 2 * pr) * KP;
+          rop = lop + KP * KP;
+          rexp = lex + KP;
+        } else {
+          lop = sops + (size_t)(in_base + 2 * pr) * KP * KP;
+          lex = sexp + (size_t)(in_base + 2 * pr) * KP;
+          rop = lop + KP * KP;
+          rexp = lex + KP;
+        }
+        double r[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = __ldcg(lop + row * KP + j);
+        int rx = __ldcg(lex + row);
+        row_times_op_lean<KP>(r, rx, rop, rexp);
+        double* dst = pairs == 1 ? buf.tile_ops + (tile * KP + row) * KP : sops + ((size_t)(out_base + pr) * KP + row) * KP;
+        int* dex = pairs == 1 ? buf.tile_exp + tile * KP + row : sexp + (size_t)(out_base + pr) * KP + row;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) dst[j] = r[j];
+        *dex = rx;
+      }
+      __threadfence_block();
+      __syncthreads();
+      in_base = out_base;
+      out_base += pairs;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_fwd_chunks_prefix (K <= 8): as k_fwd_chunks, but what it leaves in chunk_ops is, for every chunk, the
 // ordered product of the EARLIER chunk operators of its tile (exclusive prefix; identity for chunk 0), so that
 // the replay kernel gets the vector entering a chunk from one vector-operator product instead of a serial walk.
@@ -1853,6 +1996,86 @@ __global__ void k_clear_out(SweepBuffers buf) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tile scan for K > 8 on a single handle, spread over the device (the single-CTA k_fwd_tilescan spends 15 ms on
+// 5 000 tiles at K = 20: a thousand threads at 64 registers walking 3 kB operators).  Same three steps, one launch
+// each; the number of tiles is only known on the device, so the grid is sized from the host's hint and every CTA
+// derives the same split of the tiles into G groups of S:
+//   k_tilescan_groups  CTA g, thread = operator row: group operator = ordered product of the group's tile operators
+//   k_tilescan_top     one warp: forward vector entering every group (G vector-operator products)
+//   k_tilescan_apply   CTA g, one warp: forward vector entering every tile of the group
+constexpr int kScanGroupsMax = 256;  // group_ops / group_exp / group_ain hold this many entries
+
+__device__ __forceinline__ void scan_split(int nt, int grid, int& G, int& S) {
+  const int gmax = grid < kScanGroupsMax ? grid : kScanGroupsMax;
+  S = nt > 0 ? (nt + gmax - 1) / gmax : 1;
+  G = nt > 0 ? (nt + S - 1) / S : 0;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(((KP + 31) / 32) * 32) k_tilescan_groups(SweepBuffers buf) {
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
+  int G, S;
+  scan_split(nt, (int)gridDim.x, G, S);
+  const int g = blockIdx.x, i = threadIdx.x;
+  if (g >= G || i >= KP) return;
+  double r[KP];
+  int rex = 0;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+  const int t0 = g * S, t1 = min(nt, (g + 1) * S);
+#pragma unroll 1
+  for (int t = t0; t < t1; ++t)
+    row_times_op<KP, false>(r, rex, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
+#pragma unroll
+  for (int j = 0; j < KP; ++j) buf.group_ops[((size_t)g * KP + i) * KP + j] = r[j];
+  buf.group_exp[g * KP + i] = rex;
+}
+
+template <int KP>
+__global__ void __launch_bounds__(32) k_tilescan_top(SweepBuffers buf, ModelDev<KP> m, int grid) {
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
+  int G, S;
+  scan_split(nt, grid, G, S);
+  if (G == 0) return;
+  const int lane = threadIdx.x;
+  double a = lane < KP ? m.pi[lane] : 0.0;  // row 0 of the trellis is pi itself (FB.hpp:57)
+  LaneOp<KP> cur, nxt;
+  load_lane_op<KP>(cur, buf.group_ops, buf.group_exp, lane);
+#pragma unroll 1
+  for (int g = 0; g < G; ++g) {
+    if (lane < KP) buf.group_ain[g * KP + lane] = a;
+    const int gn = (g + 1 < G) ? g + 1 : g;
+    load_lane_op<KP>(nxt, buf.group_ops + (size_t)gn * KP * KP, buf.group_exp + gn * KP, lane);
+    if (g + 1 < G && !warp_apply_op<KP>(a, cur) && lane == 0) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+    cur = nxt;
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(32) k_tilescan_apply(SweepBuffers buf) {
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
+  int G, S;
+  scan_split(nt, (int)gridDim.x, G, S);
+  const int g = blockIdx.x, lane = threadIdx.x;
+  if (g >= G) return;
+  double a = lane < KP ? buf.group_ain[g * KP + lane] : 0.0;
+  const int t0 = g * S, t1 = min(nt, (g + 1) * S);
+  LaneOp<KP> cur, nxt;
+  load_lane_op<KP>(cur, buf.tile_ops + (uint64_t)t0 * KP * KP, buf.tile_exp + (uint64_t)t0 * KP, lane);
+#pragma unroll 1
+  for (int t = t0; t < t1; ++t) {
+    if (lane < KP) buf.tile_ain[(uint64_t)t * KP + lane] = a;
+    const int tn = (t + 1 < t1) ? t + 1 : t;
+    load_lane_op<KP>(nxt, buf.tile_ops + (uint64_t)tn * KP * KP, buf.tile_exp + (uint64_t)tn * KP, lane);
+    if (t + 1 < t1 && !warp_apply_op<KP>(a, cur) && lane == 0) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+    cur = nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-side orchestration (one instantiation per padded state count)
 
 inline int grid_for(uint64_t items, int threads, int sms, int per_sm) {
@@ -1912,8 +2135,19 @@ int launch_fwd_tilescan_phase(const SweepBuffers& b, const ModelDev<KP>& m, uint
     return 2;
   } else {
     static_assert(KP <= 8 || kPhase != 3, "the embedded exchange exists for K <= 8");
-    k_fwd_tilescan<KP, kPhase><<<1, 1024, 0, s>>>(b, m);
-    return 1;
+    if constexpr (kPhase == 0) {
+      // groups of tiles: about one per SM, never more than the tiles there can be
+      int grid = ntiles_hint < (uint64_t)kScanGroupsMax ? (int)ntiles_hint : kScanGroupsMax;
+      if (grid > 148) grid = 148;
+      if (grid < 1) grid = 1;
+      k_tilescan_groups<KP><<<grid, ((KP + 31) / 32) * 32, 0, s>>>(b);
+      k_tilescan_top<KP><<<1, 32, 0, s>>>(b, m, grid);
+      k_tilescan_apply<KP><<<grid, 32, 0, s>>>(b);
+      return 3;
+    } else {
+      k_fwd_tilescan<KP, kPhase><<<1, 1024, 0, s>>>(b, m);
+      return 1;
+    }
   }
 }
 // phase 3 (K <= 8, peer mailboxes): phases 1 and 2 with the operator exchange between them, in one kernel
@@ -2040,10 +2274,15 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     }
   } else {
     stage("fwd_chunks");
-    if constexpr (kPrefix)
+    if constexpr (kPrefix) {
       k_fwd_chunks_prefix<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
-    else
+    } else if (b.wide_ops != nullptr) {
+      // at most kWideCtasPerSm CTAs per SM: that many scratch areas exist (alloc_blocks)
+      k_fwd_chunks_wide<KP><<<grid_for(ntiles, 1, l.sms, kWideCtasPerSm), WideCfg<KP>::THREADS, 0, s>>>(b, m, b.wide_ops,
+                                                                                                     b.wide_exp);
+    } else {
       k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
+    }
     ++launches;
     stage("fwd_tilescan");
     const bool embed = seg && b.seg.p2p != nullptr && KP <= 8;  // collectives inside the producing kernels

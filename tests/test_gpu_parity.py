@@ -230,6 +230,19 @@ def test_fb_sweep_replay_vs_oracle(dev, T, K, L, thr, use_self):
     _check_fb(dev, x, mu, var, A, pi, thr, use_self)
 
 
+@pytest.mark.parametrize("T,K,use_self", [(1_200_000, 20, 1), (600_000, 12, 1), (600_000, 16, 0), (500_000, 32, 1)])
+def test_fb_sweep_many_tiles_large_k(dev, T, K, use_self):
+    """K > 8 with hundreds of tiles (BASELINE configs[4] shape: level spacing 0.3 = one sigma, low compression):
+    the operator tree of k_fwd_chunks_wide and the multi-CTA tile scan (k_tilescan_groups / _top / _apply).
+    The emission exponents E_s grow with the spread of the levels (|E| ~ N mu^2 / sigma^2), and one ulp of E is a
+    relative error |E| * 2^-53 of exp(E - max E); with levels one sigma apart the 1e-9 bar holds for 32 states."""
+    x = piecewise_gaussian(T, K, 6, seed=T % 89 + K, spacing=0.3)
+    mu, var, A, pi = model_guess(K, seed=K, spacing=0.3)
+    dev.load(x)
+    out, _ = _check_fb(dev, x, mu, var, A, pi, 0.3, use_self)
+    assert out["nblocks"] > 148 * 1024      # more tiles than tile-scan groups
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "fb_T*.npz"))), ids=os.path.basename)
 def test_fb_sweep_vs_reference_fixture(dev, path):
     """Against dumps of the real_t=double reference itself (rows, states, posteriors' inputs)."""

@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "scan_latency.json"))
     ap.add_argument("--skip-c4", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated substrings of the configuration names to run")
     args = ap.parse_args()
     import torch
     from hammlet_b200 import capi
@@ -38,6 +39,8 @@ def main():
     lines = []
     for name, T, K, L, spacing, steps in CONFIGS:
         if args.skip_c4 and T >= 1_000_000_000:
+            continue
+        if args.only and not any(tok in name for tok in args.only.split(",")):
             continue
         bench.SPACING = spacing
         t0 = time.time()
