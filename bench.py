@@ -292,6 +292,23 @@ def main():
     torch.cuda.synchronize()
     wall = time.perf_counter() - w0
 
+    # ---- the second number SURVEY.md §8d asks for: thinning 1 — every sweep is recorded into the state marginals
+    # (Records / StateMarginals on the host, fed with one entry per equal-state run formed on the device).  Single
+    # handle only: a segment-split sequence keeps its runs rank-local.
+    recorded = None
+    if not segments:
+        rec_steps = max(10, steps // 5)
+        barrier()
+        r0 = time.perf_counter()
+        _, nseg = chain.run_recorded(rec_steps, thinning=1)
+        torch.cuda.synchronize()
+        rec_wall = time.perf_counter() - r0
+        runs = int(h.segments()[0].size)
+        recorded = {"value": rec_steps / rec_wall * (world if world > 1 else 1), "unit": UNIT, "thinning": 1,
+                    "steps": rec_steps, "runs_last_sweep": runs, "marginal_segments": int(nseg),
+                    "how": "wall clock through hammlet_chain_run_recorded: sweep + hml_get_segments (device run-length "
+                           "compaction, D2H of one entry per run) + StateMarginals::addRecord on the host"}
+
     # ---- region 3 (not part of `value`): the same steps with per-stage CUDA events, for the roofline and stage table
     h.set_timing(True)
     stage_ms, nblocks = {}, []
@@ -392,6 +409,7 @@ def main():
                      "sweep_bytes": 4.0 * T + B * (4 + 16 + 16 * K + 2),
                      "sweep_frac_of_hbm_roofline": (4.0 * T + B * (4 + 16 + 16 * K + 2)) / (world if segments else 1)
                                                    / peak / 1e9 / (ms_per_step * 1e-3)},
+        "recorded": recorded,
         "stream_detect": stream,
         "stage_ms": busy,
         "device_busy_ms_per_step": float(sum(busy.values())),

@@ -50,7 +50,8 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hml_detect_info",
            # include/hammlet_host.h
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
-           "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run"]
+           "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
+           "hammlet_chain_save_marginals"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -354,6 +355,18 @@ class Chain:
         self._ck(self.lib.hammlet_chain_run(self.c, C.c_char(method.encode()), C.c_uint64(iterations), C.c_int(int(dynamic)),
                                             C.c_int(int(use_self)), C.byref(nb)))
         return nb.value
+
+    def run_recorded(self, iterations, thinning=1, method="F", dynamic=True, use_self=True):
+        """sampleHMM with recording: every `thinning`-th sweep joins the state marginals.  -> (blocks of the last
+        sweep, marginal segments so far)"""
+        nb, ns = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.hammlet_chain_run_recorded(self.c, C.c_char(method.encode()), C.c_uint64(iterations),
+                                                     C.c_uint64(thinning), C.c_int(int(dynamic)), C.c_int(int(use_self)),
+                                                     C.byref(nb), C.byref(ns)))
+        return nb.value, ns.value
+
+    def save_marginals(self, path):
+        self._ck(self.lib.hammlet_chain_save_marginals(self.c, path.encode()))
 
     def close(self):
         if self.c:

@@ -117,6 +117,13 @@ struct hml_ctx {
   uint64_t rows_cap = 0;
   double* replay_u = nullptr;
   uint64_t replay_cap = 0;
+  // run-length view of the last sweep's states (hml_get_segments)
+  uint32_t* seg_counts = nullptr;  // per 1024-block tile: offset of its first run; [ntiles] = number of runs
+  uint32_t* seg_starts = nullptr;
+  int16_t* seg_states = nullptr;
+  uint64_t seg_cap = 0;            // blocks the three arrays are sized for
+  bool segs_valid = false;         // seg_counts holds the offsets of the current states
+  uint64_t nsegs = 0;
   double* partials = nullptr;
   unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
   unsigned long long* outblk_host = nullptr;  // pinned mirror
@@ -200,6 +207,7 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
     CK(dev_alloc(h->states, cap));
     CK(dev_alloc(h->tile_qin, tiles));
     h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
+    h->segs_valid = false;
     dev_free(h->rows);
     h->rows_cap = 0;
   }
@@ -908,6 +916,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
       }
     }
     h->states_valid = true;
+    h->segs_valid = false;
     h->rows_valid = (flags & HML_SWEEP_KEEP_ROWS) != 0 && !mixture;
     h->last_K = mh.K;
     return HML_OK;
@@ -1087,6 +1096,9 @@ int hml_destroy(hml_t* h) {
   dev_free(h->tile_ain);
   dev_free(h->group_ops);
   dev_free(h->group_ain);
+  dev_free(h->seg_counts);
+  dev_free(h->seg_starts);
+  dev_free(h->seg_states);
   dev_free(h->wide_ops);
   dev_free(h->wide_exp);
   dev_free(h->chunk_exp);
@@ -1352,32 +1364,46 @@ int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity) {
 int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t* seg_state, uint64_t capacity) {
   if (!h || !nsegments) return HML_ERR_ARG;
   if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
+  CK(cudaSetDevice(h->device));
   const uint64_t B = h->nblocks;
-  std::vector<int16_t> st(B);
-  std::vector<uint32_t> starts(B);
-  int rc = hml_get_states(h, st.data(), B);
-  if (rc != HML_OK) return rc;
-  rc = hml_get_blocks(h, starts.data(), nullptr, nullptr, B);
-  if (rc != HML_OK) return rc;
-  // Records.hpp:166-188: a segment ends where the state changes
-  uint64_t n = 0;
-  for (uint64_t b = 0; b < B; ++b) {
-    if (b == 0 || st[b] != st[b - 1]) {
-      if (seg_size && seg_state) {
-        if (n >= capacity) return fail(h, HML_ERR_CAPACITY, "segment buffer too small");
-        seg_state[n] = st[b];
-        seg_size[n] = starts[b];  // start position for now; turned into a size below
-      }
-      ++n;
-    }
+  if (B == 0) {
+    *nsegments = 0;
+    return HML_OK;
   }
-  if (seg_size && seg_state) {
-    for (uint64_t i = 0; i < n; ++i) {
-      const uint64_t next = (i + 1 < n) ? seg_size[i + 1] : h->seg_start + h->T;
-      seg_size[i] = next - seg_size[i];
-    }
+  // Records.hpp:166-188: a segment ends where the state changes.  The runs are formed on the device; only one
+  // (start, state) pair per run travels to the host.
+  const uint64_t ntiles = (B + 1023) / 1024;
+  if (h->seg_cap < h->capacity || !h->seg_counts) {
+    CK(dev_alloc(h->seg_counts, h->capacity / 1024 + 2));
+    CK(dev_alloc(h->seg_starts, h->capacity));
+    CK(dev_alloc(h->seg_states, h->capacity));
+    h->seg_cap = h->capacity;
+    h->segs_valid = false;
   }
+  SweepBuffers b = make_buffers(h, h->KP ? h->KP : 2);
+  if (!h->segs_valid) {
+    launch_segments_count(b, B, h->seg_counts, h->sms, h->stream);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    uint32_t n32 = 0;
+    CK(cudaMemcpyAsync(&n32, h->seg_counts + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->nsegs = n32;
+    h->segs_valid = true;
+  }
+  const uint64_t n = h->nsegs;
   *nsegments = n;
+  if (!seg_size || !seg_state) return HML_OK;
+  if (n > capacity) return fail(h, HML_ERR_CAPACITY, "segment buffer too small");
+  launch_segments_write(b, B, h->seg_counts, h->seg_starts, h->seg_states, h->sms, h->stream);
+  h->launches++;
+  CK(cudaGetLastError());
+  std::vector<uint32_t> st(n);
+  CK(cudaMemcpyAsync(st.data(), h->seg_starts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(seg_state, h->seg_states, n * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const uint64_t end = h->T;  // local positions; sizes do not depend on the segment offset of a split sequence
+  for (uint64_t i = 0; i < n; ++i) seg_size[i] = (uint64_t)(i + 1 < n ? st[i + 1] : end) - st[i];
   return HML_OK;
 }
 

@@ -170,6 +170,11 @@ int launch_sweep_sequential(const ModelHost& m, const SweepBuffers& b, const Swe
 // Copies per-block arrays out of the interleaved order: dst_states (int16), dst_sum/dst_sumsq.
 void launch_unpermute(const SweepBuffers& b, int KP, uint64_t nblocks, int16_t* dst_states, double* dst_sum,
                       double* dst_sumsq, cudaStream_t s);
+// Run-length view of the sampled states (nblocks > 0): tile_counts[0..ntiles] <- exclusive offsets of the runs that
+// start in each 1024-block tile, [ntiles] = number of runs (2 launches); then (start position, state) per run (1 launch).
+void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, uint32_t* tile_counts, int sms, cudaStream_t s);
+void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const uint32_t* tile_offsets, uint32_t* seg_start,
+                           int16_t* seg_state, int sms, cudaStream_t s);
 // Only block sums (no model): gather statistics for the current starts.
 void launch_block_stats(const SweepBuffers& b, int KP, uint64_t nblocks_hint, int sms, cudaStream_t s);
 

@@ -56,6 +56,97 @@ __global__ void k_unpermute(const uint8_t* states, const double2* bS, uint64_t B
 }
 
 
+// ---- run-length view of the sampled state sequence (what Records::record forms block by block, Records.hpp:166-188):
+// a run starts at block 0 and wherever the state differs from the previous block's.  Three small kernels — heads per
+// tile, exclusive scan of the tile counts, ordered write of (start position, state) — so that a recorded sweep moves
+// one entry per run to the host instead of one per block.
+__device__ __forceinline__ bool seg_is_head(const uint8_t* states, uint64_t b, uint64_t B) {
+  if (b >= B) return false;
+  if (b == 0) return true;
+  return states[Layout::perm(b)] != states[Layout::perm(b - 1)];
+}
+
+__global__ void __launch_bounds__(1024) k_seg_count(const uint8_t* __restrict__ states, uint64_t B, uint32_t* tile_counts) {
+  const uint64_t ntiles = (B + 1023) / 1024;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int n = __syncthreads_count(seg_is_head(states, tile * 1024 + threadIdx.x, B) ? 1 : 0);
+    if (threadIdx.x == 0) tile_counts[tile] = (uint32_t)n;
+  }
+}
+
+// in-place exclusive scan of tile_counts[0..ntiles) by one CTA; tile_counts[ntiles] receives the total
+__global__ void __launch_bounds__(1024) k_seg_scan(uint32_t* tile_counts, uint32_t ntiles) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_running;
+  if (threadIdx.x == 0) s_running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < ntiles; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < ntiles ? tile_counts[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t before = s_running + (warp ? s_warp[warp - 1] : 0u);
+    if (i < ntiles) tile_counts[i] = before + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_running = before + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_counts[ntiles] = s_running;
+}
+
+__global__ void __launch_bounds__(1024) k_seg_write(const uint8_t* __restrict__ states, const uint32_t* __restrict__ starts,
+                                                    uint64_t B, const uint32_t* __restrict__ tile_offsets,
+                                                    uint32_t* __restrict__ seg_start, int16_t* __restrict__ seg_state) {
+  __shared__ uint32_t s_warp[32];
+  const uint64_t ntiles = (B + 1023) / 1024;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint64_t b = tile * 1024 + threadIdx.x;
+    const bool head = seg_is_head(states, b, B);
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (head) {
+      const uint32_t idx = tile_offsets[tile] + before + __popc(bal & ((1u << lane) - 1u));
+      seg_start[idx] = starts[b];
+      seg_state[idx] = (int16_t)states[Layout::perm(b)];
+    }
+    __syncthreads();
+  }
+}
+
+void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, uint32_t* tile_counts, int sms, cudaStream_t s) {
+  const uint64_t ntiles = (nblocks + 1023) / 1024;
+  const int g = (int)(ntiles < (uint64_t)sms * 2 ? ntiles : (uint64_t)sms * 2);
+  k_seg_count<<<g, 1024, 0, s>>>(b.states, nblocks, tile_counts);
+  k_seg_scan<<<1, 1024, 0, s>>>(tile_counts, (uint32_t)ntiles);
+}
+void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const uint32_t* tile_offsets, uint32_t* seg_start,
+                           int16_t* seg_state, int sms, cudaStream_t s) {
+  const uint64_t ntiles = (nblocks + 1023) / 1024;
+  const int g = (int)(ntiles < (uint64_t)sms * 2 ? ntiles : (uint64_t)sms * 2);
+  k_seg_write<<<g, 1024, 0, s>>>(b.states, b.starts, nblocks, tile_offsets, seg_start, seg_state);
+}
+
 size_t reduce_partials_doubles(int KP, int grid) { return (size_t)grid * 2 * KP + 64; }
 size_t wide_scratch_doubles(int KP) { return KP > 8 ? (size_t)31 * KP * KP : 0; }
 size_t wide_scratch_ints(int KP) { return KP > 8 ? (size_t)31 * KP : 0; }

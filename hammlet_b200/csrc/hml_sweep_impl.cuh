@@ -3,6 +3,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/hammlet_b200.h"
@@ -629,7 +630,9 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS) k_fwd_chunks(SweepBuffers
 //     emission terms read at their use (the K threads of a chunk read the same values: one L1 line, broadcast);
 //   * the tile operator is a pairwise tree over the 32 chunk operators (5 levels of row-times-operator products
 //     through L2, every thread busy) instead of one warp walking the 32 operators one after the other.
-// Intermediate tree nodes live in a per-CTA scratch area in global memory (30 operators; L2-resident).
+// Intermediate tree nodes live in a per-CTA scratch area in global memory (30 operators; L2-resident); the right
+// operands of a level are staged in shared memory by the whole CTA in one coalesced pass (reading them element by
+// element through L2 inside the products cost 11 us per level: 40 dependent round trips at 100 registers).
 template <int KP>
 struct WideCfg {
   static constexpr int CG = (KP <= 20) ? 32 : 8;  // chunks per pass
@@ -637,15 +640,17 @@ struct WideCfg {
   static constexpr int kTreeNodes = 31;            // 16 + 8 + 4 + 2 + 1
   static constexpr size_t kScratchDoubles = (size_t)kTreeNodes * KP * KP;
   static constexpr size_t kScratchInts = (size_t)kTreeNodes * KP;
+  // dynamic shared memory: the (at most 16) right-hand operators of one tree level and their row exponents
+  static constexpr size_t kSmem = (size_t)16 * KP * KP * sizeof(double) + (size_t)16 * KP * sizeof(int);
 };
 
-// r <- r * Op through L2 (operands written by other threads of the CTA), without keeping the KP exponents in registers
+// r <- r * Op with the operator staged in shared memory, without keeping the KP exponents in registers
 template <int KP>
 __device__ __forceinline__ void row_times_op_lean(double (&r)[KP], int& rex, const double* M, const int* X) {
   int xm = kDeadExp;
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    const int x = __ldcg(X + k);
+    const int x = X[k];
     if (r[k] > 0.0 && x > xm) xm = x;
   }
   if (rex == kDeadExp || xm == kDeadExp) {
@@ -659,9 +664,9 @@ __device__ __forceinline__ void row_times_op_lean(double (&r)[KP], int& rex, con
   for (int j = 0; j < KP; ++j) y[j] = 0.0;
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    const double a = r[k] * pow2i(__ldcg(X + k) - xm);
+    const double a = r[k] * pow2i(X[k] - xm);
 #pragma unroll
-    for (int j = 0; j < KP; ++j) y[j] = fma(a, __ldcg(M + k * KP + j), y[j]);
+    for (int j = 0; j < KP; ++j) y[j] = fma(a, M[k * KP + j], y[j]);
   }
 #pragma unroll
   for (int j = 0; j < KP; ++j) r[j] = y[j];
@@ -680,6 +685,9 @@ __global__ void __launch_bounds__(WideCfg<KP>::THREADS) k_fwd_chunks_wide(SweepB
   const int cl = threadIdx.x / KP, i = threadIdx.x % KP;
   double* const sops = scratch_ops + (size_t)blockIdx.x * WideCfg<KP>::kScratchDoubles;
   int* const sexp = scratch_exp + (size_t)blockIdx.x * WideCfg<KP>::kScratchInts;
+  extern __shared__ __align__(16) unsigned char s_dyn_wide[];
+  double* const s_rop = reinterpret_cast<double*>(s_dyn_wide);       // [pair][KP*KP]
+  int* const s_rex = reinterpret_cast<int*>(s_rop + 16 * KP * KP);   // [pair][KP]
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---- chunk operators: K independent row recursions per chunk (FB.hpp:64-125 as operator products)
 #pragma unroll 1
@@ -727,29 +735,27 @@ __global__ void __launch_bounds__(WideCfg<KP>::THREADS) k_fwd_chunks_wide(SweepB
     int out_base = 0;  // first node of this level
 #pragma unroll 1
     for (int pairs = C / 2, level = 0; pairs >= 1; pairs >>= 1, ++level) {
+      // operands of this level: nodes 2p (left) and 2p + 1 (right) of the previous one
+      const double* const in_ops = level == 0 ? buf.chunk_ops + tile * C * KP * KP : sops + (size_t)in_base * KP * KP;
+      const int* const in_exp = level == 0 ? buf.chunk_exp + tile * C * KP : sexp + (size_t)in_base * KP;
+      for (int idx = threadIdx.x; idx < pairs * KP * KP; idx += blockDim.x) {
+        const int pr = idx / (KP * KP), off = idx % (KP * KP);
+        s_rop[idx] = __ldcg(in_ops + (size_t)(2 * pr + 1) * KP * KP + off);
+      }
+      for (int idx = threadIdx.x; idx < pairs * KP; idx += blockDim.x) {
+        const int pr = idx / KP, off = idx % KP;
+        s_rex[idx] = __ldcg(in_exp + (2 * pr + 1) * KP + off);
+      }
+      __syncthreads();
 #pragma unroll 1
       for (int task = threadIdx.x; task < pairs * KP; task += blockDim.x) {
         const int pr = task / KP, row = task % KP;
-        const double* lop;
-        const int* lex;
-        const double* rop;
-        const int* rexp;
-        if (level == 0) {
-          lop = buf.chunk_ops + (tile * C + 2 * pr) * KP * KP;
-          lex = buf.chunk_exp + (tile * C + 2 * pr) * KP;
-          rop = lop + KP * KP;
-          rexp = lex + KP;
-        } else {
-          lop = sops + (size_t)(in_base + 2 * pr) * KP * KP;
-          lex = sexp + (size_t)(in_base + 2 * pr) * KP;
-          rop = lop + KP * KP;
-          rexp = lex + KP;
-        }
+        const double* lop = in_ops + (size_t)(2 * pr) * KP * KP;
         double r[KP];
 #pragma unroll
         for (int j = 0; j < KP; ++j) r[j] = __ldcg(lop + row * KP + j);
-        int rx = __ldcg(lex + row);
-        row_times_op_lean<KP>(r, rx, rop, rexp);
+        int rx = __ldcg(in_exp + (2 * pr) * KP + row);
+        row_times_op_lean<KP>(r, rx, s_rop + pr * KP * KP, s_rex + pr * KP);
         double* dst = pairs == 1 ? buf.tile_ops + (tile * KP + row) * KP : sops + ((size_t)(out_base + pr) * KP + row) * KP;
         int* dex = pairs == 1 ? buf.tile_exp + tile * KP + row : sexp + (size_t)(out_base + pr) * KP + row;
 #pragma unroll
@@ -1784,10 +1790,19 @@ __global__ void __launch_bounds__(128) k_bwd_replay(SweepBuffers buf) {
     const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
     // state following this chunk = (maps of the later chunks of the tile)(state following the tile)
     uint32_t q = Map<KP>::load(buf.chunk_maps + ch * MB).get(buf.tile_qin[tile]);
-    for (int t = steps - 1; t >= 0; --t) {
-      const uint64_t p = Layout::at(tile, c, t);
-      q = Map<KP>::load(buf.maps + p * MB).get(q);
-      buf.states[p] = (uint8_t)q;
+    // the maps do not depend on the state being resolved: eight loads in flight, then the dependent look-ups
+    for (int t0 = steps - 1; t0 >= 0; t0 -= 8) {
+      Map<KP> mp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (t0 - i >= 0) mp[i] = Map<KP>::load(buf.maps + Layout::at(tile, c, t0 - i) * MB);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (t0 - i >= 0) {
+          q = mp[i].get(q);
+          buf.states[Layout::at(tile, c, t0 - i)] = (uint8_t)q;
+        }
+      }
     }
   }
 }
@@ -2278,8 +2293,9 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       k_fwd_chunks_prefix<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
     } else if (b.wide_ops != nullptr) {
       // at most kWideCtasPerSm CTAs per SM: that many scratch areas exist (alloc_blocks)
-      k_fwd_chunks_wide<KP><<<grid_for(ntiles, 1, l.sms, kWideCtasPerSm), WideCfg<KP>::THREADS, 0, s>>>(b, m, b.wide_ops,
-                                                                                                     b.wide_exp);
+      cudaFuncSetAttribute(k_fwd_chunks_wide<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WideCfg<KP>::kSmem);
+      k_fwd_chunks_wide<KP><<<grid_for(ntiles, 1, l.sms, kWideCtasPerSm), WideCfg<KP>::THREADS, WideCfg<KP>::kSmem, s>>>(
+          b, m, b.wide_ops, b.wide_exp);
     } else {
       k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
     }

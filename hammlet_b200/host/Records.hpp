@@ -176,6 +176,36 @@ class Records {
   // one block of the iteration being recorded: N observations in `state` (Records.hpp:155-235).
   // Equal-state neighbours merge into segments; a finished segment goes to the marginals and, as
   // "size:state", to the sequences file; the line ends when all T positions have been seen.
+  // A run of `nrBlocks` consecutive blocks in one state, N observations in total: what nrBlocks calls of
+  // record(state, n_i) amount to when the per-block sizes are not written out (the device merges the runs,
+  // hml_get_segments).  `nrBlocks` may be 0 for all runs but the first of an iteration as long as the counts add up
+  // to the iteration's block count (only the total enters the compression file).
+  void recordRun(const size_t state, const size_t N, const size_t nrBlocks) {
+    if (mRecordBlocks) throw std::runtime_error("Block sizes are being recorded: blocks must be recorded one by one!");
+    const bool first = mNrObservedPos == 0;
+    if (first) {
+      mSegmentState = state;
+      mSegmentSize = N;
+    } else if (state != mSegmentState) {
+      flushSegment(false);
+      mSegmentState = state;
+      mSegmentSize = N;
+      mNrSegments++;
+    } else {
+      mSegmentSize += N;
+    }
+    mNrBlocks += nrBlocks;
+    mNrObservedPos += N;
+    if (mNrObservedPos >= mSize) {
+      if (mNrObservedPos > mSize) throw std::runtime_error("Cannot record block, exceeding data size!");
+      if (mRecordCompression) mCompressionsFile << ((double)mSize) / ((double)mNrBlocks) << std::endl;
+      if (mRecordSegments) mSegmentFile << mMarginals.nrSegments() << "\t" << mMarginals.internalSize() << std::endl;
+      flushSegment(true);
+      mNrObservedPos = mNrBlocks = mSegmentSize = mNrSegments = 0;
+    }
+  }
+  const StateMarginals& marginals() const { return mMarginals; }
+
   void record(const size_t state, const size_t N) {
     const bool firstBlock = mNrBlocks == 0;
     if (firstBlock) {

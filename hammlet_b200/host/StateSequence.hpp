@@ -42,6 +42,8 @@ class Trellis {
 template <typename Type>
 class StateSequence {
   std::vector<marginal_t> mStates;
+  std::vector<uint64_t> mRunSize;     // equal-state runs of the last recorded iteration
+  std::vector<marginal_t> mRunState;
   rng_t& mRNG;
   Trellis mTrellis;
   bool mReplay = false;
@@ -193,7 +195,19 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
   tau_A.addObservation(transitions);
   tau_pi.addObservation(stateCounts);
 
-  // ---- records (ForwardBackward.hpp:193-195): block by block, in order
+  // ---- records (ForwardBackward.hpp:193-195).  Unless the per-block sizes are written out (-O B), the device
+  // merges equal-state neighbours into runs (Records.hpp:166-188 does the same block by block) and one entry per
+  // run travels to the host: ~T / mean segment length entries instead of one per block.
+  if (doRecord && !records.wantsBlocks() && !mKeepTrellis) {
+    uint64_t nruns = 0;
+    seq.check(hml_get_segments(seq.handle(), &nruns, nullptr, nullptr, 0));
+    mRunSize.resize(nruns);
+    mRunState.resize(nruns);
+    seq.check(hml_get_segments(seq.handle(), &nruns, mRunSize.data(), mRunState.data(), nruns));
+    for (uint64_t i = 0; i < nruns; ++i) records.recordRun((size_t)mRunState[i], (size_t)mRunSize[i], i == 0 ? out.nblocks : 0);
+    return;
+  }
+  // block by block, in order
   if (doRecord || (!kIsMixture && mKeepTrellis)) {
     mStates.resize(out.nblocks);
     seq.check(hml_get_states(seq.handle(), mStates.data(), mStates.size()));

@@ -118,27 +118,58 @@ int hammlet_chain_set(hammlet_chain* c, const float* mean, const float* var, con
   }
 }
 
+static void chain_run(hammlet_chain* c, char method, uint64_t iterations, uint64_t thinning, int dynamic,
+                      int use_self_transitions, uint64_t* nblocks_last) {
+  if (!dynamic && c->blocks.dirty()) c->y.createBlocks(c->theta);  // "S": freeze the structure of the current theta
+  if (method == 'F') {
+    StateSequence<ForwardBackward> q(c->rng);
+    sampleHMM(c->y, q, c->theta, c->tau_theta, c->A, c->tau_A, c->pi, c->tau_pi, c->mapping, (size_t)iterations,
+              (size_t)thinning, c->records, dynamic != 0, use_self_transitions != 0);
+  } else if (method == 'M') {
+    StateSequence<Mixture> q(c->rng);
+    sampleHMM(c->y, q, c->theta, c->tau_theta, c->A, c->tau_A, c->pi, c->tau_pi, c->mapping, (size_t)iterations,
+              (size_t)thinning, c->records, dynamic != 0, use_self_transitions != 0);
+  } else {
+    throw std::runtime_error(std::string("Unknown sampling type ") + method + "!");
+  }
+  if (nblocks_last) {
+    uint64_t gb = 0;
+    c->sequence.check(hml_segment_info(c->sequence.handle(), nullptr, nullptr, nullptr, nullptr, nullptr, &gb));
+    *nblocks_last = gb;
+  }
+}
+
 int hammlet_chain_run(hammlet_chain* c, char method, uint64_t iterations, int dynamic, int use_self_transitions,
                       uint64_t* nblocks_last) {
   if (!c) return HML_ERR_ARG;
   try {
-    if (!dynamic && c->blocks.dirty()) c->y.createBlocks(c->theta);  // "S": freeze the structure of the current theta
-    if (method == 'F') {
-      StateSequence<ForwardBackward> q(c->rng);
-      sampleHMM(c->y, q, c->theta, c->tau_theta, c->A, c->tau_A, c->pi, c->tau_pi, c->mapping, (size_t)iterations, 0,
-                c->records, dynamic != 0, use_self_transitions != 0);
-    } else if (method == 'M') {
-      StateSequence<Mixture> q(c->rng);
-      sampleHMM(c->y, q, c->theta, c->tau_theta, c->A, c->tau_A, c->pi, c->tau_pi, c->mapping, (size_t)iterations, 0,
-                c->records, dynamic != 0, use_self_transitions != 0);
-    } else {
-      throw std::runtime_error(std::string("Unknown sampling type ") + method + "!");
-    }
-    if (nblocks_last) {
-      uint64_t gb = 0;
-      c->sequence.check(hml_segment_info(c->sequence.handle(), nullptr, nullptr, nullptr, nullptr, nullptr, &gb));
-      *nblocks_last = gb;
-    }
+    chain_run(c, method, iterations, 0, dynamic, use_self_transitions, nblocks_last);
+    return HML_OK;
+  } catch (std::exception& e) {
+    c->error = e.what();
+    return HML_ERR_STATE;
+  }
+}
+
+int hammlet_chain_run_recorded(hammlet_chain* c, char method, uint64_t iterations, uint64_t thinning, int dynamic,
+                               int use_self_transitions, uint64_t* nblocks_last, uint64_t* marginal_segments) {
+  if (!c) return HML_ERR_ARG;
+  try {
+    chain_run(c, method, iterations, thinning, dynamic, use_self_transitions, nblocks_last);
+    if (marginal_segments) *marginal_segments = c->records.marginals().nrSegments();
+    return HML_OK;
+  } catch (std::exception& e) {
+    c->error = e.what();
+    return HML_ERR_STATE;
+  }
+}
+
+int hammlet_chain_save_marginals(hammlet_chain* c, const char* path) {
+  if (!c || !path) return HML_ERR_ARG;
+  try {
+    std::ofstream f(path);
+    if (!f.is_open()) throw std::runtime_error(std::string("Cannot write to file ") + path + "!");
+    c->records.marginals().save(f);
     return HML_OK;
   } catch (std::exception& e) {
     c->error = e.what();

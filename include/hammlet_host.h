@@ -41,6 +41,15 @@ int hammlet_chain_set(hammlet_chain* c, const float* mean, const float* var, con
 int hammlet_chain_run(hammlet_chain* c, char method, uint64_t iterations, int dynamic, int use_self_transitions,
                       uint64_t* nblocks_last);
 
+/* The same with recording (HMM.hpp:104-119): every `thinning`-th sweep (thinning > 0) the sampled state sequence joins
+ * the chain's state marginals (Records::record -> StateMarginals::addRecord, Records.hpp:155-235,
+ * StateMarginals.hpp:51-137), kept in memory.  The device hands over one (size, state) entry per equal-state run
+ * (hml_get_segments).  *marginal_segments = segments of the common refinement so far. */
+int hammlet_chain_run_recorded(hammlet_chain* c, char method, uint64_t iterations, uint64_t thinning, int dynamic,
+                               int use_self_transitions, uint64_t* nblocks_last, uint64_t* marginal_segments);
+/* Writes the marginals accumulated so far in the reference's file format (StateMarginals.hpp:268-310). */
+int hammlet_chain_save_marginals(hammlet_chain* c, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

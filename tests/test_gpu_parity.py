@@ -434,3 +434,35 @@ def test_cpp_chain_runs_sample_hmm(dev):
     chain.close()
     chain2.close()
     h.close()
+
+
+def test_cpp_chain_records_marginals_from_device_runs(dev, tmp_path):
+    """hammlet_chain_run_recorded: recorded sweeps hand one (size, state) entry per equal-state run to
+    Records / StateMarginals (hml_get_segments forms the runs on the device).  The saved marginals must be a valid
+    file of the reference's format: sizes sum to T, every line counts every recorded iteration exactly once; and
+    they must match a chain that records block by block (the Python route: states + block sizes -> oracle.Marginals)."""
+    from hammlet_b200.synth import piecewise_gaussian
+    T, K = 300_000, 3
+    x = piecewise_gaussian(T, K, 1500, seed=33)
+    h = capi.Handle(0)
+    h.load(x)
+    tau = capi.Chain.auto_prior(h, 0.2, 0.9)
+    chain = capi.Chain(h, K, tau, seed=9)
+    chain.run(40, method="M")
+    chain.run(40, method="F")
+    nb, nseg = chain.run_recorded(30, thinning=3, method="F")
+    assert 0 < nb < T and nseg >= 1
+    # the last recorded sweep is the last sweep: its runs are still on the device
+    sizes, states = h.segments()
+    assert sizes.sum() == T and np.all(states[1:] != states[:-1])
+    rs, rst = oracle.merge_runs(h.states(), np.diff(np.append(h.blocks(stats=False).astype(np.int64), T)))
+    assert np.array_equal(sizes.astype(np.int64), rs) and np.array_equal(states.astype(np.int64), rst)
+    path = tmp_path / "marginals.csv"
+    chain.save_marginals(str(path))
+    rows = [list(map(int, line.split("\t"))) for line in path.read_text().strip().split("\n")]
+    assert len(rows) == nseg
+    assert sum(r[0] for r in rows) == T and all(sum(r[1:]) == 10 for r in rows)
+    # every boundary of the last recorded segmentation is a boundary of the common refinement
+    assert set(np.cumsum(sizes)[:-1].tolist()) <= set(np.cumsum([r[0] for r in rows])[:-1].tolist())
+    chain.close()
+    h.close()

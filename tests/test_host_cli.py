@@ -117,6 +117,22 @@ def read_marginals(path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed,scheme", [(5, "F 60 1"), (11, "M 20 0 S P F 30 2 D F 30 1")])
+def test_replay_run_without_block_output_uses_device_runs(tmp_path, seed, scheme):
+    """Without -O B the recorded iterations reach Records as equal-state runs formed on the device
+    (Records::recordRun); marginals, sequences, compression, segments and parameters must still equal the
+    reference's files byte for byte."""
+    ours, ref = need(os.path.join(BIN, "hammlet64")), need(os.path.join(REF, "hammlet64"))
+    write_input(tmp_path / "in.txt", 60000, 3, 300, seed)
+    common = ["-f", "in.txt", "-a", "-R", str(seed), "-s", "3", "-i"] + scheme.split() + ["-O", "M", "S", "P", "C", "G", "-w"]
+    r = run([ref] + common + ["-o", "ref-", ".csv"], cwd=tmp_path)
+    p = run([ours, "-replay"] + common + ["-o", "our-", ".csv"], cwd=tmp_path)
+    assert r.returncode == 0 and p.returncode == 0, p.stderr + r.stderr
+    for kind in ("compression", "sequences", "parameters", "marginals", "segments"):
+        assert (tmp_path / f"our-{kind}.csv").read_text() == (tmp_path / f"ref-{kind}.csv").read_text(), kind
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,scheme", [(5, "F 60 1"), (11, "M 20 0 S P F 30 2 D F 30 1")])
 def test_replay_run_is_identical_to_the_double_reference(tmp_path, seed, scheme):
     """bin/hammlet64 -replay draws every uniform and every parameter from the shared mt19937 in the
     reference's order; with fp64 host parameters the whole run — all six output files — must equal the
