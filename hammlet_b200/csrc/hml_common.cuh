@@ -2,8 +2,31 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace hml {
+
+// Launch with the programmatic-stream-serialization attribute (HML_PDL=0 in the environment: plain stream order).
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("HML_PDL") && getenv("HML_PDL")[0] == '0');
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 constexpr int kMaxStates = 32;        // HML_MAX_STATES
 constexpr int kCellLog2 = 12;         // integral-array cell = 4096 observations
@@ -18,6 +41,15 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;
+}
+
+// ---- programmatic dependent launch: a kernel launched with launch_k may be scheduled while its predecessor in the
+// stream is still running; its CTAs then park in pdl_enter() until that grid has completed and its writes are visible.
+// pdl_enter() is the FIRST statement of every kernel launched this way (a CTA that left without waiting could let the
+// grid — and the stream — get ahead of its predecessor); it also lets the successor of this kernel be scheduled.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256)
                  uint32_t nspans, uint2* __restrict__ hot, uint32_t* __restrict__ span_info, uint32_t* __restrict__ span_off,
                  unsigned int* __restrict__ ticket, unsigned long long* __restrict__ nblocks_out,
                  uint32_t* __restrict__ starts, uint64_t capacity, unsigned long long* __restrict__ hot_counter) {
+  pdl_enter();
   __shared__ uint16_t s_list[kSpanSubs];
   __shared__ uint32_t s_mask[kSpanSubs];
   __shared__ uint32_t s_warp[2][8];
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(128)
     k_scatter_hot(const uint2* __restrict__ hot, const uint32_t* __restrict__ span_info, const uint32_t* __restrict__ span_off,
                   uint32_t* __restrict__ starts, uint64_t capacity) {
+  pdl_enter();
   const uint32_t span = blockIdx.x;
   const uint32_t info = span_info[span];
   if ((info & 0x3ffffu) == 0) return;
@@ -507,10 +509,10 @@ int launch_detect(const float* w, const uint16_t* smax, uint64_t T, float thr, i
   if (smax != nullptr) {
     const uint32_t spans = (uint32_t)((T + kSpanObs - 1) / kSpanObs);
     if (cb) cb(user, "detect_hot");
-    k_detect_hot<<<spans, 256, 0, s>>>(w, reinterpret_cast<const uint4*>(smax), T, thr, force_first, spans, d.hot,
-                                       d.span_info, d.span_off, d.ticket, nblocks_out, starts, capacity, d.hot_counter);
+    launch_k(k_detect_hot, spans, 256, 0, s, w, reinterpret_cast<const uint4*>(smax), T, thr, force_first, spans, d.hot,
+             d.span_info, d.span_off, d.ticket, nblocks_out, starts, capacity, d.hot_counter);
     if (cb) cb(user, "detect_scatter");
-    k_scatter_hot<<<spans, 128, 0, s>>>(d.hot, d.span_info, d.span_off, starts, capacity);
+    launch_k(k_scatter_hot, spans, 128, 0, s, d.hot, d.span_info, d.span_off, starts, capacity);
     return 2;
   }
   const uint32_t tiles = (uint32_t)((T + kTile - 1) / kTile);

@@ -393,6 +393,7 @@ static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint3
 
 template <int KP, bool kGather, bool kEmit, bool kMix>
 __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<KP> m, int want_maxe) {
+  pdl_enter();
   if (kEmit && blockIdx.x == 0) {
     // first kernel of a sweep: zero the result block that the later kernels accumulate into
     for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
@@ -781,6 +782,7 @@ __global__ void __launch_bounds__(WideCfg<KP>::THREADS) k_fwd_chunks_wide(SweepB
 //           node's operand is overwritten in place
 template <int KP>
 __global__ void __launch_bounds__(FwdCfg<KP>::THREADS, (KP <= 5 ? 4 : (KP <= 6 ? 3 : 2))) k_fwd_chunks_prefix(SweepBuffers buf, ModelDev<KP> m) {
+  pdl_enter();
   constexpr int L = Layout::L, C = Layout::C;
   static_assert(FwdCfg<KP>::CG == C && L % 4 == 0, "small-K configuration");
   __shared__ double s_ops[C * KP * KP];
@@ -910,6 +912,7 @@ struct ReplayCfg {
 
 template <int KP, bool kExact, bool kLoglik>
 __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m) {
+  pdl_enter();
   using Cfg = ReplayCfg<KP>;
   constexpr int L = Layout::L, C = Layout::C, S = Cfg::kSlab, NS = L / S;
   static_assert(!kLoglik || kExact, "the log-likelihood needs the forward sums");
@@ -1070,6 +1073,7 @@ __device__ __forceinline__ void load_gathered_op(OpVals<KP>& o, const double* g)
 template <int KP, int kPhase>
 __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, ModelDev<KP> m, int skip_upto,
                                                             unsigned long long seq) {
+  pdl_enter();
   constexpr int GMAX = 256 / KP < 48 ? 256 / KP : 48;
   __shared__ double s_gain[GMAX][KP];
   __shared__ double s_gop[GMAX * KP * KP];
@@ -1204,6 +1208,7 @@ struct ClusterScanCfg {
 template <int KP, int kPhase>
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(256)
     k_fwd_tilescan_cluster(SweepBuffers buf, ModelDev<KP> m, unsigned long long seq) {
+  pdl_enter();
   namespace cg = cooperative_groups;
   using Cfg = ClusterScanCfg<KP>;
   constexpr int SGMAX = Cfg::SGMAX;
@@ -1608,6 +1613,7 @@ __global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDe
 // itself (FB.hpp:138).  u_t is the block's counter-based Philox uniform, or the replayed one.
 template <int KP, bool kRows>
 __global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+  pdl_enter();
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
   const int K = m.K;
@@ -1655,6 +1661,7 @@ __global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP>
 // suffix scan over the warp: X_c = G_{c+1} o ... o G_31 (per chunk) and the tile map G_0 o ... o G_31.
 template <int KP>
 __global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf) {
+  pdl_enter();
   constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W;
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
@@ -1694,6 +1701,7 @@ __global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf) {
 // exchange through the peer mailboxes and resolution in one kernel
 template <int KP, int kMode>
 __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf, unsigned long long seq) {
+  pdl_enter();
   constexpr bool kSegMap = kMode == 1;
   constexpr int MB = 8 * Map<KP>::W;
   __shared__ uint64_t s_w[32][Map<KP>::W];
@@ -1780,6 +1788,7 @@ __global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf, unsigned lo
 // k_bwd_replay: thread per chunk, q_t = f_t[q_{t+1}]  (FB.hpp:140-160)
 template <int KP>
 __global__ void __launch_bounds__(128) k_bwd_replay(SweepBuffers buf) {
+  pdl_enter();
   constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W;
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t nch = (B + L - 1) / L;
@@ -1835,6 +1844,7 @@ constexpr int kReduceThreads = 256;
 
 template <int KP>
 __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers buf, int K) {
+  pdl_enter();
   __shared__ unsigned long long s_trans[KP * KP];
   __shared__ unsigned long long s_n[KP];
   __shared__ double s_sum[kReduceThreads / 32][2 * KP];
@@ -1919,6 +1929,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
 // one CTA per output value; fixed assignment and fixed tree => deterministic
 template <int KP>
 __global__ void __launch_bounds__(128) k_reduce_final(SweepBuffers buf, int nparts) {
+  pdl_enter();
   __shared__ double sh[4];
   const int v = blockIdx.x;  // 0 .. 2*KP-1
   double t = 0.0;
@@ -1996,6 +2007,7 @@ __global__ void __launch_bounds__(256) k_reduce_final_exchange(SweepBuffers buf,
 
 template <int KP>
 __global__ void k_sum_partials(const double* partials, int n, double* out) {
+  pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < n; ++i) t += partials[i];
@@ -2144,9 +2156,9 @@ int launch_fwd_tilescan_phase(const SweepBuffers& b, const ModelDev<KP>& m, uint
     using Cfg = ClusterScanCfg<KP>;
     // per device, so set on every launch (a host-side table lookup)
     cudaFuncSetAttribute(k_fwd_tilescan_cluster<KP, kPhase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-    k_fwd_tilescan_cluster<KP, kPhase><<<kClusterCtas, 256, Cfg::kSmem, s>>>(b, m, seq);
+    launch_k(k_fwd_tilescan_cluster<KP, kPhase>, kClusterCtas, 256, Cfg::kSmem, s, b, m, seq);
     if (ntiles_hint <= (uint64_t)Cfg::kMaxTiles) return 1;
-    k_fwd_tilescan_small<KP, kPhase><<<1, 256, 0, s>>>(b, m, Cfg::kMaxTiles, seq);
+    launch_k(k_fwd_tilescan_small<KP, kPhase>, 1, 256, 0, s, b, m, (int)Cfg::kMaxTiles, seq);
     return 2;
   } else {
     static_assert(KP <= 8 || kPhase != 3, "the embedded exchange exists for K <= 8");
@@ -2187,27 +2199,27 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
     if (cb) cb(user, "bwd_maps");
     const int gm = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
     if (rows)
-      k_bwd_maps<KP, true><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
+      launch_k(k_bwd_maps<KP, true>, gm, 256, 0, s, b, m, l.seed, l.sweep);
     else
-      k_bwd_maps<KP, false><<<gm, 256, 0, s>>>(b, m, l.seed, l.sweep);
+      launch_k(k_bwd_maps<KP, false>, gm, 256, 0, s, b, m, l.seed, l.sweep);
     if (cb) cb(user, "bwd_chunkmaps");
-    k_bwd_chunkmaps<KP><<<grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s>>>(b);
+    launch_k(k_bwd_chunkmaps<KP>, grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s, b);
   }
   if (cb) cb(user, "bwd_scan");
   if (b.seg.world > 1 && b.seg.p2p != nullptr) {
-    k_bwd_scan<KP, 2><<<1, 1024, 0, s>>>(b, l.next_seq(l.exchange_user, kExchangeMaps));
+    launch_k(k_bwd_scan<KP, 2>, 1, 1024, 0, s, b, l.next_seq(l.exchange_user, kExchangeMaps));
   } else {
     if (b.seg.world > 1) {
-      k_bwd_scan<KP, 1><<<1, 1024, 0, s>>>(b, 0);
+      launch_k(k_bwd_scan<KP, 1>, 1, 1024, 0, s, b, 0ull);
       ++launches;
       if (cb) cb(user, "exchange_maps");
       if (l.exchange(l.exchange_user, kExchangeMaps) != 0) return -1;
       if (cb) cb(user, "bwd_scan2");
     }
-    k_bwd_scan<KP, 0><<<1, 1024, 0, s>>>(b, 0);
+    launch_k(k_bwd_scan<KP, 0>, 1, 1024, 0, s, b, 0ull);
   }
   if (cb) cb(user, "bwd_replay");
-  k_bwd_replay<KP><<<grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s>>>(b);
+  launch_k(k_bwd_replay<KP>, grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s, b);
   return launches;
 }
 
@@ -2215,17 +2227,17 @@ template <int KP>
 int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, const SweepLaunch& l, cudaStream_t s) {
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
   const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 4);
-  k_reduce_partial<KP><<<g, kReduceThreads, 0, s>>>(b, K);
+  launch_k(k_reduce_partial<KP>, g, kReduceThreads, 0, s, b, K);
   if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
     k_reduce_final_exchange<KP><<<1, 256, 0, s>>>(b, g, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
   else
-    k_reduce_final<KP><<<2 * KP, 128, 0, s>>>(b, g);
+    launch_k(k_reduce_final<KP>, 2 * KP, 128, 0, s, b, g);
   int launches = 2;
   for (int d = 1; d < b.D; ++d) {  // multivariate data: the remaining dimensions, written behind the log-likelihood
     SweepBuffers bd = b;
     bd.out_f64 = b.out_f64 + 2 * KP + 1 + (size_t)(d - 1) * 2 * KP;
     k_reduce_dim<KP><<<g, kReduceThreads, 0, s>>>(b, b.bS + (size_t)d * b.capacity, b.partials);
-    k_reduce_final<KP><<<2 * KP, 128, 0, s>>>(bd, g);
+    launch_k(k_reduce_final<KP>, 2 * KP, 128, 0, s, bd, g);
     launches += 2;
   }
   return launches;
@@ -2265,14 +2277,14 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
     if (l.mixture) {
       if (l.gather)
-        k_block_emit<KP, true, true, true><<<g, 256, 0, s>>>(b, m, 0);
+        launch_k(k_block_emit<KP, true, true, true>, g, 256, 0, s, b, m, (int)0);
       else
-        k_block_emit<KP, false, true, true><<<g, 256, 0, s>>>(b, m, 0);
+        launch_k(k_block_emit<KP, false, true, true>, g, 256, 0, s, b, m, (int)0);
     } else {
       if (l.gather)
-        k_block_emit<KP, true, true, false><<<g, 256, 0, s>>>(b, m, loglik);
+        launch_k(k_block_emit<KP, true, true, false>, g, 256, 0, s, b, m, (int)loglik);
       else
-        k_block_emit<KP, false, true, false><<<g, 256, 0, s>>>(b, m, loglik);
+        launch_k(k_block_emit<KP, false, true, false>, g, 256, 0, s, b, m, (int)loglik);
     }
     ++launches;
   }
@@ -2290,7 +2302,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   } else {
     stage("fwd_chunks");
     if constexpr (kPrefix) {
-      k_fwd_chunks_prefix<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
+      launch_k(k_fwd_chunks_prefix<KP>, grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s, b, m);
     } else if (b.wide_ops != nullptr) {
       // at most kWideCtasPerSm CTAs per SM: that many scratch areas exist (alloc_blocks)
       cudaFuncSetAttribute(k_fwd_chunks_wide<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WideCfg<KP>::kSmem);
@@ -2318,18 +2330,18 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     if constexpr (kPrefix) {
       using RCfg = ReplayCfg<KP>;
       if (loglik) {
-        k_fwd_replay_prefix<KP, true, true><<<gr, 32, RCfg::kSmem, s>>>(b, m);
-        k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, gr, b.out_f64 + 2 * KP);
+        launch_k(k_fwd_replay_prefix<KP, true, true>, gr, 32, RCfg::kSmem, s, b, m);
+        launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else if (rows) {
-        k_fwd_replay_prefix<KP, true, false><<<gr, 32, RCfg::kSmem, s>>>(b, m);
+        launch_k(k_fwd_replay_prefix<KP, true, false>, gr, 32, RCfg::kSmem, s, b, m);
       } else {
-        k_fwd_replay_prefix<KP, false, false><<<gr, 32, RCfg::kSmem, s>>>(b, m);
+        launch_k(k_fwd_replay_prefix<KP, false, false>, gr, 32, RCfg::kSmem, s, b, m);
       }
     } else {
       if (loglik) {
         k_fwd_replay<KP, true><<<gr, 32, 0, s>>>(b, m);
-        k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, gr, b.out_f64 + 2 * KP);
+        launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else {
         k_fwd_replay<KP, false><<<gr, 32, 0, s>>>(b, m);
@@ -2362,7 +2374,7 @@ int sequential_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunc
       const double* ain = turn == 0 ? nullptr : b.seg.ops + (size_t)(turn - 1) * (KP * KP + KP);
       if (loglik) {
         k_fwd_sequential<KP, true><<<1, 32, 0, s>>>(b, m, ain);
-        k_sum_partials<KP><<<1, 32, 0, s>>>(b.partials, 1, b.out_f64 + 2 * KP);
+        launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, 1, b.out_f64 + 2 * KP);
         launches += 2;
       } else {
         k_fwd_sequential<KP, false><<<1, 32, 0, s>>>(b, m, ain);
