@@ -200,7 +200,7 @@ void launch_unpermute(const SweepBuffers& b, int, uint64_t nblocks, int16_t* dst
 }
 
 void launch_seg_head(const SweepBuffers& b, uint64_t seg_len, unsigned long long seq, cudaStream_t s) {
-  k_seg_head<<<1, 256, 0, s>>>(b, (uint32_t)seg_len, seq);
+  launch_k(k_seg_head, 1, 256, 0, s, b, (uint32_t)seg_len, seq);
 }
 
 void launch_block_stats(const SweepBuffers& b, int, uint64_t nblocks_hint, int sms, cudaStream_t s) {

@@ -368,6 +368,7 @@ __device__ __forceinline__ void range_sums_dim(const SweepBuffers& buf, int d, u
 // an earlier rank; their partial statistics travel with the rank's block count.
 // seq != 0: the head exchange runs inside this kernel (peer mailboxes), else the caller exchanges afterwards.
 static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint32_t seg_len, unsigned long long seq) {
+  pdl_enter();
   if (threadIdx.x == 0) {
     const uint64_t raw = *buf.nblocks;
     const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
 // and emission terms summed over the dimensions.  Single handle only (no segment heads).
 template <int KP, bool kGather, bool kEmit, bool kMix>
 __global__ void __launch_bounds__(256) k_block_emit_md(SweepBuffers buf, EmitMD<KP> m, int want_maxe) {
+  pdl_enter();
   if (kEmit && blockIdx.x == 0) {
     for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
     for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
@@ -679,6 +681,7 @@ template <int KP>
 __global__ void __launch_bounds__(WideCfg<KP>::THREADS) k_fwd_chunks_wide(SweepBuffers buf, ModelDev<KP> m,
                                                                          double* __restrict__ scratch_ops,
                                                                          int* __restrict__ scratch_exp) {
+  pdl_enter();
   constexpr int L = Layout::L, C = Layout::C, CG = WideCfg<KP>::CG;
   static_assert(KP % 2 == 0, "emission terms are read as double2");
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
@@ -1464,6 +1467,7 @@ __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDe
 
 template <int KP, bool kLoglik>
 __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m) {
+  pdl_enter();
   constexpr int L = Layout::L, C = Layout::C;
   __shared__ double s_ain[C][KP + 1];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
@@ -1821,6 +1825,7 @@ __global__ void __launch_bounds__(128) k_bwd_replay(SweepBuffers buf) {
 
 template <int KP>
 __global__ void __launch_bounds__(256) k_mix_sample(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+  pdl_enter();
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t first = buf.seg.world > 1 ? seg_first_block(buf.seg) : 0;
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
@@ -1946,6 +1951,7 @@ __global__ void __launch_bounds__(128) k_reduce_final(SweepBuffers buf, int npar
 template <int KP>
 __global__ void __launch_bounds__(kReduceThreads) k_reduce_dim(SweepBuffers buf, const double2* __restrict__ bS,
                                                                double* __restrict__ partials) {
+  pdl_enter();
   __shared__ double s_sum[kReduceThreads / 32][2 * KP];
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
@@ -1991,6 +1997,7 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_dim(SweepBuffers buf,
 template <int KP>
 __global__ void __launch_bounds__(256) k_reduce_final_exchange(SweepBuffers buf, int nparts, uint32_t stats_words,
                                                                unsigned long long seq) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int v = warp; v < 2 * KP; v += 8) {
     double t = 0.0;
@@ -2040,6 +2047,7 @@ __device__ __forceinline__ void scan_split(int nt, int grid, int& G, int& S) {
 
 template <int KP>
 __global__ void __launch_bounds__(((KP + 31) / 32) * 32) k_tilescan_groups(SweepBuffers buf) {
+  pdl_enter();
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
   int G, S;
@@ -2061,6 +2069,7 @@ __global__ void __launch_bounds__(((KP + 31) / 32) * 32) k_tilescan_groups(Sweep
 
 template <int KP>
 __global__ void __launch_bounds__(32) k_tilescan_top(SweepBuffers buf, ModelDev<KP> m, int grid) {
+  pdl_enter();
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
   int G, S;
@@ -2082,6 +2091,7 @@ __global__ void __launch_bounds__(32) k_tilescan_top(SweepBuffers buf, ModelDev<
 
 template <int KP>
 __global__ void __launch_bounds__(32) k_tilescan_apply(SweepBuffers buf) {
+  pdl_enter();
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const int nt = (int)((B + Layout::TB - 1) / Layout::TB);
   int G, S;
@@ -2167,9 +2177,9 @@ int launch_fwd_tilescan_phase(const SweepBuffers& b, const ModelDev<KP>& m, uint
       int grid = ntiles_hint < (uint64_t)kScanGroupsMax ? (int)ntiles_hint : kScanGroupsMax;
       if (grid > 148) grid = 148;
       if (grid < 1) grid = 1;
-      k_tilescan_groups<KP><<<grid, ((KP + 31) / 32) * 32, 0, s>>>(b);
-      k_tilescan_top<KP><<<1, 32, 0, s>>>(b, m, grid);
-      k_tilescan_apply<KP><<<grid, 32, 0, s>>>(b);
+      launch_k(k_tilescan_groups<KP>, grid, ((KP + 31) / 32) * 32, 0, s, b);
+      launch_k(k_tilescan_top<KP>, 1, 32, 0, s, b, m, grid);
+      launch_k(k_tilescan_apply<KP>, grid, 32, 0, s, b);
       return 3;
     } else {
       k_fwd_tilescan<KP, kPhase><<<1, 1024, 0, s>>>(b, m);
@@ -2229,14 +2239,14 @@ int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, const SweepLaunch& 
   const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 4);
   launch_k(k_reduce_partial<KP>, g, kReduceThreads, 0, s, b, K);
   if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
-    k_reduce_final_exchange<KP><<<1, 256, 0, s>>>(b, g, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
+    launch_k(k_reduce_final_exchange<KP>, 1, 256, 0, s, b, g, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
   else
     launch_k(k_reduce_final<KP>, 2 * KP, 128, 0, s, b, g);
   int launches = 2;
   for (int d = 1; d < b.D; ++d) {  // multivariate data: the remaining dimensions, written behind the log-likelihood
     SweepBuffers bd = b;
     bd.out_f64 = b.out_f64 + 2 * KP + 1 + (size_t)(d - 1) * 2 * KP;
-    k_reduce_dim<KP><<<g, kReduceThreads, 0, s>>>(b, b.bS + (size_t)d * b.capacity, b.partials);
+    launch_k(k_reduce_dim<KP>, g, kReduceThreads, 0, s, b, (const double2*)(b.bS + (size_t)d * b.capacity), b.partials);
     launch_k(k_reduce_final<KP>, 2 * KP, 128, 0, s, bd, g);
     launches += 2;
   }
@@ -2263,14 +2273,14 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
     if (l.mixture) {
       if (l.gather)
-        k_block_emit_md<KP, true, true, true><<<g, 256, 0, s>>>(b, md, 0);
+        launch_k(k_block_emit_md<KP, true, true, true>, g, 256, 0, s, b, md, (int)0);
       else
-        k_block_emit_md<KP, false, true, true><<<g, 256, 0, s>>>(b, md, 0);
+        launch_k(k_block_emit_md<KP, false, true, true>, g, 256, 0, s, b, md, (int)0);
     } else {
       if (l.gather)
-        k_block_emit_md<KP, true, true, false><<<g, 256, 0, s>>>(b, md, loglik);
+        launch_k(k_block_emit_md<KP, true, true, false>, g, 256, 0, s, b, md, (int)loglik);
       else
-        k_block_emit_md<KP, false, true, false><<<g, 256, 0, s>>>(b, md, loglik);
+        launch_k(k_block_emit_md<KP, false, true, false>, g, 256, 0, s, b, md, (int)loglik);
     }
     ++launches;
   } else {
@@ -2290,7 +2300,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
   }
   if (l.mixture) {
     stage("mix_sample");
-    k_mix_sample<KP><<<grid_for(ntiles * Layout::TB, 256, l.sms, 32), 256, 0, s>>>(b, m, l.seed, l.sweep);
+    launch_k(k_mix_sample<KP>, grid_for(ntiles * Layout::TB, 256, l.sms, 32), 256, 0, s, b, m, l.seed, l.sweep);
     ++launches;
     if (seg) {
       k_mix_segmap<KP><<<1, 32, 0, s>>>(b);
@@ -2306,8 +2316,8 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     } else if (b.wide_ops != nullptr) {
       // at most kWideCtasPerSm CTAs per SM: that many scratch areas exist (alloc_blocks)
       cudaFuncSetAttribute(k_fwd_chunks_wide<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WideCfg<KP>::kSmem);
-      k_fwd_chunks_wide<KP><<<grid_for(ntiles, 1, l.sms, kWideCtasPerSm), WideCfg<KP>::THREADS, WideCfg<KP>::kSmem, s>>>(
-          b, m, b.wide_ops, b.wide_exp);
+      launch_k(k_fwd_chunks_wide<KP>, grid_for(ntiles, 1, l.sms, kWideCtasPerSm), WideCfg<KP>::THREADS, WideCfg<KP>::kSmem,
+               s, b, m, b.wide_ops, b.wide_exp);
     } else {
       k_fwd_chunks<KP><<<grid_for(ntiles, 1, l.sms, 16), FwdCfg<KP>::THREADS, 0, s>>>(b, m);
     }
@@ -2340,11 +2350,11 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       }
     } else {
       if (loglik) {
-        k_fwd_replay<KP, true><<<gr, 32, 0, s>>>(b, m);
+        launch_k(k_fwd_replay<KP, true>, gr, 32, 0, s, b, m);
         launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else {
-        k_fwd_replay<KP, false><<<gr, 32, 0, s>>>(b, m);
+        launch_k(k_fwd_replay<KP, false>, gr, 32, 0, s, b, m);
       }
     }
     ++launches;
