@@ -51,7 +51,7 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            # include/hammlet_host.h
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
-           "hammlet_chain_save_marginals"]
+           "hammlet_chain_save_marginals", "hammlet_chains_run"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -378,6 +378,19 @@ class Chain:
             self.close()
         except Exception:
             pass
+
+
+def run_chains(chains, iterations, threads=4, method="F", dynamic=True, use_self=True):
+    """hammlet_chains_run: independent chains (one per sequence), `threads` at a time on C++ host threads."""
+    if not chains:
+        return
+    lib = chains[0].lib
+    arr = (C.c_void_p * len(chains))(*[c.c for c in chains])
+    rc = lib.hammlet_chains_run(arr, C.c_int(len(chains)), C.c_int(threads), C.c_char(method.encode()),
+                                C.c_uint64(iterations), C.c_int(int(dynamic)), C.c_int(int(use_self)))
+    if rc != 0:
+        msgs = [c.lib.hammlet_chain_error(c.c).decode() for c in chains]
+        raise HmlError(rc, "; ".join(m for m in msgs if m) or "a chain failed")
 
 
 def philox_uniform(seed, sweep, stream, index):

@@ -1,7 +1,9 @@
 // hammlet_b200 host side — C entry points around the C++ model surface (include/hammlet_host.h).
 #include "../../include/hammlet_host.h"
 
+#include <atomic>
 #include <memory>
+#include <thread>
 
 #include "StateSequence.hpp"
 
@@ -162,6 +164,41 @@ int hammlet_chain_run_recorded(hammlet_chain* c, char method, uint64_t iteration
     c->error = e.what();
     return HML_ERR_STATE;
   }
+}
+
+// Independent sequences: every chain owns its handle, its CUDA stream, its parameters and its RNG,
+// so chains never interact; `threads` host threads each take the next unfinished chain (longest sequence first).
+// A single chain of 1e4-1e5 blocks is a string of latency-bound kernels; several at a time fill the device.
+int hammlet_chains_run(hammlet_chain** chains, int n, int threads, char method, uint64_t iterations, int dynamic,
+                       int use_self_transitions) {
+  if (!chains || n < 0) return HML_ERR_ARG;
+  for (int i = 0; i < n; ++i)
+    if (!chains[i]) return HML_ERR_ARG;
+  if (n == 0) return HML_OK;
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return chains[a]->sequence.size() > chains[b]->sequence.size(); });
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  std::atomic<int> next(0), failed(0);
+  auto work = [&]() {
+    for (;;) {
+      const int k = next.fetch_add(1);
+      if (k >= n) return;
+      hammlet_chain* c = chains[order[k]];
+      try {
+        chain_run(c, method, iterations, 0, dynamic, use_self_transitions, nullptr);
+      } catch (std::exception& e) {
+        c->error = e.what();
+        failed.fetch_add(1);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (std::thread& t : pool) t.join();
+  return failed.load() ? HML_ERR_STATE : HML_OK;
 }
 
 int hammlet_chain_save_marginals(hammlet_chain* c, const char* path) {

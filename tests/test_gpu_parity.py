@@ -466,3 +466,37 @@ def test_cpp_chain_records_marginals_from_device_runs(dev, tmp_path):
     assert set(np.cumsum(sizes)[:-1].tolist()) <= set(np.cumsum([r[0] for r in rows])[:-1].tolist())
     chain.close()
     h.close()
+
+
+def test_concurrent_chains_equal_sequential_chains():
+    """hammlet_chains_run: independent sequences swept several at a time (own handle, stream, RNG each) must end in
+    exactly the state that the same chains reach one after the other."""
+    from hammlet_b200.synth import piecewise_gaussian
+    K = 3
+    seqs = [piecewise_gaussian(T, K, 400, seed=40 + i) for i, T in enumerate((250_000, 90_000, 400_000, 4096, 130_001))]
+
+    def build():
+        hs, cs = [], []
+        for i, x in enumerate(seqs):
+            h = capi.Handle(0)
+            h.load(x)
+            tau = capi.Chain.auto_prior(h, 0.2, 0.9)
+            hs.append(h)
+            cs.append(capi.Chain(h, K, tau, seed=70 + i))
+        return hs, cs
+
+    h1, c1 = build()
+    h2, c2 = build()
+    for c in c1:
+        c.run(15, method="M")
+        c.run(25, method="F")
+    capi.run_chains(c2, 15, threads=3, method="M")
+    capi.run_chains(c2, 25, threads=5, method="F")
+    for a, b in zip(c1, c2):
+        assert all(np.array_equal(u, v) for u, v in zip(a.get(), b.get()))
+    for a, b in zip(h1, h2):
+        assert np.array_equal(a.states(), b.states())
+    for c in c1 + c2:
+        c.close()
+    for h in h1 + h2:
+        h.close()

@@ -6,15 +6,14 @@ bin packing (no collective; every sequence is its own chain wi
   python tools/c3_chromosomes.py [--scale 1.0] [--sweeps 200] [--streams 4] [--out gpurun_out/c3.json]
   python -m torch.distributed.run --nproc-per-node N ... tools/c3_chromosomes.py    (one rank per GPU)
 
-Two timings per GPU: the sequences swept one after the other, and `--streams` chains at a time from host threads
-(every handle owns a CUDA stream, hammlet_chain_run releases the GIL), which lets the latency-bound kernels of one
-chain (tile scans, map scans: one CTA or one cluster) overlap the wide kernels of another.
+Two timings per GPU: the sequences swept one after the other, and `--streams` chains at a time (hammlet_chains_run:
+C++ host threads, every handle owns a CUDA stream), which lets the latency-bound kernels of one chain (tile scans,
+map scans: one CTA or one cluster) overlap the wide kernels of another.
 """
 import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -77,26 +76,10 @@ def main():
     torch.cuda.synchronize()
     t_seq = time.perf_counter() - w0
 
-    # ---- `streams` chains at a time (longest first, each thread takes the next free sequence)
-    order = sorted(range(len(chains)), key=lambda j: -lengths[mine[j]])
-    lock, cursor = threading.Lock(), [0]
-
-    def worker():
-        while True:
-            with lock:
-                if cursor[0] >= len(order):
-                    return
-                j = order[cursor[0]]
-                cursor[0] += 1
-            chains[j].run(args.sweeps)
-
+    # ---- `streams` chains at a time: hammlet_chains_run (C++ host threads, longest sequence first)
     barrier()
     w0 = time.perf_counter()
-    threads = [threading.Thread(target=worker) for _ in range(max(1, args.streams))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    capi.run_chains(chains, args.sweeps, threads=max(1, args.streams))
     torch.cuda.synchronize()
     t_par = time.perf_counter() - w0
 
