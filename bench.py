@@ -293,11 +293,11 @@ def main():
     wall = time.perf_counter() - w0
 
     # ---- the second number SURVEY.md §8d asks for: thinning 1 — every sweep is recorded into the state marginals
-    # (Records / StateMarginals on the host, fed with one entry per equal-state run formed on the device).  Single
-    # handle only: a segment-split sequence keeps its runs rank-local.
+    # (Records -> device-resident marginals).  Single handle only: a segment-split sequence keeps its runs rank-local.
     recorded = None
     if not segments:
         rec_steps = max(10, steps // 5)
+        chain.run_recorded(max(3, warmup // 4), thinning=1)   # warm-up: first use allocates the run / marginal buffers
         barrier()
         r0 = time.perf_counter()
         _, nseg = chain.run_recorded(rec_steps, thinning=1)
@@ -306,8 +306,9 @@ def main():
         runs = int(h.segments()[0].size)
         recorded = {"value": rec_steps / rec_wall * (world if world > 1 else 1), "unit": UNIT, "thinning": 1,
                     "steps": rec_steps, "runs_last_sweep": runs, "marginal_segments": int(nseg),
-                    "how": "wall clock through hammlet_chain_run_recorded: sweep + hml_get_segments (device run-length "
-                           "compaction, D2H of one entry per run) + StateMarginals::addRecord on the host"}
+                    "how": "wall clock through hammlet_chain_run_recorded: sweep + equal-state runs formed on the device + "
+                           "merge into the device-resident state marginals (hml_marginals_add: StateMarginals::addRecord "
+                           "as three small kernels; nothing but a 4-byte count returns to the host per sweep)"}
 
     # ---- region 3 (not part of `value`): the same steps with per-stage CUDA events, for the roofline and stage table
     h.set_timing(True)

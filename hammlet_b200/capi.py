@@ -42,7 +42,8 @@ class _SweepOut(C.Structure):
 
 
 EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_load_f32", "hml_load_f32_device",
-           "hml_load_f32_md", "hml_load_f32_device_md", "hml_nr_dims", "hml_get_block_sums", "hml_size", "hml_sigma_hat", "hml_get_weights", "hml_get_coeffs", "hml_create_blocks", "hml_nr_blocks",
+           "hml_load_f32_md", "hml_load_f32_device_md", "hml_nr_dims", "hml_get_block_sums", "hml_marginals_reset",
+           "hml_marginals_add", "hml_marginals_info", "hml_marginals_get", "hml_size", "hml_sigma_hat", "hml_get_weights", "hml_get_coeffs", "hml_create_blocks", "hml_nr_blocks",
            "hml_get_blocks", "hml_fb_sweep", "hml_mix_sweep", "hml_get_states", "hml_get_segments", "hml_get_rows",
            "hml_set_timing", "hml_get_timing", "hml_launch_count", "hml_sync", "hml_get_stream",
            "hml_comm_unique_id", "hml_comm_init", "hml_segment_plan", "hml_load_segment_f32",
@@ -283,6 +284,23 @@ class Handle:
         sizes, st = np.empty(n.value, dtype=np.uint64), np.empty(n.value, dtype=np.int16)
         self._ck(self.lib.hml_get_segments(self.h, C.byref(n), _ptr(sizes), _ptr(st), C.c_uint64(sizes.size)))
         return sizes, st
+
+    # ---- state marginals accumulated on the device
+    def marginals_reset(self, K):
+        self._ck(self.lib.hml_marginals_reset(self.h, C.c_int(K)))
+
+    def marginals_add(self):
+        """The last sweep's state sequence joins the marginals (StateMarginals::addRecord for every run)."""
+        self._ck(self.lib.hml_marginals_add(self.h))
+
+    def marginals(self):
+        """-> (sizes[n], counts[n, K], iterations): the common refinement of all added segmentations."""
+        n, it, K = C.c_uint64(), C.c_uint64(), C.c_int()
+        self._ck(self.lib.hml_marginals_info(self.h, C.byref(n), C.byref(it), C.byref(K)))
+        sizes = np.empty(n.value, dtype=np.uint64)
+        counts = np.empty((n.value, K.value), dtype=np.int32)
+        self._ck(self.lib.hml_marginals_get(self.h, _ptr(sizes), _ptr(counts), C.c_uint64(n.value)))
+        return sizes, counts, it.value
 
     def rows(self, K):
         B = self.nr_blocks()

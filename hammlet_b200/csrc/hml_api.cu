@@ -123,7 +123,15 @@ struct hml_ctx {
   int16_t* seg_states = nullptr;
   uint64_t seg_cap = 0;            // blocks the three arrays are sized for
   bool segs_valid = false;         // seg_counts holds the offsets of the current states
+  bool runs_written = false;       // seg_starts / seg_states hold the runs of the current states
   uint64_t nsegs = 0;
+  // state marginals accumulated on the device (hml_marginals_*): sorted segment starts + K counts per segment
+  uint32_t* mg_pos[2] = {nullptr, nullptr};
+  uint16_t* mg_cnt[2] = {nullptr, nullptr};
+  uint32_t *mg_run_of_old = nullptr, *mg_olds_below = nullptr, *mg_flags = nullptr;
+  uint64_t mg_cap = 0, mg_runs_cap = 0;  // segments the double buffers hold; runs the scratch holds
+  int mg_cur = 0, mg_K = 0;
+  uint64_t mg_n = 0, mg_iterations = 0;
   double* partials = nullptr;
   unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
   unsigned long long* outblk_host = nullptr;  // pinned mirror
@@ -387,6 +395,8 @@ void load_reset(hml_t* h) {
   h->seg_start = 0;
   h->D = 1;
   h->pq_stride = h->cell_stride = 0;
+  h->mg_K = 0;  // marginals belong to the sequence that was loaded
+  h->mg_n = h->mg_iterations = 0;
   h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
 }
 
@@ -1099,6 +1109,13 @@ int hml_destroy(hml_t* h) {
   dev_free(h->seg_counts);
   dev_free(h->seg_starts);
   dev_free(h->seg_states);
+  for (int k = 0; k < 2; ++k) {
+    dev_free(h->mg_pos[k]);
+    dev_free(h->mg_cnt[k]);
+  }
+  dev_free(h->mg_run_of_old);
+  dev_free(h->mg_olds_below);
+  dev_free(h->mg_flags);
   dev_free(h->wide_ops);
   dev_free(h->wide_exp);
   dev_free(h->chunk_exp);
@@ -1361,17 +1378,10 @@ int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity) {
   return HML_OK;
 }
 
-int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t* seg_state, uint64_t capacity) {
-  if (!h || !nsegments) return HML_ERR_ARG;
-  if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
-  CK(cudaSetDevice(h->device));
+// Equal-state runs of the last sweep, formed on the device (Records.hpp:166-188: a segment ends where the state
+// changes): h->nsegs runs; with `write` their (start, state) pairs are left in h->seg_starts / h->seg_states.
+static int ensure_runs(hml_t* h, bool write) {
   const uint64_t B = h->nblocks;
-  if (B == 0) {
-    *nsegments = 0;
-    return HML_OK;
-  }
-  // Records.hpp:166-188: a segment ends where the state changes.  The runs are formed on the device; only one
-  // (start, state) pair per run travels to the host.
   const uint64_t ntiles = (B + 1023) / 1024;
   if (h->seg_cap < h->capacity || !h->seg_counts) {
     CK(dev_alloc(h->seg_counts, h->capacity / 1024 + 2));
@@ -1390,20 +1400,153 @@ int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t*
     CK(cudaStreamSynchronize(h->stream));
     h->nsegs = n32;
     h->segs_valid = true;
+    h->runs_written = false;
   }
+  if (write && !h->runs_written) {
+    launch_segments_write(b, B, h->seg_counts, h->seg_starts, h->seg_states, h->sms, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->runs_written = true;
+  }
+  return HML_OK;
+}
+
+int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t* seg_state, uint64_t capacity) {
+  if (!h || !nsegments) return HML_ERR_ARG;
+  if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
+  CK(cudaSetDevice(h->device));
+  if (h->nblocks == 0) {
+    *nsegments = 0;
+    return HML_OK;
+  }
+  const bool want = seg_size && seg_state;
+  int rc = ensure_runs(h, want);
+  if (rc != HML_OK) return rc;
   const uint64_t n = h->nsegs;
   *nsegments = n;
-  if (!seg_size || !seg_state) return HML_OK;
+  if (!want) return HML_OK;
   if (n > capacity) return fail(h, HML_ERR_CAPACITY, "segment buffer too small");
-  launch_segments_write(b, B, h->seg_counts, h->seg_starts, h->seg_states, h->sms, h->stream);
-  h->launches++;
-  CK(cudaGetLastError());
   std::vector<uint32_t> st(n);
   CK(cudaMemcpyAsync(st.data(), h->seg_starts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(seg_state, h->seg_states, n * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   const uint64_t end = h->T;  // local positions; sizes do not depend on the segment offset of a split sequence
   for (uint64_t i = 0; i < n; ++i) seg_size[i] = (uint64_t)(i + 1 < n ? st[i + 1] : end) - st[i];
+  return HML_OK;
+}
+
+// ---- state marginals accumulated on the device
+
+static int mg_reserve(hml_t* h, uint64_t segments, uint64_t runs) {
+  if (segments > h->mg_cap) {
+    const uint64_t cap = segments + segments / 2 + 1024;
+    for (int k = 0; k < 2; ++k) {
+      uint32_t* np = nullptr;
+      uint16_t* nc = nullptr;
+      CK(cudaMalloc((void**)&np, cap * sizeof(uint32_t)));
+      CK(cudaMalloc((void**)&nc, cap * (size_t)h->mg_K * sizeof(uint16_t)));
+      if (k == h->mg_cur && h->mg_n) {  // keep what has been accumulated
+        CK(cudaMemcpyAsync(np, h->mg_pos[k], h->mg_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(nc, h->mg_cnt[k], h->mg_n * (size_t)h->mg_K * sizeof(uint16_t), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+      }
+      dev_free(h->mg_pos[k]);
+      dev_free(h->mg_cnt[k]);
+      h->mg_pos[k] = np;
+      h->mg_cnt[k] = nc;
+    }
+    h->mg_cap = cap;
+    CK(dev_alloc(h->mg_run_of_old, cap));
+  }
+  if (runs > h->mg_runs_cap) {
+    const uint64_t cap = runs + runs / 2 + 1024;
+    CK(dev_alloc(h->mg_olds_below, cap));
+    CK(dev_alloc(h->mg_flags, cap + 1));
+    h->mg_runs_cap = cap;
+  }
+  return HML_OK;
+}
+
+int hml_marginals_reset(hml_t* h, int K) {
+  if (!h) return HML_ERR_ARG;
+  if (K < 1 || K > HML_MAX_STATES) return fail(h, HML_ERR_ARG, "number of states must be in [1, 32]");
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  CK(cudaSetDevice(h->device));
+  for (int k = 0; k < 2; ++k) {
+    dev_free(h->mg_pos[k]);
+    dev_free(h->mg_cnt[k]);
+  }
+  h->mg_cap = 0;
+  h->mg_K = K;
+  h->mg_cur = 0;
+  h->mg_n = 0;
+  h->mg_iterations = 0;
+  // room for one segment per 512 positions up front (the refinement has about as many segments as a sweep has
+  // equal-state runs; growing later means freeing and allocating while tens of GB are resident: ~100 ms)
+  uint64_t guess = h->T / 512;
+  if (guess > h->capacity) guess = h->capacity;
+  if (guess < (1u << 16)) guess = 1u << 16;
+  int rc = mg_reserve(h, guess, guess / 2);
+  if (rc != HML_OK) return rc;
+  // one segment covering the whole sequence, all counts zero (StateMarginals.hpp:24-33)
+  CK(cudaMemsetAsync(h->mg_pos[0], 0, sizeof(uint32_t), h->stream));
+  CK(cudaMemsetAsync(h->mg_cnt[0], 0, (size_t)K * sizeof(uint16_t), h->stream));
+  h->mg_n = 1;
+  return HML_OK;
+}
+
+int hml_marginals_add(hml_t* h) {
+  if (!h) return HML_ERR_ARG;
+  if (h->mg_K == 0) return fail(h, HML_ERR_STATE, "hml_marginals_reset has not been called");
+  if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
+  if (h->last_K > h->mg_K) return fail(h, HML_ERR_ARG, "the last sweep had more states than the marginals hold");
+  if (h->mg_iterations >= 32767) return fail(h, HML_ERR_CAPACITY, "marginal counts are 16-bit (marginal_t): 32767 iterations");
+  if (h->nblocks == 0) return HML_OK;
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_runs(h, true);
+  if (rc != HML_OK) return rc;
+  const uint64_t m = h->nsegs, n = h->mg_n;
+  rc = mg_reserve(h, n + m, m);
+  if (rc != HML_OK) return rc;
+  const int cur = h->mg_cur, nxt = cur ^ 1;
+  launch_marginals_merge(h->mg_pos[cur], (uint32_t)n, h->mg_cnt[cur], h->seg_starts, h->seg_states, (uint32_t)m,
+                         h->mg_run_of_old, h->mg_olds_below, h->mg_flags, h->mg_K, h->mg_pos[nxt], h->mg_cnt[nxt], h->sms,
+                         h->stream);
+  h->launches += 3;
+  CK(cudaGetLastError());
+  uint32_t added = 0;
+  CK(cudaMemcpyAsync(&added, h->mg_flags + m, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->mg_n = n + added;
+  h->mg_cur = nxt;
+  h->mg_iterations++;
+  return HML_OK;
+}
+
+int hml_marginals_info(const hml_t* h, uint64_t* nsegments, uint64_t* iterations, int* K) {
+  if (!h) return HML_ERR_ARG;
+  if (nsegments) *nsegments = h->mg_n;
+  if (iterations) *iterations = h->mg_iterations;
+  if (K) *K = h->mg_K;
+  return HML_OK;
+}
+
+int hml_marginals_get(hml_t* h, uint64_t* seg_size, int32_t* counts, uint64_t capacity) {
+  if (!h || !seg_size || !counts) return HML_ERR_ARG;
+  if (h->mg_K == 0) return fail(h, HML_ERR_STATE, "hml_marginals_reset has not been called");
+  if (capacity < h->mg_n) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of marginal segments");
+  CK(cudaSetDevice(h->device));
+  const uint64_t n = h->mg_n;
+  const int K = h->mg_K;
+  std::vector<uint32_t> pos(n);
+  std::vector<uint16_t> cnt(n * (size_t)K);
+  CK(cudaMemcpyAsync(pos.data(), h->mg_pos[h->mg_cur], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(cnt.data(), h->mg_cnt[h->mg_cur], n * (size_t)K * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (uint64_t i = 0; i < n; ++i) {
+    seg_size[i] = (uint64_t)(i + 1 < n ? pos[i + 1] : h->T) - pos[i];
+    for (int s = 0; s < K; ++s) counts[i * K + s] = cnt[i * (size_t)K + s];
+  }
   return HML_OK;
 }
 

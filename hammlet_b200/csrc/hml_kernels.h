@@ -175,6 +175,11 @@ void launch_unpermute(const SweepBuffers& b, int KP, uint64_t nblocks, int16_t* 
 void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, uint32_t* tile_counts, int sms, cudaStream_t s);
 void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const uint32_t* tile_offsets, uint32_t* seg_start,
                            int16_t* seg_state, int sms, cudaStream_t s);
+// State marginals on the device: merges the run starts R[m] / run states of one recorded iteration into the
+// refinement (P[n], cnt[n x K]) -> (P2, cnt2) with new_flags[m] = number of new boundaries (3 launches).
+void launch_marginals_merge(const uint32_t* P, uint32_t n, const uint16_t* cnt, const uint32_t* R, const int16_t* rstate,
+                            uint32_t m, uint32_t* run_of_old, uint32_t* olds_below, uint32_t* new_flags, int K,
+                            uint32_t* P2, uint16_t* cnt2, int sms, cudaStream_t s);
 // Only block sums (no model): gather statistics for the current starts.
 void launch_block_stats(const SweepBuffers& b, int KP, uint64_t nblocks_hint, int sms, cudaStream_t s);
 

@@ -134,6 +134,86 @@ __global__ void __launch_bounds__(1024) k_seg_write(const uint8_t* __restrict__ 
   }
 }
 
+// ---- state marginals on the device (StateMarginals.hpp:51-137): the common refinement of all recorded
+// segmentations as a sorted array of segment starts P[n] with one count per state and segment.  Adding an iteration
+// with run starts R[m] (sorted, R[0] = 0) and run states:
+//   k_mg_rank   every old start finds its run (upper bound in R), every run start its place among the old starts
+//               (lower bound in P) and whether it is a new boundary
+//   k_seg_scan  exclusive scan of the "new" flags
+//   k_mg_write  old start i goes to i + #new run starts below it, a new run start j to (#old starts below it) + #new
+//               run starts before it; counts = counts of the old segment that contains the position + 1 for the state
+//               of the run that contains it
+__device__ __forceinline__ uint32_t mg_lower_bound(const uint32_t* a, uint32_t n, uint32_t v) {  // first a[k] >= v
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ uint32_t mg_upper_bound(const uint32_t* a, uint32_t n, uint32_t v) {  // first a[k] > v
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_mg_rank(const uint32_t* __restrict__ P, uint32_t n, const uint32_t* __restrict__ R,
+                                                 uint32_t m, uint32_t* __restrict__ run_of_old,
+                                                 uint32_t* __restrict__ olds_below, uint32_t* __restrict__ is_new) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n + m; k += gridDim.x * blockDim.x) {
+    if (k < n) {
+      run_of_old[k] = mg_upper_bound(R, m, P[k]) - 1;
+    } else {
+      const uint32_t j = k - n, v = R[j];
+      const uint32_t lb = mg_lower_bound(P, n, v);
+      olds_below[j] = lb;
+      is_new[j] = (lb == n || P[lb] != v) ? 1u : 0u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_mg_write(const uint32_t* __restrict__ P, uint32_t n, const uint16_t* __restrict__ cnt,
+                                                  const uint32_t* __restrict__ R, const int16_t* __restrict__ rstate, uint32_t m,
+                                                  const uint32_t* __restrict__ run_of_old, const uint32_t* __restrict__ olds_below,
+                                                  const uint32_t* __restrict__ new_before, int K, uint32_t* __restrict__ P2,
+                                                  uint16_t* __restrict__ cnt2) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n + m; k += gridDim.x * blockDim.x) {
+    uint32_t out, parent, pos;
+    int state;
+    if (k < n) {
+      const uint32_t run = run_of_old[k];
+      out = k + new_before[run + 1];
+      parent = k;
+      pos = P[k];
+      state = rstate[run];
+    } else {
+      const uint32_t j = k - n;
+      if (new_before[j + 1] == new_before[j]) continue;  // an old boundary: written by its old start
+      out = olds_below[j] + new_before[j];
+      parent = olds_below[j] - 1;                        // P[0] = 0 <= every position
+      pos = R[j];
+      state = rstate[j];
+    }
+    P2[out] = pos;
+    for (int s = 0; s < K; ++s) cnt2[(size_t)out * K + s] = (uint16_t)(cnt[(size_t)parent * K + s] + (s == state ? 1 : 0));
+  }
+}
+
+void launch_marginals_merge(const uint32_t* P, uint32_t n, const uint16_t* cnt, const uint32_t* R, const int16_t* rstate,
+                            uint32_t m, uint32_t* run_of_old, uint32_t* olds_below, uint32_t* new_flags, int K,
+                            uint32_t* P2, uint16_t* cnt2, int sms, cudaStream_t s) {
+  const uint32_t total = n + m;
+  int g = (int)((total + 255) / 256);
+  if (g > sms * 8) g = sms * 8;
+  if (g < 1) g = 1;
+  k_mg_rank<<<g, 256, 0, s>>>(P, n, R, m, run_of_old, olds_below, new_flags);
+  k_seg_scan<<<1, 1024, 0, s>>>(new_flags, m);  // exclusive, new_flags[m] = number of new boundaries
+  k_mg_write<<<g, 256, 0, s>>>(P, n, cnt, R, rstate, m, run_of_old, olds_below, new_flags, K, P2, cnt2);
+}
+
 void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, uint32_t* tile_counts, int sms, cudaStream_t s) {
   const uint64_t ntiles = (nblocks + 1023) / 1024;
   const int g = (int)(ntiles < (uint64_t)sms * 2 ? ntiles : (uint64_t)sms * 2);

@@ -87,6 +87,7 @@ class StateMarginals {
   }
 
   size_t nrSegments() const { return mNrSegments; }
+  size_t nrIterations() const { return mNrIterations; }
   size_t internalSize() const {
     size_t n = 0;
     for (size_t i = mFront; i < mCur.size.size(); ++i) n += codeLength(&mCur.count[i * mStride]);
@@ -115,7 +116,19 @@ class StateMarginals {
   }
 };
 
+// Marginals that are kept elsewhere — on the device (DeviceMarginals in StateSequence.hpp, over hml_marginals_*).
+// Records only says when the iteration just sampled is to be added and asks for the file at the end, so this
+// header needs nothing from the C ABI (records_tool links without the CUDA library).
+struct MarginalsSink {
+  virtual ~MarginalsSink() {}
+  virtual void addIteration() = 0;
+  virtual void save(std::ofstream& ofs) = 0;
+  virtual size_t nrSegments() = 0;
+};
+
 class Records {
+  MarginalsSink* mSink = nullptr;
+  bool mSinkUsed = false;
   size_t mNrObservedPos = 0, mNrBlocks = 0, mNrSegments = 0;
   size_t mSegmentState = 0, mSegmentSize = 0;
   const size_t mSize;
@@ -151,7 +164,7 @@ class Records {
     if (mClosed) return;
     mClosed = true;
     if (mRecordMarginals) {
-      mMarginals.save(mMarginalsFile);
+      if (mMarginalsFile.is_open()) saveMarginals(mMarginalsFile);
       mMarginalsFile.close();
     }
     if (mRecordSequences) mSequenceFile.close();
@@ -168,6 +181,27 @@ class Records {
   void setRecordSegments(bool b, bool overwrite = false) { setRecordX(mSegmentFile, "segments", mRecordSegments, b, overwrite); }
   bool wantsBlocks() const { return mRecordBlocks; }
 
+  // ---- marginals accumulated on the device
+  void setMarginalsSink(MarginalsSink* sink) { mSink = sink; }
+  // a recorded iteration needs nothing on the host but the marginals (and the block count for the compression file)
+  bool canRecordOnDevice() const {
+    return mSink && mRecordMarginals && !mRecordBlocks && !mRecordSequences && !mRecordSegments && mNrObservedPos == 0 &&
+           mMarginals.nrIterations() == 0;
+  }
+  // the iteration just sampled joins the device-side marginals (StateMarginals::addRecord for all its runs at once)
+  void recordIterationOnDevice(const size_t nrBlocks) {
+    mSink->addIteration();
+    mSinkUsed = true;
+    if (mRecordCompression) mCompressionsFile << ((double)mSize) / ((double)nrBlocks) << std::endl;
+  }
+  size_t nrMarginalSegments() const { return mSinkUsed ? mSink->nrSegments() : mMarginals.nrSegments(); }
+  void saveMarginals(std::ofstream& ofs) const {
+    if (mSinkUsed)
+      mSink->save(ofs);
+    else
+      mMarginals.save(ofs);
+  }
+
   template <typename ThetaType>
   void record(const Theta<ThetaType>& theta) {
     if (mRecordTheta) mThetaFile << theta << std::endl;
@@ -182,6 +216,7 @@ class Records {
   // to the iteration's block count (only the total enters the compression file).
   void recordRun(const size_t state, const size_t N, const size_t nrBlocks) {
     if (mRecordBlocks) throw std::runtime_error("Block sizes are being recorded: blocks must be recorded one by one!");
+    if (mSinkUsed) throw std::runtime_error("The marginals of this run accumulate on the device!");
     const bool first = mNrObservedPos == 0;
     if (first) {
       mSegmentState = state;
@@ -207,6 +242,7 @@ class Records {
   const StateMarginals& marginals() const { return mMarginals; }
 
   void record(const size_t state, const size_t N) {
+    if (mSinkUsed) throw std::runtime_error("The marginals of this run accumulate on the device!");
     const bool firstBlock = mNrBlocks == 0;
     if (firstBlock) {
       mSegmentState = state;

@@ -39,6 +39,55 @@ class Trellis {
   }
 };
 
+// StateMarginals on the device (include/hammlet_b200.h: hml_marginals_*): recorded iterations never leave the GPU;
+// the marginals file is written from one device-to-host copy at the end, in the format of StateMarginals::save
+// (StateMarginals.hpp:268-310: `size TAB c_0 ... TAB c_{S-1}` with S = highest recorded label + 1).
+class DeviceMarginals : public MarginalsSink {
+  DeviceSequence& mSeq;
+
+ public:
+  DeviceMarginals(DeviceSequence& seq, size_t nrStates) : mSeq(seq) {
+    mSeq.check(hml_marginals_reset(mSeq.handle(), (int)nrStates));
+  }
+  void addIteration() override { mSeq.check(hml_marginals_add(mSeq.handle())); }
+  size_t nrSegments() override {
+    uint64_t n = 0;
+    mSeq.check(hml_marginals_info(mSeq.handle(), &n, nullptr, nullptr));
+    return n;
+  }
+  void save(std::ofstream& ofs) override {
+    uint64_t n = 0, iterations = 0;
+    int K = 0;
+    mSeq.check(hml_marginals_info(mSeq.handle(), &n, &iterations, &K));
+    std::vector<uint64_t> size(n);
+    std::vector<int32_t> counts(n * (size_t)K);
+    mSeq.check(hml_marginals_get(mSeq.handle(), size.data(), counts.data(), n));
+    size_t nrLabels = 0;  // highest recorded label + 1
+    for (uint64_t i = 0; i < n; ++i)
+      for (int s = K; s > (int)nrLabels; --s)
+        if (counts[i * K + s - 1] != 0) {
+          nrLabels = s;
+          break;
+        }
+    std::string line;
+    for (uint64_t i = 0; i < n; ++i) {
+      uint64_t sum = 0;
+      line = std::to_string(size[i]);
+      for (size_t s = 0; s < nrLabels; ++s) {
+        line += '\t';
+        line += std::to_string(counts[i * K + s]);
+        sum += counts[i * K + s];
+      }
+      line += '\n';
+      ofs << line;
+      if (sum != iterations)
+        throw std::runtime_error("Sum of marginals (" + std::to_string(sum) + ") does not match the number of iterations (" +
+                                 std::to_string(iterations) + ")!");
+    }
+    ofs.flush();
+  }
+};
+
 template <typename Type>
 class StateSequence {
   std::vector<marginal_t> mStates;
@@ -198,6 +247,10 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
   // ---- records (ForwardBackward.hpp:193-195).  Unless the per-block sizes are written out (-O B), the device
   // merges equal-state neighbours into runs (Records.hpp:166-188 does the same block by block) and one entry per
   // run travels to the host: ~T / mean segment length entries instead of one per block.
+  if (doRecord && !mKeepTrellis && records.canRecordOnDevice()) {
+    records.recordIterationOnDevice(out.nblocks);  // marginals only: the iteration never leaves the device
+    return;
+  }
   if (doRecord && !records.wantsBlocks() && !mKeepTrellis) {
     uint64_t nruns = 0;
     seq.check(hml_get_segments(seq.handle(), &nruns, nullptr, nullptr, 0));

@@ -28,6 +28,7 @@ struct hammlet_chain {
   ThetaHyperParam<NormalInverseGammaParam> tau_theta;
   Theta<NormalInverseGamma> theta;
   Records records;
+  DeviceMarginals deviceMarginals;
   std::string error;
   size_t K;
 
@@ -46,7 +47,9 @@ struct hammlet_chain {
         tau_theta(priors),
         theta(tau_theta, 1, combinations, rng),
         records(sequence.size(), "hammlet-", ".csv", nrStates),
+        deviceMarginals(sequence, nrStates),
         K(nrStates) {
+    records.setMarginalsSink(&deviceMarginals);
     // a leading "P" is implied (main.cpp:393-406)
     theta.sample(tau_theta);
     pi.sample(tau_pi);
@@ -158,7 +161,7 @@ int hammlet_chain_run_recorded(hammlet_chain* c, char method, uint64_t iteration
   if (!c) return HML_ERR_ARG;
   try {
     chain_run(c, method, iterations, thinning, dynamic, use_self_transitions, nblocks_last);
-    if (marginal_segments) *marginal_segments = c->records.marginals().nrSegments();
+    if (marginal_segments) *marginal_segments = c->records.nrMarginalSegments();
     return HML_OK;
   } catch (std::exception& e) {
     c->error = e.what();
@@ -206,7 +209,7 @@ int hammlet_chain_save_marginals(hammlet_chain* c, const char* path) {
   try {
     std::ofstream f(path);
     if (!f.is_open()) throw std::runtime_error(std::string("Cannot write to file ") + path + "!");
-    c->records.marginals().save(f);
+    c->records.saveMarginals(f);
     return HML_OK;
   } catch (std::exception& e) {
     c->error = e.what();

@@ -163,6 +163,10 @@ int main(int argc, const char* argv[]) {
     records.setRecordCompression(outputArgs.isSet("compression"), overwrite);
     records.setRecordMarginals(outputArgs.isSet("marginals"), overwrite);
     records.setRecordSegments(outputArgs.isSet("segments"), overwrite);
+    // with -O M alone (the default) the marginals accumulate on the device; any per-iteration host output
+    // (sequences, blocks, segments) keeps them in the host-side StateMarginals
+    DeviceMarginals deviceMarginals(sequence, nrStates);
+    records.setMarginalsSink(&deviceMarginals);
 
     typedef Statistics<IntegralArray, Normal> S;
     typedef Blocks<BreakpointArray> B;

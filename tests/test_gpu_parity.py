@@ -500,3 +500,41 @@ def test_concurrent_chains_equal_sequential_chains():
         c.close()
     for h in h1 + h2:
         h.close()
+
+
+def test_device_marginals_match_the_common_refinement(dev):
+    """hml_marginals_add over sweeps with changing block structures and models against oracle.Marginals (the
+    reference's observable semantics, pinned to its marginals files by tests/test_oracle_vs_golden.py)."""
+    T, K = 500_000, 4
+    x = piecewise_gaussian(T, K, 700, seed=55)
+    mu, var, A, pi = model_guess(K, seed=2)
+    dev.load(x)
+    dev.marginals_reset(K)
+    sizes, counts, it = dev.marginals()
+    assert it == 0 and sizes.tolist() == [T] and counts.tolist() == [[0] * K]
+    M = oracle.Marginals(T)
+    rng = np.random.default_rng(1)
+    for sweep, thr in enumerate((1.2, 0.5, 2.0, 0.9, 0.9, 3.5, 0.3)):
+        out = dev.fb_sweep(mu * (1 + 0.02 * sweep), var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=thr, seed=int(rng.integers(1 << 30)),
+                           sweep=sweep)
+        dev.marginals_add()
+        n = np.diff(np.append(dev.blocks(stats=False).astype(np.int64), T))
+        M.add(*oracle.merge_runs(dev.states(), n))
+        sizes, counts, it = dev.marginals()
+        rs, rc = M.lines()
+        assert it == sweep + 1 and sizes.sum() == T
+        assert np.array_equal(sizes.astype(np.int64), rs)
+        assert np.array_equal(counts[:, :rc.shape[1]], rc) and not counts[:, rc.shape[1]:].any()
+    # a mixture sweep joins the same structure
+    dev.mix_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=1.0, seed=5, sweep=0)
+    dev.marginals_add()
+    n = np.diff(np.append(dev.blocks(stats=False).astype(np.int64), T))
+    M.add(*oracle.merge_runs(dev.states(), n))
+    sizes, counts, it = dev.marginals()
+    rs, rc = M.lines()
+    assert np.array_equal(sizes.astype(np.int64), rs) and np.array_equal(counts[:, :rc.shape[1]], rc)
+    assert np.all(counts.sum(1) == it)
+    # loading new data starts over
+    dev.load(x[:5000])
+    with pytest.raises(capi.HmlError):
+        dev.marginals_add()

@@ -116,6 +116,24 @@ def read_marginals(path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("outputs", [["M"], ["M", "C", "P"]], ids=lambda o: "".join(o))
+@pytest.mark.parametrize("seed,scheme", [(5, "F 60 1"), (11, "M 20 0 S P F 30 2 D F 30 1"), (3, "M 30 1")])
+def test_replay_run_with_marginals_on_the_device(tmp_path, seed, scheme, outputs):
+    """With no per-iteration host output requested (-O M, the default, optionally with compression / parameters) the
+    recorded iterations are merged into the state marginals on the device (hml_marginals_add) and the marginals file is
+    written from one copy at the end: it must equal the reference's file byte for byte."""
+    ours, ref = need(os.path.join(BIN, "hammlet64")), need(os.path.join(REF, "hammlet64"))
+    write_input(tmp_path / "in.txt", 60000, 3, 300, seed)
+    common = ["-f", "in.txt", "-a", "-R", str(seed), "-s", "3", "-i"] + scheme.split() + ["-O"] + outputs + ["-w"]
+    r = run([ref] + common + ["-o", "ref-", ".csv"], cwd=tmp_path)
+    p = run([ours, "-replay"] + common + ["-o", "our-", ".csv"], cwd=tmp_path)
+    assert r.returncode == 0 and p.returncode == 0, p.stderr + r.stderr
+    kinds = {"M": "marginals", "C": "compression", "P": "parameters"}
+    for o in outputs:
+        assert (tmp_path / f"our-{kinds[o]}.csv").read_text() == (tmp_path / f"ref-{kinds[o]}.csv").read_text(), kinds[o]
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("seed,scheme", [(5, "F 60 1"), (11, "M 20 0 S P F 30 2 D F 30 1")])
 def test_replay_run_without_block_output_uses_device_runs(tmp_path, seed, scheme):
     """Without -O B the recorded iterations reach Records as equal-state runs formed on the device
