@@ -322,17 +322,25 @@ def main():
 
     # ---- the streaming formulation of boundary detection (4 B/observation), timed on the same data
     # (collective in segment mode, so every rank runs it)
-    _, hot = h.detect_info()             # sub-blocks of 32 weights the last pyramid pass had to read (this rank)
-    h.set_detect_mode(capi.DETECT_STREAM)
+    _, cands = h.detect_info()           # candidates the last candidate pass looked at (this rank)
     h.set_timing(True)
     _, var_now, _, _ = chain.get()
     thr_now = float(np.sqrt(np.float32(2) * np.log(np.float32(T)) * var_now.min(), dtype=np.float32))
+    h.set_detect_mode(capi.DETECT_PYRAMID)
+    tp = []
+    for _ in range(8):
+        h.create_blocks(thr_now)
+        tm = dict(h.timing())
+        tp.append(tm["detect_hot"] + tm["detect_scatter"])
+    t_pyramid = float(np.mean(tp[3:]))
+    _, hot = h.detect_info()             # sub-blocks of 32 weights the pyramid pass had to read
+    h.set_detect_mode(capi.DETECT_STREAM)
     ts = []
     for _ in range(8):
         h.create_blocks(thr_now)
         ts.append(dict(h.timing())["detect_flags"])
     t_stream = float(np.mean(ts[3:]))
-    h.set_detect_mode(capi.DETECT_PYRAMID)
+    h.set_detect_mode(capi.DETECT_CANDIDATES)
     h.set_timing(False)
 
     if dist is not None:
@@ -355,6 +363,7 @@ def main():
     busy = {k: float(np.mean(v)) for k, v in stage_ms.items()}
     # algorithmic bytes per launch of the kernels that can dominate a sweep
     alg = {
+        "detect_cand": 4.0 * cands + 4.0 * Bl + 4.0 * Bl,                              # candidate weights, positions of the hits, starts
         "detect_hot": T_local / 16.0 + 128.0 * hot + 8.0 * hot,                        # bf16 pyramid + hot sub-blocks + triples
         "detect_flags": 4.0 * T_local + 4.0 * Bl,                                      # every weight + starts
         "block_emit": Bl * (4 + 16 + 4 + 16 + 16 * K),                                 # starts, integral gathers, N, sums, e, sp
@@ -370,6 +379,12 @@ def main():
     stream = {"kernel": "k_detect_flags", "achieved": sb / (t_stream * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
               "frac": sb / (t_stream * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": sb, "avg_launch_ms": t_stream,
               "note": "hml_set_detect_mode(HML_DETECT_STREAM): reads every weight; not used by the timed sweeps"}
+    pb = T_local / 16.0 + 136.0 * hot
+    pyramid = {"kernel": "k_detect_hot + k_scatter_hot", "achieved": pb / (t_pyramid * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+               "frac": pb / (t_pyramid * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": pb, "avg_launch_ms": t_pyramid,
+               "hot_subblocks": hot,
+               "note": "hml_set_detect_mode(HML_DETECT_PYRAMID): bf16 max pyramid + the sub-blocks that can hold a boundary; "
+                       "builds the candidate list, not used by the timed sweeps otherwise"}
     h2d = 8 * (2 * K + K * K + K)        # mean, var, A, pi as doubles (kernel parameters built from host buffers)
     d2h = 8 * (2 + K + K * K + 2 + 2 * K + 1) * (world if segments else 1)
     if world == 1:
@@ -396,9 +411,11 @@ def main():
         "config": {"workload": wl, "mode": "segments" if segments else ("independent" if world > 1 else "single"),
                    "states": K, "observations": T, "observations_per_gpu": T_local, "blocks_per_sweep": B,
                    "compression_ratio": T / B,
-                   "l2_policy": f"inputs larger than L2 (per GPU and sweep: {T_local / 16e9:.3f} GB pyramid + {128.0 * hot / 1e9:.3f} GB of "
-                                f"hot weight sub-blocks + the block-level arrays vs 126 MB L2; weights {4.0 * T_local / 1e9:.2f} GB)",
-                   "detect_mode": "pyramid", "hot_subblocks_per_sweep": hot,
+                   "l2_policy": f"per GPU and sweep the kernels touch {8.0 * cands / 1e6:.0f} MB of candidates, "
+                                f"{Bl * 32 / 1e6:.0f} MB of scattered integral-array entries (out of {16.0 * T_local / 1e9:.1f} GB) and "
+                                f"{Bl * (24 + 24 * K + 10) / 1e6:.0f} MB of per-block arrays, each written by one kernel and read by a "
+                                f"later one: larger than the 126 MB L2 together, no flush between sweeps",
+                   "detect_mode": "candidates", "candidates_per_sweep": cands,
                    "carry_exchange": h.exchange_transport(),
                    "load_seconds": t_load},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -412,6 +429,7 @@ def main():
                                                    / peak / 1e9 / (ms_per_step * 1e-3)},
         "recorded": recorded,
         "stream_detect": stream,
+        "pyramid_detect": pyramid,
         "stage_ms": busy,
         "device_busy_ms_per_step": float(sum(busy.values())),
     }

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhammlet_b200.so")
 
 SWEEP_DYNAMIC, SWEEP_LOGLIK, SWEEP_KEEP_ROWS = 1, 2, 4
-DETECT_STREAM, DETECT_PYRAMID = 0, 1
+DETECT_STREAM, DETECT_PYRAMID, DETECT_CANDIDATES = 0, 1, 2
 MAX_STATES = 32
 MAX_DIMS = 5
 
@@ -206,7 +206,8 @@ class Handle:
         return n.value
 
     def set_detect_mode(self, mode):
-        """DETECT_STREAM (read every weight) or DETECT_PYRAMID (default: read only sub-blocks that can hold a boundary)."""
+        """DETECT_STREAM (read every weight), DETECT_PYRAMID (read only sub-blocks that can hold a boundary) or
+        DETECT_CANDIDATES (default: one pass over the list of positions that can be boundaries near the threshold)."""
         self._ck(self.lib.hml_set_detect_mode(self.h, C.c_int(mode)))
 
     def detect_info(self):

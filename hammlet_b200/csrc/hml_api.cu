@@ -86,7 +86,16 @@ struct hml_ctx {
   uint64_t T = 0;
   float* w = nullptr;       // breakpoint weights, padded to a tile multiple
   uint16_t* smax = nullptr; // bf16 max pyramid over sub-blocks of 32 weights (boundary detection reads only hot sub-blocks)
-  int detect_mode = HML_DETECT_PYRAMID;
+  int detect_mode = HML_DETECT_CANDIDATES;
+  // candidate list (HML_DETECT_CANDIDATES): positions, ascending, and weights of everything not below cand_floor
+  uint32_t* cand_pos = nullptr;
+  float* cand_w = nullptr;
+  uint32_t* cand_scratch = nullptr;  // per-CTA counts, offsets, ticket
+  uint64_t cand_cap = 0, cand_n = 0;
+  uint32_t cand_scratch_ctas = 0;
+  float cand_floor = 0.f;
+  bool cand_valid = false;
+  uint64_t cand_rebuilds = 0;
   float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
   double2* pq = nullptr;    // integral arrays, T+1 entries (multivariate data: D planes, pq_stride entries apart)
   double4* cell_pref = nullptr;
@@ -364,10 +373,69 @@ size_t result_words(int KP, int D = 1) {
   return 2 + words + 2 * KP + 1 + (size_t)(D - 1) * 2 * KP;
 }
 
+int alloc_blocks(hml_t* h, uint64_t cap, int KP);
+
+// Candidate list for thresholds >= floor: one pyramid pass at the floor gives the positions (it is the block list of
+// that threshold), a gather their weights.  Grows the block arrays if the list does not fit (local to this rank; no
+// collective has been issued yet at this point of a sweep).
+int rebuild_candidates(hml_t* h, float floor) {
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    h->launches += launch_detect(h->w, h->smax, h->T, floor, h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity,
+                                 h->outblk, h->stream, nullptr, nullptr);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->outblk_host, h->outblk, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const uint64_t n = h->outblk_host[0];
+    if (n > h->capacity) {
+      int rc = alloc_blocks(h, n + n / 4, h->KP);
+      if (rc != HML_OK) return rc;
+      continue;
+    }
+    if (n + 4 > h->cand_cap) {
+      h->cand_cap = n + n / 4 + 4096;
+      CK(dev_alloc(h->cand_pos, h->cand_cap));
+      CK(dev_alloc(h->cand_w, h->cand_cap));
+    }
+    const uint32_t ctas = cand_ctas((uint32_t)h->cand_cap);
+    if (ctas > h->cand_scratch_ctas) {
+      h->cand_scratch_ctas = ctas;
+      CK(dev_alloc(h->cand_scratch, 2 * (size_t)ctas + 1));
+      CK(cudaMemsetAsync(h->cand_scratch, 0, (2 * (size_t)ctas + 1) * sizeof(uint32_t), h->stream));
+    }
+    launch_cand_gather(h->w, h->starts, (uint32_t)n, h->cand_w, h->cand_pos, h->sms, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->cand_n = n;
+    h->cand_floor = floor;
+    h->cand_valid = true;
+    h->cand_rebuilds++;
+    return HML_OK;
+  }
+  return fail(h, HML_ERR_CAPACITY, "block capacity did not converge");
+}
+
 int run_detect(hml_t* h, float thr) {
-  h->launches += launch_detect(h->w, h->detect_mode == HML_DETECT_PYRAMID ? h->smax : nullptr, h->T, thr,
-                               h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity, h->outblk, h->stream,
-                               stage_cb, h);
+  bool done = false;
+  if (h->detect_mode == HML_DETECT_CANDIDATES && thr > 0.f && isfinite(thr)) {
+    // usable: every boundary of thr is a candidate; worth keeping: the list is not much longer than the block list
+    bool usable = h->cand_valid && thr >= h->cand_floor;
+    if (usable && h->blocks_valid && h->cand_n > 4 * h->nblocks + 65536 && 0.75f * thr > 1.05f * h->cand_floor) usable = false;
+    if (!usable) {
+      int rc = rebuild_candidates(h, 0.75f * thr);
+      if (rc != HML_OK) return rc;
+    }
+    if (h->cand_n > 0) {
+      h->launches += launch_detect_candidates(h->cand_w, h->cand_pos, (uint32_t)h->cand_n, thr, h->cand_scratch,
+                                              h->cand_scratch_ctas, h->starts, h->capacity, h->T, h->outblk, h->stream,
+                                              stage_cb, h);
+      done = true;
+    }
+  }
+  if (!done) {  // thresholds <= 0, NaN, inf (and an empty candidate list): every weight is looked at
+    h->launches += launch_detect(h->w, h->detect_mode != HML_DETECT_STREAM ? h->smax : nullptr, h->T, thr,
+                                 h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity, h->outblk, h->stream,
+                                 stage_cb, h);
+  }
   CK(cudaGetLastError());
   if (h->world > 1) {
     // the partial block in front of each rank's first boundary joins the last block of its owner
@@ -395,6 +463,8 @@ void load_reset(hml_t* h) {
   h->seg_start = 0;
   h->D = 1;
   h->pq_stride = h->cell_stride = 0;
+  h->cand_valid = false;
+  h->cand_n = 0;
   h->mg_K = 0;  // marginals belong to the sequence that was loaded
   h->mg_n = h->mg_iterations = 0;
   h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
@@ -840,6 +910,11 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
       if (rc != HML_OK) return rc;
       gather = true;
       h->blocks_valid = false;
+      if ((flags & HML_SWEEP_KEEP_ROWS) && h->rows_cap < (h->capacity + 1) * (uint64_t)mh.K) {
+        h->rows_cap = (h->capacity + 1) * (uint64_t)mh.K;  // the candidate build may have grown the block arrays
+        CK(dev_alloc(h->rows, h->rows_cap));
+      }
+      if (replay && h->replay_cap < h->capacity) return fail(h, HML_ERR_STATE, "replay buffer smaller than the block capacity");
     }
     SweepBuffers b = make_buffers(h, KP);
     b.rows = (flags & HML_SWEEP_KEEP_ROWS) ? h->rows : nullptr;
@@ -1106,6 +1181,9 @@ int hml_destroy(hml_t* h) {
   dev_free(h->tile_ain);
   dev_free(h->group_ops);
   dev_free(h->group_ain);
+  dev_free(h->cand_pos);
+  dev_free(h->cand_w);
+  dev_free(h->cand_scratch);
   dev_free(h->seg_counts);
   dev_free(h->seg_starts);
   dev_free(h->seg_states);
@@ -1658,7 +1736,8 @@ int hml_exchange_transport(const hml_t* h, int* transport) {
 
 int hml_set_detect_mode(hml_t* h, int mode) {
   if (!h) return HML_ERR_ARG;
-  if (mode != HML_DETECT_STREAM && mode != HML_DETECT_PYRAMID) return fail(h, HML_ERR_ARG, "unknown detection mode");
+  if (mode != HML_DETECT_STREAM && mode != HML_DETECT_PYRAMID && mode != HML_DETECT_CANDIDATES)
+    return fail(h, HML_ERR_ARG, "unknown detection mode");
   h->detect_mode = mode;
   return HML_OK;
 }
@@ -1668,7 +1747,9 @@ int hml_detect_info(hml_t* h, int* mode, uint64_t* hot_subblocks) {
   if (mode) *mode = h->detect_mode;
   if (hot_subblocks) {
     *hot_subblocks = 0;
-    if (h->T && h->detect_scratch) {
+    if (h->detect_mode == HML_DETECT_CANDIDATES) {
+      *hot_subblocks = h->cand_valid ? h->cand_n : 0;  // entries the last candidate pass looked at
+    } else if (h->T && h->detect_scratch) {
       CK(cudaSetDevice(h->device));
       unsigned long long v = 0;
       CK(cudaMemcpyAsync(&v, detect_hot_count_ptr(h->detect_scratch, h->T), sizeof(v), cudaMemcpyDeviceToHost, h->stream));

@@ -455,6 +455,170 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Candidate mode (default).  Between two sweeps of a chain the threshold moves by a hair (it follows the smallest
+// sampled variance), so almost all of the weight array can never hold a boundary.  The candidate list keeps, in
+// position order, every position whose weight is not below a FLOOR (0.75 x the threshold it was built for) together
+// with that weight; as long as thr >= floor the boundary set {t : !(w[t] < thr)} is a subset of the list and one
+// coalesced pass over the list's weights (8 bytes per candidate, ~1.3 candidates per block) finds it: same set, same
+// order, bit for bit, 6 us instead of 88 at T = 1e9.  The list is (re)built by one pyramid pass at the floor whenever
+// the threshold drops below the floor or the list has become much longer than needed (hml_api.cu: run_detect).
+//   k_cand_gather   cand_w[i] = w[starts[i]], cand_pos[i] = starts[i]          (build)
+//   k_cand_count    float4 loads, flags, per-CTA counts; the last CTA scans them, writes the block count + sentinel
+//   k_cand_scatter  flags again, block scan, starts[offset + rank] = cand_pos[i]
+constexpr int kCandPerThread = 8;                      // two float4
+constexpr int kCandPerCta = 256 * kCandPerThread;      // 2048
+
+__global__ void __launch_bounds__(256) k_cand_gather(const float* __restrict__ w, const uint32_t* __restrict__ starts,
+                                                     uint32_t n, float* __restrict__ cand_w, uint32_t* __restrict__ cand_pos) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t p = starts[i];
+    cand_pos[i] = p;
+    cand_w[i] = w[p];
+  }
+}
+
+// flags of the eight candidates of a thread: bits 0-3 = candidates base + 4 tid .. + 3, bits 4-7 = the same + 1024
+__device__ __forceinline__ uint32_t cand_flags(const float4* __restrict__ cw4, uint32_t nc, float thr) {
+  const uint32_t base = blockIdx.x * (uint32_t)kCandPerCta;
+  uint32_t f = 0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t i0 = base + half * 1024u + 4u * threadIdx.x;
+    if (i0 < nc) {  // the arrays are padded to a multiple of 4
+      const float4 v = cw4[i0 >> 2];
+      uint32_t m = (!(v.x < thr) ? 1u : 0u) | (!(v.y < thr) ? 2u : 0u) | (!(v.z < thr) ? 4u : 0u) | (!(v.w < thr) ? 8u : 0u);
+      const uint32_t left = nc - i0;
+      if (left < 4) m &= (1u << left) - 1u;
+      f |= m << (4 * half);
+    }
+  }
+  return f;
+}
+
+__global__ void __launch_bounds__(256)
+    k_cand_count(const float4* __restrict__ cw4, uint32_t nc, float thr, uint32_t nctas, uint32_t* __restrict__ cta_count,
+                 uint32_t* __restrict__ cta_off, unsigned int* __restrict__ ticket, unsigned long long* __restrict__ nblocks_out,
+                 uint32_t* __restrict__ starts, uint64_t capacity, uint64_t T) {
+  pdl_enter();
+  __shared__ uint32_t s_warp[8];
+  __shared__ bool s_last;
+  const uint32_t f = cand_flags(cw4, nc, thr);
+  uint32_t c = __popc(f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += s_warp[i];
+    cta_count[blockIdx.x] = tot;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == nctas - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // the last CTA to arrive: exclusive scan of the per-CTA counts, block count, sentinel
+  __threadfence();
+  __shared__ uint32_t s_part[256];
+  const uint32_t per = (nctas + 255) / 256;
+  const uint32_t lo = threadIdx.x * per, hi = min(nctas, lo + per);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; ++i) sum += __ldcg(cta_count + i);
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < 256; ++i) {
+      const uint32_t v = s_part[i];
+      s_part[i] = run;
+      run += v;
+    }
+    *nblocks_out = run;
+    if ((uint64_t)run <= capacity) starts[run] = (uint32_t)T;  // sentinel: block b = [starts[b], starts[b + 1])
+    *ticket = 0;
+  }
+  __syncthreads();
+  uint32_t run = s_part[threadIdx.x];
+  for (uint32_t i = lo; i < hi; ++i) {
+    const uint32_t v = __ldcg(cta_count + i);
+    cta_off[i] = run;
+    run += v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_cand_scatter(const float4* __restrict__ cw4, const uint4* __restrict__ cpos4, uint32_t nc, float thr,
+                   const uint32_t* __restrict__ cta_off, uint32_t* __restrict__ starts, uint64_t capacity) {
+  pdl_enter();
+  __shared__ uint32_t s_warp[8];
+  const uint32_t f = cand_flags(cw4, nc, thr);
+  // counts of the two halves packed (each <= 4 per thread, <= 1024 per CTA): one scan ranks both
+  const uint32_t mine = __popc(f & 0xfu) | (__popc(f >> 4) << 16);
+  uint32_t incl = mine;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t v = s_warp[i];
+    if (i < warp) before += v;
+    total += v;
+  }
+  const uint32_t excl = before + incl - mine;
+  const uint32_t base = blockIdx.x * (uint32_t)kCandPerCta;
+  const uint64_t off = cta_off[blockIdx.x];
+  uint64_t o0 = off + (excl & 0xffffu);                          // first half: ranks among first-half flags
+  uint64_t o1 = off + (total & 0xffffu) + (excl >> 16);          // second half comes after the whole first half
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t m = (f >> (4 * half)) & 0xfu;
+    if (m) {
+      const uint32_t i0 = base + half * 1024u + 4u * threadIdx.x;
+      const uint4 p = cpos4[i0 >> 2];
+      uint64_t& o = half ? o1 : o0;
+      if (m & 1u) { if (o < capacity) starts[o] = p.x; ++o; }
+      if (m & 2u) { if (o < capacity) starts[o] = p.y; ++o; }
+      if (m & 4u) { if (o < capacity) starts[o] = p.z; ++o; }
+      if (m & 8u) { if (o < capacity) starts[o] = p.w; ++o; }
+    }
+  }
+}
+
+void launch_cand_gather(const float* w, const uint32_t* starts, uint32_t n, float* cand_w, uint32_t* cand_pos, int sms,
+                        cudaStream_t s) {
+  if (n == 0) return;
+  int g = (int)((n + 255) / 256);
+  if (g > sms * 16) g = sms * 16;
+  k_cand_gather<<<g, 256, 0, s>>>(w, starts, n, cand_w, cand_pos);
+}
+
+// boundaries among the candidates; cta_scratch holds 2 * ctas + 1 words (counts, offsets, ticket = last word, zeroed
+// once by the caller and left at zero by the kernel).  Returns the number of launches.
+int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, uint32_t nc, float thr, uint32_t* cta_scratch,
+                             uint32_t scratch_ctas, uint32_t* starts, uint64_t capacity, uint64_t T,
+                             unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb, void* user) {
+  const uint32_t ctas = (nc + kCandPerCta - 1) / kCandPerCta;
+  uint32_t* cta_count = cta_scratch;
+  uint32_t* cta_off = cta_scratch + scratch_ctas;
+  unsigned int* ticket = cta_scratch + 2 * scratch_ctas;
+  if (cb) cb(user, "detect_cand");
+  launch_k(k_cand_count, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), nc, thr, ctas, cta_count, cta_off, ticket,
+           nblocks_out, starts, capacity, T);
+  if (cb) cb(user, "detect_scatter");
+  launch_k(k_cand_scatter, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), reinterpret_cast<const uint4*>(cand_pos),
+           nc, thr, (const uint32_t*)cta_off, starts, capacity);
+  return 2;
+}
+uint32_t cand_ctas(uint32_t nc) { return (nc + kCandPerCta - 1) / kCandPerCta; }
+
 // scratch layout: [stream mode] masks (512 B per tile), per-tile counts, per-CTA counts and offsets;
 // [pyramid mode] hot triples (8 B per pyramid entry), span_info, span_off, ticket; [both] hot counters
 struct DetectScratch {

@@ -30,6 +30,13 @@ size_t detect_scratch_bytes(uint64_t T);
 int launch_detect(const float* w, const uint16_t* smax, uint64_t T, float thr, int force_first, void* scratch,
                   uint32_t* starts, uint64_t capacity, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
                   void* user);
+// candidate mode: the positions (ascending) and weights of everything that can be a boundary while thr >= floor
+void launch_cand_gather(const float* w, const uint32_t* starts, uint32_t n, float* cand_w, uint32_t* cand_pos, int sms,
+                        cudaStream_t s);
+uint32_t cand_ctas(uint32_t nc);
+int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, uint32_t nc, float thr, uint32_t* cta_scratch,
+                             uint32_t scratch_ctas, uint32_t* starts, uint64_t capacity, uint64_t T,
+                             unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb, void* user);
 size_t pyramid_entries(uint64_t T);  // bf16 entries, one per 32 weights, padded to whole spans
 void launch_build_pyramid(const float* w, uint64_t T, uint16_t* smax, int sms, cudaStream_t s);
 const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);

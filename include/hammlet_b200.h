@@ -87,8 +87,15 @@ int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks);
  *   HML_DETECT_PYRAMID  (default) the device analogue of the reference's skip pointers
  *                       (Blocks/BreakpointArray.hpp:150-182): a max pyramid over sub-blocks of 32 weights is
  *                       built at load, and only sub-blocks whose maximum reaches the threshold are read.
- * hml_detect_info reports the mode and the number of sub-blocks the last detection pass had to read. */
-enum { HML_DETECT_STREAM = 0, HML_DETECT_PYRAMID = 1 };
+ *   HML_DETECT_CANDIDATES (default) the threshold of a Gibbs chain moves by a hair from sweep to sweep, so the
+ *                       positions whose weight is not below a floor (0.75 x the threshold the list was built for) are
+ *                       kept, in order, with their weights; while threshold >= floor one coalesced pass over that list
+ *                       (8 bytes per candidate, ~1.3 candidates per block) finds the boundaries.  The list is rebuilt
+ *                       by a pyramid pass when the threshold drops below the floor or the list has become much longer
+ *                       than the block list.  Thresholds <= 0, NaN and inf go through the pyramid pass.
+ * hml_detect_info reports the mode and the number of sub-blocks (pyramid) or candidates (candidate mode) the last
+ * detection pass had to read. */
+enum { HML_DETECT_STREAM = 0, HML_DETECT_PYRAMID = 1, HML_DETECT_CANDIDATES = 2 };
 int hml_set_detect_mode(hml_t* h, int mode);
 int hml_detect_info(hml_t* h, int* mode, uint64_t* hot_subblocks);
 int hml_nr_blocks(const hml_t* h, uint64_t* nblocks);

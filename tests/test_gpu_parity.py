@@ -87,7 +87,8 @@ def test_weights_vs_reference_fixture(dev, path):
 
 # ------------------------------------------------------------------------------------------ boundaries + statistics
 
-@pytest.mark.parametrize("mode", [capi.DETECT_PYRAMID, capi.DETECT_STREAM], ids=["pyramid", "stream"])
+@pytest.mark.parametrize("mode", [capi.DETECT_CANDIDATES, capi.DETECT_PYRAMID, capi.DETECT_STREAM],
+                         ids=["candidates", "pyramid", "stream"])
 @pytest.mark.parametrize("T,L", [(1, 5), (7, 3), (4096, 40), (100_000, 200), (3_000_017, 500)])
 def test_boundaries_exact_and_stats(dev, T, L, mode):
     dev.set_detect_mode(mode)
@@ -110,7 +111,7 @@ def test_boundaries_exact_and_stats(dev, T, L, mode):
             n, rs, rq = O64.block_stats(integ, ref, T)
             assert rel_err(q, rq, scale=msq) <= RTOL
             assert rel_err(s, rs, scale=np.maximum(np.sqrt(n * rq), np.sqrt(msq))) <= RTOL
-    dev.set_detect_mode(capi.DETECT_PYRAMID)
+    dev.set_detect_mode(capi.DETECT_CANDIDATES)
 
 
 def test_pyramid_and_stream_detection_agree_on_hostile_weights(dev):
@@ -127,14 +128,15 @@ def test_pyramid_and_stream_detection_agree_on_hostile_weights(dev):
     w = dev.weights()
     for thr in (0.3, 1.2, 50.0, 1e30, np.inf, np.nan):
         lists = []
-        for mode in (capi.DETECT_STREAM, capi.DETECT_PYRAMID):
+        for mode in (capi.DETECT_STREAM, capi.DETECT_PYRAMID, capi.DETECT_CANDIDATES):
             dev.set_detect_mode(mode)
             B = dev.create_blocks(thr)
             lists.append(dev.blocks(stats=False))
             assert B == lists[-1].size
         expect = np.flatnonzero(~(w < np.float32(thr)))
         expect = expect if expect.size and expect[0] == 0 else np.concatenate([[0], expect])
-        assert np.array_equal(lists[0], lists[1]) and np.array_equal(lists[0].astype(np.int64), expect)
+        assert np.array_equal(lists[0], lists[1]) and np.array_equal(lists[0], lists[2])
+        assert np.array_equal(lists[0].astype(np.int64), expect)
     dev.set_detect_mode(capi.DETECT_PYRAMID)
     B = dev.create_blocks(1.2)
     mode, hot = dev.detect_info()
@@ -142,6 +144,39 @@ def test_pyramid_and_stream_detection_agree_on_hostile_weights(dev):
     # rounding flags only a few more
     true_hot = np.unique(dev.blocks(stats=False) // 32).size
     assert mode == capi.DETECT_PYRAMID and true_hot <= hot <= true_hot * 1.1 + 8
+    dev.set_detect_mode(capi.DETECT_CANDIDATES)
+
+
+def test_candidate_list_follows_the_threshold(dev):
+    """Candidate mode: the list built at 0.75 x threshold serves every later threshold >= its floor, is rebuilt when
+    the threshold drops below the floor or the list has become much longer than the block list, and grows the block
+    arrays when it does not fit.  The boundary list must equal the oracle's for every threshold of the walk."""
+    T = 6_000_011
+    x = piecewise_gaussian(T, 5, 40, seed=17)
+    O32 = oracle.Oracle(False)
+    w = O32.weights(x)
+    dev.load(x)
+    assert dev.detect_info()[0] == capi.DETECT_CANDIDATES
+    sizes = []
+    #       build   reuse  reuse  below the floor  far above: kept once, then found too long, reuse  tiny: outgrows the block arrays
+    for thr in (1.0, 0.9999, 1.3, 0.7, 6.0, 6.5, 7.0, 0.02, 0.021, 1.0):
+        B = dev.create_blocks(thr)
+        ref = O32.boundaries(w, np.float32(thr))
+        assert B == ref.size
+        assert np.array_equal(dev.blocks(stats=False).astype(np.uint64), ref)
+        sizes.append((thr, B, dev.detect_info()[1]))
+    cand = [c for _, _, c in sizes]
+    assert cand[0] == cand[1] == cand[2]                      # one list served three thresholds
+    assert cand[3] > cand[0]                                  # 0.7: rebuilt at a lower floor
+    assert cand[4] == cand[3]                                 # 6.0: the block count that says "too long" is the previous sweep's
+    assert cand[5] < cand[3] / 4 and cand[6] == cand[5]       # 6.5: rebuilt, 7.0: reused
+    assert cand[7] > cand[3] and cand[8] == cand[7]           # 0.02: far below the floor; 0.021: reused
+    assert cand[9] == cand[8]                                 # 1.0 after 0.021: kept once more (see above)
+    assert all(c >= B for _, B, c in sizes)
+    # a dynamic sweep uses the same path
+    mu, var, A, pi = model_guess(5, seed=5)
+    out = dev.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=0.95, seed=1, sweep=0)
+    assert out["nblocks"] == O32.boundaries(w, np.float32(0.95)).size and out["trans"].sum() == T
 
 
 def test_block_stats_vs_exact_sums(dev):
