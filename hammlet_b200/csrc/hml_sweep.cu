@@ -74,17 +74,25 @@ __global__ void __launch_bounds__(1024) k_seg_count(const uint8_t* __restrict__ 
   }
 }
 
-// in-place exclusive scan of tile_counts[0..ntiles) by one CTA; tile_counts[ntiles] receives the total
+// in-place exclusive scan of tile_counts[0..ntiles) by one CTA; tile_counts[ntiles] receives the total.
+// Eight consecutive elements per thread and trip (8192 per trip): the marginal merge scans ~1.6e5 flags with it.
 __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t* tile_counts, uint32_t ntiles) {
+  constexpr int V = 8;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_running;
   if (threadIdx.x == 0) s_running = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < ntiles; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    const uint32_t v = i < ntiles ? tile_counts[i] : 0u;
-    uint32_t x = v;
+  for (uint32_t base = 0; base < ntiles; base += 1024 * V) {
+    const uint32_t i0 = base + threadIdx.x * V;
+    uint32_t v[V];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      v[k] = (i0 + k < ntiles) ? tile_counts[i0 + k] : 0u;
+      mine += v[k];
+    }
+    uint32_t x = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -103,7 +111,12 @@ __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t* tile_counts, uint32
     }
     __syncthreads();
     const uint32_t before = s_running + (warp ? s_warp[warp - 1] : 0u);
-    if (i < ntiles) tile_counts[i] = before + x - v;
+    uint32_t run = before + x - mine;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      if (i0 + k < ntiles) tile_counts[i0 + k] = run;
+      run += v[k];
+    }
     __syncthreads();
     if (threadIdx.x == 1023) s_running = before + x;
     __syncthreads();
