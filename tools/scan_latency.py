@@ -87,6 +87,56 @@ def main():
         chain.close()
         h.close()
         torch.cuda.empty_cache()
+    # ---- multivariate data (`-s C P D`): handle-level sweeps with a fixed model (the C chain of
+    # include/hammlet_host.h is univariate); same stage table
+    for name, T, P, D in (("MD 1e8 x 2 dims, P=2 (K=4)", 100_000_000, 2, 2), ("MD 5e7 x 3 dims, P=3 (K=27)", 50_000_000, 3, 3)):
+        if args.only and not any(tok in name for tok in args.only.split(",")):
+            continue
+        K = P ** D
+        gen = torch.Generator(device=device)
+        gen.manual_seed(11)
+        L = 5000
+        change = torch.rand(T, generator=gen, device=device) < (1.0 / L)
+        seg = torch.cumsum(change.to(torch.int32), 0, dtype=torch.int32).long()
+        levels = torch.randint(0, P, (int(seg[-1].item()) + 1, D), generator=gen, device=device).to(torch.float32)
+        x = (levels[seg] - (P - 1) / 2.0) + 0.3 * torch.randn(T, D, generator=gen, device=device)
+        del change, seg, levels
+        x = x.contiguous()
+        torch.cuda.synchronize()
+        h = capi.Handle(0)
+        h.load_device_md(x.data_ptr(), T, D)
+        del x
+        torch.cuda.empty_cache()
+        mapping = capi.combinations_mapping(P, D)
+        mu = np.arange(P) - (P - 1) / 2.0
+        var = np.full(P, 0.09)
+        A = np.full((K, K), 0.0002 / (K - 1)) + np.eye(K) * (0.9998 - 0.0002 / (K - 1))
+        pi = np.full(K, 1.0 / K)
+        thr = float(np.sqrt(np.float32(2) * np.log(np.float32(T)) * np.float32(0.09)))
+        for i in range(5):
+            out = h.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=thr, seed=1, sweep=i, mapping=mapping)
+        steps = 50
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for i in range(steps):
+            out = h.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=thr, seed=1, sweep=10 + i, mapping=mapping)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - w0) * 1e3 / steps
+        h.set_timing(True)
+        stage = {}
+        for i in range(20):
+            h.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=thr, seed=1, sweep=100 + i, mapping=mapping)
+            for nm, ms in h.timing():
+                stage.setdefault(nm, []).append(ms)
+        h.set_timing(False)
+        st = {k: float(np.mean(v)) * 1e3 for k, v in stage.items()}
+        line = {"config": name, "T": T, "D": D, "P": P, "K": K, "blocks_per_sweep": int(out["nblocks"]),
+                "sweep_ms_wall": wall_ms, "sweeps_per_s": 1e3 / wall_ms, "stage_us": st,
+                "how": "hml_fb_sweep from Python (ctypes) with a fixed model, wall clock incl. the call overhead"}
+        print(json.dumps(line), flush=True)
+        lines.append(line)
+        h.close()
+        torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         for ln in lines:
