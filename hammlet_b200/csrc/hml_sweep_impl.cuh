@@ -395,6 +395,13 @@ static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint3
 template <int KP, bool kGather, bool kEmit, bool kMix>
 __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<KP> m, int want_maxe) {
   pdl_enter();
+  // K <= 8: the K emission terms of a block sit KP * 8 bytes apart from the next block's, so a warp storing "term s of
+  // my block" touches 32 * KP * 8 / 32 sectors per instruction — five times the sectors the data occupies at K = 5, and
+  // the L1 store path, not DRAM, bounded the kernel.  The terms of the CTA's 256 consecutive slots are staged in shared
+  // memory and written as one contiguous piece (consecutive threads, consecutive words).
+  constexpr bool kStage = kEmit && KP <= 8;
+  __shared__ double s_e[kStage ? 256 * KP : 1];
+  __shared__ double s_sp[(kStage && !kMix) ? 256 * KP : 1];
   if (kEmit && blockIdx.x == 0) {
     // first kernel of a sweep: zero the result block that the later kernels accumulate into
     for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
@@ -402,32 +409,36 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
   }
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  // slots is a multiple of 1024 and the stride a multiple of 256: all threads of a CTA make the same trips
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = Layout::inv(p);
-    if (b >= B) continue;
-    uint32_t n;
-    double sx, sq;
-    if (kGather) {
-      const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
-      range_sums(buf, s, e, sx, sq);
-      n = e - s;
-      if (buf.seg.world > 1 && b + 1 == B) {
-        // the rank's last block continues on the following ranks up to their first boundary
-        for (int r = buf.seg.rank + 1; r < buf.seg.world; ++r) {
-          const double* hd = buf.seg.heads + 4 * r;
-          n += (uint32_t)hd[1];
-          sx += hd[2];
-          sq += hd[3];
-          if (hd[0] > 0.0) break;
+    const bool valid = b < B;
+    if (!kStage && !valid) continue;
+    uint32_t n = 0;
+    double sx = 0.0, sq = 0.0;
+    if (valid) {
+      if (kGather) {
+        const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
+        range_sums(buf, s, e, sx, sq);
+        n = e - s;
+        if (buf.seg.world > 1 && b + 1 == B) {
+          // the rank's last block continues on the following ranks up to their first boundary
+          for (int r = buf.seg.rank + 1; r < buf.seg.world; ++r) {
+            const double* hd = buf.seg.heads + 4 * r;
+            n += (uint32_t)hd[1];
+            sx += hd[2];
+            sq += hd[3];
+            if (hd[0] > 0.0) break;
+          }
         }
+        buf.bN[p] = n;
+        buf.bS[p] = make_double2(sx, sq);
+      } else {
+        n = buf.bN[p];
+        const double2 v = buf.bS[p];
+        sx = v.x;
+        sq = v.y;
       }
-      buf.bN[p] = n;
-      buf.bS[p] = make_double2(sx, sq);
-    } else {
-      n = buf.bN[p];
-      const double2 v = buf.bS[p];
-      sx = v.x;
-      sq = v.y;
     }
     if (kEmit) {
       const double N = (double)n;
@@ -441,13 +452,30 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
         E[s] = v;
         if (s < m.K) mx = fmax(mx, v);
       }
+      if (kStage) {
 #pragma unroll
-      for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp(E[s] - mx) : 0.0;
-      if (!kMix) {
+        for (int s = 0; s < KP; ++s) s_e[threadIdx.x * KP + s] = (valid && s < m.K) ? exp(E[s] - mx) : 0.0;
+        if (!kMix) {
 #pragma unroll
-        for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+          for (int s = 0; s < KP; ++s) s_sp[threadIdx.x * KP + s] = (valid && s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+        }
+        __syncthreads();
+        const uint64_t base = (p - threadIdx.x) * KP;  // first word of the CTA's 256 slots
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          buf.e[base + k * 256 + threadIdx.x] = s_e[k * 256 + threadIdx.x];
+          if (!kMix) buf.sp[base + k * 256 + threadIdx.x] = s_sp[k * 256 + threadIdx.x];
+        }
+        __syncthreads();
+      } else {
+#pragma unroll
+        for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp(E[s] - mx) : 0.0;
+        if (!kMix) {
+#pragma unroll
+          for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+        }
       }
-      if (want_maxe) buf.maxE[p] = mx;
+      if (want_maxe && valid) buf.maxE[p] = mx;
     }
   }
 }
