@@ -49,6 +49,26 @@ def test_records_files_match_reference(tmp_path, tag):
         assert (tmp_path / f"out-{kind}.csv").read_text() == str(g[f"file_{kind}{tag}"]), kind
 
 
+@pytest.mark.parametrize("tag", ["32", "64"])
+def test_records_from_runs_match_reference(tmp_path, tag):
+    """Records::recordRun — recorded iterations delivered as equal-state runs, as the device hands them over —
+    must produce the reference's marginals, sequences, compression and segments files byte for byte."""
+    tool = need(os.path.join(BIN, "records_tool"))
+    g = np.load(os.path.join(GOLD, "fb_T20000_K3_dyn5.npz"), allow_pickle=False)
+    T, K, nsw = int(g["T"]), int(g["K"]), int(g["nsweeps"])
+    sizes = [[int(v) for v in line.split("\t")] for line in str(g["file_blocks" + tag]).strip().split("\n")]
+    states = g["all_states" + tag]
+    txt, off = [f"{T} {K} {nsw}"], 0
+    for it in range(nsw):
+        B = len(sizes[it])
+        txt += [str(B), " ".join(map(str, sizes[it])), " ".join(str(int(s)) for s in states[off:off + B])]
+        off += B
+    p = run([tool, str(tmp_path / "out-"), ".csv", "runs"], stdin="\n".join(txt) + "\n")
+    assert p.returncode == 0, p.stderr
+    for kind in ("marginals", "sequences", "compression", "segments"):
+        assert (tmp_path / f"out-{kind}.csv").read_text() == str(g[f"file_{kind}{tag}"]), kind
+
+
 def test_records_refuse_overwrite_and_overrun(tmp_path):
     tool = need(os.path.join(BIN, "records_tool"))
     p = run([tool, str(tmp_path / "o-"), ".csv"], stdin="10 2 1\n2\n6 5\n0 1\n")
