@@ -133,6 +133,7 @@ struct hml_ctx {
   uint64_t seg_cap = 0;            // blocks the three arrays are sized for
   bool segs_valid = false;         // seg_counts holds the offsets of the current states
   bool runs_written = false;       // seg_starts / seg_states hold the runs of the current states
+  bool nsegs_known = false;        // nsegs (host) is the count of the current states
   uint64_t nsegs = 0;
   // state marginals accumulated on the device (hml_marginals_*): sorted segment starts + K counts per segment
   uint32_t* mg_pos[2] = {nullptr, nullptr};
@@ -140,7 +141,10 @@ struct hml_ctx {
   uint32_t *mg_run_of_old = nullptr, *mg_olds_below = nullptr, *mg_flags = nullptr;
   uint64_t mg_cap = 0, mg_runs_cap = 0;  // segments the double buffers hold; runs the scratch holds
   int mg_cur = 0, mg_K = 0;
-  uint64_t mg_n = 0, mg_iterations = 0;
+  uint64_t mg_n = 0, mg_iterations = 0;  // mg_n: segments as of the last completed copy of the device-side count
+  uint32_t* mg_n_dev = nullptr;          // [2]: segment count of buffer 0 / 1 (the merge kernels read and write them)
+  uint32_t* mg_n_host = nullptr;         // pinned mirror of the current count
+  bool mg_pending = false;               // a count copy has been queued since the last stream synchronisation
   double* partials = nullptr;
   unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
   unsigned long long* outblk_host = nullptr;  // pinned mirror
@@ -841,6 +845,7 @@ int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged) {
     CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
+  h->mg_pending = false;
   if (int rc = check_exchange(h)) return rc;
   res.global_blocks = res.first_block = 0;
   res.any_overflow = res.own_overflow = false;
@@ -1191,6 +1196,9 @@ int hml_destroy(hml_t* h) {
     dev_free(h->mg_pos[k]);
     dev_free(h->mg_cnt[k]);
   }
+  dev_free(h->mg_n_dev);
+  if (h->mg_n_host) cudaFreeHost(h->mg_n_host);
+  h->mg_n_host = nullptr;
   dev_free(h->mg_run_of_old);
   dev_free(h->mg_olds_below);
   dev_free(h->mg_flags);
@@ -1458,7 +1466,9 @@ int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity) {
 
 // Equal-state runs of the last sweep, formed on the device (Records.hpp:166-188: a segment ends where the state
 // changes): h->nsegs runs; with `write` their (start, state) pairs are left in h->seg_starts / h->seg_states.
-static int ensure_runs(hml_t* h, bool write) {
+// need_count: the host wants to know the number of runs (one small copy + synchronisation); the marginal merge does
+// not — its kernels read the count from device memory (seg_counts[ntiles]).
+static int ensure_runs(hml_t* h, bool write, bool need_count = true) {
   const uint64_t B = h->nblocks;
   const uint64_t ntiles = (B + 1023) / 1024;
   if (h->seg_cap < h->capacity || !h->seg_counts) {
@@ -1473,12 +1483,17 @@ static int ensure_runs(hml_t* h, bool write) {
     launch_segments_count(b, B, h->seg_counts, h->sms, h->stream);
     h->launches += 2;
     CK(cudaGetLastError());
+    h->segs_valid = true;
+    h->nsegs_known = false;
+    h->runs_written = false;
+  }
+  if (need_count && !h->nsegs_known) {
     uint32_t n32 = 0;
     CK(cudaMemcpyAsync(&n32, h->seg_counts + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->mg_pending = false;
     h->nsegs = n32;
-    h->segs_valid = true;
-    h->runs_written = false;
+    h->nsegs_known = true;
   }
   if (write && !h->runs_written) {
     launch_segments_write(b, B, h->seg_counts, h->seg_starts, h->seg_states, h->sms, h->stream);
@@ -1559,6 +1574,8 @@ int hml_marginals_reset(hml_t* h, int K) {
   h->mg_cur = 0;
   h->mg_n = 0;
   h->mg_iterations = 0;
+  if (!h->mg_n_dev) CK(dev_alloc(h->mg_n_dev, 2));
+  if (!h->mg_n_host) CK(cudaMallocHost((void**)&h->mg_n_host, sizeof(uint32_t)));
   // room for one segment per 512 positions up front (the refinement has about as many segments as a sweep has
   // equal-state runs; growing later means freeing and allocating while tens of GB are resident: ~100 ms)
   uint64_t guess = h->T / 512;
@@ -1569,7 +1586,24 @@ int hml_marginals_reset(hml_t* h, int K) {
   // one segment covering the whole sequence, all counts zero (StateMarginals.hpp:24-33)
   CK(cudaMemsetAsync(h->mg_pos[0], 0, sizeof(uint32_t), h->stream));
   CK(cudaMemsetAsync(h->mg_cnt[0], 0, (size_t)K * sizeof(uint16_t), h->stream));
+  const uint32_t one[2] = {1u, 1u};
+  CK(cudaMemcpyAsync(h->mg_n_dev, one, sizeof(one), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *h->mg_n_host = 1;
   h->mg_n = 1;
+  h->mg_pending = false;
+  return HML_OK;
+}
+
+// segments as of now: the count copy queued by the last hml_marginals_add has landed once the stream has been
+// synchronised (every sweep does that); otherwise wait for it
+static int mg_current_segments(hml_t* h, uint64_t* n) {
+  if (h->mg_pending) {
+    CK(cudaStreamSynchronize(h->stream));
+    h->mg_pending = false;
+  }
+  if (h->mg_n_host) h->mg_n = *h->mg_n_host;
+  *n = h->mg_n;
   return HML_OK;
 }
 
@@ -1581,29 +1615,38 @@ int hml_marginals_add(hml_t* h) {
   if (h->mg_iterations >= 32767) return fail(h, HML_ERR_CAPACITY, "marginal counts are 16-bit (marginal_t): 32767 iterations");
   if (h->nblocks == 0) return HML_OK;
   CK(cudaSetDevice(h->device));
-  int rc = ensure_runs(h, true);
+  // Nothing here waits for the device: the runs are formed and merged by kernels that read their counts from device
+  // memory; the host only needs upper bounds (segments so far + blocks of the sweep) to size buffers and grids.
+  int rc = ensure_runs(h, true, false);
   if (rc != HML_OK) return rc;
-  const uint64_t m = h->nsegs, n = h->mg_n;
-  rc = mg_reserve(h, n + m, m);
+  uint64_t n = 0;
+  rc = mg_current_segments(h, &n);
+  if (rc != HML_OK) return rc;
+  const uint64_t m_upper = h->nblocks;  // a run is at least one block
+  if (n + m_upper >= (1ull << 32)) return fail(h, HML_ERR_CAPACITY, "too many marginal segments for 32-bit indices");
+  rc = mg_reserve(h, n + m_upper, m_upper);
   if (rc != HML_OK) return rc;
   const int cur = h->mg_cur, nxt = cur ^ 1;
-  launch_marginals_merge(h->mg_pos[cur], (uint32_t)n, h->mg_cnt[cur], h->seg_starts, h->seg_states, (uint32_t)m,
-                         h->mg_run_of_old, h->mg_olds_below, h->mg_flags, h->mg_K, h->mg_pos[nxt], h->mg_cnt[nxt], h->sms,
-                         h->stream);
+  const uint64_t ntiles = (h->nblocks + 1023) / 1024;
+  launch_marginals_merge(h->mg_pos[cur], h->mg_n_dev + cur, n, h->mg_cnt[cur], h->seg_starts, h->seg_states,
+                         h->seg_counts + ntiles, m_upper, h->mg_run_of_old, h->mg_olds_below, h->mg_flags, h->mg_K,
+                         h->mg_pos[nxt], h->mg_cnt[nxt], h->mg_n_dev + nxt, h->sms, h->stream);
   h->launches += 3;
   CK(cudaGetLastError());
-  uint32_t added = 0;
-  CK(cudaMemcpyAsync(&added, h->mg_flags + m, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  h->mg_n = n + added;
+  CK(cudaMemcpyAsync(h->mg_n_host, h->mg_n_dev + nxt, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  h->mg_pending = true;
   h->mg_cur = nxt;
   h->mg_iterations++;
   return HML_OK;
 }
 
-int hml_marginals_info(const hml_t* h, uint64_t* nsegments, uint64_t* iterations, int* K) {
+int hml_marginals_info(hml_t* h, uint64_t* nsegments, uint64_t* iterations, int* K) {
   if (!h) return HML_ERR_ARG;
-  if (nsegments) *nsegments = h->mg_n;
+  if (nsegments) {
+    CK(cudaSetDevice(h->device));
+    int rc = mg_current_segments(h, nsegments);
+    if (rc != HML_OK) return rc;
+  }
   if (iterations) *iterations = h->mg_iterations;
   if (K) *K = h->mg_K;
   return HML_OK;
@@ -1612,9 +1655,11 @@ int hml_marginals_info(const hml_t* h, uint64_t* nsegments, uint64_t* iterations
 int hml_marginals_get(hml_t* h, uint64_t* seg_size, int32_t* counts, uint64_t capacity) {
   if (!h || !seg_size || !counts) return HML_ERR_ARG;
   if (h->mg_K == 0) return fail(h, HML_ERR_STATE, "hml_marginals_reset has not been called");
-  if (capacity < h->mg_n) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of marginal segments");
   CK(cudaSetDevice(h->device));
-  const uint64_t n = h->mg_n;
+  uint64_t n = 0;
+  int rc0 = mg_current_segments(h, &n);
+  if (rc0 != HML_OK) return rc0;
+  if (capacity < n) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of marginal segments");
   const int K = h->mg_K;
   std::vector<uint32_t> pos(n);
   std::vector<uint16_t> cnt(n * (size_t)K);

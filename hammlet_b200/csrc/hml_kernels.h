@@ -184,9 +184,12 @@ void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const uint32
                            int16_t* seg_state, int sms, cudaStream_t s);
 // State marginals on the device: merges the run starts R[m] / run states of one recorded iteration into the
 // refinement (P[n], cnt[n x K]) -> (P2, cnt2) with new_flags[m] = number of new boundaries (3 launches).
-void launch_marginals_merge(const uint32_t* P, uint32_t n, const uint16_t* cnt, const uint32_t* R, const int16_t* rstate,
-                            uint32_t m, uint32_t* run_of_old, uint32_t* olds_below, uint32_t* new_flags, int K,
-                            uint32_t* P2, uint16_t* cnt2, int sms, cudaStream_t s);
+// The segment count n and the run count m are read from device memory (*n_ptr, *m_ptr), the new segment count is
+// written to *n_out; n_upper / m_upper only size the grid.
+void launch_marginals_merge(const uint32_t* P, const uint32_t* n_ptr, uint64_t n_upper, const uint16_t* cnt, const uint32_t* R,
+                            const int16_t* rstate, const uint32_t* m_ptr, uint64_t m_upper, uint32_t* run_of_old,
+                            uint32_t* olds_below, uint32_t* new_flags, int K, uint32_t* P2, uint16_t* cnt2, uint32_t* n_out,
+                            int sms, cudaStream_t s);
 // Only block sums (no model): gather statistics for the current starts.
 void launch_block_stats(const SweepBuffers& b, int KP, uint64_t nblocks_hint, int sms, cudaStream_t s);
 

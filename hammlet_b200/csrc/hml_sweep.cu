@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(1024) k_seg_count(const uint8_t* __restrict__ 
 
 // in-place exclusive scan of tile_counts[0..ntiles) by one CTA; tile_counts[ntiles] receives the total.
 // Eight consecutive elements per thread and trip (8192 per trip): the marginal merge scans ~1.6e5 flags with it.
-__global__ void __launch_bounds__(1024) k_seg_scan(uint32_t* tile_counts, uint32_t ntiles) {
+__device__ __forceinline__ void seg_scan_body(uint32_t* tile_counts, uint32_t ntiles) {
   constexpr int V = 8;
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_running;
@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(1024) k_seg_scan(uint32_t* tile_counts, uint32
     __syncthreads();
   }
   if (threadIdx.x == 0) tile_counts[ntiles] = s_running;
+}
+__global__ void __launch_bounds__(1024) k_seg_scan(uint32_t* tile_counts, uint32_t ntiles) { seg_scan_body(tile_counts, ntiles); }
+// the same with the length read from device memory (the host does not know the number of runs of a recorded sweep)
+__global__ void __launch_bounds__(1024) k_seg_scan_dev(uint32_t* tile_counts, const uint32_t* __restrict__ n_ptr) {
+  seg_scan_body(tile_counts, *n_ptr);
 }
 
 __global__ void __launch_bounds__(1024) k_seg_write(const uint8_t* __restrict__ states, const uint32_t* __restrict__ starts,
@@ -173,9 +178,11 @@ __device__ __forceinline__ uint32_t mg_upper_bound(const uint32_t* a, uint32_t n
   return lo;
 }
 
-__global__ void __launch_bounds__(256) k_mg_rank(const uint32_t* __restrict__ P, uint32_t n, const uint32_t* __restrict__ R,
-                                                 uint32_t m, uint32_t* __restrict__ run_of_old,
-                                                 uint32_t* __restrict__ olds_below, uint32_t* __restrict__ is_new) {
+__global__ void __launch_bounds__(256) k_mg_rank(const uint32_t* __restrict__ P, const uint32_t* __restrict__ n_ptr,
+                                                 const uint32_t* __restrict__ R, const uint32_t* __restrict__ m_ptr,
+                                                 uint32_t* __restrict__ run_of_old, uint32_t* __restrict__ olds_below,
+                                                 uint32_t* __restrict__ is_new) {
+  const uint32_t n = *n_ptr, m = *m_ptr;  // segments so far, runs of this iteration (device-side counts)
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n + m; k += gridDim.x * blockDim.x) {
     if (k < n) {
       run_of_old[k] = mg_upper_bound(R, m, P[k]) - 1;
@@ -188,11 +195,14 @@ __global__ void __launch_bounds__(256) k_mg_rank(const uint32_t* __restrict__ P,
   }
 }
 
-__global__ void __launch_bounds__(256) k_mg_write(const uint32_t* __restrict__ P, uint32_t n, const uint16_t* __restrict__ cnt,
-                                                  const uint32_t* __restrict__ R, const int16_t* __restrict__ rstate, uint32_t m,
+__global__ void __launch_bounds__(256) k_mg_write(const uint32_t* __restrict__ P, const uint32_t* __restrict__ n_ptr,
+                                                  const uint16_t* __restrict__ cnt, const uint32_t* __restrict__ R,
+                                                  const int16_t* __restrict__ rstate, const uint32_t* __restrict__ m_ptr,
                                                   const uint32_t* __restrict__ run_of_old, const uint32_t* __restrict__ olds_below,
                                                   const uint32_t* __restrict__ new_before, int K, uint32_t* __restrict__ P2,
-                                                  uint16_t* __restrict__ cnt2) {
+                                                  uint16_t* __restrict__ cnt2, uint32_t* __restrict__ n_out) {
+  const uint32_t n = *n_ptr, m = *m_ptr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = n + new_before[m];  // segments after this iteration
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n + m; k += gridDim.x * blockDim.x) {
     uint32_t out, parent, pos;
     int state;
@@ -215,16 +225,16 @@ __global__ void __launch_bounds__(256) k_mg_write(const uint32_t* __restrict__ P
   }
 }
 
-void launch_marginals_merge(const uint32_t* P, uint32_t n, const uint16_t* cnt, const uint32_t* R, const int16_t* rstate,
-                            uint32_t m, uint32_t* run_of_old, uint32_t* olds_below, uint32_t* new_flags, int K,
-                            uint32_t* P2, uint16_t* cnt2, int sms, cudaStream_t s) {
-  const uint32_t total = n + m;
-  int g = (int)((total + 255) / 256);
-  if (g > sms * 8) g = sms * 8;
+void launch_marginals_merge(const uint32_t* P, const uint32_t* n_ptr, uint64_t n_upper, const uint16_t* cnt, const uint32_t* R,
+                            const int16_t* rstate, const uint32_t* m_ptr, uint64_t m_upper, uint32_t* run_of_old,
+                            uint32_t* olds_below, uint32_t* new_flags, int K, uint32_t* P2, uint16_t* cnt2, uint32_t* n_out,
+                            int sms, cudaStream_t s) {
+  uint64_t g64 = (n_upper + m_upper + 255) / 256;  // the counts live on the device; the grid is sized from upper bounds
+  int g = (int)(g64 > (uint64_t)sms * 8 ? (uint64_t)sms * 8 : g64);
   if (g < 1) g = 1;
-  k_mg_rank<<<g, 256, 0, s>>>(P, n, R, m, run_of_old, olds_below, new_flags);
-  k_seg_scan<<<1, 1024, 0, s>>>(new_flags, m);  // exclusive, new_flags[m] = number of new boundaries
-  k_mg_write<<<g, 256, 0, s>>>(P, n, cnt, R, rstate, m, run_of_old, olds_below, new_flags, K, P2, cnt2);
+  k_mg_rank<<<g, 256, 0, s>>>(P, n_ptr, R, m_ptr, run_of_old, olds_below, new_flags);
+  k_seg_scan_dev<<<1, 1024, 0, s>>>(new_flags, m_ptr);  // exclusive, new_flags[m] = number of new boundaries
+  k_mg_write<<<g, 256, 0, s>>>(P, n_ptr, cnt, R, rstate, m_ptr, run_of_old, olds_below, new_flags, K, P2, cnt2, n_out);
 }
 
 void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, uint32_t* tile_counts, int sms, cudaStream_t s) {

@@ -163,13 +163,14 @@ int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t*
 /* State marginals accumulated on the device: StateMarginals::addRecord / save (StateMarginals.hpp:51-137,268-310).
  * The structure is the reference's: the common refinement of all recorded segmentations, one count per state and
  * segment (marginal_t = int16, so at most 32767 iterations).  hml_marginals_add merges the equal-state runs of the
- * last sweep into it without leaving the device (three small kernels); only hml_marginals_get moves data to the
+ * last sweep into it without leaving the device and without waiting for it (six small kernels queued on the handle's
+ * stream; the counts they need live in device memory); only hml_marginals_get moves data to the
  * host: seg_size[n] and counts[n * K] (row-major), which printed as `size TAB c_0 TAB ... c_{S-1}` with S = highest
  * recorded label + 1 is the reference's marginals file.  Loading new data or calling hml_marginals_reset starts over.
  * In segment mode the marginals are those of the rank's own positions. */
 int hml_marginals_reset(hml_t* h, int K);
 int hml_marginals_add(hml_t* h);
-int hml_marginals_info(const hml_t* h, uint64_t* nsegments, uint64_t* iterations, int* K);
+int hml_marginals_info(hml_t* h, uint64_t* nsegments, uint64_t* iterations, int* K);
 int hml_marginals_get(hml_t* h, uint64_t* seg_size, int32_t* counts, uint64_t capacity);
 /* Parity/debug: forward rows of the last HML_SWEEP_KEEP_ROWS sweep, (nblocks+1) x K, as the
  * backward pass finds them (row 0 = pi; rows < nblocks carry the self-transition rescale of
