@@ -1,0 +1,45 @@
+"""bench.py's output contract: the keys of the JSON line (checked on the committed line of the final tree, which a GPU
+box produced) and the reference arm, which needs no GPU and is run here on a small sample."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    path = os.path.join(ROOT, "profiles", "r1v_bench_line_final_tree.json")
+    d = json.load(open(path))
+    assert BASE_KEYS <= set(d)
+    assert {"gpu_launches", "clocks", "roofline"} <= set(d)
+    assert d["unit"] == "sweeps/s" and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["gpu_launches"] >= d["steps"] * 10
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert abs(d["value"] - d["n_gpus"] * 1000.0 / d["ms_per_step"]) / d["value"] < 1e-6
+
+
+def test_reference_arm_runs_without_a_gpu():
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/ref_probe not built")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--T", "1e6", "--sample", "1e6",
+                        "--steps", "5", "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.strip().split("\n") if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
