@@ -4,17 +4,25 @@
   python bench.py --gpus N --steps K --warmup W            (ours; torchrun launches N ranks for N > 1)
   python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's own CPU path, rank 0)
 
-Workload (config.workload): BASELINE.json configs[3] at one GPU — a single 1e9-observation synthetic
-piecewise-constant Gaussian sequence, K = 5, dynamic wavelet blocks, FBG, self transitions on, no
-recording.  A step is one full Gibbs sweep (HMM.hpp:99-121): threshold from the current theta, boundary
-detection over all T weights, block statistics, forward filter, backward sampling, reductions on the
-device; conjugate updates and parameter draws on the host.  At N > 1 every rank runs its own sequence
-(independent sequences, no collective), i.e. weak scaling.
+Workload (config.workload): BASELINE.json configs[3] — a single 1e9-observation synthetic piecewise-constant
+Gaussian sequence, K = 5, dynamic wavelet blocks, FBG, self transitions on, no recording.  It fits one B200, so it
+is the N = 1 workload too.  A step is one full Gibbs sweep (HMM.hpp:99-121): threshold from the current theta,
+boundaries from the candidate list (the positions whose weight can reach the threshold: 8 bytes per candidate instead
+of 4 bytes per observation), block statistics from the integral arrays, emission terms, forward
+filter, backward sampling and reductions on the device; conjugate updates and parameter draws in the C++ host chain.
+At N > 1 the SAME sequence is split into N contiguous segments, one per GPU, and the scan carries travel over NVLink
+peer memory: the total work is fixed, i.e. strong scaling (`--mode independent` runs one sequence per GPU instead:
+weak scaling, no collective).
 
-One JSON line on stdout (rank 0).  `value` is timed with CUDA events on the stream the kernels run on;
-`e2e` is wall clock through the same public call with host buffers in and out; `roofline` is the
-boundary-detection kernel (the 4 B/observation HBM stream), timed live by CUDA events per launch;
-`cpu_baseline` is the reference's own sampleHMM on the box's host cores on a bounded sample.
+One JSON line on stdout (rank 0).  `value` is timed with CUDA events on the stream the kernels run on; `e2e` is wall
+clock through the same public call with host buffers in and out; `roofline` describes the per-sweep kernel with the
+largest live CUDA-event time (algorithmic bytes of DESIGN.md §4 over its mean launch duration; `traffic` from the
+ncu capture under profiles/, null when that capture predates the kernel sources of this tree); `invariants_ok` says
+that the last timed sweep's counts sum to T; `stream_detect` / `pyramid_detect` time the weight-reading formulations
+of boundary detection on the same data; `cpu_baseline` is the reference's own sampleHMM on the box's host cores on a
+bounded sample.  The reference arm runs that same code on the first --ref-sample observations and scales by the
+sample share (`extrapolated`, `sample_T` say so at the top level; profiles/r2_reference_linearity*.json pins the
+extrapolation against a measured full-size run).
 """
 import argparse
 import json
@@ -182,9 +190,21 @@ def reference_sweeps(x_sample, K, burn, timed, reps, method="F"):
     """The reference's own sampleHMM (compiled from its sources into oracle/_ref/ref_probe) on a host sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refprobe
-    r = refprobe.run("bench", x_sample, K=K, seed=1, burn=burn, timed=timed, reps=reps, method=method)
+    r = refprobe.run("bench", x_sample, K=K, seed=1, burn=burn, timed=timed, reps=reps, method=method, raw32=True)
     secs = r["bench_secs"]
     return timed / float(np.min(secs)), int(r["bench_blocks"][0]), [float(s) for s in secs]
+
+
+def kernel_sources_hash():
+    """sha256 over the CUDA sources of the tree (hammlet_b200/csrc, sorted by name): what an ncu capture belongs to."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "hammlet_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()
 
 
 def cpu_model():
@@ -210,7 +230,9 @@ def main():
     ap.add_argument("--T", type=float, default=1e9)
     ap.add_argument("--K", type=int, default=5)
     ap.add_argument("--L", type=int, default=5000)
-    ap.add_argument("--sample", type=float, default=3e7, help="observations of the CPU reference sample")
+    ap.add_argument("--sample", type=float, default=3e7, help="observations of the cpu_baseline sample (our arm)")
+    ap.add_argument("--ref-sample", type=float, default=1e8,
+                    help="observations the reference arm sweeps (>= T: the whole workload, ~15 min and ~25 GB at 1e9)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="segments", choices=["segments", "independent"],
                     help="N > 1: one sequence split into contiguous segments with NCCL carry exchange (strong scaling, "
@@ -230,24 +252,36 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        Ts = int(min(args.sample, T))
+        Ts = int(min(args.ref_sample, T))
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         x = generate(torch, T, K, L, seed=4, device=dev, limit=Ts).cpu().numpy()
         burn = 100
         sps, nb, secs = reference_sweeps(x, K, burn=burn, timed=steps, reps=max(1, warmup // 3))
         scaled = sps * Ts / T
+        pinned = None
+        try:  # the one-off full-size run that pins the extrapolation (tools/reference_linearity.py)
+            with open(os.path.join(ROOT, "profiles", "r2_reference_linearity.json")) as f:
+                doc = json.load(f)
+            pinned = {"measured_full_config_sweeps_per_s": doc.get("measured_full_config_sweeps_per_s"),
+                      "extrapolated_over_measured": doc.get("extrapolated_over_measured"), "host": doc.get("host"),
+                      "file": "profiles/r2_reference_linearity.json"}
+        except (OSError, ValueError):
+            pass
         line = {
             "impl": "reference", "metric": METRIC, "value": scaled, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": 1000.0 / scaled, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": 1000.0 / scaled, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "extrapolated": Ts < T, "sample_T": Ts, "same_config": Ts == T, "measured_on_sample_sweeps_per_s": sps,
+            "linearity": pinned,
             "config": {"workload": workload, "states": K, "observations": T},
             "cpu_baseline": {"value": scaled, "unit": UNIT, "cores": 1, "kind": "reference",
                              "sample": f"first {Ts} observations of the workload through the reference's own sampleHMM "
                                        f"(oracle/_ref/ref_probe, g++ -O3, 1 thread — the reference is single-threaded; "
                                        f"host: {cpu_model()}, {os.cpu_count()} cores); {burn} burn-in sweeps, best of "
-                                       f"{len(secs)} x {steps} timed sweeps = {sps:.2f} sweeps/s at {nb} blocks; "
-                                       f"scaled by {Ts}/{T} because the reference's sweep cost is linear in the "
-                                       f"number of blocks (SURVEY.md §6.2)"},
+                                       f"{len(secs)} x {steps} timed sweeps = {sps:.2f} sweeps/s at {nb} blocks"
+                                       + (f"; scaled by {Ts}/{T} because the reference's sweep cost is linear in the "
+                                          f"number of blocks (SURVEY.md §6.2; measured against a full-size run in "
+                                          f"profiles/r2_reference_linearity.json)" if Ts < T else "; the whole workload")},
             "e2e": {"value": scaled, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line), file=json_out, flush=True)
@@ -325,6 +359,12 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = h.launch_count() - launches0
+    # invariants of the last timed sweep (ForwardBackward.hpp:177-200): every observation is counted once in the
+    # occupancy, once as a transition target (the phantom 0 -> q0 included) and once in a parameter's term count
+    last = chain.last_sweep()
+    _, cands_now = h.detect_info()
+    inv = {"T": T, "sum_trans": int(last["trans"].sum()), "sum_counts": int(last["counts"].sum()),
+           "sum_stat_n": int(last["stat_n"].sum()), "nblocks": int(last["nblocks"]), "candidates_this_rank": int(cands_now)}
 
     # ---- timed region 2: end to end (wall clock around the public call; host buffers in and out every sweep)
     barrier()
@@ -388,6 +428,21 @@ def main():
         t = torch.tensor([dev_ms, wall * 1000.0], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall = float(t[0].item()), float(t[1].item()) / 1000.0
+        invs = allgather(inv)
+    else:
+        invs = [inv]
+    if segments:   # one sequence: every rank reports the global statistics, and they must be the same ones
+        same = all(v == invs[0] or {k: v[k] for k in v if k != "candidates_this_rank"} ==
+                   {k: invs[0][k] for k in invs[0] if k != "candidates_this_rank"} for v in invs)
+        cand_total = sum(v["candidates_this_rank"] for v in invs)
+        invariants_ok = bool(same and inv["sum_trans"] == T and inv["sum_counts"] == T and inv["sum_stat_n"] == T
+                             and 0 < inv["nblocks"] <= cand_total)
+        inv_doc = dict(invs[0], ranks_agree=same, candidates_total=cand_total)
+    else:          # one sequence per rank: each checks its own
+        invariants_ok = all(v["sum_trans"] == T and v["sum_counts"] == T and v["sum_stat_n"] == T
+                            and 0 < v["nblocks"] <= v["candidates_this_rank"] for v in invs)
+        inv_doc = dict(invs[0], ranks_checked=len(invs), candidates_total=invs[0]["candidates_this_rank"])
+    inv_doc.pop("candidates_this_rank", None)
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -436,18 +491,28 @@ def main():
         wl = f"{world} independent sequences, one per GPU, each: " + workload
 
     # DRAM bytes of one launch of the roofline kernel from an `ncu --set full` capture of this workload (profiles/)
-    traffic = None
+    # The capture is stamped with a hash of the kernel sources it was taken from (tools/ncu_traffic.py): a capture that
+    # predates the current kernels is reported as stale and `traffic` stays null.
+    traffic, traffic_note = None, "no capture under profiles/ for this kernel and workload"
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            rec = json.load(f).get("k_" + top)
+            doc = json.load(f)
+        rec = doc.get("k_" + top)
         if rec and int(rec["T"]) == T_local and int(rec["K"]) == K:
-            traffic = float(rec["dram_bytes_per_launch"])
+            if doc.get("_kernel_sources_sha256") == kernel_sources_hash():
+                traffic = float(rec["dram_bytes_per_launch"])
+                traffic_note = f"ncu --set full capture of git {doc.get('_git_head', '?')} (same kernel sources as this tree)"
+            else:
+                traffic_note = f"stale: the capture of git {doc.get('_git_head', '?')} predates the kernel sources of this tree"
     except (OSError, ValueError, KeyError):
         pass
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if segments else "weak",
+        "ms_per_step": ms_per_step, "higher_is_better": True,
+        # N ranks split ONE sequence (total work fixed): strong scaling, also the label of the N = 1 point of that curve
+        "scaling": "weak" if (world > 1 and not segments) or args.mode == "independent" else "strong",
+        "invariants_ok": invariants_ok, "invariants": inv_doc,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl, "mode": "segments" if segments else ("independent" if world > 1 else "single"),
                    "states": K, "observations": T, "observations_per_gpu": T_local, "blocks_per_sweep": B,
@@ -463,7 +528,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_" + top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": det,
                      "sweep_bytes": 4.0 * T + B * (4 + 16 + 16 * K + 2),
                      "sweep_frac_of_hbm_roofline": (4.0 * T + B * (4 + 16 + 16 * K + 2)) / (world if segments else 1)

@@ -52,7 +52,7 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            # include/hammlet_host.h
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
-           "hammlet_chain_save_marginals", "hammlet_chains_run"]
+           "hammlet_chain_save_marginals", "hammlet_chains_run", "hammlet_chain_last_sweep"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -374,6 +374,14 @@ class Chain:
         self._ck(self.lib.hammlet_chain_run(self.c, C.c_char(method.encode()), C.c_uint64(iterations), C.c_int(int(dynamic)),
                                             C.c_int(int(use_self)), C.byref(nb)))
         return nb.value
+
+    def last_sweep(self):
+        """Integer statistics of the chain's most recent sweep -> dict(nblocks, counts[K], trans[K, K], stat_n[K])."""
+        K = self.K
+        nb = C.c_uint64()
+        counts, trans, stat_n = np.zeros(K, np.uint64), np.zeros(K * K, np.uint64), np.zeros(K, np.uint64)
+        self._ck(self.lib.hammlet_chain_last_sweep(self.c, C.byref(nb), _ptr(counts), _ptr(trans), _ptr(stat_n)))
+        return {"nblocks": nb.value, "counts": counts, "trans": trans.reshape(K, K), "stat_n": stat_n}
 
     def run_recorded(self, iterations, thinning=1, method="F", dynamic=True, use_self=True):
         """sampleHMM with recording: every `thinning`-th sweep joins the state marginals.  -> (blocks of the last

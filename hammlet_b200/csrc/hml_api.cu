@@ -1,5 +1,6 @@
 // hammlet_b200 — C ABI (include/hammlet_b200.h): context, load orchestration, sweeps, getters.
 #include <dlfcn.h>
+#include <float.h>
 #include <math.h>
 #include <nccl.h>  // types only: the library is loaded with dlopen in hml_comm_init (single-GPU use needs no NCCL)
 #include <stdio.h>
@@ -94,6 +95,7 @@ struct hml_ctx {
   uint64_t cand_cap = 0, cand_n = 0;
   uint32_t cand_scratch_ctas = 0;
   float cand_floor = 0.f;
+  float cand_too_long_floor = -1.f;  // largest floor whose candidate list was not worth keeping (> T / 8 entries)
   bool cand_valid = false;
   uint64_t cand_rebuilds = 0;
   float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
@@ -185,6 +187,19 @@ void dev_free(P*& p) {
   if (p) cudaFree(p);
   p = nullptr;
 }
+// device temporary of a load / getter: freed on every way out of the function (a CK() early return included)
+template <typename P>
+struct DevTmp {
+  P* p = nullptr;
+  DevTmp() = default;
+  DevTmp(const DevTmp&) = delete;
+  DevTmp& operator=(const DevTmp&) = delete;
+  ~DevTmp() { release(); }
+  cudaError_t alloc(size_t n) { return dev_alloc(p, n); }
+  void release() { dev_free(p); }
+  operator P*() const { return p; }
+  P* operator+(size_t i) const { return p + i; }
+};
 
 void stage_cb(void* user, const char* name) {
   hml_t* h = (hml_t*)user;
@@ -382,7 +397,14 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP);
 // Candidate list for thresholds >= floor: one pyramid pass at the floor gives the positions (it is the block list of
 // that threshold), a gather their weights.  Grows the block arrays if the list does not fit (local to this rank; no
 // collective has been issued yet at this point of a sweep).
-int rebuild_candidates(hml_t* h, float floor) {
+// A list that is not much shorter than the sequence is not worth having (a tiny threshold makes every position a
+// candidate): *usable = false then, the floor is remembered so the pass is not repeated sweep after sweep, and the
+// caller takes the pyramid pass at the threshold itself.  The block arrays are never grown beyond T / kCandMaxShare
+// on behalf of the list.
+constexpr uint64_t kCandMaxShare = 8;
+int rebuild_candidates(hml_t* h, float floor, bool* usable) {
+  *usable = false;
+  const uint64_t limit = h->T / kCandMaxShare;
   for (int attempt = 0; attempt < 8; ++attempt) {
     h->launches += launch_detect(h->w, h->smax, h->T, floor, h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity,
                                  h->outblk, h->stream, nullptr, nullptr);
@@ -390,6 +412,11 @@ int rebuild_candidates(hml_t* h, float floor) {
     CK(cudaMemcpyAsync(h->outblk_host, h->outblk, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     const uint64_t n = h->outblk_host[0];
+    if (n > limit && n > (1u << 16)) {
+      h->cand_valid = false;
+      h->cand_too_long_floor = floor;
+      return HML_OK;
+    }
     if (n > h->capacity) {
       int rc = alloc_blocks(h, n + n / 4, h->KP);
       if (rc != HML_OK) return rc;
@@ -413,6 +440,7 @@ int rebuild_candidates(hml_t* h, float floor) {
     h->cand_floor = floor;
     h->cand_valid = true;
     h->cand_rebuilds++;
+    *usable = true;
     return HML_OK;
   }
   return fail(h, HML_ERR_CAPACITY, "block capacity did not converge");
@@ -420,15 +448,22 @@ int rebuild_candidates(hml_t* h, float floor) {
 
 int run_detect(hml_t* h, float thr) {
   bool done = false;
-  if (h->detect_mode == HML_DETECT_CANDIDATES && thr > 0.f && isfinite(thr)) {
+  // the block structure is being overwritten: whatever the previous sweep left (states, runs, rows) no longer
+  // belongs to it, also if this sweep fails half-way
+  h->states_valid = h->segs_valid = h->rows_valid = false;
+  const float floor = 0.75f * thr;
+  // candidate mode needs a floor that is a normal float (a denormal or zero floor selects every position) and that is
+  // well above the last floor whose list came out about as long as the sequence
+  if (h->detect_mode == HML_DETECT_CANDIDATES && thr > 0.f && isfinite(thr) && floor >= FLT_MIN &&
+      !(floor <= 1.25f * h->cand_too_long_floor)) {
     // usable: every boundary of thr is a candidate; worth keeping: the list is not much longer than the block list
     bool usable = h->cand_valid && thr >= h->cand_floor;
-    if (usable && h->blocks_valid && h->cand_n > 4 * h->nblocks + 65536 && 0.75f * thr > 1.05f * h->cand_floor) usable = false;
+    if (usable && h->blocks_valid && h->cand_n > 4 * h->nblocks + 65536 && floor > 1.05f * h->cand_floor) usable = false;
     if (!usable) {
-      int rc = rebuild_candidates(h, 0.75f * thr);
+      int rc = rebuild_candidates(h, floor, &usable);
       if (rc != HML_OK) return rc;
     }
-    if (h->cand_n > 0) {
+    if (usable && h->cand_n > 0) {
       h->launches += launch_detect_candidates(h->cand_w, h->cand_pos, (uint32_t)h->cand_n, thr, h->cand_scratch,
                                               h->cand_scratch_ctas, h->starts, h->capacity, h->T, h->outblk, h->stream,
                                               stage_cb, h);
@@ -469,6 +504,7 @@ void load_reset(hml_t* h) {
   h->pq_stride = h->cell_stride = 0;
   h->cand_valid = false;
   h->cand_n = 0;
+  h->cand_too_long_floor = -1.f;
   h->mg_K = 0;  // marginals belong to the sequence that was loaded
   h->mg_n = h->mg_iterations = 0;
   h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
@@ -491,14 +527,13 @@ void load_norms(hml_t* h) {
 // sum of the odd-index coefficients of c[0..n) (main.cpp:303-311), fp64 partials summed on the host
 int load_sum_odd(hml_t* h, const float* c, uint64_t n, double* out) {
   const int nb = 512;
-  double* part = nullptr;
-  CK(dev_alloc(part, nb));
+  DevTmp<double> part;
+  CK(part.alloc(nb));
   launch_sum_odd(c, n, part, nb, h->stream);
   h->launches++;
   std::vector<double> hp(nb);
   CK(cudaMemcpyAsync(hp.data(), part, nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  dev_free(part);
   long double s = 0;
   for (double v : hp) s += v;
   *out = (double)s;
@@ -517,8 +552,8 @@ int load_integral(hml_t* h, const float* x_dev, uint64_t T, int dim = 0, int dim
   }
   double2* const pq = h->pq + (size_t)dim * h->pq_stride;
   double4* const cell_pref = h->cell_pref + (size_t)dim * h->cell_stride;
-  double2* cell_tot = nullptr;
-  CK(dev_alloc(cell_tot, cells));
+  DevTmp<double2> cell_tot;
+  CK(cell_tot.alloc(cells));
   launch_integral_cells(x_dev, T, pq, cell_tot, h->stream);
   h->launches++;
   CK(cudaGetLastError());
@@ -546,7 +581,6 @@ int load_integral(hml_t* h, const float* x_dev, uint64_t T, int dim = 0, int dim
   }
   CK(cudaMemcpyAsync(cell_pref, pref.data(), (cells + 1) * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  dev_free(cell_tot);
   return HML_OK;
 }
 
@@ -562,8 +596,10 @@ int load_finish(hml_t* h, uint64_t T) {
   uint64_t cap = T / 64;
   if (cap < (1u << 16)) cap = 1u << 16;
   if (cap > T) cap = T;
+  // capacity = 0 makes alloc_blocks reallocate everything, the K-sized per-sweep buffers of an earlier sequence
+  // included (h->KP is kept: a sweep with the same K must not find them at the old capacity)
   h->capacity = 0;
-  int rc = alloc_blocks(h, cap, 0);
+  int rc = alloc_blocks(h, cap, h->KP);
   if (rc != HML_OK) return rc;
   CK(cudaStreamSynchronize(h->stream));
   return HML_OK;
@@ -598,17 +634,17 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult, int D = 1)
 
   // ---- maxlet coefficients, 12 levels per pass
   CK(dev_alloc(h->coeffs, tiles * kTile));
-  float* sums[2] = {nullptr, nullptr};
-  CK(dev_alloc(sums[0], tiles + 1));
-  CK(dev_alloc(sums[1], tiles / kTile + 2));
+  DevTmp<float> sum0, sum1, plane, cdim;  // plane, cdim: multivariate input, one dimension at a time
+  CK(sum0.alloc(tiles + 1));
+  CK(sum1.alloc(tiles / kTile + 2));
+  float* sums[2] = {sum0, sum1};
   int rc = HML_OK;
-  float *plane = nullptr, *cdim = nullptr;  // multivariate: one dimension at a time
   if (D == 1) {
     rc = load_upper_passes(h, x_dev, T, T, 1, 0, h->coeffs, sums);
     if (rc != HML_OK) return rc;
   } else {
-    CK(dev_alloc(plane, T));
-    CK(dev_alloc(cdim, tiles * kTile));
+    CK(plane.alloc(T));
+    CK(cdim.alloc(tiles * kTile));
     for (int d = 0; d < D; ++d) {
       launch_deinterleave(x_dev, T, D, d, plane, h->sms, h->stream);
       h->launches++;
@@ -622,7 +658,7 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult, int D = 1)
       rc = load_integral(h, plane, T, d, D);
       if (rc != HML_OK) return rc;
     }
-    dev_free(cdim);
+    cdim.release();
   }
   const float inf = INFINITY;
   CK(cudaMemcpyAsync(h->coeffs, &inf, sizeof(float), cudaMemcpyHostToDevice, h->stream));  // wavelet.hpp:183
@@ -648,9 +684,9 @@ int load_common(hml_t* h, const float* x_dev, uint64_t T, float mult, int D = 1)
     rc = load_integral(h, x_dev, T);
     if (rc != HML_OK) return rc;
   }
-  dev_free(plane);
-  dev_free(sums[0]);
-  dev_free(sums[1]);
+  plane.release();
+  sum0.release();
+  sum1.release();
   if (T > (1ull << 26)) dev_free(h->coeffs);  // 4 B/observation is not worth keeping for big inputs
   rc = load_finish(h, T);
   h->T_global = T;
@@ -690,9 +726,9 @@ int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, 
 
   // ---- pass 0 on the local observations
   CK(dev_alloc(h->coeffs, tiles * kTile));
-  float *send = nullptr, *recv = nullptr, *gsum = nullptr, *ctop = nullptr;
-  CK(dev_alloc(send, slot));
-  CK(dev_alloc(recv, slot * world));
+  DevTmp<float> send, recv, gsum, ctop, sum0, sum1;
+  CK(send.alloc(slot));
+  CK(recv.alloc(slot * world));
   CK(cudaMemsetAsync(send, 0, slot * sizeof(float), h->stream));
   launch_maxlet_level(x_dev, len, len, 1, 0, h->coeffs, send, h->stream);
   h->launches++;
@@ -703,22 +739,22 @@ int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, 
   if (rc != HML_OK) return rc;
 
   // ---- upper levels from the global tile sums, replicated: ctop[m] = coefficient at position 4096 m
-  CK(dev_alloc(gsum, per * world));
+  CK(gsum.alloc(per * world));
   for (int r = 0; r < world; ++r) {
     const uint64_t t0 = plan_first_tile(tiles_total, world, r), t1 = plan_first_tile(tiles_total, world, r + 1);
     if (t1 > t0)
       CK(cudaMemcpyAsync(gsum + t0, recv + (size_t)r * slot, (t1 - t0) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   }
   const uint64_t top_tiles = (tiles_total + kTile - 1) / kTile;
-  CK(dev_alloc(ctop, top_tiles * kTile));
+  CK(ctop.alloc(top_tiles * kTile));
   {
     std::vector<float> infs(top_tiles * kTile, INFINITY);
     CK(cudaMemcpyAsync(ctop, infs.data(), infs.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
-  float* sums[2] = {nullptr, nullptr};
-  CK(dev_alloc(sums[0], top_tiles + 1));
-  CK(dev_alloc(sums[1], top_tiles / kTile + 2));
+  CK(sum0.alloc(top_tiles + 1));
+  CK(sum1.alloc(top_tiles / kTile + 2));
+  float* sums[2] = {sum0, sum1};
   rc = load_upper_passes(h, gsum, T / kTile, tiles_total, 1, kTileLog2, ctop, sums);
   if (rc != HML_OK) return rc;
 
@@ -727,17 +763,15 @@ int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, 
     double part = 0;
     rc = load_sum_odd(h, h->coeffs, len, &part);
     if (rc != HML_OK) return rc;
-    double *ds = nullptr, *dr = nullptr;
-    CK(dev_alloc(ds, 1));
-    CK(dev_alloc(dr, world));
+    DevTmp<double> ds, dr;
+    CK(ds.alloc(1));
+    CK(dr.alloc(world));
     CK(cudaMemcpyAsync(ds, &part, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     rc = all_gather(h, ds, dr, sizeof(double));
     if (rc != HML_OK) return rc;
     std::vector<double> parts(world);
     CK(cudaMemcpyAsync(parts.data(), dr, world * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    dev_free(ds);
-    dev_free(dr);
     long double s = 0;
     for (double v : parts) s += v;
     const uint64_t n = T / 2;
@@ -754,12 +788,12 @@ int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, 
   rc = load_integral(h, x_dev, len);
   if (rc != HML_OK) return rc;
   CK(cudaStreamSynchronize(h->stream));
-  dev_free(send);
-  dev_free(recv);
-  dev_free(gsum);
-  dev_free(ctop);
-  dev_free(sums[0]);
-  dev_free(sums[1]);
+  send.release();
+  recv.release();
+  gsum.release();
+  ctop.release();
+  sum0.release();
+  sum1.release();
   if (len > (1ull << 26)) dev_free(h->coeffs);
   rc = load_finish(h, len);
   h->T_global = T;
@@ -1045,9 +1079,9 @@ int setup_p2p(hml_t* h) {
   memset(&msg, 0, sizeof(msg));
   msg.handle = mine;
   msg.ok = ok;
-  Msg *dsend = nullptr, *drecv = nullptr;
-  CK(dev_alloc(dsend, 1));
-  CK(dev_alloc(drecv, world));
+  DevTmp<Msg> dsend, drecv;
+  CK(dsend.alloc(1));
+  CK(drecv.alloc(world));
   std::vector<Msg> all(world);
   CK(cudaMemcpyAsync(dsend, &msg, sizeof(Msg), cudaMemcpyHostToDevice, h->stream));
   int rc = all_gather(h, dsend, drecv, sizeof(Msg));
@@ -1079,8 +1113,6 @@ int setup_p2p(hml_t* h) {
   CK(cudaMemcpyAsync(all.data(), drecv, world * sizeof(Msg), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < world; ++r) ok = ok && all[r].ok;
-  dev_free(dsend);
-  dev_free(drecv);
   if (ok) {
     P2PDev dev;
     memset(&dev, 0, sizeof(dev));
@@ -1151,6 +1183,9 @@ int hml_create(hml_t** out, int device) {
   if (cudaMalloc((void**)&h->outblk, kOutWords * 8) != cudaSuccess ||
       cudaMallocHost((void**)&h->outblk_host, kOutWords * 8) != cudaSuccess) {
     g_create_error = "allocation of the result block failed";
+    dev_free(h->outblk);
+    if (h->outblk_host) cudaFreeHost(h->outblk_host);
+    cudaStreamDestroy(h->stream);
     delete h;
     return HML_ERR_CUDA;
   }
@@ -1395,8 +1430,8 @@ int hml_get_block_sums(hml_t* h, uint32_t dim, double* sum, double* sumsq, uint6
   if (capacity < h->nblocks) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of blocks");
   CK(cudaSetDevice(h->device));
   const uint64_t B = h->nblocks;
-  double* tmp = nullptr;
-  CK(dev_alloc(tmp, 2 * B));
+  DevTmp<double> tmp;
+  CK(tmp.alloc(2 * B));
   SweepBuffers b = make_buffers(h, 2);
   b.bS = h->bS + (size_t)dim * h->capacity;
   launch_unpermute(b, 0, B, nullptr, tmp, tmp + B, h->stream);
@@ -1404,7 +1439,6 @@ int hml_get_block_sums(hml_t* h, uint32_t dim, double* sum, double* sumsq, uint6
   CK(cudaMemcpyAsync(sum, tmp, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(sumsq, tmp + B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  dev_free(tmp);
   return HML_OK;
 }
 
@@ -1423,15 +1457,14 @@ int hml_get_blocks(hml_t* h, uint32_t* starts, double* sum, double* sumsq, uint6
   }
   if (sum || sumsq) {
     if (!sum || !sumsq) return fail(h, HML_ERR_ARG, "sum and sumsq must be given together");
-    double* tmp = nullptr;
-    CK(dev_alloc(tmp, 2 * B));
+    DevTmp<double> tmp;
+    CK(tmp.alloc(2 * B));
     SweepBuffers b = make_buffers(h, 2);
     launch_unpermute(b, 0, B, nullptr, tmp, tmp + B, h->stream);
     h->launches++;
     CK(cudaMemcpyAsync(sum, tmp, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(sumsq, tmp + B, B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    dev_free(tmp);
   }
   CK(cudaStreamSynchronize(h->stream));
   return HML_OK;
@@ -1453,14 +1486,13 @@ int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity) {
   if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
   if (capacity < h->nblocks) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of blocks");
   CK(cudaSetDevice(h->device));
-  int16_t* tmp = nullptr;
-  CK(dev_alloc(tmp, h->nblocks));
+  DevTmp<int16_t> tmp;
+  CK(tmp.alloc(h->nblocks));
   SweepBuffers b = make_buffers(h, 2);
   launch_unpermute(b, 0, h->nblocks, tmp, nullptr, nullptr, h->stream);
   h->launches++;
   CK(cudaMemcpyAsync(states, tmp, h->nblocks * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  dev_free(tmp);
   return HML_OK;
 }
 

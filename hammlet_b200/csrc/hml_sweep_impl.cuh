@@ -291,14 +291,35 @@ __device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, 
 #pragma unroll
   for (int k = 0; k < KP; ++k) s += (k < K) ? p[k] : 0.0;
   if (!(s > 0.0)) return 0u;
+  // libstdc++ divides every weight by the sum (__normalize).  Multiplying by the reciprocal is cheaper and gives
+  // partial sums within K * 2^-51 of those; the two can only disagree about `cp[k] >= u` if a partial sum lands that
+  // close to u, and then — about once in 1e11 draws — the draw is repeated with the divisions, so the result is the
+  // reference's for every u.
   const double inv = 1.0 / s;
   double acc = 0.0;
   uint32_t res = (uint32_t)(K - 1);
-  bool found = false;
+  bool found = false, tie = false;
 #pragma unroll
   for (int k = 0; k < KP - 1; ++k) {
     if (k < K - 1) {
       acc += p[k] * inv;
+      tie |= fabs(acc - u) < 1e-12;
+      if (!found && acc >= u) {
+        res = (uint32_t)k;
+        found = true;
+      }
+    }
+  }
+  if (tie) {
+    acc = 0.0;
+    res = (uint32_t)(K - 1);
+    found = false;
+#pragma unroll 1
+    for (int k = 0; k < K - 1; ++k) {
+      double pk = 0.0;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) pk = (j == k) ? p[j] : pk;
+      acc += pk / s;
       if (!found && acc >= u) {
         res = (uint32_t)k;
         found = true;

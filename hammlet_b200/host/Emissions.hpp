@@ -70,6 +70,15 @@ class DeviceSequence {
   }
   // noise estimate from the finest detail coefficients (main.cpp:303-311)
   double noiseStdev() const { return mSigmaHat; }
+
+  // integer statistics of the most recent sweep on this sequence as the sampler received them (ForwardBackward.hpp:
+  // 177-200): callers that only drive whole runs (bench.py) check their invariants — transition counts, occupancy and
+  // per-parameter counts each sum to the sequence length
+  struct LastSweep {
+    uint64_t nblocks = 0;
+    std::vector<uint64_t> counts, trans, statN;
+  };
+  LastSweep lastSweep;
 };
 
 // Reads whitespace-separated numbers with the result of `input >> v` (wavelet.hpp:131), through the

@@ -221,6 +221,10 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
   seq.check(fn(seq.handle(), &model, flags, (float)blocks.threshold(), key, 0, mReplay ? uniforms.data() : nullptr,
                uniforms.size(), &out));
   blocks.markBuilt();
+  seq.lastSweep.nblocks = out.nblocks;
+  seq.lastSweep.counts = counts;
+  seq.lastSweep.trans = trans;
+  seq.lastSweep.statN.assign(statN.begin(), statN.begin() + nrParams);
   for (uint64_t i = 0; i < out.uniform_fallbacks; ++i) std::cout << "[WARNING] Uniform sampling of forward variables!" << std::endl;
   mLogLikelihood = out.loglik;
   if (mKeepTrellis && !kIsMixture) {

@@ -169,6 +169,23 @@ int hammlet_chain_run_recorded(hammlet_chain* c, char method, uint64_t iteration
   }
 }
 
+int hammlet_chain_last_sweep(hammlet_chain* c, uint64_t* nblocks, uint64_t* counts, uint64_t* trans, uint64_t* stat_n) {
+  if (!c) return HML_ERR_ARG;
+  const DeviceSequence::LastSweep& l = c->sequence.lastSweep;
+  if (l.counts.size() != c->K) {
+    c->error = "no sweep has been run on this chain";
+    return HML_ERR_STATE;
+  }
+  if (nblocks) *nblocks = l.nblocks;
+  for (size_t s = 0; s < c->K; ++s) {
+    if (counts) counts[s] = l.counts[s];
+    if (stat_n) stat_n[s] = l.statN[s];
+    if (trans)
+      for (size_t j = 0; j < c->K; ++j) trans[s * c->K + j] = l.trans[s * c->K + j];
+  }
+  return HML_OK;
+}
+
 // Independent sequences: every chain owns its handle, its CUDA stream, its parameters and its RNG,
 // so chains never interact; `threads` host threads each take the next unfinished chain (longest sequence first).
 // A single chain of 1e4-1e5 blocks is a string of latency-bound kernels; several at a time fill the device.

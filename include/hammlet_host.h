@@ -41,6 +41,12 @@ int hammlet_chain_set(hammlet_chain* c, const float* mean, const float* var, con
 int hammlet_chain_run(hammlet_chain* c, char method, uint64_t iterations, int dynamic, int use_self_transitions,
                       uint64_t* nblocks_last);
 
+/* Integer statistics of the chain's most recent sweep as the sampler received them from the device
+ * (ForwardBackward.hpp:177-200): block count, occupancy counts[K], transition counts trans[K*K] (incl. the phantom
+ * 0 -> q0), observations per emission parameter stat_n[K].  Each of the three sums to the sequence length — the
+ * invariant bench.py asserts on the timed run.  Any pointer may be NULL. */
+int hammlet_chain_last_sweep(hammlet_chain* c, uint64_t* nblocks, uint64_t* counts, uint64_t* trans, uint64_t* stat_n);
+
 /* The same with recording (HMM.hpp:104-119): every `thinning`-th sweep (thinning > 0) the sampled state sequence joins
  * the chain's state marginals (Records::record -> StateMarginals::addRecord, Records.hpp:155-235,
  * StateMarginals.hpp:51-137), kept in memory.  The device hands over one (size, state) entry per equal-state run

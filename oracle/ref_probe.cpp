@@ -14,7 +14,9 @@
 //                 replaced by an instrumented double with identical arithmetic that snapshots
 //                 the forward rows before the backward pass overwrites and clears them
 //                 (StateSequence/ForwardBackward.hpp:140-162 mutates, :162 clears).
-//                 tests/test_oracle_vs_ref.py checks that both flavours sample identical states.
+//                 oracle/make_golden.py asserts, for every fixture it writes, that both flavours sample identical
+//                 states and leave identical posteriors; tests/test_oracle_vs_golden.py::test_probe_flavours_agree
+//                 repeats that check wherever oracle/_ref is built.
 //
 // The include order below follows src/main.cpp:2-15; other orders do not compile (circular
 // headers).  Private members are reached with -fno-access-control, so no reference line changes.
@@ -134,6 +136,34 @@ static void dumpI64( const std::string& name, const V& v ) {
 	o.write( ( const char* ) d.data(), d.size() * sizeof( int64_t ) );
 }
 
+// std::streambuf over a raw float32 file that yields the values as text, "%.9g\n" each (9 significant digits
+// round-trip a float), 65536 values per refill
+class TextOfFloats : public std::streambuf {
+		std::ifstream mFile;
+		size_t mCount;
+		std::vector<float> mVals;
+		std::vector<char> mText;
+	public:
+		explicit TextOfFloats( const std::string& path ) : mFile( path, std::ios::binary | std::ios::ate ), mCount( 0 ) {
+			if ( !mFile ) { throw std::runtime_error( "cannot read " + path ); }
+			mCount = ( size_t ) mFile.tellg() / sizeof( float );
+			mFile.seekg( 0 );
+			mVals.resize( 65536 );
+			mText.resize( 65536 * 20 );
+		}
+		size_t count() const { return mCount; }
+	protected:
+		int_type underflow() override {
+			mFile.read( ( char* ) mVals.data(), mVals.size() * sizeof( float ) );
+			const size_t n = ( size_t ) mFile.gcount() / sizeof( float );
+			if ( n == 0 ) { return traits_type::eof(); }
+			size_t len = 0;
+			for ( size_t i = 0; i < n; ++i ) { len += ( size_t ) snprintf( mText.data() + len, 20, "%.9g\n", ( double ) mVals[i] ); }
+			setg( mText.data(), mText.data(), mText.data() + len );
+			return traits_type::to_int_type( *gptr() );
+		}
+};
+
 typedef Statistics<IntegralArray, Normal> S;
 typedef Blocks<BreakpointArray> B;
 typedef Emissions<S, B> Y;
@@ -149,27 +179,37 @@ int main( int argc, const char* argv[] ) {
 		// ---- load: data arrives as raw float64; it is rendered with 17 significant digits so that
 		// the reference's own text front end (wavelet.hpp:131 `input >> v`) recovers exactly the same
 		// real number whether real_t is float or double (inputs are float-representable).
-		std::vector<double> raw;
-		{
-			std::ifstream f( jstr( "data" ), std::ios::binary | std::ios::ate );
-			if ( !f ) { throw std::runtime_error( "cannot read data" ); }
-			size_t bytes = f.tellg();
-			f.seekg( 0 );
-			raw.resize( bytes / sizeof( double ) );
-			f.read( ( char* ) raw.data(), bytes );
-		}
-		std::stringstream text;
-		{
-			char buf[64];
-			for ( double v : raw ) { snprintf( buf, sizeof buf, "%.17g\n", v ); text << buf; }
-		}
 		// multivariate jobs ("dims D"): the data file holds T*D values, position-major (wavelet.hpp:131-136)
 		const size_t nrDataDim = has( "dims" ) ? jint( "dims" ) : 1;
 		std::vector<real_t> inputValues;
 		std::vector<SufficientStatistics<Normal>> stats;
-		MaxletTransform( text, inputValues, stats, nrDataDim, raw.size() + 1 );      // main.cpp:277
+		// "quiet 1" (the bench arm at 1e8..1e9 observations): no dumps of per-observation arrays
+		const bool quiet = has( "quiet" ) && jint( "quiet" ) != 0;
+		if ( has( "data32" ) ) {
+			// large inputs: raw float32 on disk, rendered as text in 64k-value pieces by a stream buffer, so the
+			// reference's text front end still does the parsing but nothing of size T besides its own arrays exists
+			TextOfFloats tb( jstr( "data32" ) );
+			std::istream text( &tb );
+			MaxletTransform( text, inputValues, stats, nrDataDim, tb.count() + 1 );
+		} else {
+			std::vector<double> raw;
+			{
+				std::ifstream f( jstr( "data" ), std::ios::binary | std::ios::ate );
+				if ( !f ) { throw std::runtime_error( "cannot read data" ); }
+				size_t bytes = f.tellg();
+				f.seekg( 0 );
+				raw.resize( bytes / sizeof( double ) );
+				f.read( ( char* ) raw.data(), bytes );
+			}
+			std::stringstream text;
+			{
+				char buf[64];
+				for ( double v : raw ) { snprintf( buf, sizeof buf, "%.17g\n", v ); text << buf; }
+			}
+			MaxletTransform( text, inputValues, stats, nrDataDim, raw.size() + 1 );      // main.cpp:277
+		}
 		const size_t T = inputValues.size();
-		dumpF64( "coeffs", inputValues );
+		if ( !quiet ) { dumpF64( "coeffs", inputValues ); }
 
 		// noise estimate, main.cpp:303-311 (glue inside main(); restated, it is not callable)
 		double stdEstimate = 0;
@@ -182,7 +222,7 @@ int main( int argc, const char* argv[] ) {
 		HaarBreakpointWeights( inputValues );                                            // main.cpp:318
 		const real_t weightMultiplier = has( "wmult" ) ? ( real_t ) jnum( "wmult" ) : ( real_t ) 1;
 		for ( auto& w : inputValues ) { w *= weightMultiplier; }                        // main.cpp:332-334
-		dumpF64( "weights", inputValues );
+		if ( !quiet ) { dumpF64( "weights", inputValues ); }
 		if ( mode == "weights" ) { return 0; }
 
 		S ia( stats, nrDataDim );                                                        // main.cpp:340

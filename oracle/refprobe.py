@@ -38,9 +38,14 @@ def run(mode, data, fp64=False, trellis=False, keep_dir=None, **kw):
         raise FileNotFoundError(exe + " not built (make -C oracle ref)")
     tmp = keep_dir or tempfile.mkdtemp(prefix="refprobe_")
     os.makedirs(tmp, exist_ok=True)
-    data = np.ascontiguousarray(np.asarray(data, dtype=np.float32).astype(np.float64))
-    data.tofile(os.path.join(tmp, "data.f64"))
-    lines = ["mode " + mode, "data " + os.path.join(tmp, "data.f64"), "out " + tmp]
+    if kw.pop("raw32", False):
+        # large inputs (the bench arm): raw float32 on disk, the probe renders it as text piece by piece
+        np.ascontiguousarray(np.asarray(data, dtype=np.float32)).tofile(os.path.join(tmp, "data.f32"))
+        lines = ["mode " + mode, "data32 " + os.path.join(tmp, "data.f32"), "out " + tmp, "quiet 1"]
+    else:
+        data = np.ascontiguousarray(np.asarray(data, dtype=np.float32).astype(np.float64))
+        data.tofile(os.path.join(tmp, "data.f64"))
+        lines = ["mode " + mode, "data " + os.path.join(tmp, "data.f64"), "out " + tmp]
     for k, v in kw.items():
         if v is None:
             continue

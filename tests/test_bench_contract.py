@@ -34,12 +34,32 @@ def test_reference_arm_runs_without_a_gpu():
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
     if not os.path.exists(ref):
         pytest.skip("oracle/_ref/ref_probe not built")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--T", "1e6", "--sample", "1e6",
-                        "--steps", "5", "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=ROOT)
-    assert p.returncode == 0, p.stderr[-2000:]
-    lines = [ln for ln in p.stdout.strip().split("\n") if ln.startswith("{")]
-    assert len(lines) == 1
-    d = json.loads(lines[0])
+    def arm(T, sample):
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--T", T, "--ref-sample",
+                            sample, "--steps", "5", "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert p.returncode == 0, p.stderr[-2000:]
+        lines = [ln for ln in p.stdout.strip().split("\n") if ln.startswith("{")]
+        assert len(lines) == 1
+        return json.loads(lines[0])
+
+    d = arm("1e6", "1e6")
     assert d["impl"] == "reference" and BASE_KEYS <= set(d)
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
+    # the whole workload was swept: a measurement, and the line says so at the top level
+    assert d["extrapolated"] is False and d["same_config"] is True and d["sample_T"] == 1_000_000
+    assert abs(d["value"] - d["measured_on_sample_sweeps_per_s"]) < 1e-9
+    # a sample of the workload: the scaled number is flagged as extrapolated where nobody can miss it
+    e = arm("2e6", "1e6")
+    assert e["extrapolated"] is True and e["same_config"] is False and e["sample_T"] == 1_000_000
+    assert abs(e["value"] - e["measured_on_sample_sweeps_per_s"] * 0.5) < 1e-9
+
+
+def test_traffic_capture_is_bound_to_the_kernel_sources():
+    """profiles/ncu_traffic.json carries the hash of the kernel sources it was captured from; bench.py reports the
+    DRAM traffic only while that hash matches the tree (a stale capture gives traffic = null and says why)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    doc = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    assert len(bench.kernel_sources_hash()) == 64
+    assert "_kernel_sources_sha256" in doc and "_git_head" in doc

@@ -220,6 +220,50 @@ def test_capacity_growth(dev):
     assert np.array_equal(dev.blocks(stats=False).astype(np.uint64), ref)
 
 
+def test_reload_longer_sequence_same_k():
+    """A used handle that loads a longer sequence: the K-sized per-sweep buffers must follow the new block capacity
+    (they were left at the old one while the kernels indexed up to the new one).  T = 1000 gives the smallest
+    capacity (65536 blocks); the second sequence has ~4x that many blocks at the same K."""
+    h = capi.Handle(0)
+    try:
+        mu, var, A, pi = model_guess(5, seed=5)
+        x0 = piecewise_gaussian(1000, 5, 50, seed=1)
+        h.load(x0)
+        _check_fb(h, x0, mu, var, A, pi, 0.8, 1)
+        x1 = piecewise_gaussian(2_000_000, 5, 6, seed=2)
+        h.load(x1)
+        out, ref = _check_fb(h, x1, mu, var, A, pi, 0.3, 1)
+        assert out["nblocks"] > 200_000
+        # and back to a short one
+        h.load(x0)
+        _check_fb(h, x0, mu, var, A, pi, 0.8, 1)
+    finally:
+        h.close()
+
+
+def test_tiny_threshold_takes_the_pyramid_pass():
+    """A threshold whose candidate list would be about as long as the sequence (every weight reaches 0.75 thr): the
+    candidate path stands down instead of growing the block arrays to 1.25 T, and the boundaries are still exact."""
+    h = capi.Handle(0)
+    try:
+        T = 300_000
+        x = piecewise_gaussian(T, 3, 200, seed=9)
+        O32 = oracle.Oracle(False)
+        w = O32.weights(x)
+        h.load(x)
+        for thr in (1e-30, 1e-42, float(np.nextafter(np.float32(0), np.float32(1))), 1e-3):
+            B = h.create_blocks(thr)
+            ref = O32.boundaries(w, thr)
+            assert B == ref.size and np.array_equal(h.blocks(stats=False).astype(np.uint64), ref)
+            mode, looked = h.detect_info()
+            assert mode == capi.DETECT_CANDIDATES
+        # a usable threshold afterwards goes back to the candidate list
+        B = h.create_blocks(0.9)
+        assert B == O32.boundaries(w, 0.9).size and h.detect_info()[1] < T // 8
+    finally:
+        h.close()
+
+
 # ------------------------------------------------------------------------------------------ sweeps
 
 def _check_fb(dev, x, mu, var, A, pi, thr, use_self, seed=123, uniforms=None):

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 import oracle
+import refprobe
 
 QB = 10
 
@@ -162,3 +163,31 @@ def test_nig_update_edge_cases():
     assert O.nig_update([2, 1, 0, 1], 1.0, -1.0, 3)[0] == -1  # negative sum of squares throws
     rc, hp = O.nig_update([2, 1, 0, 1], 3.0, 2.9, 3)          # (sum^2)/N > sumSq is clamped (:152-156)
     assert rc == 0 and hp[1] >= 1.0
+
+
+@pytest.mark.skipif(not (refprobe.available(True, True) and refprobe.available(True, False)),
+                    reason="oracle/_ref not built (needs /root/reference)")
+def test_probe_flavours_agree():
+    """The instrumented Trellis stand-in of ref_probe*_t (oracle/ref_probe.cpp) must not change what the reference
+    samples: same states, same posteriors, same Records files as the probe built on the reference's own Trellis."""
+    from hammlet_b200.synth import model_guess, piecewise_gaussian
+    x = piecewise_gaussian(6000, 3, 80, seed=11)
+    mu, var, A, pi = model_guess(3, seed=3)
+    kw = dict(K=3, seed=5, theta=np.stack([mu, var], 1).ravel(), A=A.ravel(), pi=pi, thr=0.7, self=1, method="F",
+              tau_theta=[2.0, 1.0, 0.0, 1.0], tau_A=[0.5, 0.5], tau_pi=0.5, nsweeps=3, dynamic=1)
+    r = refprobe.run("sweep", x, fp64=True, trellis=True, **kw)
+    r0 = refprobe.run("sweep", x, fp64=True, trellis=False, **kw)
+    for k in ("all_states", "post_theta", "post_A", "post_pi", "drawn", "all_uniforms"):
+        assert np.array_equal(r[k], r0[k]), k
+    assert r["files"] == r0["files"]
+
+
+@pytest.mark.skipif(not refprobe.available(False, False), reason="oracle/_ref not built (needs /root/reference)")
+def test_probe_float32_file_loader_equals_text_loader():
+    """bench.py's reference arm hands ref_probe a raw float32 file (rendered as text piecewise, so a 1e9-observation
+    run needs no T-sized text buffer); the reference must see the same numbers as through the fp64 route."""
+    from hammlet_b200.synth import piecewise_gaussian
+    x = piecewise_gaussian(150_000, 5, 300, seed=3)
+    a = refprobe.run("bench", x, K=5, seed=1, burn=5, timed=3, reps=1, method="F")
+    b = refprobe.run("bench", x, K=5, seed=1, burn=5, timed=3, reps=1, method="F", raw32=True)
+    assert a["bench_blocks"][0] == b["bench_blocks"][0] and a["sigma_hat"][0] == b["sigma_hat"][0]
