@@ -288,7 +288,7 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
-    from hammlet_b200 import capi, gibbs
+    from hammlet_b200 import capi
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: hammlet_b200 has no CPU fallback")
@@ -331,7 +331,8 @@ def main():
 
     # The chain is the C++ host side (include/hammlet_host.h): sampleHMM, conjugate updates and parameter draws
     # in C++ with libstdc++ <random> like the reference; Python only starts and stops the clock.
-    tau = gibbs.auto_prior(h, 0.2, 0.9, allgather=allgather) if segments else capi.Chain.auto_prior(h, 0.2, 0.9)
+    # (auto priors of a split sequence: the C++ side gathers the ranks' block lists, Emissions.hpp Blocks::fetch)
+    tau = capi.Chain.auto_prior(h, 0.2, 0.9)
     # segment mode: every rank draws the same parameters from the same (all-gathered) statistics
     chain = capi.Chain(h, K, tau, trans=0.5, self_trans=0.5, alpha_pi=0.5, seed=100 if segments else 100 + rank)
     # start near the generating model so that the warm-up sweeps reach the stationary compression ratio quickly
@@ -374,22 +375,25 @@ def main():
     wall = time.perf_counter() - w0
 
     # ---- the second number SURVEY.md §8d asks for: thinning 1 — every sweep is recorded into the state marginals
-    # (Records -> device-resident marginals).  Single handle only: a segment-split sequence keeps its runs rank-local.
-    recorded = None
-    if not segments:
-        rec_steps = max(10, steps // 5)
-        chain.run_recorded(max(3, warmup // 4), thinning=1)   # warm-up: first use allocates the run / marginal buffers
-        barrier()
-        r0 = time.perf_counter()
-        _, nseg = chain.run_recorded(rec_steps, thinning=1)
-        torch.cuda.synchronize()
-        rec_wall = time.perf_counter() - r0
-        runs = int(h.segments()[0].size)
-        recorded = {"value": rec_steps / rec_wall * (world if world > 1 else 1), "unit": UNIT, "thinning": 1,
-                    "steps": rec_steps, "runs_last_sweep": runs, "marginal_segments": int(nseg),
-                    "how": "wall clock through hammlet_chain_run_recorded: sweep + equal-state runs formed on the device + "
-                           "merge into the device-resident state marginals (hml_marginals_add: StateMarginals::addRecord "
-                           "as three small kernels; nothing but a 4-byte count returns to the host per sweep)"}
+    # (Records -> device-resident marginals).  A split sequence keeps the marginals of each rank's positions on that
+    # rank (the ranks trade 8 bytes per recorded sweep so that runs continue across borders) and merges them when asked.
+    rec_steps = max(10, steps // 5)
+    chain.run_recorded(max(3, warmup // 4), thinning=1)   # warm-up: first use allocates the run / marginal buffers
+    barrier()
+    r0 = time.perf_counter()
+    _, nseg = chain.run_recorded(rec_steps, thinning=1)
+    torch.cuda.synchronize()
+    rec_wall = time.perf_counter() - r0
+    runs = int(h.segments()[0].size)
+    if dist is not None:
+        t = torch.tensor([rec_wall], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rec_wall = float(t[0].item())
+    recorded = {"value": rec_steps / rec_wall * (world if (world > 1 and not segments) else 1), "unit": UNIT, "thinning": 1,
+                "steps": rec_steps, "runs_last_sweep": runs, "marginal_segments": int(nseg),
+                "how": "wall clock through hammlet_chain_run_recorded: sweep + equal-state runs formed on the device + "
+                       "merge into the device-resident state marginals (hml_marginals_add: StateMarginals::addRecord "
+                       "as three small kernels; nothing but a 4-byte count returns to the host per sweep)"}
 
     # ---- region 3 (not part of `value`): the same steps with per-stage CUDA events, for the roofline and stage table
     h.set_timing(True)

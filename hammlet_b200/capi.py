@@ -52,7 +52,8 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            # include/hammlet_host.h
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
-           "hammlet_chain_save_marginals", "hammlet_chains_run", "hammlet_chain_last_sweep"]
+           "hammlet_chain_save_marginals", "hammlet_chains_run", "hammlet_chain_last_sweep",
+           "hml_comm_allgather"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None

@@ -82,6 +82,16 @@ struct hml_ctx {
   double* seg_dev = nullptr;                    // send slots + gathered carries (one allocation)
   unsigned long long* stats_gather = nullptr;   // world x kOutWords
   unsigned long long* stats_gather_host = nullptr;
+  // run formation across rank borders (recorded sweeps): [0] this rank's last state, [8..8+world) everybody's
+  unsigned long long* run_states = nullptr;
+  uint32_t* run_border = nullptr;               // [0] position 0 started a run in some recorded iteration, [1] in the last
+  // merged (whole-sequence) views, filled by collective getters in segment mode
+  bool g_valid = false;                         // g_seg_* hold the runs of the current states
+  std::vector<uint64_t> g_seg_size;
+  std::vector<int16_t> g_seg_state;
+  bool g_mg_valid = false;                      // g_mg_* hold the merged marginals as of the last hml_marginals_add
+  std::vector<uint64_t> g_mg_size;
+  std::vector<int32_t> g_mg_counts;
 
   // sequence (resident since load); in segment mode T is the length of the local segment
   uint64_t T = 0;
@@ -243,7 +253,7 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
     CK(dev_alloc(h->states, cap));
     CK(dev_alloc(h->tile_qin, tiles));
     h->blocks_valid = h->stats_valid = h->states_valid = h->rows_valid = false;
-    h->segs_valid = false;
+    h->segs_valid = h->g_valid = false;
     dev_free(h->rows);
     h->rows_cap = 0;
   }
@@ -450,7 +460,7 @@ int run_detect(hml_t* h, float thr) {
   bool done = false;
   // the block structure is being overwritten: whatever the previous sweep left (states, runs, rows) no longer
   // belongs to it, also if this sweep fails half-way
-  h->states_valid = h->segs_valid = h->rows_valid = false;
+  h->states_valid = h->segs_valid = h->g_valid = h->rows_valid = false;
   const float floor = 0.75f * thr;
   // candidate mode needs a floor that is a normal float (a denormal or zero floor selects every position) and that is
   // well above the last floor whose list came out about as long as the sequence
@@ -1040,7 +1050,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
       }
     }
     h->states_valid = true;
-    h->segs_valid = false;
+    h->segs_valid = h->g_valid = false;
     h->rows_valid = (flags & HML_SWEEP_KEEP_ROWS) != 0 && !mixture;
     h->last_K = mh.K;
     return HML_OK;
@@ -1248,6 +1258,8 @@ int hml_destroy(hml_t* h) {
   dev_free(h->outblk);
   dev_free(h->seg_dev);
   dev_free(h->stats_gather);
+  dev_free(h->run_states);
+  dev_free(h->run_border);
   teardown_p2p(h);
   if (h->stats_gather_host) cudaFreeHost(h->stats_gather_host);
   if (h->comm) g_nccl.CommDestroy(h->comm);
@@ -1500,19 +1512,28 @@ int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity) {
 // changes): h->nsegs runs; with `write` their (start, state) pairs are left in h->seg_starts / h->seg_states.
 // need_count: the host wants to know the number of runs (one small copy + synchronisation); the marginal merge does
 // not — its kernels read the count from device memory (seg_counts[ntiles]).
-static int ensure_runs(hml_t* h, bool write, bool need_count = true) {
+static int ensure_runs(hml_t* h, bool write, bool need_count = true, bool accumulate = false) {
   const uint64_t B = h->nblocks;
-  const uint64_t ntiles = (B + 1023) / 1024;
+  const bool seg = h->world > 1;
+  uint64_t ntiles = (B + 1023) / 1024;
+  if (seg && ntiles == 0) ntiles = 1;  // a rank without blocks still has its virtual run
   if (h->seg_cap < h->capacity || !h->seg_counts) {
     CK(dev_alloc(h->seg_counts, h->capacity / 1024 + 2));
-    CK(dev_alloc(h->seg_starts, h->capacity));
-    CK(dev_alloc(h->seg_states, h->capacity));
+    CK(dev_alloc(h->seg_starts, h->capacity + 1));
+    CK(dev_alloc(h->seg_states, h->capacity + 1));
     h->seg_cap = h->capacity;
-    h->segs_valid = false;
+    h->segs_valid = h->g_valid = false;
   }
   SweepBuffers b = make_buffers(h, h->KP ? h->KP : 2);
   if (!h->segs_valid) {
-    launch_segments_count(b, B, h->seg_counts, h->sms, h->stream);
+    if (seg) {
+      // the state of every rank's last block: a run that crosses a rank border is ONE segment (Records.hpp:166-188)
+      launch_segments_last_state(b, h->run_states, h->stream);
+      h->launches++;
+      int rc = exchange(h, kSlotMaps, h->run_states, h->run_states + 8, 8);
+      if (rc != HML_OK) return rc;
+    }
+    launch_segments_count(b, B, h->run_states ? h->run_states + 8 : nullptr, h->seg_counts, h->sms, h->stream);
     h->launches += 2;
     CK(cudaGetLastError());
     h->segs_valid = true;
@@ -1524,14 +1545,62 @@ static int ensure_runs(hml_t* h, bool write, bool need_count = true) {
     CK(cudaMemcpyAsync(&n32, h->seg_counts + ntiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->mg_pending = false;
+    if (int rc = check_exchange(h)) return rc;
     h->nsegs = n32;
     h->nsegs_known = true;
   }
-  if (write && !h->runs_written) {
-    launch_segments_write(b, B, h->seg_counts, h->seg_starts, h->seg_states, h->sms, h->stream);
+  if (write && (!h->runs_written || accumulate)) {
+    launch_segments_write(b, B, h->run_states ? h->run_states + 8 : nullptr, h->run_border, accumulate ? 1 : 0, h->seg_counts,
+                          h->seg_starts, h->seg_states, h->sms, h->stream);
     h->launches++;
     CK(cudaGetLastError());
     h->runs_written = true;
+  }
+  return HML_OK;
+}
+
+// Collective over the handle's communicator: every rank contributes `bytes` bytes of host memory and receives all
+// contributions in rank order (world x bytes).  NCCL on temporary device buffers; the stream is drained on return.
+static int comm_allgather_host(hml_t* h, const void* send, size_t bytes, void* recv) {
+  if (h->world <= 1) {
+    memcpy(recv, send, bytes);
+    return HML_OK;
+  }
+  DevTmp<unsigned char> ds, dr;
+  const size_t padded = (bytes + 15) / 16 * 16;
+  CK(ds.alloc(padded));
+  CK(dr.alloc(padded * h->world));
+  CK(cudaMemcpyAsync(ds, send, bytes, cudaMemcpyHostToDevice, h->stream));
+  int rc = all_gather(h, ds, dr, padded);
+  if (rc != HML_OK) return rc;
+  std::vector<unsigned char> tmp(padded * h->world);
+  CK(cudaMemcpyAsync(tmp.data(), dr, tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->mg_pending = false;
+  for (int r = 0; r < h->world; ++r) memcpy((unsigned char*)recv + (size_t)r * bytes, tmp.data() + (size_t)r * padded, bytes);
+  return HML_OK;
+}
+
+// the same for contributions of different lengths: counts[r] elements of `elem` bytes from rank r, concatenated
+static int comm_allgatherv_host(hml_t* h, const void* send, uint64_t n, size_t elem, std::vector<unsigned char>& out,
+                                std::vector<uint64_t>& counts) {
+  counts.assign(h->world > 1 ? h->world : 1, 0);
+  int rc = comm_allgather_host(h, &n, sizeof(uint64_t), counts.data());
+  if (rc != HML_OK) return rc;
+  uint64_t nmax = 0, total = 0;
+  for (uint64_t c : counts) {
+    nmax = c > nmax ? c : nmax;
+    total += c;
+  }
+  std::vector<unsigned char> mine((size_t)nmax * elem + 16, 0), all(((size_t)nmax * elem + 16) * counts.size());
+  if (n) memcpy(mine.data(), send, (size_t)n * elem);
+  rc = comm_allgather_host(h, mine.data(), mine.size(), all.data());
+  if (rc != HML_OK) return rc;
+  out.resize((size_t)total * elem);
+  size_t o = 0;
+  for (size_t r = 0; r < counts.size(); ++r) {
+    memcpy(out.data() + o, all.data() + r * mine.size(), (size_t)counts[r] * elem);
+    o += (size_t)counts[r] * elem;
   }
   return HML_OK;
 }
@@ -1540,11 +1609,58 @@ int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t*
   if (!h || !nsegments) return HML_ERR_ARG;
   if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
   CK(cudaSetDevice(h->device));
-  if (h->nblocks == 0) {
+  const bool seg = h->world > 1;
+  if (h->nblocks == 0 && !seg) {
     *nsegments = 0;
     return HML_OK;
   }
   const bool want = seg_size && seg_state;
+  if (seg) {
+    // Collective: the runs of the whole sequence, identical on every rank.  A rank's run at local position 0 is a run
+    // of the sequence only if its first block begins there in a state other than the previous rank's last one.
+    if (!h->g_valid) {
+      int rc = ensure_runs(h, true);
+      if (rc != HML_OK) return rc;
+      const uint64_t n = h->nsegs;
+      std::vector<uint32_t> st(n);
+      std::vector<int16_t> ss(n);
+      uint32_t border[2] = {0, 0};
+      CK(cudaMemcpyAsync(st.data(), h->seg_starts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(ss.data(), h->seg_states, n * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaMemcpyAsync(border, h->run_border, sizeof(border), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      struct Run {
+        uint64_t start;  // position in the whole sequence
+        int64_t state;
+      };
+      std::vector<Run> mine;
+      mine.reserve(n);
+      for (uint64_t i = 0; i < n; ++i) {
+        if (i == 0 && h->rank > 0 && !border[1]) continue;  // continues the previous rank's run
+        mine.push_back({h->seg_start + st[i], ss[i]});
+      }
+      std::vector<unsigned char> all;
+      std::vector<uint64_t> counts;
+      rc = comm_allgatherv_host(h, mine.data(), mine.size(), sizeof(Run), all, counts);
+      if (rc != HML_OK) return rc;
+      const Run* runs = reinterpret_cast<const Run*>(all.data());
+      const uint64_t total = all.size() / sizeof(Run);
+      h->g_seg_size.resize(total);
+      h->g_seg_state.resize(total);
+      for (uint64_t i = 0; i < total; ++i) {
+        h->g_seg_size[i] = (i + 1 < total ? runs[i + 1].start : h->T_global) - runs[i].start;
+        h->g_seg_state[i] = (int16_t)runs[i].state;
+      }
+      h->g_valid = true;
+    }
+    const uint64_t n = h->g_seg_size.size();
+    *nsegments = n;
+    if (!want) return HML_OK;
+    if (n > capacity) return fail(h, HML_ERR_CAPACITY, "segment buffer too small");
+    memcpy(seg_size, h->g_seg_size.data(), n * sizeof(uint64_t));
+    memcpy(seg_state, h->g_seg_state.data(), n * sizeof(int16_t));
+    return HML_OK;
+  }
   int rc = ensure_runs(h, want);
   if (rc != HML_OK) return rc;
   const uint64_t n = h->nsegs;
@@ -1555,9 +1671,15 @@ int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t*
   CK(cudaMemcpyAsync(st.data(), h->seg_starts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(seg_state, h->seg_states, n * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  const uint64_t end = h->T;  // local positions; sizes do not depend on the segment offset of a split sequence
+  const uint64_t end = h->T;
   for (uint64_t i = 0; i < n; ++i) seg_size[i] = (uint64_t)(i + 1 < n ? st[i + 1] : end) - st[i];
   return HML_OK;
+}
+
+int hml_comm_allgather(hml_t* h, const void* send_host, uint64_t bytes, void* recv_host) {
+  if (!h || !send_host || !recv_host || bytes == 0) return HML_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  return comm_allgather_host(h, send_host, (size_t)bytes, recv_host);
 }
 
 // ---- state marginals accumulated on the device
@@ -1620,6 +1742,8 @@ int hml_marginals_reset(hml_t* h, int K) {
   CK(cudaMemsetAsync(h->mg_cnt[0], 0, (size_t)K * sizeof(uint16_t), h->stream));
   const uint32_t one[2] = {1u, 1u};
   CK(cudaMemcpyAsync(h->mg_n_dev, one, sizeof(one), cudaMemcpyHostToDevice, h->stream));
+  if (h->run_border) CK(cudaMemsetAsync(h->run_border, 0, 2 * sizeof(uint32_t), h->stream));
+  h->g_mg_valid = false;
   CK(cudaStreamSynchronize(h->stream));
   *h->mg_n_host = 1;
   h->mg_n = 1;
@@ -1645,21 +1769,25 @@ int hml_marginals_add(hml_t* h) {
   if (!h->states_valid) return fail(h, HML_ERR_STATE, "no sweep has been run on the current block structure");
   if (h->last_K > h->mg_K) return fail(h, HML_ERR_ARG, "the last sweep had more states than the marginals hold");
   if (h->mg_iterations >= 32767) return fail(h, HML_ERR_CAPACITY, "marginal counts are 16-bit (marginal_t): 32767 iterations");
-  if (h->nblocks == 0) return HML_OK;
+  const bool seg = h->world > 1;
+  if (h->nblocks == 0 && !seg) return HML_OK;
   CK(cudaSetDevice(h->device));
   // Nothing here waits for the device: the runs are formed and merged by kernels that read their counts from device
   // memory; the host only needs upper bounds (segments so far + blocks of the sweep) to size buffers and grids.
-  int rc = ensure_runs(h, true, false);
+  // Segment mode: collective (the ranks trade the state of their last block so that runs continue across borders);
+  // each rank keeps the marginals of its own positions, hml_marginals_get merges them.
+  int rc = ensure_runs(h, true, false, true);
   if (rc != HML_OK) return rc;
   uint64_t n = 0;
   rc = mg_current_segments(h, &n);
   if (rc != HML_OK) return rc;
-  const uint64_t m_upper = h->nblocks;  // a run is at least one block
+  const uint64_t m_upper = h->nblocks + (seg ? 1 : 0);  // a run is at least one block (+ the virtual run of a rank > 0)
   if (n + m_upper >= (1ull << 32)) return fail(h, HML_ERR_CAPACITY, "too many marginal segments for 32-bit indices");
   rc = mg_reserve(h, n + m_upper, m_upper);
   if (rc != HML_OK) return rc;
   const int cur = h->mg_cur, nxt = cur ^ 1;
-  const uint64_t ntiles = (h->nblocks + 1023) / 1024;
+  uint64_t ntiles = (h->nblocks + 1023) / 1024;
+  if (seg && ntiles == 0) ntiles = 1;
   launch_marginals_merge(h->mg_pos[cur], h->mg_n_dev + cur, n, h->mg_cnt[cur], h->seg_starts, h->seg_states,
                          h->seg_counts + ntiles, m_upper, h->mg_run_of_old, h->mg_olds_below, h->mg_flags, h->mg_K,
                          h->mg_pos[nxt], h->mg_cnt[nxt], h->mg_n_dev + nxt, h->sms, h->stream);
@@ -1669,6 +1797,61 @@ int hml_marginals_add(hml_t* h) {
   h->mg_pending = true;
   h->mg_cur = nxt;
   h->mg_iterations++;
+  h->g_mg_valid = false;
+  return HML_OK;
+}
+
+// Segment mode: the marginals of the whole sequence from the ranks' own ones (collective).  The lists are
+// concatenated in rank order; the segment that begins at a rank's first observation joins the previous rank's last
+// segment unless that position started a run of the sequence in some recorded iteration (run_border[0]) — in every
+// iteration the same run then covered both pieces, so their counts agree (checked).
+static int mg_merge_global(hml_t* h) {
+  if (h->g_mg_valid) return HML_OK;
+  uint64_t n = 0;
+  int rc = mg_current_segments(h, &n);
+  if (rc != HML_OK) return rc;
+  const int K = h->mg_K;
+  const size_t elem = 8 + 2 * (size_t)K;  // start (global, 8 bytes) + K counts
+  std::vector<uint32_t> pos(n);
+  std::vector<uint16_t> cnt(n * (size_t)K);
+  uint32_t border[2] = {0, 0};
+  CK(cudaMemcpyAsync(pos.data(), h->mg_pos[h->mg_cur], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(cnt.data(), h->mg_cnt[h->mg_cur], n * (size_t)K * sizeof(uint16_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(border, h->run_border, sizeof(border), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<unsigned char> mine(n * elem);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t start = h->seg_start + pos[i];
+    if (i == 0 && h->rank > 0 && !border[0]) start = ~0ull;  // marks "joins the previous segment"
+    memcpy(mine.data() + i * elem, &start, 8);
+    memcpy(mine.data() + i * elem + 8, cnt.data() + i * (size_t)K, 2 * (size_t)K);
+  }
+  std::vector<unsigned char> all;
+  std::vector<uint64_t> counts;
+  rc = comm_allgatherv_host(h, mine.data(), n, elem, all, counts);
+  if (rc != HML_OK) return rc;
+  const uint64_t total = all.size() / elem;
+  std::vector<uint64_t> starts;
+  starts.reserve(total);
+  h->g_mg_counts.clear();
+  h->g_mg_counts.reserve(total * (size_t)K);
+  for (uint64_t i = 0; i < total; ++i) {
+    uint64_t start;
+    memcpy(&start, all.data() + i * elem, 8);
+    const uint16_t* c = reinterpret_cast<const uint16_t*>(all.data() + i * elem + 8);
+    if (start == ~0ull) {
+      if (starts.empty()) return fail(h, HML_ERR_STATE, "marginal merge: a continued segment without a predecessor");
+      for (int s2 = 0; s2 < K; ++s2)
+        if (h->g_mg_counts[(starts.size() - 1) * (size_t)K + s2] != (int32_t)c[s2])
+          return fail(h, HML_ERR_STATE, "marginal merge: a run crossing a rank border has different counts on its two sides");
+      continue;
+    }
+    starts.push_back(start);
+    for (int s2 = 0; s2 < K; ++s2) h->g_mg_counts.push_back((int32_t)c[s2]);
+  }
+  h->g_mg_size.resize(starts.size());
+  for (size_t i = 0; i < starts.size(); ++i) h->g_mg_size[i] = (i + 1 < starts.size() ? starts[i + 1] : h->T_global) - starts[i];
+  h->g_mg_valid = true;
   return HML_OK;
 }
 
@@ -1676,8 +1859,29 @@ int hml_marginals_info(hml_t* h, uint64_t* nsegments, uint64_t* iterations, int*
   if (!h) return HML_ERR_ARG;
   if (nsegments) {
     CK(cudaSetDevice(h->device));
-    int rc = mg_current_segments(h, nsegments);
-    if (rc != HML_OK) return rc;
+    if (h->world > 1 && h->mg_K) {
+      if (h->g_mg_valid) {
+        *nsegments = h->g_mg_size.size();
+      } else {
+        // the count alone needs 16 bytes per rank: own segments, and whether the one at position 0 is a real border
+        uint64_t mine[2] = {0, 0};
+        int rc = mg_current_segments(h, &mine[0]);
+        if (rc != HML_OK) return rc;
+        uint32_t border[2] = {0, 0};
+        CK(cudaMemcpyAsync(border, h->run_border, sizeof(border), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        mine[1] = border[0];
+        std::vector<uint64_t> all(2 * (size_t)h->world);
+        rc = comm_allgather_host(h, mine, sizeof(mine), all.data());
+        if (rc != HML_OK) return rc;
+        uint64_t n = 0;
+        for (int r = 0; r < h->world; ++r) n += all[2 * r] - ((r > 0 && !all[2 * r + 1]) ? 1 : 0);
+        *nsegments = n;
+      }
+    } else {
+      int rc = mg_current_segments(h, nsegments);
+      if (rc != HML_OK) return rc;
+    }
   }
   if (iterations) *iterations = h->mg_iterations;
   if (K) *K = h->mg_K;
@@ -1688,6 +1892,15 @@ int hml_marginals_get(hml_t* h, uint64_t* seg_size, int32_t* counts, uint64_t ca
   if (!h || !seg_size || !counts) return HML_ERR_ARG;
   if (h->mg_K == 0) return fail(h, HML_ERR_STATE, "hml_marginals_reset has not been called");
   CK(cudaSetDevice(h->device));
+  if (h->world > 1) {
+    int rc = mg_merge_global(h);
+    if (rc != HML_OK) return rc;
+    const uint64_t n = h->g_mg_size.size();
+    if (capacity < n) return fail(h, HML_ERR_CAPACITY, "buffer smaller than the number of marginal segments");
+    memcpy(seg_size, h->g_mg_size.data(), n * sizeof(uint64_t));
+    memcpy(counts, h->g_mg_counts.data(), n * (size_t)h->mg_K * sizeof(int32_t));
+    return HML_OK;
+  }
   uint64_t n = 0;
   int rc0 = mg_current_segments(h, &n);
   if (rc0 != HML_OK) return rc0;
@@ -1749,6 +1962,10 @@ int hml_comm_init(hml_t* h, int rank, int world, const uint8_t id[HML_UNIQUE_ID_
   CK(dev_alloc(h->seg_dev, seg_words));
   CK(cudaMemsetAsync(h->seg_dev, 0, seg_words * sizeof(double), h->stream));
   CK(dev_alloc(h->stats_gather, (size_t)world * kOutWords));
+  CK(dev_alloc(h->run_states, 8 + (size_t)world));
+  CK(cudaMemsetAsync(h->run_states, 0, (8 + (size_t)world) * sizeof(unsigned long long), h->stream));
+  CK(dev_alloc(h->run_border, 2));
+  CK(cudaMemsetAsync(h->run_border, 0, 2 * sizeof(uint32_t), h->stream));
   CK(cudaMallocHost((void**)&h->stats_gather_host, (size_t)world * kOutWords * 8));
   CK(cudaStreamSynchronize(h->stream));
   return setup_p2p(h);

@@ -177,11 +177,18 @@ int launch_sweep_sequential(const ModelHost& m, const SweepBuffers& b, const Swe
 // Copies per-block arrays out of the interleaved order: dst_states (int16), dst_sum/dst_sumsq.
 void launch_unpermute(const SweepBuffers& b, int KP, uint64_t nblocks, int16_t* dst_states, double* dst_sum,
                       double* dst_sumsq, cudaStream_t s);
-// Run-length view of the sampled states (nblocks > 0): tile_counts[0..ntiles] <- exclusive offsets of the runs that
-// start in each 1024-block tile, [ntiles] = number of runs (2 launches); then (start position, state) per run (1 launch).
-void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, uint32_t* tile_counts, int sms, cudaStream_t s);
-void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const uint32_t* tile_offsets, uint32_t* seg_start,
-                           int16_t* seg_state, int sms, cudaStream_t s);
+// Run-length view of the sampled states: tile_counts[0..ntiles] <- exclusive offsets of the runs that start in each
+// 1024-block tile, [ntiles] = number of runs (2 launches); then (start position, state) per run (1 launch).
+// Segment mode: `last_states` holds the all-gathered state of every rank's last block (launch_segments_last_state
+// fills this rank's word before the exchange); ranks > 0 always emit a run start at local position 0 (a virtual run in
+// the previous rank's state unless their first block begins there) and record in border[1] / accumulate in border[0]
+// whether that position started a run of the whole sequence.  ntiles = max(1, ceil(nblocks / 1024)) then.
+void launch_segments_last_state(const SweepBuffers& b, unsigned long long* send, cudaStream_t s);
+void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, const unsigned long long* last_states,
+                           uint32_t* tile_counts, int sms, cudaStream_t s);
+void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const unsigned long long* last_states, uint32_t* border,
+                           int accumulate, const uint32_t* tile_offsets, uint32_t* seg_start, int16_t* seg_state, int sms,
+                           cudaStream_t s);
 // State marginals on the device: merges the run starts R[m] / run states of one recorded iteration into the
 // refinement (P[n], cnt[n x K]) -> (P2, cnt2) with new_flags[m] = number of new boundaries (3 launches).
 // The segment count n and the run count m are read from device memory (*n_ptr, *m_ptr), the new segment count is

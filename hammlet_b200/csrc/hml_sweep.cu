@@ -60,18 +60,53 @@ __global__ void k_unpermute(const uint8_t* states, const double2* bS, uint64_t B
 // a run starts at block 0 and wherever the state differs from the previous block's.  Three small kernels — heads per
 // tile, exclusive scan of the tile counts, ordered write of (start position, state) — so that a recorded sweep moves
 // one entry per run to the host instead of one per block.
-__device__ __forceinline__ bool seg_is_head(const uint8_t* states, uint64_t b, uint64_t B) {
+// Segment mode (one sequence split over ranks): a run may continue across a rank border, so whether a rank's first
+// block starts a run depends on the state of the previous rank's last block (`prev`, all-gathered per recorded sweep,
+// RunCtx::last_states).  Every rank > 0 keeps a run start at its local position 0 — the device-side marginals need
+// one (P[0] = 0) —: the rank's block 0 if that block begins exactly at the rank's first observation, else a VIRTUAL
+// run in the previous rank's last state that covers the observations in front of the first boundary (they belong to a
+// block owned by an earlier rank).  Whether position 0 is also a run start of the whole sequence (`border_real`) is
+// remembered so that the merged outputs can drop the border where it never was one.
+struct RunCtx {
+  int rank, world;
+  const double* heads;          // world x 4 (block count of every rank first), from the sweep's head exchange
+  const uint64_t* last_states;  // world words: state of every rank's last block (~0: the rank has no block)
+  uint32_t* border;             // [0] |= 1 if position 0 of this rank started a run of the whole sequence in a recorded
+                                // iteration (k_seg_write with `accumulate`), [1] = the same for the last iteration only
+};
+__device__ __forceinline__ uint32_t run_prev_state(const RunCtx& c) {
+  for (int r = c.rank - 1; r >= 0; --r)
+    if (c.heads[4 * r] > 0.0) return (uint32_t)c.last_states[r];
+  return 0u;  // unreachable: rank 0 always owns the block that starts at position 0
+}
+// does a virtual run precede the rank's blocks?
+__device__ __forceinline__ bool run_virtual(const RunCtx& c, const uint32_t* starts, uint64_t B) {
+  return c.world > 1 && c.rank > 0 && (B == 0 || starts[0] != 0u);
+}
+
+__device__ __forceinline__ bool seg_is_head(const uint8_t* states, uint64_t b, uint64_t B, bool virt, uint32_t prev) {
   if (b >= B) return false;
-  if (b == 0) return true;
+  if (b == 0) return virt ? states[Layout::perm(0)] != prev : true;
   return states[Layout::perm(b)] != states[Layout::perm(b - 1)];
 }
 
-__global__ void __launch_bounds__(1024) k_seg_count(const uint8_t* __restrict__ states, uint64_t B, uint32_t* tile_counts) {
-  const uint64_t ntiles = (B + 1023) / 1024;
+// tiles: max(1, ceil(B / 1024)) in segment mode (a rank without blocks still has its virtual run)
+__global__ void __launch_bounds__(1024) k_seg_count(const uint8_t* __restrict__ states, const uint32_t* __restrict__ starts,
+                                                    uint64_t B, uint64_t ntiles, RunCtx ctx, uint32_t* tile_counts) {
+  const bool virt = run_virtual(ctx, starts, B);
+  const uint32_t prev = virt ? run_prev_state(ctx) : 0u;
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int n = __syncthreads_count(seg_is_head(states, tile * 1024 + threadIdx.x, B) ? 1 : 0);
-    if (threadIdx.x == 0) tile_counts[tile] = (uint32_t)n;
+    const int n = __syncthreads_count(seg_is_head(states, tile * 1024 + threadIdx.x, B, virt, prev) ? 1 : 0);
+    if (threadIdx.x == 0) tile_counts[tile] = (uint32_t)n + ((tile == 0 && virt) ? 1u : 0u);
   }
+}
+
+// the state of this rank's last block for the neighbour (segment mode, before k_seg_count)
+__global__ void k_seg_last_state(const uint8_t* __restrict__ states, const unsigned long long* __restrict__ nblocks,
+                                 uint64_t capacity, unsigned long long* send) {
+  const uint64_t raw = *nblocks;
+  const uint64_t B = raw <= capacity ? raw : 0;
+  send[0] = B ? (unsigned long long)states[Layout::perm(B - 1)] : ~0ull;
 }
 
 // in-place exclusive scan of tile_counts[0..ntiles) by one CTA; tile_counts[ntiles] receives the total.
@@ -130,21 +165,34 @@ __global__ void __launch_bounds__(1024) k_seg_scan_dev(uint32_t* tile_counts, co
 }
 
 __global__ void __launch_bounds__(1024) k_seg_write(const uint8_t* __restrict__ states, const uint32_t* __restrict__ starts,
-                                                    uint64_t B, const uint32_t* __restrict__ tile_offsets,
+                                                    uint64_t B, uint64_t ntiles, RunCtx ctx, int accumulate,
+                                                    const uint32_t* __restrict__ tile_offsets,
                                                     uint32_t* __restrict__ seg_start, int16_t* __restrict__ seg_state) {
   __shared__ uint32_t s_warp[32];
-  const uint64_t ntiles = (B + 1023) / 1024;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool virt = run_virtual(ctx, starts, B);
+  const uint32_t prev = (ctx.world > 1 && ctx.rank > 0) ? run_prev_state(ctx) : 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (virt) {
+      seg_start[0] = 0u;
+      seg_state[0] = (int16_t)prev;
+    }
+    if (ctx.border) {
+      const uint32_t real = (ctx.world > 1 && ctx.rank > 0 && !virt && states[Layout::perm(0)] != prev) ? 1u : 0u;
+      ctx.border[1] = real;
+      if (accumulate && real) ctx.border[0] = 1u;
+    }
+  }
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint64_t b = tile * 1024 + threadIdx.x;
-    const bool head = seg_is_head(states, b, B);
+    const bool head = seg_is_head(states, b, B, virt, prev);
     const unsigned bal = __ballot_sync(0xffffffffu, head);
     if (lane == 0) s_warp[warp] = __popc(bal);
     __syncthreads();
     uint32_t before = 0;
     for (int w = 0; w < warp; ++w) before += s_warp[w];
     if (head) {
-      const uint32_t idx = tile_offsets[tile] + before + __popc(bal & ((1u << lane) - 1u));
+      const uint32_t idx = tile_offsets[tile] + ((tile == 0 && virt) ? 1u : 0u) + before + __popc(bal & ((1u << lane) - 1u));
       seg_start[idx] = starts[b];
       seg_state[idx] = (int16_t)states[Layout::perm(b)];
     }
@@ -237,17 +285,36 @@ void launch_marginals_merge(const uint32_t* P, const uint32_t* n_ptr, uint64_t n
   k_mg_write<<<g, 256, 0, s>>>(P, n_ptr, cnt, R, rstate, m_ptr, run_of_old, olds_below, new_flags, K, P2, cnt2, n_out);
 }
 
-void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, uint32_t* tile_counts, int sms, cudaStream_t s) {
+static RunCtx make_run_ctx(const SweepBuffers& b, const unsigned long long* last_states, uint32_t* border) {
+  RunCtx c;
+  c.rank = b.seg.world > 1 ? b.seg.rank : 0;
+  c.world = b.seg.world > 1 ? b.seg.world : 1;
+  c.heads = b.seg.heads;
+  c.last_states = reinterpret_cast<const uint64_t*>(last_states);
+  c.border = border;
+  return c;
+}
+static uint64_t run_tiles(const SweepBuffers& b, uint64_t nblocks) {
   const uint64_t ntiles = (nblocks + 1023) / 1024;
+  return (b.seg.world > 1 && ntiles == 0) ? 1 : ntiles;
+}
+void launch_segments_last_state(const SweepBuffers& b, unsigned long long* send, cudaStream_t s) {
+  k_seg_last_state<<<1, 1, 0, s>>>(b.states, b.nblocks, b.capacity, send);
+}
+void launch_segments_count(const SweepBuffers& b, uint64_t nblocks, const unsigned long long* last_states,
+                           uint32_t* tile_counts, int sms, cudaStream_t s) {
+  const uint64_t ntiles = run_tiles(b, nblocks);
   const int g = (int)(ntiles < (uint64_t)sms * 2 ? ntiles : (uint64_t)sms * 2);
-  k_seg_count<<<g, 1024, 0, s>>>(b.states, nblocks, tile_counts);
+  k_seg_count<<<g, 1024, 0, s>>>(b.states, b.starts, nblocks, ntiles, make_run_ctx(b, last_states, nullptr), tile_counts);
   k_seg_scan<<<1, 1024, 0, s>>>(tile_counts, (uint32_t)ntiles);
 }
-void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const uint32_t* tile_offsets, uint32_t* seg_start,
-                           int16_t* seg_state, int sms, cudaStream_t s) {
-  const uint64_t ntiles = (nblocks + 1023) / 1024;
+void launch_segments_write(const SweepBuffers& b, uint64_t nblocks, const unsigned long long* last_states, uint32_t* border,
+                           int accumulate, const uint32_t* tile_offsets, uint32_t* seg_start, int16_t* seg_state, int sms,
+                           cudaStream_t s) {
+  const uint64_t ntiles = run_tiles(b, nblocks);
   const int g = (int)(ntiles < (uint64_t)sms * 2 ? ntiles : (uint64_t)sms * 2);
-  k_seg_write<<<g, 1024, 0, s>>>(b.states, b.starts, nblocks, tile_offsets, seg_start, seg_state);
+  k_seg_write<<<g, 1024, 0, s>>>(b.states, b.starts, nblocks, ntiles, make_run_ctx(b, last_states, border), accumulate,
+                                 tile_offsets, seg_start, seg_state);
 }
 
 size_t reduce_partials_doubles(int KP, int grid) { return (size_t)grid * 2 * KP + 64; }

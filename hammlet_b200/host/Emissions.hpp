@@ -27,6 +27,7 @@ class DeviceSequence {
   uint64_t mSize = 0;
   size_t mNrDim = 1;
   double mSigmaHat = 0;
+  int mRank = 0, mWorld = 1;  // > 1: this handle holds one segment of a sequence split over several GPUs
 
  public:
   DeviceSequence(const DeviceSequence&) = delete;
@@ -42,6 +43,7 @@ class DeviceSequence {
     uint32_t d = 1;
     check(hml_nr_dims(mHandle, &d));
     mNrDim = d;
+    check(hml_segment_info(mHandle, &mRank, &mWorld, nullptr, nullptr, nullptr, nullptr));
   }
   ~DeviceSequence() {
     if (mOwns) hml_destroy(mHandle);
@@ -71,6 +73,47 @@ class DeviceSequence {
   // noise estimate from the finest detail coefficients (main.cpp:303-311)
   double noiseStdev() const { return mSigmaHat; }
 
+  // ---- one sequence split into contiguous segments, one per GPU and process (the reference has no
+  // counterpart).  Every rank runs the same host code on the same parameters; only rank 0 writes files.
+  int rank() const { return mRank; }
+  int world() const { return mWorld; }
+  bool split() const { return mWorld > 1; }
+  // joins the communicator (collective) and loads this rank's slice of `values` (the whole sequence, univariate)
+  void loadSegment(const std::vector<float>& values, float weightMultiplier, int rank, int world,
+                   const uint8_t id[HML_UNIQUE_ID_BYTES]) {
+    if (values.empty()) throw std::runtime_error("Input vector for breakpoint weights is empty!");
+    check(hml_comm_init(mHandle, rank, world, id));
+    uint64_t start = 0, len = 0;
+    if (hml_segment_plan(values.size(), world, rank, &start, &len) != HML_OK)
+      throw std::runtime_error("Sequence too short to split over " + std::to_string(world) + " devices (4096 observations each at least)!");
+    check(hml_load_segment_f32(mHandle, values.data() + start, len, values.size(), weightMultiplier));
+    mSize = values.size();
+    mNrDim = 1;
+    mRank = rank;
+    mWorld = world;
+    check(hml_sigma_hat(mHandle, &mSigmaHat));
+  }
+  // concatenation, in rank order, of every rank's `mine` (collective; a copy without a communicator)
+  template <typename T>
+  std::vector<T> allgatherv(const std::vector<T>& mine) const {
+    if (mWorld <= 1) return mine;
+    std::vector<uint64_t> counts(mWorld);
+    const uint64_t n = mine.size();
+    check(hml_comm_allgather(mHandle, &n, sizeof(uint64_t), counts.data()));
+    uint64_t nmax = 0, total = 0;
+    for (uint64_t c : counts) {
+      nmax = std::max(nmax, c);
+      total += c;
+    }
+    std::vector<T> padded(nmax + 1), all((nmax + 1) * (size_t)mWorld);
+    std::copy(mine.begin(), mine.end(), padded.begin());
+    check(hml_comm_allgather(mHandle, padded.data(), (nmax + 1) * sizeof(T), all.data()));
+    std::vector<T> out;
+    out.reserve(total);
+    for (int r = 0; r < mWorld; ++r) out.insert(out.end(), all.begin() + r * (nmax + 1), all.begin() + r * (nmax + 1) + counts[r]);
+    return out;
+  }
+
   // integer statistics of the most recent sweep on this sequence as the sampler received them (ForwardBackward.hpp:
   // 177-200): callers that only drive whole runs (bench.py) check their invariants — transition counts, occupancy and
   // per-parameter counts each sum to the sequence length
@@ -83,9 +126,7 @@ class DeviceSequence {
 
 // Reads whitespace-separated numbers with the result of `input >> v` (wavelet.hpp:131), through the
 // multi-threaded parser of FastParse.hpp, and loads them.
-inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size_t nrDim, const float weightMultiplier,
-                            const size_t reserveT = 0) {
-  if (nrDim <= 0) throw std::runtime_error("Number of dimensions must be positive!");
+inline std::vector<float> readValues(std::istream& input, const size_t reserveT = 0) {
   if (!input) throw std::runtime_error("Cannot read input file or stream!");
   std::vector<float> values;
   values.reserve(reserveT);
@@ -96,7 +137,12 @@ inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size
     const std::string text = fastparse::slurp(input);
     fastparse::parseFloats(text.data(), text.size(), values);
   }
-  seq.load(values, weightMultiplier, nrDim);
+  return values;
+}
+inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size_t nrDim, const float weightMultiplier,
+                            const size_t reserveT = 0) {
+  if (nrDim <= 0) throw std::runtime_error("Number of dimensions must be positive!");
+  seq.load(readValues(input, reserveT), weightMultiplier, nrDim);
 }
 
 template <typename T> class Blocks;
@@ -145,13 +191,16 @@ class Blocks<BreakpointArray> {
       mDirty = false;
       mHostValid = false;
     }
+    // blocks of the whole sequence (for a split sequence hml_nr_blocks counts the rank's own)
     uint64_t n = 0;
-    mSeq.check(hml_nr_blocks(mSeq.handle(), &n));
+    mSeq.check(hml_segment_info(mSeq.handle(), nullptr, nullptr, nullptr, nullptr, nullptr, &n));
     return n;
   }
   void fetch(bool stats) {
-    const size_t n = materialize();
+    materialize();
     if (mHostValid && (!stats || !mSum.empty())) return;
+    uint64_t n = 0;  // blocks on this handle
+    mSeq.check(hml_nr_blocks(mSeq.handle(), &n));
     mStarts.resize(n);
     if (stats) {
       const size_t D = mSeq.nrDim();
@@ -164,6 +213,23 @@ class Blocks<BreakpointArray> {
       mSum.clear();
       mSumSq.clear();
       mSeq.check(hml_get_blocks(mSeq.handle(), mStarts.data(), nullptr, nullptr, n));
+    }
+    if (mSeq.split()) {
+      // every rank sees the block list of the whole sequence (starts are positions in the whole sequence already;
+      // a block that crosses a rank border is listed, with its complete sums, by the rank where it starts)
+      const size_t D = stats ? mSeq.nrDim() : 0;
+      std::vector<std::vector<double>> sums, sqs;
+      for (size_t d = 0; d < D; ++d) {
+        sums.push_back(mSeq.allgatherv(std::vector<double>(mSum.begin() + d * n, mSum.begin() + (d + 1) * n)));
+        sqs.push_back(mSeq.allgatherv(std::vector<double>(mSumSq.begin() + d * n, mSumSq.begin() + (d + 1) * n)));
+      }
+      mStarts = mSeq.allgatherv(mStarts);
+      mSum.clear();
+      mSumSq.clear();
+      for (size_t d = 0; d < D; ++d) {
+        mSum.insert(mSum.end(), sums[d].begin(), sums[d].end());
+        mSumSq.insert(mSumSq.end(), sqs[d].begin(), sqs[d].end());
+      }
     }
     mHostValid = true;
   }

@@ -138,10 +138,13 @@ class Records {
        mRecordTheta = false, mRecordSegments = false;
   std::ofstream mMarginalsFile, mSequenceFile, mBlocksFile, mThetaFile, mCompressionsFile, mSegmentFile;
   bool mClosed = false;
+  // A rank > 0 of a split sequence records like rank 0 (the same calls in the same order, some of them collective)
+  // but owns no files: its streams stay closed, so everything written to them is dropped.
+  bool mMute = false;
 
   void setRecordX(std::ofstream& file, const std::string& type, bool& member, const bool flag, const bool overwrite) {
     member = flag;
-    if (member && !file.is_open()) {
+    if (member && !file.is_open() && !mMute) {
       const std::string filename = mPrefix + type + mSuffix;
       if (hammlet::fileExists(filename) && !overwrite)
         throw std::runtime_error("File " + filename + " already exists! Use -w to allow overwrite!");
@@ -164,7 +167,7 @@ class Records {
     if (mClosed) return;
     mClosed = true;
     if (mRecordMarginals) {
-      if (mMarginalsFile.is_open()) saveMarginals(mMarginalsFile);
+      if (mMarginalsFile.is_open() || mMute) saveMarginals(mMarginalsFile);
       mMarginalsFile.close();
     }
     if (mRecordSequences) mSequenceFile.close();
@@ -180,6 +183,7 @@ class Records {
   void setRecordTheta(bool b, bool overwrite = false) { setRecordX(mThetaFile, "parameters", mRecordTheta, b, overwrite); }
   void setRecordSegments(bool b, bool overwrite = false) { setRecordX(mSegmentFile, "segments", mRecordSegments, b, overwrite); }
   bool wantsBlocks() const { return mRecordBlocks; }
+  void setMute(bool on) { mMute = on; }  // before any setRecord*()
 
   // ---- marginals accumulated on the device
   void setMarginalsSink(MarginalsSink* sink) { mSink = sink; }

@@ -225,7 +225,7 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
   seq.lastSweep.counts = counts;
   seq.lastSweep.trans = trans;
   seq.lastSweep.statN.assign(statN.begin(), statN.begin() + nrParams);
-  for (uint64_t i = 0; i < out.uniform_fallbacks; ++i) std::cout << "[WARNING] Uniform sampling of forward variables!" << std::endl;
+  for (uint64_t i = 0; i < out.uniform_fallbacks && seq.rank() == 0; ++i) std::cout << "[WARNING] Uniform sampling of forward variables!" << std::endl;
   mLogLikelihood = out.loglik;
   if (mKeepTrellis && !kIsMixture) {
     mTrellis.setNrStates(nrStates);
@@ -266,8 +266,11 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
   }
   // block by block, in order
   if (doRecord || (!kIsMixture && mKeepTrellis)) {
-    mStates.resize(out.nblocks);
-    seq.check(hml_get_states(seq.handle(), mStates.data(), mStates.size()));
+    uint64_t local = 0;  // a split sequence: the rank's own blocks, then everybody's in rank order
+    seq.check(hml_nr_blocks(seq.handle(), &local));
+    mStates.resize(local);
+    if (local) seq.check(hml_get_states(seq.handle(), mStates.data(), mStates.size()));
+    if (seq.split()) mStates = seq.allgatherv(mStates);
   }
   if (doRecord) {
     blocks.fetch(false);

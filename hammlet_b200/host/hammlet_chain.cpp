@@ -224,8 +224,11 @@ int hammlet_chains_run(hammlet_chain** chains, int n, int threads, char method, 
 int hammlet_chain_save_marginals(hammlet_chain* c, const char* path) {
   if (!c || !path) return HML_ERR_ARG;
   try {
-    std::ofstream f(path);
-    if (!f.is_open()) throw std::runtime_error(std::string("Cannot write to file ") + path + "!");
+    std::ofstream f;  // a split sequence: every rank takes part in the merge, rank 0 writes the file
+    if (c->sequence.rank() == 0) {
+      f.open(path);
+      if (!f.is_open()) throw std::runtime_error(std::string("Cannot write to file ") + path + "!");
+    }
     c->records.saveMarginals(f);
     return HML_OK;
   } catch (std::exception& e) {

@@ -5,13 +5,44 @@
 // are parsed on the host, handed once to the device (hml_load_f32) and every sweep of the scheme runs
 // there; see StateSequence.hpp.  Additional flags (none collides with the reference's):
 //   -device N            CUDA device index (default 0)
+//   -devices a b c ...   split the sequence into contiguous segments over the listed devices (also `a,b,c`): one
+//                        process per device is forked after the input has been parsed, every process runs the same
+//                        chain on the same parameters, the scan carries travel between the GPUs,
+//                        process 0 writes the files — the same files a single device writes.  Univariate data.
 //   -replay              draw the per-block uniforms from the shared mt19937 exactly as the reference
 //                        does (draw-for-draw comparable runs; slower: one host round trip per sweep)
 //   -timing              print sweeps/s per run token to stderr
+#include <signal.h>
+#include <sys/prctl.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <ctime>
 
 #include "StateSequence.hpp"
+
+// ---- one process per device (-devices): children of process 0, wired by pipes that carry the communicator id
+static std::vector<pid_t> g_children;
+static void killChildren() {
+  for (pid_t p : g_children) kill(p, SIGTERM);
+}
+static void onChild(int) {  // a rank that dies would leave the others waiting in a collective
+  int status = 0;
+  pid_t p;
+  while ((p = waitpid(-1, &status, WNOHANG)) > 0) {
+    const bool ok = WIFEXITED(status) && WEXITSTATUS(status) == 0;
+    for (pid_t& c : g_children)
+      if (c == p) c = ok ? 0 : -1;
+    if (!ok) {
+      const char msg[] = "\n[ERROR] A device process failed!\nTerminating HaMMLET. The rest is silence.\n";
+      if (write(2, msg, sizeof(msg) - 1) < 0) {}
+      for (pid_t c : g_children)
+        if (c > 0) kill(c, SIGTERM);
+      _exit(1);
+    }
+  }
+}
 
 using std::cerr;
 using std::cout;
@@ -36,7 +67,8 @@ static const char* kHelp =
     "  -i|-iterations ...         scheme, e.g. `M 500 0 S P F 200 0 F 300 3` (M|F iterations thinning; P S D)\n"
     "  -m|-weight-multiplier x    multiply breakpoint weights (default 1)\n"
     "  -v -g -h                   verbose, print parsed arguments, this help\n"
-    "  -device N  -replay  -timing   see the header of hammlet_main.cpp\n";
+    "  -device N  -replay  -timing   see the header of hammlet_main.cpp\n"
+    "  -devices a b ...           split the sequence over several GPUs (one process each), same output files\n";
 
 int main(int argc, const char* argv[]) {
   try {
@@ -58,12 +90,13 @@ int main(int argc, const char* argv[]) {
     args.registerFlags({"-i", "-iterations"}, "M 500 0 S P F 200 0 F 300 3");
     args.registerFlags({"-m", "-weight-multiplier"}, "1");
     args.registerFlags({"-device"}, "0");
+    args.registerFlags({"-devices"});
     args.registerFlags({"-replay"});
     args.registerFlags({"-timing"});
     args.parseArgs();
 
     if (args.isSet("-g")) args.print();
-    const bool verbose = args.isSet("-v");
+    bool verbose = args.isSet("-v");
     const bool overwrite = args.isSet("-w");
     if (args.isSet("-h")) {
       cout << endl << kHelp << endl;
@@ -137,19 +170,97 @@ int main(int argc, const char* argv[]) {
     outputArgs.registerFlags({"G", "segments"});
     outputArgs.parseArgs();
 
-    // ---- load: parse on the host, transform on the device
-    DeviceSequence sequence(args.parse<int>("-device"));
+    // ---- devices: one (-device) or several (-devices: the sequence is split into contiguous segments)
+    vector<int> devices{args.parse<int>("-device")};
+    if (args.isSet("-devices")) {
+      devices.clear();
+      for (const string& tok : args.tokens("-devices")) {
+        std::stringstream ss(tok);
+        string item;
+        while (std::getline(ss, item, ',')) {
+          size_t used = 0;
+          int d = -1;
+          try {
+            d = std::stoi(item, &used);
+          } catch (std::exception&) {
+            used = 0;
+          }
+          if (item.empty() || used != item.size() || d < 0) throw std::runtime_error("Cannot parse device list \"" + tok + "\"!");
+          devices.push_back(d);
+        }
+      }
+      if (devices.empty()) throw std::runtime_error("Flag -devices needs at least one device index!");
+    }
+    const int world = (int)devices.size();
+    if (world > 1 && nrDataDim != 1) throw std::runtime_error("A sequence split over several devices must be univariate!");
+
+    // ---- load: parse on the host (before any process is forked and before CUDA is touched), transform on the device
+    vector<float> values;
     if (args.isSet("-f")) {
       const vector<string> files = args.parseVector<string>("-f");
       if (files.size() > 1) throw std::runtime_error("Coefficient array must be empty!");  // as wavelet.hpp:111-113
       if (verbose) cout << "Reading " + files[0] << endl << flush;
       std::ifstream fin(files[0]);
       if (!fin) throw std::runtime_error("Cannot read from input file " + files[0] + "!");
-      MaxletTransform(fin, sequence, nrDataDim, (float)weightMultiplier);
+      values = readValues(fin);
     } else {
       if (verbose) cout << "Reading from standard input" << endl << flush;
-      MaxletTransform(std::cin, sequence, nrDataDim, (float)weightMultiplier);
+      values = readValues(std::cin);
     }
+    if (nrDataDim <= 0) throw std::runtime_error("Number of dimensions must be positive!");
+
+    int rank = 0;
+    uint8_t commId[HML_UNIQUE_ID_BYTES] = {0};
+    if (world > 1) {
+      cout << flush;
+      vector<int> toChild(world, -1);
+      int fromParent = -1;
+      signal(SIGCHLD, onChild);
+      for (int r = 1; r < world; ++r) {
+        int fds[2];
+        if (pipe(fds) != 0) throw std::runtime_error("Cannot create a pipe for a device process!");
+        const pid_t pid = fork();
+        if (pid < 0) throw std::runtime_error("Cannot fork a device process!");
+        if (pid == 0) {  // child: rank r
+          prctl(PR_SET_PDEATHSIG, SIGTERM);
+          signal(SIGCHLD, SIG_DFL);
+          g_children.clear();
+          for (int q = 1; q < r; ++q) close(toChild[q]);
+          close(fds[1]);
+          fromParent = fds[0];
+          rank = r;
+          break;
+        }
+        close(fds[0]);
+        toChild[r] = fds[1];
+        g_children.push_back(pid);
+      }
+      if (rank == 0) {
+        if (hml_comm_unique_id(commId) != HML_OK) throw std::runtime_error(hml_last_error(nullptr));
+        for (int r = 1; r < world; ++r) {
+          if (write(toChild[r], commId, sizeof(commId)) != (ssize_t)sizeof(commId))
+            throw std::runtime_error("Cannot reach a device process!");
+          close(toChild[r]);
+        }
+      } else {
+        size_t got = 0;
+        while (got < sizeof(commId)) {
+          const ssize_t n = read(fromParent, commId + got, sizeof(commId) - got);
+          if (n <= 0) throw std::runtime_error("Lost the connection to device process 0!");
+          got += (size_t)n;
+        }
+        close(fromParent);
+      }
+    }
+    const bool lead = rank == 0;  // the process that talks and writes
+    if (!lead) verbose = false;
+
+    DeviceSequence sequence(devices[rank]);
+    if (world > 1)
+      sequence.loadSegment(values, (float)weightMultiplier, rank, world, commId);
+    else
+      sequence.load(values, (float)weightMultiplier, nrDataDim);
+    vector<float>().swap(values);
     if (verbose) cout << "Output will be written to " + outputPrefix + "*" + outputSuffix << endl << flush;
     const size_t T = sequence.size();
     if (verbose) cout << "Number of data points: " + std::to_string(T) << endl << flush;
@@ -157,6 +268,7 @@ int main(int argc, const char* argv[]) {
     if (verbose) cout << "Calculating Haar breakpoint weights" << endl << flush;
 
     Records records(T, outputPrefix, outputSuffix, nrStates);
+    records.setMute(!lead);
     records.setRecordStateSequence(outputArgs.isSet("sequences"), overwrite);
     records.setRecordTheta(outputArgs.isSet("parameters"), overwrite);
     records.setRecordBlocks(outputArgs.isSet("blocks"), overwrite);
@@ -233,16 +345,28 @@ int main(int argc, const char* argv[]) {
       } else {
         throw std::runtime_error("Unknown sampling type " + method + "!");
       }
-      if (timing) {
+      if (timing && lead) {
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         cerr << "[timing] " << method << " " << iterations << " sweeps in " << s << " s = " << (s > 0 ? iterations / s : 0)
              << " sweeps/s" << endl;
       }
     }
     records.close();  // writes the marginals (the reference does this in ~Records)
+    if (lead && !g_children.empty()) {  // the other device processes have nothing left to do: collect them
+      signal(SIGCHLD, SIG_DFL);
+      for (pid_t p : g_children) {
+        int status = 0;
+        if (p > 0 && waitpid(p, &status, 0) == p && !(WIFEXITED(status) && WEXITSTATUS(status) == 0))
+          throw std::runtime_error("A device process failed!");
+        if (p < 0) throw std::runtime_error("A device process failed!");
+      }
+      g_children.clear();
+    }
     if (verbose) cout << "Exit HaMMLET" << endl << flush;
     return 0;
   } catch (std::exception& e) {
+    signal(SIGCHLD, SIG_DFL);
+    killChildren();
     cout << flush;
     cerr << endl << flush << "[ERROR] " << e.what() << endl;
     cerr << "Terminating HaMMLET. The rest is silence." << endl << flush;

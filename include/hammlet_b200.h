@@ -84,7 +84,7 @@ int hml_get_coeffs(hml_t* h, float* dst_host, uint64_t n);
 int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks);
 /* How the boundary positions are found (the result is the same set):
  *   HML_DETECT_STREAM   every weight is read each time (4 bytes/observation, the HBM-roofline formulation);
- *   HML_DETECT_PYRAMID  (default) the device analogue of the reference's skip pointers
+ *   HML_DETECT_PYRAMID  the device analogue of the reference's skip pointers
  *                       (Blocks/BreakpointArray.hpp:150-182): a max pyramid over sub-blocks of 32 weights is
  *                       built at load, and only sub-blocks whose maximum reaches the threshold are read.
  *   HML_DETECT_CANDIDATES (default) the threshold of a Gibbs chain moves by a hair from sweep to sweep, so the
@@ -158,7 +158,9 @@ int hml_mix_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold,
 int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity);
 /* The last sweep's state sequence merged into maximal equal-state runs, as Records::record forms
  * them (Records.hpp:166-188): seg_size[i] observations in state seg_state[i].  Call with NULL
- * arrays to get *nsegments only. */
+ * arrays to get *nsegments only.  Segment mode: a COLLECTIVE call (every rank makes it after the same sweep) that
+ * returns the runs of the WHOLE sequence on every rank — a run that crosses a rank border is one entry, as it is one
+ * segment in the reference's files. */
 int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t* seg_state, uint64_t capacity);
 /* State marginals accumulated on the device: StateMarginals::addRecord / save (StateMarginals.hpp:51-137,268-310).
  * The structure is the reference's: the common refinement of all recorded segmentations, one count per state and
@@ -167,7 +169,12 @@ int hml_get_segments(hml_t* h, uint64_t* nsegments, uint64_t* seg_size, int16_t*
  * stream; the counts they need live in device memory); only hml_marginals_get moves data to the
  * host: seg_size[n] and counts[n * K] (row-major), which printed as `size TAB c_0 TAB ... c_{S-1}` with S = highest
  * recorded label + 1 is the reference's marginals file.  Loading new data or calling hml_marginals_reset starts over.
- * In segment mode the marginals are those of the rank's own positions. */
+ * Segment mode: every rank accumulates the marginals of its own positions on its own device; hml_marginals_add is
+ * collective (the ranks trade the state of their last block — 8 bytes — so that runs continue across rank borders), and
+ * hml_marginals_info(nsegments) / hml_marginals_get are collective and return the marginals of the WHOLE sequence on
+ * every rank: the ranks' lists concatenated, with the segment at a rank's first observation joined to its left
+ * neighbour unless a run of some recorded iteration really started there.  The result is the list a single handle
+ * holding the whole sequence accumulates (tests/mgpu_worker.py compares them entry by entry). */
 int hml_marginals_reset(hml_t* h, int K);
 int hml_marginals_add(hml_t* h);
 int hml_marginals_info(hml_t* h, uint64_t* nsegments, uint64_t* iterations, int* K);
@@ -208,6 +215,11 @@ int hml_load_segment_f32_device(hml_t* h, const float* x_dev, uint64_t len, uint
  * block starts reported as global positions). */
 int hml_segment_info(const hml_t* h, int* rank, int* world, uint64_t* seg_start, uint64_t* seg_len,
                      uint64_t* first_block, uint64_t* global_blocks);
+
+/* All-gather of `bytes` bytes of host memory per rank over the handle's communicator (recv_host: world x bytes, rank
+ * order); a plain copy without a communicator.  For the host side of a split sequence: the block lists behind the
+ * automatic priors, per-block outputs of recorded iterations.  Collective. */
+int hml_comm_allgather(hml_t* h, const void* send_host, uint64_t bytes, void* recv_host);
 
 /* How the per-sweep carries travel: peer mailboxes written over NVLink by one exchange kernel per rank
  * (CUDA IPC mappings made in hml_comm_init), or NCCL all-gathers when peer mapping is unavailable or the

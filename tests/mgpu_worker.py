@@ -3,7 +3,9 @@
 Every rank also loads the WHOLE sequence into a second, single handle on its own GPU and checks that the
 segment-split run reproduces it: weights bit for bit, block lists, sampled states (the Philox counters and
 the replayed uniforms are indexed by global block number, so the partition must not change a single draw),
-integer statistics exactly and fp64 statistics to 1e-12.  gloo carries the NCCL unique id.
+integer statistics exactly and fp64 statistics to 1e-12; the equal-state runs and the state marginals of recorded
+sweeps, which each rank accumulates for its own positions, merge to exactly the single handle's lists.  gloo carries
+the NCCL unique id.
 """
 import os
 import sys
@@ -40,6 +42,13 @@ def local_states_match(h, ref):
     fb = info["first_block"]
     assert np.array_equal(mine, full[fb:fb + mine.size]), "sampled states differ from the single-GPU run"
     return mine.size
+
+
+def runs_match(h, ref, what):
+    """hml_get_segments in segment mode is collective and returns the runs of the whole sequence on every rank."""
+    n, q = h.segments()
+    rn, rq = ref.segments()
+    assert np.array_equal(n, rn) and np.array_equal(q, rq), (what, n.size, rn.size)
 
 
 def allgather(obj):
@@ -99,12 +108,14 @@ def main():
         check_same(o, r, f"case {ci} replay")
         assert close(o["loglik"], r["loglik"], 1e-11), (ci, o["loglik"], r["loglik"])
         local_states_match(h, ref)
+        runs_match(h, ref, f"case {ci} replay")
 
         # ---- mixture sweep, static structure, Philox
         o = h.mix_sweep(mu, var, A, pi, seed=5, sweep=3)
         r = ref.mix_sweep(mu, var, A, pi, seed=5, sweep=3)
         check_same(o, r, f"case {ci} mixture")
         local_states_match(h, ref)
+        runs_match(h, ref, f"case {ci} mixture")
 
         # ---- dynamic Philox chain through the Gibbs driver: identical chains sweep by sweep
         if thr < 1e29:
@@ -115,11 +126,24 @@ def main():
             for state in (sa, sb):
                 state.mean, state.var = mu.copy(), var.copy()
                 state.A, state.pi = A.copy(), pi.copy()
+            # every sweep is recorded: the ranks keep the marginals of their own positions, the merged view must be the
+            # single handle's, entry by entry (a run that crosses a rank border is ONE segment: Records.hpp:166-188)
+            h.marginals_reset(K)
+            ref.marginals_reset(K)
             for i in range(6):
                 oa = gibbs.sample_hmm(h, sa, 1, seed=77, sweep0=i, use_self=bool(use_self))
                 ob = gibbs.sample_hmm(ref, sb, 1, seed=77, sweep0=i, use_self=bool(use_self))
                 check_same(oa, ob, f"case {ci} dynamic sweep {i}")
                 local_states_match(h, ref)
+                if i % 2 == 0:
+                    runs_match(h, ref, f"case {ci} dynamic sweep {i}")
+                h.marginals_add()
+                ref.marginals_add()
+                if i in (0, 3, 5):
+                    ms, mc, mi = h.marginals()
+                    rs, rc, ri = ref.marginals()
+                    assert mi == ri == i + 1 and ms.sum() == T
+                    assert np.array_equal(ms, rs) and np.array_equal(mc, rc), f"case {ci} sweep {i}: merged marginals differ"
                 # keep the two chains on identical parameters (the fp64 sums may differ in the last bits)
                 sb.mean, sb.var, sb.A, sb.pi = sa.mean.copy(), sa.var.copy(), sa.A.copy(), sa.pi.copy()
                 sb.rng.bit_generator.state = sa.rng.bit_generator.state
