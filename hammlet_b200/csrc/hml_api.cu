@@ -101,11 +101,14 @@ struct hml_ctx {
   // candidate list (HML_DETECT_CANDIDATES): positions, ascending, and weights of everything not below cand_floor
   uint32_t* cand_pos = nullptr;
   float* cand_w = nullptr;
+  double2* cand_pq = nullptr;        // integral pair of every candidate (univariate data)
+  double2* spq = nullptr;            // integral pairs of the block starts, in block order (capacity + 1)
+  bool spq_valid = false;            // ... of the current block structure
   uint32_t* cand_scratch = nullptr;  // per-CTA counts, offsets, ticket
   uint64_t cand_cap = 0, cand_n = 0;
   uint32_t cand_scratch_ctas = 0;
   float cand_floor = 0.f;
-  float cand_too_long_floor = -1.f;  // largest floor whose candidate list was not worth keeping (> T / 8 entries)
+  float cand_too_long_floor = -1.f;  // largest floor whose candidate list was not worth keeping (> T / 2 entries)
   bool cand_valid = false;
   uint64_t cand_rebuilds = 0;
   float* coeffs = nullptr;  // maxlet coefficients (kept for hml_get_coeffs while T is small)
@@ -248,6 +251,8 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
   const int MB = KP ? map_bytes(KP) : 8;
   if (cap != h->capacity) {
     CK(dev_alloc(h->starts, cap + 1));
+    CK(dev_alloc(h->spq, h->D == 1 ? cap + 1 : 1));
+    h->spq_valid = false;
     CK(dev_alloc(h->bN, cap));
     CK(dev_alloc(h->bS, cap * (uint64_t)h->D));
     CK(dev_alloc(h->states, cap));
@@ -297,6 +302,7 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.pq_stride = h->pq_stride;
   b.cell_stride = h->cell_stride;
   b.starts = h->starts;
+  b.spq = h->spq_valid ? h->spq : nullptr;
   b.nblocks = h->outblk;
   b.capacity = h->capacity;
   b.bN = h->bN;
@@ -407,11 +413,12 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP);
 // Candidate list for thresholds >= floor: one pyramid pass at the floor gives the positions (it is the block list of
 // that threshold), a gather their weights.  Grows the block arrays if the list does not fit (local to this rank; no
 // collective has been issued yet at this point of a sweep).
-// A list that is not much shorter than the sequence is not worth having (a tiny threshold makes every position a
-// candidate): *usable = false then, the floor is remembered so the pass is not repeated sweep after sweep, and the
-// caller takes the pyramid pass at the threshold itself.  The block arrays are never grown beyond T / kCandMaxShare
-// on behalf of the list.
-constexpr uint64_t kCandMaxShare = 8;
+// A list that holds most of the sequence is not worth having (a tiny threshold makes every position a candidate; the
+// pass over the list would read 8 bytes per candidate where the pyramid pass reads the weights once): *usable = false
+// then, the floor is remembered so the pass is not repeated sweep after sweep, and the caller takes the pyramid pass at
+// the threshold itself.  The block arrays are never grown beyond T / kCandMaxShare on behalf of the list (low
+// compression — C5: one block per 2 to 10 observations — still gets its list).
+constexpr uint64_t kCandMaxShare = 2;
 int rebuild_candidates(hml_t* h, float floor, bool* usable) {
   *usable = false;
   const uint64_t limit = h->T / kCandMaxShare;
@@ -436,14 +443,16 @@ int rebuild_candidates(hml_t* h, float floor, bool* usable) {
       h->cand_cap = n + n / 4 + 4096;
       CK(dev_alloc(h->cand_pos, h->cand_cap));
       CK(dev_alloc(h->cand_w, h->cand_cap));
+      if (h->D == 1) CK(dev_alloc(h->cand_pq, h->cand_cap));
     }
+    if (h->D != 1) dev_free(h->cand_pq);
     const uint32_t ctas = cand_ctas((uint32_t)h->cand_cap);
     if (ctas > h->cand_scratch_ctas) {
       h->cand_scratch_ctas = ctas;
       CK(dev_alloc(h->cand_scratch, 2 * (size_t)ctas + 1));
       CK(cudaMemsetAsync(h->cand_scratch, 0, (2 * (size_t)ctas + 1) * sizeof(uint32_t), h->stream));
     }
-    launch_cand_gather(h->w, h->starts, (uint32_t)n, h->cand_w, h->cand_pos, h->sms, h->stream);
+    launch_cand_gather(h->w, h->pq, h->starts, (uint32_t)n, h->cand_w, h->cand_pos, h->cand_pq, h->sms, h->stream);
     h->launches++;
     CK(cudaGetLastError());
     h->cand_n = n;
@@ -474,12 +483,14 @@ int run_detect(hml_t* h, float thr) {
       if (rc != HML_OK) return rc;
     }
     if (usable && h->cand_n > 0) {
-      h->launches += launch_detect_candidates(h->cand_w, h->cand_pos, (uint32_t)h->cand_n, thr, h->cand_scratch,
-                                              h->cand_scratch_ctas, h->starts, h->capacity, h->T, h->outblk, h->stream,
-                                              stage_cb, h);
+      h->launches += launch_detect_candidates(h->cand_w, h->cand_pos, h->cand_pq, (uint32_t)h->cand_n, thr, h->cand_scratch,
+                                              h->cand_scratch_ctas, h->starts, h->spq, h->pq, h->capacity, h->T, h->outblk,
+                                              h->stream, stage_cb, h);
+      h->spq_valid = h->cand_pq != nullptr;
       done = true;
     }
   }
+  if (!done) h->spq_valid = false;
   if (!done) {  // thresholds <= 0, NaN, inf (and an empty candidate list): every weight is looked at
     h->launches += launch_detect(h->w, h->detect_mode != HML_DETECT_STREAM ? h->smax : nullptr, h->T, thr,
                                  h->rank == 0 ? 1 : 0, h->detect_scratch, h->starts, h->capacity, h->outblk, h->stream,
@@ -1233,6 +1244,8 @@ int hml_destroy(hml_t* h) {
   dev_free(h->group_ain);
   dev_free(h->cand_pos);
   dev_free(h->cand_w);
+  dev_free(h->cand_pq);
+  dev_free(h->spq);
   dev_free(h->cand_scratch);
   dev_free(h->seg_counts);
   dev_free(h->seg_starts);

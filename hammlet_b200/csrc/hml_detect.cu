@@ -469,12 +469,17 @@ __global__ void __launch_bounds__(256)
 constexpr int kCandPerThread = 8;                      // two float4
 constexpr int kCandPerCta = 256 * kCandPerThread;      // 2048
 
-__global__ void __launch_bounds__(256) k_cand_gather(const float* __restrict__ w, const uint32_t* __restrict__ starts,
-                                                     uint32_t n, float* __restrict__ cand_w, uint32_t* __restrict__ cand_pos) {
+__global__ void __launch_bounds__(256) k_cand_gather(const float* __restrict__ w, const double2* __restrict__ pq,
+                                                     const uint32_t* __restrict__ starts, uint32_t n,
+                                                     float* __restrict__ cand_w, uint32_t* __restrict__ cand_pos,
+                                                     double2* __restrict__ cand_pq) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t p = starts[i];
     cand_pos[i] = p;
     cand_w[i] = w[p];
+    // the integral pair of the candidate travels with it (univariate data): the random 16-byte gathers into the
+    // T-sized integral arrays — a 64-byte DRAM burst each — are paid once per list, not twice per block and sweep
+    if (cand_pq) cand_pq[i] = pq[p];
   }
 }
 
@@ -499,7 +504,8 @@ __device__ __forceinline__ uint32_t cand_flags(const float4* __restrict__ cw4, u
 __global__ void __launch_bounds__(256)
     k_cand_count(const float4* __restrict__ cw4, uint32_t nc, float thr, uint32_t nctas, uint32_t* __restrict__ cta_count,
                  uint32_t* __restrict__ cta_off, unsigned int* __restrict__ ticket, unsigned long long* __restrict__ nblocks_out,
-                 uint32_t* __restrict__ starts, uint64_t capacity, uint64_t T) {
+                 uint32_t* __restrict__ starts, uint64_t capacity, uint64_t T, const double2* __restrict__ pq,
+                 double2* __restrict__ spq) {
   pdl_enter();
   __shared__ uint32_t s_warp[8];
   __shared__ bool s_last;
@@ -536,7 +542,10 @@ __global__ void __launch_bounds__(256)
       run += v;
     }
     *nblocks_out = run;
-    if ((uint64_t)run <= capacity) starts[run] = (uint32_t)T;  // sentinel: block b = [starts[b], starts[b + 1])
+    if ((uint64_t)run <= capacity) {
+      starts[run] = (uint32_t)T;  // sentinel: block b = [starts[b], starts[b + 1])
+      if (spq) spq[run] = pq[T];
+    }
     *ticket = 0;
   }
   __syncthreads();
@@ -550,7 +559,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_cand_scatter(const float4* __restrict__ cw4, const uint4* __restrict__ cpos4, uint32_t nc, float thr,
-                   const uint32_t* __restrict__ cta_off, uint32_t* __restrict__ starts, uint64_t capacity) {
+                   const uint32_t* __restrict__ cta_off, uint32_t* __restrict__ starts, uint64_t capacity,
+                   const double2* __restrict__ cand_pq, double2* __restrict__ spq) {
   pdl_enter();
   __shared__ uint32_t s_warp[8];
   const uint32_t f = cand_flags(cw4, nc, thr);
@@ -584,37 +594,48 @@ __global__ void __launch_bounds__(256)
       const uint32_t i0 = base + half * 1024u + 4u * threadIdx.x;
       const uint4 p = cpos4[i0 >> 2];
       uint64_t& o = half ? o1 : o0;
-      if (m & 1u) { if (o < capacity) starts[o] = p.x; ++o; }
-      if (m & 2u) { if (o < capacity) starts[o] = p.y; ++o; }
-      if (m & 4u) { if (o < capacity) starts[o] = p.z; ++o; }
-      if (m & 8u) { if (o < capacity) starts[o] = p.w; ++o; }
+      // the surviving candidates' integral pairs land next to each other in block order: the emission kernel reads
+      // the pairs of block b and b + 1 from adjacent slots
+      if (spq) {
+        if (m & 1u) { if (o < capacity) { starts[o] = p.x; spq[o] = cand_pq[i0]; } ++o; }
+        if (m & 2u) { if (o < capacity) { starts[o] = p.y; spq[o] = cand_pq[i0 + 1]; } ++o; }
+        if (m & 4u) { if (o < capacity) { starts[o] = p.z; spq[o] = cand_pq[i0 + 2]; } ++o; }
+        if (m & 8u) { if (o < capacity) { starts[o] = p.w; spq[o] = cand_pq[i0 + 3]; } ++o; }
+      } else {
+        if (m & 1u) { if (o < capacity) starts[o] = p.x; ++o; }
+        if (m & 2u) { if (o < capacity) starts[o] = p.y; ++o; }
+        if (m & 4u) { if (o < capacity) starts[o] = p.z; ++o; }
+        if (m & 8u) { if (o < capacity) starts[o] = p.w; ++o; }
+      }
     }
   }
 }
 
-void launch_cand_gather(const float* w, const uint32_t* starts, uint32_t n, float* cand_w, uint32_t* cand_pos, int sms,
-                        cudaStream_t s) {
+void launch_cand_gather(const float* w, const double2* pq, const uint32_t* starts, uint32_t n, float* cand_w,
+                        uint32_t* cand_pos, double2* cand_pq, int sms, cudaStream_t s) {
   if (n == 0) return;
   int g = (int)((n + 255) / 256);
   if (g > sms * 16) g = sms * 16;
-  k_cand_gather<<<g, 256, 0, s>>>(w, starts, n, cand_w, cand_pos);
+  k_cand_gather<<<g, 256, 0, s>>>(w, pq, starts, n, cand_w, cand_pos, cand_pq);
 }
 
 // boundaries among the candidates; cta_scratch holds 2 * ctas + 1 words (counts, offsets, ticket = last word, zeroed
 // once by the caller and left at zero by the kernel).  Returns the number of launches.
-int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, uint32_t nc, float thr, uint32_t* cta_scratch,
-                             uint32_t scratch_ctas, uint32_t* starts, uint64_t capacity, uint64_t T,
-                             unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb, void* user) {
+int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, const double2* cand_pq, uint32_t nc, float thr,
+                             uint32_t* cta_scratch, uint32_t scratch_ctas, uint32_t* starts, double2* spq, const double2* pq,
+                             uint64_t capacity, uint64_t T, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
+                             void* user) {
+  if (!cand_pq) spq = nullptr;
   const uint32_t ctas = (nc + kCandPerCta - 1) / kCandPerCta;
   uint32_t* cta_count = cta_scratch;
   uint32_t* cta_off = cta_scratch + scratch_ctas;
   unsigned int* ticket = cta_scratch + 2 * scratch_ctas;
   if (cb) cb(user, "detect_cand");
   launch_k(k_cand_count, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), nc, thr, ctas, cta_count, cta_off, ticket,
-           nblocks_out, starts, capacity, T);
+           nblocks_out, starts, capacity, T, pq, spq);
   if (cb) cb(user, "detect_scatter");
   launch_k(k_cand_scatter, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), reinterpret_cast<const uint4*>(cand_pos),
-           nc, thr, (const uint32_t*)cta_off, starts, capacity);
+           nc, thr, (const uint32_t*)cta_off, starts, capacity, cand_pq, spq);
   return 2;
 }
 uint32_t cand_ctas(uint32_t nc) { return (nc + kCandPerCta - 1) / kCandPerCta; }

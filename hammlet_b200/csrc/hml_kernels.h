@@ -31,12 +31,16 @@ int launch_detect(const float* w, const uint16_t* smax, uint64_t T, float thr, i
                   uint32_t* starts, uint64_t capacity, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
                   void* user);
 // candidate mode: the positions (ascending) and weights of everything that can be a boundary while thr >= floor
-void launch_cand_gather(const float* w, const uint32_t* starts, uint32_t n, float* cand_w, uint32_t* cand_pos, int sms,
-                        cudaStream_t s);
+// cand_pq (may be null: multivariate data) receives the integral pair pq[position] of every candidate
+void launch_cand_gather(const float* w, const double2* pq, const uint32_t* starts, uint32_t n, float* cand_w,
+                        uint32_t* cand_pos, double2* cand_pq, int sms, cudaStream_t s);
 uint32_t cand_ctas(uint32_t nc);
-int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, uint32_t nc, float thr, uint32_t* cta_scratch,
-                             uint32_t scratch_ctas, uint32_t* starts, uint64_t capacity, uint64_t T,
-                             unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb, void* user);
+// spq (capacity + 1 entries; ignored without cand_pq) receives the integral pairs of the block starts, in block order,
+// and pq[T] behind the last one: SweepBuffers::spq for the block statistics of this structure
+int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, const double2* cand_pq, uint32_t nc, float thr,
+                             uint32_t* cta_scratch, uint32_t scratch_ctas, uint32_t* starts, double2* spq, const double2* pq,
+                             uint64_t capacity, uint64_t T, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
+                             void* user);
 size_t pyramid_entries(uint64_t T);  // bf16 entries, one per 32 weights, padded to whole spans
 void launch_build_pyramid(const float* w, uint64_t T, uint16_t* smax, int sms, cudaStream_t s);
 const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);
@@ -105,6 +109,8 @@ struct SweepBuffers {
   uint64_t pq_stride, cell_stride;
   // block structure
   const uint32_t* starts;   // capacity+1, natural order
+  const double2* spq;       // capacity+1, natural order: pq[starts[b]] (and pq[T] behind the last block) when the block
+                            // list came from the candidate list (univariate data), else null: gather from pq
   const unsigned long long* nblocks;  // device scalar
   uint64_t capacity;        // blocks the per-block arrays can hold
   uint32_t* bN;             // block sizes

@@ -295,6 +295,8 @@ __device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, 
   // partial sums within K * 2^-51 of those; the two can only disagree about `cp[k] >= u` if a partial sum lands that
   // close to u, and then — about once in 1e11 draws — the draw is repeated with the divisions, so the result is the
   // reference's for every u.
+  // The comparison is made on the sign of d = acc - u (a rounded difference has the sign of the exact one) and the
+  // closeness test on d's exponent field, both in the integer pipe: the fp64 pipe sees one add where it saw one compare.
   const double inv = 1.0 / s;
   double acc = 0.0;
   uint32_t res = (uint32_t)(K - 1);
@@ -302,9 +304,10 @@ __device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, 
 #pragma unroll
   for (int k = 0; k < KP - 1; ++k) {
     if (k < K - 1) {
-      acc += p[k] * inv;
-      tie |= fabs(acc - u) < 1e-12;
-      if (!found && acc >= u) {
+      acc = fma(p[k], inv, acc);
+      const int hi = __double2hiint(acc - u);
+      tie |= (hi & 0x7fffffff) < 0x3D700000;  // |acc - u| < 2^-40
+      if (!found && hi >= 0) {                 // acc >= u
         res = (uint32_t)k;
         found = true;
       }
@@ -357,6 +360,17 @@ __device__ __forceinline__ bool seg_later_blocks(const SegInfo& g) {  // does an
 
 // (sum x, sum x^2) over the local observations [s, e) from the integral arrays
 // (Statistics/IntegralArray.hpp:104-124): cell-local running sums + double-double cell offsets
+__device__ __forceinline__ void range_sums_from(const SweepBuffers& buf, const double2 ps, const double2 pe, uint32_t s,
+                                                uint32_t e, double& sx, double& sq) {
+  sx = pe.x - ps.x;
+  sq = pe.y - ps.y;
+  const uint32_t cs = s >> kCellLog2, ce = e >> kCellLog2;
+  if (cs != ce) {
+    const double4 a = buf.cell_pref[cs], z = buf.cell_pref[ce];
+    sx += (z.x - a.x) + (z.y - a.y);
+    sq += (z.z - a.z) + (z.w - a.w);
+  }
+}
 __device__ __forceinline__ void range_sums(const SweepBuffers& buf, uint32_t s, uint32_t e, double& sx, double& sq) {
   const double2 ps = buf.pq[s], pe = buf.pq[e];
   sx = pe.x - ps.x;
@@ -423,6 +437,11 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
   constexpr bool kStage = kEmit && KP <= 8;
   __shared__ double s_e[kStage ? 256 * KP : 1];
   __shared__ double s_sp[(kStage && !kMix) ? 256 * KP : 1];
+  __shared__ double s_tab[kEmit ? 64 : 1];  // 2^(j/64) for exp_nonpos
+  if (kEmit) {
+    exp_table_load(s_tab);
+    __syncthreads();
+  }
   if (kEmit && blockIdx.x == 0) {
     // first kernel of a sweep: zero the result block that the later kernels accumulate into
     for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
@@ -440,7 +459,10 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
     if (valid) {
       if (kGather) {
         const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
-        range_sums(buf, s, e, sx, sq);
+        if (buf.spq)  // the pairs of this block's start and end sit next to each other (candidate list)
+          range_sums_from(buf, buf.spq[b], buf.spq[b + 1], s, e, sx, sq);
+        else
+          range_sums(buf, s, e, sx, sq);
         n = e - s;
         if (buf.seg.world > 1 && b + 1 == B) {
           // the rank's last block continues on the following ranks up to their first boundary
@@ -475,10 +497,10 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
       }
       if (kStage) {
 #pragma unroll
-        for (int s = 0; s < KP; ++s) s_e[threadIdx.x * KP + s] = (valid && s < m.K) ? exp(E[s] - mx) : 0.0;
+        for (int s = 0; s < KP; ++s) s_e[threadIdx.x * KP + s] = (valid && s < m.K) ? exp_nonpos(E[s] - mx, s_tab) : 0.0;
         if (!kMix) {
 #pragma unroll
-          for (int s = 0; s < KP; ++s) s_sp[threadIdx.x * KP + s] = (valid && s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+          for (int s = 0; s < KP; ++s) s_sp[threadIdx.x * KP + s] = (valid && s < m.K) ? exp_nonpos((N - 1.0) * m.loga[s], s_tab) : 0.0;
         }
         __syncthreads();
         const uint64_t base = (p - threadIdx.x) * KP;  // first word of the CTA's 256 slots
@@ -490,10 +512,10 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
         __syncthreads();
       } else {
 #pragma unroll
-        for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp(E[s] - mx) : 0.0;
+        for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp_nonpos(E[s] - mx, s_tab) : 0.0;
         if (!kMix) {
 #pragma unroll
-          for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+          for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp_nonpos((N - 1.0) * m.loga[s], s_tab) : 0.0;
         }
       }
       if (want_maxe && valid) buf.maxE[p] = mx;
@@ -506,6 +528,11 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
 template <int KP, bool kGather, bool kEmit, bool kMix>
 __global__ void __launch_bounds__(256) k_block_emit_md(SweepBuffers buf, EmitMD<KP> m, int want_maxe) {
   pdl_enter();
+  __shared__ double s_tab[kEmit ? 64 : 1];
+  if (kEmit) {
+    exp_table_load(s_tab);
+    __syncthreads();
+  }
   if (kEmit && blockIdx.x == 0) {
     for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
     for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
@@ -556,10 +583,10 @@ __global__ void __launch_bounds__(256) k_block_emit_md(SweepBuffers buf, EmitMD<
         if (s < m.K) mx = fmax(mx, v);
       }
 #pragma unroll
-      for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp(E[s] - mx) : 0.0;
+      for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp_nonpos(E[s] - mx, s_tab) : 0.0;
       if (!kMix) {
 #pragma unroll
-        for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp((N - 1.0) * m.loga[s]) : 0.0;
+        for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp_nonpos((N - 1.0) * m.loga[s], s_tab) : 0.0;
       }
       if (want_maxe) buf.maxE[p] = mx;
     }

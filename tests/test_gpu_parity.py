@@ -158,7 +158,7 @@ def test_candidate_list_follows_the_threshold(dev):
     dev.load(x)
     assert dev.detect_info()[0] == capi.DETECT_CANDIDATES
     sizes = []
-    #       build   reuse  reuse  below the floor  far above: kept once, then found too long, reuse  tiny: outgrows the block arrays
+    #       build   reuse  reuse  below the floor  far above: kept once, then found too long, reuse  tiny: no list worth keeping
     for thr in (1.0, 0.9999, 1.3, 0.7, 6.0, 6.5, 7.0, 0.02, 0.021, 1.0):
         B = dev.create_blocks(thr)
         ref = O32.boundaries(w, np.float32(thr))
@@ -170,9 +170,10 @@ def test_candidate_list_follows_the_threshold(dev):
     assert cand[3] > cand[0]                                  # 0.7: rebuilt at a lower floor
     assert cand[4] == cand[3]                                 # 6.0: the block count that says "too long" is the previous sweep's
     assert cand[5] < cand[3] / 4 and cand[6] == cand[5]       # 6.5: rebuilt, 7.0: reused
-    assert cand[7] > cand[3] and cand[8] == cand[7]           # 0.02: far below the floor; 0.021: reused
-    assert cand[9] == cand[8]                                 # 1.0 after 0.021: kept once more (see above)
-    assert all(c >= B for _, B, c in sizes)
+    assert cand[7] == 0 and cand[8] == 0                      # 0.02, 0.021: the list would hold most of the sequence (> T / 2):
+    #                                                           the candidate path stands down, the pyramid pass runs
+    assert cand[9] == cand[0]                                 # 1.0 again: rebuilt at the floor of the first list
+    assert all(c >= B for _, B, c in sizes if c)
     # a dynamic sweep uses the same path
     mu, var, A, pi = model_guess(5, seed=5)
     out = dev.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=0.95, seed=1, sweep=0)
