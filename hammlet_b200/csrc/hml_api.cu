@@ -132,7 +132,7 @@ struct hml_ctx {
   // per-sweep buffers (sized by capacity and KP)
   int KP = 0;
   int last_K = 0;
-  double *e = nullptr, *sp = nullptr, *maxE = nullptr, *alpha = nullptr;
+  double *e = nullptr, *maxE = nullptr, *alpha = nullptr;
   uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *tile_maps = nullptr, *tile_qin = nullptr;
   double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr, *group_ain = nullptr;
   int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr, *wide_exp = nullptr;
@@ -264,7 +264,6 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
   }
   if (KP && (cap != h->capacity || KP != h->KP)) {
     CK(dev_alloc(h->e, cap * KP));
-    CK(dev_alloc(h->sp, cap * KP));
     CK(dev_alloc(h->alpha, cap * KP));
     CK(dev_alloc(h->maxE, cap));
     CK(dev_alloc(h->maps, cap * MB));
@@ -308,7 +307,6 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.bN = h->bN;
   b.bS = h->bS;
   b.e = h->e;
-  b.sp = h->sp;
   b.maxE = h->maxE;
   b.alpha = h->alpha;
   b.maps = h->maps;
@@ -1229,7 +1227,6 @@ int hml_destroy(hml_t* h) {
   dev_free(h->bN);
   dev_free(h->bS);
   dev_free(h->e);
-  dev_free(h->sp);
   dev_free(h->maxE);
   dev_free(h->alpha);
   dev_free(h->maps);

@@ -558,11 +558,12 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    k_cand_scatter(const float4* __restrict__ cw4, const uint4* __restrict__ cpos4, uint32_t nc, float thr,
+    k_cand_scatter(const float4* __restrict__ cw4, const uint32_t* __restrict__ cpos, uint32_t nc, float thr,
                    const uint32_t* __restrict__ cta_off, uint32_t* __restrict__ starts, uint64_t capacity,
                    const double2* __restrict__ cand_pq, double2* __restrict__ spq) {
   pdl_enter();
   __shared__ uint32_t s_warp[8];
+  __shared__ uint16_t s_rank[kCandPerCta];  // rank of every candidate of the CTA among its boundaries, 0xffff: none
   const uint32_t f = cand_flags(cw4, nc, thr);
   // counts of the two halves packed (each <= 4 per thread, <= 1024 per CTA): one scan ranks both
   const uint32_t mine = __popc(f & 0xfu) | (__popc(f >> 4) << 16);
@@ -583,30 +584,35 @@ __global__ void __launch_bounds__(256)
     total += v;
   }
   const uint32_t excl = before + incl - mine;
-  const uint32_t base = blockIdx.x * (uint32_t)kCandPerCta;
-  const uint64_t off = cta_off[blockIdx.x];
-  uint64_t o0 = off + (excl & 0xffffu);                          // first half: ranks among first-half flags
-  uint64_t o1 = off + (total & 0xffffu) + (excl >> 16);          // second half comes after the whole first half
+  uint32_t r0 = excl & 0xffffu;                       // first half: ranks among first-half flags
+  uint32_t r1 = (total & 0xffffu) + (excl >> 16);     // second half comes after the whole first half
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const uint32_t m = (f >> (4 * half)) & 0xfu;
-    if (m) {
-      const uint32_t i0 = base + half * 1024u + 4u * threadIdx.x;
-      const uint4 p = cpos4[i0 >> 2];
-      uint64_t& o = half ? o1 : o0;
-      // the surviving candidates' integral pairs land next to each other in block order: the emission kernel reads
-      // the pairs of block b and b + 1 from adjacent slots
-      if (spq) {
-        if (m & 1u) { if (o < capacity) { starts[o] = p.x; spq[o] = cand_pq[i0]; } ++o; }
-        if (m & 2u) { if (o < capacity) { starts[o] = p.y; spq[o] = cand_pq[i0 + 1]; } ++o; }
-        if (m & 4u) { if (o < capacity) { starts[o] = p.z; spq[o] = cand_pq[i0 + 2]; } ++o; }
-        if (m & 8u) { if (o < capacity) { starts[o] = p.w; spq[o] = cand_pq[i0 + 3]; } ++o; }
-      } else {
-        if (m & 1u) { if (o < capacity) starts[o] = p.x; ++o; }
-        if (m & 2u) { if (o < capacity) starts[o] = p.y; ++o; }
-        if (m & 4u) { if (o < capacity) starts[o] = p.z; ++o; }
-        if (m & 8u) { if (o < capacity) starts[o] = p.w; ++o; }
-      }
+    uint32_t& r = half ? r1 : r0;
+    uint16_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = (m >> k) & 1u ? (uint16_t)r : (uint16_t)0xffffu;
+      r += (m >> k) & 1u;
+    }
+    *reinterpret_cast<uint2*>(&s_rank[half * 1024 + 4 * threadIdx.x]) =
+        make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+  }
+  __syncthreads();
+  // Second phase, thread per candidate with consecutive threads on consecutive candidates: positions and integral
+  // pairs are read as contiguous pieces and the survivors land next to each other in block order — the emission kernel
+  // reads the pairs of block b and b + 1 from adjacent slots.  (Four consecutive candidates per thread, loaded where
+  // they are stored, cost a 64-byte stride between lanes and one DRAM round trip after the other: 22 us against 11.)
+  const uint32_t base = blockIdx.x * (uint32_t)kCandPerCta;
+  const uint64_t off = cta_off[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kCandPerThread; ++k) {
+    const uint32_t li = k * 256u + threadIdx.x;
+    const uint32_t r = s_rank[li];
+    if (r != 0xffffu && off + r < capacity) {
+      starts[off + r] = cpos[base + li];
+      if (spq) spq[off + r] = cand_pq[base + li];
     }
   }
 }
@@ -634,8 +640,8 @@ int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, cons
   launch_k(k_cand_count, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), nc, thr, ctas, cta_count, cta_off, ticket,
            nblocks_out, starts, capacity, T, pq, spq);
   if (cb) cb(user, "detect_scatter");
-  launch_k(k_cand_scatter, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), reinterpret_cast<const uint4*>(cand_pos),
-           nc, thr, (const uint32_t*)cta_off, starts, capacity, cand_pq, spq);
+  launch_k(k_cand_scatter, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), cand_pos, nc, thr,
+           (const uint32_t*)cta_off, starts, capacity, cand_pq, spq);
   return 2;
 }
 uint32_t cand_ctas(uint32_t nc) { return (nc + kCandPerCta - 1) / kCandPerCta; }

@@ -117,7 +117,6 @@ struct SweepBuffers {
   double2* bS;              // block (sum x, sum x^2)
   // per sweep
   double* e;                // KP per block: exp(E_s - maxE)
-  double* sp;               // KP per block: exp((N-1) log A_ss)   (self-transition rescale, FB.hpp:115-119)
   double* maxE;             // per block (only filled for loglik)
   double* alpha;            // KP per block: normalised forward vector alpha_t
   uint8_t* maps;            // KPB bytes per block: backward map j -> state

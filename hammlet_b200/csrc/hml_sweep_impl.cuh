@@ -283,46 +283,35 @@ struct Map {
 };
 
 // std::discrete_distribution rule (libstdc++ bits/random.tcc, used by Trellis.hpp:61-66 and
-// Mixture.hpp:111-112): normalise, partial sums, last := 1, first k with cp[k] >= u.  A row without
-// positive mass gives NaN partial sums in the reference, for which lower_bound returns index 0.
+// Mixture.hpp:111-112): normalise (every weight divided by the sum), partial sums, last := 1, first k with
+// cp[k] >= u.  A row without positive mass gives NaN partial sums in the reference, for which lower_bound
+// returns index 0.
+//
+// discrete_draw_exact follows it operation for operation (round-to-nearest intrinsics, so nothing is contracted).
+// discrete_draw_fast needs no division at all: with c[k] the running sums of the weights, cp[k] >= u is decided as
+// c[k] >= u * c[K-1].  The two can disagree only if some cp[k] lies within K * 2^-51 of u; the fast version reports
+// |c[k] - u s| < 2^-40 s as a tie and the caller then takes the exact path — about once in 1e11 draws — so the result
+// is the reference's for every u.  The comparison is made on the sign and the exponent field of d = c[k] - u s in the
+// integer pipe (a rounded difference has the sign of the exact one).
 template <int KP>
-__device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, double u) {
+struct Weights {
+  double v[KP];
+};
+// out of line: it runs about once in 1e11 draws and its divisions must not cost the callers registers
+template <int KP>
+__device__ __noinline__ uint32_t discrete_draw_exact(const Weights<KP> wp, int K, double u) {
+  const double (&p)[KP] = wp.v;
   double s = 0.0;
 #pragma unroll
-  for (int k = 0; k < KP; ++k) s += (k < K) ? p[k] : 0.0;
+  for (int k = 0; k < KP; ++k) s = (k < K) ? __dadd_rn(s, p[k]) : s;
   if (!(s > 0.0)) return 0u;
-  // libstdc++ divides every weight by the sum (__normalize).  Multiplying by the reciprocal is cheaper and gives
-  // partial sums within K * 2^-51 of those; the two can only disagree about `cp[k] >= u` if a partial sum lands that
-  // close to u, and then — about once in 1e11 draws — the draw is repeated with the divisions, so the result is the
-  // reference's for every u.
-  // The comparison is made on the sign of d = acc - u (a rounded difference has the sign of the exact one) and the
-  // closeness test on d's exponent field, both in the integer pipe: the fp64 pipe sees one add where it saw one compare.
-  const double inv = 1.0 / s;
   double acc = 0.0;
   uint32_t res = (uint32_t)(K - 1);
-  bool found = false, tie = false;
+  bool found = false;
 #pragma unroll
   for (int k = 0; k < KP - 1; ++k) {
     if (k < K - 1) {
-      acc = fma(p[k], inv, acc);
-      const int hi = __double2hiint(acc - u);
-      tie |= (hi & 0x7fffffff) < 0x3D700000;  // |acc - u| < 2^-40
-      if (!found && hi >= 0) {                 // acc >= u
-        res = (uint32_t)k;
-        found = true;
-      }
-    }
-  }
-  if (tie) {
-    acc = 0.0;
-    res = (uint32_t)(K - 1);
-    found = false;
-#pragma unroll 1
-    for (int k = 0; k < K - 1; ++k) {
-      double pk = 0.0;
-#pragma unroll
-      for (int j = 0; j < KP; ++j) pk = (j == k) ? p[j] : pk;
-      acc += pk / s;
+      acc = __dadd_rn(acc, __ddiv_rn(p[k], s));
       if (!found && acc >= u) {
         res = (uint32_t)k;
         found = true;
@@ -330,6 +319,48 @@ __device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, 
     }
   }
   return res;
+}
+
+// c[k] = p[0] + ... + p[k] (c[KP-1] = the sum: weights of padded states are zero)
+template <int KP>
+__device__ __forceinline__ uint32_t discrete_draw_fast(const double (&c)[KP], int K, double u, bool& tie) {
+  const double s = c[KP - 1];
+  tie = false;
+  if (!(s > 0.0)) return 0u;
+  const double us = u * s;
+  const int lim = (__double2hiint(s) & 0x7ff00000) - (40 << 20);
+  uint32_t res = (uint32_t)(K - 1);
+  bool found = false;
+#pragma unroll
+  for (int k = 0; k < KP - 1; ++k) {
+    if (k < K - 1) {
+      const int hi = __double2hiint(c[k] - us);
+      tie |= (hi & 0x7ff00000) < lim;
+      if (!found && hi >= 0) {
+        res = (uint32_t)k;
+        found = true;
+      }
+    }
+  }
+  return res;
+}
+
+// weights given directly (the last block of the backward pass, the mixture sampler)
+template <int KP>
+__device__ __forceinline__ uint32_t discrete_draw(const double (&p)[KP], int K, double u) {
+  double c[KP];
+  c[0] = p[0];
+#pragma unroll
+  for (int k = 1; k < KP; ++k) c[k] = c[k - 1] + ((k < K) ? p[k] : 0.0);
+  bool tie;
+  uint32_t r = discrete_draw_fast<KP>(c, K, u, tie);
+  if (tie) {
+    Weights<KP> w;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) w.v[k] = p[k];
+    r = discrete_draw_exact<KP>(w, K, u);
+  }
+  return r;
 }
 
 // Number of blocks the kernels may touch.  If boundary detection found more blocks than the per-block
@@ -425,18 +456,60 @@ static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint3
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_block_emit: thread per storage slot
+// k_block_emit: block statistics + emission terms
 
+// block b's (N, sum x, sum x^2) from the integral arrays; in segment mode the rank's last block continues on the
+// following ranks up to their first boundary
+__device__ __forceinline__ void block_sums(const SweepBuffers& buf, uint64_t b, uint64_t B, uint32_t& n, double& sx, double& sq) {
+  const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
+  if (buf.spq)  // the pairs of this block's start and end sit next to each other (candidate list)
+    range_sums_from(buf, buf.spq[b], buf.spq[b + 1], s, e, sx, sq);
+  else
+    range_sums(buf, s, e, sx, sq);
+  n = e - s;
+  if (buf.seg.world > 1 && b + 1 == B) {
+    for (int r = buf.seg.rank + 1; r < buf.seg.world; ++r) {
+      const double* hd = buf.seg.heads + 4 * r;
+      n += (uint32_t)hd[1];
+      sx += hd[2];
+      sq += hd[3];
+      if (hd[0] > 0.0) break;
+    }
+  }
+}
+
+// the K emission log-weights of a block, EFD.hpp:23-32 then FB.hpp:74-81 (Mixture.hpp:98 has no self-transition term)
+template <int KP, bool kMix>
+__device__ __forceinline__ double emission_terms(const ModelDev<KP>& m, double N, double sx, double sq, double (&E)[KP]) {
+  double mx = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < KP; ++s) {
+    double v = (2.0 * m.mean[s] * sx - sq) * m.inv2var[s] - N * m.lognorm[s];
+    if (!kMix) v += (N - 1.0) * m.loga[s];
+    E[s] = v;
+    if (s < m.K) mx = fmax(mx, v);
+  }
+  return mx;
+}
+
+// The self-transition rescale A_ss^(N-1) of FB.hpp:115-119 is not stored: k_bwd_maps, its only reader, derives it
+// from the block size (5 table-based exps there against 8 K bytes per block written here and read there).
 template <int KP, bool kGather, bool kEmit, bool kMix>
 __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<KP> m, int want_maxe) {
   pdl_enter();
-  // K <= 8: the K emission terms of a block sit KP * 8 bytes apart from the next block's, so a warp storing "term s of
-  // my block" touches 32 * KP * 8 / 32 sectors per instruction — five times the sectors the data occupies at K = 5, and
-  // the L1 store path, not DRAM, bounded the kernel.  The terms of the CTA's 256 consecutive slots are staged in shared
-  // memory and written as one contiguous piece (consecutive threads, consecutive words).
-  constexpr bool kStage = kEmit && KP <= 8;
-  __shared__ double s_e[kStage ? 256 * KP : 1];
-  __shared__ double s_sp[(kStage && !kMix) ? 256 * KP : 1];
+  // K <= 8, dynamic blocks (the default path): the CTA takes 256 CONSECUTIVE blocks — eight chunks of a tile — so that
+  // the block starts and the integral pairs are read as contiguous pieces (a thread per storage slot reads 32 different
+  // sectors per warp instruction: 11 of 32 bytes used, the L1 pipe 70 % busy, the kernel bound by it), and hands its
+  // results to the chunk-interleaved layout through shared memory: the eight chunks' values of a step sit next to each
+  // other in storage, so every step is one contiguous piece of 8 * KP doubles.  Row pitches (33 * KP doubles, 36
+  // scalars) keep both the natural-order writes and the storage-order reads at the minimum of two wavefronts per
+  // 64-bit access.
+  constexpr bool kNatural = kEmit && kGather && KP <= 8;
+  constexpr bool kStage = kEmit && KP <= 8 && !kNatural;
+  constexpr int PE = 33 * KP, PB = 36;
+  __shared__ double s_e[kNatural ? 8 * PE : (kStage ? 256 * KP : 1)];
+  __shared__ double s_sx[kNatural ? 8 * PB : 1], s_sq[kNatural ? 8 * PB : 1];
+  __shared__ uint32_t s_n[kNatural ? 8 * PB : 1];
   __shared__ double s_tab[kEmit ? 64 : 1];  // 2^(j/64) for exp_nonpos
   if (kEmit) {
     exp_table_load(s_tab);
@@ -449,6 +522,43 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
   }
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
+  if constexpr (kNatural) {
+    const int cl = threadIdx.x >> 5, t = threadIdx.x & 31;   // chunk within the group, step
+    const int oc = threadIdx.x & 7, ot = threadIdx.x >> 3;   // the slot this thread writes out: chunk, step
+    for (uint64_t g = blockIdx.x; g < slots / 256; g += gridDim.x) {
+      const uint64_t b = g * 256 + threadIdx.x;
+      const uint64_t tile = g >> 2;
+      const int c0 = (int)(g & 3) * 8;
+      const bool valid = b < B;
+      uint32_t n = 0;
+      double sx = 0.0, sq = 0.0;
+      if (valid) block_sums(buf, b, B, n, sx, sq);
+      s_n[cl * PB + t] = n;
+      s_sx[cl * PB + t] = sx;
+      s_sq[cl * PB + t] = sq;
+      const double N = (double)n;
+      double E[KP];
+      const double mx = emission_terms<KP, kMix>(m, N, sx, sq, E);
+#pragma unroll
+      for (int s = 0; s < KP; ++s) s_e[cl * PE + t * KP + s] = (valid && s < m.K) ? exp_nonpos(E[s] - mx, s_tab) : 0.0;
+      if (want_maxe && valid) buf.maxE[Layout::at(tile, c0 + cl, t)] = mx;
+      __syncthreads();
+      const uint64_t ob = tile * Layout::TB + (uint64_t)(c0 + oc) * Layout::L + ot;  // natural index of the slot written
+      const uint64_t op = Layout::at(tile, c0 + oc, ot);
+      if (ob < B) {
+        buf.bN[op] = s_n[oc * PB + ot];
+        buf.bS[op] = make_double2(s_sx[oc * PB + ot], s_sq[oc * PB + ot]);
+      }
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        const int q = k * 256 + threadIdx.x;     // word of the group's emission terms in storage order
+        const int qt = q / (8 * KP), within = q % (8 * KP);
+        buf.e[(Layout::at(tile, c0, qt)) * KP + within] = s_e[(within / KP) * PE + qt * KP + within % KP];
+      }
+      __syncthreads();
+    }
+    return;
+  }
   // slots is a multiple of 1024 and the stride a multiple of 256: all threads of a CTA make the same trips
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = Layout::inv(p);
@@ -458,22 +568,7 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
     double sx = 0.0, sq = 0.0;
     if (valid) {
       if (kGather) {
-        const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
-        if (buf.spq)  // the pairs of this block's start and end sit next to each other (candidate list)
-          range_sums_from(buf, buf.spq[b], buf.spq[b + 1], s, e, sx, sq);
-        else
-          range_sums(buf, s, e, sx, sq);
-        n = e - s;
-        if (buf.seg.world > 1 && b + 1 == B) {
-          // the rank's last block continues on the following ranks up to their first boundary
-          for (int r = buf.seg.rank + 1; r < buf.seg.world; ++r) {
-            const double* hd = buf.seg.heads + 4 * r;
-            n += (uint32_t)hd[1];
-            sx += hd[2];
-            sq += hd[3];
-            if (hd[0] > 0.0) break;
-          }
-        }
+        block_sums(buf, b, B, n, sx, sq);
         buf.bN[p] = n;
         buf.bS[p] = make_double2(sx, sq);
       } else {
@@ -486,37 +581,20 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
     if (kEmit) {
       const double N = (double)n;
       double E[KP];
-      double mx = -INFINITY;
-#pragma unroll
-      for (int s = 0; s < KP; ++s) {
-        // EFD.hpp:23-32 then FB.hpp:74-81 (Mixture.hpp:98 has no self-transition term)
-        double v = (2.0 * m.mean[s] * sx - sq) * m.inv2var[s] - N * m.lognorm[s];
-        if (!kMix) v += (N - 1.0) * m.loga[s];
-        E[s] = v;
-        if (s < m.K) mx = fmax(mx, v);
-      }
+      const double mx = emission_terms<KP, kMix>(m, N, sx, sq, E);
       if (kStage) {
+        // the KP terms of a block sit KP * 8 bytes apart from the next block's: staged in shared memory and written as
+        // one contiguous piece (lane-strided stores cost five times the sectors at K = 5)
 #pragma unroll
         for (int s = 0; s < KP; ++s) s_e[threadIdx.x * KP + s] = (valid && s < m.K) ? exp_nonpos(E[s] - mx, s_tab) : 0.0;
-        if (!kMix) {
-#pragma unroll
-          for (int s = 0; s < KP; ++s) s_sp[threadIdx.x * KP + s] = (valid && s < m.K) ? exp_nonpos((N - 1.0) * m.loga[s], s_tab) : 0.0;
-        }
         __syncthreads();
         const uint64_t base = (p - threadIdx.x) * KP;  // first word of the CTA's 256 slots
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          buf.e[base + k * 256 + threadIdx.x] = s_e[k * 256 + threadIdx.x];
-          if (!kMix) buf.sp[base + k * 256 + threadIdx.x] = s_sp[k * 256 + threadIdx.x];
-        }
+        for (int k = 0; k < KP; ++k) buf.e[base + k * 256 + threadIdx.x] = s_e[k * 256 + threadIdx.x];
         __syncthreads();
       } else {
 #pragma unroll
         for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp_nonpos(E[s] - mx, s_tab) : 0.0;
-        if (!kMix) {
-#pragma unroll
-          for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp_nonpos((N - 1.0) * m.loga[s], s_tab) : 0.0;
-        }
       }
       if (want_maxe && valid) buf.maxE[p] = mx;
     }
@@ -584,10 +662,6 @@ __global__ void __launch_bounds__(256) k_block_emit_md(SweepBuffers buf, EmitMD<
       }
 #pragma unroll
       for (int s = 0; s < KP; ++s) buf.e[p * KP + s] = (s < m.K) ? exp_nonpos(E[s] - mx, s_tab) : 0.0;
-      if (!kMix) {
-#pragma unroll
-        for (int s = 0; s < KP; ++s) buf.sp[p * KP + s] = (s < m.K) ? exp_nonpos((N - 1.0) * m.loga[s], s_tab) : 0.0;
-      }
       if (want_maxe) buf.maxE[p] = mx;
     }
   }
@@ -1692,8 +1766,11 @@ __global__ void __launch_bounds__(32) k_fwd_sequential(SweepBuffers buf, ModelDe
 // with alpha'_t = alpha_t * A_ss^(N_t - 1) (FB.hpp:115-119,145-146); the last block draws from alpha_B
 // itself (FB.hpp:138).  u_t is the block's counter-based Philox uniform, or the replayed one.
 template <int KP, bool kRows>
-__global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
+__global__ void __launch_bounds__(256, KP <= 5 ? 5 : 1) k_bwd_maps(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep) {
   pdl_enter();
+  __shared__ double s_tab[64];  // 2^(j/64) for exp_nonpos
+  exp_table_load(s_tab);
+  __syncthreads();
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t slots = (B + Layout::TB - 1) / Layout::TB * Layout::TB;
   const int K = m.K;
@@ -1703,11 +1780,13 @@ __global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP>
     if (b < B) {
       const bool last = (b + 1 == B) && !(buf.seg.world > 1 && seg_later_blocks(buf.seg));
       const uint64_t gb = buf.seg.world > 1 ? seg_first_block(buf.seg) + b : b;  // global block index
+      // alpha'_t = alpha_t * A_ss^(N_t - 1): the rescale FB.hpp:115-119 applies to a row once its successor exists
+      const double Nm1 = (double)buf.bN[p] - 1.0;
       double ap[KP];
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
         const double al = buf.alpha[p * KP + j];
-        ap[j] = (last || !m.use_self) ? al : al * buf.sp[p * KP + j];
+        ap[j] = (last || !m.use_self || j >= K) ? al : al * exp_nonpos(Nm1 * m.loga[j], s_tab);
       }
       if (kRows) {
         if (b == 0)
@@ -1725,10 +1804,20 @@ __global__ void __launch_bounds__(256) k_bwd_maps(SweepBuffers buf, ModelDev<KP>
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
           if (j < K) {
-            double w[KP];
+            // running sums of alpha'_t(k) A(k, j) (rows and columns of padded states are zero)
+            double c[KP];
+            c[0] = ap[0] * m.A[0][j];
 #pragma unroll
-            for (int k = 0; k < KP; ++k) w[k] = ap[k] * m.A[k][j];
-            fm.set(j, discrete_draw<KP>(w, K, u));
+            for (int k = 1; k < KP; ++k) c[k] = fma(ap[k], m.A[k][j], c[k - 1]);
+            bool tie;
+            uint32_t q = discrete_draw_fast<KP>(c, K, u, tie);
+            if (tie) {  // the reference's own arithmetic: rounded products (FB.hpp:145-146), then discrete_distribution
+              Weights<KP> w;
+#pragma unroll
+              for (int k = 0; k < KP; ++k) w.v[k] = __dmul_rn(ap[k], m.A[k][j]);
+              q = discrete_draw_exact<KP>(w, K, u);
+            }
+            fm.set(j, q);
           }
         }
       }
