@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhammlet_b200.so")
 
-SWEEP_DYNAMIC, SWEEP_LOGLIK, SWEEP_KEEP_ROWS = 1, 2, 4
+SWEEP_DYNAMIC, SWEEP_LOGLIK, SWEEP_KEEP_ROWS, SWEEP_FUSED = 1, 2, 4, 8
 DETECT_STREAM, DETECT_PYRAMID, DETECT_CANDIDATES = 0, 1, 2
 MAX_STATES = 32
 MAX_DIMS = 5
@@ -53,7 +53,7 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
            "hammlet_chain_save_marginals", "hammlet_chains_run", "hammlet_chain_last_sweep",
-           "hml_comm_allgather"]
+           "hml_comm_allgather", "hml_chain_init", "hml_chain_set", "hml_chain_get", "hml_chain_run"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -272,6 +272,34 @@ class Handle:
                   mapping=None):
         return self._sweep(self.lib.hml_mix_sweep, mean, var, A, pi, use_self, flags, threshold, seed, sweep, replay,
                            mapping)
+
+    # ---- device-resident Gibbs chain (parameters, conjugate updates and draws on the device)
+    def chain_init(self, K, prior, trans=0.5, self_trans=0.5, alpha_pi=0.5, seed=0, use_self=True):
+        pr = (C.c_float * 4)(*[float(v) for v in prior])
+        self._ck(self.lib.hml_chain_init(self.h, C.c_int(K), pr, C.c_float(trans), C.c_float(self_trans), C.c_float(alpha_pi),
+                                         C.c_uint64(seed), C.c_int(int(use_self))))
+        self.chain_K = K
+
+    def chain_set(self, mean=None, var=None, A=None, pi=None):
+        a = [None if v is None else np.ascontiguousarray(v, np.float64) for v in (mean, var, A, pi)]
+        self._ck(self.lib.hml_chain_set(self.h, *[None if v is None else _ptr(v) for v in a]))
+
+    def chain_get(self):
+        K = self.chain_K
+        mean, var, A, pi = np.empty(K), np.empty(K), np.empty(K * K), np.empty(K)
+        thr, sweeps = C.c_float(), C.c_uint64()
+        self._ck(self.lib.hml_chain_get(self.h, _ptr(mean), _ptr(var), _ptr(A), _ptr(pi), C.byref(thr), C.byref(sweeps)))
+        return dict(mean=mean, var=var, A=A.reshape(K, K), pi=pi, threshold=thr.value, sweeps=sweeps.value)
+
+    def chain_run(self, nsweeps):
+        """-> statistics of the last sweep (as fb_sweep) + 'fused': sweeps that ran inside the persistent kernel."""
+        K = self.chain_K
+        ssum, ssq = np.zeros(K), np.zeros(K)
+        sn, cnt, tr = np.zeros(K, np.uint64), np.zeros(K, np.uint64), np.zeros((K, K), np.uint64)
+        out = _SweepOut(0, 0, 0.0, _ptr(ssum), _ptr(ssq), _ptr(sn), _ptr(tr), _ptr(cnt))
+        fused = C.c_uint64()
+        self._ck(self.lib.hml_chain_run(self.h, C.c_uint64(nsweeps), C.byref(fused), C.byref(out)))
+        return dict(nblocks=out.nblocks, stat_sum=ssum, stat_sq=ssq, stat_n=sn, trans=tr, counts=cnt, fused=fused.value)
 
     # ---- records / debug
     def states(self):

@@ -164,6 +164,15 @@ struct hml_ctx {
   unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
   unsigned long long* outblk_host = nullptr;  // pinned mirror
 
+  // the whole sweep in one persistent kernel + device-resident Gibbs chain (hml_fused.cuh)
+  ChainDev* chain_dev = nullptr;
+  ChainDev* chain_host = nullptr;      // pinned mirror: parameters and status as of the last synchronisation
+  uint32_t* fused_cta_count = nullptr;
+  unsigned long long* chain_stats = nullptr;  // result block of the whole sequence (segment mode: summed over the ranks)
+  bool chain_ready = false;            // hml_chain_init has been called
+  uint64_t chain_fused_sweeps = 0, chain_standard_sweeps = 0;
+  float last_thr = NAN;                // threshold of the current block structure
+
   // timing
   bool timing = false;
   std::vector<Stage> stages;
@@ -463,24 +472,37 @@ int rebuild_candidates(hml_t* h, float floor, bool* usable) {
   return fail(h, HML_ERR_CAPACITY, "block capacity did not converge");
 }
 
+// Makes the candidate list serve `thr` if it can: *usable says whether the boundaries of thr are a subset of the list.
+int ensure_candidates(hml_t* h, float thr, bool* usable) {
+  *usable = false;
+  const float floor = 0.75f * thr;
+  // candidate mode needs a floor that is a normal float (a denormal or zero floor selects every position) and that is
+  // well above the last floor whose list came out about as long as the sequence
+  if (!(h->detect_mode == HML_DETECT_CANDIDATES && thr > 0.f && isfinite(thr) && floor >= FLT_MIN &&
+        !(floor <= 1.25f * h->cand_too_long_floor)))
+    return HML_OK;
+  // usable: every boundary of thr is a candidate; worth keeping: the list is not much longer than the block list
+  bool ok = h->cand_valid && thr >= h->cand_floor;
+  if (ok && h->blocks_valid && h->cand_n > 4 * h->nblocks + 65536 && floor > 1.05f * h->cand_floor) ok = false;
+  if (!ok) {
+    int rc = rebuild_candidates(h, floor, &ok);
+    if (rc != HML_OK) return rc;
+  }
+  *usable = ok && h->cand_n > 0;
+  return HML_OK;
+}
+
 int run_detect(hml_t* h, float thr) {
   bool done = false;
   // the block structure is being overwritten: whatever the previous sweep left (states, runs, rows) no longer
   // belongs to it, also if this sweep fails half-way
   h->states_valid = h->segs_valid = h->g_valid = h->rows_valid = false;
-  const float floor = 0.75f * thr;
-  // candidate mode needs a floor that is a normal float (a denormal or zero floor selects every position) and that is
-  // well above the last floor whose list came out about as long as the sequence
-  if (h->detect_mode == HML_DETECT_CANDIDATES && thr > 0.f && isfinite(thr) && floor >= FLT_MIN &&
-      !(floor <= 1.25f * h->cand_too_long_floor)) {
-    // usable: every boundary of thr is a candidate; worth keeping: the list is not much longer than the block list
-    bool usable = h->cand_valid && thr >= h->cand_floor;
-    if (usable && h->blocks_valid && h->cand_n > 4 * h->nblocks + 65536 && floor > 1.05f * h->cand_floor) usable = false;
-    if (!usable) {
-      int rc = rebuild_candidates(h, floor, &usable);
-      if (rc != HML_OK) return rc;
-    }
-    if (usable && h->cand_n > 0) {
+  h->last_thr = thr;
+  {
+    bool usable = false;
+    int rc = ensure_candidates(h, thr, &usable);
+    if (rc != HML_OK) return rc;
+    if (usable) {
       h->launches += launch_detect_candidates(h->cand_w, h->cand_pos, h->cand_pq, (uint32_t)h->cand_n, thr, h->cand_scratch,
                                               h->cand_scratch_ctas, h->starts, h->spq, h->pq, h->capacity, h->T, h->outblk,
                                               h->stream, stage_cb, h);
@@ -921,6 +943,80 @@ int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged) {
   return HML_OK;
 }
 
+// ---- the fused path (hml_fused.cuh)
+
+int chain_alloc(hml_t* h) {
+  if (!h->chain_dev) {
+    CK(dev_alloc(h->chain_dev, 1));
+    CK(cudaMallocHost((void**)&h->chain_host, sizeof(ChainDev)));
+    memset(h->chain_host, 0, sizeof(ChainDev));
+    CK(dev_alloc(h->fused_cta_count, 1024));
+    CK(dev_alloc(h->chain_stats, kOutWords));
+  }
+  return HML_OK;
+}
+
+// can this handle run sweeps of K states through the fused kernel at all?
+bool fused_possible(const hml_t* h, int KP) {
+  return KP >= 2 && KP <= kChainMaxStates && h->D == 1 && h->world <= 1 && h->detect_mode == HML_DETECT_CANDIDATES &&
+         h->T < (1ull << 32);
+}
+
+// grid of the cooperative launch: one CTA per tile the block list can have (the candidates bound it), at most one per SM
+int fused_grid(const hml_t* h, int KP) {
+  const int max_grid = fused_max_grid(KP, h->sms);
+  if (max_grid <= 0) return 0;
+  uint64_t g = (h->cand_n + kTileBlocks - 1) / kTileBlocks;
+  if (g < 1) g = 1;
+  if (g > (uint64_t)max_grid) g = max_grid;
+  if (g > 1024) g = 1024;
+  return (int)g;
+}
+
+// Launches `nsweeps` fused sweeps on the chain state as it stands on the device (h->chain_host is uploaded first if
+// `upload`), waits, and mirrors the chain back.  The candidate list must serve the chain's threshold.
+int fused_launch(hml_t* h, int KP, int nsweeps, bool sample_params, bool philox_from_chain, uint64_t seed, uint64_t sweep,
+                 const double* replay_dev, bool upload) {
+  ChainDev* c = h->chain_host;
+  c->abort_code = 0;
+  c->sweeps_done = 0;
+  c->nblocks_seen = 0;
+  c->cand_floor = h->cand_floor;
+  for (unsigned int& f : c->phase_abort) f = 0;
+  if (upload) {
+    CK(cudaMemcpyAsync(h->chain_dev, c, sizeof(ChainDev), cudaMemcpyHostToDevice, h->stream));
+  } else {  // only the launch status and what the host knows better (the floor of the current list)
+    const size_t off = offsetof(ChainDev, abort_code);
+    CK(cudaMemcpyAsync((char*)h->chain_dev + off, (const char*)c + off, sizeof(ChainDev) - off, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(&h->chain_dev->cand_floor, &c->cand_floor, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  h->spq_valid = true;  // the kernel fills spq from the candidates' pairs
+  SweepBuffers b = make_buffers(h, KP);
+  b.replay_u = replay_dev;
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.chain = h->chain_dev;
+  a.cand_w = h->cand_w;
+  a.cand_pos = h->cand_pos;
+  a.cand_pq = h->cand_pq;
+  a.nc = (uint32_t)h->cand_n;
+  a.T_local = (uint32_t)h->T;
+  a.cta_count = h->fused_cta_count;
+  a.nsweeps = nsweeps;
+  a.sample_params = sample_params ? 1 : 0;
+  a.philox_sweep_from_chain = philox_from_chain ? 1 : 0;
+  a.seed = seed;
+  a.sweep = sweep;
+  const int grid = fused_grid(h, KP);
+  if (grid <= 0) return fail(h, HML_ERR_CUDA, "the fused sweep kernel does not fit this device");
+  const int e = launch_sweep_fused(KP, b, a, grid, h->stream);
+  if (e == -2) return fail(h, HML_ERR_ARG, "unsupported number of states for the fused sweep");
+  if (e != 0) return fail(h, HML_ERR_CUDA, std::string("fused sweep launch: ") + cudaGetErrorString((cudaError_t)e));
+  h->launches++;
+  CK(cudaMemcpyAsync(c, h->chain_dev, sizeof(ChainDev), cudaMemcpyDeviceToHost, h->stream));
+  return HML_OK;  // the caller synchronises (fetch_result)
+}
+
 int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64_t seed, uint64_t sweep,
                  const double* replay, uint64_t n_replay, hml_sweep_out* out, bool mixture) {
   if (!h) return HML_ERR_ARG;
@@ -942,6 +1038,15 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
   if (replay && n_replay < replay_need) return fail(h, HML_ERR_ARG, "fewer replay uniforms than blocks");
   if (seg && (flags & HML_SWEEP_KEEP_ROWS))
     return fail(h, HML_ERR_ARG, "forward rows are not kept in segment mode");
+  bool fused = (flags & HML_SWEEP_FUSED) != 0;
+  if (fused) {
+    if (mixture || (flags & (HML_SWEEP_LOGLIK | HML_SWEEP_KEEP_ROWS)) || !fused_possible(h, KP))
+      return fail(h, HML_ERR_ARG, "HML_SWEEP_FUSED: forward-backward sweeps of at most 8 states on a single univariate handle "
+                                  "in candidate detection mode, without log-likelihood or kept rows");
+    if (!dynamic && !(h->last_thr == h->last_thr)) return fail(h, HML_ERR_STATE, "no block structure: call hml_create_blocks first");
+    rc = chain_alloc(h);
+    if (rc != HML_OK) return rc;
+  }
 
   for (int attempt = 0; attempt < 8; ++attempt) {
     if (KP != h->KP) {
@@ -962,6 +1067,76 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     }
     h->stages.clear();
     h->stage_used = 0;
+    if (fused) {
+      // one persistent kernel does the whole sweep, boundary detection included (from the candidate list)
+      const float t_use = dynamic ? thr : h->last_thr;
+      bool usable = false;
+      rc = ensure_candidates(h, t_use, &usable);
+      if (rc != HML_OK) return rc;
+      if (!usable || h->cand_pq == nullptr || h->cand_n > (uint64_t)2 * kFusedMaxTiles * kTileBlocks) {
+        fused = false;  // the threshold is not one the candidate list serves, or far too many blocks: the multi-kernel path
+        continue;
+      }
+      ChainDev* c = h->chain_host;
+      const bool keep_chain = h->chain_ready;  // a device-resident chain keeps its priors and RNG position
+      ChainDev saved;
+      if (keep_chain) saved = *c;
+      for (int i = 0; i < mh.K; ++i) {
+        c->mean[i] = mh.mean[i];
+        c->var[i] = mh.var[i];
+        c->pi[i] = mh.pi[i];
+        for (int j = 0; j < mh.K; ++j) c->A[i * mh.K + j] = mh.A[i * mh.K + j];
+      }
+      c->K = mh.K;
+      c->use_self = mh.use_self;
+      c->T = (uint32_t)h->T;
+      c->thr = t_use;
+      h->last_thr = t_use;
+      h->states_valid = h->segs_valid = h->g_valid = h->rows_valid = false;
+      h->blocks_valid = false;
+      stage_cb(h, "fused_sweep");
+      rc = fused_launch(h, KP, 1, false, false, seed, sweep, replay ? h->replay_u : nullptr, true);
+      stage_cb(h, "end");
+      if (rc != HML_OK) return rc;
+      SweepResult res;
+      rc = fetch_result(h, KP, res, false);
+      if (rc != HML_OK) return rc;
+      const unsigned code = c->abort_code;
+      const unsigned long long seen = c->nblocks_seen;
+      if (keep_chain) {  // the single sweep borrowed the chain's slot for its model: put the chain back
+        *c = saved;
+        CK(cudaMemcpyAsync(h->chain_dev, c, sizeof(ChainDev), cudaMemcpyHostToDevice, h->stream));
+      }
+      if (code == kChainCapacity && seen > h->capacity && seen <= (uint64_t)kFusedMaxTiles * kTileBlocks) {
+        rc = alloc_blocks(h, seen + seen / 4, KP);
+        if (rc != HML_OK) return rc;
+        continue;
+      }
+      if (code != kChainOk) {  // too many blocks for one CTA per tile, a vanished forward sum, ...: the multi-kernel path
+        fused = false;
+        continue;
+      }
+      collect_timing(h);
+      h->nblocks = res.local_blocks;
+      h->global_blocks = res.global_blocks;
+      h->first_block = 0;
+      h->blocks_valid = h->stats_valid = true;
+      out->nblocks = res.global_blocks;
+      out->uniform_fallbacks = 0;
+      out->loglik = NAN;
+      for (int s2 = 0; s2 < mh.K; ++s2) {
+        if (out->counts) out->counts[s2] = res.o64[s2];
+        if (out->stat_n) out->stat_n[s2] = res.o64[s2];
+        if (out->stat_sum) out->stat_sum[s2] = res.of[s2];
+        if (out->stat_sumsq) out->stat_sumsq[s2] = res.of[KP + s2];
+        if (out->trans)
+          for (int j = 0; j < mh.K; ++j) out->trans[s2 * mh.K + j] = res.o64[KP + s2 * KP + j];
+      }
+      h->states_valid = true;
+      h->rows_valid = false;
+      h->last_K = mh.K;
+      return HML_OK;
+    }
     bool gather = !h->stats_valid;
     if (dynamic) {
       rc = run_detect(h, thr);
@@ -1270,6 +1445,11 @@ int hml_destroy(hml_t* h) {
   dev_free(h->stats_gather);
   dev_free(h->run_states);
   dev_free(h->run_border);
+  dev_free(h->chain_dev);
+  dev_free(h->fused_cta_count);
+  dev_free(h->chain_stats);
+  if (h->chain_host) cudaFreeHost(h->chain_host);
+  h->chain_host = nullptr;
   teardown_p2p(h);
   if (h->stats_gather_host) cudaFreeHost(h->stats_gather_host);
   if (h->comm) g_nccl.CommDestroy(h->comm);
@@ -1501,6 +1681,227 @@ int hml_mix_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold,
                   const double* replay_uniforms, uint64_t n_replay, hml_sweep_out* out) {
   return sweep_common(h, m, flags & ~(uint32_t)(HML_SWEEP_LOGLIK | HML_SWEEP_KEEP_ROWS), threshold, seed, sweep_index,
                       replay_uniforms, n_replay, out, true);
+}
+
+// ---- device-resident Gibbs chain
+
+int hml_chain_init(hml_t* h, int K, const float* nig_prior, float trans, float self_trans, float alpha_pi, uint64_t seed,
+                   int use_self_transitions) {
+  if (!h || !nig_prior) return HML_ERR_ARG;
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  if (K < 2 || K > kChainMaxStates) return fail(h, HML_ERR_ARG, "a device-resident chain has 2 to 8 states");
+  if (h->D != 1) return fail(h, HML_ERR_ARG, "a device-resident chain needs univariate data");
+  CK(cudaSetDevice(h->device));
+  int rc = chain_alloc(h);
+  if (rc != HML_OK) return rc;
+  ChainDev* c = h->chain_host;
+  memset(c, 0, sizeof(ChainDev));
+  c->K = K;
+  c->use_self = use_self_transitions ? 1 : 0;
+  c->T = (uint32_t)(h->world > 1 ? h->T_global : h->T);
+  c->seed = seed;
+  c->sweep = 0;
+  for (int s = 0; s < K; ++s)
+    for (int k = 0; k < 4; ++k) c->prior_theta[s][k] = nig_prior[k];
+  c->prior_trans = trans;
+  c->prior_self = self_trans;
+  c->prior_pi = alpha_pi;
+  // a leading "P" (main.cpp:393-406): theta, pi and A from their priors — the parameter phase on an empty result block
+  CK(cudaMemsetAsync(h->chain_stats, 0, kOutWords * 8, h->stream));
+  CK(cudaMemcpyAsync(h->chain_dev, c, sizeof(ChainDev), cudaMemcpyHostToDevice, h->stream));
+  const int KP = padded_states(K);
+  size_t words = (size_t)KP + (size_t)KP * KP + 1;
+  words += words & 1;
+  const int e = launch_chain_params(KP, h->chain_dev, h->chain_stats, (const double*)(h->chain_stats + words), h->stream);
+  if (e != 0) return fail(h, HML_ERR_CUDA, "parameter kernel launch failed");
+  h->launches++;
+  CK(cudaMemcpyAsync(c, h->chain_dev, sizeof(ChainDev), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (c->phase_abort[6]) return fail(h, HML_ERR_NUMERIC, "Variance must be positive!");
+  h->chain_ready = true;
+  h->chain_fused_sweeps = h->chain_standard_sweeps = 0;
+  return HML_OK;
+}
+
+int hml_chain_set(hml_t* h, const double* mean, const double* var, const double* A, const double* pi) {
+  if (!h) return HML_ERR_ARG;
+  if (!h->chain_ready) return fail(h, HML_ERR_STATE, "hml_chain_init has not been called");
+  CK(cudaSetDevice(h->device));
+  ChainDev* c = h->chain_host;
+  const int K = c->K;
+  for (int s = 0; s < K; ++s) {
+    if (mean) c->mean[s] = mean[s];
+    if (var) {
+      if (!(var[s] > 0) || !isfinite(var[s])) return fail(h, HML_ERR_ARG, "Variance must be positive!");
+      c->var[s] = var[s];
+    }
+    if (pi) c->pi[s] = pi[s];
+    if (A)
+      for (int j = 0; j < K; ++j) c->A[s * K + j] = A[s * K + j];
+  }
+  float mv = (float)c->var[0];
+  for (int s = 1; s < K; ++s) mv = fminf(mv, (float)c->var[s]);
+  c->thr = sqrtf(2.0f * logf((float)c->T) * mv);
+  CK(cudaMemcpyAsync(h->chain_dev, c, sizeof(ChainDev), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return HML_OK;
+}
+
+int hml_chain_get(hml_t* h, double* mean, double* var, double* A, double* pi, float* threshold, uint64_t* sweeps) {
+  if (!h) return HML_ERR_ARG;
+  if (!h->chain_ready) return fail(h, HML_ERR_STATE, "hml_chain_init has not been called");
+  const ChainDev* c = h->chain_host;  // current as of the last hml_chain_* call (they end with a synchronisation)
+  const int K = c->K;
+  for (int s = 0; s < K; ++s) {
+    if (mean) mean[s] = c->mean[s];
+    if (var) var[s] = c->var[s];
+    if (pi) pi[s] = c->pi[s];
+    if (A)
+      for (int j = 0; j < K; ++j) A[s * K + j] = c->A[s * K + j];
+  }
+  if (threshold) *threshold = c->thr;
+  if (sweeps) *sweeps = c->sweep;
+  return HML_OK;
+}
+
+int hml_chain_run(hml_t* h, uint64_t nsweeps, uint64_t* fused_sweeps, hml_sweep_out* last) {
+  if (!h) return HML_ERR_ARG;
+  if (!h->chain_ready) return fail(h, HML_ERR_STATE, "hml_chain_init has not been called");
+  if (h->T == 0) return fail(h, HML_ERR_STATE, "no data loaded");
+  CK(cudaSetDevice(h->device));
+  ChainDev* c = h->chain_host;
+  const int K = c->K, KP = padded_states(K);
+  if (KP != h->KP) {
+    int rc = alloc_blocks(h, h->capacity, KP);
+    if (rc != HML_OK) return rc;
+  }
+  size_t words = (size_t)KP + (size_t)KP * KP + 1;
+  words += words & 1;
+  uint64_t done = 0, fused_done = 0;
+  int stalled = 0;
+  bool last_fused = false;
+  std::vector<double> ssum(K), ssq(K);
+  std::vector<uint64_t> sn(K), trans((size_t)K * K), counts(K);
+  uint64_t last_nblocks = 0;
+  while (done < nsweeps) {
+    const float thr = c->thr;
+    bool use_fused = fused_possible(h, KP);
+    if (use_fused) {
+      bool usable = false;
+      int rc = ensure_candidates(h, thr, &usable);
+      if (rc != HML_OK) return rc;
+      use_fused = usable && h->cand_pq != nullptr && h->cand_n <= (uint64_t)2 * kFusedMaxTiles * kTileBlocks;
+    }
+    if (use_fused && stalled < 2) {
+      const uint64_t want = nsweeps - done;
+      const int batch = (int)(want > (1u << 20) ? (1u << 20) : want);
+      h->states_valid = h->segs_valid = h->g_valid = h->rows_valid = false;
+      h->blocks_valid = false;
+      h->last_thr = thr;
+      int rc = fused_launch(h, KP, batch, true, true, c->seed, 0, nullptr, false);
+      if (rc != HML_OK) return rc;
+      CK(cudaStreamSynchronize(h->stream));
+      h->mg_pending = false;
+      done += c->sweeps_done;
+      fused_done += c->sweeps_done;
+      h->chain_fused_sweeps += c->sweeps_done;
+      stalled = c->sweeps_done ? 0 : stalled + 1;
+      if (c->sweeps_done) last_fused = true;
+      if (c->phase_abort[6] == kChainNumeric) return fail(h, HML_ERR_NUMERIC, "Variance must be positive!");
+      if (c->abort_code == kChainCapacity && c->nblocks_seen > h->capacity &&
+          c->nblocks_seen <= (uint64_t)kFusedMaxTiles * kTileBlocks) {
+        rc = alloc_blocks(h, c->nblocks_seen + c->nblocks_seen / 4, KP);
+        if (rc != HML_OK) return rc;
+        stalled = 0;
+        continue;
+      }
+      if (c->abort_code == kChainOk || c->abort_code == kChainThreshold) continue;  // done, or the list is rebuilt above
+      stalled = 2;  // this sweep needs the multi-kernel path (too many blocks, a vanished forward sum)
+      continue;
+    }
+    // ---- one sweep through the multi-kernel path on the chain's current parameters, then the parameter phase
+    hml_model m;
+    memset(&m, 0, sizeof(m));
+    m.K = K;
+    m.use_self_transitions = c->use_self;
+    m.mean = c->mean;
+    m.var = c->var;
+    m.A = c->A;
+    m.pi = c->pi;
+    hml_sweep_out o;
+    memset(&o, 0, sizeof(o));
+    o.stat_sum = ssum.data();
+    o.stat_sumsq = ssq.data();
+    o.stat_n = sn.data();
+    o.trans = trans.data();
+    o.counts = counts.data();
+    int rc = sweep_common(h, &m, HML_SWEEP_DYNAMIC, thr, c->seed, c->sweep, nullptr, 0, &o, false);
+    if (rc != HML_OK) return rc;
+    // statistics of the whole sequence in the layout of the result block (segment mode: the host summed the ranks')
+    std::vector<unsigned long long> blk(kOutWords, 0ull);
+    for (int s = 0; s < K; ++s) {
+      blk[s] = sn[s];
+      for (int j = 0; j < K; ++j) blk[KP + s * KP + j] = trans[(size_t)s * K + j];
+    }
+    double* of = reinterpret_cast<double*>(blk.data() + words);
+    for (int s = 0; s < K; ++s) {
+      of[s] = ssum[s];
+      of[KP + s] = ssq[s];
+    }
+    CK(cudaMemcpyAsync(h->chain_stats, blk.data(), (words + 2 * KP + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    for (unsigned int& f : c->phase_abort) f = 0;
+    CK(cudaMemcpyAsync(h->chain_dev->phase_abort, c->phase_abort, sizeof(c->phase_abort), cudaMemcpyHostToDevice, h->stream));
+    const int e = launch_chain_params(KP, h->chain_dev, h->chain_stats, (const double*)(h->chain_stats + words), h->stream);
+    if (e != 0) return fail(h, HML_ERR_CUDA, "parameter kernel launch failed");
+    h->launches++;
+    CK(cudaMemcpyAsync(c, h->chain_dev, sizeof(ChainDev), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (c->phase_abort[6] == kChainNumeric) return fail(h, HML_ERR_NUMERIC, "Variance must be positive!");
+    done++;
+    h->chain_standard_sweeps++;
+    stalled = 0;
+    last_fused = false;
+    last_nblocks = o.nblocks;
+  }
+  if (fused_sweeps) *fused_sweeps = fused_done;
+  if (!last_fused && done && last) {
+    last->nblocks = last_nblocks;
+    last->uniform_fallbacks = 0;
+    last->loglik = NAN;
+    for (int s = 0; s < K; ++s) {
+      if (last->counts) last->counts[s] = counts[s];
+      if (last->stat_n) last->stat_n[s] = sn[s];
+      if (last->stat_sum) last->stat_sum[s] = ssum[s];
+      if (last->stat_sumsq) last->stat_sumsq[s] = ssq[s];
+      if (last->trans)
+        for (int j = 0; j < K; ++j) last->trans[s * K + j] = trans[(size_t)s * K + j];
+    }
+  }
+  if (last_fused) {
+    // block structure and statistics of the last sweep, as after hml_fb_sweep
+    SweepResult res;
+    int rc = fetch_result(h, KP, res, false);
+    if (rc != HML_OK) return rc;
+    h->nblocks = res.local_blocks;
+    h->global_blocks = res.global_blocks;
+    h->first_block = 0;
+    h->blocks_valid = h->stats_valid = h->states_valid = true;
+    h->last_K = K;
+    if (last) {
+      last->nblocks = res.global_blocks;
+      last->uniform_fallbacks = 0;
+      last->loglik = NAN;
+      for (int s = 0; s < K; ++s) {
+        if (last->counts) last->counts[s] = res.o64[s];
+        if (last->stat_n) last->stat_n[s] = res.o64[s];
+        if (last->stat_sum) last->stat_sum[s] = res.of[s];
+        if (last->stat_sumsq) last->stat_sumsq[s] = res.of[KP + s];
+        if (last->trans)
+          for (int j = 0; j < K; ++j) last->trans[s * K + j] = res.o64[KP + s * KP + j];
+      }
+    }
+  }
+  return HML_OK;
 }
 
 int hml_get_states(hml_t* h, int16_t* states, uint64_t capacity) {

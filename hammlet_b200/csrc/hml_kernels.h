@@ -152,6 +152,52 @@ constexpr int kWideCtasPerSm = 2;  // CTAs of k_fwd_chunks_wide launched per SM 
 size_t wide_scratch_doubles(int KP);  // per CTA; 0 for K <= 8
 size_t wide_scratch_ints(int KP);
 
+// ---- the whole sweep in one persistent kernel + device-resident Gibbs chain (hml_fused.cuh; K <= 8, univariate,
+// single handle, candidate-list detection, at most kFusedMaxTiles tiles)
+constexpr int kFusedThreads = 256;
+constexpr int kFusedMaxTiles = 64;
+constexpr int kChainMaxStates = 8;
+
+enum { kChainOk = 0, kChainThreshold = 1, kChainCapacity = 2, kChainFallback = 3, kChainNumeric = 4 };
+
+// Device-resident Gibbs chain (one per handle): parameters, priors, RNG position, status of the last launch.
+struct ChainDev {
+  double mean[kChainMaxStates], var[kChainMaxStates], A[kChainMaxStates * kChainMaxStates], pi[kChainMaxStates];
+  float prior_theta[kChainMaxStates][4];  // NIG hyper-parameters alpha, beta, mu0, nu per state (real_t = float)
+  float prior_trans, prior_self, prior_pi;
+  float thr;         // threshold of the current parameters, BreakpointArray.hpp:195-199
+  float cand_floor;  // the candidate list serves thresholds >= this
+  uint32_t T;        // observations of the whole sequence
+  int K, use_self;
+  unsigned long long seed, sweep;  // Philox key; sweeps sampled so far (the counter of the parameter streams)
+  unsigned int abort_code, sweeps_done;
+  unsigned long long nblocks_seen;  // block count that did not fit (kChainCapacity)
+  // One word per phase of a sweep: a phase reports through its own word, which is read after the grid barrier that
+  // ends the phase and is not written again before the next sweep — so all threads of the grid take the same decision
+  // (a single word could be raised by a CTA that is already a phase ahead while a slower one still reads it).
+  unsigned int phase_abort[8];
+};
+
+struct FusedArgs {
+  ChainDev* chain;
+  const float* cand_w;
+  const uint32_t* cand_pos;
+  const double2* cand_pq;
+  uint32_t nc;
+  uint32_t T_local;
+  uint32_t* cta_count;  // gridDim.x words
+  int nsweeps;
+  int sample_params;    // 0: the model stays as it is (single sweeps with a caller-provided model)
+  int philox_sweep_from_chain;  // uniforms keyed by chain->sweep (chain mode) or by `sweep` (single sweep)
+  unsigned long long seed, sweep;
+};
+
+// cooperative launch of a.nsweeps sweeps on `grid` CTAs; cudaError_t as int, or -2 for an unsupported K
+int launch_sweep_fused(int KP, const SweepBuffers& b, const FusedArgs& a, int grid, cudaStream_t s);
+int fused_max_grid(int KP, int sms);
+// the parameter phase alone (after a sweep of the multi-kernel path): theta, pi, A of the next sweep from the result block
+int launch_chain_params(int KP, ChainDev* ch, const unsigned long long* out_u64, const double* out_f64, cudaStream_t s);
+
 struct SweepLaunch {
   uint32_t flags;      // HML_SWEEP_* bits
   bool gather;         // recompute block sums from the integral arrays

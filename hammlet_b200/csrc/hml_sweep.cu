@@ -353,6 +353,38 @@ int launch_sweep(const ModelHost& m, const SweepBuffers& b, const SweepLaunch& l
   return n;
 }
 
+template <int KP> int fused_launch_kp(const SweepBuffers& b, const FusedArgs& a, int grid, cudaStream_t s);
+template <int KP> int fused_max_grid_kp(int sms);
+template <int KP> int chain_params_kp(ChainDev* ch, const unsigned long long* o64, const double* of, cudaStream_t s);
+#define HML_EXTERN_FUSED(KP)                                                                                 \
+  extern template int fused_launch_kp<KP>(const SweepBuffers&, const FusedArgs&, int, cudaStream_t);           \
+  extern template int fused_max_grid_kp<KP>(int);                                                             \
+  extern template int chain_params_kp<KP>(ChainDev*, const unsigned long long*, const double*, cudaStream_t);
+HML_EXTERN_FUSED(2) HML_EXTERN_FUSED(3) HML_EXTERN_FUSED(4) HML_EXTERN_FUSED(5) HML_EXTERN_FUSED(6) HML_EXTERN_FUSED(8)
+HML_EXTERN_FUSED(12) HML_EXTERN_FUSED(16) HML_EXTERN_FUSED(20) HML_EXTERN_FUSED(32)
+
+int launch_sweep_fused(int KP, const SweepBuffers& b, const FusedArgs& a, int grid, cudaStream_t s) {
+  int n = -2;
+#define CALL(X) n = fused_launch_kp<X>(b, a, grid, s)
+  HML_DISPATCH_KP(KP, CALL)
+#undef CALL
+  return n;
+}
+int fused_max_grid(int KP, int sms) {
+  int n = 0;
+#define CALL(X) n = fused_max_grid_kp<X>(sms)
+  HML_DISPATCH_KP(KP, CALL)
+#undef CALL
+  return n;
+}
+int launch_chain_params(int KP, ChainDev* ch, const unsigned long long* out_u64, const double* out_f64, cudaStream_t s) {
+  int n = -2;
+#define CALL(X) n = chain_params_kp<X>(ch, out_u64, out_f64, s)
+  HML_DISPATCH_KP(KP, CALL)
+#undef CALL
+  return n;
+}
+
 int launch_sweep_sequential(const ModelHost& m, const SweepBuffers& b, const SweepLaunch& l, cudaStream_t s) {
   const int KP = padded_states(m.K);
   int n = -1;

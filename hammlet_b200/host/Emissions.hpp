@@ -126,7 +126,8 @@ class DeviceSequence {
 
 // Reads whitespace-separated numbers with the result of `input >> v` (wavelet.hpp:131), through the
 // multi-threaded parser of FastParse.hpp, and loads them.
-inline std::vector<float> readValues(std::istream& input, const size_t reserveT = 0) {
+inline std::vector<float> readValues(std::istream& input, const size_t reserveT = 0,
+                                     fastparse::Format format = fastparse::Format::Auto) {
   if (!input) throw std::runtime_error("Cannot read input file or stream!");
   std::vector<float> values;
   values.reserve(reserveT);
@@ -134,9 +135,21 @@ inline std::vector<float> readValues(std::istream& input, const size_t reserveT 
     float v;
     while (input >> v) values.push_back(v);
   } else {
-    const std::string text = fastparse::slurp(input);
-    fastparse::parseFloats(text.data(), text.size(), values);
+    const std::string bytes = fastparse::slurp(input);
+    fastparse::parseAny(bytes.data(), bytes.size(), format, values);
   }
+  return values;
+}
+// a file: text, gzip'd text (recognised by its magic number) or raw little-endian float32 (`-F f32`)
+inline std::vector<float> readValuesFile(const std::string& path, fastparse::Format format = fastparse::Format::Auto) {
+  if (std::getenv("HAMMLET_SLOW_PARSE")) {
+    std::ifstream fin(path);
+    if (!fin) throw std::runtime_error("Cannot read from input file " + path + "!");
+    return readValues(fin);
+  }
+  const std::string bytes = fastparse::slurpFile(path);
+  std::vector<float> values;
+  fastparse::parseAny(bytes.data(), bytes.size(), format, values);
   return values;
 }
 inline void MaxletTransform(std::istream& input, DeviceSequence& seq, const size_t nrDim, const float weightMultiplier,

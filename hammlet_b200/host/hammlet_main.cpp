@@ -9,6 +9,8 @@
 //                        process per device is forked after the input has been parsed, every process runs the same
 //                        chain on the same parameters, the scan carries travel between the GPUs,
 //                        process 0 writes the files — the same files a single device writes.  Univariate data.
+//   -F|-input-format X   auto (default: gzip'd text is recognised by its magic number, anything else is text), text, gz,
+//                        f32 (raw little-endian float32: 4 bytes per value instead of ~9 of text)
 //   -replay              draw the per-block uniforms from the shared mt19937 exactly as the reference
 //                        does (draw-for-draw comparable runs; slower: one host round trip per sweep)
 //   -timing              print sweeps/s per run token to stderr
@@ -32,9 +34,13 @@ static void onChild(int) {  // a rank that dies would leave the others waiting i
   pid_t p;
   while ((p = waitpid(-1, &status, WNOHANG)) > 0) {
     const bool ok = WIFEXITED(status) && WEXITSTATUS(status) == 0;
+    bool mine = false;
     for (pid_t& c : g_children)
-      if (c == p) c = ok ? 0 : -1;
-    if (!ok) {
+      if (c == p) {
+        c = ok ? 0 : -1;
+        mine = true;
+      }
+    if (mine && !ok) {
       const char msg[] = "\n[ERROR] A device process failed!\nTerminating HaMMLET. The rest is silence.\n";
       if (write(2, msg, sizeof(msg) - 1) < 0) {}
       for (pid_t c : g_children)
@@ -68,10 +74,14 @@ static const char* kHelp =
     "  -m|-weight-multiplier x    multiply breakpoint weights (default 1)\n"
     "  -v -g -h                   verbose, print parsed arguments, this help\n"
     "  -device N  -replay  -timing   see the header of hammlet_main.cpp\n"
-    "  -devices a b ...           split the sequence over several GPUs (one process each), same output files\n";
+    "  -devices a b ...           split the sequence over several GPUs (one process each), same output files\n"
+    "  -F|-input-format X         auto|text|gz|f32: gzip'd text (e.g. samToCounts' *-count.csv.gz) is recognised by\n"
+    "                             itself; f32 = raw little-endian float32\n";
 
-int main(int argc, const char* argv[]) {
-  try {
+// everything but the wait for the other device processes: when this returns, the sequence (and with it the NCCL
+// communicator, whose teardown is collective) has been released
+static int hammletMain(int argc, const char* argv[]) {
+  {
     Parser args(argc, argv);
     args.registerFlags({"-v", "-verbose"});
     args.registerFlags({"-g", "-arguments"});
@@ -91,6 +101,7 @@ int main(int argc, const char* argv[]) {
     args.registerFlags({"-m", "-weight-multiplier"}, "1");
     args.registerFlags({"-device"}, "0");
     args.registerFlags({"-devices"});
+    args.registerFlags({"-F", "-input-format"}, "auto");
     args.registerFlags({"-replay"});
     args.registerFlags({"-timing"});
     args.parseArgs();
@@ -195,17 +206,16 @@ int main(int argc, const char* argv[]) {
     if (world > 1 && nrDataDim != 1) throw std::runtime_error("A sequence split over several devices must be univariate!");
 
     // ---- load: parse on the host (before any process is forked and before CUDA is touched), transform on the device
+    const fastparse::Format inputFormat = fastparse::formatFromName(args.parse<string>("-F"));
     vector<float> values;
     if (args.isSet("-f")) {
       const vector<string> files = args.parseVector<string>("-f");
       if (files.size() > 1) throw std::runtime_error("Coefficient array must be empty!");  // as wavelet.hpp:111-113
       if (verbose) cout << "Reading " + files[0] << endl << flush;
-      std::ifstream fin(files[0]);
-      if (!fin) throw std::runtime_error("Cannot read from input file " + files[0] + "!");
-      values = readValues(fin);
+      values = readValuesFile(files[0], inputFormat);
     } else {
       if (verbose) cout << "Reading from standard input" << endl << flush;
-      values = readValues(std::cin);
+      values = readValues(std::cin, 0, inputFormat);
     }
     if (nrDataDim <= 0) throw std::runtime_error("Number of dimensions must be positive!");
 
@@ -352,18 +362,24 @@ int main(int argc, const char* argv[]) {
       }
     }
     records.close();  // writes the marginals (the reference does this in ~Records)
-    if (lead && !g_children.empty()) {  // the other device processes have nothing left to do: collect them
-      signal(SIGCHLD, SIG_DFL);
-      for (pid_t p : g_children) {
-        int status = 0;
-        if (p > 0 && waitpid(p, &status, 0) == p && !(WIFEXITED(status) && WEXITSTATUS(status) == 0))
-          throw std::runtime_error("A device process failed!");
-        if (p < 0) throw std::runtime_error("A device process failed!");
-      }
-      g_children.clear();
-    }
     if (verbose) cout << "Exit HaMMLET" << endl << flush;
     return 0;
+  }
+}
+
+int main(int argc, const char* argv[]) {
+  try {
+    const int rc = hammletMain(argc, argv);
+    // the other device processes have nothing left to do: collect them (only now — the communicator is torn down by all
+    // ranks together, so process 0 must have left hammletMain before it waits for anybody)
+    signal(SIGCHLD, SIG_DFL);
+    for (pid_t p : g_children) {
+      int status = 0;
+      if (p < 0 || (p > 0 && waitpid(p, &status, 0) == p && !(WIFEXITED(status) && WEXITSTATUS(status) == 0)))
+        throw std::runtime_error("A device process failed!");
+    }
+    g_children.clear();
+    return rc;
   } catch (std::exception& e) {
     signal(SIGCHLD, SIG_DFL);
     killChildren();

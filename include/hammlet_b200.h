@@ -139,7 +139,16 @@ typedef struct {
 enum {
   HML_SWEEP_DYNAMIC = 1, /* re-derive the block structure from `threshold` first (HMM.hpp:100-102) */
   HML_SWEEP_LOGLIK = 2,  /* also accumulate the forward log-likelihood */
-  HML_SWEEP_KEEP_ROWS = 4 /* keep the forward rows (B+1)xK for hml_get_rows (parity/debug) */
+  HML_SWEEP_KEEP_ROWS = 4, /* keep the forward rows (B+1)xK for hml_get_rows (parity/debug) */
+  HML_SWEEP_FUSED = 8 /* hml_fb_sweep only: run the sweep as ONE persistent cooperative kernel (boundaries from the
+                         candidate list, emission terms, forward filter, backward sampling, statistics; one CTA per tile
+                         of 1024 blocks, grid-wide barriers instead of kernel boundaries) — the building block of the
+                         device-resident chain below, 3-4x faster than the 13-kernel sweep for block structures of up to
+                         65 536 blocks.  Same arrays, same numerics, same uniforms (Philox counters or replayed): the
+                         result is that of the multi-kernel sweep.  K <= 8, univariate data, single handle, candidate
+                         detection mode, no log-likelihood / kept rows; sweeps that do not qualify at run time (more
+                         blocks than 64 tiles, a threshold the candidate list cannot serve, a vanished forward sum) take
+                         the multi-kernel path by themselves. */
 };
 
 /* One FBG sweep.  Uniforms: counter-based Philox4x32-10 keyed by (seed, sweep_index, block), or —
@@ -151,6 +160,32 @@ int hml_fb_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold, 
 /* One mixture sweep (per-block independent draw); replay uniforms are consumed in block order. */
 int hml_mix_sweep(hml_t* h, const hml_model* m, uint32_t flags, float threshold, uint64_t seed, uint64_t sweep_index,
                   const double* replay_uniforms, uint64_t n_replay, hml_sweep_out* out);
+
+/* ---- device-resident Gibbs chain: sampleHMM (HMM.hpp:99-121) without a host round trip per sweep ----------------
+ *
+ * theta, pi and A, their conjugate hyper-parameters and the random streams live in device memory.  After every sweep
+ * one CTA performs the Normal-Inverse-Gamma and Dirichlet updates from the sweep's statistics (Conjugate.hpp:120-205,
+ * real_t = float like the reference; pi from the occupancy counts, ForwardBackward.hpp:211) and draws theta_k
+ * (var = 1 / Gamma(alpha, 1 / beta), mean ~ N(mu0, sqrt(var / nu)); Theta.hpp:203-211, Distribution.hpp:76-87), pi and
+ * the rows of A (normalised Gamma draws, Distribution.hpp:116-139) for the next one, then the threshold
+ * sqrtf(2 logf(T) min var) (BreakpointArray.hpp:195-199); the posteriors fall back to the priors after every draw
+ * (Theta.hpp:209).  Draws come from Philox streams keyed by (seed, sweep number, draw): a chain is reproducible and does
+ * not depend on how its sweeps were batched, but it is not the reference's mt19937 stream — `hammlet -replay` and
+ * hml_fb_sweep with host parameters keep that.  hml_chain_run(n) puts n sweeps on the device and returns when they are
+ * done: as ONE launch of the persistent kernel of HML_SWEEP_FUSED where that applies (nothing crosses PCIe between
+ * sweeps), sweep by sweep through the multi-kernel path otherwise (more than 64 tiles of blocks, a segment-split
+ * sequence, a threshold outside the candidate list: the parameter phase then still runs on the device, and the host only
+ * forwards the parameters).  K <= 8, univariate data.  Every rank of a split sequence runs the same chain. */
+int hml_chain_init(hml_t* h, int K, const float nig_prior[4] /* alpha, beta, mu0, nu for every state: main.cpp:348-362 */,
+                   float trans, float self_trans /* main.cpp:146-155 */, float alpha_pi /* main.cpp:165-166 */, uint64_t seed,
+                   int use_self_transitions);
+/* Parameters as of the last hml_chain_* call; any pointer may be NULL.  A is K*K row-major. */
+int hml_chain_set(hml_t* h, const double* mean, const double* var, const double* A, const double* pi);
+int hml_chain_get(hml_t* h, double* mean, double* var, double* A, double* pi, float* threshold, uint64_t* sweeps_so_far);
+/* nsweeps dynamic forward-backward sweeps.  *fused_sweeps (may be NULL) = how many of them ran inside the persistent
+ * kernel; `last` (may be NULL) receives the statistics of the last sweep.  Afterwards hml_get_states / hml_get_segments /
+ * hml_marginals_add see the last sweep's state sequence, as after hml_fb_sweep. */
+int hml_chain_run(hml_t* h, uint64_t nsweeps, uint64_t* fused_sweeps, hml_sweep_out* last);
 
 /* ---- records: inputs of Records::record(state, N) (Records.hpp:155-235) -------------------- */
 

@@ -217,6 +217,28 @@ def test_multivariate_replay_run_is_identical_to_the_double_reference(tmp_path, 
 
 
 @pytest.mark.gpu
+def test_gzip_and_float32_inputs_give_the_text_run(tmp_path):
+    """-f takes gzip'd text (recognised by its magic number: the *-count.csv.gz files of the reference's samToCounts)
+    and, with -F f32, raw little-endian float32; both runs must write the files of the plain-text run."""
+    import gzip
+    ours = need(os.path.join(BIN, "hammlet"))
+    x = write_input(tmp_path / "in.txt", 80000, 3, 400, 6)
+    (tmp_path / "in.txt.gz").write_bytes(gzip.compress((tmp_path / "in.txt").read_bytes(), compresslevel=1))
+    np.loadtxt(tmp_path / "in.txt", dtype=np.float32).tofile(tmp_path / "in.f32")
+    assert x.size == 80000
+    common = ["-a", "-R", "4", "-s", "3", "-i", "F", "40", "2", "-O", "M", "P", "C", "-w"]
+    runs = {"txt": ["-f", "in.txt"], "gz": ["-f", "in.txt.gz"], "f32": ["-f", "in.f32", "-F", "f32"]}
+    for tag, src in runs.items():
+        p = run([ours] + src + common + ["-o", tag + "-", ".csv"], cwd=tmp_path)
+        assert p.returncode == 0, p.stderr
+    for kind in ("marginals", "parameters", "compression"):
+        ref = (tmp_path / f"txt-{kind}.csv").read_text()
+        assert (tmp_path / f"gz-{kind}.csv").read_text() == ref and (tmp_path / f"f32-{kind}.csv").read_text() == ref, kind
+    p = run([ours, "-f", "in.txt", "-F", "bogus"] + common, cwd=tmp_path)
+    assert p.returncode == 1 and "Unknown input format" in p.stderr
+
+
+@pytest.mark.gpu
 def test_multivariate_input_must_fill_all_dimensions(tmp_path):
     ours = need(os.path.join(BIN, "hammlet"))
     p = run([ours, "-a", "-s", "C", "2", "2", "-w"], stdin="1 2 3 4 5\n", cwd=tmp_path)

@@ -57,7 +57,7 @@ def test_cli_devices_replay_run_equals_the_reference(tmp_path, world, outputs):
               "-O"] + outputs + ["-w"]
     r = subprocess.run([ref] + common + ["-o", "ref-", ".csv"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     p = subprocess.run([ours, "-replay", "-devices"] + [str(d) for d in range(world)] + common + ["-o", "our-", ".csv"],
-                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+                       cwd=tmp_path, capture_output=True, text=True, timeout=150)
     assert r.returncode == 0 and p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:] + r.stderr[-2000:]
     kinds = {"M": "marginals", "S": "sequences", "P": "parameters", "B": "blocks", "C": "compression", "G": "segments"}
     for o in outputs:
@@ -79,7 +79,7 @@ def test_cli_devices_philox_run_equals_single_device(tmp_path):
     common = ["-f", "in.txt", "-a", "-R", "9", "-s", "4", "-i", "F", "60", "3", "-O", "M", "P", "C", "-w"]
     a = subprocess.run([ours] + common + ["-o", "one-", ".csv"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     b = subprocess.run([ours, "-devices", "0,1"] + common + ["-o", "two-", ".csv"], cwd=tmp_path, capture_output=True, text=True,
-                       timeout=600)
+                       timeout=150)
     assert a.returncode == 0 and b.returncode == 0, a.stderr[-2000:] + b.stderr[-2000:]
     for kind in ("marginals", "compression", "parameters"):
         assert (tmp_path / f"one-{kind}.csv").read_text() == (tmp_path / f"two-{kind}.csv").read_text(), kind
