@@ -53,7 +53,8 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hammlet_auto_prior", "hammlet_chain_create", "hammlet_chain_destroy", "hammlet_chain_error",
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
            "hammlet_chain_save_marginals", "hammlet_chains_run", "hammlet_chain_last_sweep",
-           "hml_comm_allgather", "hml_chain_init", "hml_chain_set", "hml_chain_get", "hml_chain_run"]
+           "hml_comm_allgather", "hml_chain_init", "hml_chain_set", "hml_chain_get", "hml_chain_run",
+           "hml_chain_phase_ns"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -300,6 +301,11 @@ class Handle:
         fused = C.c_uint64()
         self._ck(self.lib.hml_chain_run(self.h, C.c_uint64(nsweeps), C.byref(fused), C.byref(out)))
         return dict(nblocks=out.nblocks, stat_sum=ssum, stat_sq=ssq, stat_n=sn, trans=tr, counts=cnt, fused=fused.value)
+
+    def chain_phase_ns(self):
+        st = np.zeros(16, np.uint64)
+        self._ck(self.lib.hml_chain_phase_ns(self.h, _ptr(st)))
+        return st
 
     # ---- records / debug
     def states(self):

@@ -168,6 +168,10 @@ struct hml_ctx {
   ChainDev* chain_dev = nullptr;
   ChainDev* chain_host = nullptr;      // pinned mirror: parameters and status as of the last synchronisation
   uint32_t* fused_cta_count = nullptr;
+  unsigned* fused_barriers = nullptr;
+  double* fused_qtot = nullptr;
+  unsigned long long* fused_qmap = nullptr;
+  unsigned long long* fused_phase_ns = nullptr;
   unsigned long long* chain_stats = nullptr;  // result block of the whole sequence (segment mode: summed over the ranks)
   bool chain_ready = false;            // hml_chain_init has been called
   uint64_t chain_fused_sweeps = 0, chain_standard_sweeps = 0;
@@ -951,6 +955,11 @@ int chain_alloc(hml_t* h) {
     CK(cudaMallocHost((void**)&h->chain_host, sizeof(ChainDev)));
     memset(h->chain_host, 0, sizeof(ChainDev));
     CK(dev_alloc(h->fused_cta_count, 1024));
+    CK(dev_alloc(h->fused_barriers, 1 + kFusedMaxTiles));
+    CK(dev_alloc(h->fused_qtot, (size_t)4 * kFusedMaxTiles * (kChainMaxStates * kChainMaxStates + kChainMaxStates)));
+    CK(dev_alloc(h->fused_qmap, (size_t)4 * kFusedMaxTiles));
+    CK(dev_alloc(h->fused_phase_ns, 16));
+    CK(cudaMemsetAsync(h->fused_phase_ns, 0, 16 * 8, h->stream));
     CK(dev_alloc(h->chain_stats, kOutWords));
   }
   return HML_OK;
@@ -966,9 +975,10 @@ bool fused_possible(const hml_t* h, int KP) {
 int fused_grid(const hml_t* h, int KP) {
   const int max_grid = fused_max_grid(KP, h->sms);
   if (max_grid <= 0) return 0;
-  uint64_t g = (h->cand_n + kTileBlocks - 1) / kTileBlocks;
-  if (g < 1) g = 1;
-  if (g > (uint64_t)max_grid) g = max_grid;
+  // one CTA per quarter tile (256 blocks) the block list can have — the candidates bound it —, a multiple of four
+  uint64_t g = 4 * ((h->cand_n + kTileBlocks - 1) / kTileBlocks);
+  if (g < 4) g = 4;
+  if (g > (uint64_t)max_grid) g = max_grid / 4 * 4;
   if (g > 1024) g = 1024;
   return (int)g;
 }
@@ -1002,6 +1012,11 @@ int fused_launch(hml_t* h, int KP, int nsweeps, bool sample_params, bool philox_
   a.nc = (uint32_t)h->cand_n;
   a.T_local = (uint32_t)h->T;
   a.cta_count = h->fused_cta_count;
+  a.barriers = h->fused_barriers;
+  a.qtot = h->fused_qtot;
+  a.qmap = h->fused_qmap;
+  a.phase_ns = h->timing ? h->fused_phase_ns : nullptr;
+  CK(cudaMemsetAsync(h->fused_barriers, 0, (1 + kFusedMaxTiles) * sizeof(unsigned), h->stream));
   a.nsweeps = nsweeps;
   a.sample_params = sample_params ? 1 : 0;
   a.philox_sweep_from_chain = philox_from_chain ? 1 : 0;
@@ -1447,6 +1462,10 @@ int hml_destroy(hml_t* h) {
   dev_free(h->run_border);
   dev_free(h->chain_dev);
   dev_free(h->fused_cta_count);
+  dev_free(h->fused_barriers);
+  dev_free(h->fused_qtot);
+  dev_free(h->fused_qmap);
+  dev_free(h->fused_phase_ns);
   dev_free(h->chain_stats);
   if (h->chain_host) cudaFreeHost(h->chain_host);
   h->chain_host = nullptr;
@@ -1901,6 +1920,15 @@ int hml_chain_run(hml_t* h, uint64_t nsweeps, uint64_t* fused_sweeps, hml_sweep_
       }
     }
   }
+  return HML_OK;
+}
+
+int hml_chain_phase_ns(hml_t* h, uint64_t stamps[16]) {
+  if (!h || !stamps) return HML_ERR_ARG;
+  if (!h->fused_phase_ns) return fail(h, HML_ERR_STATE, "no fused sweep has been run");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(stamps, h->fused_phase_ns, 16 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return HML_OK;
 }
 

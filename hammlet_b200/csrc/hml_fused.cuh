@@ -8,8 +8,9 @@
 // Why: the multi-kernel sweep (hml_sweep_impl.cuh) is 13 dependent launches and one host round trip per sweep.  At
 // 1e9 observations that overhead hides behind 240 us of work; at 1e6 (1.3 k blocks) or 1e7 observations (15 k blocks)
 // every kernel sits on its 7-17 us floor and the sweep costs 65-85 us of which the GPU works a fraction.  Here a
-// cooperative grid of one CTA per tile (at most one per SM) keeps everything of a tile — emission terms, chunk
-// operators, forward rows, backward maps, states — in that CTA, the phases of a sweep are separated by six grid-wide
+// cooperative grid of one CTA per quarter tile (256 blocks; at most one CTA per SM) keeps everything of those blocks —
+// emission terms, chunk operators, forward rows, backward maps, states — in that CTA; the four CTAs of a tile combine
+// their chunk operators and chunk maps at a tile-local barrier, the phases of a sweep are separated by six grid-wide
 // barriers instead of kernel boundaries, and the kernel loops over sweeps: the model of sweep i+1 is drawn by CTA 0
 // from the statistics of sweep i (Philox streams) while the other CTAs wait at the barrier, so nothing returns to the
 // host until the requested sweeps are done or the kernel stands down (the threshold left the candidate list, the block
@@ -33,27 +34,33 @@ struct DrawStream {
   uint32_t stream;
   unsigned long long ctr;
   __device__ __forceinline__ double uniform() { return Philox::uniform(seed, sweep, stream, ctr++); }
-  __device__ __forceinline__ double normal() {  // Box-Muller, one value per two uniforms
-    const double u1 = 1.0 - uniform(), u2 = uniform();
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+  // The draws are real_t = float in the reference (std::gamma_distribution<float>, std::normal_distribution<float>);
+  // here the transcendental functions are float too (a tenth of the instructions of their double versions: the
+  // parameter phase is one warp on the critical path of every sweep), the accumulation of d * v stays double.
+  __device__ __forceinline__ float normal() {  // Box-Muller, one value per two uniforms
+    const float u1 = (float)(1.0 - uniform());
+    const float u2 = (float)uniform();
+    return sqrtf(-2.0f * logf(fmaxf(u1, 1e-38f))) * cospif(2.0f * u2);
   }
   // Gamma(alpha, 1): Marsaglia & Tsang 2000 (the method libstdc++'s gamma_distribution uses), boosted for alpha < 1
   __device__ double gamma(double alpha) {
     const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
-    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    const double d = a - 1.0 / 3.0;
+    const float c = rsqrtf((float)(9.0 * d));
     double g = 0.0;
     for (int tries = 0; tries < 1000; ++tries) {
-      const double x = normal();
-      double v = 1.0 + c * x;
-      if (v <= 0.0) continue;
-      v = v * v * v;
-      const double u = 1.0 - uniform();
-      if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+      const float x = normal();
+      const float v1 = 1.0f + c * x;
+      if (v1 <= 0.0f) continue;
+      const double v = (double)v1 * (double)v1 * (double)v1;
+      const float u = fmaxf((float)(1.0 - uniform()), 1e-38f);
+      // log u < x^2 / 2 + d (1 - v + log v): for large d the bracket is a small difference, taken in double
+      if ((double)logf(u) < 0.5 * (double)x * (double)x + d * (1.0 - v + (double)log1pf((float)(v - 1.0)))) {
         g = d * v;
         break;
       }
     }
-    if (alpha < 1.0) g *= pow(1.0 - uniform(), 1.0 / alpha);
+    if (alpha < 1.0) g *= (double)powf(fmaxf((float)(1.0 - uniform()), 1e-38f), (float)(1.0 / alpha));
     return g;
   }
 };
@@ -86,7 +93,7 @@ __device__ void chain_sample_params(ChainDev* ch, const unsigned long long* out_
     rs.stream = 2u + (uint32_t)tid;
     const float gam = (float)(rs.gamma((double)alpha) / (double)beta);
     const float var = 1.0f / gam;
-    const float mean = (float)((double)mu0 + sqrt((double)(var / nu)) * rs.normal());
+    const float mean = mu0 + sqrtf(var / nu) * rs.normal();
     if (!(var > 0.0f) || !isfinite(var) || !isfinite(mean)) ch->phase_abort[6] = kChainNumeric;  // Observation.hpp:177-179
     ch->mean[tid] = (double)mean;
     ch->var[tid] = (double)var;
@@ -172,25 +179,65 @@ __device__ __forceinline__ void block_sums_cg(const SweepBuffers& buf, uint64_t 
   n = e - s;
 }
 
+// ---- barriers of the persistent kernel.  All CTAs of a cooperative launch are resident, so spinning is safe.  The
+// counters only grow (the host zeroes them before a launch): the k-th barrier of a group of n CTAs waits for k * n.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (ld_acquire_u32(ctr) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
+// One CTA per QUARTER of a tile (256 consecutive blocks = 8 chunks of 32); the four CTAs of a tile meet at a tile-local
+// barrier where the tile's chunk operators / chunk maps are combined.  Grid = 4 x tiles (a multiple of 4, at most one
+// CTA per SM); with more quarters than CTAs a CTA takes several, the four of a tile always in the same round.
 template <int KP>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers buf, FusedArgs args) {
   constexpr int L = Layout::L, C = Layout::C, TB = Layout::TB, MB = 8 * Map<KP>::W;
-  constexpr int PE = 33 * KP, PB = 36;
-  cg::grid_group grid = cg::this_grid();
+  constexpr int QC = 8;                 // chunks per quarter
+  constexpr int PE = 33 * KP, PB = 36;  // row pitches of the emission staging (see k_block_emit)
+  constexpr int OPW = KP * KP + KP;     // doubles of one operator in the quarter-total exchange (mantissas, exponents)
+  static_assert(Map<KP>::W == 1, "K <= 8: maps are one word");
   __shared__ ModelDev<KP> m;
   __shared__ double s_tab[64];
-  __shared__ double s_ops[C * KP * KP];
-  __shared__ int s_exp[C * KP];
-  __shared__ double s_e[8 * PE];
-  __shared__ double s_sx[8 * PB], s_sq[8 * PB];
-  __shared__ uint32_t s_n[8 * PB];
+  __shared__ double s_ops[QC * KP * KP];  // chunk operators of the quarter
+  __shared__ int s_exp[QC * KP];
+  __shared__ double s_pre[QC * KP * KP];  // their exclusive prefixes inside the quarter
+  __shared__ int s_pex[QC * KP];
+  __shared__ double s_base[KP * KP];      // product of the quarters in front of this one (identity for quarter 0)
+  __shared__ int s_bex[KP];
+  __shared__ double s_e[QC * PE];
+  __shared__ double s_sx[QC * PB], s_sq[QC * PB];
+  __shared__ uint32_t s_n[QC * PB];
   __shared__ double s_red[kFusedThreads / 32][2 * KP];
   __shared__ unsigned long long s_cnt[KP * KP + KP];
   __shared__ float s_g[KP * KP + 2 * KP];
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_misc[4];
-  __shared__ double s_ain[KP];
+  // hand-offs between the phases of a quarter: forward rows (for the maps), maps (for the chunk maps and the states),
+  // states (for the statistics).  What another phase of the same CTA wrote to global memory comes back from L2 at
+  // ~0.35 us per dependent access; a CTA that owns one quarter per phase (`resident`) keeps all of it in shared memory.
+  // (the rows take the place of the emission terms they were computed from: same chunk, same step, same pitch)
+  double* const s_alpha = s_e;
+  __shared__ unsigned long long s_maps[256];
+  __shared__ uint8_t s_states[256 + 8];
   ChainDev* ch = args.chain;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t G = gridDim.x, cta = blockIdx.x;
@@ -199,8 +246,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
   unsigned long long* nb_out = const_cast<unsigned long long*>(buf.nblocks);
   uint32_t* starts = const_cast<uint32_t*>(buf.starts);
   double2* spq = const_cast<double2*>(buf.spq);
+  unsigned* gctr = args.barriers;  // [0]: grid barrier, [1 + tile]: barrier of the tile's four CTAs
+  unsigned ggen = 0;
+  // Uses of the tile barrier so far, per round of the quarter loops: round r of this CTA is always the same tile, and
+  // its four CTAs take part in exactly the sweeps in which the tile exists — a count per (CTA, round) is the tile's.
+  __shared__ unsigned s_tuse[4 * kFusedMaxTiles / 4];
+  for (int i = threadIdx.x; i < 4 * kFusedMaxTiles / 4; i += kFusedThreads) s_tuse[i] = 0;
 
+  // phase time stamps of the sweep in progress (globaltimer, CTA 0): where a sweep of the persistent kernel spends its time
+#define HML_STAMP(k)                                                    \
+  do {                                                                  \
+    if (args.phase_ns && cta == 0 && tid == 0) args.phase_ns[k] = global_ns(); \
+  } while (0)
   for (int it = 0; it < args.nsweeps; ++it) {
+    HML_STAMP(0);
     // ---------------- model of this sweep (written by CTA 0 before the barrier that ended the previous one)
     if (tid < KP) model_from_chain<KP>(ch, m, tid);
     __syncthreads();
@@ -230,7 +289,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
         args.cta_count[cta] = t;
       }
     }
-    grid.sync();  // (1) counts of all slices
+    HML_STAMP(1);
+    spin_barrier(gctr, ++ggen * G);  // (1) counts of all slices
+    HML_STAMP(2);
     if (const unsigned code = __ldcg(&ch->phase_abort[1])) {
       if (cta == 0 && tid == 0) ch->abort_code = code;
       break;
@@ -290,18 +351,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
         spq[B] = buf.pq[args.T_local];
       }
     }
-    grid.sync();  // (2) the block list
+    HML_STAMP(3);
+    spin_barrier(gctr, ++ggen * G);  // (2) the block list
+    HML_STAMP(4);
     if (const unsigned code = __ldcg(&ch->phase_abort[2])) {
       if (cta == 0 && tid == 0) ch->abort_code = code;
       break;
     }
     const uint32_t ntiles = (uint32_t)((B + TB - 1) / TB);
+    const uint32_t nq = 4 * ntiles;  // quarters, the empty ones of the last tile included (their CTAs keep the barriers whole)
 
-    // ---------------- per owned tile: block statistics, emission terms, chunk operators, their scan inside the tile
-    for (uint32_t tile = cta; tile < ntiles; tile += G) {
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const uint64_t b = (uint64_t)tile * TB + g4 * 256 + tid;
-        const int cl = tid >> 5, t = tid & 31, c0 = g4 * 8;
+    // ================ phase I, per quarter: block statistics, emission terms, chunk operators and their prefixes
+    for (uint32_t Q = cta; Q < nq; Q += G) {
+      const uint32_t tile = Q >> 2;
+      const int qi = (int)(Q & 3u), c0 = qi * QC;
+      {  // ---- 256 consecutive blocks, one per thread (as k_block_emit)
+        const uint64_t b = (uint64_t)Q * 256 + tid;
+        const int cl = tid >> 5, t = tid & 31;
         const int oc = tid & 7, ot = tid >> 3;
         const bool valid = b < B;
         uint32_t n = 0;
@@ -327,130 +393,159 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
           const int qt = q / (8 * KP), within = q % (8 * KP);
           buf.e[(Layout::at(tile, c0, qt)) * KP + within] = s_e[(within / KP) * PE + qt * KP + within % KP];
         }
-        __syncthreads();
       }
-      // chunk operators: thread (chunk, row), row recursion over the 32 blocks of the chunk (as k_fwd_chunks_prefix)
-      {
-        const int c = tid / KP, i = tid % KP;
-        if (c < C) {
-          const uint64_t first = (uint64_t)tile * TB + (uint64_t)c * L;
-          int steps = 0;
-          if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
-          double r[KP];
-          int rex = 0;
+      // ---- chunk operators: thread (chunk, row) runs the row recursion over the 32 blocks of the chunk, emission terms
+      // straight from the staging area in shared memory
+      const int c = tid / KP, i = tid % KP;
+      if (c < QC) {
+        const uint64_t first = (uint64_t)tile * TB + (uint64_t)(c0 + c) * L;
+        int steps = 0;
+        if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+        double r[KP];
+        int rex = 0;
 #pragma unroll
-          for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
-          const double* ep = buf.e + Layout::at(tile, c, 0) * KP;
+        for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
 #pragma unroll 1
-          for (int t0 = 0; t0 < steps; t0 += 4) {
-            double ev[4][KP];
+        for (int t0 = 0; t0 < steps; t0 += 4) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 4; ++q) {
+            if (t0 + q < steps) {
+              const double* ev = s_e + c * PE + (t0 + q) * KP;
+              double y[KP];
 #pragma unroll
-              for (int j = 0; j < KP; ++j) ev[q][j] = (t0 + q < steps) ? __ldcg(ep + (uint64_t)(t0 + q) * C * KP + j) : 0.0;
-            }
+              for (int j = 0; j < KP; ++j) y[j] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (t0 + q < steps) {
-                double y[KP];
+              for (int k = 0; k < KP; ++k) {
 #pragma unroll
-                for (int j = 0; j < KP; ++j) y[j] = 0.0;
-#pragma unroll
-                for (int k = 0; k < KP; ++k) {
-#pragma unroll
-                  for (int j = 0; j < KP; ++j) y[j] = fma(r[k], m.A[k][j], y[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < KP; ++j) r[j] = y[j] * ev[q][j];
+                for (int j = 0; j < KP; ++j) y[j] = fma(r[k], m.A[k][j], y[j]);
               }
+#pragma unroll
+              for (int j = 0; j < KP; ++j) r[j] = y[j] * ev[j];
             }
-            if (rex != kDeadExp) renorm_pow2<KP>(r, rex);
           }
-#pragma unroll
-          for (int j = 0; j < KP; ++j) s_ops[(c * KP + i) * KP + j] = r[j];
-          s_exp[c * KP + i] = rex;
+          if (rex != kDeadExp) renorm_pow2<KP>(r, rex);
         }
-        __syncthreads();
-        const int pr = tid / KP, row = tid % KP;
-        for (int stride = 1; stride < C; stride <<= 1) {  // up-sweep
-          const int n2 = (pr + 1) * 2 * stride - 1;
-          const bool on = n2 < C;
-          double r[KP];
-          int rex = 0;
-          if (on) {
 #pragma unroll
-            for (int j = 0; j < KP; ++j) r[j] = s_ops[((n2 - stride) * KP + row) * KP + j];
-            rex = s_exp[(n2 - stride) * KP + row];
-            row_times_op<KP, false>(r, rex, s_ops + n2 * KP * KP, s_exp + n2 * KP);
-          }
-          __syncthreads();
-          if (on) {
-#pragma unroll
-            for (int j = 0; j < KP; ++j) s_ops[(n2 * KP + row) * KP + j] = r[j];
-            s_exp[n2 * KP + row] = rex;
-          }
-          __syncthreads();
-        }
-        if (tid < KP) {
-#pragma unroll
-          for (int j = 0; j < KP; ++j) {
-            buf.tile_ops[((uint64_t)tile * KP + tid) * KP + j] = s_ops[((C - 1) * KP + tid) * KP + j];
-            s_ops[((C - 1) * KP + tid) * KP + j] = (j == tid) ? 1.0 : 0.0;
-          }
-          buf.tile_exp[(uint64_t)tile * KP + tid] = s_exp[(C - 1) * KP + tid];
-          s_exp[(C - 1) * KP + tid] = 0;
-        }
-        __syncthreads();
-        for (int stride = C / 2; stride >= 1; stride >>= 1) {  // down-sweep
-          const int n2 = (pr + 1) * 2 * stride - 1;
-          const bool on = n2 < C;
-          double pfx[KP], r[KP];
-          int pex = 0, rex = 0;
-          if (on) {
-#pragma unroll
-            for (int j = 0; j < KP; ++j) pfx[j] = r[j] = s_ops[(n2 * KP + row) * KP + j];
-            pex = rex = s_exp[n2 * KP + row];
-            row_times_op<KP, false>(r, rex, s_ops + (n2 - stride) * KP * KP, s_exp + (n2 - stride) * KP);
-          }
-          __syncthreads();
-          if (on) {
-#pragma unroll
-            for (int j = 0; j < KP; ++j) {
-              s_ops[((n2 - stride) * KP + row) * KP + j] = pfx[j];
-              s_ops[(n2 * KP + row) * KP + j] = r[j];
-            }
-            s_exp[(n2 - stride) * KP + row] = pex;
-            s_exp[n2 * KP + row] = rex;
-          }
-          __syncthreads();
-        }
-        for (int k = tid; k < C * KP * KP; k += kFusedThreads) buf.chunk_ops[(uint64_t)tile * C * KP * KP + k] = s_ops[k];
-        for (int k = tid; k < C * KP; k += kFusedThreads) buf.chunk_exp[(uint64_t)tile * C * KP + k] = s_exp[k];
-        __syncthreads();
+        for (int j = 0; j < KP; ++j) s_ops[(c * KP + i) * KP + j] = r[j];
+        s_exp[c * KP + i] = rex;
       }
+      __syncthreads();
+      // ---- exclusive prefixes inside the quarter: thread (c, i) multiplies row i of the identity through chunks 0..c-1;
+      // thread (7, i) goes one further: the quarter's total, published for the other CTAs of the tile
+      if (c < QC) {
+        double r[KP];
+        int rex = 0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
+        for (int k = 0; k < c; ++k) row_times_op<KP, false>(r, rex, s_ops + k * KP * KP, s_exp + k * KP);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) s_pre[(c * KP + i) * KP + j] = r[j];
+        s_pex[c * KP + i] = rex;
+        if (c == QC - 1) {
+          row_times_op<KP, false>(r, rex, s_ops + c * KP * KP, s_exp + c * KP);
+          double* dst = args.qtot + (size_t)Q * OPW;
+#pragma unroll
+          for (int j = 0; j < KP; ++j) dst[i * KP + j] = r[j];
+          dst[KP * KP + i] = (double)rex;
+        }
+      }
+      {
+        const uint32_t round = (Q - cta) / G;
+        const unsigned target = 4u * (s_tuse[round] + 1u);
+        spin_barrier(gctr + 1 + tile, target);  // the four quarters of the tile
+        if (tid == 0) s_tuse[round] += 1u;
+      }
+      // ---- product of the quarters in front of this one (row i by thread i), then prefix in the tile = base x prefix in
+      // the quarter; the last quarter also forms the tile operator
+      if (tid < KP) {
+        double r[KP];
+        int rex = 0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = (j == tid) ? 1.0 : 0.0;
+        if constexpr (KP <= 5) {
+          double M3[3][KP * KP];  // the totals of the (up to three) quarters in front: all loads in flight together
+          int X3[3][KP];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (k < qi) {
+              const double* src = args.qtot + (size_t)(tile * 4 + k) * OPW;
+#pragma unroll
+              for (int w = 0; w < KP * KP; ++w) M3[k][w] = __ldcg(src + w);
+#pragma unroll
+              for (int w = 0; w < KP; ++w) X3[k][w] = (int)__ldcg(src + KP * KP + w);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (k < qi) row_times_op<KP, false>(r, rex, M3[k], X3[k]);
+        } else {  // (192 registers for three 8 x 8 operators: one at a time)
+          for (int k = 0; k < qi; ++k) {
+            double M[KP * KP];
+            int X[KP];
+            const double* src = args.qtot + (size_t)(tile * 4 + k) * OPW;
+#pragma unroll
+            for (int w = 0; w < KP * KP; ++w) M[w] = __ldcg(src + w);
+#pragma unroll
+            for (int w = 0; w < KP; ++w) X[w] = (int)__ldcg(src + KP * KP + w);
+            row_times_op<KP, false>(r, rex, M, X);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < KP; ++j) s_base[tid * KP + j] = r[j];
+        s_bex[tid] = rex;
+        if (qi == 3) {  // tile operator = base x own total
+          double M[KP * KP];
+          int X[KP];
+          const double* src = args.qtot + (size_t)Q * OPW;
+#pragma unroll
+          for (int w = 0; w < KP * KP; ++w) M[w] = __ldcg(src + w);
+#pragma unroll
+          for (int w = 0; w < KP; ++w) X[w] = (int)__ldcg(src + KP * KP + w);
+          row_times_op<KP, false>(r, rex, M, X);
+#pragma unroll
+          for (int j = 0; j < KP; ++j) buf.tile_ops[((uint64_t)tile * KP + tid) * KP + j] = r[j];
+          buf.tile_exp[(uint64_t)tile * KP + tid] = rex;
+        }
+      }
+      __syncthreads();
+      if (c < QC) {
+        double r[KP];
+        int rex = s_bex[i];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) r[j] = s_base[i * KP + j];
+        row_times_op<KP, false>(r, rex, s_pre + c * KP * KP, s_pex + c * KP);
+        const uint64_t ch_idx = (uint64_t)tile * C + c0 + c;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.chunk_ops[(ch_idx * KP + i) * KP + j] = r[j];
+        buf.chunk_exp[ch_idx * KP + i] = rex;
+      }
+      __syncthreads();
     }
-    grid.sync();  // (3) tile operators
+    HML_STAMP(5);
+    spin_barrier(gctr, ++ggen * G);  // (3) tile operators
+    HML_STAMP(6);
 
-    // ---------------- forward: vector entering each owned tile, rows of the tile, backward maps, chunk and tile maps
+    // ================ phase II, per quarter: forward rows, backward maps, chunk and quarter maps, tile map
+    const bool resident = nq <= G;  // one quarter per CTA: its emission terms, block sizes and sums are still in shared memory
     unsigned fallbacks = 0;
-    for (uint32_t tile = cta; tile < ntiles; tile += G) {
+    for (uint32_t Q = cta; Q < nq; Q += G) {
+      const uint32_t tile = Q >> 2;
+      const int qi = (int)(Q & 3u), c0 = qi * QC;
       if (warp == 0) {
         // every CTA walks the tile operators in front of its tile itself (at most 63 vector-operator products)
         double a[KP];
 #pragma unroll
         for (int j = 0; j < KP; ++j) a[j] = m.pi[j];
-        OpVals<KP> cur, nxt;
-        if (tile > 0) load_op_cg<KP>(cur, buf.tile_ops, buf.tile_exp);
         for (uint32_t t = 0; t < tile; ++t) {
-          if (t + 1 < tile) load_op_cg<KP>(nxt, buf.tile_ops + (uint64_t)(t + 1) * KP * KP, buf.tile_exp + (uint64_t)(t + 1) * KP);
-          if (!vec_apply_op<KP>(a, cur)) fallbacks++;
-          cur = nxt;
+          OpVals<KP> o;
+          load_op_cg<KP>(o, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
+          if (!vec_apply_op<KP>(a, o)) fallbacks++;
         }
-        // ---- rows: lane c owns chunk c (as k_fwd_replay_prefix, power-of-two rescaling instead of the division)
-        const int c = lane;
+        // ---- rows: lane c < 8 owns chunk c0 + c (as k_fwd_replay_prefix, power-of-two rescaling instead of the division)
+        const int cq = lane & 7, c = c0 + cq;
         const uint64_t first = (uint64_t)tile * TB + (uint64_t)c * L;
         int steps = 0;
-        if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+        if (lane < QC && first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
         if (c > 0 && steps > 0) {
           OpVals<KP> o;
           load_op<KP>(o, buf.chunk_ops + ((uint64_t)tile * C + c) * KP * KP, buf.chunk_exp + ((uint64_t)tile * C + c) * KP);
@@ -463,7 +558,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
 #pragma unroll
-            for (int j = 0; j < KP; ++j) ev[q][j] = (t0 + q < steps) ? __ldcg(ep + (uint64_t)(t0 + q) * C * KP + j) : 0.0;
+            for (int j = 0; j < KP; ++j)
+              ev[q][j] = (t0 + q < steps) ? (resident ? s_e[cq * PE + (t0 + q) * KP + j] : ep[(uint64_t)(t0 + q) * C * KP + j]) : 0.0;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -493,26 +589,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
 #pragma unroll
                 for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
               }
-              const uint64_t p = Layout::at(tile, c, t0 + q);
 #pragma unroll
-              for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
+              for (int j = 0; j < KP; ++j) s_alpha[cq * PE + (t0 + q) * KP + j] = a[j];
             }
           }
         }
       }
       __syncthreads();
-      // ---- backward maps of the tile's blocks (as k_bwd_maps)
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const uint64_t p = (uint64_t)tile * TB + g4 * 256 + tid;
-        const uint64_t b = Layout::inv(p);
+      HML_STAMP(13);
+      {  // ---- backward map of this thread's block (as k_bwd_maps)
+        const uint64_t b = (uint64_t)Q * 256 + tid;
+        const uint64_t p = Layout::perm(b);
         Map<KP> fm = Map<KP>::identity();
         if (b < B) {
           const bool last = b + 1 == B;
-          const double Nm1 = (double)buf.bN[p] - 1.0;
+          const double Nm1 = (double)(resident ? s_n[(tid >> 5) * PB + (tid & 31)] : buf.bN[p]) - 1.0;
           double ap[KP];
 #pragma unroll
           for (int j = 0; j < KP; ++j) {
-            const double al = buf.alpha[p * KP + j];
+            const double al = s_alpha[(tid >> 5) * PE + (tid & 31) * KP + j];
             ap[j] = (last || !m.use_self || j >= K) ? al : al * exp_nonpos(Nm1 * m.loga[j], s_tab);
           }
           const double u = buf.replay_u ? buf.replay_u[B - 1 - b] : Philox::uniform(args.seed, sweep_key, 0u, b);
@@ -542,38 +637,67 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
             }
           }
         }
-        fm.store(buf.maps + p * MB);
+        s_maps[tid] = fm.w[0];
+        if (!resident) fm.store(buf.maps + p * MB);  // phase III of a CTA with several quarters reads them back
       }
       __syncthreads();
-      if (warp == 0) {  // chunk maps and the tile map (as k_bwd_chunkmaps)
+      HML_STAMP(14);
+      if (warp == 0) {
+        // chunk maps of the quarter's 8 chunks (lanes 0..7), their suffixes inside the quarter, the quarter map
         Map<KP> Gm = Map<KP>::identity();
-#pragma unroll 4
-        for (int t = 0; t < L; ++t) Gm = Gm.after(Map<KP>::load(buf.maps + Layout::at(tile, lane, t) * MB));
-        Map<KP> inc = Gm;
+        if (lane < QC) {
+#pragma unroll 8
+          for (int t = 0; t < L; ++t) {
+            Map<KP> f;
+            f.w[0] = s_maps[lane * L + t];
+            Gm = Gm.after(f);
+          }
+        }
+        Map<KP> inc = Gm;  // inclusive suffix over lanes lane..7
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < QC; o <<= 1) {
           Map<KP> other;
-#pragma unroll
-          for (int i = 0; i < Map<KP>::W; ++i) other.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], o);
-          if (lane + o < 32) inc = inc.after(other);
+          other.w[0] = __shfl_down_sync(0xffffffffu, inc.w[0], o);
+          if (lane + o < QC) inc = inc.after(other);
         }
         Map<KP> excl;
-#pragma unroll
-        for (int i = 0; i < Map<KP>::W; ++i) excl.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
-        if (lane == 31) excl = Map<KP>::identity();
-        excl.store(buf.chunk_maps + ((uint64_t)tile * C + lane) * MB);
-        if (lane == 0) inc.store(buf.tile_maps + (uint64_t)tile * MB);
+        excl.w[0] = __shfl_down_sync(0xffffffffu, inc.w[0], 1);
+        if (lane == QC - 1) excl = Map<KP>::identity();
+        if (lane < QC) excl.store(buf.chunk_maps + ((uint64_t)tile * C + c0 + lane) * MB);  // later chunks of the QUARTER
+        if (lane == 0) args.qmap[Q] = inc.w[0];
       }
-      __syncthreads();
+      HML_STAMP(15);
+      {
+        const uint32_t round = (Q - cta) / G;
+        const unsigned target = 4u * (s_tuse[round] + 1u);
+        spin_barrier(gctr + 1 + tile, target);
+        if (tid == 0) s_tuse[round] += 1u;
+      }
+      if (qi == 0 && tid == 0) {  // tile map = composition of the four quarter maps
+        unsigned long long w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w4[k] = __ldcg(args.qmap + Q + k);
+        Map<KP> tm;
+        tm.w[0] = w4[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          Map<KP> o;
+          o.w[0] = w4[k];
+          tm = tm.after(o);
+        }
+        tm.store(buf.tile_maps + (uint64_t)tile * MB);
+      }
     }
     if (fallbacks) ch->phase_abort[4] = kChainFallback;
-    grid.sync();  // (4) tile maps
+    HML_STAMP(7);
+    spin_barrier(gctr, ++ggen * G);  // (4) tile maps
+    HML_STAMP(8);
     if (const unsigned code = __ldcg(&ch->phase_abort[4])) {
       if (cta == 0 && tid == 0) ch->abort_code = code;
       break;
     }
 
-    // ---------------- backward: state following each owned tile, states of the tile, statistics
+    // ================ phase III, per quarter: the state following it, the states of its blocks, their statistics
     double ax[KP], aq[KP];
     unsigned long long an[KP], ad[KP];
 #pragma unroll
@@ -583,65 +707,89 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
     }
     for (int i = tid; i < KP * KP + KP; i += kFusedThreads) s_cnt[i] = 0;
     __syncthreads();
-    for (uint32_t tile = cta; tile < ntiles; tile += G) {
-      if (tid == 0) {
+    for (uint32_t Q = cta; Q < nq; Q += G) {
+      const uint32_t tile = Q >> 2;
+      const int qi = (int)(Q & 3u), c0 = qi * QC;
+      if (warp == 0) {
+        // maps of the later tiles (lane t holds tiles 32 k + t) and of the later quarters of this tile: all loads are in
+        // flight together, then the look-ups run from the last tile down
+        unsigned long long tw[kFusedMaxTiles / 32];
+#pragma unroll
+        for (int k = 0; k < kFusedMaxTiles / 32; ++k) {
+          const uint32_t t = 32u * k + lane;
+          tw[k] = (t > tile && t < ntiles) ? __ldcg(reinterpret_cast<const unsigned long long*>(buf.tile_maps + (uint64_t)t * MB)) : 0ull;
+        }
+        const unsigned long long qw = (lane > (unsigned)qi && lane < 4) ? __ldcg(args.qmap + tile * 4 + lane) : 0ull;
         uint32_t q = 0;  // the last block of the sequence carries a constant map: the start value is irrelevant
-        for (uint32_t t = ntiles - 1; t > tile; --t) q = load_map_cg<KP>(buf.tile_maps + (uint64_t)t * MB).get(q);
-        s_misc[2] = q;
-        buf.tile_qin[tile] = (uint8_t)q;
-      }
-      __syncthreads();
-      const uint32_t qin = s_misc[2];
-      if (tid < C) {  // states of the tile's chunks (as k_bwd_replay)
-        const int c = tid;
-        const uint64_t first = (uint64_t)tile * TB + (uint64_t)c * L;
-        if (first < B) {
-          const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
-          uint32_t q = Map<KP>::load(buf.chunk_maps + ((uint64_t)tile * C + c) * MB).get(qin);
-          for (int t0 = steps - 1; t0 >= 0; t0 -= 8) {
-            Map<KP> mp[8];
+        for (uint32_t t = ntiles - 1; t > tile; --t) {
+          unsigned long long w = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (t0 - i >= 0) mp[i] = Map<KP>::load(buf.maps + Layout::at(tile, c, t0 - i) * MB);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (t0 - i >= 0) {
-                q = mp[i].get(q);
-                buf.states[Layout::at(tile, c, t0 - i)] = (uint8_t)q;
-              }
+          for (int k = 0; k < kFusedMaxTiles / 32; ++k)
+            if ((t >> 5) == (uint32_t)k) w = __shfl_sync(0xffffffffu, tw[k], t & 31);
+          q = (uint32_t)(w >> (8 * q)) & 0xffu;
+        }
+        if (qi == 0 && lane == 0) buf.tile_qin[tile] = (uint8_t)q;
+        for (int k = 3; k > qi; --k) {
+          const unsigned long long w = __shfl_sync(0xffffffffu, qw, k);
+          q = (uint32_t)(w >> (8 * q)) & 0xffu;
+        }
+        if (lane == 0) s_misc[2] = q;  // state of the block that follows the quarter
+        // ---- states of the quarter's chunks (as k_bwd_replay): lane c < 8
+        if (lane < QC) {
+          const int c = c0 + lane;
+          const uint64_t first = (uint64_t)tile * TB + (uint64_t)c * L;
+          if (first < B) {
+            const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+            uint32_t qs = Map<KP>::load(buf.chunk_maps + ((uint64_t)tile * C + c) * MB).get(q);
+            for (int t = steps - 1; t >= 0; --t) {
+              Map<KP> f;
+              f.w[0] = resident ? s_maps[lane * L + t] : *reinterpret_cast<const unsigned long long*>(buf.maps + Layout::at(tile, c, t) * MB);
+              qs = f.get(qs);
+              s_states[lane * L + t] = (uint8_t)qs;
+              buf.states[Layout::at(tile, c, t)] = (uint8_t)qs;
             }
           }
         }
       }
       __syncthreads();
-      // statistics of the tile's blocks (as k_reduce_partial; the successor of the tile's last block is qin)
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const uint64_t p = (uint64_t)tile * TB + g4 * 256 + tid;
-        const uint64_t b = Layout::inv(p);
-        if (b >= B) continue;
-        const uint32_t st = buf.states[p];
-        const bool has_next = b + 1 < B;
-        uint32_t next = st;
-        if (has_next) next = ((b + 1) % TB == 0) ? qin : (uint32_t)buf.states[Layout::perm(b + 1)];
-        const uint32_t n = buf.bN[p];
-        const double2 v = buf.bS[p];
-        unsigned long long dg = (unsigned long long)(n - 1) + ((has_next && next == st) ? 1ull : 0ull);
-        if (b == 0) {  // the phantom transition 0 -> q_0 (FB.hpp:177,182-184)
-          if (st == 0u)
-            dg += 1ull;
-          else
-            atomicAdd(&s_cnt[st], 1ull);
-        }
+      const uint32_t qafter = s_misc[2];
+      {  // statistics of this thread's block (as k_reduce_partial; the successor of the quarter's last block is qafter)
+        const uint64_t b = (uint64_t)Q * 256 + tid;
+        if (b < B) {
+          const uint64_t p = Layout::perm(b);
+          const uint32_t st = s_states[tid];
+          const bool has_next = b + 1 < B;
+          uint32_t next = st;
+          if (has_next) next = (tid == 255) ? qafter : (uint32_t)s_states[tid + 1];
+          uint32_t n;
+          double2 v;
+          if (resident) {
+            const int si = (tid >> 5) * PB + (tid & 31);
+            n = s_n[si];
+            v = make_double2(s_sx[si], s_sq[si]);
+          } else {
+            n = buf.bN[p];
+            v = buf.bS[p];
+          }
+          unsigned long long dg = (unsigned long long)(n - 1) + ((has_next && next == st) ? 1ull : 0ull);
+          if (b == 0) {  // the phantom transition 0 -> q_0 (FB.hpp:177,182-184)
+            if (st == 0u)
+              dg += 1ull;
+            else
+              atomicAdd(&s_cnt[st], 1ull);
+          }
 #pragma unroll
-        for (int s = 0; s < KP; ++s) {
-          const bool hit = st == (uint32_t)s;
-          ax[s] += hit ? v.x : 0.0;
-          aq[s] += hit ? v.y : 0.0;
-          an[s] += hit ? (unsigned long long)n : 0ull;
-          ad[s] += hit ? dg : 0ull;
+          for (int s = 0; s < KP; ++s) {
+            const bool hit = st == (uint32_t)s;
+            ax[s] += hit ? v.x : 0.0;
+            aq[s] += hit ? v.y : 0.0;
+            an[s] += hit ? (unsigned long long)n : 0ull;
+            ad[s] += hit ? dg : 0ull;
+          }
+          if (has_next && next != st) atomicAdd(&s_cnt[st * KP + next], 1ull);
         }
-        if (has_next && next != st) atomicAdd(&s_cnt[st * KP + next], 1ull);
       }
+      __syncthreads();
     }
 #pragma unroll
     for (int s = 0; s < KP; ++s) {
@@ -672,13 +820,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
       if (s_cnt[i]) atomicAdd(&buf.out_u64[KP + i], s_cnt[i]);
     for (int i = tid; i < KP; i += kFusedThreads)
       if (s_cnt[KP * KP + i]) atomicAdd(&buf.out_u64[i], s_cnt[KP * KP + i]);
-    grid.sync();  // (5) partial statistics
+    HML_STAMP(9);
+    spin_barrier(gctr, ++ggen * G);  // (5) partial statistics
+    HML_STAMP(10);
     if (cta == 0) {
       // final sums in a fixed order (deterministic), then the parameters of the next sweep
-      if (tid < 2 * KP) {
+      for (int v = warp; v < 2 * KP; v += kFusedThreads / 32) {  // lanes stride over the CTAs, then a fixed tree
         double t = 0.0;
-        for (uint32_t c2 = 0; c2 < G; ++c2) t += __ldcg(buf.partials + (size_t)c2 * 2 * KP + tid);
-        buf.out_f64[tid] = t;
+        for (uint32_t c2 = lane; c2 < G; c2 += 32) t += __ldcg(buf.partials + (size_t)c2 * 2 * KP + v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += shfl_xor_double(t, o);
+        if (lane == 0) buf.out_f64[v] = t;
       }
       __syncthreads();
       if (tid == 0) ch->sweeps_done += 1u;
@@ -688,12 +840,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
       }
       __threadfence();
     }
-    grid.sync();  // (6) the model of the next sweep
+    HML_STAMP(11);
+    spin_barrier(gctr, ++ggen * G);  // (6) the model of the next sweep
+    HML_STAMP(12);
     if (const unsigned code = __ldcg(&ch->phase_abort[6])) {
       if (cta == 0 && tid == 0) ch->abort_code = code;
       break;
     }
   }
+#undef HML_STAMP
 }
 
 // one cooperative launch of `a.nsweeps` sweeps; returns the cudaError_t of the launch

@@ -186,6 +186,10 @@ struct FusedArgs {
   uint32_t nc;
   uint32_t T_local;
   uint32_t* cta_count;  // gridDim.x words
+  unsigned* barriers;   // 1 + kFusedMaxTiles words, zero at launch: grid barrier, then one barrier per tile
+  double* qtot;         // 4 * kFusedMaxTiles operators of K*K + K doubles: the quarter-tile totals
+  unsigned long long* qmap;  // 4 * kFusedMaxTiles words: the quarter-tile maps
+  unsigned long long* phase_ns;  // 16 words or null: globaltimer stamps of CTA 0 at the phase borders of the last sweep
   int nsweeps;
   int sample_params;    // 0: the model stays as it is (single sweeps with a caller-provided model)
   int philox_sweep_from_chain;  // uniforms keyed by chain->sweep (chain mode) or by `sweep` (single sweep)

@@ -557,10 +557,9 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
       }
       __syncthreads();
     }
-    return;
   }
   // slots is a multiple of 1024 and the stride a multiple of 256: all threads of a CTA make the same trips
-  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; !kNatural && p < slots; p += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = Layout::inv(p);
     const bool valid = b < B;
     if (!kStage && !valid) continue;

@@ -270,6 +270,10 @@ int hml_exchange_transport(const hml_t* h, int* transport);
  * stream.  hml_get_timing returns the stage names and the milliseconds of the LAST sweep. */
 int hml_set_timing(hml_t* h, int on);
 int hml_get_timing(hml_t* h, int* nstages, const char** names, float* ms, int capacity);
+/* With timing on, CTA 0 of the persistent kernel stamps %globaltimer at the 13 phase borders of a sweep (model, candidate
+ * count | barrier | scatter | barrier | statistics + emission + chunk operators | barrier | forward rows + maps | barrier
+ * | states + statistics | barrier | final sums + parameter draws | barrier): nanoseconds of the last fused sweep. */
+int hml_chain_phase_ns(hml_t* h, uint64_t stamps[16]);
 /* Number of kernel launches issued by this handle since creation. */
 int hml_launch_count(const hml_t* h, uint64_t* n);
 /* Blocks until all work queued on the handle's stream has finished. */

@@ -55,13 +55,25 @@ def main():
         for _ in range(200):
             out1 = h.chain_run(1)
         single_rate = 200 / (time.perf_counter() - t0)
+        h.set_timing(True)
+        h.chain_run(50)
+        st = h.chain_phase_ns().astype(np.int64)
+        h.set_timing(False)
+        names = ["model+count", "barrier1", "scatter", "barrier2", "stats+emit+chunk_ops", "barrier3", "rows+maps+chunk_maps",
+                 "barrier4", "states+reduce", "barrier5", "final+params", "barrier6"]
+        phases = {names[i]: float(st[i + 1] - st[i]) / 1000.0 for i in range(12)} if st[12] > st[0] > 0 else None
+        if phases and st[13] > 0:   # inside "rows+maps+chunk_maps" (CTA 0's first quarter)
+            phases["  of which rows"] = float(st[13] - st[6]) / 1000.0
+            phases["  of which maps"] = float(st[14] - st[13]) / 1000.0
+            phases["  of which chunk maps"] = float(st[15] - st[14]) / 1000.0
+            phases["  of which tile barrier + tile map"] = float(st[7] - st[15]) / 1000.0
         ok = bool(out["trans"].sum() == T and out["counts"].sum() == T and out["stat_n"].sum() == T)
         print(json.dumps({"config": name, "note": cfg["note"], "T": T, "K": K, "blocks_host_chain": int(nb_host),
                           "blocks_device_chain": int(out["nblocks"]), "sweeps_timed": n,
                           "host_chain_sweeps_per_s": host_rate, "host_chain_us_per_sweep": 1e6 / host_rate,
                           "device_chain_sweeps_per_s": dev_rate, "device_chain_us_per_sweep": 1e6 / dev_rate,
                           "device_chain_fused_sweeps": int(out["fused"]), "device_chain_one_sweep_per_call_per_s": single_rate,
-                          "speedup": dev_rate / host_rate, "invariants_ok": ok and int(out1["fused"]) in (0, 1)}), flush=True)
+                          "speedup": dev_rate / host_rate, "fused_phase_us": phases, "invariants_ok": ok and int(out1["fused"]) in (0, 1)}), flush=True)
         h.close()
 
 
