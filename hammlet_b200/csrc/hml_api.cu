@@ -172,6 +172,8 @@ struct hml_ctx {
   double* fused_qtot = nullptr;
   unsigned long long* fused_qmap = nullptr;
   unsigned long long* fused_phase_ns = nullptr;
+  double* fused_subops = nullptr;
+  unsigned long long* fused_submaps = nullptr;
   unsigned long long* chain_stats = nullptr;  // result block of the whole sequence (segment mode: summed over the ranks)
   bool chain_ready = false;            // hml_chain_init has been called
   uint64_t chain_fused_sweeps = 0, chain_standard_sweeps = 0;
@@ -958,6 +960,8 @@ int chain_alloc(hml_t* h) {
     CK(dev_alloc(h->fused_barriers, 1 + kFusedMaxTiles));
     CK(dev_alloc(h->fused_qtot, (size_t)4 * kFusedMaxTiles * (kChainMaxStates * kChainMaxStates + kChainMaxStates)));
     CK(dev_alloc(h->fused_qmap, (size_t)4 * kFusedMaxTiles));
+    CK(dev_alloc(h->fused_subops, (size_t)4 * kFusedMaxTiles * 32 * (kChainMaxStates * kChainMaxStates + kChainMaxStates)));
+    CK(dev_alloc(h->fused_submaps, (size_t)4 * kFusedMaxTiles * 32));
     CK(dev_alloc(h->fused_phase_ns, 16));
     CK(cudaMemsetAsync(h->fused_phase_ns, 0, 16 * 8, h->stream));
     CK(dev_alloc(h->chain_stats, kOutWords));
@@ -1016,6 +1020,8 @@ int fused_launch(hml_t* h, int KP, int nsweeps, bool sample_params, bool philox_
   a.qtot = h->fused_qtot;
   a.qmap = h->fused_qmap;
   a.phase_ns = h->timing ? h->fused_phase_ns : nullptr;
+  a.subops = h->fused_subops;
+  a.submaps = h->fused_submaps;
   CK(cudaMemsetAsync(h->fused_barriers, 0, (1 + kFusedMaxTiles) * sizeof(unsigned), h->stream));
   a.nsweeps = nsweeps;
   a.sample_params = sample_params ? 1 : 0;
@@ -1466,6 +1472,8 @@ int hml_destroy(hml_t* h) {
   dev_free(h->fused_qtot);
   dev_free(h->fused_qmap);
   dev_free(h->fused_phase_ns);
+  dev_free(h->fused_subops);
+  dev_free(h->fused_submaps);
   dev_free(h->chain_stats);
   if (h->chain_host) cudaFreeHost(h->chain_host);
   h->chain_host = nullptr;

@@ -205,22 +205,27 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One CTA per QUARTER of a tile (256 consecutive blocks = 8 chunks of 32); the four CTAs of a tile meet at a tile-local
-// barrier where the tile's chunk operators / chunk maps are combined.  Grid = 4 x tiles (a multiple of 4, at most one
+// One CTA per QUARTER of a tile (256 consecutive blocks = 8 chunks of 32 = 32 sub-chunks of 8); the four CTAs of a tile
+// meet at a tile-local barrier where the tile's operators / maps are combined.  Grid = 4 x tiles (a multiple of 4, at most one
 // CTA per SM); with more quarters than CTAs a CTA takes several, the four of a tile always in the same round.
 template <int KP>
 __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers buf, FusedArgs args) {
   constexpr int L = Layout::L, C = Layout::C, TB = Layout::TB, MB = 8 * Map<KP>::W;
   constexpr int QC = 8;                 // chunks per quarter
+  constexpr int NS = 32, SL = 8;        // sub-chunks per quarter, blocks per sub-chunk
   constexpr int PE = 33 * KP, PB = 36;  // row pitches of the emission staging (see k_block_emit)
-  constexpr int OPW = KP * KP + KP;     // doubles of one operator in the quarter-total exchange (mantissas, exponents)
+  constexpr int OPW = KP * KP + KP;     // doubles of one operator in the exchanges (mantissas, then exponents)
   static_assert(Map<KP>::W == 1, "K <= 8: maps are one word");
+  static_assert(NS * KP <= kFusedThreads, "thread (sub-chunk, row)");
+  extern __shared__ __align__(16) double s_fdyn[];  // two operator buffers of the quarter's 32 sub-chunks (scan ping-pong)
+  double* const s_opA = s_fdyn;
+  double* const s_opB = s_fdyn + NS * KP * KP;
+  __shared__ int s_exA[NS * KP], s_exB[NS * KP];
+  double* s_pfx = s_opA;                  // where the prefixes of the sub-chunks inside the tile ended up
+  int* s_pfxx = s_exA;
+  __shared__ unsigned long long s_subx[NS];  // per sub-chunk: map of the later sub-chunks of the quarter
   __shared__ ModelDev<KP> m;
   __shared__ double s_tab[64];
-  __shared__ double s_ops[QC * KP * KP];  // chunk operators of the quarter
-  __shared__ int s_exp[QC * KP];
-  __shared__ double s_pre[QC * KP * KP];  // their exclusive prefixes inside the quarter
-  __shared__ int s_pex[QC * KP];
   __shared__ double s_base[KP * KP];      // product of the quarters in front of this one (identity for quarter 0)
   __shared__ int s_bex[KP];
   __shared__ double s_e[QC * PE];
@@ -361,7 +366,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
     const uint32_t ntiles = (uint32_t)((B + TB - 1) / TB);
     const uint32_t nq = 4 * ntiles;  // quarters, the empty ones of the last tile included (their CTAs keep the barriers whole)
 
-    // ================ phase I, per quarter: block statistics, emission terms, chunk operators and their prefixes
+    // ================ phase I, per quarter: block statistics, emission terms, sub-chunk operators and their prefixes
+    // A quarter is 32 SUB-CHUNKS of 8 consecutive blocks (four per chunk).  The phases that walk blocks one after the
+    // other — operator recursion, forward rows, map composition, state look-up — are a single warp per SM-quarter paced
+    // by instruction latency (~6.5 cycles per dependent instruction): 8 steps per lane instead of 32 is four times less
+    // of that, paid for with a 32-element operator scan inside the quarter.
+    const bool resident = nq <= G;  // one quarter per CTA: what a phase leaves in shared memory is there for the next
     for (uint32_t Q = cta; Q < nq; Q += G) {
       const uint32_t tile = Q >> 2;
       const int qi = (int)(Q & 3u), c0 = qi * QC;
@@ -387,30 +397,34 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
           buf.bN[op] = s_n[oc * PB + ot];
           buf.bS[op] = make_double2(s_sx[oc * PB + ot], s_sq[oc * PB + ot]);
         }
+        if (!resident) {  // a CTA with several quarters reads the emission terms back in phase II
 #pragma unroll
-        for (int k = 0; k < KP; ++k) {
-          const int q = k * 256 + tid;
-          const int qt = q / (8 * KP), within = q % (8 * KP);
-          buf.e[(Layout::at(tile, c0, qt)) * KP + within] = s_e[(within / KP) * PE + qt * KP + within % KP];
+          for (int k = 0; k < KP; ++k) {
+            const int q = k * 256 + tid;
+            const int qt = q / (8 * KP), within = q % (8 * KP);
+            buf.e[(Layout::at(tile, c0, qt)) * KP + within] = s_e[(within / KP) * PE + qt * KP + within % KP];
+          }
         }
       }
-      // ---- chunk operators: thread (chunk, row) runs the row recursion over the 32 blocks of the chunk, emission terms
+      // ---- sub-chunk operators: thread (sub-chunk, row) runs the row recursion over its 8 blocks, emission terms
       // straight from the staging area in shared memory
-      const int c = tid / KP, i = tid % KP;
-      if (c < QC) {
-        const uint64_t first = (uint64_t)tile * TB + (uint64_t)(c0 + c) * L;
+      const int sc = tid / KP, i = tid % KP;
+      const uint64_t qfirst = (uint64_t)Q * 256;
+      if (sc < NS) {
+        const uint64_t first = qfirst + (uint64_t)sc * SL;
         int steps = 0;
-        if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+        if (first < B) steps = (B - first) < (uint64_t)SL ? (int)(B - first) : SL;
         double r[KP];
         int rex = 0;
 #pragma unroll
         for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
-#pragma unroll 1
-        for (int t0 = 0; t0 < steps; t0 += 4) {
+        const double* ev0 = s_e + (sc >> 2) * PE + (sc & 3) * SL * KP;
+#pragma unroll
+        for (int h4 = 0; h4 < SL; h4 += 4) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (t0 + q < steps) {
-              const double* ev = s_e + c * PE + (t0 + q) * KP;
+            if (h4 + q < steps) {
+              const double* ev = ev0 + (h4 + q) * KP;
               double y[KP];
 #pragma unroll
               for (int j = 0; j < KP; ++j) y[j] = 0.0;
@@ -423,31 +437,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
               for (int j = 0; j < KP; ++j) r[j] = y[j] * ev[j];
             }
           }
-          if (rex != kDeadExp) renorm_pow2<KP>(r, rex);
+          if (rex != kDeadExp && h4 < steps) renorm_pow2<KP>(r, rex);
         }
 #pragma unroll
-        for (int j = 0; j < KP; ++j) s_ops[(c * KP + i) * KP + j] = r[j];
-        s_exp[c * KP + i] = rex;
+        for (int j = 0; j < KP; ++j) s_opA[(sc * KP + i) * KP + j] = r[j];
+        s_exA[sc * KP + i] = rex;
       }
       __syncthreads();
-      // ---- exclusive prefixes inside the quarter: thread (c, i) multiplies row i of the identity through chunks 0..c-1;
-      // thread (7, i) goes one further: the quarter's total, published for the other CTAs of the tile
-      if (c < QC) {
-        double r[KP];
-        int rex = 0;
+      // ---- inclusive scan over the 32 sub-chunk operators (Hillis-Steele, ping-pong between two buffers): after level d
+      // entry sc holds op[max(0, sc - 2d + 1)] x ... x op[sc]
+      double* src = s_opA;
+      double* dst = s_opB;
+      int* srcx = s_exA;
+      int* dstx = s_exB;
+#pragma unroll 1
+      for (int d = 1; d < NS; d <<= 1) {
+        if (sc < NS) {
+          double r[KP];
+          int rex;
+          if (sc >= d) {
 #pragma unroll
-        for (int j = 0; j < KP; ++j) r[j] = (j == i) ? 1.0 : 0.0;
-        for (int k = 0; k < c; ++k) row_times_op<KP, false>(r, rex, s_ops + k * KP * KP, s_exp + k * KP);
+            for (int j = 0; j < KP; ++j) r[j] = src[((sc - d) * KP + i) * KP + j];
+            rex = srcx[(sc - d) * KP + i];
+            row_times_op<KP, false>(r, rex, src + sc * KP * KP, srcx + sc * KP);
+          } else {
 #pragma unroll
-        for (int j = 0; j < KP; ++j) s_pre[(c * KP + i) * KP + j] = r[j];
-        s_pex[c * KP + i] = rex;
-        if (c == QC - 1) {
-          row_times_op<KP, false>(r, rex, s_ops + c * KP * KP, s_exp + c * KP);
-          double* dst = args.qtot + (size_t)Q * OPW;
+            for (int j = 0; j < KP; ++j) r[j] = src[(sc * KP + i) * KP + j];
+            rex = srcx[sc * KP + i];
+          }
 #pragma unroll
-          for (int j = 0; j < KP; ++j) dst[i * KP + j] = r[j];
-          dst[KP * KP + i] = (double)rex;
+          for (int j = 0; j < KP; ++j) dst[(sc * KP + i) * KP + j] = r[j];
+          dstx[sc * KP + i] = rex;
         }
+        __syncthreads();
+        double* t1 = src; src = dst; dst = t1;
+        int* t2 = srcx; srcx = dstx; dstx = t2;
+      }
+      // src: inclusive products.  The quarter's total goes to the other CTAs of the tile.
+      if (sc == NS - 1) {
+        double* out = args.qtot + (size_t)Q * OPW;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) out[i * KP + j] = src[((NS - 1) * KP + i) * KP + j];
+        out[KP * KP + i] = (double)srcx[(NS - 1) * KP + i];
       }
       {
         const uint32_t round = (Q - cta) / G;
@@ -455,82 +486,70 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
         spin_barrier(gctr + 1 + tile, target);  // the four quarters of the tile
         if (tid == 0) s_tuse[round] += 1u;
       }
-      // ---- product of the quarters in front of this one (row i by thread i), then prefix in the tile = base x prefix in
-      // the quarter; the last quarter also forms the tile operator
+      // ---- product of the quarters in front of this one (row i by thread i); the last quarter also forms the tile operator
       if (tid < KP) {
         double r[KP];
         int rex = 0;
 #pragma unroll
         for (int j = 0; j < KP; ++j) r[j] = (j == tid) ? 1.0 : 0.0;
-        if constexpr (KP <= 5) {
-          double M3[3][KP * KP];  // the totals of the (up to three) quarters in front: all loads in flight together
-          int X3[3][KP];
+        for (int k = 0; k <= qi; ++k) {
+          if (k == qi && qi != 3) break;
+          double M[KP * KP];
+          int X[KP];
+          const double* qsrc = args.qtot + (size_t)(tile * 4 + k) * OPW;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            if (k < qi) {
-              const double* src = args.qtot + (size_t)(tile * 4 + k) * OPW;
+          for (int w = 0; w < KP * KP; ++w) M[w] = __ldcg(qsrc + w);
 #pragma unroll
-              for (int w = 0; w < KP * KP; ++w) M3[k][w] = __ldcg(src + w);
+          for (int w = 0; w < KP; ++w) X[w] = (int)__ldcg(qsrc + KP * KP + w);
+          if (k == qi) {  // qi == 3: tile operator = base x own total
+            double r2[KP];
+            int rex2 = rex;
 #pragma unroll
-              for (int w = 0; w < KP; ++w) X3[k][w] = (int)__ldcg(src + KP * KP + w);
-            }
-          }
+            for (int j = 0; j < KP; ++j) r2[j] = r[j];
+            row_times_op<KP, false>(r2, rex2, M, X);
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (k < qi) row_times_op<KP, false>(r, rex, M3[k], X3[k]);
-        } else {  // (192 registers for three 8 x 8 operators: one at a time)
-          for (int k = 0; k < qi; ++k) {
-            double M[KP * KP];
-            int X[KP];
-            const double* src = args.qtot + (size_t)(tile * 4 + k) * OPW;
-#pragma unroll
-            for (int w = 0; w < KP * KP; ++w) M[w] = __ldcg(src + w);
-#pragma unroll
-            for (int w = 0; w < KP; ++w) X[w] = (int)__ldcg(src + KP * KP + w);
+            for (int j = 0; j < KP; ++j) buf.tile_ops[((uint64_t)tile * KP + tid) * KP + j] = r2[j];
+            buf.tile_exp[(uint64_t)tile * KP + tid] = rex2;
+          } else {
             row_times_op<KP, false>(r, rex, M, X);
           }
         }
 #pragma unroll
         for (int j = 0; j < KP; ++j) s_base[tid * KP + j] = r[j];
         s_bex[tid] = rex;
-        if (qi == 3) {  // tile operator = base x own total
-          double M[KP * KP];
-          int X[KP];
-          const double* src = args.qtot + (size_t)Q * OPW;
-#pragma unroll
-          for (int w = 0; w < KP * KP; ++w) M[w] = __ldcg(src + w);
-#pragma unroll
-          for (int w = 0; w < KP; ++w) X[w] = (int)__ldcg(src + KP * KP + w);
-          row_times_op<KP, false>(r, rex, M, X);
-#pragma unroll
-          for (int j = 0; j < KP; ++j) buf.tile_ops[((uint64_t)tile * KP + tid) * KP + j] = r[j];
-          buf.tile_exp[(uint64_t)tile * KP + tid] = rex;
-        }
       }
       __syncthreads();
-      if (c < QC) {
+      // ---- prefix of sub-chunk sc inside the tile = base x (inclusive product up to sc - 1); into the free buffer
+      if (sc < NS) {
         double r[KP];
         int rex = s_bex[i];
 #pragma unroll
         for (int j = 0; j < KP; ++j) r[j] = s_base[i * KP + j];
-        row_times_op<KP, false>(r, rex, s_pre + c * KP * KP, s_pex + c * KP);
-        const uint64_t ch_idx = (uint64_t)tile * C + c0 + c;
+        if (sc > 0) row_times_op<KP, false>(r, rex, src + (sc - 1) * KP * KP, srcx + (sc - 1) * KP);
 #pragma unroll
-        for (int j = 0; j < KP; ++j) buf.chunk_ops[(ch_idx * KP + i) * KP + j] = r[j];
-        buf.chunk_exp[ch_idx * KP + i] = rex;
+        for (int j = 0; j < KP; ++j) dst[(sc * KP + i) * KP + j] = r[j];
+        dstx[sc * KP + i] = rex;
+        if (!resident) {
+          double* g = args.subops + ((size_t)Q * NS + sc) * OPW;
+#pragma unroll
+          for (int j = 0; j < KP; ++j) g[i * KP + j] = r[j];
+          g[KP * KP + i] = (double)rex;
+        }
       }
       __syncthreads();
+      s_pfx = dst;  // (uniform across the CTA: the scan makes the same number of swaps everywhere)
+      s_pfxx = dstx;
     }
     HML_STAMP(5);
     spin_barrier(gctr, ++ggen * G);  // (3) tile operators
     HML_STAMP(6);
 
-    // ================ phase II, per quarter: forward rows, backward maps, chunk and quarter maps, tile map
-    const bool resident = nq <= G;  // one quarter per CTA: its emission terms, block sizes and sums are still in shared memory
+    // ================ phase II, per quarter: forward rows, backward maps, sub-chunk and quarter maps, tile map
     unsigned fallbacks = 0;
     for (uint32_t Q = cta; Q < nq; Q += G) {
       const uint32_t tile = Q >> 2;
       const int qi = (int)(Q & 3u), c0 = qi * QC;
+      const uint64_t qfirst = (uint64_t)Q * 256;
       if (warp == 0) {
         // every CTA walks the tile operators in front of its tile itself (at most 63 vector-operator products)
         double a[KP];
@@ -541,29 +560,51 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
           load_op_cg<KP>(o, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
           if (!vec_apply_op<KP>(a, o)) fallbacks++;
         }
-        // ---- rows: lane c < 8 owns chunk c0 + c (as k_fwd_replay_prefix, power-of-two rescaling instead of the division)
-        const int cq = lane & 7, c = c0 + cq;
-        const uint64_t first = (uint64_t)tile * TB + (uint64_t)c * L;
+        // ---- rows: lane = sub-chunk; vector entering it = normalise(vector entering the tile x its prefix), then the
+        // recursion over its 8 blocks with a power-of-two rescaling after every fourth (the backward pass normalises its
+        // weights itself; four steps cannot move the largest entry by more than min(A)^4 unless the product dies)
+        const int sc = lane;
+        const uint64_t first = qfirst + (uint64_t)sc * SL;
         int steps = 0;
-        if (lane < QC && first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
-        if (c > 0 && steps > 0) {
+        if (first < B) steps = (B - first) < (uint64_t)SL ? (int)(B - first) : SL;
+        if ((qi > 0 || sc > 0) && steps > 0) {
           OpVals<KP> o;
-          load_op<KP>(o, buf.chunk_ops + ((uint64_t)tile * C + c) * KP * KP, buf.chunk_exp + ((uint64_t)tile * C + c) * KP);
+          if (resident) {
+#pragma unroll
+            for (int w = 0; w < KP * KP; ++w) o.m[w] = s_pfx[sc * KP * KP + w];
+#pragma unroll
+            for (int w = 0; w < KP; ++w) o.x[w] = s_pfxx[sc * KP + w];
+          } else {
+            const double* g = args.subops + ((size_t)Q * NS + sc) * OPW;
+#pragma unroll
+            for (int w = 0; w < KP * KP; ++w) o.m[w] = g[w];
+#pragma unroll
+            for (int w = 0; w < KP; ++w) o.x[w] = (int)g[KP * KP + w];
+          }
           if (!vec_apply_op<KP>(a, o)) fallbacks++;
         }
-        const double* ep = buf.e + Layout::at(tile, c, 0) * KP;
-#pragma unroll 1
-        for (int t0 = 0; t0 < steps; t0 += 4) {
+        const int cq = sc >> 2, t0 = (sc & 3) * SL;
+        double* const row = s_alpha + cq * PE + t0 * KP;  // also where the emission terms of these blocks are (resident)
+        const double* ep = buf.e + Layout::at(tile, c0 + cq, t0) * KP;
+#pragma unroll
+        for (int h4 = 0; h4 < SL; h4 += 4) {
           double ev[4][KP];
+          if (resident) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 4; ++q) {
 #pragma unroll
-            for (int j = 0; j < KP; ++j)
-              ev[q][j] = (t0 + q < steps) ? (resident ? s_e[cq * PE + (t0 + q) * KP + j] : ep[(uint64_t)(t0 + q) * C * KP + j]) : 0.0;
+              for (int j = 0; j < KP; ++j) ev[q][j] = row[(h4 + q) * KP + j];
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+#pragma unroll
+              for (int j = 0; j < KP; ++j) ev[q][j] = (h4 + q < steps) ? ep[(uint64_t)(h4 + q) * C * KP + j] : 0.0;
+            }
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (t0 + q < steps) {
+            if (h4 + q < steps) {
               double f[KP];
 #pragma unroll
               for (int j = 0; j < KP; ++j) f[j] = 0.0;
@@ -572,25 +613,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
 #pragma unroll
                 for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
               }
-              double mxv = 0.0;
 #pragma unroll
               for (int j = 0; j < KP; ++j) {
-                f[j] *= ev[q][j];
-                mxv = fmax(mxv, f[j]);
+                a[j] = f[j] * ev[q][j];
+                row[(h4 + q) * KP + j] = a[j];
               }
-              if (mxv > 0.0) {
-                int e2 = exponent_of(mxv);
-                if (e2 < -1000) e2 = -1000;
-                const double sc = pow2i(-e2);
+            }
+          }
+          if (h4 < steps) {
+            double mxv = 0.0;
 #pragma unroll
-                for (int j = 0; j < KP; ++j) a[j] = f[j] * sc;
-              } else {  // FB.hpp:106-111: the uniform fallback is not an operator product; the host re-runs the sweep
-                fallbacks++;
+            for (int j = 0; j < KP; ++j) mxv = fmax(mxv, a[j]);
+            if (mxv > 1e-250) {
+              const double scl = pow2i(-exponent_of(mxv));
 #pragma unroll
-                for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;
-              }
-#pragma unroll
-              for (int j = 0; j < KP; ++j) s_alpha[cq * PE + (t0 + q) * KP + j] = a[j];
+              for (int j = 0; j < KP; ++j) a[j] *= scl;
+            } else {  // a vanished (or nearly vanished) forward sum, FB.hpp:106-111: the host re-runs the sweep
+              fallbacks++;
             }
           }
         }
@@ -598,7 +637,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
       __syncthreads();
       HML_STAMP(13);
       {  // ---- backward map of this thread's block (as k_bwd_maps)
-        const uint64_t b = (uint64_t)Q * 256 + tid;
+        const uint64_t b = qfirst + tid;
         const uint64_t p = Layout::perm(b);
         Map<KP> fm = Map<KP>::identity();
         if (b < B) {
@@ -643,27 +682,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
       __syncthreads();
       HML_STAMP(14);
       if (warp == 0) {
-        // chunk maps of the quarter's 8 chunks (lanes 0..7), their suffixes inside the quarter, the quarter map
+        // maps of the quarter's 32 sub-chunks, their suffixes inside the quarter, the quarter map
         Map<KP> Gm = Map<KP>::identity();
-        if (lane < QC) {
-#pragma unroll 8
-          for (int t = 0; t < L; ++t) {
-            Map<KP> f;
-            f.w[0] = s_maps[lane * L + t];
-            Gm = Gm.after(f);
-          }
-        }
-        Map<KP> inc = Gm;  // inclusive suffix over lanes lane..7
 #pragma unroll
-        for (int o = 1; o < QC; o <<= 1) {
+        for (int t = 0; t < SL; ++t) {
+          Map<KP> f;
+          f.w[0] = s_maps[lane * SL + t];
+          Gm = Gm.after(f);
+        }
+        Map<KP> inc = Gm;  // inclusive suffix over lanes lane..31
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
           Map<KP> other;
           other.w[0] = __shfl_down_sync(0xffffffffu, inc.w[0], o);
-          if (lane + o < QC) inc = inc.after(other);
+          if (lane + o < 32) inc = inc.after(other);
         }
         Map<KP> excl;
         excl.w[0] = __shfl_down_sync(0xffffffffu, inc.w[0], 1);
-        if (lane == QC - 1) excl = Map<KP>::identity();
-        if (lane < QC) excl.store(buf.chunk_maps + ((uint64_t)tile * C + c0 + lane) * MB);  // later chunks of the QUARTER
+        if (lane == 31) excl = Map<KP>::identity();
+        s_subx[lane] = excl.w[0];  // the later sub-chunks of the quarter
+        if (!resident) args.submaps[(size_t)Q * NS + lane] = excl.w[0];
         if (lane == 0) args.qmap[Q] = inc.w[0];
       }
       HML_STAMP(15);
@@ -710,6 +748,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
     for (uint32_t Q = cta; Q < nq; Q += G) {
       const uint32_t tile = Q >> 2;
       const int qi = (int)(Q & 3u), c0 = qi * QC;
+      const uint64_t qfirst = (uint64_t)Q * 256;
       if (warp == 0) {
         // maps of the later tiles (lane t holds tiles 32 k + t) and of the later quarters of this tile: all loads are in
         // flight together, then the look-ups run from the last tile down
@@ -720,6 +759,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
           tw[k] = (t > tile && t < ntiles) ? __ldcg(reinterpret_cast<const unsigned long long*>(buf.tile_maps + (uint64_t)t * MB)) : 0ull;
         }
         const unsigned long long qw = (lane > (unsigned)qi && lane < 4) ? __ldcg(args.qmap + tile * 4 + lane) : 0ull;
+        const unsigned long long sx0 = resident ? s_subx[lane] : args.submaps[(size_t)Q * NS + lane];
         uint32_t q = 0;  // the last block of the sequence carries a constant map: the start value is irrelevant
         for (uint32_t t = ntiles - 1; t > tile; --t) {
           unsigned long long w = 0;
@@ -734,19 +774,23 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
           q = (uint32_t)(w >> (8 * q)) & 0xffu;
         }
         if (lane == 0) s_misc[2] = q;  // state of the block that follows the quarter
-        // ---- states of the quarter's chunks (as k_bwd_replay): lane c < 8
-        if (lane < QC) {
-          const int c = c0 + lane;
-          const uint64_t first = (uint64_t)tile * TB + (uint64_t)c * L;
-          if (first < B) {
-            const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
-            uint32_t qs = Map<KP>::load(buf.chunk_maps + ((uint64_t)tile * C + c) * MB).get(q);
-            for (int t = steps - 1; t >= 0; --t) {
-              Map<KP> f;
-              f.w[0] = resident ? s_maps[lane * L + t] : *reinterpret_cast<const unsigned long long*>(buf.maps + Layout::at(tile, c, t) * MB);
-              qs = f.get(qs);
-              s_states[lane * L + t] = (uint8_t)qs;
-              buf.states[Layout::at(tile, c, t)] = (uint8_t)qs;
+        // ---- states of the quarter's sub-chunks (as k_bwd_replay): lane = sub-chunk, 8 look-ups
+        const uint64_t first = qfirst + (uint64_t)lane * SL;
+        if (first < B) {
+          const int steps = (B - first) < (uint64_t)SL ? (int)(B - first) : SL;
+          uint32_t qs = (uint32_t)(sx0 >> (8 * q)) & 0xffu;  // state of the block that follows the sub-chunk
+          const int cq = lane >> 2, t0 = (lane & 3) * SL;
+          unsigned long long f8[SL];
+#pragma unroll
+          for (int t = 0; t < SL; ++t)
+            f8[t] = resident ? s_maps[lane * SL + t]
+                             : *reinterpret_cast<const unsigned long long*>(buf.maps + Layout::at(tile, c0 + cq, t0 + t) * MB);
+#pragma unroll
+          for (int t = SL - 1; t >= 0; --t) {
+            if (t < steps) {
+              qs = (uint32_t)(f8[t] >> (8 * qs)) & 0xffu;
+              s_states[lane * SL + t] = (uint8_t)qs;
+              buf.states[Layout::at(tile, c0 + cq, t0 + t)] = (uint8_t)qs;
             }
           }
         }
@@ -754,7 +798,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
       __syncthreads();
       const uint32_t qafter = s_misc[2];
       {  // statistics of this thread's block (as k_reduce_partial; the successor of the quarter's last block is qafter)
-        const uint64_t b = (uint64_t)Q * 256 + tid;
+        const uint64_t b = qfirst + tid;
         if (b < B) {
           const uint64_t p = Layout::perm(b);
           const uint32_t st = s_states[tid];
@@ -851,19 +895,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
 #undef HML_STAMP
 }
 
+template <int KP>
+constexpr size_t fused_dyn_smem() { return (size_t)2 * 32 * KP * KP * sizeof(double); }
+
 // one cooperative launch of `a.nsweeps` sweeps; returns the cudaError_t of the launch
 template <int KP>
 int fused_impl(const SweepBuffers& b, const FusedArgs& a, int grid, cudaStream_t s) {
   SweepBuffers bb = b;
   FusedArgs aa = a;
   void* params[] = {(void*)&bb, (void*)&aa};
-  return (int)cudaLaunchCooperativeKernel((const void*)k_sweep_fused<KP>, dim3(grid), dim3(kFusedThreads), params, 0, s);
+  cudaFuncSetAttribute(k_sweep_fused<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn_smem<KP>());
+  return (int)cudaLaunchCooperativeKernel((const void*)k_sweep_fused<KP>, dim3(grid), dim3(kFusedThreads), params,
+                                          fused_dyn_smem<KP>(), s);
 }
 // CTAs of k_sweep_fused<KP> that can be resident at once on the current device (0: the kernel does not fit)
 template <int KP>
 int fused_max_grid_impl(int sms) {
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fused<KP>, kFusedThreads, 0) != cudaSuccess) return 0;
+  cudaFuncSetAttribute(k_sweep_fused<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_dyn_smem<KP>());
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_fused<KP>, kFusedThreads, fused_dyn_smem<KP>()) != cudaSuccess)
+    return 0;
   return per_sm > 0 ? sms : 0;  // one CTA per SM is all the kernel asks for
 }
 template <int KP>

@@ -189,6 +189,8 @@ struct FusedArgs {
   unsigned* barriers;   // 1 + kFusedMaxTiles words, zero at launch: grid barrier, then one barrier per tile
   double* qtot;         // 4 * kFusedMaxTiles operators of K*K + K doubles: the quarter-tile totals
   unsigned long long* qmap;  // 4 * kFusedMaxTiles words: the quarter-tile maps
+  double* subops;       // per quarter 32 sub-chunk prefix operators (K*K + K doubles): CTAs with several quarters per phase
+  unsigned long long* submaps;  // per quarter 32 sub-chunk suffix maps: the same
   unsigned long long* phase_ns;  // 16 words or null: globaltimer stamps of CTA 0 at the phase borders of the last sweep
   int nsweeps;
   int sample_params;    // 0: the model stays as it is (single sweeps with a caller-provided model)

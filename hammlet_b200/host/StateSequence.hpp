@@ -152,6 +152,9 @@ class StateSequence {
   StateSequence(rng_t& RNG) : mRNG(RNG) {}
 
   void setReplay(bool on) { mReplay = on; }
+  rng_t& rng() { return mRNG; }
+  // forward-backward sampling with Philox uniforms may run whole on the device (sampleHMMOnDevice)
+  bool deviceChainAllowed() const { return !kIsMixture && !mReplay && !mKeepTrellis; }
   void setKeepTrellis(bool on) { mKeepTrellis = on; }
   const Trellis& trellis() const { return mTrellis; }
   double logLikelihood() const { return mLogLikelihood; }
@@ -283,6 +286,91 @@ void StateSequence<Type>::sample(Emissions<Statistics<StatsStructure, StatsType>
   }
 }
 
+// sampleHMM on the device-resident chain (include/hammlet_b200.h: hml_chain_*): the conjugate updates and the draws of
+// theta, pi and A happen on the device after every sweep (Philox streams keyed by one 64-bit draw from the shared
+// mt19937), a run of sweeps between two recorded iterations is ONE launch of the persistent sweep kernel, and nothing
+// crosses PCIe in between.  Forward-backward sampling with dynamic blocks on a single univariate sequence of at most 8
+// states whose block structure fits the persistent kernel (64 tiles); recorded iterations need nothing on the host but
+// the marginals (and the compression / parameters files).  Returns false — nothing done — where that does not apply:
+// -replay, mixture sampling, static blocks, multivariate data, a split sequence, per-iteration sequence / block output.
+// HAMMLET_HOST_PARAMS=1 in the environment keeps the host-side parameter draws.
+template <typename EmissionsType, typename ThetaType, typename ThetaParamType, typename TransitionType,
+          typename TransitionParamType, typename InitialType, typename InitialParamType>
+bool sampleHMMOnDevice(EmissionsType& y, rng_t& rng, ThetaType& theta, ThetaParamType& tau_theta, TransitionType& A,
+                       TransitionParamType& tau_A, InitialType& pi, InitialParamType& tau_pi, const Mapping& mapping,
+                       const size_t iterations, const size_t thinning, Records& records, const bool useSelfTransitions) {
+  auto& blocks = y.blocks();
+  DeviceSequence& seq = blocks.sequence();
+  const size_t K = A.nrStates();
+  if (std::getenv("HAMMLET_HOST_PARAMS") || iterations == 0 || seq.split() || seq.nrDim() != 1 || mapping.nrDataDims() != 1 ||
+      tau_theta.nrParams() != K || K < 2 || K > 8)
+    return false;
+  const bool recording = thinning > 0 && thinning <= iterations;
+  if (recording && !records.canRecordOnDevice()) return false;
+  // one prior for all states, one off-diagonal and one diagonal transition prior, one initial prior (what main.cpp builds)
+  const auto& p0 = tau_theta.prior(0);
+  for (size_t s = 0; s < K; ++s) {
+    const auto& ps = tau_theta.prior(s);
+    if (ps.alpha() != p0.alpha() || ps.beta() != p0.beta() || ps.mu0() != p0.mu0() || ps.nu() != p0.nu()) return false;
+    if (tau_pi.prior()[s] != tau_pi.prior()[0]) return false;
+    for (size_t j = 0; j < K; ++j)
+      if (tau_A.prior()[s][j] != (s == j ? tau_A.prior()[0][0] : tau_A.prior()[0][1])) return false;
+  }
+  // does the block structure of the current parameters fit the persistent kernel?  (one detection pass; a chain whose
+  // structure outgrows it later still runs: those sweeps take the multi-kernel path, parameter phase on the device)
+  y.createBlocks(theta);
+  if (blocks.materialize() > (size_t)60000) return false;
+  const float prior[4] = {(float)p0.alpha(), (float)p0.beta(), (float)p0.mu0(), (float)p0.nu()};
+  const uint64_t seed = ((uint64_t)rng() << 32) | (uint64_t)rng();
+  seq.check(hml_chain_init(seq.handle(), (int)K, prior, (float)tau_A.prior()[0][1], (float)tau_A.prior()[0][0],
+                           (float)tau_pi.prior()[0], seed, useSelfTransitions ? 1 : 0));
+  std::vector<double> mean(K), var(K), a(K * K), p(K);
+  const std::vector<real_t> pv = pi.valueVector();
+  for (size_t s = 0; s < K; ++s) {
+    mean[s] = theta.value()[s].mean();
+    var[s] = theta.value()[s].var();
+    p[s] = pv[s];
+    for (size_t j = 0; j < K; ++j) a[s * K + j] = A(s, j);
+  }
+  seq.check(hml_chain_set(seq.handle(), mean.data(), var.data(), a.data(), p.data()));
+  auto pull = [&]() {  // theta, pi, A as they stand on the device
+    seq.check(hml_chain_get(seq.handle(), mean.data(), var.data(), a.data(), p.data(), nullptr, nullptr));
+    for (size_t s = 0; s < K; ++s) {
+      theta.param(s).setValue((real_t)mean[s], (real_t)var[s]);
+      pi.values()[s] = (real_t)p[s];
+      for (size_t j = 0; j < K; ++j) A(s, j) = (real_t)a[s * K + j];
+    }
+  };
+  if (thinning > iterations)
+    std::cout << "[WARNING] Thinning parameter is larger than number of iterations. No data will be recorded!" << std::endl;
+  size_t done = 0;
+  std::vector<double> statSum(K), statSq(K);
+  std::vector<uint64_t> statN(K), trans(K * K), counts(K);
+  while (done < iterations) {
+    const size_t batch = recording ? std::min(thinning, iterations - done) : iterations - done;
+    hml_sweep_out last{};
+    last.stat_sum = statSum.data();
+    last.stat_sumsq = statSq.data();
+    last.stat_n = statN.data();
+    last.trans = trans.data();
+    last.counts = counts.data();
+    seq.check(hml_chain_run(seq.handle(), batch, nullptr, &last));
+    done += batch;
+    seq.lastSweep.nblocks = last.nblocks;
+    seq.lastSweep.counts = counts;
+    seq.lastSweep.trans = trans;
+    seq.lastSweep.statN = statN;
+    if (recording && done % thinning == 0) {  // HMM.hpp:104-119
+      records.recordIterationOnDevice(last.nblocks);
+      pull();
+      records.record(theta);
+    }
+  }
+  pull();
+  blocks.createBlocks(theta);  // the host's view: threshold of the final parameters, structure to be rebuilt on use
+  return true;
+}
+
 // The Gibbs driver, reference: HMM.hpp:60-125.
 template <typename StateSequenceType, typename EmissionsType, typename ThetaType, typename ThetaParamType,
           typename TransitionType, typename TransitionParamType, typename InitialType, typename InitialParamType>
@@ -290,6 +378,10 @@ void sampleHMM(EmissionsType& y, StateSequenceType& q, ThetaType& theta, ThetaPa
                TransitionParamType& tau_A, InitialType& pi, InitialParamType& tau_pi, const Mapping& mapping,
                const size_t iterations, const size_t thinning, Records& records, const bool dynamic = true,
                const bool useSelfTransitions = true) {
+  if (dynamic && q.deviceChainAllowed() &&
+      sampleHMMOnDevice(y, q.rng(), theta, tau_theta, A, tau_A, pi, tau_pi, mapping, iterations, thinning, records,
+                        useSelfTransitions))
+    return;
   if (thinning > iterations)
     std::cout << "[WARNING] Thinning parameter is larger than number of iterations. No data will be recorded!" << std::endl;
   for (size_t i = 0; i < iterations; ++i) {
