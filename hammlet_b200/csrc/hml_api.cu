@@ -1112,6 +1112,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
       c->use_self = mh.use_self;
       c->T = (uint32_t)h->T;
       c->thr = t_use;
+      chain_derive(c);
       h->last_thr = t_use;
       h->states_valid = h->segs_valid = h->g_valid = h->rows_valid = false;
       h->blocks_valid = false;
@@ -1769,6 +1770,7 @@ int hml_chain_set(hml_t* h, const double* mean, const double* var, const double*
   float mv = (float)c->var[0];
   for (int s = 1; s < K; ++s) mv = fminf(mv, (float)c->var[s]);
   c->thr = sqrtf(2.0f * logf((float)c->T) * mv);
+  chain_derive(c);
   CK(cudaMemcpyAsync(h->chain_dev, c, sizeof(ChainDev), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return HML_OK;

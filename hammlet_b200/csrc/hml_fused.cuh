@@ -33,34 +33,48 @@ struct DrawStream {
   unsigned long long seed, sweep;
   uint32_t stream;
   unsigned long long ctr;
-  __device__ __forceinline__ double uniform() { return Philox::uniform(seed, sweep, stream, ctr++); }
-  // The draws are real_t = float in the reference (std::gamma_distribution<float>, std::normal_distribution<float>);
-  // here the transcendental functions are float too (a tenth of the instructions of their double versions: the
-  // parameter phase is one warp on the critical path of every sweep), the accumulation of d * v stays double.
-  __device__ __forceinline__ float normal() {  // Box-Muller, one value per two uniforms
-    const float u1 = (float)(1.0 - uniform());
-    const float u2 = (float)uniform();
-    return sqrtf(-2.0f * logf(fmaxf(u1, 1e-38f))) * cospif(2.0f * u2);
+  // four uniforms in (0, 1] from one Philox call (24 bits each: the draws are real_t = float in the reference,
+  // std::gamma_distribution<float> / std::normal_distribution<float>)
+  __device__ __forceinline__ void next4(float (&u)[4]) {
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)sweep, (uint32_t)(sweep >> 32) ^ (stream << 24)};
+    ++ctr;
+    Philox::run(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = (float)((c[k] >> 8) + 1u) * (1.0f / 16777216.0f);
   }
-  // Gamma(alpha, 1): Marsaglia & Tsang 2000 (the method libstdc++'s gamma_distribution uses), boosted for alpha < 1
+  // The transcendental functions are float (a tenth of the instructions of their double versions: the parameter phase is
+  // one warp on the critical path of every sweep); the value d * v is formed in double.
+  __device__ __forceinline__ float normal_from(float u1, float u2) {  // Box-Muller
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  }
+  __device__ __forceinline__ float normal() {
+    float u[4];
+    next4(u);
+    return normal_from(u[0], u[1]);
+  }
+  // Gamma(alpha, 1): Marsaglia & Tsang 2000 (the method libstdc++'s gamma_distribution uses) with its squeeze test,
+  // boosted for alpha < 1; one Philox call per trial
   __device__ double gamma(double alpha) {
     const double a = alpha < 1.0 ? alpha + 1.0 : alpha;
     const double d = a - 1.0 / 3.0;
     const float c = rsqrtf((float)(9.0 * d));
     double g = 0.0;
+    float u[4] = {1.f, 1.f, 1.f, 1.f};
     for (int tries = 0; tries < 1000; ++tries) {
-      const float x = normal();
+      next4(u);
+      const float x = normal_from(u[0], u[1]);
       const float v1 = 1.0f + c * x;
       if (v1 <= 0.0f) continue;
       const double v = (double)v1 * (double)v1 * (double)v1;
-      const float u = fmaxf((float)(1.0 - uniform()), 1e-38f);
+      const float x2 = x * x;
       // log u < x^2 / 2 + d (1 - v + log v): for large d the bracket is a small difference, taken in double
-      if ((double)logf(u) < 0.5 * (double)x * (double)x + d * (1.0 - v + (double)log1pf((float)(v - 1.0)))) {
+      if (u[2] < 1.0f - 0.0331f * x2 * x2 ||
+          (double)logf(u[2]) < 0.5 * (double)x2 + d * (1.0 - v + (double)log1pf((float)(v - 1.0)))) {
         g = d * v;
         break;
       }
     }
-    if (alpha < 1.0) g *= (double)powf(fmaxf((float)(1.0 - uniform()), 1e-38f), (float)(1.0 / alpha));
+    if (alpha < 1.0) g *= (double)powf(u[3], (float)(1.0 / alpha));
     return g;
   }
 };
@@ -97,6 +111,9 @@ __device__ void chain_sample_params(ChainDev* ch, const unsigned long long* out_
     if (!(var > 0.0f) || !isfinite(var) || !isfinite(mean)) ch->phase_abort[6] = kChainNumeric;  // Observation.hpp:177-179
     ch->mean[tid] = (double)mean;
     ch->var[tid] = (double)var;
+    // what the kernels use of theta_k, once per sweep instead of once per CTA (make_model)
+    ch->inv2var[tid] = 1.0 / (2.0 * (double)var);
+    ch->lognorm[tid] = log(sqrt((double)var)) + (double)mean * (double)mean / (2.0 * (double)var);
     s_var[tid] = var;
   }
   if (tid >= 32 && tid < 32 + K) {  // ---- pi ~ Dirichlet(alpha_I + occupancy) (FB.hpp:211: the quirk of A11)
@@ -115,6 +132,7 @@ __device__ void chain_sample_params(ChainDev* ch, const unsigned long long* out_
     float s = 0.f;
     for (int j = 0; j < K; ++j) s += g_A[tid * KP + j];
     for (int j = 0; j < K; ++j) ch->A[tid * K + j] = (double)(g_A[tid * KP + j] / s);
+    ch->loga[tid] = ch->use_self ? log((double)(g_A[tid * KP + tid] / s)) : 0.0;  // FB.hpp:47-50
   }
   if (tid == 32) {
     float s = 0.f;
@@ -153,7 +171,7 @@ __device__ __forceinline__ Map<KP> load_map_cg(const uint8_t* p) {
   return r;
 }
 
-// thread i < KP fills row i of the model (mirrors make_model)
+// thread i < KP fills row i of the model from the chain (the derived values come with it, chain_derive)
 template <int KP>
 __device__ __forceinline__ void model_from_chain(const ChainDev* ch, ModelDev<KP>& m, int i) {
   const int K = ch->K;
@@ -162,11 +180,10 @@ __device__ __forceinline__ void model_from_chain(const ChainDev* ch, ModelDev<KP
     m.use_self = ch->use_self;
   }
   const bool on = i < K;
-  const double mu = on ? __ldcg(&ch->mean[i]) : 0.0, var = on ? __ldcg(&ch->var[i]) : 1.0;
-  m.mean[i] = mu;
-  m.inv2var[i] = on ? 1.0 / (2.0 * var) : 0.0;
-  m.lognorm[i] = on ? log(sqrt(var)) + mu * mu / (2 * var) : 0.0;
-  m.loga[i] = (on && ch->use_self) ? log(__ldcg(&ch->A[i * K + i])) : 0.0;
+  m.mean[i] = on ? __ldcg(&ch->mean[i]) : 0.0;
+  m.inv2var[i] = on ? __ldcg(&ch->inv2var[i]) : 0.0;
+  m.lognorm[i] = on ? __ldcg(&ch->lognorm[i]) : 0.0;
+  m.loga[i] = on ? __ldcg(&ch->loga[i]) : 0.0;
   m.pi[i] = on ? __ldcg(&ch->pi[i]) : 0.0;
   for (int j = 0; j < KP; ++j) m.A[i][j] = (on && j < K) ? __ldcg(&ch->A[i * K + j]) : 0.0;
 }
@@ -220,6 +237,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
   extern __shared__ __align__(16) double s_fdyn[];  // two operator buffers of the quarter's 32 sub-chunks (scan ping-pong)
   double* const s_opA = s_fdyn;
   double* const s_opB = s_fdyn + NS * KP * KP;
+  double* const s_top = s_fdyn + 2 * NS * KP * KP;  // the tile operators in front of this CTA's tile (tree product)
+  __shared__ int s_tex[kFusedMaxTiles * KP];
   __shared__ int s_exA[NS * KP], s_exB[NS * KP];
   double* s_pfx = s_opA;                  // where the prefixes of the sub-chunks inside the tile ended up
   int* s_pfxx = s_exA;
@@ -550,15 +569,47 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
       const uint32_t tile = Q >> 2;
       const int qi = (int)(Q & 3u), c0 = qi * QC;
       const uint64_t qfirst = (uint64_t)Q * 256;
+      // The vector entering the tile = normalise(pi x T_0 x ... x T_{tile-1}).  Every CTA forms it itself: a few tiles by
+      // walking them (0.5 us each: one L2 round trip and one vector-operator product after the other), more by a tree
+      // over the operators in shared memory, the whole CTA working (log2(tile) levels of operator products, ~0.45 us
+      // each) — the walk made the CTAs of the last tiles arrive at the next barrier 9 us late at 18 tiles.
+      const bool tree = tile > 4;
+      if (tree) {
+        for (uint32_t w = tid; w < tile * KP * KP; w += kFusedThreads) s_top[w] = __ldcg(buf.tile_ops + w);
+        for (uint32_t w = tid; w < tile * KP; w += kFusedThreads) s_tex[w] = __ldcg(buf.tile_exp + w);
+        __syncthreads();
+        const int row = tid % KP;
+        for (uint32_t d = 1; d < tile; d <<= 1) {
+          for (uint32_t pr = tid / KP; pr < (uint32_t)(kFusedThreads / KP); pr += kFusedThreads / KP) {
+            for (uint32_t left = 2 * d * pr; left + d < tile; left += 2 * d * (kFusedThreads / KP)) {
+              // row `row` of T_left <- (row of T_left) x T_{left + d}: in place, nobody else touches this row
+              double r[KP];
+              int rex = s_tex[left * KP + row];
+#pragma unroll
+              for (int j = 0; j < KP; ++j) r[j] = s_top[(left * KP + row) * KP + j];
+              row_times_op<KP, false>(r, rex, s_top + (left + d) * KP * KP, s_tex + (left + d) * KP);
+#pragma unroll
+              for (int j = 0; j < KP; ++j) s_top[(left * KP + row) * KP + j] = r[j];
+              s_tex[left * KP + row] = rex;
+            }
+          }
+          __syncthreads();
+        }
+      }
       if (warp == 0) {
-        // every CTA walks the tile operators in front of its tile itself (at most 63 vector-operator products)
         double a[KP];
 #pragma unroll
         for (int j = 0; j < KP; ++j) a[j] = m.pi[j];
-        for (uint32_t t = 0; t < tile; ++t) {
+        if (tree) {
           OpVals<KP> o;
-          load_op_cg<KP>(o, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
+          load_op<KP>(o, s_top, s_tex);
           if (!vec_apply_op<KP>(a, o)) fallbacks++;
+        } else {
+          for (uint32_t t = 0; t < tile; ++t) {
+            OpVals<KP> o;
+            load_op_cg<KP>(o, buf.tile_ops + (uint64_t)t * KP * KP, buf.tile_exp + (uint64_t)t * KP);
+            if (!vec_apply_op<KP>(a, o)) fallbacks++;
+          }
         }
         // ---- rows: lane = sub-chunk; vector entering it = normalise(vector entering the tile x its prefix), then the
         // recursion over its 8 blocks with a power-of-two rescaling after every fourth (the backward pass normalises its
@@ -896,7 +947,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
 }
 
 template <int KP>
-constexpr size_t fused_dyn_smem() { return (size_t)2 * 32 * KP * KP * sizeof(double); }
+constexpr size_t fused_dyn_smem() { return (size_t)(2 * 32 + kFusedMaxTiles) * KP * KP * sizeof(double); }
 
 // one cooperative launch of `a.nsweeps` sweeps; returns the cudaError_t of the launch
 template <int KP>

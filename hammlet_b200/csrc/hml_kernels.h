@@ -1,6 +1,7 @@
 // hammlet_b200 — internal kernel launch interface (host side of hammlet_b200/csrc/*.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace hml {
@@ -163,6 +164,8 @@ enum { kChainOk = 0, kChainThreshold = 1, kChainCapacity = 2, kChainFallback = 3
 // Device-resident Gibbs chain (one per handle): parameters, priors, RNG position, status of the last launch.
 struct ChainDev {
   double mean[kChainMaxStates], var[kChainMaxStates], A[kChainMaxStates * kChainMaxStates], pi[kChainMaxStates];
+  // derived from them (make_model): 1 / (2 var), log sd + mean^2 / (2 var), log A_ss (0 without self transitions)
+  double inv2var[kChainMaxStates], lognorm[kChainMaxStates], loga[kChainMaxStates];
   float prior_theta[kChainMaxStates][4];  // NIG hyper-parameters alpha, beta, mu0, nu per state (real_t = float)
   float prior_trans, prior_self, prior_pi;
   float thr;         // threshold of the current parameters, BreakpointArray.hpp:195-199
@@ -198,6 +201,14 @@ struct FusedArgs {
   unsigned long long seed, sweep;
 };
 
+// fills inv2var / lognorm / loga from mean / var / A (host side: hml_chain_set, single fused sweeps)
+inline void chain_derive(ChainDev* c) {
+  for (int i = 0; i < c->K; ++i) {
+    c->inv2var[i] = 1.0 / (2.0 * c->var[i]);
+    c->lognorm[i] = log(sqrt(c->var[i])) + c->mean[i] * c->mean[i] / (2 * c->var[i]);
+    c->loga[i] = c->use_self ? log(c->A[i * c->K + i]) : 0.0;
+  }
+}
 // cooperative launch of a.nsweeps sweeps on `grid` CTAs; cudaError_t as int, or -2 for an unsupported K
 int launch_sweep_fused(int KP, const SweepBuffers& b, const FusedArgs& a, int grid, cudaStream_t s);
 int fused_max_grid(int KP, int sms);

@@ -4,6 +4,7 @@ with libstdc++ <random>) and `hml_chain_run` (parameters on the device; the whol
 the block structure has at most 64 tiles, n sweeps per launch).  One JSON line per configuration.
 usage: python tools/chain_rate.py [c1 c2 c3chr c4over8]"""
 import json
+import os
 import sys
 import time
 
@@ -32,7 +33,8 @@ def main():
         tau = capi.Chain.auto_prior(h, 0.2, 0.9)
         levels = ((np.arange(K) - (K - 1) / 2.0)).astype(np.float64)
         A0 = np.full((K, K), 0.0002 / (K - 1)) + np.eye(K) * (0.9998 - 0.0002 / (K - 1))
-        # ---- host-driven chain
+        # ---- host-driven chain (HAMMLET_HOST_PARAMS keeps sampleHMM off the device-resident chain)
+        os.environ["HAMMLET_HOST_PARAMS"] = "1"
         chain = capi.Chain(h, K, tau, seed=100)
         chain.set(levels.astype(np.float32), np.full(K, 0.09, np.float32), A0.astype(np.float32), np.full(K, 1.0 / K, np.float32))
         chain.run(200)
@@ -43,6 +45,7 @@ def main():
         h.sync()
         host_rate = n / (time.perf_counter() - t0)
         chain.close()
+        del os.environ["HAMMLET_HOST_PARAMS"]
         # ---- device-resident chain
         h.chain_init(K, tau, seed=100)
         h.chain_set(mean=levels, var=np.full(K, 0.09), A=A0, pi=np.full(K, 1.0 / K))
