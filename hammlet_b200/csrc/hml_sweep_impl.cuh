@@ -525,6 +525,16 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
   if constexpr (kNatural) {
     const int cl = threadIdx.x >> 5, t = threadIdx.x & 31;   // chunk within the group, step
     const int oc = threadIdx.x & 7, ot = threadIdx.x >> 3;   // the slot this thread writes out: chunk, step
+    // where the words this thread copies out sit in the staging area and, relative to the group's first slot, in storage
+    // (the grid is a few CTAs per SM and every CTA takes several groups: worked out once)
+    int src_w[KP], dst_w[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int q = k * 256 + threadIdx.x;  // word of the group's emission terms in storage order
+      const int qt = q / (8 * KP), within = q % (8 * KP);
+      src_w[k] = (within / KP) * PE + qt * KP + within % KP;
+      dst_w[k] = qt * Layout::C * KP + within;
+    }
     for (uint64_t g = blockIdx.x; g < slots / 256; g += gridDim.x) {
       const uint64_t b = g * 256 + threadIdx.x;
       const uint64_t tile = g >> 2;
@@ -549,12 +559,9 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
         buf.bN[op] = s_n[oc * PB + ot];
         buf.bS[op] = make_double2(s_sx[oc * PB + ot], s_sq[oc * PB + ot]);
       }
+      double* const eg = buf.e + (tile * Layout::TB + c0) * KP;
 #pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        const int q = k * 256 + threadIdx.x;     // word of the group's emission terms in storage order
-        const int qt = q / (8 * KP), within = q % (8 * KP);
-        buf.e[(Layout::at(tile, c0, qt)) * KP + within] = s_e[(within / KP) * PE + qt * KP + within % KP];
-      }
+      for (int k = 0; k < KP; ++k) eg[dst_w[k]] = s_e[src_w[k]];
       __syncthreads();
     }
   }
@@ -2448,7 +2455,8 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     }
     ++launches;
   } else {
-    const int g = grid_for(ntiles * Layout::TB, 256, l.sms, 32);
+    // K <= 8 with fresh block sums: CTAs take groups of 256 consecutive blocks in a loop, 4 resident CTAs per SM (60 registers)
+    const int g = (l.gather && KP <= 8) ? grid_for(ntiles * Layout::TB, 256, l.sms, 4) : grid_for(ntiles * Layout::TB, 256, l.sms, 32);
     if (l.mixture) {
       if (l.gather)
         launch_k(k_block_emit<KP, true, true, true>, g, 256, 0, s, b, m, (int)0);

@@ -79,6 +79,9 @@ def main():
         (2_500_000, 20, 100, 0.9, 1),
         (3_000_017, 8, 2000, 1.3, 1),
     ]
+    small = bool(os.environ.get("HML_MGPU_SMALL"))   # tools/gpu.sh sanitize_mgpu: the first cases only (memcheck is slow)
+    if small:
+        cases = cases[:4]
     for ci, (T, K, L, thr, use_self) in enumerate(cases):
         x = piecewise_gaussian(T, K, L, seed=100 + ci)
         mu, var, A, pi = model_guess(K, seed=ci)
@@ -151,7 +154,7 @@ def main():
             print(f"case {ci} ok: T={T} K={K} world={world} blocks={Br}", flush=True)
 
     # ---- capacity growth must stay collective: tiny threshold => far more blocks than the initial capacity
-    T = 2_000_000
+    T = 200_000 if small else 2_000_000
     x = piecewise_gaussian(T, 3, 50, seed=3)
     mu, var, A, pi = model_guess(3, seed=3)
     s, n = capi.Handle.segment_plan(T, world, rank)

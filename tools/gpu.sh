@@ -10,6 +10,7 @@
 #   full            ncu --set full of one whole sweep (13 kernels) + raw csv
 #   traffic         regenerates profiles/ncu_traffic.json from the full capture of this run (stamped with the tree's hash)
 #   sanitize        compute-sanitizer memcheck + racecheck over the reduced selection (tools/sanitize_cases.py)
+#   sanitize_mgpu   memcheck over the reduced 2-GPU segment-split worker, both transports (needs --gpus 2)
 #   mgpu:N          multi-GPU parity workers (tests/test_multi_gpu.py) + bench --gpus N on the N GPUs of this box
 #   latency         tools/scan_latency.py (C1, C2, C4/8 stage tables)
 TAG=$1; shift
@@ -43,6 +44,14 @@ for step in "$@"; do
       for tool in memcheck racecheck; do
         timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_cases.py > ${OUT}_sanitizer_$tool.log 2>&1
         echo "$tool exit $?"; tail -4 ${OUT}_sanitizer_$tool.log
+      done ;;
+    sanitize_mgpu)
+      # the reduced segment-split worker under memcheck, both transports (peer mailboxes over NVLink, NCCL all-gathers)
+      for tr in peer nccl; do
+        HML_MGPU_SMALL=1 HML_EXCHANGE=$tr HML_EXPECT_TRANSPORT=$tr timeout 900 compute-sanitizer --tool memcheck --target-processes all \
+          --error-exitcode 9 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
+          tests/mgpu_worker.py > ${OUT}_sanitizer_memcheck_2gpu_$tr.log 2>&1
+        echo "memcheck 2gpu $tr exit $?"; grep -E "ERROR SUMMARY|MGPU WORKER OK" ${OUT}_sanitizer_memcheck_2gpu_$tr.log | tail -4
       done ;;
     mgpu:*)
       N=${step#mgpu:}
