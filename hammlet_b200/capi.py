@@ -54,7 +54,7 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
            "hammlet_chain_save_marginals", "hammlet_chains_run", "hammlet_chain_last_sweep",
            "hml_comm_allgather", "hml_chain_init", "hml_chain_set", "hml_chain_get", "hml_chain_run",
-           "hml_chain_phase_ns"]
+           "hml_chain_phase_ns", "hml_load_segment_f32_md", "hml_load_segment_f32_device_md"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -162,9 +162,13 @@ class Handle:
         return s.value, n.value
 
     def load_segment(self, x_local, T, weight_multiplier=1.0):
+        """x_local: this rank's observations, (len,) or (len, D) for D-dimensional data; T: positions of the whole sequence."""
         x = np.ascontiguousarray(x_local, dtype=np.float32)
-        self._ck(self.lib.hml_load_segment_f32(self.h, _ptr(x), C.c_uint64(x.size), C.c_uint64(T),
-                                               C.c_float(weight_multiplier)))
+        if x.ndim == 2:
+            self._ck(self.lib.hml_load_segment_f32_md(self.h, _ptr(x), C.c_uint64(x.shape[0]), C.c_uint64(T),
+                                                      C.c_uint32(x.shape[1]), C.c_float(weight_multiplier)))
+        else:
+            self._ck(self.lib.hml_load_segment_f32(self.h, _ptr(x), C.c_uint64(x.size), C.c_uint64(T), C.c_float(weight_multiplier)))
         self.T = int(T)
 
     def load_segment_device(self, dev_ptr, n, T, weight_multiplier=1.0):

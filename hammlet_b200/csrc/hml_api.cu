@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <float.h>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges appear when a profiler injects its library, else no-ops
 #include <nccl.h>  // types only: the library is loaded with dlopen in hml_comm_init (single-GPU use needs no NCCL)
 #include <stdio.h>
 #include <stdlib.h>
@@ -180,6 +181,7 @@ struct hml_ctx {
   float last_thr = NAN;                // threshold of the current block structure
 
   // timing
+  bool nvtx_open = false;
   bool timing = false;
   std::vector<Stage> stages;
   size_t stage_used = 0;
@@ -229,8 +231,20 @@ struct DevTmp {
   P* operator+(size_t i) const { return p + i; }
 };
 
+// HML_NVTX=1 in the environment: every stage of a sweep is an NVTX range (nsys / ncu --nvtx show the kernels of a stage
+// under its name); independent of the CUDA-event timing below
+bool nvtx_enabled() {
+  static const bool on = getenv("HML_NVTX") && getenv("HML_NVTX")[0] != '0';
+  return on;
+}
+
 void stage_cb(void* user, const char* name) {
   hml_t* h = (hml_t*)user;
+  if (nvtx_enabled()) {
+    if (h->nvtx_open) nvtxRangePop();
+    h->nvtx_open = strcmp(name, "end") != 0;
+    if (h->nvtx_open) nvtxRangePushA(name);
+  }
   if (!h->timing) return;
   if (h->stage_used == h->event_pool.size()) {
     cudaEvent_t ev;
@@ -349,12 +363,12 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
     b.seg.rank = h->rank;
     b.seg.world = h->world;
     b.seg.send_head = d;
-    b.seg.send_map = (uint64_t*)(d + 4);
-    b.seg.send_op = d + 8;
-    d += 8 + kOpDoubles;
+    b.seg.send_map = (uint64_t*)(d + kHeadWords);
+    b.seg.send_op = d + kHeadWords + 4;
+    d += kHeadWords + 4 + kOpDoubles;
     b.seg.heads = d;
-    b.seg.maps = (const uint64_t*)(d + 4 * (size_t)h->world);
-    b.seg.ops = d + 8 * (size_t)h->world;
+    b.seg.maps = (const uint64_t*)(d + kHeadWords * (size_t)h->world);
+    b.seg.ops = d + (kHeadWords + 4) * (size_t)h->world;
     b.seg.overflow = h->outblk + 1;
     b.seg.p2p = h->p2p ? h->p2p_dev : nullptr;
     b.seg.stats_send = h->outblk;
@@ -396,7 +410,7 @@ int exchange_cb(void* user, int which) {
   hml_t* h = (hml_t*)user;
   SweepBuffers b = make_buffers(h, h->KP ? h->KP : 2);
   switch (which) {
-    case kExchangeHeads: return exchange(h, kSlotHeads, b.seg.send_head, (void*)b.seg.heads, 4 * sizeof(double));
+    case kExchangeHeads: return exchange(h, kSlotHeads, b.seg.send_head, (void*)b.seg.heads, kHeadWords * sizeof(double));
     case kExchangeMaps: return exchange(h, kSlotMaps, b.seg.send_map, (void*)b.seg.maps, 4 * sizeof(uint64_t));
     case kExchangeOps: {
       const size_t n = (size_t)h->KP * h->KP + h->KP;
@@ -757,52 +771,80 @@ void segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t* le
 // Collective load of one segment.  Levels 1..12 of the Haar transform are local to 4096-tiles; the levels
 // above are computed by every rank from the all-gathered tile sums (T/4096 floats), so no rank needs
 // another rank's observations.
-int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float mult) {
+int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float mult, int D = 1) {
   if (h->world <= 1 || !h->comm) return fail(h, HML_ERR_STATE, "hml_comm_init has not been called on this handle");
   uint64_t start = 0, plan_len = 0;
   if (T < (uint64_t)kTile * h->world) return fail(h, HML_ERR_ARG, "sequence too short to split: T < 4096 * world");
   segment_plan(T, h->world, h->rank, &start, &plan_len);
   if (len != plan_len || len == 0) return fail(h, HML_ERR_ARG, "segment length does not match hml_segment_plan");
   load_reset(h);
+  h->D = D;
   load_norms(h);
   const int world = h->world;
   const uint64_t tiles_total = (T + kTile - 1) / kTile;
   const uint64_t per = (tiles_total + world - 1) / world;
   const uint64_t tiles = (len + kTile - 1) / kTile;
   const uint64_t slot = per + 16;  // floats per rank in the all-gather: tile sums + 12 edge coefficients
+  const uint64_t top_tiles = (tiles_total + kTile - 1) / kTile;
 
-  // ---- pass 0 on the local observations
   CK(dev_alloc(h->coeffs, tiles * kTile));
-  DevTmp<float> send, recv, gsum, ctop, sum0, sum1;
+  DevTmp<float> send, recv, gsum, ctop, ctop_d, sum0, sum1, plane, cdim;
   CK(send.alloc(slot));
   CK(recv.alloc(slot * world));
+  CK(gsum.alloc(per * world));
+  CK(ctop.alloc(top_tiles * kTile));
+  CK(sum0.alloc(top_tiles + 1));
+  CK(sum1.alloc(top_tiles / kTile + 2));
+  if (D > 1) {
+    CK(plane.alloc(len));
+    CK(cdim.alloc(tiles * kTile));
+    CK(ctop_d.alloc(top_tiles * kTile));
+  }
+  std::vector<float> infs(top_tiles * kTile, INFINITY);
+  int rc = HML_OK;
+  // Per data dimension (wavelet.hpp:150-163: the coefficient is the maximum over the dimensions of the normalised
+  // |detail|): levels 1..12 on the local observations, the tile sums of all ranks, the levels above from those.
+  for (int d = 0; d < D; ++d) {
+    const float* xd = x_dev;
+    if (D > 1) {
+      launch_deinterleave(x_dev, len, D, d, plane, h->sms, h->stream);
+      h->launches++;
+      xd = plane;
+    }
+    float* const cl = d == 0 ? h->coeffs : cdim.p;   // local coefficients of this dimension
+    float* const ct = d == 0 ? ctop.p : ctop_d.p;    // coefficients at multiples of 4096 (replicated)
+    CK(cudaMemsetAsync(send, 0, slot * sizeof(float), h->stream));
+    launch_maxlet_level(xd, len, len, 1, 0, cl, send, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    rc = all_gather(h, send, recv, slot * sizeof(float));
+    if (rc != HML_OK) return rc;
+    for (int r = 0; r < world; ++r) {
+      const uint64_t t0 = plan_first_tile(tiles_total, world, r), t1 = plan_first_tile(tiles_total, world, r + 1);
+      if (t1 > t0)
+        CK(cudaMemcpyAsync(gsum + t0, recv + (size_t)r * slot, (t1 - t0) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(ct, infs.data(), infs.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    float* sums[2] = {sum0, sum1};
+    rc = load_upper_passes(h, gsum, T / kTile, tiles_total, 1, kTileLog2, ct, sums);
+    if (rc != HML_OK) return rc;
+    if (d > 0) {
+      launch_max_combine(h->coeffs, cdim, len, h->sms, h->stream);
+      launch_max_combine(ctop, ctop_d, top_tiles * kTile, h->sms, h->stream);
+      h->launches += 2;
+    }
+    if (D > 1) {
+      rc = load_integral(h, plane, len, d, D);
+      if (rc != HML_OK) return rc;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  // ---- the 12 edge coefficients of the (combined) local array for the next rank
   CK(cudaMemsetAsync(send, 0, slot * sizeof(float), h->stream));
-  launch_maxlet_level(x_dev, len, len, 1, 0, h->coeffs, send, h->stream);
-  h->launches++;
   launch_pack_edge(h->coeffs, len, send + per, h->stream);
   h->launches++;
   CK(cudaGetLastError());
-  int rc = all_gather(h, send, recv, slot * sizeof(float));
-  if (rc != HML_OK) return rc;
-
-  // ---- upper levels from the global tile sums, replicated: ctop[m] = coefficient at position 4096 m
-  CK(gsum.alloc(per * world));
-  for (int r = 0; r < world; ++r) {
-    const uint64_t t0 = plan_first_tile(tiles_total, world, r), t1 = plan_first_tile(tiles_total, world, r + 1);
-    if (t1 > t0)
-      CK(cudaMemcpyAsync(gsum + t0, recv + (size_t)r * slot, (t1 - t0) * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-  }
-  const uint64_t top_tiles = (tiles_total + kTile - 1) / kTile;
-  CK(ctop.alloc(top_tiles * kTile));
-  {
-    std::vector<float> infs(top_tiles * kTile, INFINITY);
-    CK(cudaMemcpyAsync(ctop, infs.data(), infs.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-  }
-  CK(sum0.alloc(top_tiles + 1));
-  CK(sum1.alloc(top_tiles / kTile + 2));
-  float* sums[2] = {sum0, sum1};
-  rc = load_upper_passes(h, gsum, T / kTile, tiles_total, 1, kTileLog2, ctop, sums);
+  rc = all_gather(h, send, recv, slot * sizeof(float));
   if (rc != HML_OK) return rc;
 
   // ---- sigma-hat: odd positions are odd locally too (segments start at multiples of 4096)
@@ -832,15 +874,11 @@ int load_segment_common(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, 
   h->launches++;
   CK(cudaGetLastError());
 
-  rc = load_integral(h, x_dev, len);
-  if (rc != HML_OK) return rc;
+  if (D == 1) {
+    rc = load_integral(h, x_dev, len);
+    if (rc != HML_OK) return rc;
+  }
   CK(cudaStreamSynchronize(h->stream));
-  send.release();
-  recv.release();
-  gsum.release();
-  ctop.release();
-  sum0.release();
-  sum1.release();
   if (len > (1ull << 26)) dev_free(h->coeffs);
   rc = load_finish(h, len);
   h->T_global = T;
@@ -1181,11 +1219,14 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     l.seed = seed;
     l.sweep = sweep;
     l.sms = h->sms;
-    l.nblocks_hint = dynamic ? h->capacity : h->nblocks;
+    // upper bound of the block count for grid sizes: boundaries found among the candidates cannot outnumber them
+    l.nblocks_hint = dynamic ? ((h->spq_valid && h->cand_n < h->capacity) ? h->cand_n : h->capacity) : h->nblocks;
     l.exchange = exchange_cb;
     l.next_seq = next_seq_cb;
     l.exchange_user = h;
-    const bool fused_stats = seg && h->p2p;
+    // (multivariate data: the sums of the further dimensions are reduced after the first, so the result blocks are
+    // exchanged by a kernel of their own afterwards)
+    const bool fused_stats = seg && h->p2p && h->D == 1;
     l.stats_words = fused_stats ? (uint32_t)result_words(KP) : 0u;
     const int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
     if (n == -2) return fail(h, HML_ERR_ARG, "unsupported number of states");
@@ -2407,7 +2448,7 @@ int hml_comm_init(hml_t* h, int rank, int world, const uint8_t id[HML_UNIQUE_ID_
   CKN(g_nccl.CommInitRank(&h->comm, world, u, rank));
   h->rank = rank;
   h->world = world;
-  const size_t seg_words = 8 + kOpDoubles + (size_t)world * (8 + kOpDoubles);
+  const size_t seg_words = kHeadWords + 4 + kOpDoubles + (size_t)world * (kHeadWords + 4 + kOpDoubles);
   CK(dev_alloc(h->seg_dev, seg_words));
   CK(cudaMemsetAsync(h->seg_dev, 0, seg_words * sizeof(double), h->stream));
   CK(dev_alloc(h->stats_gather, (size_t)world * kOutWords));
@@ -2432,13 +2473,41 @@ int hml_segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t*
   return HML_OK;
 }
 
-int hml_load_segment_f32_device(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float weight_multiplier) {
+int hml_load_segment_f32_device_md(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, uint32_t nr_dims,
+                                   float weight_multiplier) {
   if (!h) return HML_ERR_ARG;
   if (!x_dev) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (nr_dims == 0) return fail(h, HML_ERR_ARG, "Number of dimensions must be positive!");
+  if (nr_dims > HML_MAX_DIMS)
+    return fail(h, HML_ERR_ARG, "at most " + std::to_string(HML_MAX_DIMS) + " data dimensions are supported");
   if (T >= (1ull << 32)) return fail(h, HML_ERR_ARG, "a sequence holds fewer than 2^32 observations");
   CK(cudaSetDevice(h->device));
-  if (h->world <= 1) return len == T ? load_common(h, x_dev, T, weight_multiplier) : fail(h, HML_ERR_ARG, "len != T without a communicator");
-  return load_segment_common(h, x_dev, len, T, weight_multiplier);
+  if (h->world <= 1)
+    return len == T ? load_common(h, x_dev, T, weight_multiplier, (int)nr_dims)
+                    : fail(h, HML_ERR_ARG, "len != T without a communicator");
+  return load_segment_common(h, x_dev, len, T, weight_multiplier, (int)nr_dims);
+}
+
+int hml_load_segment_f32_device(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float weight_multiplier) {
+  return hml_load_segment_f32_device_md(h, x_dev, len, T, 1, weight_multiplier);
+}
+
+int hml_load_segment_f32_md(hml_t* h, const float* x_host, uint64_t len, uint64_t T, uint32_t nr_dims, float weight_multiplier) {
+  if (!h) return HML_ERR_ARG;
+  if (!x_host) return fail(h, HML_ERR_ARG, "x must not be NULL");
+  if (len == 0 || nr_dims == 0) return fail(h, HML_ERR_ARG, "Input vector for breakpoint weights is empty!");
+  CK(cudaSetDevice(h->device));
+  float* xd = nullptr;
+  CK(dev_alloc(xd, len * nr_dims));
+  cudaError_t e = cudaMemcpyAsync(xd, x_host, len * nr_dims * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e != cudaSuccess) {
+    dev_free(xd);
+    return fail(h, HML_ERR_CUDA, cudaGetErrorString(e));
+  }
+  const int rc = hml_load_segment_f32_device_md(h, xd, len, T, nr_dims, weight_multiplier);
+  cudaStreamSynchronize(h->stream);
+  dev_free(xd);
+  return rc;
 }
 
 int hml_load_segment_f32(hml_t* h, const float* x_host, uint64_t len, uint64_t T, float weight_multiplier) {

@@ -49,7 +49,7 @@ const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);
 // ---- peer-memory carry exchange of the segment-split mode (hml_p2p.cu)
 constexpr int kP2PMaxWorld = 64;
 constexpr int kP2PSlots = 4;            // heads, operators, maps, statistics
-constexpr size_t kP2PPayload = 9216;    // largest payload: the result block of a K = 32 sweep
+constexpr size_t kP2PPayload = 12288;   // largest payload: the result block of a K = 32 sweep on 5-dimensional data
 constexpr size_t kP2PEntry = 2 * kP2PPayload;  // on the wire every 4 payload bytes travel with a 4-byte sequence tag
 constexpr unsigned long long kP2PTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
 struct P2PPeers {
@@ -85,9 +85,12 @@ struct ModelHost {  // what the C ABI receives, validated
 // Device buffers of one handle that the sweep kernels touch.  All per-block arrays are stored in
 // the chunk-interleaved order defined in hml_sweep.cu (Layout::perm).
 // Segment mode (world > 1): gathered carries of all ranks and this rank's send slots.
+// head record of a rank in segment mode: {blocks of the rank, length of the head = observations in front of the rank's
+// first boundary, then (sum x, sum x^2) of the head per data dimension}
+constexpr int kHeadWords = 2 + 2 * kMaxDims;
 struct SegInfo {
   int rank, world;
-  const double* heads;   // world x 4: {blocks of the rank, head length, head sum x, head sum x^2}
+  const double* heads;   // world x kHeadWords
   const double* ops;     // world x (KP*KP + KP): segment operator mantissas (row-major) then row exponents
   const uint64_t* maps;  // world x 4 words: segment map f_first o ... o f_last (byte-packed)
   double* send_head;

@@ -76,7 +76,7 @@ struct RunCtx {
 };
 __device__ __forceinline__ uint32_t run_prev_state(const RunCtx& c) {
   for (int r = c.rank - 1; r >= 0; --r)
-    if (c.heads[4 * r] > 0.0) return (uint32_t)c.last_states[r];
+    if (c.heads[kHeadWords * r] > 0.0) return (uint32_t)c.last_states[r];
   return 0u;  // unreachable: rank 0 always owns the block that starts at position 0
 }
 // does a virtual run precede the rank's blocks?

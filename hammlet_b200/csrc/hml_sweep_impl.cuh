@@ -374,18 +374,18 @@ __device__ __forceinline__ uint64_t device_nblocks(const unsigned long long* nb,
 // ---- segment mode: what a rank derives from the all-gathered heads {blocks, head length, head sums}
 __device__ __forceinline__ uint64_t seg_first_block(const SegInfo& g) {  // global index of this rank's block 0
   uint64_t o = 0;
-  for (int r = 0; r < g.rank; ++r) o += (uint64_t)g.heads[4 * r];
+  for (int r = 0; r < g.rank; ++r) o += (uint64_t)g.heads[kHeadWords * r];
   return o;
 }
 __device__ __forceinline__ uint64_t seg_global_blocks(const SegInfo& g, uint64_t local) {
   if (g.world <= 1) return local;
   uint64_t o = 0;
-  for (int r = 0; r < g.world; ++r) o += (uint64_t)g.heads[4 * r];
+  for (int r = 0; r < g.world; ++r) o += (uint64_t)g.heads[kHeadWords * r];
   return o;
 }
 __device__ __forceinline__ bool seg_later_blocks(const SegInfo& g) {  // does any later rank own a block?
   for (int r = g.rank + 1; r < g.world; ++r)
-    if (g.heads[4 * r] > 0.0) return true;
+    if (g.heads[kHeadWords * r] > 0.0) return true;
   return false;
 }
 
@@ -440,17 +440,19 @@ static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint3
     const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
     if (buf.seg.overflow) *buf.seg.overflow = raw > buf.capacity ? 1ull : 0ull;
     const uint32_t e = B ? buf.starts[0] : seg_len;
-    double sx = 0.0, sq = 0.0;
-    if (e > 0) range_sums(buf, 0u, e, sx, sq);
     buf.seg.send_head[0] = (double)B;
     buf.seg.send_head[1] = (double)e;
-    buf.seg.send_head[2] = sx;
-    buf.seg.send_head[3] = sq;
+    for (int d = 0; d < kMaxDims; ++d) {  // one pair per data dimension (IntegralArray.hpp:176-182)
+      double sx = 0.0, sq = 0.0;
+      if (e > 0 && d < buf.D) range_sums_dim(buf, d, 0u, e, sx, sq);
+      buf.seg.send_head[2 + 2 * d] = sx;
+      buf.seg.send_head[3 + 2 * d] = sq;
+    }
   }
   if (seq && buf.seg.p2p) {
     __threadfence();
     __syncthreads();
-    p2p_exchange_cta(buf.seg.p2p, kSlotHeads, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_head), 4,
+    p2p_exchange_cta(buf.seg.p2p, kSlotHeads, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_head), kHeadWords,
                      reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.heads)));
   }
 }
@@ -469,7 +471,7 @@ __device__ __forceinline__ void block_sums(const SweepBuffers& buf, uint64_t b, 
   n = e - s;
   if (buf.seg.world > 1 && b + 1 == B) {
     for (int r = buf.seg.rank + 1; r < buf.seg.world; ++r) {
-      const double* hd = buf.seg.heads + 4 * r;
+      const double* hd = buf.seg.heads + kHeadWords * r;
       n += (uint32_t)hd[1];
       sx += hd[2];
       sq += hd[3];
@@ -632,14 +634,28 @@ __global__ void __launch_bounds__(256) k_block_emit_md(SweepBuffers buf, EmitMD<
     if (kGather) {
       const uint32_t s = buf.starts[b], e = buf.starts[b + 1];
       n = e - s;
-      buf.bN[p] = n;
 #pragma unroll
-      for (int d = 0; d < kMaxDims; ++d) {
-        if (d < D) {
-          range_sums_dim(buf, d, s, e, sx[d], sq[d]);
-          buf.bS[(size_t)d * buf.capacity + p] = make_double2(sx[d], sq[d]);
+      for (int d = 0; d < kMaxDims; ++d)
+        if (d < D) range_sums_dim(buf, d, s, e, sx[d], sq[d]);
+      if (buf.seg.world > 1 && b + 1 == B) {
+        // the rank's last block continues on the following ranks up to their first boundary
+        for (int r = buf.seg.rank + 1; r < buf.seg.world; ++r) {
+          const double* hd = buf.seg.heads + kHeadWords * r;
+          n += (uint32_t)hd[1];
+#pragma unroll
+          for (int d = 0; d < kMaxDims; ++d) {
+            if (d < D) {
+              sx[d] += hd[2 + 2 * d];
+              sq[d] += hd[3 + 2 * d];
+            }
+          }
+          if (hd[0] > 0.0) break;
         }
       }
+      buf.bN[p] = n;
+#pragma unroll
+      for (int d = 0; d < kMaxDims; ++d)
+        if (d < D) buf.bS[(size_t)d * buf.capacity + p] = make_double2(sx[d], sq[d]);
     } else {
       n = buf.bN[p];
 #pragma unroll
@@ -1311,7 +1327,7 @@ __global__ void __launch_bounds__(256) k_fwd_tilescan_small(SweepBuffers buf, Mo
       for (int r = 0; r < buf.seg.rank; ++r) {
         OpVals<KP> o;
         load_gathered_op<KP>(o, buf.seg.ops + (size_t)r * (KP * KP + KP));
-        if (buf.seg.heads[4 * r] > 0.0 && !vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+        if (buf.seg.heads[kHeadWords * r] > 0.0 && !vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
       }
     }
 #pragma unroll 1
@@ -1480,7 +1496,7 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(256)
       for (int r = 0; r < buf.seg.rank; ++r) {
         OpVals<KP> o;
         load_gathered_op<KP>(o, buf.seg.ops + (size_t)r * (KP * KP + KP));
-        if (buf.seg.heads[4 * r] > 0.0 && !vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
+        if (buf.seg.heads[kHeadWords * r] > 0.0 && !vec_apply_op<KP>(a, o)) atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
       }
     }
 #pragma unroll 1
@@ -1584,7 +1600,7 @@ __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDe
 #pragma unroll
         for (int k = 0; k < KP; ++k) o.col[k] = lane < KP ? go[k * KP + lane] : 0.0;
         o.x = lane < KP ? (int)go[KP * KP + lane] : kDeadExp;
-        if (buf.seg.heads[4 * r] > 0.0 && !warp_apply_op<KP>(a, o) && lane == 0)
+        if (buf.seg.heads[kHeadWords * r] > 0.0 && !warp_apply_op<KP>(a, o) && lane == 0)
           atomicAdd(&buf.out_u64[KP + KP * KP], 1ull);
       }
     }

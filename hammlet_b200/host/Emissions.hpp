@@ -78,17 +78,21 @@ class DeviceSequence {
   int rank() const { return mRank; }
   int world() const { return mWorld; }
   bool split() const { return mWorld > 1; }
-  // joins the communicator (collective) and loads this rank's slice of `values` (the whole sequence, univariate)
+  // joins the communicator (collective) and loads this rank's slice of `values` (the whole sequence as read: nrDim
+  // values per position)
   void loadSegment(const std::vector<float>& values, float weightMultiplier, int rank, int world,
-                   const uint8_t id[HML_UNIQUE_ID_BYTES]) {
+                   const uint8_t id[HML_UNIQUE_ID_BYTES], size_t nrDim = 1) {
     if (values.empty()) throw std::runtime_error("Input vector for breakpoint weights is empty!");
+    if (values.size() % nrDim != 0)
+      throw std::runtime_error("Input stream did not contain enough values to fill all dimensions at last position!");
+    const uint64_t T = values.size() / nrDim;
     check(hml_comm_init(mHandle, rank, world, id));
     uint64_t start = 0, len = 0;
-    if (hml_segment_plan(values.size(), world, rank, &start, &len) != HML_OK)
+    if (hml_segment_plan(T, world, rank, &start, &len) != HML_OK)
       throw std::runtime_error("Sequence too short to split over " + std::to_string(world) + " devices (4096 observations each at least)!");
-    check(hml_load_segment_f32(mHandle, values.data() + start, len, values.size(), weightMultiplier));
-    mSize = values.size();
-    mNrDim = 1;
+    check(hml_load_segment_f32_md(mHandle, values.data() + start * nrDim, len, T, (uint32_t)nrDim, weightMultiplier));
+    mSize = T;
+    mNrDim = nrDim;
     mRank = rank;
     mWorld = world;
     check(hml_sigma_hat(mHandle, &mSigmaHat));

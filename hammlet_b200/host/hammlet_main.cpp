@@ -8,7 +8,7 @@
 //   -devices a b c ...   split the sequence into contiguous segments over the listed devices (also `a,b,c`): one
 //                        process per device is forked after the input has been parsed, every process runs the same
 //                        chain on the same parameters, the scan carries travel between the GPUs,
-//                        process 0 writes the files — the same files a single device writes.  Univariate data.
+//                        process 0 writes the files — the same files a single device writes.
 //   -F|-input-format X   auto (default: gzip'd text is recognised by its magic number, anything else is text), text, gz,
 //                        f32 (raw little-endian float32: 4 bytes per value instead of ~9 of text)
 //   -replay              draw the per-block uniforms from the shared mt19937 exactly as the reference
@@ -203,7 +203,6 @@ static int hammletMain(int argc, const char* argv[]) {
       if (devices.empty()) throw std::runtime_error("Flag -devices needs at least one device index!");
     }
     const int world = (int)devices.size();
-    if (world > 1 && nrDataDim != 1) throw std::runtime_error("A sequence split over several devices must be univariate!");
 
     // ---- load: parse on the host (before any process is forked and before CUDA is touched), transform on the device
     const fastparse::Format inputFormat = fastparse::formatFromName(args.parse<string>("-F"));
@@ -267,7 +266,7 @@ static int hammletMain(int argc, const char* argv[]) {
 
     DeviceSequence sequence(devices[rank]);
     if (world > 1)
-      sequence.loadSegment(values, (float)weightMultiplier, rank, world, commId);
+      sequence.loadSegment(values, (float)weightMultiplier, rank, world, commId, nrDataDim);
     else
       sequence.load(values, (float)weightMultiplier, nrDataDim);
     vector<float>().swap(values);

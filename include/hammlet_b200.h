@@ -62,8 +62,8 @@ int hml_load_f32_device(hml_t* h, const float* x_dev, uint64_t T, float weight_m
 /* Multivariate data (main.cpp:114-137 `-s C p d`, wavelet.hpp:131-163): x holds T positions x nr_dims values,
  * position-major as they stand in the input stream.  The breakpoint weights come from the maxlet transform (the
  * maximum over the dimensions of the absolute Haar coefficients, wavelet.hpp:155-160); integral arrays are kept per
- * dimension (Statistics/IntegralArray.hpp:176-182).  nr_dims = 1 is hml_load_f32.  Not available on a handle that
- * joined a communicator (a segment-split sequence is univariate). */
+ * dimension (Statistics/IntegralArray.hpp:176-182).  nr_dims = 1 is hml_load_f32.  A handle that joined a communicator
+ * loads its share with hml_load_segment_f32_md. */
 int hml_load_f32_md(hml_t* h, const float* x_host, uint64_t T, uint32_t nr_dims, float weight_multiplier);
 int hml_load_f32_device_md(hml_t* h, const float* x_dev, uint64_t T, uint32_t nr_dims, float weight_multiplier);
 int hml_nr_dims(const hml_t* h, uint32_t* nr_dims);
@@ -245,6 +245,12 @@ int hml_segment_plan(uint64_t T, int world, int rank, uint64_t* start, uint64_t*
  * (host or device memory respectively); T is the length of the whole sequence. */
 int hml_load_segment_f32(hml_t* h, const float* x_host, uint64_t len, uint64_t T, float weight_multiplier);
 int hml_load_segment_f32_device(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, float weight_multiplier);
+/* The same for multivariate data: x holds this rank's len positions x nr_dims values, position-major (hml_load_f32_md).
+ * Per dimension the ranks exchange their tile sums (the levels of the transform above 4096 observations); the partial
+ * block in front of a rank's first boundary travels with one (sum x, sum x^2) pair per dimension. */
+int hml_load_segment_f32_md(hml_t* h, const float* x_host, uint64_t len, uint64_t T, uint32_t nr_dims, float weight_multiplier);
+int hml_load_segment_f32_device_md(hml_t* h, const float* x_dev, uint64_t len, uint64_t T, uint32_t nr_dims,
+                                   float weight_multiplier);
 /* After a sweep in segment mode: this rank's first global block index and the global block count
  * (hml_sweep_out.nblocks is the global count; hml_nr_blocks / hml_get_* stay rank-local, with
  * block starts reported as global positions). */

@@ -153,6 +153,38 @@ def main():
         if rank == 0:
             print(f"case {ci} ok: T={T} K={K} world={world} blocks={Br}", flush=True)
 
+    # ---- multivariate data on a split sequence (-s C P D): maxlet weights = maximum over the dimensions of per-dimension
+    # coefficients whose upper levels come from all-gathered tile sums; heads carry one pair of sums per dimension
+    from hammlet_b200.synth import piecewise_gaussian_md
+    for ci, (T, P, D, thr) in enumerate([(4096 * world + 77, 2, 2, 0.9), (150_001 if small else 900_001, 3, 2, 0.7),
+                                         (70_000 if small else 400_000, 2, 3, 1e30)]):
+        xm = piecewise_gaussian_md(T, P, D, 300, 40 + ci, quantum_bits=10)
+        Kmd = P ** D
+        mapping = np.array([[(st // (P ** d)) % P for d in range(D)] for st in range(Kmd)], np.int32)
+        mu, var, _, _ = model_guess(P, seed=ci + 3)
+        _, _, A, pi = model_guess(Kmd, seed=ci + 3)
+        s, n = capi.Handle.segment_plan(T, world, rank)
+        h.load_segment(xm[s:s + n], T)
+        ref.load(xm)
+        assert np.array_equal(h.weights().view(np.uint32), ref.weights()[s:s + n].view(np.uint32)), f"md case {ci}: weights differ"
+        assert abs(h.sigma_hat() - ref.sigma_hat()) <= 1e-12 * abs(ref.sigma_hat())
+        Bg, Br = h.create_blocks(thr), ref.create_blocks(thr)
+        assert Bg == Br
+        u = np.random.default_rng(ci).random(Br)
+        o = h.fb_sweep(mu, var, A, pi, replay=u, mapping=mapping)
+        r = ref.fb_sweep(mu, var, A, pi, replay=u, mapping=mapping)
+        check_same(o, r, f"md case {ci} replay")
+        local_states_match(h, ref)
+        runs_match(h, ref, f"md case {ci} replay")
+        if thr < 1e29:
+            for i in range(3):
+                o = h.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=thr * (1 + 0.05 * i), seed=5, sweep=i, mapping=mapping)
+                r = ref.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=thr * (1 + 0.05 * i), seed=5, sweep=i, mapping=mapping)
+                check_same(o, r, f"md case {ci} dynamic {i}")
+                local_states_match(h, ref)
+        if rank == 0:
+            print(f"md case {ci} ok: T={T} P={P} D={D} world={world} blocks={Br}", flush=True)
+
     # ---- capacity growth must stay collective: tiny threshold => far more blocks than the initial capacity
     T = 200_000 if small else 2_000_000
     x = piecewise_gaussian(T, 3, 50, seed=3)

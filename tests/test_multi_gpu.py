@@ -83,3 +83,26 @@ def test_cli_devices_philox_run_equals_single_device(tmp_path):
     assert a.returncode == 0 and b.returncode == 0, a.stderr[-2000:] + b.stderr[-2000:]
     for kind in ("marginals", "compression", "parameters"):
         assert (tmp_path / f"one-{kind}.csv").read_text() == (tmp_path / f"two-{kind}.csv").read_text(), kind
+
+
+@pytest.mark.gpu
+def test_cli_devices_multivariate_replay_run_equals_the_reference(tmp_path):
+    """`-s C 2 2` (two values per position, four states) on a sequence split over two GPUs: all six files equal the
+    real_t = double reference's byte for byte."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+    from hammlet_b200.synth import piecewise_gaussian_md
+    ours = _need(os.path.join(ROOT, "hammlet_b200", "bin", "hammlet64"))
+    ref = _need(os.path.join(ROOT, "oracle", "_ref", "hammlet64"))
+    x = piecewise_gaussian_md(50000, 2, 2, 250, 7, quantum_bits=10)
+    with open(tmp_path / "in.txt", "w") as f:
+        f.write("\n".join(" ".join(f"{v:.10f}" for v in row) for row in x.astype(np.float64)) + "\n")
+    common = ["-f", "in.txt", "-a", "-R", "7", "-s", "C", "2", "2", "-i", "M", "5", "0", "F", "30", "2",
+              "-O", "M", "S", "P", "B", "C", "G", "-w"]
+    r = subprocess.run([ref] + common + ["-o", "ref-", ".csv"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    p = subprocess.run([ours, "-replay", "-devices", "0", "1"] + common + ["-o", "our-", ".csv"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=150)
+    assert r.returncode == 0 and p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:] + r.stderr[-2000:]
+    for kind in ("blocks", "compression", "sequences", "parameters", "marginals", "segments"):
+        assert (tmp_path / f"our-{kind}.csv").read_text() == (tmp_path / f"ref-{kind}.csv").read_text(), kind
