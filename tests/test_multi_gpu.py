@@ -67,7 +67,9 @@ def test_cli_devices_replay_run_equals_the_reference(tmp_path, world, outputs):
 @pytest.mark.gpu
 def test_cli_devices_philox_run_equals_single_device(tmp_path):
     """Without -replay the uniforms are Philox counters indexed by the global block number, so a run split over two
-    GPUs must write the same marginals file as the same run on one GPU."""
+    GPUs must write the same marginals file as the same run on one GPU.  Both runs draw the parameters on the host
+    (`HAMMLET_HOST_PARAMS=1`): left to itself the single-device run would use the device-resident chain, whose parameter
+    draws are Philox streams and not the host's mt19937."""
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
     import numpy as np
@@ -77,9 +79,11 @@ def test_cli_devices_philox_run_equals_single_device(tmp_path):
     with open(tmp_path / "in.txt", "w") as f:
         f.write("\n".join(f"{v:.10f}" for v in x.astype(np.float64)) + "\n")
     common = ["-f", "in.txt", "-a", "-R", "9", "-s", "4", "-i", "F", "60", "3", "-O", "M", "P", "C", "-w"]
-    a = subprocess.run([ours] + common + ["-o", "one-", ".csv"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, HAMMLET_HOST_PARAMS="1")
+    a = subprocess.run([ours] + common + ["-o", "one-", ".csv"], cwd=tmp_path, capture_output=True, text=True, timeout=600,
+                       env=env)
     b = subprocess.run([ours, "-devices", "0,1"] + common + ["-o", "two-", ".csv"], cwd=tmp_path, capture_output=True, text=True,
-                       timeout=150)
+                       timeout=150, env=env)
     assert a.returncode == 0 and b.returncode == 0, a.stderr[-2000:] + b.stderr[-2000:]
     for kind in ("marginals", "compression", "parameters"):
         assert (tmp_path / f"one-{kind}.csv").read_text() == (tmp_path / f"two-{kind}.csv").read_text(), kind
