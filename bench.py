@@ -469,6 +469,8 @@ def main():
         "block_emit": Bl * (4 + 16 + 4 + 16 + 16 * K),                                 # starts, integral gathers, N, sums, e, sp
         "fwd_chunks": Bl * 8 * K * (1 + K / 32.0),
         "fwd_replay": Bl * 16 * K,
+        "fwd_spec": Bl * 8 * K * (2 + 4 / 32.0),                                       # e (+ 4 warm-up blocks per chunk of 32), rows
+        "bwd_maps": Bl * (8 * K + 4 + 8),                                              # rows, N, the K -> K map of the block
     }
     kernels = {k: v for k, v in busy.items() if k in alg}
     top = max(kernels, key=kernels.get)

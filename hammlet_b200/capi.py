@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libhammlet_b200.so")
 
 SWEEP_DYNAMIC, SWEEP_LOGLIK, SWEEP_KEEP_ROWS, SWEEP_FUSED = 1, 2, 4, 8
 DETECT_STREAM, DETECT_PYRAMID, DETECT_CANDIDATES = 0, 1, 2
+FORWARD_AUTO, FORWARD_OPERATORS, FORWARD_SPECULATIVE = 0, 1, 2
 MAX_STATES = 32
 MAX_DIMS = 5
 
@@ -54,7 +55,8 @@ EXPORTS = ["hml_create", "hml_destroy", "hml_last_error", "hml_version", "hml_lo
            "hammlet_chain_get", "hammlet_chain_set", "hammlet_chain_run", "hammlet_chain_run_recorded",
            "hammlet_chain_save_marginals", "hammlet_chains_run", "hammlet_chain_last_sweep",
            "hml_comm_allgather", "hml_chain_init", "hml_chain_set", "hml_chain_get", "hml_chain_run",
-           "hml_chain_phase_ns", "hml_load_segment_f32_md", "hml_load_segment_f32_device_md"]
+           "hml_chain_phase_ns", "hml_load_segment_f32_md", "hml_load_segment_f32_device_md",
+           "hml_set_forward_mode", "hml_forward_info"]
 UNIQUE_ID_BYTES = 128
 
 _lib = None
@@ -215,6 +217,16 @@ class Handle:
         """DETECT_STREAM (read every weight), DETECT_PYRAMID (read only sub-blocks that can hold a boundary) or
         DETECT_CANDIDATES (default: one pass over the list of positions that can be boundaries near the threshold)."""
         self._ck(self.lib.hml_set_detect_mode(self.h, C.c_int(mode)))
+
+    def set_forward_mode(self, mode):
+        """FORWARD_AUTO (default: speculative, operator scan after a failure), FORWARD_OPERATORS, FORWARD_SPECULATIVE."""
+        self._ck(self.lib.hml_set_forward_mode(self.h, C.c_int(mode)))
+
+    def forward_info(self):
+        """(mode, speculative sweeps so far, how many of them were repeated through the operator scan)"""
+        mode, n, f = C.c_int(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.hml_forward_info(self.h, C.byref(mode), C.byref(n), C.byref(f)))
+        return mode.value, n.value, f.value
 
     def detect_info(self):
         mode, hot = C.c_int(), C.c_uint64()

@@ -162,6 +162,10 @@ struct hml_ctx {
   uint32_t* mg_n_host = nullptr;         // pinned mirror of the current count
   bool mg_pending = false;               // a count copy has been queued since the last stream synchronisation
   double* partials = nullptr;
+  // forward filter: speculative (guessed chunk starts + repair pass) unless it keeps failing on this data
+  int forward_mode = HML_FORWARD_AUTO;
+  uint64_t spec_sweeps = 0, spec_failures = 0;
+  uint32_t spec_skip = 0, spec_streak = 0;  // sweeps still to run through the operator scan / failures in a row
   unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
   unsigned long long* outblk_host = nullptr;  // pinned mirror
 
@@ -1228,7 +1232,13 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     // exchanged by a kernel of their own afterwards)
     const bool fused_stats = seg && h->p2p && h->D == 1;
     l.stats_words = fused_stats ? (uint32_t)result_words(KP) : 0u;
-    const int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
+    // the speculative forward filter: single handle, forward-backward sweeps; after a failure the operator scan takes
+    // the next sweeps (1, 2, 4, ... up to 64 after failures in a row), so data on which the filter does not forget its
+    // start pays the wasted pass rarely
+    l.speculate = !mixture && !seg && h->forward_mode != HML_FORWARD_OPERATORS &&
+                  (h->forward_mode == HML_FORWARD_SPECULATIVE || h->spec_skip == 0);
+    if (!l.speculate && h->spec_skip > 0 && !mixture && !seg) h->spec_skip--;
+    int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
     if (n == -2) return fail(h, HML_ERR_ARG, "unsupported number of states");
     if (n < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
     h->launches += n;
@@ -1236,6 +1246,27 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     SweepResult res;
     rc = fetch_result(h, KP, res, fused_stats);
     if (rc != HML_OK) return rc;
+    if (l.speculate && !(dynamic && res.any_overflow)) {
+      h->spec_sweeps++;
+      if (res.o64[KP + KP * KP + 1] > 0) {  // some chunk's rows did not meet the guess's: the exact operator scan
+        h->spec_failures++;
+        h->spec_streak = h->spec_streak < 6 ? h->spec_streak + 1 : 6;
+        h->spec_skip = (1u << h->spec_streak) - 1;
+        l.speculate = false;
+        l.gather = false;  // the block sums of this block list are in place
+        l.nblocks_hint = res.local_blocks;
+        h->stages.clear();
+        h->stage_used = 0;
+        n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
+        if (n < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
+        h->launches += n;
+        CK(cudaGetLastError());
+        rc = fetch_result(h, KP, res, fused_stats);
+        if (rc != HML_OK) return rc;
+      } else {
+        h->spec_streak = 0;
+      }
+    }
     if (dynamic && res.any_overflow) {  // some rank's block arrays were too small: grow and run the sweep again
       if (res.own_overflow) {
         rc = alloc_blocks(h, res.local_blocks + res.local_blocks / 4, KP);
@@ -2551,6 +2582,23 @@ int hml_set_detect_mode(hml_t* h, int mode) {
   if (mode != HML_DETECT_STREAM && mode != HML_DETECT_PYRAMID && mode != HML_DETECT_CANDIDATES)
     return fail(h, HML_ERR_ARG, "unknown detection mode");
   h->detect_mode = mode;
+  return HML_OK;
+}
+
+int hml_set_forward_mode(hml_t* h, int mode) {
+  if (!h) return HML_ERR_ARG;
+  if (mode != HML_FORWARD_AUTO && mode != HML_FORWARD_OPERATORS && mode != HML_FORWARD_SPECULATIVE)
+    return fail(h, HML_ERR_ARG, "unknown forward mode");
+  h->forward_mode = mode;
+  h->spec_skip = h->spec_streak = 0;
+  return HML_OK;
+}
+
+int hml_forward_info(hml_t* h, int* mode, uint64_t* speculative_sweeps, uint64_t* failures) {
+  if (!h) return HML_ERR_ARG;
+  if (mode) *mode = h->forward_mode;
+  if (speculative_sweeps) *speculative_sweeps = h->spec_sweeps;
+  if (failures) *failures = h->spec_failures;
   return HML_OK;
 }
 

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) k_sweep_fused(SweepBuffers b
     const unsigned long long sweep_key = args.philox_sweep_from_chain ? __ldcg(&ch->sweep) : args.sweep;
     if (cta == 0) {
       // the first phase that writes the result block of this sweep
-      for (int i = tid; i < KP + KP * KP + 1; i += kFusedThreads) buf.out_u64[i] = 0;
+      for (int i = tid; i < KP + KP * KP + 2; i += kFusedThreads) buf.out_u64[i] = 0;
       for (int i = tid; i < 2 * KP + 1; i += kFusedThreads) buf.out_f64[i] = 0.0;
       if (tid == 0 && !(thr >= ch->cand_floor && thr > 0.f && isfinite(thr))) ch->phase_abort[1] = kChainThreshold;
     }

@@ -231,6 +231,7 @@ struct SweepLaunch {
   unsigned long long (*next_seq)(void* user, int which);
   void* exchange_user;
   uint32_t stats_words;  // 8-byte words of the result block travelling in the statistics exchange (0: not fused)
+  bool speculate;        // forward filter by guessed chunk starts + repair pass (result word KP + KP*KP + 1 counts failures)
 };
 enum { kExchangeHeads = 0, kExchangeOps = 1, kExchangeMaps = 2, kExchangeStats = 3 };
 // segment mode: head partial of this rank -> seg.send_head (to be all-gathered before the block statistics)

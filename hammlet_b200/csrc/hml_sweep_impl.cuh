@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) k_block_emit(SweepBuffers buf, ModelDev<K
   }
   if (kEmit && blockIdx.x == 0) {
     // first kernel of a sweep: zero the result block that the later kernels accumulate into
-    for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
+    for (int i = threadIdx.x; i < KP + KP * KP + 2; i += blockDim.x) buf.out_u64[i] = 0;
     for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
   }
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(256) k_block_emit_md(SweepBuffers buf, EmitMD<
     __syncthreads();
   }
   if (kEmit && blockIdx.x == 0) {
-    for (int i = threadIdx.x; i < KP + KP * KP + 1; i += blockDim.x) buf.out_u64[i] = 0;
+    for (int i = threadIdx.x; i < KP + KP * KP + 2; i += blockDim.x) buf.out_u64[i] = 0;
     for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
   }
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
@@ -1070,6 +1070,106 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS, (KP <= 5 ? 4 : (KP <= 6 ?
 }
 
 // ------------------------------------------------------------------------------------------------
+// Speculative forward pass (rank convergence).  The filter forgets where it started: two runs of the recursion
+// alpha_t = normalise(e_t o (alpha_{t-1} A)) from different vectors become parallel after a few informative blocks.
+// So instead of products of K x K chunk operators (2 K^3 flop per block) every chunk runs the VECTOR recursion
+// (2 K^2) from a guess — uniform, pushed through the last kSpecWarm blocks of the chunk before it — and a second
+// pass repairs the first rows of every chunk from the (by then known) last row of its predecessor until the repaired
+// row is parallel to the stored one; the rest of the chunk is then right as it stands.  A chunk whose rows have not
+// met by its last block reports a failure and the host runs the sweep again through the operator scan, which needs
+// no such assumption.  (ForwardBackward.hpp:64-125 is one sequential loop; SURVEY.md §7 "rank-1 collapse".)
+template <int KP>
+struct SpecCfg {
+  static constexpr int kWarm = KP <= 8 ? 4 : 8;  // warm-up blocks before a chunk
+};
+constexpr double kSpecTol = 1e-13;  // relative agreement of every component of two rows that count as parallel
+
+// index of the result slot that counts chunks whose repair did not converge (the pad word after the fallbacks)
+template <int KP>
+__device__ __forceinline__ int spec_fail_slot() {
+  return KP + KP * KP + 1;
+}
+
+// the guess for the vector entering chunk (tile, c): pi for the very first chunk, otherwise uniform pushed through
+// the last kWarm blocks of the previous chunk (rescaled by exact powers of two; a vanished vector restarts uniform)
+template <int KP>
+__device__ __forceinline__ void spec_entry(const SweepBuffers& buf, const ModelDev<KP>& m, uint64_t tile, int c,
+                                           double (&a)[KP]) {
+  constexpr int L = Layout::L, C = Layout::C, W = SpecCfg<KP>::kWarm;
+  const int K = m.K;
+  if (tile == 0 && c == 0) {
+    if (buf.seg.world > 1 && buf.seg.rank > 0) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;  // repaired from the previous rank's last row
+    } else {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = m.pi[j];
+    }
+    return;
+  }
+  const uint64_t pt = c > 0 ? tile : tile - 1;
+  const int pc = c > 0 ? c - 1 : C - 1;
+  const double* ep = buf.e + Layout::at(pt, pc, L - W) * KP;
+  double en[KP];  // emission terms one step ahead of their use
+#pragma unroll
+  for (int j = 0; j < KP; ++j) en[j] = ep[j];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 : 0.0;
+#pragma unroll 1
+  for (int t = 0; t < W; ++t) {
+    double ev[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) ev[j] = en[j];
+    if (t + 1 < W) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) en[j] = ep[(uint64_t)(t + 1) * C * KP + j];
+    }
+    double f[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) f[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
+    }
+    double mxv = 0.0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      f[j] *= ev[j];
+      mxv = fmax(mxv, f[j]);
+    }
+    if (mxv > 0.0) {
+      int e2 = exponent_of(mxv);
+      if (e2 < -1000) e2 = -1000;
+      const double sc = pow2i(-e2);
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = f[j] * sc;
+    } else {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 : 0.0;
+    }
+  }
+}
+
+// are x and y parallel?  |x_j / sum(x) - y_j / sum(y)| <= tol * x_j / sum(x) for every j, without dividing
+template <int KP>
+__device__ __forceinline__ bool rows_parallel(const double (&x)[KP], const double (&y)[KP]) {
+  double sx = 0.0, sy = 0.0;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    sx += x[j];
+    sy += y[j];
+  }
+  bool ok = sx > 0.0 && sy > 0.0;
+#pragma unroll
+  for (int j = 0; j < KP; ++j) {
+    const double l = x[j] * sy, r = y[j] * sx;
+    ok = ok && (fabs(l - r) <= kSpecTol * l + 1e-300);
+  }
+  return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_fwd_replay_prefix (K <= 8): one warp per tile, lane c owns chunk c.  The vector entering the chunk is
 // normalise(vector entering the tile x prefix operator of the chunk); then the reference's own recursion
 // alpha_t = e_t o (alpha_{t-1} A) runs over the chunk, with e arriving in slabs of kSlab steps by
@@ -1085,8 +1185,10 @@ struct ReplayCfg {
   static constexpr size_t kSmem = 2 * kStage;
 };
 
-template <int KP, bool kExact, bool kLoglik>
-__global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m) {
+//   kSpec    speculative pass: the vector entering the chunk is a guess (spec_entry), k_fwd_fixup repairs the rows;
+//            the log-likelihood terms go to `lognorm` per block and are summed after the repair
+template <int KP, bool kExact, bool kLoglik, bool kSpec = false>
+__global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm = nullptr) {
   pdl_enter();
   using Cfg = ReplayCfg<KP>;
   constexpr int L = Layout::L, C = Layout::C, S = Cfg::kSlab, NS = L / S;
@@ -1125,12 +1227,18 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
     if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
     // ---- vector entering chunk c
     double a[KP];
+    if constexpr (kSpec) {
 #pragma unroll
-    for (int j = 0; j < KP; ++j) a[j] = buf.tile_ain[tile * KP + j];
-    if (c > 0 && steps > 0) {
-      OpVals<KP> o;
-      load_op<KP>(o, buf.chunk_ops + (tile * C + c) * KP * KP, buf.chunk_exp + (tile * C + c) * KP);
-      if (!vec_apply_op<KP>(a, o)) fallbacks++;
+      for (int j = 0; j < KP; ++j) a[j] = 0.0;
+      if (steps > 0) spec_entry<KP>(buf, m, tile, c, a);
+    } else {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = buf.tile_ain[tile * KP + j];
+      if (c > 0 && steps > 0) {
+        OpVals<KP> o;
+        load_op<KP>(o, buf.chunk_ops + (tile * C + c) * KP * KP, buf.chunk_exp + (tile * C + c) * KP);
+        if (!vec_apply_op<KP>(a, o)) fallbacks++;
+      }
     }
 #pragma unroll 1
     for (int slab = 0; slab < NS; ++slab) {
@@ -1168,7 +1276,12 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
               const double inv = 1.0 / fs;
 #pragma unroll
               for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
-              if (kLoglik) ll += buf.maxE[p] + log(fs);
+              if (kLoglik) {
+                if (kSpec)
+                  lognorm[p] = buf.maxE[p] + log(fs);
+                else
+                  ll += buf.maxE[p] + log(fs);
+              }
             } else {          // FB.hpp:106-111: uniform fallback (the host then re-runs the sweep sequentially)
               fallbacks++;
 #pragma unroll
@@ -1205,14 +1318,112 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
     }
     __syncwarp();
   }
-  if (kLoglik) {
+  if (kLoglik && !kSpec) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ll += shfl_xor_double(ll, o);
     if (lane == 0) buf.partials[blockIdx.x] = ll;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
-  if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[KP + KP * KP], (unsigned long long)fallbacks);
+  // a vanished forward sum under a guessed start proves nothing about the true recursion: the sweep is run again
+  if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[kSpec ? spec_fail_slot<KP>() : KP + KP * KP], (unsigned long long)fallbacks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fwd_fixup: second pass of the speculative forward filter, thread per chunk.  Chunk g > 0 restarts from the stored
+// last row of chunk g - 1 and rewrites its own rows until the new row is parallel to the stored one.  The last row of
+// a chunk is never rewritten (the next chunk reads it in this same pass): a chunk that has not converged before it
+// counts as a failure — except the very last chunk of the sequence, which nobody continues from.
+//   kExact   rows are normalised by their sum (kept rows, log-likelihood), otherwise by a power of two
+//   kLoglik  sums the per-block terms after the repair (partials[blockIdx.x])
+template <int KP, bool kExact, bool kLoglik>
+__global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm) {
+  pdl_enter();
+  constexpr int L = Layout::L, C = Layout::C;
+  static_assert(!kLoglik || kExact, "the log-likelihood needs the forward sums");
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t nchunks = (B + L - 1) / L;
+  const uint64_t rounded = (nchunks + blockDim.x - 1) / blockDim.x * blockDim.x;
+  double ll = 0.0;
+  unsigned fails = 0;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rounded; g += (uint64_t)gridDim.x * blockDim.x) {
+    if (g >= nchunks) continue;
+    const uint64_t tile = g / C;
+    const int c = (int)(g % C);
+    const uint64_t first = g * L;
+    const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+    const bool last_chunk = first + steps == B;
+    const bool have_entry = g > 0;  // (segment mode: chunk 0 of a later rank is repaired by k_fwd_fixup_head)
+    if (have_entry) {
+      const uint64_t pt = c > 0 ? tile : tile - 1;
+      const int pc = c > 0 ? c - 1 : C - 1;
+      double a[KP];
+      const double* ap = buf.alpha + Layout::at(pt, pc, L - 1) * KP;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = ap[j];
+#pragma unroll 1
+      for (int t = 0; t < steps; ++t) {
+        const uint64_t p = Layout::at(tile, c, t);
+        double ev[KP], as[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          ev[j] = buf.e[p * KP + j];
+          as[j] = buf.alpha[p * KP + j];
+        }
+        double f[KP];
+#pragma unroll
+        for (int j = 0; j < KP; ++j) f[j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+#pragma unroll
+          for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
+        }
+        double fs = 0.0, mxv = 0.0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          f[j] *= ev[j];
+          fs += f[j];
+          mxv = fmax(mxv, f[j]);
+        }
+        if (!(fs > 0.0)) {  // FB.hpp:106-111 would reset the filter here: not this pass's business
+          fails++;
+          break;
+        }
+        if (kExact) {
+          const double inv = 1.0 / fs;
+#pragma unroll
+          for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
+        } else {
+          int e2 = exponent_of(mxv);
+          if (e2 < -1000) e2 = -1000;
+          const double sc = pow2i(-e2);
+#pragma unroll
+          for (int j = 0; j < KP; ++j) a[j] = f[j] * sc;
+        }
+        const bool met = rows_parallel<KP>(a, as);
+        if (!met && t + 1 == steps && !last_chunk) {
+          fails++;
+          break;
+        }
+        if (kLoglik) lognorm[p] = buf.maxE[p] + log(fs);  // also at the meeting step: its stored term came from a wrong row
+        if (met) break;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
+      }
+    }
+    if (kLoglik) {
+      for (int t = 0; t < steps; ++t) ll += lognorm[Layout::at(tile, c, t)];
+    }
+  }
+  if (kLoglik) {
+    __shared__ double s_ll[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ll += shfl_xor_double(ll, o);
+    if ((threadIdx.x & 31) == 0) s_ll[threadIdx.x >> 5] = ll;
+    __syncthreads();
+    if (threadIdx.x == 0) buf.partials[blockIdx.x] = s_ll[0] + s_ll[1] + s_ll[2] + s_ll[3];
+  }
+  if (fails) atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], (unsigned long long)fails);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1637,8 +1848,9 @@ __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDe
 // k_fwd_replay: one warp per tile; lane c owns chunk c.  Only the inherently sequential part of the
 // filter runs here: alpha_t = normalise(e_t o (alpha_{t-1} A)), written per block (interleaved order).
 
-template <int KP, bool kLoglik>
-__global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m) {
+//   kSpec: speculative pass (see spec_entry / k_fwd_fixup): no operators, the entering vectors are guesses
+template <int KP, bool kLoglik, bool kSpec = false>
+__global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm = nullptr) {
   pdl_enter();
   constexpr int L = Layout::L, C = Layout::C;
   __shared__ double s_ain[C][KP + 1];
@@ -1650,7 +1862,7 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
   unsigned fallbacks = 0;
   for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---- vector entering each chunk (warp-cooperative walk over the 32 chunk operators)
-    {
+    if constexpr (!kSpec) {
       double a = lane < KP ? buf.tile_ain[tile * KP + lane] : 0.0;
       LaneOp<KP> cur, nxt;
       load_lane_op<KP>(cur, buf.chunk_ops + tile * C * KP * KP, buf.chunk_exp + tile * C * KP, lane);
@@ -1673,8 +1885,14 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
     int steps = 0;
     if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
     double a[KP];
+    if constexpr (kSpec) {
 #pragma unroll
-    for (int j = 0; j < KP; ++j) a[j] = s_ain[c][j];
+      for (int j = 0; j < KP; ++j) a[j] = 0.0;
+      if (steps > 0) spec_entry<KP>(buf, m, tile, c, a);
+    } else {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) a[j] = s_ain[c][j];
+    }
     const double* ep = buf.e + Layout::at(tile, c, 0) * KP;
     double en[KP];
 #pragma unroll
@@ -1710,7 +1928,12 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
         const double inv = 1.0 / fs;
 #pragma unroll
         for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
-        if (kLoglik) ll += mx + log(fs);
+        if (kLoglik) {
+          if (kSpec)
+            lognorm[p] = mx + log(fs);
+          else
+            ll += mx + log(fs);
+        }
       } else {          // FB.hpp:106-111: uniform fallback (the host then re-runs the sweep sequentially)
         fallbacks++;
 #pragma unroll
@@ -1721,14 +1944,14 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
     }
     __syncwarp();
   }
-  if (kLoglik) {
+  if (kLoglik && !kSpec) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ll += shfl_xor_double(ll, o);
     if (lane == 0) buf.partials[blockIdx.x] = ll;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fallbacks += __shfl_xor_sync(0xffffffffu, fallbacks, o);
-  if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[KP + KP * KP], (unsigned long long)fallbacks);
+  if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[kSpec ? spec_fail_slot<KP>() : KP + KP * KP], (unsigned long long)fallbacks);
 }
 
 // Sequential forward recursion (one thread): the exact reference recursion, used only when the
@@ -2211,7 +2434,7 @@ __global__ void k_sum_partials(const double* partials, int n, double* out) {
 
 template <int KP>
 __global__ void k_clear_out(SweepBuffers buf) {
-  const int n = KP + KP * KP + 1;
+  const int n = KP + KP * KP + 2;
   for (int i = threadIdx.x; i < n; i += blockDim.x) buf.out_u64[i] = 0;
   for (int i = threadIdx.x; i < 2 * KP + 1; i += blockDim.x) buf.out_f64[i] = 0.0;
 }
@@ -2497,6 +2720,41 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       k_mix_qend<KP><<<1, 32, 0, s>>>(b);
       launches += 2;
     }
+  } else if (l.speculate && !seg) {
+    // speculative filter: vector recursions from guessed starts, then the repair pass (two kernels, no operators)
+    double* const lognorm = reinterpret_cast<double*>(b.maps);  // per-block scratch until k_bwd_maps writes the maps
+    stage("fwd_spec");
+    const int gr = grid_for(ntiles, 1, l.sms, 32);
+    if constexpr (kPrefix) {
+      using RCfg = ReplayCfg<KP>;
+      if (loglik)
+        launch_k(k_fwd_replay_prefix<KP, true, true, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm);
+      else if (rows)
+        launch_k(k_fwd_replay_prefix<KP, true, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm);
+      else
+        launch_k(k_fwd_replay_prefix<KP, false, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm);
+    } else {
+      if (loglik)
+        launch_k(k_fwd_replay<KP, true, true>, gr, 32, 0, s, b, m, lognorm);
+      else
+        launch_k(k_fwd_replay<KP, false, true>, gr, 32, 0, s, b, m, lognorm);
+    }
+    ++launches;
+    stage("fwd_fixup");
+    const int gf = grid_for(ntiles * Layout::C, 128, l.sms, 8);
+    if (loglik) {
+      launch_k(k_fwd_fixup<KP, true, true>, gf, 128, 0, s, b, m, lognorm);
+      launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gf, b.out_f64 + 2 * KP);
+      ++launches;
+    } else if (rows || !kPrefix) {
+      launch_k(k_fwd_fixup<KP, true, false>, gf, 128, 0, s, b, m, lognorm);
+    } else {
+      launch_k(k_fwd_fixup<KP, false, false>, gf, 128, 0, s, b, m, lognorm);
+    }
+    ++launches;
+    const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
+    if (nbw < 0) return -1;
+    launches += nbw;
   } else {
     stage("fwd_chunks");
     if constexpr (kPrefix) {
@@ -2528,21 +2786,21 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     if constexpr (kPrefix) {
       using RCfg = ReplayCfg<KP>;
       if (loglik) {
-        launch_k(k_fwd_replay_prefix<KP, true, true>, gr, 32, RCfg::kSmem, s, b, m);
+        launch_k(k_fwd_replay_prefix<KP, true, true>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr);
         launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else if (rows) {
-        launch_k(k_fwd_replay_prefix<KP, true, false>, gr, 32, RCfg::kSmem, s, b, m);
+        launch_k(k_fwd_replay_prefix<KP, true, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr);
       } else {
-        launch_k(k_fwd_replay_prefix<KP, false, false>, gr, 32, RCfg::kSmem, s, b, m);
+        launch_k(k_fwd_replay_prefix<KP, false, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr);
       }
     } else {
       if (loglik) {
-        launch_k(k_fwd_replay<KP, true>, gr, 32, 0, s, b, m);
+        launch_k(k_fwd_replay<KP, true>, gr, 32, 0, s, b, m, (double*)nullptr);
         launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else {
-        launch_k(k_fwd_replay<KP, false>, gr, 32, 0, s, b, m);
+        launch_k(k_fwd_replay<KP, false>, gr, 32, 0, s, b, m, (double*)nullptr);
       }
     }
     ++launches;

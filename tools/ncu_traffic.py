@@ -50,7 +50,7 @@ for rec in doc.values():
     rec["ncu_us_per_launch"] = rec.pop("ncu_us") / n
     rec["launches_in_capture"] = n
 # bench.py names the roofline kernel after its stage ("k_" + stage name)
-for alias, kernel in (("k_fwd_chunks", "k_fwd_chunks_prefix"), ("k_fwd_replay", "k_fwd_replay_prefix"),
+for alias, kernel in (("k_fwd_chunks", "k_fwd_chunks_prefix"), ("k_fwd_replay", "k_fwd_replay_prefix"), ("k_fwd_spec", "k_fwd_replay_prefix"),
                       ("k_detect_cand", "k_cand_count"), ("k_detect_scatter", "k_cand_scatter")):
     if kernel in doc and alias not in doc:
         doc[alias] = dict(doc[kernel], alias_of=kernel)
