@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -166,6 +167,10 @@ struct hml_ctx {
   int forward_mode = HML_FORWARD_AUTO;
   uint64_t spec_sweeps = 0, spec_failures = 0;
   uint32_t spec_skip = 0, spec_streak = 0;  // sweeps still to run through the operator scan / failures in a row
+  int spec_warm = kSpecWarmMin;             // warm-up blocks of the guesses: x4 after a failure, halved after 64 good sweeps
+  uint32_t spec_good = 0;
+  // HML_HOST_TIMING=1: where the host thread spends a sweep (printed when the handle is destroyed)
+  uint64_t host_ns_prepare = 0, host_ns_launch = 0, host_ns_wait = 0, host_sweeps = 0;
   unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
   unsigned long long* outblk_host = nullptr;  // pinned mirror
 
@@ -1201,6 +1206,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
       h->last_K = mh.K;
       return HML_OK;
     }
+    const auto hc0 = std::chrono::steady_clock::now();
     bool gather = !h->stats_valid;
     if (dynamic) {
       rc = run_detect(h, thr);
@@ -1235,23 +1241,43 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     // the speculative forward filter: single handle, forward-backward sweeps; after a failure the operator scan takes
     // the next sweeps (1, 2, 4, ... up to 64 after failures in a row), so data on which the filter does not forget its
     // start pays the wasted pass rarely
-    l.speculate = !mixture && !seg && h->forward_mode != HML_FORWARD_OPERATORS &&
+    // (segment mode: every rank takes the same decision — the failure counter arrives summed over the ranks)
+    const bool spec_ok = !mixture && !(seg && (flags & HML_SWEEP_LOGLIK));
+    l.speculate = spec_ok && h->forward_mode != HML_FORWARD_OPERATORS &&
                   (h->forward_mode == HML_FORWARD_SPECULATIVE || h->spec_skip == 0);
-    if (!l.speculate && h->spec_skip > 0 && !mixture && !seg) h->spec_skip--;
+    if (!l.speculate && h->spec_skip > 0 && spec_ok) h->spec_skip--;
+    l.spec_warm = h->spec_warm;
+    const auto hc1 = std::chrono::steady_clock::now();
     int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
     if (n == -2) return fail(h, HML_ERR_ARG, "unsupported number of states");
     if (n < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
     h->launches += n;
     CK(cudaGetLastError());
+    const auto hc2 = std::chrono::steady_clock::now();
     SweepResult res;
     rc = fetch_result(h, KP, res, fused_stats);
     if (rc != HML_OK) return rc;
+    {
+      const auto hc3 = std::chrono::steady_clock::now();
+      using ns = std::chrono::nanoseconds;
+      h->host_ns_prepare += std::chrono::duration_cast<ns>(hc1 - hc0).count();
+      h->host_ns_launch += std::chrono::duration_cast<ns>(hc2 - hc1).count();
+      h->host_ns_wait += std::chrono::duration_cast<ns>(hc3 - hc2).count();
+      h->host_sweeps++;
+    }
     if (l.speculate && !(dynamic && res.any_overflow)) {
       h->spec_sweeps++;
       if (res.o64[KP + KP * KP + 1] > 0) {  // some chunk's rows did not meet the guess's: the exact operator scan
+        // first remedy: longer warm-ups (the filter forgets, but not within a chunk); once they are as long as they
+        // get, the operator scan takes the next 1, 3, 7, ... 63 sweeps
         h->spec_failures++;
-        h->spec_streak = h->spec_streak < 6 ? h->spec_streak + 1 : 6;
-        h->spec_skip = (1u << h->spec_streak) - 1;
+        h->spec_good = 0;
+        if (h->spec_warm < kSpecWarmMax) {
+          h->spec_warm = h->spec_warm * 4 < kSpecWarmMax ? h->spec_warm * 4 : kSpecWarmMax;
+        } else {
+          h->spec_streak = h->spec_streak < 6 ? h->spec_streak + 1 : 6;
+          h->spec_skip = (1u << h->spec_streak) - 1;
+        }
         l.speculate = false;
         l.gather = false;  // the block sums of this block list are in place
         l.nblocks_hint = res.local_blocks;
@@ -1265,6 +1291,10 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
         if (rc != HML_OK) return rc;
       } else {
         h->spec_streak = 0;
+        if (++h->spec_good >= 64 && h->spec_warm > kSpecWarmMin) {
+          h->spec_warm /= 2;
+          h->spec_good = 0;
+        }
       }
     }
     if (dynamic && res.any_overflow) {  // some rank's block arrays were too small: grow and run the sweep again
@@ -1486,6 +1516,12 @@ int hml_destroy(hml_t* h) {
   if (!h) return HML_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->host_sweeps && getenv("HML_HOST_TIMING")) {
+    const double n = (double)h->host_sweeps;
+    fprintf(stderr, "[hml host timing] rank %d: %llu sweeps; per sweep: detection launches %.1f us, sweep launches %.1f us, "
+                    "waiting for the result %.1f us\n", h->rank, (unsigned long long)h->host_sweeps,
+            h->host_ns_prepare / n * 1e-3, h->host_ns_launch / n * 1e-3, h->host_ns_wait / n * 1e-3);
+  }
   dev_free(h->w);
   dev_free(h->smax);
   dev_free(h->coeffs);
@@ -2590,7 +2626,8 @@ int hml_set_forward_mode(hml_t* h, int mode) {
   if (mode != HML_FORWARD_AUTO && mode != HML_FORWARD_OPERATORS && mode != HML_FORWARD_SPECULATIVE)
     return fail(h, HML_ERR_ARG, "unknown forward mode");
   h->forward_mode = mode;
-  h->spec_skip = h->spec_streak = 0;
+  h->spec_skip = h->spec_streak = h->spec_good = 0;
+  h->spec_warm = kSpecWarmMin;
   return HML_OK;
 }
 

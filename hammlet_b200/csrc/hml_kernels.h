@@ -232,7 +232,9 @@ struct SweepLaunch {
   void* exchange_user;
   uint32_t stats_words;  // 8-byte words of the result block travelling in the statistics exchange (0: not fused)
   bool speculate;        // forward filter by guessed chunk starts + repair pass (result word KP + KP*KP + 1 counts failures)
+  int spec_warm;         // blocks in front of a chunk its guess is pushed through
 };
+constexpr int kSpecWarmMin = 4, kSpecWarmMax = 128;
 enum { kExchangeHeads = 0, kExchangeOps = 1, kExchangeMaps = 2, kExchangeStats = 3 };
 // segment mode: head partial of this rank -> seg.send_head (to be all-gathered before the block statistics)
 // seq != 0: the kernel also runs the head exchange itself (seg.p2p != null)

@@ -1073,15 +1073,11 @@ __global__ void __launch_bounds__(FwdCfg<KP>::THREADS, (KP <= 5 ? 4 : (KP <= 6 ?
 // Speculative forward pass (rank convergence).  The filter forgets where it started: two runs of the recursion
 // alpha_t = normalise(e_t o (alpha_{t-1} A)) from different vectors become parallel after a few informative blocks.
 // So instead of products of K x K chunk operators (2 K^3 flop per block) every chunk runs the VECTOR recursion
-// (2 K^2) from a guess — uniform, pushed through the last kSpecWarm blocks of the chunk before it — and a second
+// (2 K^2) from a guess — uniform, pushed through the `warm` blocks in front of the chunk — and a second
 // pass repairs the first rows of every chunk from the (by then known) last row of its predecessor until the repaired
 // row is parallel to the stored one; the rest of the chunk is then right as it stands.  A chunk whose rows have not
 // met by its last block reports a failure and the host runs the sweep again through the operator scan, which needs
 // no such assumption.  (ForwardBackward.hpp:64-125 is one sequential loop; SURVEY.md §7 "rank-1 collapse".)
-template <int KP>
-struct SpecCfg {
-  static constexpr int kWarm = KP <= 8 ? 4 : 8;  // warm-up blocks before a chunk
-};
 constexpr double kSpecTol = 1e-13;  // relative agreement of every component of two rows that count as parallel
 
 // index of the result slot that counts chunks whose repair did not converge (the pad word after the fallbacks)
@@ -1090,39 +1086,47 @@ __device__ __forceinline__ int spec_fail_slot() {
   return KP + KP * KP + 1;
 }
 
-// the guess for the vector entering chunk (tile, c): pi for the very first chunk, otherwise uniform pushed through
-// the last kWarm blocks of the previous chunk (rescaled by exact powers of two; a vanished vector restarts uniform)
+// the guess for the vector entering chunk (tile, c): uniform pushed through the `warm` blocks in front of the chunk
+// (rescaled by exact powers of two; a vanished vector restarts uniform).  A chunk with fewer than `warm` blocks in
+// front of it starts from pi at block 0, i.e. exactly; the first chunk of a later rank of a split sequence has no
+// blocks in front of it on this device and starts uniform (k_fwd_fixup_head repairs it).
 template <int KP>
-__device__ __forceinline__ void spec_entry(const SweepBuffers& buf, const ModelDev<KP>& m, uint64_t tile, int c,
+__device__ __forceinline__ void spec_entry(const SweepBuffers& buf, const ModelDev<KP>& m, uint64_t tile, int c, int warm,
                                            double (&a)[KP]) {
-  constexpr int L = Layout::L, C = Layout::C, W = SpecCfg<KP>::kWarm;
+  constexpr int L = Layout::L, C = Layout::C;
   const int K = m.K;
-  if (tile == 0 && c == 0) {
+  const uint64_t first = (tile * C + (uint64_t)c) * L;  // block index of the chunk's first block
+  uint64_t b0 = first;                                  // first warm-up block
+  if (first <= (uint64_t)warm) {
+    b0 = 0;
     if (buf.seg.world > 1 && buf.seg.rank > 0) {
 #pragma unroll
-      for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 / (double)K : 0.0;  // repaired from the previous rank's last row
+      for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 : 0.0;
     } else {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = m.pi[j];
     }
-    return;
+  } else {
+    b0 = first - (uint64_t)warm;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 : 0.0;
   }
-  const uint64_t pt = c > 0 ? tile : tile - 1;
-  const int pc = c > 0 ? c - 1 : C - 1;
-  const double* ep = buf.e + Layout::at(pt, pc, L - W) * KP;
+  if (b0 == first) return;
   double en[KP];  // emission terms one step ahead of their use
+  {
+    const double* ep = buf.e + Layout::perm(b0) * KP;
 #pragma unroll
-  for (int j = 0; j < KP; ++j) en[j] = ep[j];
-#pragma unroll
-  for (int j = 0; j < KP; ++j) a[j] = (j < K) ? 1.0 : 0.0;
+    for (int j = 0; j < KP; ++j) en[j] = ep[j];
+  }
 #pragma unroll 1
-  for (int t = 0; t < W; ++t) {
+  for (uint64_t b = b0; b < first; ++b) {
     double ev[KP];
 #pragma unroll
     for (int j = 0; j < KP; ++j) ev[j] = en[j];
-    if (t + 1 < W) {
+    if (b + 1 < first) {
+      const double* ep = buf.e + Layout::perm(b + 1) * KP;
 #pragma unroll
-      for (int j = 0; j < KP; ++j) en[j] = ep[(uint64_t)(t + 1) * C * KP + j];
+      for (int j = 0; j < KP; ++j) en[j] = ep[j];
     }
     double f[KP];
 #pragma unroll
@@ -1188,7 +1192,7 @@ struct ReplayCfg {
 //   kSpec    speculative pass: the vector entering the chunk is a guess (spec_entry), k_fwd_fixup repairs the rows;
 //            the log-likelihood terms go to `lognorm` per block and are summed after the repair
 template <int KP, bool kExact, bool kLoglik, bool kSpec = false>
-__global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm = nullptr) {
+__global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm, int warm) {
   pdl_enter();
   using Cfg = ReplayCfg<KP>;
   constexpr int L = Layout::L, C = Layout::C, S = Cfg::kSlab, NS = L / S;
@@ -1230,7 +1234,7 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
     if constexpr (kSpec) {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = 0.0;
-      if (steps > 0) spec_entry<KP>(buf, m, tile, c, a);
+      if (steps > 0) spec_entry<KP>(buf, m, tile, c, warm, a);
     } else {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = buf.tile_ain[tile * KP + j];
@@ -1424,6 +1428,87 @@ __global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP
     if (threadIdx.x == 0) buf.partials[blockIdx.x] = s_ll[0] + s_ll[1] + s_ll[2] + s_ll[3];
   }
   if (fails) atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], (unsigned long long)fails);
+}
+
+// k_fwd_fixup_head (segment mode): what k_fwd_fixup cannot do for chunk 0 of a later rank.  Every rank publishes the
+// last row it holds (+ its block count; all-gather of KP + 1 words, inside this kernel when the peer mailboxes are up),
+// then restarts its first chunk from the last row of the nearest earlier rank that owns blocks.  The published row is
+// right if the rank's own chunk 0 meets its guess before its last block (nothing behind chunk 0 then depended on the
+// guess); a rank with a single chunk cannot promise that and reports a failure.
+//   phase 1: publish only (the caller runs the all-gather), 2: repair only, 3: publish + embedded exchange + repair
+template <int KP, bool kExact>
+__global__ void __launch_bounds__(256) k_fwd_fixup_head(SweepBuffers buf, ModelDev<KP> m, int phase, int stride,
+                                                        unsigned long long seq) {
+  pdl_enter();
+  constexpr int L = Layout::L;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  if (phase & 1) {
+    if (threadIdx.x == 0) {
+      const double* last = buf.alpha + (B ? Layout::perm(B - 1) : 0) * KP;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) buf.seg.send_op[j] = B ? last[j] : 0.0;
+      buf.seg.send_op[KP] = (double)B;
+    }
+    if (phase == 1) return;
+    __threadfence();
+    __syncthreads();
+    p2p_exchange_cta(buf.seg.p2p, kSlotOps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_op), (uint32_t)(KP + 1),
+                     reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.ops)));
+  }
+  if (threadIdx.x != 0 || buf.seg.rank == 0 || B == 0) return;
+  int src = buf.seg.rank - 1;
+  while (src > 0 && !(__ldcg(buf.seg.ops + (size_t)src * stride + KP) > 0.0)) --src;  // rank 0 always owns block 0
+  if (B <= (uint64_t)L) {  // one chunk: the row this rank published came straight from the guess
+    atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], 1ull);
+    return;
+  }
+  double a[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) a[j] = __ldcg(buf.seg.ops + (size_t)src * stride + j);
+#pragma unroll 1
+  for (int t = 0; t < L; ++t) {
+    const uint64_t p = Layout::at(0, 0, t);
+    double f[KP], as[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      f[j] = 0.0;
+      as[j] = buf.alpha[p * KP + j];
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
+    }
+    double fs = 0.0, mxv = 0.0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      f[j] *= buf.e[p * KP + j];
+      fs += f[j];
+      mxv = fmax(mxv, f[j]);
+    }
+    bool met = false;
+    if (fs > 0.0) {
+      if (kExact) {
+        const double inv = 1.0 / fs;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
+      } else {
+        int e2 = exponent_of(mxv);
+        if (e2 < -1000) e2 = -1000;
+        const double sc = pow2i(-e2);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) a[j] = f[j] * sc;
+      }
+      met = rows_parallel<KP>(a, as);
+    }
+    if (!(fs > 0.0) || (!met && t + 1 == L)) {
+      atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], 1ull);
+      return;
+    }
+    if (met) return;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1850,7 +1935,7 @@ __global__ void __launch_bounds__(1024) k_fwd_tilescan(SweepBuffers buf, ModelDe
 
 //   kSpec: speculative pass (see spec_entry / k_fwd_fixup): no operators, the entering vectors are guesses
 template <int KP, bool kLoglik, bool kSpec = false>
-__global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm = nullptr) {
+__global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm, int warm) {
   pdl_enter();
   constexpr int L = Layout::L, C = Layout::C;
   __shared__ double s_ain[C][KP + 1];
@@ -1888,7 +1973,7 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
     if constexpr (kSpec) {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = 0.0;
-      if (steps > 0) spec_entry<KP>(buf, m, tile, c, a);
+      if (steps > 0) spec_entry<KP>(buf, m, tile, c, warm, a);
     } else {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = s_ain[c][j];
@@ -2720,7 +2805,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       k_mix_qend<KP><<<1, 32, 0, s>>>(b);
       launches += 2;
     }
-  } else if (l.speculate && !seg) {
+  } else if (l.speculate && !(seg && loglik)) {
     // speculative filter: vector recursions from guessed starts, then the repair pass (two kernels, no operators)
     double* const lognorm = reinterpret_cast<double*>(b.maps);  // per-block scratch until k_bwd_maps writes the maps
     stage("fwd_spec");
@@ -2728,16 +2813,16 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     if constexpr (kPrefix) {
       using RCfg = ReplayCfg<KP>;
       if (loglik)
-        launch_k(k_fwd_replay_prefix<KP, true, true, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm);
+        launch_k(k_fwd_replay_prefix<KP, true, true, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm);
       else if (rows)
-        launch_k(k_fwd_replay_prefix<KP, true, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm);
+        launch_k(k_fwd_replay_prefix<KP, true, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm);
       else
-        launch_k(k_fwd_replay_prefix<KP, false, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm);
+        launch_k(k_fwd_replay_prefix<KP, false, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm);
     } else {
       if (loglik)
-        launch_k(k_fwd_replay<KP, true, true>, gr, 32, 0, s, b, m, lognorm);
+        launch_k(k_fwd_replay<KP, true, true>, gr, 32, 0, s, b, m, lognorm, (int)l.spec_warm);
       else
-        launch_k(k_fwd_replay<KP, false, true>, gr, 32, 0, s, b, m, lognorm);
+        launch_k(k_fwd_replay<KP, false, true>, gr, 32, 0, s, b, m, lognorm, (int)l.spec_warm);
     }
     ++launches;
     stage("fwd_fixup");
@@ -2752,6 +2837,21 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       launch_k(k_fwd_fixup<KP, false, false>, gf, 128, 0, s, b, m, lognorm);
     }
     ++launches;
+    if (seg) {  // chunk 0 of the later ranks, from the last row of the rank before
+      stage("fwd_fixup_head");
+      constexpr bool kEx = !kPrefix;
+      if (b.seg.p2p != nullptr) {
+        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)3, (int)(KP + 1), l.next_seq(l.exchange_user, kExchangeOps));
+        ++launches;
+      } else {
+        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)1, (int)(KP * KP + KP), 0ull);
+        stage("exchange_ops");
+        if (l.exchange(l.exchange_user, kExchangeOps) != 0) return -1;
+        stage("fwd_fixup_head2");
+        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)2, (int)(KP * KP + KP), 0ull);
+        launches += 2;
+      }
+    }
     const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
     if (nbw < 0) return -1;
     launches += nbw;
@@ -2786,21 +2886,21 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     if constexpr (kPrefix) {
       using RCfg = ReplayCfg<KP>;
       if (loglik) {
-        launch_k(k_fwd_replay_prefix<KP, true, true>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr);
+        launch_k(k_fwd_replay_prefix<KP, true, true>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0);
         launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else if (rows) {
-        launch_k(k_fwd_replay_prefix<KP, true, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr);
+        launch_k(k_fwd_replay_prefix<KP, true, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0);
       } else {
-        launch_k(k_fwd_replay_prefix<KP, false, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr);
+        launch_k(k_fwd_replay_prefix<KP, false, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0);
       }
     } else {
       if (loglik) {
-        launch_k(k_fwd_replay<KP, true>, gr, 32, 0, s, b, m, (double*)nullptr);
+        launch_k(k_fwd_replay<KP, true>, gr, 32, 0, s, b, m, (double*)nullptr, (int)0);
         launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else {
-        launch_k(k_fwd_replay<KP, false>, gr, 32, 0, s, b, m, (double*)nullptr);
+        launch_k(k_fwd_replay<KP, false>, gr, 32, 0, s, b, m, (double*)nullptr, (int)0);
       }
     }
     ++launches;

@@ -98,18 +98,23 @@ int hml_create_blocks(hml_t* h, float threshold, uint64_t* nblocks);
 enum { HML_DETECT_STREAM = 0, HML_DETECT_PYRAMID = 1, HML_DETECT_CANDIDATES = 2 };
 int hml_set_detect_mode(hml_t* h, int mode);
 int hml_detect_info(hml_t* h, int* mode, uint64_t* hot_subblocks);
-/* How the forward filter (ForwardBackward.hpp:64-125) of a sweep is parallelised on a single handle.
+/* How the forward filter (ForwardBackward.hpp:64-125) of a sweep is parallelised.
  *   HML_FORWARD_OPERATORS    scan of K x K operators over chunks, tiles and the sequence: exact for any data, 2 K^3 flop
  *                            per block.
  *   HML_FORWARD_SPECULATIVE  every chunk of 32 blocks runs the reference's vector recursion (2 K^2 flop per block) from
- *                            a guessed start (uniform pushed through the blocks just before the chunk); a second pass
+ *                            a guessed start (uniform pushed through the blocks in front of the chunk); a second pass
  *                            restarts every chunk from the last row of its predecessor and rewrites rows until the new
  *                            row is parallel to the stored one (every component within 1e-13 relative).  If a chunk has
  *                            not met its guess by its last block the sweep is run again through the operator scan, so
  *                            the result never depends on the assumption that the filter forgets its start.
- *   HML_FORWARD_AUTO (default) speculative; after a failure the operator scan takes the next 1, 3, 7, ... 63 sweeps.
- * Segment mode, mixture sweeps and the fused kernel use the operator scan.  hml_forward_info: the mode, the number of
- * speculative sweeps so far and how many of them had to be repeated. */
+ *   HML_FORWARD_AUTO (default) speculative.  A failed sweep is repeated through the operator scan and the following
+ *                            sweeps push their guesses through more blocks (4, 16, 64, 128; halved again after 64 good
+ *                            sweeps); if 128 are not enough either the operator scan takes the next 1, 3, 7, ... 63
+ *                            sweeps before the next attempt.
+ * A split sequence speculates too (the first chunk of a rank is repaired from the last row of the rank before: one
+ * all-gather of K + 1 words instead of the K x K segment operators), except when the log-likelihood is asked for.
+ * Mixture sweeps have no forward filter; the fused kernel uses the operator scan.  hml_forward_info: the mode, the
+ * number of speculative sweeps so far and how many of them had to be repeated. */
 enum { HML_FORWARD_AUTO = 0, HML_FORWARD_OPERATORS = 1, HML_FORWARD_SPECULATIVE = 2 };
 int hml_set_forward_mode(hml_t* h, int mode);
 int hml_forward_info(hml_t* h, int* mode, uint64_t* speculative_sweeps, uint64_t* failures);

@@ -113,6 +113,15 @@ def main():
         local_states_match(h, ref)
         runs_match(h, ref, f"case {ci} replay")
 
+        # ---- the same sweep with the forward filter forced either way (speculative: chunk 0 of the later ranks is repaired
+        # from the last row of the rank before, one all-gather of K + 1 words; a rank with a single chunk falls back)
+        for mode in (capi.FORWARD_SPECULATIVE, capi.FORWARD_OPERATORS):
+            h.set_forward_mode(mode)
+            o = h.fb_sweep(mu, var, A, pi, use_self=use_self, replay=u)
+            check_same(o, r, f"case {ci} replay, forward mode {mode}")
+            local_states_match(h, ref)
+        h.set_forward_mode(capi.FORWARD_AUTO)
+
         # ---- mixture sweep, static structure, Philox
         o = h.mix_sweep(mu, var, A, pi, seed=5, sweep=3)
         r = ref.mix_sweep(mu, var, A, pi, seed=5, sweep=3)
@@ -200,6 +209,8 @@ def main():
     if rank == 0:
         print("capacity growth ok", flush=True)
 
+    if rank == 0:
+        print("forward filter (mode, speculative sweeps, repeated):", h.forward_info(), flush=True)
     h.close()
     ref.close()
     dist.barrier()
