@@ -136,6 +136,7 @@ struct hml_ctx {
   int last_K = 0;
   double *e = nullptr, *maxE = nullptr, *alpha = nullptr;
   uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *tile_maps = nullptr, *tile_qin = nullptr;
+  unsigned* tickets = nullptr;
   double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr, *group_ain = nullptr;
   int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr, *wide_exp = nullptr;
   double* wide_ops = nullptr;  // K > 8: scratch of k_fwd_chunks_wide
@@ -354,6 +355,7 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.chunk_maps = h->chunk_maps;
   b.tile_maps = h->tile_maps;
   b.tile_qin = h->tile_qin;
+  b.tickets = h->tickets;
   b.tile_ops = h->tile_ops;
   b.tile_exp = h->tile_exp;
   b.tile_ain = h->tile_ain;
@@ -522,7 +524,7 @@ int ensure_candidates(hml_t* h, float thr, bool* usable) {
 }
 
 int run_detect(hml_t* h, float thr) {
-  bool done = false;
+  bool done = false, head_done = false;
   // the block structure is being overwritten: whatever the previous sweep left (states, runs, rows) no longer
   // belongs to it, also if this sweep fails half-way
   h->states_valid = h->segs_valid = h->g_valid = h->rows_valid = false;
@@ -532,11 +534,17 @@ int run_detect(hml_t* h, float thr) {
     int rc = ensure_candidates(h, thr, &usable);
     if (rc != HML_OK) return rc;
     if (usable) {
+      // split sequence over peer mailboxes: the scatter's last CTA forms the head partial and exchanges the heads
+      SweepBuffers hb;
+      const bool with_head = h->world > 1 && h->p2p;
+      if (with_head) hb = make_buffers(h, h->KP ? h->KP : 2);
       h->launches += launch_detect_candidates(h->cand_w, h->cand_pos, h->cand_pq, (uint32_t)h->cand_n, thr, h->cand_scratch,
                                               h->cand_scratch_ctas, h->starts, h->spq, h->pq, h->capacity, h->T, h->outblk,
-                                              h->stream, stage_cb, h);
+                                              h->stream, stage_cb, h, with_head ? &hb : nullptr,
+                                              with_head ? ++h->p2p_seq[kSlotHeads] : 0ull);
       h->spq_valid = h->cand_pq != nullptr;
       done = true;
+      head_done = with_head;
     }
   }
   if (!done) h->spq_valid = false;
@@ -546,7 +554,7 @@ int run_detect(hml_t* h, float thr) {
                                  stage_cb, h);
   }
   CK(cudaGetLastError());
-  if (h->world > 1) {
+  if (h->world > 1 && !head_done) {
     // the partial block in front of each rank's first boundary joins the last block of its owner
     stage_cb(h, "seg_head");
     launch_seg_head(make_buffers(h, h->KP ? h->KP : 2), h->T, h->p2p ? ++h->p2p_seq[kSlotHeads] : 0ull, h->stream);
@@ -1272,8 +1280,8 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
         // get, the operator scan takes the next 1, 3, 7, ... 63 sweeps
         h->spec_failures++;
         h->spec_good = 0;
-        if (h->spec_warm < kSpecWarmMax) {
-          h->spec_warm = h->spec_warm * 4 < kSpecWarmMax ? h->spec_warm * 4 : kSpecWarmMax;
+        if (h->spec_warm < spec_warm_max(KP)) {
+          h->spec_warm = h->spec_warm * 4 < spec_warm_max(KP) ? h->spec_warm * 4 : spec_warm_max(KP);
         } else {
           h->spec_streak = h->spec_streak < 6 ? h->spec_streak + 1 : 6;
           h->spec_skip = (1u << h->spec_streak) - 1;
@@ -1508,6 +1516,12 @@ int hml_create(hml_t** out, int device) {
     return HML_ERR_CUDA;
   }
   cudaMemset(h->outblk, 0, kOutWords * 8);
+  if (cudaMalloc((void**)&h->tickets, kTickets * sizeof(unsigned)) != cudaSuccess) {
+    g_create_error = "allocation of the arrival counters failed";
+    hml_destroy(h);
+    return HML_ERR_CUDA;
+  }
+  cudaMemset(h->tickets, 0, kTickets * sizeof(unsigned));
   *out = h;
   return HML_OK;
 }
@@ -1539,6 +1553,7 @@ int hml_destroy(hml_t* h) {
   dev_free(h->chunk_maps);
   dev_free(h->tile_maps);
   dev_free(h->tile_qin);
+  dev_free(h->tickets);
   dev_free(h->chunk_ops);
   dev_free(h->tile_ops);
   dev_free(h->tile_ain);

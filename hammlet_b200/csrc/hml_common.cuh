@@ -52,6 +52,25 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Called by all threads of every CTA of a grid when the CTA's part of a step is written: true in the one CTA that
+// arrives last, which can then finish the step (a scan, a final sum, an exchange) in the same launch instead of a
+// follow-up kernel.  What the other CTAs wrote before the call is visible to it through L2 (__ldcg).  The counter is
+// back at zero when the kernel ends.
+__device__ __forceinline__ bool last_cta_arrives(unsigned* ticket) {
+  __shared__ int s_last_cta;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last_cta = (t == gridDim.x - 1u) ? 1 : 0;
+    if (s_last_cta) *ticket = 0u;
+  }
+  __syncthreads();
+  const bool last = s_last_cta != 0;
+  if (last) __threadfence();
+  return last;
+}
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;

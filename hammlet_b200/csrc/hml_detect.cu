@@ -29,6 +29,7 @@
 // drops from 4 T bytes to T/16 + 128 * (hot sub-blocks).
 #include "hml_common.cuh"
 #include "hml_kernels.h"
+#include "hml_seg_head.cuh"
 
 namespace hml {
 
@@ -557,10 +558,14 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// kHead (split sequence, peer mailboxes): the CTA that arrives last also forms the head partial of the rank's segment
+// and runs the head exchange (seg_head_cta) — the block list is complete at that point — instead of a kernel of its own
+template <bool kHead>
 __global__ void __launch_bounds__(256)
     k_cand_scatter(const float4* __restrict__ cw4, const uint32_t* __restrict__ cpos, uint32_t nc, float thr,
                    const uint32_t* __restrict__ cta_off, uint32_t* __restrict__ starts, uint64_t capacity,
-                   const double2* __restrict__ cand_pq, double2* __restrict__ spq) {
+                   const double2* __restrict__ cand_pq, double2* __restrict__ spq, SweepBuffers head, uint32_t seg_len,
+                   unsigned long long seq) {
   pdl_enter();
   __shared__ uint32_t s_warp[8];
   __shared__ uint16_t s_rank[kCandPerCta];  // rank of every candidate of the CTA among its boundaries, 0xffff: none
@@ -615,6 +620,9 @@ __global__ void __launch_bounds__(256)
       if (spq) spq[off + r] = cand_pq[base + li];
     }
   }
+  if constexpr (kHead) {
+    if (last_cta_arrives(head.tickets + kTicketScatter)) seg_head_cta(head, seg_len, seq);
+  }
 }
 
 void launch_cand_gather(const float* w, const double2* pq, const uint32_t* starts, uint32_t n, float* cand_w,
@@ -630,7 +638,7 @@ void launch_cand_gather(const float* w, const double2* pq, const uint32_t* start
 int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, const double2* cand_pq, uint32_t nc, float thr,
                              uint32_t* cta_scratch, uint32_t scratch_ctas, uint32_t* starts, double2* spq, const double2* pq,
                              uint64_t capacity, uint64_t T, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
-                             void* user) {
+                             void* user, const SweepBuffers* head, unsigned long long head_seq) {
   if (!cand_pq) spq = nullptr;
   const uint32_t ctas = (nc + kCandPerCta - 1) / kCandPerCta;
   uint32_t* cta_count = cta_scratch;
@@ -640,8 +648,15 @@ int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, cons
   launch_k(k_cand_count, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), nc, thr, ctas, cta_count, cta_off, ticket,
            nblocks_out, starts, capacity, T, pq, spq);
   if (cb) cb(user, "detect_scatter");
-  launch_k(k_cand_scatter, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), cand_pos, nc, thr,
-           (const uint32_t*)cta_off, starts, capacity, cand_pq, spq);
+  if (head != nullptr && head->tickets != nullptr) {
+    launch_k(k_cand_scatter<true>, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), cand_pos, nc, thr,
+             (const uint32_t*)cta_off, starts, capacity, cand_pq, spq, *head, (uint32_t)T, head_seq);
+  } else {
+    SweepBuffers none;
+    memset(&none, 0, sizeof(none));
+    launch_k(k_cand_scatter<false>, ctas, 256, 0, s, reinterpret_cast<const float4*>(cand_w), cand_pos, nc, thr,
+             (const uint32_t*)cta_off, starts, capacity, cand_pq, spq, none, (uint32_t)0, 0ull);
+  }
   return 2;
 }
 uint32_t cand_ctas(uint32_t nc) { return (nc + kCandPerCta - 1) / kCandPerCta; }

@@ -41,7 +41,9 @@ uint32_t cand_ctas(uint32_t nc);
 int launch_detect_candidates(const float* cand_w, const uint32_t* cand_pos, const double2* cand_pq, uint32_t nc, float thr,
                              uint32_t* cta_scratch, uint32_t scratch_ctas, uint32_t* starts, double2* spq, const double2* pq,
                              uint64_t capacity, uint64_t T, unsigned long long* nblocks_out, cudaStream_t s, stage_cb_t cb,
-                             void* user);
+                             void* user, const struct SweepBuffers* head, unsigned long long head_seq);
+// head != null (split sequence with peer mailboxes): the scatter's last CTA also forms the head partial of the rank's
+// segment and runs the head exchange number head_seq (what launch_seg_head does as a kernel of its own)
 size_t pyramid_entries(uint64_t T);  // bf16 entries, one per 32 weights, padded to whole spans
 void launch_build_pyramid(const float* w, uint64_t T, uint16_t* smax, int sms, cudaStream_t s);
 const unsigned long long* detect_hot_count_ptr(const void* scratch, uint64_t T);
@@ -130,6 +132,7 @@ struct SweepBuffers {
   uint8_t* chunk_maps;      // per chunk KPB: composed map of the LATER chunks of the same tile
   uint8_t* tile_maps;       // per tile KPB: composed map of the tile
   uint8_t* tile_qin;        // per tile: state of the block following the tile
+  unsigned* tickets;        // kTickets arrival counters (zero between launches): the CTA that arrives last finishes the step
   double* tile_ops;         // per tile KP*KP
   int* tile_exp;            // per tile KP
   double* tile_ain;         // per tile KP: normalised forward vector entering the tile
@@ -234,7 +237,10 @@ struct SweepLaunch {
   bool speculate;        // forward filter by guessed chunk starts + repair pass (result word KP + KP*KP + 1 counts failures)
   int spec_warm;         // blocks in front of a chunk its guess is pushed through
 };
-constexpr int kSpecWarmMin = 4, kSpecWarmMax = 128;
+// warm-up lengths: 4, 16, 64 (and 128 for K > 8); longer ones cost more than the operator scan they replace
+constexpr int kSpecWarmMin = 4;
+inline int spec_warm_max(int KP) { return KP <= 8 ? 64 : 128; }
+enum { kTicketScatter = 0, kTicketFixup = 1, kTicketChunkMaps = 2, kTicketReduce = 3, kTickets = 8 };
 enum { kExchangeHeads = 0, kExchangeOps = 1, kExchangeMaps = 2, kExchangeStats = 3 };
 // segment mode: head partial of this rank -> seg.send_head (to be all-gathered before the block statistics)
 // seq != 0: the kernel also runs the head exchange itself (seg.p2p != null)

@@ -10,6 +10,7 @@
 #include "hml_common.cuh"
 #include "hml_kernels.h"
 #include "hml_p2p.cuh"
+#include "hml_seg_head.cuh"
 
 namespace hml {
 
@@ -280,6 +281,14 @@ struct Map {
     for (int i = 0; i < W; ++i) m.w[i] = q[i];
     return m;
   }
+  // through L2: the map was written by another CTA of the running kernel
+  __device__ __forceinline__ static Map load_cg(const uint8_t* p) {
+    Map m;
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(p);
+#pragma unroll
+    for (int i = 0; i < W; ++i) m.w[i] = __ldcg(q + i);
+    return m;
+  }
 };
 
 // std::discrete_distribution rule (libstdc++ bits/random.tcc, used by Trellis.hpp:61-66 and
@@ -414,47 +423,12 @@ __device__ __forceinline__ void range_sums(const SweepBuffers& buf, uint32_t s, 
   }
 }
 
-// the same for data dimension d of multivariate input (per-dimension planes of the integral arrays)
-__device__ __forceinline__ void range_sums_dim(const SweepBuffers& buf, int d, uint32_t s, uint32_t e, double& sx,
-                                               double& sq) {
-  const double2* pq = buf.pq + (size_t)d * buf.pq_stride;
-  const double2 ps = pq[s], pe = pq[e];
-  sx = pe.x - ps.x;
-  sq = pe.y - ps.y;
-  const uint32_t cs = s >> kCellLog2, ce = e >> kCellLog2;
-  if (cs != ce) {
-    const double4* cp = buf.cell_pref + (size_t)d * buf.cell_stride;
-    const double4 a = cp[cs], z = cp[ce];
-    sx += (z.x - a.x) + (z.y - a.y);
-    sq += (z.z - a.z) + (z.w - a.w);
-  }
-}
+// (range_sums_dim and the head of a rank's segment: hml_seg_head.cuh)
 
-// k_seg_head: the observations in front of this rank's first boundary belong to a block that starts on
-// an earlier rank; their partial statistics travel with the rank's block count.
-// seq != 0: the head exchange runs inside this kernel (peer mailboxes), else the caller exchanges afterwards.
+// k_seg_head: the head partial as a kernel of its own (the candidate scatter does it in its last CTA when it can)
 static __global__ void __launch_bounds__(256) k_seg_head(SweepBuffers buf, uint32_t seg_len, unsigned long long seq) {
   pdl_enter();
-  if (threadIdx.x == 0) {
-    const uint64_t raw = *buf.nblocks;
-    const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
-    if (buf.seg.overflow) *buf.seg.overflow = raw > buf.capacity ? 1ull : 0ull;
-    const uint32_t e = B ? buf.starts[0] : seg_len;
-    buf.seg.send_head[0] = (double)B;
-    buf.seg.send_head[1] = (double)e;
-    for (int d = 0; d < kMaxDims; ++d) {  // one pair per data dimension (IntegralArray.hpp:176-182)
-      double sx = 0.0, sq = 0.0;
-      if (e > 0 && d < buf.D) range_sums_dim(buf, d, 0u, e, sx, sq);
-      buf.seg.send_head[2 + 2 * d] = sx;
-      buf.seg.send_head[3 + 2 * d] = sq;
-    }
-  }
-  if (seq && buf.seg.p2p) {
-    __threadfence();
-    __syncthreads();
-    p2p_exchange_cta(buf.seg.p2p, kSlotHeads, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_head), kHeadWords,
-                     reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.heads)));
-  }
+  seg_head_cta(buf, seg_len, seq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1333,6 +1307,93 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
   if (lane == 0 && fallbacks) atomicAdd(&buf.out_u64[kSpec ? spec_fail_slot<KP>() : KP + KP * KP], (unsigned long long)fallbacks);
 }
 
+// k_fwd_fixup_head (segment mode): what k_fwd_fixup cannot do for chunk 0 of a later rank.  Every rank publishes the
+// last row it holds (+ its block count; all-gather of KP + 1 words, inside this kernel when the peer mailboxes are up),
+// then restarts its first chunk from the last row of the nearest earlier rank that owns blocks.  The published row is
+// right if the rank's own chunk 0 meets its guess before its last block (nothing behind chunk 0 then depended on the
+// guess); a rank with a single chunk cannot promise that and reports a failure.
+//   phase 1: publish only (the caller runs the all-gather), 2: repair only, 3: publish + embedded exchange + repair
+template <int KP, bool kExact>
+__device__ __forceinline__ void fwd_fixup_head_cta(const SweepBuffers& buf, const ModelDev<KP>& m, int phase, int stride,
+                                                   unsigned long long seq) {
+  constexpr int L = Layout::L;
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  if (phase & 1) {
+    if (threadIdx.x == 0) {
+      const double* last = buf.alpha + (B ? Layout::perm(B - 1) : 0) * KP;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) buf.seg.send_op[j] = B ? __ldcg(last + j) : 0.0;
+      buf.seg.send_op[KP] = (double)B;
+    }
+    if (phase == 1) return;
+    __threadfence();
+    __syncthreads();
+    p2p_exchange_cta(buf.seg.p2p, kSlotOps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_op), (uint32_t)(KP + 1),
+                     reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.ops)));
+  }
+  if (threadIdx.x != 0 || buf.seg.rank == 0 || B == 0) return;
+  int src = buf.seg.rank - 1;
+  while (src > 0 && !(__ldcg(buf.seg.ops + (size_t)src * stride + KP) > 0.0)) --src;  // rank 0 always owns block 0
+  if (B <= (uint64_t)L) {  // one chunk: the row this rank published came straight from the guess
+    atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], 1ull);
+    return;
+  }
+  double a[KP];
+#pragma unroll
+  for (int j = 0; j < KP; ++j) a[j] = __ldcg(buf.seg.ops + (size_t)src * stride + j);
+#pragma unroll 1
+  for (int t = 0; t < L; ++t) {
+    const uint64_t p = Layout::at(0, 0, t);
+    double f[KP], as[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      f[j] = 0.0;
+      as[j] = __ldcg(buf.alpha + p * KP + j);
+    }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+#pragma unroll
+      for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
+    }
+    double fs = 0.0, mxv = 0.0;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+      f[j] *= buf.e[p * KP + j];
+      fs += f[j];
+      mxv = fmax(mxv, f[j]);
+    }
+    bool met = false;
+    if (fs > 0.0) {
+      if (kExact) {
+        const double inv = 1.0 / fs;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
+      } else {
+        int e2 = exponent_of(mxv);
+        if (e2 < -1000) e2 = -1000;
+        const double sc = pow2i(-e2);
+#pragma unroll
+        for (int j = 0; j < KP; ++j) a[j] = f[j] * sc;
+      }
+      met = rows_parallel<KP>(a, as);
+    }
+    if (!(fs > 0.0) || (!met && t + 1 == L)) {
+      atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], 1ull);
+      return;
+    }
+    if (met) return;
+#pragma unroll
+    for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
+  }
+}
+
+template <int KP, bool kExact>
+__global__ void __launch_bounds__(256) k_fwd_fixup_head(SweepBuffers buf, ModelDev<KP> m, int phase, int stride,
+                                                        unsigned long long seq) {
+  pdl_enter();
+  fwd_fixup_head_cta<KP, kExact>(buf, m, phase, stride, seq);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_fwd_fixup: second pass of the speculative forward filter, thread per chunk.  Chunk g > 0 restarts from the stored
 // last row of chunk g - 1 and rewrites its own rows until the new row is parallel to the stored one.  The last row of
@@ -1340,8 +1401,11 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
 // counts as a failure — except the very last chunk of the sequence, which nobody continues from.
 //   kExact   rows are normalised by their sum (kept rows, log-likelihood), otherwise by a power of two
 //   kLoglik  sums the per-block terms after the repair (partials[blockIdx.x])
-template <int KP, bool kExact, bool kLoglik>
-__global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm) {
+//   kHead    split sequence over peer mailboxes: the CTA that arrives last publishes the rank's last row, exchanges and
+//            repairs the rank's first chunk (fwd_fixup_head_cta) in the same launch
+template <int KP, bool kExact, bool kLoglik, bool kHead = false>
+__global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm,
+                                                   unsigned long long seq) {
   pdl_enter();
   constexpr int L = Layout::L, C = Layout::C;
   static_assert(!kLoglik || kExact, "the log-likelihood needs the forward sums");
@@ -1428,86 +1492,8 @@ __global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP
     if (threadIdx.x == 0) buf.partials[blockIdx.x] = s_ll[0] + s_ll[1] + s_ll[2] + s_ll[3];
   }
   if (fails) atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], (unsigned long long)fails);
-}
-
-// k_fwd_fixup_head (segment mode): what k_fwd_fixup cannot do for chunk 0 of a later rank.  Every rank publishes the
-// last row it holds (+ its block count; all-gather of KP + 1 words, inside this kernel when the peer mailboxes are up),
-// then restarts its first chunk from the last row of the nearest earlier rank that owns blocks.  The published row is
-// right if the rank's own chunk 0 meets its guess before its last block (nothing behind chunk 0 then depended on the
-// guess); a rank with a single chunk cannot promise that and reports a failure.
-//   phase 1: publish only (the caller runs the all-gather), 2: repair only, 3: publish + embedded exchange + repair
-template <int KP, bool kExact>
-__global__ void __launch_bounds__(256) k_fwd_fixup_head(SweepBuffers buf, ModelDev<KP> m, int phase, int stride,
-                                                        unsigned long long seq) {
-  pdl_enter();
-  constexpr int L = Layout::L;
-  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
-  if (phase & 1) {
-    if (threadIdx.x == 0) {
-      const double* last = buf.alpha + (B ? Layout::perm(B - 1) : 0) * KP;
-#pragma unroll
-      for (int j = 0; j < KP; ++j) buf.seg.send_op[j] = B ? last[j] : 0.0;
-      buf.seg.send_op[KP] = (double)B;
-    }
-    if (phase == 1) return;
-    __threadfence();
-    __syncthreads();
-    p2p_exchange_cta(buf.seg.p2p, kSlotOps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_op), (uint32_t)(KP + 1),
-                     reinterpret_cast<uint64_t*>(const_cast<double*>(buf.seg.ops)));
-  }
-  if (threadIdx.x != 0 || buf.seg.rank == 0 || B == 0) return;
-  int src = buf.seg.rank - 1;
-  while (src > 0 && !(__ldcg(buf.seg.ops + (size_t)src * stride + KP) > 0.0)) --src;  // rank 0 always owns block 0
-  if (B <= (uint64_t)L) {  // one chunk: the row this rank published came straight from the guess
-    atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], 1ull);
-    return;
-  }
-  double a[KP];
-#pragma unroll
-  for (int j = 0; j < KP; ++j) a[j] = __ldcg(buf.seg.ops + (size_t)src * stride + j);
-#pragma unroll 1
-  for (int t = 0; t < L; ++t) {
-    const uint64_t p = Layout::at(0, 0, t);
-    double f[KP], as[KP];
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      f[j] = 0.0;
-      as[j] = buf.alpha[p * KP + j];
-    }
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-#pragma unroll
-      for (int j = 0; j < KP; ++j) f[j] = fma(a[k], m.A[k][j], f[j]);
-    }
-    double fs = 0.0, mxv = 0.0;
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-      f[j] *= buf.e[p * KP + j];
-      fs += f[j];
-      mxv = fmax(mxv, f[j]);
-    }
-    bool met = false;
-    if (fs > 0.0) {
-      if (kExact) {
-        const double inv = 1.0 / fs;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) a[j] = f[j] * inv;
-      } else {
-        int e2 = exponent_of(mxv);
-        if (e2 < -1000) e2 = -1000;
-        const double sc = pow2i(-e2);
-#pragma unroll
-        for (int j = 0; j < KP; ++j) a[j] = f[j] * sc;
-      }
-      met = rows_parallel<KP>(a, as);
-    }
-    if (!(fs > 0.0) || (!met && t + 1 == L)) {
-      atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], 1ull);
-      return;
-    }
-    if (met) return;
-#pragma unroll
-    for (int j = 0; j < KP; ++j) buf.alpha[p * KP + j] = a[j];
+  if constexpr (kHead) {
+    if (last_cta_arrives(buf.tickets + kTicketFixup)) fwd_fixup_head_cta<KP, kExact>(buf, m, 3, KP + 1, seq);
   }
 }
 
@@ -2156,10 +2142,114 @@ __global__ void __launch_bounds__(256, KP <= 5 ? 5 : 1) k_bwd_maps(SweepBuffers 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_bwd_scan: one CTA; suffix composition of the tile maps.
+// tile_qin[t] = state of the first block after tile t (irrelevant for the last tile, whose last block
+// carries a constant map).
+
+// kSegMap: only the composed map of the whole segment is wanted (-> seg.send_map, identity without
+// blocks); otherwise the state following the segment comes from the gathered maps of the later ranks
+// (the last block of the sequence carries a constant map, so the start value is irrelevant).
+// kMode 0: resolve (gathered maps of the later ranks, if any); 1: segment map only; 2: segment map, map
+// exchange through the peer mailboxes and resolution in one kernel
+// NT threads of one CTA; the tile maps are read through L2 (the chunk-map kernel's last CTA calls this in the same launch)
+template <int KP, int kMode, int NT>
+__device__ __forceinline__ void bwd_scan_cta(const SweepBuffers& buf, unsigned long long seq) {
+  constexpr bool kSegMap = kMode == 1;
+  constexpr int MB = 8 * Map<KP>::W, NW = NT / 32;
+  __shared__ uint64_t s_w[NW][Map<KP>::W];
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const int64_t nt = (int64_t)((B + Layout::TB - 1) / Layout::TB);
+  if (nt == 0) {
+    if (kMode != 0 && threadIdx.x == 0) {
+      const Map<KP> id = Map<KP>::identity();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? id.w[i] : 0ull;
+    }
+    if (kMode == 2) {  // a rank without blocks still takes part in the collective
+      __threadfence();
+      __syncthreads();
+      p2p_exchange_cta(buf.seg.p2p, kSlotMaps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_map), 4,
+                       const_cast<uint64_t*>(buf.seg.maps));
+    }
+    return;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t per = (nt + NT - 1) / NT;
+  // thread `tid` owns tiles [lo, hi); threads are ordered by position, so thread 0 holds the earliest
+  const int64_t lo = min(nt, (int64_t)tid * per), hi = min(nt, lo + per);
+  Map<KP> own = Map<KP>::identity();  // own = f_lo o f_{lo+1} o ... o f_{hi-1}
+  for (int64_t t = lo; t < hi; ++t) own = own.after(Map<KP>::load_cg(buf.tile_maps + t * MB));
+  // inclusive suffix within the warp by shuffles
+  Map<KP> inc = own;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    Map<KP> other;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) other.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], o);
+    if (lane + o < 32) inc = inc.after(other);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) s_w[warp][i] = inc.w[i];
+  }
+  __syncthreads();
+  if (kMode != 0) {
+    if (tid == 0) {
+      Map<KP> tot = Map<KP>::identity();
+      for (int wv = 0; wv < NW; ++wv) {
+        Map<KP> o;
+#pragma unroll
+        for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = s_w[wv][i];
+        tot = tot.after(o);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? tot.w[i] : 0ull;
+    }
+    if (kSegMap) return;
+    __threadfence();
+    __syncthreads();
+    p2p_exchange_cta(buf.seg.p2p, kSlotMaps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_map), 4,
+                     const_cast<uint64_t*>(buf.seg.maps));
+  }
+  uint32_t q_end = 0;
+  for (int r = buf.seg.world - 1; r > buf.seg.rank; --r) {
+    Map<KP> o;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = __ldcg(buf.seg.maps + 4 * r + i);
+    q_end = o.get(q_end);
+  }
+  Map<KP> after_warp = Map<KP>::identity();  // map of everything after this warp
+  for (int wv = warp + 1; wv < NW; ++wv) {
+    Map<KP> o;
+#pragma unroll
+    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = s_w[wv][i];
+    after_warp = after_warp.after(o);
+  }
+  Map<KP> nxt;
+#pragma unroll
+  for (int i = 0; i < Map<KP>::W; ++i) nxt.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
+  const Map<KP> suf = (lane == 31) ? after_warp : nxt.after(after_warp);
+  // on the rank holding the sequence's last block the suffix map is constant in its argument
+  uint32_t q = suf.get(q_end);
+  for (int64_t t = hi - 1; t >= lo; --t) {
+    buf.tile_qin[t] = (uint8_t)q;
+    q = Map<KP>::load_cg(buf.tile_maps + t * MB).get(q);
+  }
+}
+
+template <int KP, int kMode>
+__global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf, unsigned long long seq) {
+  pdl_enter();
+  bwd_scan_cta<KP, kMode, 1024>(buf, seq);
+}
+
 // k_bwd_chunkmaps: warp per tile, lane per chunk: G_c = f_first o ... o f_last of the chunk, then a
 // suffix scan over the warp: X_c = G_{c+1} o ... o G_31 (per chunk) and the tile map G_0 o ... o G_31.
-template <int KP>
-__global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf) {
+// kScan -1: chunk and tile maps only; 0 / 2: the CTA that arrives last also runs the scan over the tile maps
+// (bwd_scan_cta<kScan>: 0 resolve, 2 with the map exchange of a split sequence), saving the follow-up launch
+template <int KP, int kScan>
+__global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf, unsigned long long seq) {
   pdl_enter();
   constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W;
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
@@ -2186,101 +2276,8 @@ __global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf) {
     excl.store(buf.chunk_maps + (tile * C + lane) * MB);
     if (lane == 0) inc.store(buf.tile_maps + tile * MB);
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_bwd_scan: one CTA; suffix composition of the tile maps.
-// tile_qin[t] = state of the first block after tile t (irrelevant for the last tile, whose last block
-// carries a constant map).
-
-// kSegMap: only the composed map of the whole segment is wanted (-> seg.send_map, identity without
-// blocks); otherwise the state following the segment comes from the gathered maps of the later ranks
-// (the last block of the sequence carries a constant map, so the start value is irrelevant).
-// kMode 0: resolve (gathered maps of the later ranks, if any); 1: segment map only; 2: segment map, map
-// exchange through the peer mailboxes and resolution in one kernel
-template <int KP, int kMode>
-__global__ void __launch_bounds__(1024) k_bwd_scan(SweepBuffers buf, unsigned long long seq) {
-  pdl_enter();
-  constexpr bool kSegMap = kMode == 1;
-  constexpr int MB = 8 * Map<KP>::W;
-  __shared__ uint64_t s_w[32][Map<KP>::W];
-  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
-  const int64_t nt = (int64_t)((B + Layout::TB - 1) / Layout::TB);
-  if (nt == 0) {
-    if (kMode != 0 && threadIdx.x == 0) {
-      const Map<KP> id = Map<KP>::identity();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? id.w[i] : 0ull;
-    }
-    if (kMode == 2) {  // a rank without blocks still takes part in the collective
-      __threadfence();
-      __syncthreads();
-      p2p_exchange_cta(buf.seg.p2p, kSlotMaps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_map), 4,
-                       const_cast<uint64_t*>(buf.seg.maps));
-    }
-    return;
-  }
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t per = (nt + 1023) / 1024;
-  // thread `tid` owns tiles [lo, hi); threads are ordered by position, so thread 0 holds the earliest
-  const int64_t lo = min(nt, (int64_t)tid * per), hi = min(nt, lo + per);
-  Map<KP> own = Map<KP>::identity();  // own = f_lo o f_{lo+1} o ... o f_{hi-1}
-  for (int64_t t = lo; t < hi; ++t) own = own.after(Map<KP>::load(buf.tile_maps + t * MB));
-  // inclusive suffix within the warp by shuffles
-  Map<KP> inc = own;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    Map<KP> other;
-#pragma unroll
-    for (int i = 0; i < Map<KP>::W; ++i) other.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], o);
-    if (lane + o < 32) inc = inc.after(other);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < Map<KP>::W; ++i) s_w[warp][i] = inc.w[i];
-  }
-  __syncthreads();
-  if (kMode != 0) {
-    if (tid == 0) {
-      Map<KP> tot = Map<KP>::identity();
-      for (int wv = 0; wv < 32; ++wv) {
-        Map<KP> o;
-#pragma unroll
-        for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = s_w[wv][i];
-        tot = tot.after(o);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) buf.seg.send_map[i] = i < Map<KP>::W ? tot.w[i] : 0ull;
-    }
-    if (kSegMap) return;
-    __threadfence();
-    __syncthreads();
-    p2p_exchange_cta(buf.seg.p2p, kSlotMaps, seq, reinterpret_cast<const uint64_t*>(buf.seg.send_map), 4,
-                     const_cast<uint64_t*>(buf.seg.maps));
-  }
-  uint32_t q_end = 0;
-  for (int r = buf.seg.world - 1; r > buf.seg.rank; --r) {
-    Map<KP> o;
-#pragma unroll
-    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = __ldcg(buf.seg.maps + 4 * r + i);
-    q_end = o.get(q_end);
-  }
-  Map<KP> after_warp = Map<KP>::identity();  // map of everything after this warp
-  for (int wv = warp + 1; wv < 32; ++wv) {
-    Map<KP> o;
-#pragma unroll
-    for (int i = 0; i < Map<KP>::W; ++i) o.w[i] = s_w[wv][i];
-    after_warp = after_warp.after(o);
-  }
-  Map<KP> nxt;
-#pragma unroll
-  for (int i = 0; i < Map<KP>::W; ++i) nxt.w[i] = __shfl_down_sync(0xffffffffu, inc.w[i], 1);
-  const Map<KP> suf = (lane == 31) ? after_warp : nxt.after(after_warp);
-  // on the rank holding the sequence's last block the suffix map is constant in its argument
-  uint32_t q = suf.get(q_end);
-  for (int64_t t = hi - 1; t >= lo; --t) {
-    buf.tile_qin[t] = (uint8_t)q;
-    q = Map<KP>::load(buf.tile_maps + t * MB).get(q);
+  if constexpr (kScan >= 0) {
+    if (last_cta_arrives(buf.tickets + kTicketChunkMaps)) bwd_scan_cta<KP, kScan, 128>(buf, seq);
   }
 }
 
@@ -2342,8 +2339,44 @@ __global__ void __launch_bounds__(256) k_mix_sample(SweepBuffers buf, ModelDev<K
 
 constexpr int kReduceThreads = 256;
 
-template <int KP>
-__global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers buf, int K) {
+// kFinal 0: partial sums only (k_reduce_final / k_reduce_final_exchange follow); 1: the CTA that arrives last also
+// forms the final sums (same fixed order and tree as k_reduce_final_exchange); 2: ... and runs the statistics exchange
+// Final sums by one CTA of NT threads (the one that arrived last): out_f64[v] = sum over the CTAs' partial rows, fixed
+// assignment and fixed tree => deterministic.  Thread t adds up rows t, t + NT, ... (all 2 KP loads of a row in flight),
+// then warp shuffles and one pass over the warps.
+template <int KP, int NT>
+__device__ __forceinline__ void reduce_final_cta(const SweepBuffers& buf, int nparts) {
+  __shared__ double s_fin[NT / 32][2 * KP];
+  double acc[2 * KP];
+#pragma unroll
+  for (int v = 0; v < 2 * KP; ++v) acc[v] = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += NT) {
+    double row[2 * KP];
+#pragma unroll
+    for (int v = 0; v < 2 * KP; ++v) row[v] = __ldcg(buf.partials + (size_t)i * 2 * KP + v);
+#pragma unroll
+    for (int v = 0; v < 2 * KP; ++v) acc[v] += row[v];
+  }
+#pragma unroll
+  for (int v = 0; v < 2 * KP; ++v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[v] += shfl_xor_double(acc[v], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int v = 0; v < 2 * KP; ++v) s_fin[threadIdx.x >> 5][v] = acc[v];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * KP) {
+    double t = 0.0;
+    for (int wv = 0; wv < NT / 32; ++wv) t += s_fin[wv][threadIdx.x];
+    buf.out_f64[threadIdx.x] = t;
+  }
+}
+
+template <int KP, int kFinal>
+__global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers buf, int K, uint32_t stats_words,
+                                                                   unsigned long long seq) {
   pdl_enter();
   __shared__ unsigned long long s_trans[KP * KP];
   __shared__ unsigned long long s_n[KP];
@@ -2424,6 +2457,141 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
     if (s_trans[i]) atomicAdd(&buf.out_u64[KP + i], s_trans[i]);
   for (int i = threadIdx.x; i < KP; i += blockDim.x)
     if (s_n[i]) atomicAdd(&buf.out_u64[i], s_n[i]);
+  if constexpr (kFinal != 0) {
+    if (!last_cta_arrives(buf.tickets + kTicketReduce)) return;
+    reduce_final_cta<KP, kReduceThreads>(buf, (int)gridDim.x);
+    if constexpr (kFinal == 2) {
+      __threadfence();
+      __syncthreads();
+      p2p_exchange_cta(buf.seg.p2p, kSlotStats, seq, reinterpret_cast<const uint64_t*>(buf.seg.stats_send), stats_words,
+                       reinterpret_cast<uint64_t*>(buf.seg.stats_recv));
+    }
+  }
+}
+
+// k_bwd_replay_reduce (K <= 8): k_bwd_replay and the statistics pass in one kernel, thread per chunk.  Walking its 32
+// blocks backwards the thread knows every block's state and its successor's, so transitions are counted on the way; the
+// sums go to the thread's own per-state slots in shared memory, indexed by the state (4 read-modify-writes per block;
+// K-way selects into registers cost 4 K, and "flush when the state changes" does not help a warp whose 32 lanes change
+// state at different blocks).  The CTA that arrives last forms the final sums (and, kFinal == 2, runs the statistics
+// exchange of a split sequence).
+template <int KP, int kFinal>
+__global__ void __launch_bounds__(128) k_bwd_replay_reduce(SweepBuffers buf, uint32_t stats_words, unsigned long long seq) {
+  pdl_enter();
+  constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W, NT = 128;
+  __shared__ unsigned long long s_trans[KP * KP];
+  __shared__ unsigned long long s_n[KP];
+  __shared__ double s_sum[NT / 32][2 * KP];
+  // [value][state][thread]: a warp's 32 lanes hit 32 different banks whatever their states are
+  __shared__ double s_ax[KP][NT], s_aq[KP][NT];
+  __shared__ unsigned long long s_an[KP][NT], s_ad[KP][NT];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < KP * KP; i += NT) s_trans[i] = 0;
+  for (int i = tid; i < KP; i += NT) s_n[i] = 0;
+#pragma unroll
+  for (int s = 0; s < KP; ++s) {
+    s_ax[s][tid] = s_aq[s][tid] = 0.0;
+    s_an[s][tid] = s_ad[s][tid] = 0ull;
+  }
+  __syncthreads();
+  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
+  const uint64_t nch = (B + L - 1) / L;
+  const bool seg = buf.seg.world > 1;
+  const bool has_after = seg && seg_later_blocks(buf.seg);
+  const bool first_rank = !seg || buf.seg.rank == 0;
+  for (uint64_t ch = (uint64_t)blockIdx.x * NT + tid; ch < nch; ch += (uint64_t)gridDim.x * NT) {
+    const uint64_t tile = ch / C;
+    const int c = (int)(ch % C);
+    const uint64_t first = ch * L;
+    const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+    // state following this chunk = (maps of the later chunks of the tile)(state following the tile)
+    uint32_t next = Map<KP>::load(buf.chunk_maps + ch * MB).get(buf.tile_qin[tile]);
+    bool has_next = (first + steps < B) || has_after;  // does the chunk's last block have a successor anywhere?
+    for (int t0 = steps - 1; t0 >= 0; t0 -= 8) {
+      Map<KP> mp[8];
+      uint32_t nn[8];
+      double2 vv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (t0 - i >= 0) {
+          const uint64_t p = Layout::at(tile, c, t0 - i);
+          mp[i] = Map<KP>::load(buf.maps + p * MB);
+          nn[i] = buf.bN[p];
+          vv[i] = buf.bS[p];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (t0 - i >= 0) {
+          const uint32_t q = mp[i].get(next);
+          buf.states[Layout::at(tile, c, t0 - i)] = (uint8_t)q;
+          // FB.hpp:177,182-184: N - 1 self transitions inside the block, one transition to the successor
+          unsigned long long dg = (unsigned long long)(nn[i] - 1u);
+          if (has_next) {
+            if (next == q)
+              dg += 1ull;
+            else
+              atomicAdd(&s_trans[q * KP + next], 1ull);  // state changes are rare: low contention
+          }
+          if (first + (uint64_t)(t0 - i) == 0 && first_rank) {  // the phantom 0 -> q_0 in front of the sequence
+            if (q == 0u)
+              dg += 1ull;
+            else
+              atomicAdd(&s_trans[q], 1ull);  // row 0, column q
+          }
+          s_ax[q][tid] += vv[i].x;
+          s_aq[q][tid] += vv[i].y;
+          s_an[q][tid] += nn[i];
+          s_ad[q][tid] += dg;
+          next = q;
+          has_next = true;
+        }
+      }
+    }
+  }
+  double ax[KP], aq[KP];
+  unsigned long long an[KP], ad[KP];  // observations per state; diagonal transition counts
+#pragma unroll
+  for (int s = 0; s < KP; ++s) {
+    ax[s] = s_ax[s][tid];
+    aq[s] = s_aq[s][tid];
+    an[s] = s_an[s][tid];
+    ad[s] = s_ad[s][tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax[s] += shfl_xor_double(ax[s], o);
+      aq[s] += shfl_xor_double(aq[s], o);
+      an[s] += __shfl_xor_sync(0xffffffffu, an[s], o);
+      ad[s] += __shfl_xor_sync(0xffffffffu, ad[s], o);
+    }
+  }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int s = 0; s < KP; ++s) {
+      s_sum[tid >> 5][s] = ax[s];
+      s_sum[tid >> 5][KP + s] = aq[s];
+      if (an[s]) atomicAdd(&s_n[s], an[s]);
+      if (ad[s]) atomicAdd(&s_trans[s * KP + s], ad[s]);
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * KP) {
+    double t = 0.0;
+    for (int wv = 0; wv < NT / 32; ++wv) t += s_sum[wv][tid];
+    buf.partials[(size_t)blockIdx.x * 2 * KP + tid] = t;
+  }
+  for (int i = tid; i < KP * KP; i += NT)
+    if (s_trans[i]) atomicAdd(&buf.out_u64[KP + i], s_trans[i]);
+  for (int i = tid; i < KP; i += NT)
+    if (s_n[i]) atomicAdd(&buf.out_u64[i], s_n[i]);
+  if (!last_cta_arrives(buf.tickets + kTicketReduce)) return;
+  reduce_final_cta<KP, NT>(buf, (int)gridDim.x);
+  if constexpr (kFinal == 2) {
+    __threadfence();
+    __syncthreads();
+    p2p_exchange_cta(buf.seg.p2p, kSlotStats, seq, reinterpret_cast<const uint64_t*>(buf.seg.stats_send), stats_words,
+                     reinterpret_cast<uint64_t*>(buf.seg.stats_recv));
+  }
 }
 
 // one CTA per output value; fixed assignment and fixed tree => deterministic
@@ -2696,9 +2864,10 @@ int launch_fwd_tilescan(const SweepBuffers& b, const ModelDev<KP>& m, int phase,
 // maps -> chunk/tile maps -> suffix scan over tiles -> states; returns the number of launches
 template <int KP>
 int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLaunch& l, bool rows, uint64_t nb,
-                    cudaStream_t s, stage_cb_t cb, void* user, bool have_maps = false) {
+                    cudaStream_t s, stage_cb_t cb, void* user, bool have_maps = false, bool* reduce_too = nullptr) {
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
   int launches = 2;
+  bool scanned = false;
   if (!have_maps) {  // k_replay_maps already wrote the block, chunk and tile maps
     launches += 2;
     if (cb) cb(user, "bwd_maps");
@@ -2708,36 +2877,70 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
     else
       launch_k(k_bwd_maps<KP, false>, gm, 256, 0, s, b, m, l.seed, l.sweep);
     if (cb) cb(user, "bwd_chunkmaps");
-    launch_k(k_bwd_chunkmaps<KP>, grid_for(ntiles * 32, 128, l.sms, 16), 128, 0, s, b);
-  }
-  if (cb) cb(user, "bwd_scan");
-  if (b.seg.world > 1 && b.seg.p2p != nullptr) {
-    launch_k(k_bwd_scan<KP, 2>, 1, 1024, 0, s, b, l.next_seq(l.exchange_user, kExchangeMaps));
-  } else {
-    if (b.seg.world > 1) {
-      launch_k(k_bwd_scan<KP, 1>, 1, 1024, 0, s, b, 0ull);
-      ++launches;
-      if (cb) cb(user, "exchange_maps");
-      if (l.exchange(l.exchange_user, kExchangeMaps) != 0) return -1;
-      if (cb) cb(user, "bwd_scan2");
+    const int gc = grid_for(ntiles * 32, 128, l.sms, 16);
+    if (b.tickets != nullptr && !(b.seg.world > 1 && b.seg.p2p == nullptr)) {
+      // the CTA that arrives last scans the tile maps (and runs the map exchange of a split sequence) in the same launch
+      if (b.seg.world > 1)
+        launch_k(k_bwd_chunkmaps<KP, 2>, gc, 128, 0, s, b, l.next_seq(l.exchange_user, kExchangeMaps));
+      else
+        launch_k(k_bwd_chunkmaps<KP, 0>, gc, 128, 0, s, b, 0ull);
+      scanned = true;
+      --launches;
+    } else {
+      launch_k(k_bwd_chunkmaps<KP, -1>, gc, 128, 0, s, b, 0ull);
     }
-    launch_k(k_bwd_scan<KP, 0>, 1, 1024, 0, s, b, 0ull);
+  }
+  if (!scanned) {
+    if (cb) cb(user, "bwd_scan");
+    if (b.seg.world > 1 && b.seg.p2p != nullptr) {
+      launch_k(k_bwd_scan<KP, 2>, 1, 1024, 0, s, b, l.next_seq(l.exchange_user, kExchangeMaps));
+    } else {
+      if (b.seg.world > 1) {
+        launch_k(k_bwd_scan<KP, 1>, 1, 1024, 0, s, b, 0ull);
+        ++launches;
+        if (cb) cb(user, "exchange_maps");
+        if (l.exchange(l.exchange_user, kExchangeMaps) != 0) return -1;
+        if (cb) cb(user, "bwd_scan2");
+      }
+      launch_k(k_bwd_scan<KP, 0>, 1, 1024, 0, s, b, 0ull);
+    }
   }
   if (cb) cb(user, "bwd_replay");
-  launch_k(k_bwd_replay<KP>, grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16), 128, 0, s, b);
+  const int gp = grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16);
+  if constexpr (KP <= 8) {
+    if (reduce_too != nullptr && b.tickets != nullptr) {  // states and statistics in one kernel
+      if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
+        launch_k(k_bwd_replay_reduce<KP, 2>, gp, 128, 0, s, b, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
+      else
+        launch_k(k_bwd_replay_reduce<KP, 1>, gp, 128, 0, s, b, (uint32_t)0, 0ull);
+      *reduce_too = true;
+      return launches;
+    }
+  }
+  launch_k(k_bwd_replay<KP>, gp, 128, 0, s, b);
   return launches;
 }
 
 template <int KP>
-int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, const SweepLaunch& l, cudaStream_t s) {
+int launch_reduce(const SweepBuffers& b, int K, uint64_t nb, const SweepLaunch& l, cudaStream_t s, bool first_done = false) {
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
   const int g = grid_for(ntiles * Layout::TB, kReduceThreads, l.sms, 4);
-  launch_k(k_reduce_partial<KP>, g, kReduceThreads, 0, s, b, K);
-  if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
-    launch_k(k_reduce_final_exchange<KP>, 1, 256, 0, s, b, g, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
-  else
-    launch_k(k_reduce_final<KP>, 2 * KP, 128, 0, s, b, g);
-  int launches = 2;
+  int launches = first_done ? 0 : 1;
+  if (first_done) {
+    // k_bwd_replay_reduce left the counts and the sums of the first dimension
+  } else if (b.D == 1 && b.tickets != nullptr) {  // the last CTA finishes: final sums (+ statistics exchange) in the same launch
+    if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
+      launch_k(k_reduce_partial<KP, 2>, g, kReduceThreads, 0, s, b, K, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
+    else
+      launch_k(k_reduce_partial<KP, 1>, g, kReduceThreads, 0, s, b, K, (uint32_t)0, 0ull);
+  } else {
+    launch_k(k_reduce_partial<KP, 0>, g, kReduceThreads, 0, s, b, K, (uint32_t)0, 0ull);
+    if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
+      launch_k(k_reduce_final_exchange<KP>, 1, 256, 0, s, b, g, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
+    else
+      launch_k(k_reduce_final<KP>, 2 * KP, 128, 0, s, b, g);
+    ++launches;
+  }
   for (int d = 1; d < b.D; ++d) {  // multivariate data: the remaining dimensions, written behind the log-likelihood
     SweepBuffers bd = b;
     bd.out_f64 = b.out_f64 + 2 * KP + 1 + (size_t)(d - 1) * 2 * KP;
@@ -2762,6 +2965,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     if (cb) cb(user, name);
   };
   constexpr bool kPrefix = KP <= 8;  // k_fwd_chunks_prefix + k_fwd_replay_prefix
+  bool reduced = false;              // the backward replay kernel also did the statistics pass
   stage("block_emit");
   if (b.D > 1) {
     const EmitMD<KP> md = make_emit_md<KP>(mh);
@@ -2827,17 +3031,22 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     ++launches;
     stage("fwd_fixup");
     const int gf = grid_for(ntiles * Layout::C, 128, l.sms, 8);
+    bool head_done = false;
     if (loglik) {
-      launch_k(k_fwd_fixup<KP, true, true>, gf, 128, 0, s, b, m, lognorm);
+      launch_k(k_fwd_fixup<KP, true, true>, gf, 128, 0, s, b, m, lognorm, 0ull);
       launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gf, b.out_f64 + 2 * KP);
       ++launches;
+    } else if (seg && b.seg.p2p != nullptr && b.tickets != nullptr) {
+      // split sequence: the repair of the rank's first chunk (one all-gather of K + 1 words) rides in the last CTA
+      launch_k(k_fwd_fixup<KP, !kPrefix, false, true>, gf, 128, 0, s, b, m, lognorm, l.next_seq(l.exchange_user, kExchangeOps));
+      head_done = true;
     } else if (rows || !kPrefix) {
-      launch_k(k_fwd_fixup<KP, true, false>, gf, 128, 0, s, b, m, lognorm);
+      launch_k(k_fwd_fixup<KP, true, false>, gf, 128, 0, s, b, m, lognorm, 0ull);
     } else {
-      launch_k(k_fwd_fixup<KP, false, false>, gf, 128, 0, s, b, m, lognorm);
+      launch_k(k_fwd_fixup<KP, false, false>, gf, 128, 0, s, b, m, lognorm, 0ull);
     }
     ++launches;
-    if (seg) {  // chunk 0 of the later ranks, from the last row of the rank before
+    if (seg && !head_done) {  // chunk 0 of the later ranks, from the last row of the rank before
       stage("fwd_fixup_head");
       constexpr bool kEx = !kPrefix;
       if (b.seg.p2p != nullptr) {
@@ -2852,7 +3061,7 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
         launches += 2;
       }
     }
-    const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
+    const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user, false, &reduced);
     if (nbw < 0) return -1;
     launches += nbw;
   } else {
@@ -2904,12 +3113,12 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
       }
     }
     ++launches;
-    const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user);
+    const int nbw = launch_backward<KP>(b, m, l, rows, nb, s, cb, user, false, &reduced);
     if (nbw < 0) return -1;
     launches += nbw;
   }
-  stage("reduce");
-  launches += launch_reduce<KP>(b, mh.K, nb, l, s);
+  if (!reduced) stage("reduce");
+  launches += launch_reduce<KP>(b, mh.K, nb, l, s, reduced);
   stage("end");
   return launches;
 }

@@ -108,9 +108,10 @@ int hml_detect_info(hml_t* h, int* mode, uint64_t* hot_subblocks);
  *                            not met its guess by its last block the sweep is run again through the operator scan, so
  *                            the result never depends on the assumption that the filter forgets its start.
  *   HML_FORWARD_AUTO (default) speculative.  A failed sweep is repeated through the operator scan and the following
- *                            sweeps push their guesses through more blocks (4, 16, 64, 128; halved again after 64 good
- *                            sweeps); if 128 are not enough either the operator scan takes the next 1, 3, 7, ... 63
- *                            sweeps before the next attempt.
+ *                            sweeps push their guesses through more blocks (4, 16, 64, and 128 for K > 8; halved again
+ *                            after 64 good sweeps); if that is not enough either — blocks of one or two observations
+ *                            with levels a sigma apart can take hundreds of blocks to forget — the operator scan takes
+ *                            the next 1, 3, 7, ... 63 sweeps before the next attempt.
  * A split sequence speculates too (the first chunk of a rank is repaired from the last row of the rank before: one
  * all-gather of K + 1 words instead of the K x K segment operators), except when the log-likelihood is asked for.
  * Mixture sweeps have no forward filter; the fused kernel uses the operator scan.  hml_forward_info: the mode, the

@@ -85,42 +85,44 @@ def test_auto_mode_backs_off_after_a_failure_and_comes_back(dev):
     dev.create_blocks(0.5)
     dev.set_forward_mode(capi.FORWARD_AUTO)
     _, n0, f0 = dev.forward_info()
-    for i in range(4):                                         # speculative with warm-ups of 4, 16, 64, 128 blocks: all fail
+    for i in range(3):                                         # speculative with warm-ups of 4, 16, 64 blocks: all fail
         dev.fb_sweep(*flat, use_self=1, seed=1, sweep=i)
         assert dev.forward_info()[1:] == (n0 + 1 + i, f0 + 1 + i)
     dev.fb_sweep(*flat, use_self=1, seed=1, sweep=4)           # operator scan (one sweep of back-off)
-    assert dev.forward_info()[1:] == (n0 + 4, f0 + 4)
+    assert dev.forward_info()[1:] == (n0 + 3, f0 + 3)
     dev.fb_sweep(*flat, use_self=1, seed=1, sweep=5)           # speculative again, fails again
-    assert dev.forward_info()[1:] == (n0 + 5, f0 + 5)
+    assert dev.forward_info()[1:] == (n0 + 4, f0 + 4)
     for s in range(3):                                         # three sweeps of back-off
         dev.fb_sweep(*sharp, use_self=1, seed=1, sweep=6 + s)
-    assert dev.forward_info()[1:] == (n0 + 5, f0 + 5)
+    assert dev.forward_info()[1:] == (n0 + 4, f0 + 4)
     dev.fb_sweep(*sharp, use_self=1, seed=1, sweep=9)          # speculative, holds
-    assert dev.forward_info()[1:] == (n0 + 6, f0 + 5)
+    assert dev.forward_info()[1:] == (n0 + 5, f0 + 4)
     dev.fb_sweep(*sharp, use_self=1, seed=1, sweep=10)         # and stays on
-    assert dev.forward_info()[1:] == (n0 + 7, f0 + 5)
+    assert dev.forward_info()[1:] == (n0 + 6, f0 + 4)
 
 
 def test_longer_warm_ups_take_over_on_weakly_informative_blocks(dev):
-    """Levels one sigma apart, blocks of a few observations: the first speculative sweep does not meet its guesses, the
+    """Levels two sigma apart, blocks of a few observations: the first speculative sweeps do not meet their guesses, the
     following ones warm up over more blocks and hold; every sweep equals the operator scan's, states included."""
     T, K = 300_000, 5
-    x = piecewise_gaussian(T, K, 8, seed=16, spacing=0.3)
-    mu, var, A, pi = model_guess(K, seed=K, spacing=0.3)
+    x = piecewise_gaussian(T, K, 8, seed=16, spacing=0.6)
+    mu, var, A, pi = model_guess(K, seed=K, spacing=0.6)
     dev.load(x)
     B = dev.create_blocks(0.3)
     dev.set_forward_mode(capi.FORWARD_OPERATORS)
     want = []
-    for i in range(6):
+    for i in range(8):
         dev.fb_sweep(mu, var, A, pi, use_self=1, seed=4, sweep=i)
         want.append(dev.states().copy())
     dev.set_forward_mode(capi.FORWARD_AUTO)
     _, n0, f0 = dev.forward_info()
-    for i in range(6):
+    for i in range(8):
+        before = dev.forward_info()
         out = dev.fb_sweep(mu, var, A, pi, use_self=1, seed=4, sweep=i)
         assert out["nblocks"] == B and np.array_equal(dev.states(), want[i]), i
     _, n1, f1 = dev.forward_info()
-    assert n1 == n0 + 6 and 1 <= f1 - f0 <= 3     # warm-ups of 4 (fails), 16, 64 ... until they hold
+    assert 1 <= f1 - f0 <= 3 and n1 - n0 >= 6          # warm-ups of 4 and 16 fail, 64 hold
+    assert dev.forward_info()[1:] == (before[1] + 1, before[2])   # the last sweep was speculative and held
 
 
 def test_philox_states_do_not_depend_on_the_forward_mode(dev):
