@@ -395,6 +395,14 @@ def main():
                        "merge into the device-resident state marginals (hml_marginals_add: StateMarginals::addRecord "
                        "as three small kernels; nothing but a 4-byte count returns to the host per sweep)"}
 
+    # how the forward filter ran so far (warm-up, the timed regions, the recorded sweeps): speculative sweeps, how many had
+    # to be repeated through the operator scan, and the (piece, warm-up) level it settled on
+    def forward_doc():
+        _, nspec, nrep = h.forward_info()
+        piece, warm = h.forward_level()
+        return {"speculative_sweeps": nspec, "repeated": nrep, "piece_blocks": piece, "warmup_blocks": warm}
+    forward_timed = forward_doc()
+
     # ---- region 3 (not part of `value`): the same steps with per-stage CUDA events, for the roofline and stage table
     h.set_timing(True)
     stage_ms, nblocks = {}, []
@@ -403,6 +411,7 @@ def main():
         for name, ms in h.timing():
             stage_ms.setdefault(name, []).append(ms)
     h.set_timing(False)
+    forward_staged = forward_doc()
     clocks = sampler.stop()
 
     # ---- the streaming formulation of boundary detection (4 B/observation), timed on the same data
@@ -540,6 +549,8 @@ def main():
                      "sweep_frac_of_hbm_roofline": (4.0 * T + B * (4 + 16 + 16 * K + 2)) / (world if segments else 1)
                                                    / peak / 1e9 / (ms_per_step * 1e-3)},
         "recorded": recorded,
+        "forward_filter": {"mode": "auto (speculative pieces + repair pass; operator scan after a failure)",
+                           "after_timed_regions": forward_timed, "after_stage_pass": forward_staged},
         "stream_detect": stream,
         "pyramid_detect": pyramid,
         "stage_ms": busy,

@@ -225,8 +225,14 @@ class Handle:
     def forward_info(self):
         """(mode, speculative sweeps so far, how many of them were repeated through the operator scan)"""
         mode, n, f = C.c_int(), C.c_uint64(), C.c_uint64()
-        self._ck(self.lib.hml_forward_info(self.h, C.byref(mode), C.byref(n), C.byref(f)))
+        self._ck(self.lib.hml_forward_info(self.h, C.byref(mode), C.byref(n), C.byref(f), None, None))
         return mode.value, n.value, f.value
+
+    def forward_level(self):
+        """(blocks per piece, warm-up blocks) the next speculative sweep would use"""
+        piece, warm = C.c_int(), C.c_int()
+        self._ck(self.lib.hml_forward_info(self.h, None, None, None, C.byref(piece), C.byref(warm)))
+        return piece.value, warm.value
 
     def detect_info(self):
         mode, hot = C.c_int(), C.c_uint64()

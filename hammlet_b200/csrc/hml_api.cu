@@ -136,6 +136,7 @@ struct hml_ctx {
   int last_K = 0;
   double *e = nullptr, *maxE = nullptr, *alpha = nullptr;
   uint8_t *maps = nullptr, *states = nullptr, *chunk_maps = nullptr, *tile_maps = nullptr, *tile_qin = nullptr;
+  uint8_t* chunk_submaps = nullptr;
   unsigned* tickets = nullptr;
   double *chunk_ops = nullptr, *tile_ops = nullptr, *tile_ain = nullptr, *group_ops = nullptr, *group_ain = nullptr;
   int *chunk_exp = nullptr, *tile_exp = nullptr, *group_exp = nullptr, *wide_exp = nullptr;
@@ -168,8 +169,9 @@ struct hml_ctx {
   int forward_mode = HML_FORWARD_AUTO;
   uint64_t spec_sweeps = 0, spec_failures = 0;
   uint32_t spec_skip = 0, spec_streak = 0;  // sweeps still to run through the operator scan / failures in a row
-  int spec_warm = kSpecWarmMin;             // warm-up blocks of the guesses: x4 after a failure, halved after 64 good sweeps
-  uint32_t spec_good = 0;
+  bool spec_lowered = false;
+  int spec_level = 0;                       // (piece length, warm-up) of the guesses: up after a failure, down after 64 good sweeps
+  uint32_t spec_good = 0, spec_patience = 64;  // good sweeps in a row / how many it takes to try the level below again
   // HML_HOST_TIMING=1: where the host thread spends a sweep (printed when the handle is destroyed)
   uint64_t host_ns_prepare = 0, host_ns_launch = 0, host_ns_wait = 0, host_sweeps = 0;
   unsigned long long* outblk = nullptr;       // device result block: [0] nblocks, [2..] per-sweep outputs
@@ -307,6 +309,7 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
     CK(dev_alloc(h->maxE, cap));
     CK(dev_alloc(h->maps, cap * MB));
     CK(dev_alloc(h->chunk_maps, chunks * MB));
+    CK(dev_alloc(h->chunk_submaps, chunks * MB * 3));
     CK(dev_alloc(h->tile_maps, tiles * MB));
     CK(dev_alloc(h->chunk_ops, chunks * KP * KP));
     CK(dev_alloc(h->chunk_exp, chunks * KP));
@@ -353,6 +356,7 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.chunk_ops = h->chunk_ops;
   b.chunk_exp = h->chunk_exp;
   b.chunk_maps = h->chunk_maps;
+  b.chunk_submaps = h->chunk_submaps;
   b.tile_maps = h->tile_maps;
   b.tile_qin = h->tile_qin;
   b.tickets = h->tickets;
@@ -1254,7 +1258,8 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     l.speculate = spec_ok && h->forward_mode != HML_FORWARD_OPERATORS &&
                   (h->forward_mode == HML_FORWARD_SPECULATIVE || h->spec_skip == 0);
     if (!l.speculate && h->spec_skip > 0 && spec_ok) h->spec_skip--;
-    l.spec_warm = h->spec_warm;
+    l.spec_warm = spec_warm_of(KP, h->spec_level);
+    l.spec_sub = spec_sub_of(KP, h->spec_level);
     const auto hc1 = std::chrono::steady_clock::now();
     int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
     if (n == -2) return fail(h, HML_ERR_ARG, "unsupported number of states");
@@ -1276,12 +1281,15 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     if (l.speculate && !(dynamic && res.any_overflow)) {
       h->spec_sweeps++;
       if (res.o64[KP + KP * KP + 1] > 0) {  // some chunk's rows did not meet the guess's: the exact operator scan
-        // first remedy: longer warm-ups (the filter forgets, but not within a chunk); once they are as long as they
-        // get, the operator scan takes the next 1, 3, 7, ... 63 sweeps
+        // first remedy: longer pieces with longer warm-ups (the filter forgets, but not within a piece); past the last
+        // level the operator scan takes the next 1, 3, 7, ... 63 sweeps
         h->spec_failures++;
+        // failing right after stepping down a level: that level is not for this data, ask for more patience next time
+        if (h->spec_lowered && h->spec_good < 8 && h->spec_patience < 16384) h->spec_patience *= 4;
+        h->spec_lowered = false;
         h->spec_good = 0;
-        if (h->spec_warm < spec_warm_max(KP)) {
-          h->spec_warm = h->spec_warm * 4 < spec_warm_max(KP) ? h->spec_warm * 4 : spec_warm_max(KP);
+        if (h->spec_level + 1 < kSpecLevels) {
+          h->spec_level++;
         } else {
           h->spec_streak = h->spec_streak < 6 ? h->spec_streak + 1 : 6;
           h->spec_skip = (1u << h->spec_streak) - 1;
@@ -1299,9 +1307,10 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
         if (rc != HML_OK) return rc;
       } else {
         h->spec_streak = 0;
-        if (++h->spec_good >= 64 && h->spec_warm > kSpecWarmMin) {
-          h->spec_warm /= 2;
+        if (++h->spec_good >= h->spec_patience && h->spec_level > 0) {
+          h->spec_level--;
           h->spec_good = 0;
+          h->spec_lowered = true;
         }
       }
     }
@@ -1551,6 +1560,7 @@ int hml_destroy(hml_t* h) {
   dev_free(h->maps);
   dev_free(h->states);
   dev_free(h->chunk_maps);
+  dev_free(h->chunk_submaps);
   dev_free(h->tile_maps);
   dev_free(h->tile_qin);
   dev_free(h->tickets);
@@ -2642,15 +2652,21 @@ int hml_set_forward_mode(hml_t* h, int mode) {
     return fail(h, HML_ERR_ARG, "unknown forward mode");
   h->forward_mode = mode;
   h->spec_skip = h->spec_streak = h->spec_good = 0;
-  h->spec_warm = kSpecWarmMin;
+  h->spec_level = 0;
+  h->spec_patience = 64;
+  h->spec_lowered = false;
   return HML_OK;
 }
 
-int hml_forward_info(hml_t* h, int* mode, uint64_t* speculative_sweeps, uint64_t* failures) {
+int hml_forward_info(hml_t* h, int* mode, uint64_t* speculative_sweeps, uint64_t* failures, int* piece_blocks,
+                     int* warmup_blocks) {
   if (!h) return HML_ERR_ARG;
   if (mode) *mode = h->forward_mode;
   if (speculative_sweeps) *speculative_sweeps = h->spec_sweeps;
   if (failures) *failures = h->spec_failures;
+  const int KP = h->KP ? h->KP : 2;
+  if (piece_blocks) *piece_blocks = spec_sub_of(KP, h->spec_level);
+  if (warmup_blocks) *warmup_blocks = spec_warm_of(KP, h->spec_level);
   return HML_OK;
 }
 

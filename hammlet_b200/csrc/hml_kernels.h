@@ -130,6 +130,7 @@ struct SweepBuffers {
   double* chunk_ops;        // per chunk KP*KP
   int* chunk_exp;           // per chunk KP
   uint8_t* chunk_maps;      // per chunk KPB: composed map of the LATER chunks of the same tile
+  uint8_t* chunk_submaps;   // per chunk 3 x KPB: composed maps of the chunk's blocks from step 8, 16 and 24 on
   uint8_t* tile_maps;       // per tile KPB: composed map of the tile
   uint8_t* tile_qin;        // per tile: state of the block following the tile
   unsigned* tickets;        // kTickets arrival counters (zero between launches): the CTA that arrives last finishes the step
@@ -235,11 +236,15 @@ struct SweepLaunch {
   void* exchange_user;
   uint32_t stats_words;  // 8-byte words of the result block travelling in the statistics exchange (0: not fused)
   bool speculate;        // forward filter by guessed chunk starts + repair pass (result word KP + KP*KP + 1 counts failures)
-  int spec_warm;         // blocks in front of a chunk its guess is pushed through
+  int spec_warm;         // blocks in front of a piece its guess is pushed through
+  int spec_sub;          // K <= 8: blocks per piece of the speculative pass (8, 16 or 32)
 };
-// warm-up lengths: 4, 16, 64 (and 128 for K > 8); longer ones cost more than the operator scan they replace
-constexpr int kSpecWarmMin = 4;
-inline int spec_warm_max(int KP) { return KP <= 8 ? 64 : 128; }
+// Levels of the speculative pass: (piece length, warm-up).  Short pieces give a latency-bound recursion more warps;
+// data on which the filter forgets slowly needs long warm-ups, which only pay with long pieces.  Past the last level
+// the operator scan is cheaper.
+constexpr int kSpecLevels = 3;
+inline int spec_sub_of(int KP, int level) { return KP <= 8 ? (level == 0 ? 8 : level == 1 ? 16 : 32) : 32; }
+inline int spec_warm_of(int KP, int level) { return KP <= 8 ? (level == 0 ? 4 : level == 1 ? 16 : 64) : (level == 0 ? 8 : level == 1 ? 32 : 128); }
 enum { kTicketScatter = 0, kTicketFixup = 1, kTicketChunkMaps = 2, kTicketReduce = 3, kTickets = 8 };
 enum { kExchangeHeads = 0, kExchangeOps = 1, kExchangeMaps = 2, kExchangeStats = 3 };
 // segment mode: head partial of this rank -> seg.send_head (to be all-gathered before the block statistics)

@@ -1060,17 +1060,15 @@ __device__ __forceinline__ int spec_fail_slot() {
   return KP + KP * KP + 1;
 }
 
-// the guess for the vector entering chunk (tile, c): uniform pushed through the `warm` blocks in front of the chunk
-// (rescaled by exact powers of two; a vanished vector restarts uniform).  A chunk with fewer than `warm` blocks in
-// front of it starts from pi at block 0, i.e. exactly; the first chunk of a later rank of a split sequence has no
-// blocks in front of it on this device and starts uniform (k_fwd_fixup_head repairs it).
+// the guess for the vector entering the piece that starts at block `first`: uniform pushed through the `warm` blocks
+// in front of it (rescaled by exact powers of two; a vanished vector restarts uniform).  A piece with fewer than `warm`
+// blocks in front of it starts from pi at block 0, i.e. exactly; the first piece of a later rank of a split sequence
+// has no blocks in front of it on this device and starts uniform (k_fwd_fixup_head repairs it).
 template <int KP>
-__device__ __forceinline__ void spec_entry(const SweepBuffers& buf, const ModelDev<KP>& m, uint64_t tile, int c, int warm,
+__device__ __forceinline__ void spec_entry(const SweepBuffers& buf, const ModelDev<KP>& m, uint64_t first, int warm,
                                            double (&a)[KP]) {
-  constexpr int L = Layout::L, C = Layout::C;
   const int K = m.K;
-  const uint64_t first = (tile * C + (uint64_t)c) * L;  // block index of the chunk's first block
-  uint64_t b0 = first;                                  // first warm-up block
+  uint64_t b0 = first;  // first warm-up block (`first`: block index of the piece's first block)
   if (first <= (uint64_t)warm) {
     b0 = 0;
     if (buf.seg.world > 1 && buf.seg.rank > 0) {
@@ -1166,7 +1164,10 @@ struct ReplayCfg {
 //   kSpec    speculative pass: the vector entering the chunk is a guess (spec_entry), k_fwd_fixup repairs the rows;
 //            the log-likelihood terms go to `lognorm` per block and are summed after the repair
 template <int KP, bool kExact, bool kLoglik, bool kSpec = false>
-__global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm, int warm) {
+//            and the warp takes one PIECE of `sub` steps (8, 16 or 32) of every chunk of a tile at a time — the chunk
+//            length is no longer tied to anything, and shorter pieces mean more warps for a latency-bound recursion
+__global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm, int warm,
+                                                          int sub) {
   pdl_enter();
   using Cfg = ReplayCfg<KP>;
   constexpr int L = Layout::L, C = Layout::C, S = Cfg::kSlab, NS = L / S;
@@ -1193,22 +1194,28 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
     mbar_expect_tx(bar, (uint32_t)Cfg::kStage);
     bulk_g2s(dst, buf.e + off, (uint32_t)Cfg::kStage, bar);
   };
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int nsub = kSpec ? L / sub : 1;               // pieces per chunk
+  const int slab0_of = kSpec ? sub / S : NS;          // slabs per piece
+  for (uint64_t unit = blockIdx.x; unit < ntiles * nsub; unit += gridDim.x) {
+    const uint64_t tile = unit / nsub;
+    const int piece = (int)(unit % nsub);
+    const int s_lo = piece * slab0_of, s_hi = s_lo + slab0_of;  // this unit's slabs
+    const int t_lo = s_lo * S;
     if (lane == 0) {
       fence_proxy_async();
-      issue_slab(tile, 0, stage0, &s_bar[0]);
-      issue_slab(tile, 1, stage1, &s_bar[1]);
+      issue_slab(tile, s_lo, stage0, &s_bar[0]);
+      issue_slab(tile, s_lo + 1, stage1, &s_bar[1]);
     }
     const int c = lane;
     const uint64_t first = tile * Layout::TB + (uint64_t)c * L;
-    int steps = 0;
+    int steps = 0;  // steps of the chunk that exist (the piece covers [t_lo, t_lo + slab0_of * S) of them)
     if (first < B) steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
     // ---- vector entering chunk c
     double a[KP];
     if constexpr (kSpec) {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = 0.0;
-      if (steps > 0) spec_entry<KP>(buf, m, tile, c, warm, a);
+      if (steps > t_lo) spec_entry<KP>(buf, m, first + (uint64_t)t_lo, warm, a);
     } else {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = buf.tile_ain[tile * KP + j];
@@ -1219,8 +1226,8 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
       }
     }
 #pragma unroll 1
-    for (int slab = 0; slab < NS; ++slab) {
-      const int bi = slab & 1;
+    for (int slab = s_lo; slab < s_hi; ++slab) {
+      const int bi = (slab - s_lo) & 1;
       if (bi == 0) {
         mbar_wait(&s_bar[0], ph0);
         ph0 ^= 1u;
@@ -1289,7 +1296,7 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
         }
       }
       __syncwarp();
-      if (slab + 2 < NS && lane == 0) {
+      if (slab + 2 < s_hi && lane == 0) {
         fence_proxy_async();
         issue_slab(tile, slab + 2, bi ? stage1 : stage0, bi ? &s_bar[1] : &s_bar[0]);
       }
@@ -1311,12 +1318,12 @@ __global__ void __launch_bounds__(32) k_fwd_replay_prefix(SweepBuffers buf, Mode
 // last row it holds (+ its block count; all-gather of KP + 1 words, inside this kernel when the peer mailboxes are up),
 // then restarts its first chunk from the last row of the nearest earlier rank that owns blocks.  The published row is
 // right if the rank's own chunk 0 meets its guess before its last block (nothing behind chunk 0 then depended on the
-// guess); a rank with a single chunk cannot promise that and reports a failure.
+// guess); a rank with a single piece cannot promise that and reports a failure.
 //   phase 1: publish only (the caller runs the all-gather), 2: repair only, 3: publish + embedded exchange + repair
 template <int KP, bool kExact>
 __device__ __forceinline__ void fwd_fixup_head_cta(const SweepBuffers& buf, const ModelDev<KP>& m, int phase, int stride,
-                                                   unsigned long long seq) {
-  constexpr int L = Layout::L;
+                                                   unsigned long long seq, int sub) {
+  const int L = sub;  // the rank's first piece
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   if (phase & 1) {
     if (threadIdx.x == 0) {
@@ -1389,9 +1396,9 @@ __device__ __forceinline__ void fwd_fixup_head_cta(const SweepBuffers& buf, cons
 
 template <int KP, bool kExact>
 __global__ void __launch_bounds__(256) k_fwd_fixup_head(SweepBuffers buf, ModelDev<KP> m, int phase, int stride,
-                                                        unsigned long long seq) {
+                                                        unsigned long long seq, int sub) {
   pdl_enter();
-  fwd_fixup_head_cta<KP, kExact>(buf, m, phase, stride, seq);
+  fwd_fixup_head_cta<KP, kExact>(buf, m, phase, stride, seq, sub);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1405,33 +1412,37 @@ __global__ void __launch_bounds__(256) k_fwd_fixup_head(SweepBuffers buf, ModelD
 //            repairs the rank's first chunk (fwd_fixup_head_cta) in the same launch
 template <int KP, bool kExact, bool kLoglik, bool kHead = false>
 __global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP> m, double* __restrict__ lognorm,
-                                                   unsigned long long seq) {
+                                                   unsigned long long seq, int sub) {
   pdl_enter();
   constexpr int L = Layout::L, C = Layout::C;
   static_assert(!kLoglik || kExact, "the log-likelihood needs the forward sums");
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
-  const uint64_t nchunks = (B + L - 1) / L;
-  const uint64_t rounded = (nchunks + blockDim.x - 1) / blockDim.x * blockDim.x;
+  // pieces of `sub` blocks, the unit of the speculative pass; thread index = ((tile, piece), chunk): the 32 lanes of a
+  // warp take the same piece of the 32 chunks of a tile, whose rows sit next to each other
+  const int nsub = L / sub;
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const uint64_t nthreads = ntiles * (uint64_t)nsub * C;  // a multiple of 32
+  const uint64_t rounded = (nthreads + blockDim.x - 1) / blockDim.x * blockDim.x;
   double ll = 0.0;
   unsigned fails = 0;
   for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rounded; g += (uint64_t)gridDim.x * blockDim.x) {
-    if (g >= nchunks) continue;
-    const uint64_t tile = g / C;
+    if (g >= nthreads) continue;
     const int c = (int)(g % C);
-    const uint64_t first = g * L;
-    const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
+    const uint64_t unit = g / C, tile = unit / nsub;
+    const int t_lo = (int)(unit % nsub) * sub;
+    const uint64_t first = tile * Layout::TB + (uint64_t)c * L + t_lo;
+    if (first >= B) continue;
+    const int steps = (B - first) < (uint64_t)sub ? (int)(B - first) : sub;
     const bool last_chunk = first + steps == B;
-    const bool have_entry = g > 0;  // (segment mode: chunk 0 of a later rank is repaired by k_fwd_fixup_head)
+    const bool have_entry = first > 0;  // (segment mode: piece 0 of a later rank is repaired by k_fwd_fixup_head)
     if (have_entry) {
-      const uint64_t pt = c > 0 ? tile : tile - 1;
-      const int pc = c > 0 ? c - 1 : C - 1;
       double a[KP];
-      const double* ap = buf.alpha + Layout::at(pt, pc, L - 1) * KP;
+      const double* ap = buf.alpha + Layout::perm(first - 1) * KP;
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = ap[j];
 #pragma unroll 1
       for (int t = 0; t < steps; ++t) {
-        const uint64_t p = Layout::at(tile, c, t);
+        const uint64_t p = Layout::at(tile, c, t_lo + t);
         double ev[KP], as[KP];
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
@@ -1480,7 +1491,7 @@ __global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP
       }
     }
     if (kLoglik) {
-      for (int t = 0; t < steps; ++t) ll += lognorm[Layout::at(tile, c, t)];
+      for (int t = 0; t < steps; ++t) ll += lognorm[Layout::at(tile, c, t_lo + t)];
     }
   }
   if (kLoglik) {
@@ -1493,7 +1504,7 @@ __global__ void __launch_bounds__(128) k_fwd_fixup(SweepBuffers buf, ModelDev<KP
   }
   if (fails) atomicAdd(&buf.out_u64[spec_fail_slot<KP>()], (unsigned long long)fails);
   if constexpr (kHead) {
-    if (last_cta_arrives(buf.tickets + kTicketFixup)) fwd_fixup_head_cta<KP, kExact>(buf, m, 3, KP + 1, seq);
+    if (last_cta_arrives(buf.tickets + kTicketFixup)) fwd_fixup_head_cta<KP, kExact>(buf, m, 3, KP + 1, seq, sub);
   }
 }
 
@@ -1959,7 +1970,7 @@ __global__ void __launch_bounds__(32) k_fwd_replay(SweepBuffers buf, ModelDev<KP
     if constexpr (kSpec) {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = 0.0;
-      if (steps > 0) spec_entry<KP>(buf, m, tile, c, warm, a);
+      if (steps > 0) spec_entry<KP>(buf, m, first, warm, a);
     } else {
 #pragma unroll
       for (int j = 0; j < KP; ++j) a[j] = s_ain[c][j];
@@ -2252,15 +2263,22 @@ template <int KP, int kScan>
 __global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf, unsigned long long seq) {
   pdl_enter();
   constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W;
+  static_assert(L == 32, "quarter chunks of 8 blocks");
   const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
   const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t tile = warp; tile < ntiles; tile += nwarps) {
+    // from the chunk's last block down: G = f_t o (f_{t+1} o ... o f_31); the maps of the last 24, 16 and 8 blocks are
+    // kept for the replay, whose threads take a quarter chunk each
     Map<KP> G = Map<KP>::identity();
-#pragma unroll 4
-    for (int t = 0; t < L; ++t) G = G.after(Map<KP>::load(buf.maps + Layout::at(tile, lane, t) * MB));
+#pragma unroll
+    for (int q4 = 3; q4 >= 0; --q4) {
+#pragma unroll
+      for (int t = 8 * q4 + 7; t >= 8 * q4; --t) G = Map<KP>::load(buf.maps + Layout::at(tile, lane, t) * MB).after(G);
+      if (q4 > 0) G.store(buf.chunk_submaps + ((tile * C + lane) * 3 + (q4 - 1)) * MB);
+    }
     Map<KP> inc = G;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -2469,7 +2487,8 @@ __global__ void __launch_bounds__(kReduceThreads) k_reduce_partial(SweepBuffers 
   }
 }
 
-// k_bwd_replay_reduce (K <= 8): k_bwd_replay and the statistics pass in one kernel, thread per chunk.  Walking its 32
+// k_bwd_replay_reduce (K <= 8): k_bwd_replay and the statistics pass in one kernel, thread per quarter chunk (the chunk-map
+// kernel keeps the maps of a chunk's later quarters: a latency-bound walk wants many short ones).  Walking its 8
 // blocks backwards the thread knows every block's state and its successor's, so transitions are counted on the way; the
 // sums go to the thread's own per-state slots in shared memory, indexed by the state (4 read-modify-writes per block;
 // K-way selects into registers cost 4 K, and "flush when the state changes" does not help a warp whose 32 lanes change
@@ -2499,22 +2518,31 @@ __global__ void __launch_bounds__(128) k_bwd_replay_reduce(SweepBuffers buf, uin
   const bool seg = buf.seg.world > 1;
   const bool has_after = seg && seg_later_blocks(buf.seg);
   const bool first_rank = !seg || buf.seg.rank == 0;
-  for (uint64_t ch = (uint64_t)blockIdx.x * NT + tid; ch < nch; ch += (uint64_t)gridDim.x * NT) {
-    const uint64_t tile = ch / C;
-    const int c = (int)(ch % C);
-    const uint64_t first = ch * L;
-    const int steps = (B - first) < (uint64_t)L ? (int)(B - first) : L;
-    // state following this chunk = (maps of the later chunks of the tile)(state following the tile)
+  // thread index = ((tile, quarter), chunk): the 32 lanes of a warp take the same quarter of the 32 chunks of a tile
+  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
+  const uint64_t nthreads = ntiles * 4 * C;
+  for (uint64_t g = (uint64_t)blockIdx.x * NT + tid; g < nthreads; g += (uint64_t)gridDim.x * NT) {
+    const int c = (int)(g % C);
+    const uint64_t unit = g / C, tile = unit / 4;
+    const int q4 = (int)(unit % 4), t_lo = 8 * q4;
+    const uint64_t ch = tile * C + c;
+    const uint64_t first = ch * L + t_lo;  // first block of the quarter
+    if (first >= B) continue;
+    const int steps = (B - first) < 8ull ? (int)(B - first) : 8;
+    // state following the chunk = (maps of the later chunks of the tile)(state following the tile); the state following
+    // the quarter = (map of the chunk's later quarters)(state following the chunk)
     uint32_t next = Map<KP>::load(buf.chunk_maps + ch * MB).get(buf.tile_qin[tile]);
-    bool has_next = (first + steps < B) || has_after;  // does the chunk's last block have a successor anywhere?
-    for (int t0 = steps - 1; t0 >= 0; t0 -= 8) {
+    if (q4 < 3) next = Map<KP>::load(buf.chunk_submaps + (ch * 3 + q4) * MB).get(next);
+    bool has_next = (first + steps < B) || has_after;  // does the quarter's last block have a successor anywhere?
+    {
+      const int t0 = steps - 1;
       Map<KP> mp[8];
       uint32_t nn[8];
       double2 vv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (t0 - i >= 0) {
-          const uint64_t p = Layout::at(tile, c, t0 - i);
+          const uint64_t p = Layout::at(tile, c, t_lo + t0 - i);
           mp[i] = Map<KP>::load(buf.maps + p * MB);
           nn[i] = buf.bN[p];
           vv[i] = buf.bS[p];
@@ -2524,7 +2552,7 @@ __global__ void __launch_bounds__(128) k_bwd_replay_reduce(SweepBuffers buf, uin
       for (int i = 0; i < 8; ++i) {
         if (t0 - i >= 0) {
           const uint32_t q = mp[i].get(next);
-          buf.states[Layout::at(tile, c, t0 - i)] = (uint8_t)q;
+          buf.states[Layout::at(tile, c, t_lo + t0 - i)] = (uint8_t)q;
           // FB.hpp:177,182-184: N - 1 self transitions inside the block, one transition to the successor
           unsigned long long dg = (unsigned long long)(nn[i] - 1u);
           if (has_next) {
@@ -2908,11 +2936,12 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
   if (cb) cb(user, "bwd_replay");
   const int gp = grid_for((nb + Layout::L - 1) / Layout::L, 128, l.sms, 16);
   if constexpr (KP <= 8) {
-    if (reduce_too != nullptr && b.tickets != nullptr) {  // states and statistics in one kernel
+    if (reduce_too != nullptr && b.tickets != nullptr) {  // states and statistics in one kernel, thread per quarter chunk
+      const int gq = grid_for(ntiles * Layout::C * 4, 128, l.sms, 8);
       if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
-        launch_k(k_bwd_replay_reduce<KP, 2>, gp, 128, 0, s, b, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
+        launch_k(k_bwd_replay_reduce<KP, 2>, gq, 128, 0, s, b, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
       else
-        launch_k(k_bwd_replay_reduce<KP, 1>, gp, 128, 0, s, b, (uint32_t)0, 0ull);
+        launch_k(k_bwd_replay_reduce<KP, 1>, gq, 128, 0, s, b, (uint32_t)0, 0ull);
       *reduce_too = true;
       return launches;
     }
@@ -3014,14 +3043,16 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     double* const lognorm = reinterpret_cast<double*>(b.maps);  // per-block scratch until k_bwd_maps writes the maps
     stage("fwd_spec");
     const int gr = grid_for(ntiles, 1, l.sms, 32);
+    const int sub = kPrefix ? l.spec_sub : Layout::L;                    // piece length of the speculative pass
+    const int gs = grid_for(ntiles * (Layout::L / sub), 1, l.sms, 32);  // one warp per (tile, piece)
     if constexpr (kPrefix) {
       using RCfg = ReplayCfg<KP>;
       if (loglik)
-        launch_k(k_fwd_replay_prefix<KP, true, true, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm);
+        launch_k(k_fwd_replay_prefix<KP, true, true, true>, gs, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm, sub);
       else if (rows)
-        launch_k(k_fwd_replay_prefix<KP, true, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm);
+        launch_k(k_fwd_replay_prefix<KP, true, false, true>, gs, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm, sub);
       else
-        launch_k(k_fwd_replay_prefix<KP, false, false, true>, gr, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm);
+        launch_k(k_fwd_replay_prefix<KP, false, false, true>, gs, 32, RCfg::kSmem, s, b, m, lognorm, (int)l.spec_warm, sub);
     } else {
       if (loglik)
         launch_k(k_fwd_replay<KP, true, true>, gr, 32, 0, s, b, m, lognorm, (int)l.spec_warm);
@@ -3030,34 +3061,34 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     }
     ++launches;
     stage("fwd_fixup");
-    const int gf = grid_for(ntiles * Layout::C, 128, l.sms, 8);
+    const int gf = grid_for(ntiles * Layout::C * (Layout::L / sub), 128, l.sms, 8);
     bool head_done = false;
     if (loglik) {
-      launch_k(k_fwd_fixup<KP, true, true>, gf, 128, 0, s, b, m, lognorm, 0ull);
+      launch_k(k_fwd_fixup<KP, true, true>, gf, 128, 0, s, b, m, lognorm, 0ull, sub);
       launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gf, b.out_f64 + 2 * KP);
       ++launches;
     } else if (seg && b.seg.p2p != nullptr && b.tickets != nullptr) {
       // split sequence: the repair of the rank's first chunk (one all-gather of K + 1 words) rides in the last CTA
-      launch_k(k_fwd_fixup<KP, !kPrefix, false, true>, gf, 128, 0, s, b, m, lognorm, l.next_seq(l.exchange_user, kExchangeOps));
+      launch_k(k_fwd_fixup<KP, !kPrefix, false, true>, gf, 128, 0, s, b, m, lognorm, l.next_seq(l.exchange_user, kExchangeOps), sub);
       head_done = true;
     } else if (rows || !kPrefix) {
-      launch_k(k_fwd_fixup<KP, true, false>, gf, 128, 0, s, b, m, lognorm, 0ull);
+      launch_k(k_fwd_fixup<KP, true, false>, gf, 128, 0, s, b, m, lognorm, 0ull, sub);
     } else {
-      launch_k(k_fwd_fixup<KP, false, false>, gf, 128, 0, s, b, m, lognorm, 0ull);
+      launch_k(k_fwd_fixup<KP, false, false>, gf, 128, 0, s, b, m, lognorm, 0ull, sub);
     }
     ++launches;
     if (seg && !head_done) {  // chunk 0 of the later ranks, from the last row of the rank before
       stage("fwd_fixup_head");
       constexpr bool kEx = !kPrefix;
       if (b.seg.p2p != nullptr) {
-        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)3, (int)(KP + 1), l.next_seq(l.exchange_user, kExchangeOps));
+        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)3, (int)(KP + 1), l.next_seq(l.exchange_user, kExchangeOps), sub);
         ++launches;
       } else {
-        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)1, (int)(KP * KP + KP), 0ull);
+        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)1, (int)(KP * KP + KP), 0ull, sub);
         stage("exchange_ops");
         if (l.exchange(l.exchange_user, kExchangeOps) != 0) return -1;
         stage("fwd_fixup_head2");
-        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)2, (int)(KP * KP + KP), 0ull);
+        launch_k(k_fwd_fixup_head<KP, kEx>, 1, 256, 0, s, b, m, (int)2, (int)(KP * KP + KP), 0ull, sub);
         launches += 2;
       }
     }
@@ -3095,13 +3126,13 @@ int sweep_impl(const ModelHost& mh, const SweepBuffers& b, const SweepLaunch& l,
     if constexpr (kPrefix) {
       using RCfg = ReplayCfg<KP>;
       if (loglik) {
-        launch_k(k_fwd_replay_prefix<KP, true, true>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0);
+        launch_k(k_fwd_replay_prefix<KP, true, true>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0, (int)Layout::L);
         launch_k(k_sum_partials<KP>, 1, 32, 0, s, b.partials, gr, b.out_f64 + 2 * KP);
         ++launches;
       } else if (rows) {
-        launch_k(k_fwd_replay_prefix<KP, true, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0);
+        launch_k(k_fwd_replay_prefix<KP, true, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0, (int)Layout::L);
       } else {
-        launch_k(k_fwd_replay_prefix<KP, false, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0);
+        launch_k(k_fwd_replay_prefix<KP, false, false>, gr, 32, RCfg::kSmem, s, b, m, (double*)nullptr, (int)0, (int)Layout::L);
       }
     } else {
       if (loglik) {

@@ -101,24 +101,28 @@ int hml_detect_info(hml_t* h, int* mode, uint64_t* hot_subblocks);
 /* How the forward filter (ForwardBackward.hpp:64-125) of a sweep is parallelised.
  *   HML_FORWARD_OPERATORS    scan of K x K operators over chunks, tiles and the sequence: exact for any data, 2 K^3 flop
  *                            per block.
- *   HML_FORWARD_SPECULATIVE  every chunk of 32 blocks runs the reference's vector recursion (2 K^2 flop per block) from
- *                            a guessed start (uniform pushed through the blocks in front of the chunk); a second pass
- *                            restarts every chunk from the last row of its predecessor and rewrites rows until the new
- *                            row is parallel to the stored one (every component within 1e-13 relative).  If a chunk has
- *                            not met its guess by its last block the sweep is run again through the operator scan, so
- *                            the result never depends on the assumption that the filter forgets its start.
+ *   HML_FORWARD_SPECULATIVE  every piece of 8, 16 or 32 blocks runs the reference's vector recursion (2 K^2 flop per
+ *                            block) from a guessed start (uniform pushed through the blocks in front of the piece); a
+ *                            second pass restarts every piece from the last row of its predecessor and rewrites rows
+ *                            until the new row is parallel to the stored one (every component within 1e-13 relative).
+ *                            If a piece has not met its guess by its last block the sweep is run again through the
+ *                            operator scan, so the result never depends on the assumption that the filter forgets its
+ *                            start.
  *   HML_FORWARD_AUTO (default) speculative.  A failed sweep is repeated through the operator scan and the following
- *                            sweeps push their guesses through more blocks (4, 16, 64, and 128 for K > 8; halved again
- *                            after 64 good sweeps); if that is not enough either — blocks of one or two observations
- *                            with levels a sigma apart can take hundreds of blocks to forget — the operator scan takes
- *                            the next 1, 3, 7, ... 63 sweeps before the next attempt.
+ *                            sweeps use longer pieces behind longer warm-ups: (8, 4) -> (16, 16) -> (32, 64) blocks for
+ *                            K <= 8, (32, 8) -> (32, 32) -> (32, 128) above; back down after 64 good sweeps (4 x as
+ *                            many each time that turns out wrong).  If the last level is not enough either — blocks
+ *                            of one or two observations with levels a sigma apart can take hundreds of blocks to
+ *                            forget — the operator scan takes the next 1, 3, 7, ... 63 sweeps before the next attempt.
  * A split sequence speculates too (the first chunk of a rank is repaired from the last row of the rank before: one
  * all-gather of K + 1 words instead of the K x K segment operators), except when the log-likelihood is asked for.
  * Mixture sweeps have no forward filter; the fused kernel uses the operator scan.  hml_forward_info: the mode, the
- * number of speculative sweeps so far and how many of them had to be repeated. */
+ * number of speculative sweeps so far, how many of them had to be repeated, and the piece length and warm-up the next
+ * speculative sweep would use (any pointer may be NULL). */
 enum { HML_FORWARD_AUTO = 0, HML_FORWARD_OPERATORS = 1, HML_FORWARD_SPECULATIVE = 2 };
 int hml_set_forward_mode(hml_t* h, int mode);
-int hml_forward_info(hml_t* h, int* mode, uint64_t* speculative_sweeps, uint64_t* failures);
+int hml_forward_info(hml_t* h, int* mode, uint64_t* speculative_sweeps, uint64_t* failures, int* piece_blocks,
+                     int* warmup_blocks);
 int hml_nr_blocks(const hml_t* h, uint64_t* nblocks);
 /* Copies the current block structure to host: starts[nblocks] (block b = [starts[b], starts[b+1])
  * with starts[nblocks] = T implied), sum[nblocks], sumsq[nblocks].  Any pointer may be NULL. */

@@ -44,10 +44,11 @@ def test_speculative_sweep_vs_oracle_and_operator_scan(dev, T, K, L, thr, spacin
     dev.set_forward_mode(capi.FORWARD_SPECULATIVE)
     b, _ = _check_fb(dev, x, mu, var, A, pi, thr, 1)
     _, n1, f1 = dev.forward_info()
-    # (levels one sigma apart or blocks of single observations: the filter needs more than the 4 + 31 blocks the first
-    # attempt gives it — the sweep then repeats itself through the operator scan and the next one warms up longer)
-    hard = spacing < 1.0 or L == 1
-    assert n1 == n0 + 1 and (f1 == f0 or (hard and f1 == f0 + 1)), "the speculative pass should hold on informative data"
+    # (the first attempt uses pieces of 8 blocks behind 4 warm-up blocks: enough where a block or two pin the state down;
+    # levels one sigma apart or blocks of a few observations need more — the sweep then repeats itself through the
+    # operator scan and the next one would use longer pieces and warm-ups)
+    easy = spacing >= 1.0 and L >= 300 and T <= 200_000
+    assert n1 == n0 + 1 and f1 - f0 <= (0 if easy else 1), "the speculative pass should hold on informative data"
     assert np.array_equal(dev.states(), states_a)
     assert rel_err(dev.rows(K), rows_a, scale=1e-300) <= 1e-11   # every component, however small
     assert abs(a["loglik"] - b["loglik"]) <= 1e-12 * abs(a["loglik"])
@@ -85,7 +86,7 @@ def test_auto_mode_backs_off_after_a_failure_and_comes_back(dev):
     dev.create_blocks(0.5)
     dev.set_forward_mode(capi.FORWARD_AUTO)
     _, n0, f0 = dev.forward_info()
-    for i in range(3):                                         # speculative with warm-ups of 4, 16, 64 blocks: all fail
+    for i in range(3):                                         # speculative at the three levels (pieces of 8, 16, 32 blocks): all fail
         dev.fb_sweep(*flat, use_self=1, seed=1, sweep=i)
         assert dev.forward_info()[1:] == (n0 + 1 + i, f0 + 1 + i)
     dev.fb_sweep(*flat, use_self=1, seed=1, sweep=4)           # operator scan (one sweep of back-off)
@@ -121,7 +122,7 @@ def test_longer_warm_ups_take_over_on_weakly_informative_blocks(dev):
         out = dev.fb_sweep(mu, var, A, pi, use_self=1, seed=4, sweep=i)
         assert out["nblocks"] == B and np.array_equal(dev.states(), want[i]), i
     _, n1, f1 = dev.forward_info()
-    assert 1 <= f1 - f0 <= 3 and n1 - n0 >= 6          # warm-ups of 4 and 16 fail, 64 hold
+    assert 1 <= f1 - f0 <= 3 and n1 - n0 >= 6          # pieces of 8 and 16 blocks fail, 32 behind 64 warm-up blocks hold
     assert dev.forward_info()[1:] == (before[1] + 1, before[2])   # the last sweep was speculative and held
 
 

@@ -11,3 +11,5 @@ r = d.get("roofline") or {}
 print("roofline", r.get("kernel"), "frac", r.get("frac"), "traffic", r.get("traffic"), "| clocks", d["clocks"]["sm_mhz"],
       d["clocks"]["reasons"], "| invariants", d.get("invariants_ok"))
 print("cpu_baseline", d.get("cpu_baseline"))
+if d.get("forward_filter"):
+    print("forward filter", d["forward_filter"]["after_timed_regions"], "->", d["forward_filter"]["after_stage_pass"])
