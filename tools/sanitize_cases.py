@@ -1,7 +1,8 @@
 """A reduced selection of the GPU suite for compute-sanitizer (tools/gpu.sh sanitize): one case per kernel family,
 sized so that `--tool memcheck` and `--tool racecheck` finish in minutes — load (univariate, multivariate, non-power-of-
 two lengths), the three boundary-detection modes and a candidate-list rebuild, block statistics, the multi-kernel sweep
-for K = 5 (cluster tile scan, replay and Philox, log-likelihood and kept rows), K = 20 (wide path) and multivariate data,
+for K = 5 (operator scan and speculative filter incl. its fall-back, replay and Philox, log-likelihood and kept rows; the
+kernels whose last CTA finishes the step), K = 20 (wide path) and multivariate data,
 the mixture sampler, runs and device-side state marginals of recorded sweeps, the persistent fused sweep and the
 device-resident chain (spin barriers across CTAs, shared-memory hand-offs), capacity growth and a handle reload.
 Every result is still checked against the oracle where that is cheap, so a sanitizer-clean run is also a correct one."""
@@ -52,6 +53,19 @@ def main():
         assert out["trans"].sum() == T
     out = h.mix_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=0.8, seed=3, sweep=9)
     assert out["counts"].sum() == T
+    # ---- the forward filter both ways (operator scan; speculative pieces + repair pass), and a model on which the
+    # speculative pass has to give up and the sweep repeats itself through the operator scan
+    B = h.create_blocks(thr)
+    for mode in (capi.FORWARD_OPERATORS, capi.FORWARD_SPECULATIVE):
+        h.set_forward_mode(mode)
+        out = h.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_LOGLIK | capi.SWEEP_KEEP_ROWS, replay=u)
+        assert np.array_equal(h.states(), ref["states"]) and np.array_equal(out["trans"], ref["trans"]), mode
+    flat_var = np.full(5, 1e6, np.float32)
+    flat_A = (np.full((5, 5), 1e-7) + np.eye(5) * (1 - 5e-7)).astype(np.float32)
+    failed = h.forward_info()[2]
+    out = h.fb_sweep(mu, flat_var, flat_A, pi, replay=u)
+    assert h.forward_info()[2] == failed + 1 and out["trans"].sum() == T
+    h.set_forward_mode(capi.FORWARD_AUTO)
     print("K=5 sweeps ok", flush=True)
     # ---- recorded sweeps: runs + marginals on the device
     h.marginals_reset(5)
@@ -91,6 +105,10 @@ def main():
     mu3, var3, A3, pi3 = model_guess(3, seed=3)
     out = h.fb_sweep(mu3, var3, A3, pi3, flags=capi.SWEEP_DYNAMIC, threshold=0.1, seed=1, sweep=0)
     assert out["nblocks"] > 65536 and out["trans"].sum() == 300_000
+    # every observation a block: more tiles than SMs, i.e. block maps, chunk maps + scan and replay + statistics as
+    # separate launches (short lists take the CTA-per-tile map kernel)
+    out = h.fb_sweep(mu3, var3, A3, pi3, flags=capi.SWEEP_DYNAMIC, threshold=0.0, seed=1, sweep=1)
+    assert out["nblocks"] == 300_000 and out["trans"].sum() == 300_000
     h.load(x[:20000])
     out = h.fb_sweep(mu, var, A, pi, flags=capi.SWEEP_DYNAMIC, threshold=0.8, seed=1, sweep=0)
     assert out["trans"].sum() == 20000
