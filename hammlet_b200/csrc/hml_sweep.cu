@@ -8,15 +8,20 @@
 //   k_block_emit   per block: (N, sum x, sum x^2) gathered from the integral arrays
 //                  (Statistics/IntegralArray.hpp:104-124), emission terms e_s = exp(E_s - max E)
 //                  (EFD.hpp:23-38, FB.hpp:74-84) and the self-transition rescale A_ss^(N-1) (FB.hpp:115-119)
-//   k_fwd_chunks   forward filter as a scan of KxK operators M_t = A diag(e_t): each chunk of 32
-//                  blocks is reduced to one operator (K independent row recursions, exact
-//                  power-of-two rescaling), 32 chunk operators to one tile operator
-//   k_fwd_tilescan single CTA: prefix over tile operators -> normalised forward vector entering each tile
-//   k_fwd_replay   per chunk: the reference's vector recursion from the exact incoming vector; emits,
-//                  per block, the backward map j -> i = discrete_distribution(alpha'_t(.) A(., j))(u_t)
-//                  and the composed map of the chunk (backward sampling as map composition)
-//   k_bwd_scan     single CTA: suffix composition of chunk maps -> state following each chunk
-//   k_bwd_replay   per chunk: q_t = f_t[q_{t+1}]
+//   forward filter, speculative (default): k_fwd_replay_prefix / k_fwd_replay with kSpec run the reference's vector
+//                  recursion per piece of 8-32 blocks from a guessed start, k_fwd_fixup repairs the heads of the pieces
+//                  from the true row of the block before and reports pieces that did not meet their guess (the host
+//                  then repeats the sweep through the operator scan); on a split sequence its last CTA repairs the
+//                  rank's first piece from the previous rank's last row
+//   forward filter, operator scan (fallback): k_fwd_chunks* reduce each chunk of 32 blocks to one K x K operator
+//                  M = prod A diag(e_t) (K independent row recursions, exact power-of-two rescaling) and each tile
+//                  to one operator, k_fwd_tilescan* scan the tile operators, k_fwd_replay* run the vector recursion
+//                  from the exact incoming vector
+//   k_bwd_maps     per block: the backward map j -> i = discrete_distribution(alpha'_t(.) A(., j))(u_t)
+//   k_bwd_chunkmaps  composed maps per chunk / quarter chunk / tile; its last CTA scans the tile maps (bwd_scan_cta)
+//                  (k_bwd_maps_tile: both in one CTA-per-tile launch for short block lists)
+//   k_bwd_replay_reduce (K <= 8)  per quarter chunk: q_t = f_t[q_{t+1}] and the statistics pass in the same walk;
+//                  k_bwd_replay + k_reduce_partial otherwise
 //   k_mix_sample   mixture sampler: independent categorical draw per block
 //   k_reduce_*     per-state (N, sum x, sum x^2), KxK transition counts incl. the phantom 0 -> q0
 //                  transition, occupancy (FB.hpp:177-200); deterministic summation order
