@@ -2977,14 +2977,15 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
   bool tiled = false;
   if constexpr (KP <= 8) {
     // block maps, chunk maps and the scan of the tile maps in one launch (a CTA per tile) — only where the block list
-    // is short (at most one tile per SM): with 1 394 tiles (C4 on one GPU) the two launches are 11 us faster, with 697
-    // (two GPUs) still 3 us — the barriers of the tile kernel cost the map kernel its occupancy.
+    // is short: the barriers of the tile kernel cost the map kernel occupancy, about 12 ns per tile, and the launch it
+    // saves is worth about 6 us (measured: 1 394 tiles, C4 on one GPU: 11 us slower than two launches; 697 tiles, two
+    // GPUs: 3 us slower), so the tile kernel takes lists of up to three tiles per SM.
     // HML_MAPS_TILE=always|never overrides for measurements.
     static const int tile_mode = [] {
       const char* e = getenv("HML_MAPS_TILE");
       return e == nullptr ? 0 : (strcmp(e, "always") == 0 ? 1 : (strcmp(e, "never") == 0 ? -1 : 0));
     }();
-    const bool want_tiled = tile_mode > 0 || (tile_mode == 0 && ntiles <= (uint64_t)l.sms);
+    const bool want_tiled = tile_mode > 0 || (tile_mode == 0 && ntiles <= (uint64_t)3 * l.sms);
     if (want_tiled && !have_maps && b.tickets != nullptr && !(b.seg.world > 1 && b.seg.p2p == nullptr)) {
       if (cb) cb(user, "bwd_maps");
       const int gt = grid_for(ntiles, 1, l.sms, 4);
