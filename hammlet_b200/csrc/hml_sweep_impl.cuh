@@ -2306,77 +2306,6 @@ __global__ void __launch_bounds__(128) k_bwd_chunkmaps(SweepBuffers buf, unsigne
   }
 }
 
-// k_bwd_maps_tile (K <= 8): k_bwd_maps and k_bwd_chunkmaps in one launch.  A CTA takes whole tiles: its 256 threads
-// write the 1024 block maps (four rounds of 8 steps x 32 chunks), keeping a copy in shared memory; then warp w composes
-// quarter w (8 maps) of each of the 32 chunks, warp 0 joins the quarters (the maps of a chunk's last 24, 16, 8 blocks for
-// the replay, the chunk map), scans the 32 chunk maps by shuffles and writes the tile map.  The CTA that arrives last
-// scans the tile maps (bwd_scan_cta), as in k_bwd_chunkmaps.
-template <int KP, bool kRows, int kScan>
-__global__ void __launch_bounds__(256, KP <= 5 ? 4 : 1) k_bwd_maps_tile(SweepBuffers buf, ModelDev<KP> m, uint64_t seed, uint64_t sweep,
-                                                                        unsigned long long seq) {
-  pdl_enter();
-  static_assert(KP <= 8 && Layout::L == 32 && Layout::C == 32, "one 8-byte map per block, 32 x 32 tiles");
-  constexpr int C = Layout::C, MB = 8;
-  __shared__ double s_tab[64];  // 2^(j/64) for exp_nonpos
-  __shared__ uint64_t s_map[Layout::TB];  // [step][chunk]
-  __shared__ uint64_t s_quarter[4][C];    // composed map of quarter w of chunk c
-  exp_table_load(s_tab);
-  __syncthreads();
-  const uint64_t B = device_nblocks(buf.nblocks, buf.capacity);
-  const uint64_t ntiles = (B + Layout::TB - 1) / Layout::TB;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-#pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
-      const uint64_t p = tile * Layout::TB + (uint64_t)r * 256 + tid;
-      const Map<KP> fm = block_map<KP, kRows>(buf, m, p, Layout::inv(p), B, seed, sweep, s_tab);
-      fm.store(buf.maps + p * MB);
-      s_map[r * 256 + tid] = fm.w[0];
-    }
-    __syncthreads();
-    if (warp < 4) {  // quarter `warp` of chunk `lane`: f_{8w} o ... o f_{8w+7}
-      Map<KP> G = Map<KP>::identity();
-#pragma unroll
-      for (int t = 8 * warp + 7; t >= 8 * warp; --t) {
-        Map<KP> f;
-        f.w[0] = s_map[t * C + lane];
-        G = f.after(G);
-      }
-      s_quarter[warp][lane] = G.w[0];
-    }
-    __syncthreads();
-    if (warp == 0) {
-      Map<KP> G;
-      G.w[0] = s_quarter[3][lane];
-#pragma unroll
-      for (int q4 = 3; q4 >= 1; --q4) {
-        G.store(buf.chunk_submaps + ((tile * C + lane) * 3 + (q4 - 1)) * MB);  // map of the blocks from step 8 q4 on
-        Map<KP> f;
-        f.w[0] = s_quarter[q4 - 1][lane];
-        G = f.after(G);
-      }
-      Map<KP> inc = G;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        Map<KP> other;
-        other.w[0] = __shfl_down_sync(0xffffffffu, inc.w[0], o);
-        if (lane + o < 32) inc = inc.after(other);
-      }
-      Map<KP> excl;
-      excl.w[0] = __shfl_down_sync(0xffffffffu, inc.w[0], 1);
-      if (lane == 31) excl = Map<KP>::identity();
-      excl.store(buf.chunk_maps + (tile * C + lane) * MB);
-      if (lane == 0) inc.store(buf.tile_maps + tile * MB);
-    }
-    // (the next round's writes to s_map / s_quarter are behind the two barriers of that round for every warp but 0,
-    // which is the one still reading: it joins them at the first barrier)
-    __syncthreads();
-  }
-  if constexpr (kScan >= 0) {
-    if (last_cta_arrives(buf.tickets + kTicketChunkMaps)) bwd_scan_cta<KP, kScan, 256>(buf, seq);
-  }
-}
-
 // k_bwd_replay: thread per chunk, q_t = f_t[q_{t+1}]  (FB.hpp:140-160)
 template <int KP>
 __global__ void __launch_bounds__(128) k_bwd_replay(SweepBuffers buf) {
@@ -2974,39 +2903,7 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
   const uint64_t ntiles = (nb + Layout::TB - 1) / Layout::TB;
   int launches = 2;
   bool scanned = false;
-  bool tiled = false;
-  if constexpr (KP <= 8) {
-    // block maps, chunk maps and the scan of the tile maps in one launch (a CTA per tile) — only where the block list
-    // is short: the barriers of the tile kernel cost the map kernel occupancy, about 12 ns per tile, and the launch it
-    // saves is worth about 6 us (measured: 1 394 tiles, C4 on one GPU: 11 us slower than two launches; 697 tiles, two
-    // GPUs: 3 us slower), so the tile kernel takes lists of up to three tiles per SM.
-    // HML_MAPS_TILE=always|never overrides for measurements.
-    static const int tile_mode = [] {
-      const char* e = getenv("HML_MAPS_TILE");
-      return e == nullptr ? 0 : (strcmp(e, "always") == 0 ? 1 : (strcmp(e, "never") == 0 ? -1 : 0));
-    }();
-    const bool want_tiled = tile_mode > 0 || (tile_mode == 0 && ntiles <= (uint64_t)3 * l.sms);
-    if (want_tiled && !have_maps && b.tickets != nullptr && !(b.seg.world > 1 && b.seg.p2p == nullptr)) {
-      if (cb) cb(user, "bwd_maps");
-      const int gt = grid_for(ntiles, 1, l.sms, 4);
-      const bool seg = b.seg.world > 1;
-      const unsigned long long seq = seg ? l.next_seq(l.exchange_user, kExchangeMaps) : 0ull;
-      if (rows) {
-        if (seg)
-          launch_k(k_bwd_maps_tile<KP, true, 2>, gt, 256, 0, s, b, m, l.seed, l.sweep, seq);
-        else
-          launch_k(k_bwd_maps_tile<KP, true, 0>, gt, 256, 0, s, b, m, l.seed, l.sweep, seq);
-      } else {
-        if (seg)
-          launch_k(k_bwd_maps_tile<KP, false, 2>, gt, 256, 0, s, b, m, l.seed, l.sweep, seq);
-        else
-          launch_k(k_bwd_maps_tile<KP, false, 0>, gt, 256, 0, s, b, m, l.seed, l.sweep, seq);
-      }
-      tiled = scanned = true;
-      launches += 1 - 1;  // maps (+ chunk maps + scan): one launch; the scan's own launch is not needed
-    }
-  }
-  if (!have_maps && !tiled) {  // k_replay_maps already wrote the block, chunk and tile maps
+  if (!have_maps) {  // k_replay_maps already wrote the block, chunk and tile maps
     launches += 2;
     if (cb) cb(user, "bwd_maps");
     const int gm = grid_for(ntiles * Layout::TB, 256, l.sms, 32);

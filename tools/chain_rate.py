@@ -1,5 +1,5 @@
 """Sweep rate of a Gibbs chain on one GPU for the small and medium configurations, host-driven against
-device-resident: `Chain.run` (C++ host chain: 13 kernels + one host round trip per sweep, parameters drawn on the host
+device-resident: `Chain.run` (C++ host chain: 8 kernels + one host round trip per sweep, parameters drawn on the host
 with libstdc++ <random>) and `hml_chain_run` (parameters on the device; the whole sweep in one persistent kernel where
 the block structure has at most 64 tiles, n sweeps per launch).  One JSON line per configuration.
 usage: python tools/chain_rate.py [c1 c2 c3chr c4over8]"""
