@@ -19,7 +19,6 @@
 //                  from the exact incoming vector
 //   k_bwd_maps     per block: the backward map j -> i = discrete_distribution(alpha'_t(.) A(., j))(u_t)
 //   k_bwd_chunkmaps  composed maps per chunk / quarter chunk / tile; its last CTA scans the tile maps (bwd_scan_cta)
-//                  (k_bwd_maps_tile: both in one CTA-per-tile launch for short block lists)
 //   k_bwd_replay_reduce (K <= 8)  per quarter chunk: q_t = f_t[q_{t+1}] and the statistics pass in the same walk;
 //                  k_bwd_replay + k_reduce_partial otherwise
 //   k_mix_sample   mixture sampler: independent categorical draw per block
