@@ -2507,7 +2507,7 @@ __global__ void __launch_bounds__(128) k_bwd_replay_reduce(SweepBuffers buf, uin
   constexpr int L = Layout::L, C = Layout::C, MB = 8 * Map<KP>::W, NT = 128;
   __shared__ unsigned long long s_trans[KP * KP];
   __shared__ unsigned long long s_n[KP];
-  __shared__ double s_sum[NT / 32][2 * KP];
+  static_assert(NT == 128, "the CTA sums add four slots per lane");
   // [value][state][thread]: a warp's 32 lanes hit 32 different banks whatever their states are
   __shared__ double s_ax[KP][NT], s_aq[KP][NT];
   __shared__ unsigned long long s_an[KP][NT], s_ad[KP][NT];
@@ -2584,37 +2584,35 @@ __global__ void __launch_bounds__(128) k_bwd_replay_reduce(SweepBuffers buf, uin
       }
     }
   }
-  double ax[KP], aq[KP];
-  unsigned long long an[KP], ad[KP];  // observations per state; diagonal transition counts
+  // sums over the CTA's threads: warp w takes the arrays w, w + 4, ... of the 4 K (value, state) arrays — each lane adds
+  // the four slots tid, tid + 32, ... and five shuffle steps finish it (fixed order: deterministic); a thread reducing
+  // its own 4 K slots by shuffles would spend more instructions here than in its eight blocks
+  __syncthreads();
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int a = warp; a < 4 * KP; a += NT / 32) {
+      const int kind = a / KP, st = a % KP;  // 0: sum x, 1: sum x^2, 2: observations, 3: diagonal transitions
+      if (kind < 2) {
+        const double* src = kind == 0 ? s_ax[st] : s_aq[st];
+        double t = (src[lane] + src[lane + 32]) + (src[lane + 64] + src[lane + 96]);
 #pragma unroll
-  for (int s = 0; s < KP; ++s) {
-    ax[s] = s_ax[s][tid];
-    aq[s] = s_aq[s][tid];
-    an[s] = s_an[s][tid];
-    ad[s] = s_ad[s][tid];
+        for (int o = 16; o > 0; o >>= 1) t += shfl_xor_double(t, o);
+        if (lane == 0) buf.partials[(size_t)blockIdx.x * 2 * KP + kind * KP + st] = t;
+      } else {
+        const unsigned long long* src = kind == 2 ? s_an[st] : s_ad[st];
+        unsigned long long t = (src[lane] + src[lane + 32]) + (src[lane + 64] + src[lane + 96]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ax[s] += shfl_xor_double(ax[s], o);
-      aq[s] += shfl_xor_double(aq[s], o);
-      an[s] += __shfl_xor_sync(0xffffffffu, an[s], o);
-      ad[s] += __shfl_xor_sync(0xffffffffu, ad[s], o);
-    }
-  }
-  if ((tid & 31) == 0) {
-#pragma unroll
-    for (int s = 0; s < KP; ++s) {
-      s_sum[tid >> 5][s] = ax[s];
-      s_sum[tid >> 5][KP + s] = aq[s];
-      if (an[s]) atomicAdd(&s_n[s], an[s]);
-      if (ad[s]) atomicAdd(&s_trans[s * KP + s], ad[s]);
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && t) {
+          if (kind == 2)
+            atomicAdd(&s_n[st], t);
+          else
+            atomicAdd(&s_trans[st * KP + st], t);
+        }
+      }
     }
   }
   __syncthreads();
-  if (tid < 2 * KP) {
-    double t = 0.0;
-    for (int wv = 0; wv < NT / 32; ++wv) t += s_sum[wv][tid];
-    buf.partials[(size_t)blockIdx.x * 2 * KP + tid] = t;
-  }
   for (int i = tid; i < KP * KP; i += NT)
     if (s_trans[i]) atomicAdd(&buf.out_u64[KP + i], s_trans[i]);
   for (int i = tid; i < KP; i += NT)
