@@ -334,6 +334,8 @@ int alloc_blocks(hml_t* h, uint64_t cap, int KP) {
   return HML_OK;
 }
 
+size_t result_words(int KP, int D);
+
 SweepBuffers make_buffers(hml_t* h, int KP) {
   SweepBuffers b;
   memset(&b, 0, sizeof(b));
@@ -360,6 +362,13 @@ SweepBuffers make_buffers(hml_t* h, int KP) {
   b.tile_maps = h->tile_maps;
   b.tile_qin = h->tile_qin;
   b.tickets = h->tickets;
+  // (pinned memory is device-addressable under its own address with unified addressing; checked once, else copies)
+  unsigned long long* const mirror = h->world > 1 ? h->stats_gather_host : h->outblk_host;
+  void* dp = nullptr;
+  b.result_host = (mirror != nullptr && cudaHostGetDevicePointer(&dp, mirror, 0) == cudaSuccess && dp == (void*)mirror)
+                      ? mirror : nullptr;
+  if (b.result_host == nullptr) (void)cudaGetLastError();
+  b.result_words = (uint32_t)result_words(KP, h->D);
   b.tile_ops = h->tile_ops;
   b.tile_exp = h->tile_exp;
   b.tile_ain = h->tile_ain;
@@ -444,7 +453,7 @@ unsigned long long next_seq_cb(void* user, int which) {
 }
 
 // 8-byte words of the result block that travel to the host (and between ranks)
-size_t result_words(int KP, int D = 1) {
+size_t result_words(int KP, int D) {
   size_t words = (size_t)KP + (size_t)KP * KP + 1;
   words += words & 1;
   return 2 + words + 2 * KP + 1 + (size_t)(D - 1) * 2 * KP;
@@ -965,7 +974,8 @@ struct SweepResult {
 };
 
 // exchanged: the sweep's last kernel already gathered the result blocks of all ranks into stats_gather
-int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged) {
+// on_host: the sweep's last kernel wrote the block(s) into the pinned mirror itself (SweepBuffers::result_host)
+int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged, bool on_host = false) {
   size_t words = (size_t)KP + (size_t)KP * KP + 1;
   words += words & 1;
   const size_t copy_words = result_words(KP, h->D);
@@ -979,9 +989,10 @@ int fetch_result(hml_t* h, int KP, SweepResult& res, bool exchanged) {
       int rc = exchange(h, kSlotStats, h->outblk, h->stats_gather, copy_words * 8);
       if (rc != HML_OK) return rc;
     }
-    CK(cudaMemcpyAsync(h->stats_gather_host, h->stats_gather, world * copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (!(on_host && exchanged))
+      CK(cudaMemcpyAsync(h->stats_gather_host, h->stats_gather, world * copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
     host = h->stats_gather_host;
-  } else {
+  } else if (!on_host) {
     CK(cudaMemcpyAsync(h->outblk_host, h->outblk, copy_words * 8, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
@@ -1234,7 +1245,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     SweepBuffers b = make_buffers(h, KP);
     b.rows = (flags & HML_SWEEP_KEEP_ROWS) ? h->rows : nullptr;
     b.replay_u = replay ? h->replay_u : nullptr;
-    SweepLaunch l;
+    SweepLaunch l{};
     l.flags = flags;
     l.gather = gather;
     l.mixture = mixture;
@@ -1249,7 +1260,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     // (multivariate data: the sums of the further dimensions are reduced after the first, so the result blocks are
     // exchanged by a kernel of their own afterwards)
     const bool fused_stats = seg && h->p2p && h->D == 1;
-    l.stats_words = fused_stats ? (uint32_t)result_words(KP) : 0u;
+    l.stats_words = fused_stats ? (uint32_t)result_words(KP, 1) : 0u;
     // the speculative forward filter: single handle, forward-backward sweeps; after a failure the operator scan takes
     // the next sweeps (1, 2, 4, ... up to 64 after failures in a row), so data on which the filter does not forget its
     // start pays the wasted pass rarely
@@ -1260,6 +1271,8 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     if (!l.speculate && h->spec_skip > 0 && spec_ok) h->spec_skip--;
     l.spec_warm = spec_warm_of(KP, h->spec_level);
     l.spec_sub = spec_sub_of(KP, h->spec_level);
+    bool on_host = false;
+    l.result_on_host = &on_host;
     const auto hc1 = std::chrono::steady_clock::now();
     int n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
     if (n == -2) return fail(h, HML_ERR_ARG, "unsupported number of states");
@@ -1268,7 +1281,7 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
     CK(cudaGetLastError());
     const auto hc2 = std::chrono::steady_clock::now();
     SweepResult res;
-    rc = fetch_result(h, KP, res, fused_stats);
+    rc = fetch_result(h, KP, res, fused_stats, on_host);
     if (rc != HML_OK) return rc;
     {
       const auto hc3 = std::chrono::steady_clock::now();
@@ -1299,11 +1312,12 @@ int sweep_common(hml_t* h, const hml_model* m, uint32_t flags, float thr, uint64
         l.nblocks_hint = res.local_blocks;
         h->stages.clear();
         h->stage_used = 0;
+        on_host = false;
         n = launch_sweep(mh, b, l, h->stream, stage_cb, h);
         if (n < 0) return h->err.empty() ? fail(h, HML_ERR_CUDA, "carry exchange failed") : HML_ERR_CUDA;
         h->launches += n;
         CK(cudaGetLastError());
-        rc = fetch_result(h, KP, res, fused_stats);
+        rc = fetch_result(h, KP, res, fused_stats, on_host);
         if (rc != HML_OK) return rc;
       } else {
         h->spec_streak = 0;

@@ -134,6 +134,10 @@ struct SweepBuffers {
   uint8_t* tile_maps;       // per tile KPB: composed map of the tile
   uint8_t* tile_qin;        // per tile: state of the block following the tile
   unsigned* tickets;        // kTickets arrival counters (zero between launches): the CTA that arrives last finishes the step
+  // pinned host memory (device-addressable): where the sweep's last kernel leaves the result block — the blocks of all
+  // ranks when it ran the statistics exchange itself — so that no copy has to follow it; result_words words per rank
+  unsigned long long* result_host;
+  uint32_t result_words;
   double* tile_ops;         // per tile KP*KP
   int* tile_exp;            // per tile KP
   double* tile_ain;         // per tile KP: normalised forward vector entering the tile
@@ -238,6 +242,7 @@ struct SweepLaunch {
   bool speculate;        // forward filter by guessed chunk starts + repair pass (result word KP + KP*KP + 1 counts failures)
   int spec_warm;         // blocks in front of a piece its guess is pushed through
   int spec_sub;          // K <= 8: blocks per piece of the speculative pass (8, 16 or 32)
+  bool* result_on_host;  // set when the last kernel wrote the result block(s) to SweepBuffers::result_host
 };
 // Levels of the speculative pass: (piece length, warm-up).  Short pieces give a latency-bound recursion more warps;
 // data on which the filter forgets slowly needs long warm-ups, which only pay with long pieces.  Past the last level

@@ -2619,11 +2619,17 @@ __global__ void __launch_bounds__(128) k_bwd_replay_reduce(SweepBuffers buf, uin
     if (s_n[i]) atomicAdd(&buf.out_u64[i], s_n[i]);
   if (!last_cta_arrives(buf.tickets + kTicketReduce)) return;
   reduce_final_cta<KP, NT>(buf, (int)gridDim.x);
-  if constexpr (kFinal == 2) {
-    __threadfence();
-    __syncthreads();
+  __threadfence();
+  __syncthreads();
+  if constexpr (kFinal == 2)
     p2p_exchange_cta(buf.seg.p2p, kSlotStats, seq, reinterpret_cast<const uint64_t*>(buf.seg.stats_send), stats_words,
                      reinterpret_cast<uint64_t*>(buf.seg.stats_recv));
+  // the result block (of every rank after the exchange) straight into the host's pinned mirror: the kernel's end is then
+  // all the host waits for, no copy behind it
+  if (buf.result_host != nullptr) {
+    const unsigned long long* src = kFinal == 2 ? buf.seg.stats_recv : buf.nblocks;
+    const uint32_t n = kFinal == 2 ? stats_words * (uint32_t)buf.seg.world : buf.result_words;
+    for (uint32_t i = tid; i < n; i += NT) buf.result_host[i] = __ldcg(src + i);
   }
 }
 
@@ -2943,10 +2949,17 @@ int launch_backward(const SweepBuffers& b, const ModelDev<KP>& m, const SweepLau
   if constexpr (KP <= 8) {
     if (reduce_too != nullptr && b.tickets != nullptr) {  // states and statistics in one kernel, thread per quarter chunk
       const int gq = grid_for(ntiles * Layout::C * 4, 128, l.sms, 8);
-      if (b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words)
-        launch_k(k_bwd_replay_reduce<KP, 2>, gq, 128, 0, s, b, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
+      // the host's mirror of the result is written by the kernel when nothing adds to the result afterwards: one data
+      // dimension; on a split sequence only if the kernel runs the statistics exchange itself
+      const bool in_kernel_exchange = b.seg.world > 1 && b.seg.p2p != nullptr && l.stats_words;
+      SweepBuffers bb = b;
+      const bool to_host = b.result_host != nullptr && b.D == 1 && (b.seg.world <= 1 || in_kernel_exchange);
+      if (!to_host) bb.result_host = nullptr;
+      if (in_kernel_exchange)
+        launch_k(k_bwd_replay_reduce<KP, 2>, gq, 128, 0, s, bb, l.stats_words, l.next_seq(l.exchange_user, kExchangeStats));
       else
-        launch_k(k_bwd_replay_reduce<KP, 1>, gq, 128, 0, s, b, (uint32_t)0, 0ull);
+        launch_k(k_bwd_replay_reduce<KP, 1>, gq, 128, 0, s, bb, (uint32_t)0, 0ull);
+      if (to_host && l.result_on_host) *l.result_on_host = true;
       *reduce_too = true;
       return launches;
     }
