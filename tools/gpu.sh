@@ -7,7 +7,7 @@
 #   benchlong       bench.py --steps 300 --warmup 20 --no-cpu-baseline
 #   ref             bench.py --impl reference (default flags)
 #   launches        ncu launch list of bench.py --steps 3 --warmup 3
-#   full            ncu --set full of one whole sweep (13 kernels) + raw csv
+#   full            ncu --set full of one whole sweep (NCU_SKIP / NCU_COUNT select it: 8 kernels -> NCU_SKIP=40 NCU_COUNT=8) + raw csv
 #   traffic         regenerates profiles/ncu_traffic.json from the full capture of this run (stamped with the tree's hash)
 #   sanitize        compute-sanitizer memcheck + racecheck over the reduced selection (tools/sanitize_cases.py)
 #   sanitize_mgpu   memcheck over the reduced 2-GPU segment-split worker, both transports (needs --gpus 2)
