@@ -9,6 +9,7 @@ exactly what the CUDA library all-gathers (hammlet_b200/csrc/hml_api.cu: exchang
   maps    one K -> K map per rank (composition of the per-block backward maps): the state following rank r
           is resolved through the maps of the later ranks
   stats   per-rank statistics, summed in rank order on every rank
+  rows    (speculative forward filter) instead of `ops`: the last forward row of every rank + its block count
 The per-block arithmetic follows the reference (ForwardBackward.hpp:64-212) in fp64; this file is the executable
 statement of the protocol the kernels implement, run under gloo on CPU (tests/test_segments_gloo.py) and compared
 with the unsplit oracle.
@@ -36,8 +37,72 @@ def emissions(n, sx, sq, mean, var, A, use_self):
     return np.exp(E - mx), np.exp((N - 1.0) * loga), mx[:, 0]
 
 
-def run_rank(dist, rank, world, seg_start, seg_len, T, starts_local, x_local, mean, var, A, pi, use_self, u_global):
-    """One FBG sweep of this rank's segment; returns the local states and the rank-order-summed statistics."""
+def _parallel(x, y, tol=1e-13):
+    l, r = x * y.sum(), y * x.sum()
+    return bool(np.all(np.abs(l - r) <= tol * l + 1e-300))
+
+
+def speculative_rows(gather, rank, world, heads, e, A, pi, sub, warm):
+    """The speculative forward filter on a split sequence (csrc/hml_sweep_impl.cuh: spec_entry, k_fwd_fixup,
+    fwd_fixup_head_cta): pieces of `sub` blocks from guessed starts, repair pass, then ONE all-gather of (last row,
+    block count) and the repair of the rank's first piece from the last row of the nearest earlier rank with blocks.
+    Returns (rows, failures summed over the ranks); rows are only meaningful when failures == 0."""
+    B, K = e.shape
+    rows = np.empty((B, K))
+    fails = 0
+    for first in range(0, B, sub):                               # pass 1
+        if first <= warm:
+            a, b0 = (np.asarray(pi, np.float64).copy() if rank == 0 else np.full(K, 1.0 / K)), 0
+        else:
+            a, b0 = np.full(K, 1.0 / K), first - warm
+        for b in range(b0, first):
+            f = (a @ A) * e[b]
+            a = f / f.max() if f.max() > 0 else np.full(K, 1.0 / K)
+        for b in range(first, min(B, first + sub)):
+            f = (a @ A) * e[b]
+            if not f.sum() > 0:
+                fails += 1
+                f = np.full(K, 1.0 / K)
+            a = f / f.sum()
+            rows[b] = a
+    stored = rows.copy()
+
+    def repair(first, entry, may_run_out):
+        """-> 1 if the piece starting at `first` did not meet its guess before its last block"""
+        a = entry
+        steps = min(B, first + sub) - first
+        for t in range(steps):
+            f = (a @ A) * e[first + t]
+            if not f.sum() > 0:
+                return 1
+            a = f / f.sum()
+            met = _parallel(a, stored[first + t])
+            if not met and t + 1 == steps and not may_run_out:
+                return 1
+            if met:
+                return 0
+            rows[first + t] = a
+        return 0
+
+    for first in range(sub, B, sub):                             # pass 2 (every piece but the rank's first)
+        fails += repair(first, stored[first - 1], first + sub >= B)
+    pub = gather((rows[B - 1].copy() if B else np.zeros(K), B))  # the rank's last row as it stands after pass 2
+    if rank > 0 and B > 0:
+        if B <= sub:
+            fails += 1                                           # a single piece: the published row came from the guess
+        else:
+            src = rank - 1
+            while src > 0 and not pub[src][1] > 0:
+                src -= 1
+            fails += repair(0, pub[src][0], False)
+    return rows, sum(gather(fails))
+
+
+def run_rank(dist, rank, world, seg_start, seg_len, T, starts_local, x_local, mean, var, A, pi, use_self, u_global,
+             forward="operators", sub=8, warm=4):
+    """One FBG sweep of this rank's segment; returns the local states and the rank-order-summed statistics.
+    forward="speculative": the forward rows come from speculative_rows; if any rank reports a failure the function
+    returns (None, None) on every rank — the host then repeats the sweep with forward="operators"."""
     K = len(mean)
     x64 = x_local.astype(np.float64)
     csum, csq = np.concatenate([[0.0], np.cumsum(x64)]), np.concatenate([[0.0], np.cumsum(x64 * x64)])
@@ -86,6 +151,13 @@ def run_rank(dist, rank, world, seg_start, seg_len, T, starts_local, x_local, me
         a = f / fs
         loglik += mx[t] + np.log(fs)
         alpha[t] = a
+    if forward == "speculative":
+        # (the operator exchange above still ran: this model keeps both so that the test can compare the rows)
+        spec, failures = speculative_rows(gather, rank, world, heads, e, A, pi, sub, warm)
+        if failures > 0:
+            return None, None
+        assert B == 0 or np.max(np.abs(spec - alpha) / np.maximum(alpha, 1e-300)) <= 1e-10, "speculative rows differ"
+        alpha = spec
 
     # ---- (iii) backward maps, segment map, state following the segment
     maps = np.empty((B, K), dtype=np.int64)

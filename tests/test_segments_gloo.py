@@ -38,6 +38,16 @@ def _worker(rank, world, port, case, ret):
         mine = starts[(starts >= seg_start) & (starts < seg_start + seg_len)] - seg_start
         states, tot = sp.run_rank(dist, rank, world, seg_start, seg_len, T, mine, x[seg_start:seg_start + seg_len],
                                   mu, var, A, pi, use_self, u)
+        # the speculative forward filter over the same split: either every rank reports a failure-free pass whose rows
+        # (checked inside) and states are the operator scan's, or every rank is told to repeat the sweep
+        s2, t2 = sp.run_rank(dist, rank, world, seg_start, seg_len, T, mine, x[seg_start:seg_start + seg_len],
+                             mu, var, A, pi, use_self, u, forward="speculative")
+        verdicts = [None] * world
+        dist.all_gather_object(verdicts, s2 is None)
+        assert all(v == verdicts[0] for v in verdicts), "the ranks disagree on whether the speculative pass held"
+        if s2 is not None:
+            assert np.array_equal(s2, states) and np.array_equal(t2["trans"], tot["trans"])
+        ret[f"spec{rank}"] = "failed" if s2 is None else "held"
         fb = tot["first_block"]
         assert tot["nblocks"] == starts.size
         assert np.array_equal(states, ref["states"][fb:fb + states.size]), "states differ from the unsplit oracle"
@@ -75,6 +85,10 @@ def test_segment_protocol_matches_unsplit_oracle(world, case):
     port = 29600 + (hash((world, case)) % 300)
     mp.spawn(_worker, args=(world, port, case, ret), nprocs=world, join=True)
     assert all(ret.get(r) == "ok" for r in range(world)), dict(ret)
+    # informative data and ranks with more than one piece: the speculative pass holds; a rank whose only blocks fit one
+    # piece (the forced-boundaries case) cannot vouch for the row it publishes, so the sweep is repeated
+    held = {ret.get(f"spec{r}") for r in range(world)}
+    assert held == ({"failed"} if case[3] > 1e29 else {"held"}), dict(ret)
 
 
 def test_segment_plan_partitions_the_sequence():
